@@ -1,0 +1,66 @@
+"""ctypes binding of libnfk.so (see include/nfk.h). There is no fallback: if the library is missing and cannot
+be built, importing this module raises."""
+from __future__ import annotations
+
+import ctypes
+import os
+
+from . import build as _build
+
+_c = ctypes
+_vp, _i, _ll, _f = _c.c_void_p, _c.c_int, _c.c_longlong, _c.c_float
+
+ERRORS = {
+    -1: "NFK_ERR_SHAPE (unsupported / inconsistent sizes)",
+    -2: "NFK_ERR_ALIGN (pointer or leading dimension not 16-byte aligned)",
+    -3: "NFK_ERR_ARG (missing / invalid argument)",
+    -4: "NFK_ERR_LAUNCH (CUDA launch failure)",
+    -5: "NFK_ERR_DRIVER (tensor-map encode failure)",
+}
+
+# name -> argtypes; every function returns int. Keep in the same order as include/nfk.h.
+SIGNATURES: dict[str, list] = {
+    "nfk_version": [],
+    "nfk_gemm_nt_bf16": [_vp, _ll, _vp, _ll, _i, _i, _i, _i, _vp, _ll, _vp, _vp, _ll, _vp, _vp],
+    "nfk_gemm_tn_bf16": [_vp, _ll, _vp, _ll, _i, _i, _i, _vp, _ll, _i, _vp],
+}
+
+
+class NfkError(RuntimeError):
+    pass
+
+
+def _load() -> ctypes.CDLL:
+    path = _build.LIB_PATH
+    if _build.needs_build():
+        try:
+            _build.build()
+        except Exception as e:  # stale .so + no nvcc on this machine
+            if not os.path.exists(path):
+                raise ImportError(
+                    f"libnfk.so is not built and cannot be built here ({e}); there is no CPU fallback") from e
+    lib = ctypes.CDLL(path)
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the header and the library diverge
+        fn.argtypes = argtypes
+        fn.restype = _c.c_int
+    return lib
+
+
+LIB = _load()
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise NfkError(f"{what} failed: {ERRORS.get(rc, rc)}")
+
+
+def ptr(t) -> int | None:
+    """Device pointer of a torch tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def stream_ptr() -> int:
+    import torch
+
+    return torch.cuda.current_stream().cuda_stream

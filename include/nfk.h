@@ -49,6 +49,75 @@ int nfk_gemm_nt_bf16(const void* A, long long lda, const void* B, long long ldb,
 int nfk_gemm_tn_bf16(const void* A, long long lda, const void* B, long long ldb, int Mo, int No, int Kpix,
                      float* out, long long ldo, int sm_count, void* stream);
 
+/* ---- parameter-space prep ("K0") ---------------------------------------------------------------------------
+ * Fused ActNorm o InvertibleConv1x1 matrix of one FlowStep (models/layers.py:376-397 get_weight + :101-142).
+ *   forward (reverse=0):  outW = W diag(exp(logs)), outb = outW * an_bias, W = P (L o tril + I)(U o triu + diag(s))
+ *   inverse (reverse=1):  outW = diag(exp(-logs)) W^-1 (triangular solves in shared memory), outb = -an_bias
+ *   out_sl[0] = +-(sum(an_logs) + sum(log_s))   (multiply by H*W for the per-sample log-det)
+ *   transpose=1 selects the 1-D convention z = x @ W (models/layers.py:410-411).
+ *   weight != NULL selects the non-LU branch (models/layers.py:366-375): in-kernel Gauss-Jordan slogdet/inverse. */
+int nfk_invconv_prep(const float* an_bias, const float* an_logs, const float* lower, const float* upper,
+                     const float* log_s, const float* p, const float* sign_s, const float* weight, int C, int reverse,
+                     int transpose, float* outW, float* outb, float* out_sl, void* stream);
+
+/* Chain rule of the forward-direction prep: (dWf, dbf, g_ld[B]) -> gradients of actnorm.{bias,logs} and
+ * invconv.{lower,upper,log_s} (or invconv.weight). `pixels` = H*W (1 in 1-D). Outputs are overwritten. */
+int nfk_invconv_prep_bwd(const float* an_bias, const float* an_logs, const float* lower, const float* upper,
+                         const float* log_s, const float* p, const float* sign_s, const float* weight, int C,
+                         int transpose, const float* Wf, const float* dWf, const float* dbf, const float* g_ld, int B,
+                         float pixels, float* d_bias, float* d_logs, float* d_lower, float* d_upper, float* d_log_s,
+                         float* d_weight, void* stream);
+
+/* Coupling-network weights -> bf16 GEMM operands with the ActNorm affine (models/layers.py:223-228) and the
+ * Conv2dZeros exp(3*logs) scale (:257-260) folded in. K1p / K3p = 9*cin / 9*cout rounded up to 64.
+ *   B1 [hid,K1p] (k = tap*cin+ci), B2 [hid,hid], B3 [K3p,hid] (row = tap*cout+co); *T = transposes for dgrads. */
+int nfk_coupling_prep(const float* w1, const float* b1, const float* l1, const float* w2, const float* b2,
+                      const float* l2, const float* w3, const float* b3, const float* l3, int cin, int hid, int cout,
+                      int K1p, int K3p, void* B1, void* B1T, void* B2, void* B2T, void* B3, void* B3T, float* bias1,
+                      float* bias2, float* bias3, int with_transposed, void* stream);
+
+int nfk_coupling_prep_bwd(const float* w1, const float* b1, const float* l1, const float* w2, const float* b2,
+                          const float* l2, const float* w3, const float* b3, const float* l3, int cin, int hid,
+                          int cout, int K1p, int K3p, const float* dB1, const float* dbias1, const float* dB2,
+                          const float* dbias2, const float* dB3, const float* dbias3, float* dw1, float* db1,
+                          float* dl1, float* dw2, float* db2, float* dl2, float* dw3, float* db3, float* dl3,
+                          void* stream);
+
+/* ---- fp32 z path of a 2-D FlowStep (models/flows.py:142-202) ------------------------------------------------
+ * y = Wf x + bf per pixel (ActNorm + invconv, models/layers.py:129-142,404-421); ld_out = ld_in + H*W*sl[0];
+ * col = bf16 im2col (3x3, pad 1) of y[:, :C/2] -> [B*H*W, K1p] for the first coupling conv.
+ * Wf == NULL: im2col of x only (inverse pass). C in {12,24,48,96}. */
+int nfk_affine1x1_fwd(const float* x, const float* Wf, const float* bf, const float* sl, float* y, void* col,
+                      int K1p, const float* ld_in, float* ld_out, int B, int C, int H, int W, void* stream);
+
+/* h = col2im(P) + bias3 (last conv of the coupling net as per-tap products P [B*H*W, K3p], column = tap*C+co);
+ * shift = h[0::2], s = sigmoid(h[1::2] + 2); forward y2 = (y2 + shift) * s, ld += sum log s
+ * (models/flows.py:160-168); reverse y2 = y2 / s - shift, ld -= sum log s (:185-193). y updated in place. */
+int nfk_coupling_fwd(const float* P, int K3p, const float* bias3, float* y, float* hsave, float* ld, int B, int C,
+                     int H, int W, int reverse, void* stream);
+
+int nfk_coupling_bwd(const float* g_out, const float* g_ld, const float* z_out, const float* hsave, float* dy,
+                     void* dhcol, int K3p, float* dbias3, int B, int C, int H, int W, void* stream);
+
+int nfk_affine1x1_bwd(const float* dy, const float* dcol, int K1p, const float* x, const float* Wf, float* dx,
+                      float* dWf, float* dbf, int B, int C, int H, int W, void* stream);
+
+/* ---- Split2d (models/layers.py:293-313), prior / bpd (models/kd_flows.py:134-150), KD MSE (pl_module.py:266-282) */
+int nfk_split2d_fwd(const float* x, const float* w, const float* bias, const float* logs, float* z1_out, float* ld,
+                    int B, int C, int H, int W, void* stream);
+int nfk_split2d_rev(const float* z1, const float* w, const float* bias, const float* logs, const float* eps,
+                    float temperature, float* out, int B, int C, int H, int W, void* stream);
+int nfk_split2d_bwd(const float* x, const float* w, const float* bias, const float* logs, const float* g_z1,
+                    const float* g_ld, float* dx, float* dw, float* dbias, float* dlogs, int B, int C, int H, int W,
+                    void* stream);
+int nfk_prior_bpd_fwd(const float* z, const float* mean, const float* logs, const float* logdet, int B, int n,
+                      float scale, float* out, void* stream);
+int nfk_prior_bpd_bwd(const float* z, const float* mean, const float* logs, const float* g_bpd, int B, int n,
+                      float scale, float* dz, float* dlogdet, void* stream);
+int nfk_kd_mse_fwd(const float* s, const float* t, int B, int n, float scale, float* acc, void* stream);
+int nfk_kd_mse_bwd(const float* s, const float* t, const float* g, int B, int n, float scale, float* ds,
+                   int accumulate, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

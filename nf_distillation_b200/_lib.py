@@ -23,6 +23,21 @@ SIGNATURES: dict[str, list] = {
     "nfk_version": [],
     "nfk_gemm_nt_bf16": [_vp, _ll, _vp, _ll, _i, _i, _i, _i, _vp, _ll, _vp, _vp, _ll, _vp, _vp],
     "nfk_gemm_tn_bf16": [_vp, _ll, _vp, _ll, _i, _i, _i, _vp, _ll, _i, _vp],
+    "nfk_invconv_prep": [_vp] * 8 + [_i, _i, _i, _vp, _vp, _vp, _vp],
+    "nfk_invconv_prep_bwd": [_vp] * 8 + [_i, _i, _vp, _vp, _vp, _vp, _i, _f] + [_vp] * 6 + [_vp],
+    "nfk_coupling_prep": [_vp] * 9 + [_i] * 5 + [_vp] * 9 + [_i, _vp],
+    "nfk_coupling_prep_bwd": [_vp] * 9 + [_i] * 5 + [_vp] * 6 + [_vp] * 9 + [_vp],
+    "nfk_affine1x1_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _vp],
+    "nfk_coupling_fwd": [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
+    "nfk_coupling_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _vp],
+    "nfk_affine1x1_bwd": [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
+    "nfk_split2d_fwd": [_vp] * 6 + [_i] * 4 + [_vp],
+    "nfk_split2d_rev": [_vp] * 5 + [_f, _vp] + [_i] * 4 + [_vp],
+    "nfk_split2d_bwd": [_vp] * 10 + [_i] * 4 + [_vp],
+    "nfk_prior_bpd_fwd": [_vp] * 4 + [_i, _i, _f, _vp, _vp],
+    "nfk_prior_bpd_bwd": [_vp] * 4 + [_i, _i, _f, _vp, _vp, _vp],
+    "nfk_kd_mse_fwd": [_vp, _vp, _i, _i, _f, _vp, _vp],
+    "nfk_kd_mse_bwd": [_vp, _vp, _vp, _i, _i, _f, _vp, _i, _vp],
 }
 
 

@@ -1,0 +1,387 @@
+// Split2d (reference: models/layers.py:293-313), the Gaussian prior / bits-per-dim objective
+// (models/layers.py:10-23, models/kd_flows.py:134-150) and the multi-level latent MSE of the KD loss
+// (pl_module.py:266-282). fp32, HBM-bound reductions with one per-sample result.
+#include <cuda_runtime.h>
+#include <cstdint>
+
+#include "../../include/nfk.h"
+
+namespace nfk {
+
+constexpr int ST = 256;
+constexpr float kLog2Pi = 1.8378770664093453f;
+
+struct SGeo {
+  int B, C, HW, W, H, ipc, pixt;
+};
+
+// smem: ws[C*CH*9] | bsc[2*C] (bias, exp(3 logs)) | z1s[CH*ldp] | z2s[CH*ldp] | ls[CH*ldp]
+__global__ void __launch_bounds__(ST)
+split2d_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                   const float* __restrict__ logs, float* __restrict__ z1_out, const float* __restrict__ eps,
+                   float temperature, float* __restrict__ out_full, float* __restrict__ ld, SGeo g, int reverse) {
+  extern __shared__ float sm[];
+  const int C = g.C, CH = C / 2, ldp = g.pixt + 1;
+  float* ws = sm;
+  float* bsc = ws + C * CH * 9;
+  float* z1s = bsc + 2 * C;
+  float* z2s = z1s + CH * ldp;
+  float* ls = z2s + CH * ldp;
+  const int tid = threadIdx.x;
+  const int b0 = blockIdx.x * g.ipc;
+  const int nimg = min(g.ipc, g.B - b0);
+  const int npix = nimg * g.HW;
+  const int cin_total = reverse ? CH : C;  // channels of the input tensor x
+
+  for (int i = tid; i < C * CH * 9; i += ST) ws[i] = w[i];
+  for (int i = tid; i < C; i += ST) { bsc[i] = bias[i]; bsc[C + i] = expf(3.f * logs[i]); }
+  for (int i = tid; i < CH * npix; i += ST) {
+    const int img = i / (CH * g.HW), r = i - img * CH * g.HW;
+    const int c = r / g.HW, p = r - c * g.HW;
+    const long long base = (static_cast<long long>(b0 + img) * cin_total) * g.HW;
+    const float v1 = x[base + static_cast<long long>(c) * g.HW + p];
+    z1s[c * ldp + img * g.HW + p] = v1;
+    if (!reverse) {
+      z2s[c * ldp + img * g.HW + p] = x[base + static_cast<long long>(CH + c) * g.HW + p];
+      z1_out[(static_cast<long long>(b0 + img) * CH + c) * g.HW + p] = v1;
+    } else {
+      out_full[(static_cast<long long>(b0 + img) * C + c) * g.HW + p] = v1;
+      z2s[c * ldp + img * g.HW + p] =
+          eps ? eps[(static_cast<long long>(b0 + img) * CH + c) * g.HW + p] : 0.f;
+    }
+  }
+  __syncthreads();
+  const int PPP = ST / CH;
+  const int j = tid % CH, pl0 = tid / CH;
+  if (pl0 < PPP) {
+    for (int pl = pl0; pl < npix; pl += PPP) {
+      const int img = pl / g.HW, rem = pl - img * g.HW;
+      const int yy = rem / g.W, xx = rem - yy * g.W;
+      float mean = 0.f, lsg = 0.f;
+      for (int tap = 0; tap < 9; ++tap) {
+        const int ny = yy + tap / 3 - 1, nx = xx + tap % 3 - 1;
+        if (ny < 0 || ny >= g.H || nx < 0 || nx >= g.W) continue;
+        const int q = img * g.HW + ny * g.W + nx;
+        const float* wm = ws + (2 * j) * CH * 9 + tap;
+        const float* wl = wm + CH * 9;
+        for (int ci = 0; ci < CH; ++ci) {
+          const float v = z1s[ci * ldp + q];
+          mean = fmaf(wm[ci * 9], v, mean);
+          lsg = fmaf(wl[ci * 9], v, lsg);
+        }
+      }
+      mean = (mean + bsc[2 * j]) * bsc[C + 2 * j];
+      lsg = (lsg + bsc[2 * j + 1]) * bsc[C + 2 * j + 1];
+      const float z2 = z2s[j * ldp + pl];
+      if (!reverse) {
+        const float d = z2 - mean;
+        ls[j * ldp + pl] = -0.5f * (2.f * lsg + d * d * expf(-2.f * lsg) + kLog2Pi);
+      } else {
+        z2s[j * ldp + pl] = mean + expf(lsg) * temperature * z2;  // z2 held eps
+      }
+    }
+  }
+  __syncthreads();
+  if (!reverse) {
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int img = warp; img < nimg; img += ST / 32) {
+      float acc = 0.f;
+      for (int i = lane; i < CH * g.HW; i += 32) {
+        const int jj = i / g.HW, p = i - jj * g.HW;
+        acc += ls[jj * ldp + img * g.HW + p];
+      }
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0 && ld) ld[b0 + img] += acc;
+    }
+  } else {
+    for (int i = tid; i < CH * npix; i += ST) {
+      const int img = i / (CH * g.HW), r = i - img * CH * g.HW;
+      const int c = r / g.HW, p = r - c * g.HW;
+      out_full[(static_cast<long long>(b0 + img) * C + CH + c) * g.HW + p] = z2s[c * ldp + img * g.HW + p];
+    }
+  }
+}
+
+// smem: ws[C*CH*9] | bsc[2C] | z1s[CH*ldp] | dps[C*ldp] | accw[C*CH*9] | accb[2C]
+__global__ void __launch_bounds__(ST)
+split2d_bwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                   const float* __restrict__ logs, const float* __restrict__ g_z1, const float* __restrict__ g_ld,
+                   float* __restrict__ dx, float* __restrict__ dw, float* __restrict__ dbias,
+                   float* __restrict__ dlogs, SGeo g) {
+  extern __shared__ float sm[];
+  const int C = g.C, CH = C / 2, ldp = g.pixt + 1;
+  float* ws = sm;
+  float* bsc = ws + C * CH * 9;
+  float* z1s = bsc + 2 * C;
+  float* dps = z1s + CH * ldp;
+  float* accb = dps + C * ldp;
+  const int tid = threadIdx.x;
+  const int b0 = blockIdx.x * g.ipc;
+  const int nimg = min(g.ipc, g.B - b0);
+  const int npix = nimg * g.HW;
+
+  for (int i = tid; i < C * CH * 9; i += ST) ws[i] = w[i];
+  for (int i = tid; i < C; i += ST) { bsc[i] = bias[i]; bsc[C + i] = expf(3.f * logs[i]); }
+  for (int i = tid; i < 2 * C; i += ST) accb[i] = 0.f;
+  for (int i = tid; i < CH * npix; i += ST) {
+    const int img = i / (CH * g.HW), r = i - img * CH * g.HW;
+    const int c = r / g.HW, p = r - c * g.HW;
+    z1s[c * ldp + img * g.HW + p] = x[(static_cast<long long>(b0 + img) * C + c) * g.HW + p];
+  }
+  __syncthreads();
+  const int PPP = ST / CH;
+  const int j = tid % CH, pl0 = tid / CH;
+  if (pl0 < PPP) {
+    float a_bm = 0.f, a_bl = 0.f, a_lm = 0.f, a_ll = 0.f;
+    for (int pl = pl0; pl < npix; pl += PPP) {
+      const int img = pl / g.HW, rem = pl - img * g.HW;
+      const int yy = rem / g.W, xx = rem - yy * g.W;
+      float mean = 0.f, lsg = 0.f;
+      for (int tap = 0; tap < 9; ++tap) {
+        const int ny = yy + tap / 3 - 1, nx = xx + tap % 3 - 1;
+        if (ny < 0 || ny >= g.H || nx < 0 || nx >= g.W) continue;
+        const int q = img * g.HW + ny * g.W + nx;
+        const float* wm = ws + (2 * j) * CH * 9 + tap;
+        const float* wl = wm + CH * 9;
+        for (int ci = 0; ci < CH; ++ci) {
+          const float v = z1s[ci * ldp + q];
+          mean = fmaf(wm[ci * 9], v, mean);
+          lsg = fmaf(wl[ci * 9], v, lsg);
+        }
+      }
+      const float em = bsc[C + 2 * j], el = bsc[C + 2 * j + 1];
+      mean = (mean + bsc[2 * j]) * em;
+      lsg = (lsg + bsc[2 * j + 1]) * el;
+      const long long zi = (static_cast<long long>(b0 + img) * C + CH + j) * g.HW + rem;
+      const float z2 = x[zi];
+      const float gl = g_ld[b0 + img];
+      const float d = z2 - mean;
+      const float r = d * expf(-2.f * lsg);
+      const float dmean = gl * r;
+      const float dlsg = gl * (d * r - 1.f);
+      dx[zi] = -gl * r;
+      const float dpm = dmean * em, dpl = dlsg * el;
+      dps[(2 * j) * ldp + pl] = dpm;
+      dps[(2 * j + 1) * ldp + pl] = dpl;
+      a_bm += dpm; a_bl += dpl;
+      a_lm += dmean * mean; a_ll += dlsg * lsg;
+    }
+    atomicAdd(&accb[2 * j], a_bm);
+    atomicAdd(&accb[2 * j + 1], a_bl);
+    atomicAdd(&accb[C + 2 * j], 3.f * a_lm);
+    atomicAdd(&accb[C + 2 * j + 1], 3.f * a_ll);
+  }
+  __syncthreads();
+  for (int i = tid; i < C; i += ST) { atomicAdd(dbias + i, accb[i]); atomicAdd(dlogs + i, accb[C + i]); }
+  // dz1[ci, m] = g_z1 + sum_{co,tap} dpre[co, m - off(tap)] * w[co][ci][tap]
+  if (pl0 < PPP) {
+    const int ci = j;
+    for (int pl = pl0; pl < npix; pl += PPP) {
+      const int img = pl / g.HW, rem = pl - img * g.HW;
+      const int yy = rem / g.W, xx = rem - yy * g.W;
+      float a = 0.f;
+      for (int tap = 0; tap < 9; ++tap) {
+        const int ny = yy - (tap / 3 - 1), nx = xx - (tap % 3 - 1);
+        if (ny < 0 || ny >= g.H || nx < 0 || nx >= g.W) continue;
+        const int q = img * g.HW + ny * g.W + nx;
+        const float* wp = ws + ci * 9 + tap;
+        for (int co = 0; co < C; ++co) a = fmaf(dps[co * ldp + q], wp[co * CH * 9], a);
+      }
+      const long long gi = (static_cast<long long>(b0 + img) * CH + ci) * g.HW + rem;
+      dx[(static_cast<long long>(b0 + img) * C + ci) * g.HW + rem] = a + (g_z1 ? g_z1[gi] : 0.f);
+    }
+  }
+  // dw[co][ci][tap] += sum_m dpre[co, m] * z1[ci, m + off(tap)]
+  for (int e = tid; e < C * CH * 9; e += ST) {
+    const int co = e / (CH * 9), r = e - co * CH * 9;
+    const int ci = r / 9, tap = r - ci * 9;
+    const int dyy = tap / 3 - 1, dxx = tap % 3 - 1;
+    float a = 0.f;
+    for (int img = 0; img < nimg; ++img) {
+      const int y0 = max(0, -dyy), y1 = min(g.H, g.H - dyy);
+      const int x0 = max(0, -dxx), x1 = min(g.W, g.W - dxx);
+      for (int yy = y0; yy < y1; ++yy)
+        for (int xx = x0; xx < x1; ++xx)
+          a = fmaf(dps[co * ldp + img * g.HW + yy * g.W + xx],
+                   z1s[ci * ldp + img * g.HW + (yy + dyy) * g.W + xx + dxx], a);
+    }
+    atomicAdd(dw + e, a);
+  }
+}
+
+// One warp per sample: out[b] = -(logdet[b] + sum_i logN(z_i; mean_i, exp(logs_i))) * scale
+__global__ void prior_bpd_fwd_kernel(const float* __restrict__ z, const float* __restrict__ mean,
+                                     const float* __restrict__ logs, const float* __restrict__ logdet, int B, int n,
+                                     float scale, float* __restrict__ out) {
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (b >= B) return;
+  const float* zp = z + static_cast<long long>(b) * n;
+  float acc = 0.f;
+  for (int i = lane; i < n; i += 32) {
+    const float l = logs[i], d = zp[i] - mean[i];
+    acc += -0.5f * (2.f * l + d * d * expf(-2.f * l) + kLog2Pi);
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) out[b] = -(logdet[b] + acc) * scale;
+}
+
+__global__ void prior_bpd_bwd_kernel(const float* __restrict__ z, const float* __restrict__ mean,
+                                     const float* __restrict__ logs, const float* __restrict__ g_bpd, int B, int n,
+                                     float scale, float* __restrict__ dz, float* __restrict__ dlogdet) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= static_cast<long long>(B) * n) return;
+  const int b = static_cast<int>(i / n), k = static_cast<int>(i - static_cast<long long>(b) * n);
+  const float gs = g_bpd[b] * scale;
+  dz[i] = gs * (z[i] - mean[k]) * expf(-2.f * logs[k]);
+  if (k == 0) dlogdet[b] = -gs;
+}
+
+// acc[b] += scale * sum_i (s - t)^2 ; GROUP threads per sample
+template <int GROUP>
+__global__ void kd_mse_fwd_kernel(const float* __restrict__ s, const float* __restrict__ t, int B, int n, float scale,
+                                  float* __restrict__ acc) {
+  __shared__ float red[ST / 32];
+  const int per_cta = ST / GROUP;
+  const int b = blockIdx.x * per_cta + threadIdx.x / GROUP;
+  const int l = threadIdx.x % GROUP;
+  float a = 0.f;
+  if (b < B) {
+    const float* sp = s + static_cast<long long>(b) * n;
+    const float* tp = t + static_cast<long long>(b) * n;
+    if ((n & 3) == 0) {
+      const float4* s4 = reinterpret_cast<const float4*>(sp);
+      const float4* t4 = reinterpret_cast<const float4*>(tp);
+      for (int i = l; i < n / 4; i += GROUP) {
+        const float4 u = __ldg(s4 + i), v = __ldg(t4 + i);
+        const float d0 = u.x - v.x, d1 = u.y - v.y, d2 = u.z - v.z, d3 = u.w - v.w;
+        a += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+      }
+    } else {
+      for (int i = l; i < n; i += GROUP) {
+        const float d = sp[i] - tp[i];
+        a += d * d;
+      }
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  if (GROUP == 32) {
+    if (l == 0 && b < B) acc[b] += a * scale;
+  } else {
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = a;
+    __syncthreads();
+    if (threadIdx.x == 0 && b < B) {
+      float tot = 0.f;
+      for (int i = 0; i < ST / 32; ++i) tot += red[i];
+      acc[b] += tot * scale;
+    }
+  }
+}
+
+__global__ void kd_mse_bwd_kernel(const float* __restrict__ s, const float* __restrict__ t,
+                                  const float* __restrict__ g, long long total, int n, float scale2,
+                                  float* __restrict__ ds, int accumulate) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= total) return;
+  const float v = scale2 * g[i / n] * (s[i] - t[i]);
+  ds[i] = accumulate ? ds[i] + v : v;
+}
+
+static SGeo make_sgeo(int B, int C, int H, int W, int target) {
+  SGeo g;
+  g.B = B; g.C = C; g.H = H; g.W = W; g.HW = H * W;
+  g.ipc = g.HW >= target ? 1 : target / g.HW;
+  if (g.ipc > B) g.ipc = B;
+  g.pixt = g.ipc * g.HW;
+  return g;
+}
+
+}  // namespace nfk
+
+using namespace nfk;
+
+extern "C" int nfk_split2d_fwd(const float* x, const float* w, const float* bias, const float* logs, float* z1_out,
+                               float* ld, int B, int C, int H, int W, void* stream) {
+  if (B <= 0 || C <= 0 || C % 2 || C > 128 || H * W > 4096) return NFK_ERR_SHAPE;
+  if (!x || !w || !bias || !logs || !z1_out) return NFK_ERR_ARG;
+  SGeo g = make_sgeo(B, C, H, W, 256);
+  const int smem = (C * (C / 2) * 9 + 2 * C + 3 * (C / 2) * (g.pixt + 1)) * 4;
+  if (smem > 227 * 1024) return NFK_ERR_SHAPE;
+  if (smem > 48 * 1024 &&
+      cudaFuncSetAttribute(split2d_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+    return NFK_ERR_LAUNCH;
+  split2d_fwd_kernel<<<(B + g.ipc - 1) / g.ipc, ST, smem, static_cast<cudaStream_t>(stream)>>>(
+      x, w, bias, logs, z1_out, nullptr, 0.f, nullptr, ld, g, 0);
+  return cudaGetLastError() == cudaSuccess ? NFK_OK : NFK_ERR_LAUNCH;
+}
+
+extern "C" int nfk_split2d_rev(const float* z1, const float* w, const float* bias, const float* logs,
+                               const float* eps, float temperature, float* out, int B, int C, int H, int W,
+                               void* stream) {
+  if (B <= 0 || C <= 0 || C % 2 || C > 128 || H * W > 4096) return NFK_ERR_SHAPE;
+  if (!z1 || !w || !bias || !logs || !out) return NFK_ERR_ARG;
+  SGeo g = make_sgeo(B, C, H, W, 256);
+  const int smem = (C * (C / 2) * 9 + 2 * C + 3 * (C / 2) * (g.pixt + 1)) * 4;
+  if (smem > 227 * 1024) return NFK_ERR_SHAPE;
+  if (smem > 48 * 1024 &&
+      cudaFuncSetAttribute(split2d_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+    return NFK_ERR_LAUNCH;
+  split2d_fwd_kernel<<<(B + g.ipc - 1) / g.ipc, ST, smem, static_cast<cudaStream_t>(stream)>>>(
+      z1, w, bias, logs, nullptr, eps, temperature, out, nullptr, g, 1);
+  return cudaGetLastError() == cudaSuccess ? NFK_OK : NFK_ERR_LAUNCH;
+}
+
+extern "C" int nfk_split2d_bwd(const float* x, const float* w, const float* bias, const float* logs,
+                               const float* g_z1, const float* g_ld, float* dx, float* dw, float* dbias,
+                               float* dlogs, int B, int C, int H, int W, void* stream) {
+  if (B <= 0 || C <= 0 || C % 2 || C > 128 || H * W > 4096) return NFK_ERR_SHAPE;
+  if (!x || !w || !bias || !logs || !g_ld || !dx || !dw || !dbias || !dlogs) return NFK_ERR_ARG;
+  SGeo g = make_sgeo(B, C, H, W, 128);
+  const int smem = (C * (C / 2) * 9 + 2 * C + (C / 2 + C) * (g.pixt + 1) + 2 * C) * 4;
+  if (smem > 227 * 1024) return NFK_ERR_SHAPE;
+  if (smem > 48 * 1024 &&
+      cudaFuncSetAttribute(split2d_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+    return NFK_ERR_LAUNCH;
+  split2d_bwd_kernel<<<(B + g.ipc - 1) / g.ipc, ST, smem, static_cast<cudaStream_t>(stream)>>>(
+      x, w, bias, logs, g_z1, g_ld, dx, dw, dbias, dlogs, g);
+  return cudaGetLastError() == cudaSuccess ? NFK_OK : NFK_ERR_LAUNCH;
+}
+
+extern "C" int nfk_prior_bpd_fwd(const float* z, const float* mean, const float* logs, const float* logdet, int B,
+                                 int n, float scale, float* out, void* stream) {
+  if (B <= 0 || n <= 0) return NFK_ERR_SHAPE;
+  if (!z || !mean || !logs || !logdet || !out) return NFK_ERR_ARG;
+  const long long threads = static_cast<long long>(B) * 32;
+  prior_bpd_fwd_kernel<<<static_cast<int>((threads + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      z, mean, logs, logdet, B, n, scale, out);
+  return cudaGetLastError() == cudaSuccess ? NFK_OK : NFK_ERR_LAUNCH;
+}
+
+extern "C" int nfk_prior_bpd_bwd(const float* z, const float* mean, const float* logs, const float* g_bpd, int B,
+                                 int n, float scale, float* dz, float* dlogdet, void* stream) {
+  if (B <= 0 || n <= 0) return NFK_ERR_SHAPE;
+  if (!z || !mean || !logs || !g_bpd || !dz || !dlogdet) return NFK_ERR_ARG;
+  const long long total = static_cast<long long>(B) * n;
+  prior_bpd_bwd_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      z, mean, logs, g_bpd, B, n, scale, dz, dlogdet);
+  return cudaGetLastError() == cudaSuccess ? NFK_OK : NFK_ERR_LAUNCH;
+}
+
+extern "C" int nfk_kd_mse_fwd(const float* s, const float* t, int B, int n, float scale, float* acc, void* stream) {
+  if (B <= 0 || n <= 0) return NFK_ERR_SHAPE;
+  if (!s || !t || !acc) return NFK_ERR_ARG;
+  if ((reinterpret_cast<uintptr_t>(s) | reinterpret_cast<uintptr_t>(t)) & 15) return NFK_ERR_ALIGN;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (n >= 1024) kd_mse_fwd_kernel<256><<<B, ST, 0, st>>>(s, t, B, n, scale, acc);
+  else kd_mse_fwd_kernel<32><<<(B + 7) / 8, ST, 0, st>>>(s, t, B, n, scale, acc);
+  return cudaGetLastError() == cudaSuccess ? NFK_OK : NFK_ERR_LAUNCH;
+}
+
+extern "C" int nfk_kd_mse_bwd(const float* s, const float* t, const float* g, int B, int n, float scale, float* ds,
+                              int accumulate, void* stream) {
+  if (B <= 0 || n <= 0) return NFK_ERR_SHAPE;
+  if (!s || !t || !g || !ds) return NFK_ERR_ARG;
+  const long long total = static_cast<long long>(B) * n;
+  kd_mse_bwd_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      s, t, g, total, n, 2.f * scale, ds, accumulate);
+  return cudaGetLastError() == cudaSuccess ? NFK_OK : NFK_ERR_LAUNCH;
+}

@@ -1,0 +1,509 @@
+// fp32 "z path" kernels of a 2-D FlowStep (reference: models/flows.py:142-202, models/layers.py:101-142,404-421).
+// All tensors are contiguous NCHW fp32; HBM-bound, coalesced along the pixel axis.
+//
+//  affine1x1_fwd   y = W' x + b' per pixel (ActNorm folded into the invertible 1x1 conv), logdet += pixels*sl,
+//                  and the bf16 im2col matrix of y1 = y[:, :C/2] that feeds the first coupling conv (3x3, pad 1).
+//  coupling_fwd    col2im of the last conv's per-tap products P, + folded bias, then the affine coupling
+//                  z2 = (z2 + shift) * sigmoid(s + 2)  (or its inverse), log-det reduced per sample.
+//  coupling_bwd    gradient of the coupling wrt (z2, h) and the im2col matrix of dh for the dgrad / wgrad GEMMs.
+//  affine1x1_bwd   col2im of the first conv's input gradient, dx = W'^T dy, dW' and db' reductions.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+
+#include "../../include/nfk.h"
+
+namespace nfk {
+
+constexpr int ZT = 256;  // threads per CTA
+
+__device__ __forceinline__ uint32_t bf2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// log(sigmoid(t)) and sigmoid(t), stable for both signs.
+__device__ __forceinline__ void sigmoid_logsigmoid(float t, float& s, float& ls) {
+  const float e = expf(-fabsf(t));
+  const float l1p = log1pf(e);
+  if (t >= 0.f) {
+    s = 1.f / (1.f + e);
+    ls = -l1p;
+  } else {
+    s = e / (1.f + e);
+    ls = t - l1p;
+  }
+}
+
+struct Geo {
+  int B, HW, W, H;
+  int ipc;   // images per CTA
+  int pixt;  // ipc * HW
+};
+
+// ------------------------------------------------------------------------------------------ affine1x1 fwd
+// smem: Ws[C*C] bs[C] | y1s[(C/2) * (pixt+1)] | lut[K1p]
+template <int C>
+__global__ void __launch_bounds__(ZT)
+affine1x1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ Wf, const float* __restrict__ bf,
+                     const float* __restrict__ sl, float* __restrict__ y, __nv_bfloat16* __restrict__ col,
+                     const float* __restrict__ ld_in, float* __restrict__ ld_out, Geo g, int K1p) {
+  extern __shared__ float sm[];
+  constexpr int CH = C / 2;
+  float* Ws = sm;
+  float* bs = Ws + C * C;
+  float* y1s = bs + C;
+  int* lut = reinterpret_cast<int*>(y1s + CH * (g.pixt + 1));
+  const int tid = threadIdx.x;
+  const int b0 = blockIdx.x * g.ipc;
+  const int nimg = min(g.ipc, g.B - b0);
+  const int npix = nimg * g.HW;
+  const int ldp = g.pixt + 1;
+
+  if (Wf) {
+    for (int i = tid; i < C * C; i += ZT) Ws[i] = Wf[i];
+    for (int i = tid; i < C; i += ZT) bs[i] = bf[i];
+  }
+  if (col) {
+    for (int k = tid; k < K1p; k += ZT) {
+      int v = -1;
+      if (k < 9 * CH) {
+        const int tap = k / CH, ci = k % CH;
+        v = ci | ((tap / 3) << 8) | ((tap % 3) << 10);
+      }
+      lut[k] = v;
+    }
+  }
+  if (ld_out && tid < nimg) ld_out[b0 + tid] = ld_in[b0 + tid] + sl[0] * static_cast<float>(g.HW);
+  __syncthreads();
+
+  for (int pl = tid; pl < npix; pl += ZT) {
+    const int img = pl / g.HW, p = pl - img * g.HW;
+    const float* xp = x + (static_cast<long long>(b0 + img) * C) * g.HW + p;
+    float xv[C];
+#pragma unroll
+    for (int i = 0; i < C; ++i) xv[i] = __ldg(xp + static_cast<long long>(i) * g.HW);
+    if (Wf) {
+      float* yp = y + (static_cast<long long>(b0 + img) * C) * g.HW + p;
+#pragma unroll 4
+      for (int o = 0; o < C; ++o) {
+        float acc = bs[o];
+        const float4* wr = reinterpret_cast<const float4*>(Ws + o * C);
+#pragma unroll
+        for (int i = 0; i < C / 4; ++i) {
+          const float4 w = wr[i];
+          acc = fmaf(w.x, xv[4 * i], acc);
+          acc = fmaf(w.y, xv[4 * i + 1], acc);
+          acc = fmaf(w.z, xv[4 * i + 2], acc);
+          acc = fmaf(w.w, xv[4 * i + 3], acc);
+        }
+        yp[static_cast<long long>(o) * g.HW] = acc;
+        if (col && o < CH) y1s[o * ldp + pl] = acc;
+      }
+    } else if (col) {
+#pragma unroll
+      for (int o = 0; o < CH; ++o) y1s[o * ldp + pl] = xv[o];
+    }
+  }
+  if (!col) return;
+  __syncthreads();
+  const int cpr = K1p / 8;  // 16-byte chunks per im2col row
+  const int nchunk = npix * cpr;
+  for (int c = tid; c < nchunk; c += ZT) {
+    const int pl = c / cpr, k0 = (c - pl * cpr) * 8;
+    const int img = pl / g.HW, rem = pl - img * g.HW;
+    const int yy = rem / g.W, xx = rem - yy * g.W;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int e = lut[k0 + j];
+      float t = 0.f;
+      if (e >= 0) {
+        const int ci = e & 0xFF, ny = yy + ((e >> 8) & 3) - 1, nx = xx + ((e >> 10) & 3) - 1;
+        if (ny >= 0 && ny < g.H && nx >= 0 && nx < g.W) t = y1s[ci * ldp + img * g.HW + ny * g.W + nx];
+      }
+      v[j] = t;
+    }
+    uint4 pk = make_uint4(bf2(v[0], v[1]), bf2(v[2], v[3]), bf2(v[4], v[5]), bf2(v[6], v[7]));
+    *reinterpret_cast<uint4*>(col + (static_cast<long long>(b0) * g.HW + pl) * K1p + k0) = pk;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ coupling fwd / inv
+// smem: ys[J*(pixt+1)] ls[J*(pixt+1)]
+template <int C>
+__global__ void __launch_bounds__(ZT)
+coupling_fwd_kernel(const float* __restrict__ P, int K3p, const float* __restrict__ bias3, float* __restrict__ y,
+                    float* __restrict__ hsave, float* __restrict__ ld, Geo g, int reverse) {
+  extern __shared__ float sm[];
+  constexpr int J = C / 2;
+  const int ldp = g.pixt + 1;
+  float* ys = sm;
+  float* ls = ys + J * ldp;
+  const int tid = threadIdx.x;
+  const int b0 = blockIdx.x * g.ipc;
+  const int nimg = min(g.ipc, g.B - b0);
+  const int npix = nimg * g.HW;
+
+  for (int i = tid; i < J * npix; i += ZT) {
+    // (img, j, p) with p fastest
+    const int img = i / (J * g.HW), r = i - img * J * g.HW;
+    const int j = r / g.HW, p = r - j * g.HW;
+    ys[j * ldp + img * g.HW + p] = y[(static_cast<long long>(b0 + img) * C + J + j) * g.HW + p];
+  }
+  __syncthreads();
+  constexpr int PPP = ZT / J;  // pixels per pass
+  const int j = tid % J, pl0 = tid / J;
+  if (pl0 < PPP) {
+    const float bsh = bias3[2 * j], blg = bias3[2 * j + 1];
+    for (int pl = pl0; pl < npix; pl += PPP) {
+      const int img = pl / g.HW, rem = pl - img * g.HW;
+      const int yy = rem / g.W, xx = rem - yy * g.W;
+      const long long m = static_cast<long long>(b0) * g.HW + pl;
+      float sh = bsh, lg = blg;
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+        const int ny = yy + dy, nx = xx + dx;
+        if (ny >= 0 && ny < g.H && nx >= 0 && nx < g.W) {
+          const float2 v = __ldg(reinterpret_cast<const float2*>(P + (m + dy * g.W + dx) * K3p + tap * C + 2 * j));
+          sh += v.x;
+          lg += v.y;
+        }
+      }
+      if (hsave) *reinterpret_cast<float2*>(hsave + m * C + 2 * j) = make_float2(sh, lg);
+      float s, lsv;
+      sigmoid_logsigmoid(lg + 2.f, s, lsv);
+      const float z2 = ys[j * ldp + pl];
+      ys[j * ldp + pl] = reverse ? (z2 / s - sh) : (z2 + sh) * s;
+      ls[j * ldp + pl] = lsv;
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < J * npix; i += ZT) {
+    const int img = i / (J * g.HW), r = i - img * J * g.HW;
+    const int jj = r / g.HW, p = r - jj * g.HW;
+    y[(static_cast<long long>(b0 + img) * C + J + jj) * g.HW + p] = ys[jj * ldp + img * g.HW + p];
+  }
+  if (ld) {
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int img = warp; img < nimg; img += ZT / 32) {
+      float acc = 0.f;
+      for (int i = lane; i < J * g.HW; i += 32) {
+        const int jj = i / g.HW, p = i - jj * g.HW;
+        acc += ls[jj * ldp + img * g.HW + p];
+      }
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) ld[b0 + img] += reverse ? -acc : acc;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ coupling bwd
+// smem: gs[J*ldp] os[J*ldp] dhs[C*ldp] dbs[C] lut[K3p]
+template <int C>
+__global__ void __launch_bounds__(ZT)
+coupling_bwd_kernel(const float* __restrict__ g_out, const float* __restrict__ g_ld, const float* __restrict__ z_out,
+                    const float* __restrict__ hsave, float* __restrict__ dy, __nv_bfloat16* __restrict__ dhcol,
+                    int K3p, float* __restrict__ dbias3, Geo g) {
+  extern __shared__ float sm[];
+  constexpr int J = C / 2;
+  const int ldp = g.pixt + 1;
+  float* gs = sm;
+  float* os = gs + J * ldp;
+  float* dhs = os + J * ldp;
+  float* dbs = dhs + C * ldp;
+  int* lut = reinterpret_cast<int*>(dbs + C);
+  const int tid = threadIdx.x;
+  const int b0 = blockIdx.x * g.ipc;
+  const int nimg = min(g.ipc, g.B - b0);
+  const int npix = nimg * g.HW;
+
+  for (int i = tid; i < C; i += ZT) dbs[i] = 0.f;
+  for (int k = tid; k < K3p; k += ZT) {
+    int v = -1;
+    if (k < 9 * C) {
+      const int tap = k / C, co = k % C;
+      v = co | ((tap / 3) << 8) | ((tap % 3) << 10);
+    }
+    lut[k] = v;
+  }
+  for (int i = tid; i < J * npix; i += ZT) {
+    const int img = i / (J * g.HW), r = i - img * J * g.HW;
+    const int j = r / g.HW, p = r - j * g.HW;
+    const long long lo = (static_cast<long long>(b0 + img) * C + j) * g.HW + p;
+    const long long hi = lo + static_cast<long long>(J) * g.HW;
+    dy[lo] = g_out[lo];  // z1 passes through; the coupling-net gradient is added by affine1x1_bwd
+    gs[j * ldp + img * g.HW + p] = g_out[hi];
+    os[j * ldp + img * g.HW + p] = z_out[hi];
+  }
+  __syncthreads();
+  constexpr int PPP = ZT / J;
+  const int j = tid % J, pl0 = tid / J;
+  if (pl0 < PPP) {
+    float a_sh = 0.f, a_lg = 0.f;
+    for (int pl = pl0; pl < npix; pl += PPP) {
+      const int img = pl / g.HW;
+      const long long m = static_cast<long long>(b0) * g.HW + pl;
+      const float2 h = *reinterpret_cast<const float2*>(hsave + m * C + 2 * j);
+      float s, lsv;
+      sigmoid_logsigmoid(h.y + 2.f, s, lsv);
+      const float g2 = gs[j * ldp + pl], o2 = os[j * ldp + pl];
+      const float dsh = g2 * s;
+      const float dlg = (g2 * o2 + g_ld[b0 + img]) * (1.f - s);
+      gs[j * ldp + pl] = dsh;  // = dL/dy2
+      dhs[(2 * j) * ldp + pl] = dsh;
+      dhs[(2 * j + 1) * ldp + pl] = dlg;
+      a_sh += dsh;
+      a_lg += dlg;
+    }
+    atomicAdd(&dbs[2 * j], a_sh);
+    atomicAdd(&dbs[2 * j + 1], a_lg);
+  }
+  __syncthreads();
+  for (int i = tid; i < C; i += ZT) atomicAdd(dbias3 + i, dbs[i]);
+  for (int i = tid; i < J * npix; i += ZT) {
+    const int img = i / (J * g.HW), r = i - img * J * g.HW;
+    const int jj = r / g.HW, p = r - jj * g.HW;
+    dy[(static_cast<long long>(b0 + img) * C + J + jj) * g.HW + p] = gs[jj * ldp + img * g.HW + p];
+  }
+  const int cpr = K3p / 8;
+  const int nchunk = npix * cpr;
+  for (int c = tid; c < nchunk; c += ZT) {
+    const int pl = c / cpr, k0 = (c - pl * cpr) * 8;
+    const int img = pl / g.HW, rem = pl - img * g.HW;
+    const int yy = rem / g.W, xx = rem - yy * g.W;
+    float v[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int e = lut[k0 + q];
+      float t = 0.f;
+      if (e >= 0) {
+        // P[m', (tap, co)] fed output pixel m' - off(tap): gather dh from there
+        const int co = e & 0xFF, ny = yy - (((e >> 8) & 3) - 1), nx = xx - (((e >> 10) & 3) - 1);
+        if (ny >= 0 && ny < g.H && nx >= 0 && nx < g.W) t = dhs[co * ldp + img * g.HW + ny * g.W + nx];
+      }
+      v[q] = t;
+    }
+    uint4 pk = make_uint4(bf2(v[0], v[1]), bf2(v[2], v[3]), bf2(v[4], v[5]), bf2(v[6], v[7]));
+    *reinterpret_cast<uint4*>(dhcol + (static_cast<long long>(b0) * g.HW + pl) * K3p + k0) = pk;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ affine1x1 bwd
+// smem: Ws[C*C] (W'^T) | dys[C*ldp] | xs[C*ldp] | acc[C*C + C]
+template <int C>
+__global__ void __launch_bounds__(ZT)
+affine1x1_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ dcol, int K1p,
+                     const float* __restrict__ x, const float* __restrict__ Wf, float* __restrict__ dx,
+                     float* __restrict__ dWf, float* __restrict__ dbf, Geo g) {
+  extern __shared__ float sm[];
+  constexpr int CH = C / 2;
+  const int ldp = g.pixt + 1;
+  float* WT = sm;
+  float* dys = WT + C * C;
+  float* xs = dys + C * ldp;
+  float* acc = xs + C * ldp;
+  const int tid = threadIdx.x;
+  const int b0 = blockIdx.x * g.ipc;
+  const int nimg = min(g.ipc, g.B - b0);
+  const int npix = nimg * g.HW;
+
+  for (int i = tid; i < C * C; i += ZT) {
+    const int o = i / C, c = i % C;
+    WT[c * C + o] = Wf[i];
+  }
+  for (int i = tid; i < C * C + C; i += ZT) acc[i] = 0.f;
+  // coalesced tile loads (p fastest)
+  for (int i = tid; i < C * npix; i += ZT) {
+    const int img = i / (C * g.HW), r = i - img * C * g.HW;
+    const int c = r / g.HW, p = r - c * g.HW;
+    const long long gi = (static_cast<long long>(b0 + img) * C + c) * g.HW + p;
+    xs[c * ldp + img * g.HW + p] = x[gi];
+    dys[c * ldp + img * g.HW + p] = dy[gi];
+  }
+  __syncthreads();
+  // col2im of the first conv's input gradient: dy1[ci, m] += sum_tap dcol[m - off(tap), tap*CH + ci]
+  if (dcol) {
+    constexpr int PPP = ZT / CH;
+    const int ci = tid % CH, pl0 = tid / CH;
+    if (pl0 < PPP) {
+      for (int pl = pl0; pl < npix; pl += PPP) {
+        const int img = pl / g.HW, rem = pl - img * g.HW;
+        const int yy = rem / g.W, xx = rem - yy * g.W;
+        const long long m = static_cast<long long>(b0) * g.HW + pl;
+        float a = 0.f;
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+          const int ddy = tap / 3 - 1, ddx = tap % 3 - 1;
+          const int ny = yy - ddy, nx = xx - ddx;
+          if (ny >= 0 && ny < g.H && nx >= 0 && nx < g.W)
+            a += __ldg(dcol + (m - ddy * g.W - ddx) * K1p + tap * CH + ci);
+        }
+        dys[ci * ldp + pl] += a;
+      }
+    }
+    __syncthreads();
+  }
+  // dx = W'^T dy
+  for (int pl = tid; pl < npix; pl += ZT) {
+    const int img = pl / g.HW, p = pl - img * g.HW;
+    float dv[C];
+#pragma unroll
+    for (int o = 0; o < C; ++o) dv[o] = dys[o * ldp + pl];
+    float* dxp = dx + (static_cast<long long>(b0 + img) * C) * g.HW + p;
+#pragma unroll 4
+    for (int i = 0; i < C; ++i) {
+      float a = 0.f;
+      const float4* wr = reinterpret_cast<const float4*>(WT + i * C);
+#pragma unroll
+      for (int o = 0; o < C / 4; ++o) {
+        const float4 w = wr[o];
+        a = fmaf(w.x, dv[4 * o], a);
+        a = fmaf(w.y, dv[4 * o + 1], a);
+        a = fmaf(w.z, dv[4 * o + 2], a);
+        a = fmaf(w.w, dv[4 * o + 3], a);
+      }
+      dxp[static_cast<long long>(i) * g.HW] = a;
+    }
+  }
+  // dW'[o][i] += sum_p dy[o][p] x[i][p] with 4x4 register blocks, pixel range split over thread slices
+  constexpr int NBK = (C / 4) * (C / 4);
+  constexpr int SL = NBK >= ZT ? 1 : ZT / NBK;
+  for (int blk = tid % (NBK < ZT ? NBK : ZT); blk < NBK; blk += ZT) {
+    const int slice = NBK < ZT ? tid / NBK : 0;
+    if (slice >= SL) break;
+    const int to = blk / (C / 4), ti = blk % (C / 4);
+    float a[4][4] = {};
+    for (int p = slice; p < npix; p += SL) {
+      float dv[4], xv[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        dv[q] = dys[(4 * to + q) * ldp + p];
+        xv[q] = xs[(4 * ti + q) * ldp + p];
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) a[q][r] = fmaf(dv[q], xv[r], a[q][r]);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) atomicAdd(&acc[(4 * to + q) * C + 4 * ti + r], a[q][r]);
+  }
+  // db'[o] += sum_p dy[o][p]: one warp per channel
+  {
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int o = warp; o < C; o += ZT / 32) {
+      float a = 0.f;
+      for (int p = lane; p < npix; p += 32) a += dys[o * ldp + p];
+      for (int s = 16; s > 0; s >>= 1) a += __shfl_xor_sync(0xffffffffu, a, s);
+      if (lane == 0) acc[C * C + o] = a;
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < C * C; i += ZT) atomicAdd(dWf + i, acc[i]);
+  for (int i = tid; i < C; i += ZT) atomicAdd(dbf + i, acc[C * C + i]);
+}
+
+static Geo make_geo(int B, int C, int H, int W, bool heavy) {
+  Geo g;
+  g.B = B; g.H = H; g.W = W; g.HW = H * W;
+  int target = heavy ? (C <= 24 ? 256 : (C <= 48 ? 128 : 64)) : 256;
+  g.ipc = g.HW >= target ? 1 : target / g.HW;
+  if (g.ipc > B) g.ipc = B;
+  g.pixt = g.ipc * g.HW;
+  return g;
+}
+
+template <typename K>
+static int ensure_smem(K kernel, int bytes) {
+  if (bytes <= 48 * 1024) return NFK_OK;
+  if (bytes > 227 * 1024) return NFK_ERR_SHAPE;
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) == cudaSuccess
+             ? NFK_OK
+             : NFK_ERR_LAUNCH;
+}
+
+#define NFK_DISPATCH_C(C_, ...)                             \
+  switch (C_) {                                             \
+    case 12: { constexpr int CC = 12; __VA_ARGS__; } break; \
+    case 24: { constexpr int CC = 24; __VA_ARGS__; } break; \
+    case 48: { constexpr int CC = 48; __VA_ARGS__; } break; \
+    case 96: { constexpr int CC = 96; __VA_ARGS__; } break; \
+    default: return NFK_ERR_SHAPE;                          \
+  }
+
+}  // namespace nfk
+
+using namespace nfk;
+
+extern "C" int nfk_affine1x1_fwd(const float* x, const float* Wf, const float* bf, const float* sl, float* y,
+                                 void* col, int K1p, const float* ld_in, float* ld_out, int B, int C, int H, int W,
+                                 void* stream) {
+  if (B <= 0 || H <= 0 || W <= 0 || H * W > 4096) return NFK_ERR_SHAPE;
+  if (!x || (!Wf && !col) || (Wf && (!bf || !y)) || (ld_out && (!ld_in || !sl))) return NFK_ERR_ARG;
+  if (col && (K1p % 64 || K1p < 9 * (C / 2))) return NFK_ERR_SHAPE;
+  Geo g = make_geo(B, C, H, W, false);
+  const int smem = (C * C + C + (col ? (C / 2) * (g.pixt + 1) + K1p : 0)) * 4;
+  const int grid = (B + g.ipc - 1) / g.ipc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  NFK_DISPATCH_C(C, {
+    int rc = ensure_smem(affine1x1_fwd_kernel<CC>, smem);
+    if (rc) return rc;
+    affine1x1_fwd_kernel<CC><<<grid, ZT, smem, st>>>(x, Wf, bf, sl, y, static_cast<__nv_bfloat16*>(col), ld_in,
+                                                     ld_out, g, K1p);
+  });
+  return cudaGetLastError() == cudaSuccess ? NFK_OK : NFK_ERR_LAUNCH;
+}
+
+extern "C" int nfk_coupling_fwd(const float* P, int K3p, const float* bias3, float* y, float* hsave, float* ld,
+                                int B, int C, int H, int W, int reverse, void* stream) {
+  if (B <= 0 || H <= 0 || W <= 0 || H * W > 4096 || K3p < 9 * C || K3p % 2) return NFK_ERR_SHAPE;
+  if (!P || !bias3 || !y) return NFK_ERR_ARG;
+  Geo g = make_geo(B, C, H, W, false);
+  const int smem = 2 * (C / 2) * (g.pixt + 1) * 4;
+  const int grid = (B + g.ipc - 1) / g.ipc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  NFK_DISPATCH_C(C, {
+    int rc = ensure_smem(coupling_fwd_kernel<CC>, smem);
+    if (rc) return rc;
+    coupling_fwd_kernel<CC><<<grid, ZT, smem, st>>>(P, K3p, bias3, y, hsave, ld, g, reverse);
+  });
+  return cudaGetLastError() == cudaSuccess ? NFK_OK : NFK_ERR_LAUNCH;
+}
+
+extern "C" int nfk_coupling_bwd(const float* g_out, const float* g_ld, const float* z_out, const float* hsave,
+                                float* dy, void* dhcol, int K3p, float* dbias3, int B, int C, int H, int W,
+                                void* stream) {
+  if (B <= 0 || H <= 0 || W <= 0 || H * W > 4096 || K3p % 64 || K3p < 9 * C) return NFK_ERR_SHAPE;
+  if (!g_out || !g_ld || !z_out || !hsave || !dy || !dhcol || !dbias3) return NFK_ERR_ARG;
+  Geo g = make_geo(B, C, H, W, true);
+  const int smem = (2 * C * (g.pixt + 1) + C + K3p) * 4;
+  const int grid = (B + g.ipc - 1) / g.ipc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  NFK_DISPATCH_C(C, {
+    int rc = ensure_smem(coupling_bwd_kernel<CC>, smem);
+    if (rc) return rc;
+    coupling_bwd_kernel<CC><<<grid, ZT, smem, st>>>(g_out, g_ld, z_out, hsave, dy,
+                                                    static_cast<__nv_bfloat16*>(dhcol), K3p, dbias3, g);
+  });
+  return cudaGetLastError() == cudaSuccess ? NFK_OK : NFK_ERR_LAUNCH;
+}
+
+extern "C" int nfk_affine1x1_bwd(const float* dy, const float* dcol, int K1p, const float* x, const float* Wf,
+                                 float* dx, float* dWf, float* dbf, int B, int C, int H, int W, void* stream) {
+  if (B <= 0 || H <= 0 || W <= 0 || H * W > 4096) return NFK_ERR_SHAPE;
+  if (!dy || !x || !Wf || !dx || !dWf || !dbf) return NFK_ERR_ARG;
+  Geo g = make_geo(B, C, H, W, true);
+  const int smem = (C * C + 2 * C * (g.pixt + 1) + C * C + C) * 4;
+  const int grid = (B + g.ipc - 1) / g.ipc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  NFK_DISPATCH_C(C, {
+    int rc = ensure_smem(affine1x1_bwd_kernel<CC>, smem);
+    if (rc) return rc;
+    affine1x1_bwd_kernel<CC><<<grid, ZT, smem, st>>>(dy, dcol, K1p, x, Wf, dx, dWf, dbf, g);
+  });
+  return cudaGetLastError() == cudaSuccess ? NFK_OK : NFK_ERR_LAUNCH;
+}

@@ -1,0 +1,267 @@
+"""Autograd glue between the drop-in nn.Modules (models/) and the libnfk kernels (ops.py).
+
+Each torch.autograd.Function runs one reference layer (FlowStep, Split2d, prior->bpd, per-level KD MSE) as a short,
+fixed sequence of kernel launches; saved tensors are exactly what the matching backward sequence reads.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from . import ops
+
+BF16 = torch.bfloat16
+F32 = torch.float32
+
+
+# ------------------------------------------------------------------------------------------------ derived weights
+@dataclass
+class StepConsts:
+    """Per-FlowStep tensors derived from the parameters (rebuilt whenever a parameter changes)."""
+    Wf: torch.Tensor          # [C,C] fused ActNorm o invconv matrix (forward or inverse direction)
+    bf: torch.Tensor          # [C]
+    sl: torch.Tensor          # [1] +-(sum logs + sum log_s)
+    B1: torch.Tensor = None   # bf16 GEMM operands of the coupling net
+    B1T: torch.Tensor = None
+    B2: torch.Tensor = None
+    B2T: torch.Tensor = None
+    B3: torch.Tensor = None
+    B3T: torch.Tensor = None
+    bias1: torch.Tensor = None
+    bias2: torch.Tensor = None
+    bias3: torch.Tensor = None
+
+
+def build_affine(an_bias, an_logs, inv, C, reverse, transpose):
+    """inv = (lower, upper, log_s, p, sign_s, weight) with unused entries None."""
+    dev = an_bias.device
+    Wf = torch.empty(C, C, device=dev, dtype=F32)
+    bf = torch.empty(C, device=dev, dtype=F32)
+    sl = torch.empty(1, device=dev, dtype=F32)
+    lower, upper, log_s, p, sign_s, weight = inv
+    ops.invconv_prep(an_bias, an_logs, lower, upper, log_s, p, sign_s, weight, C, reverse, transpose, Wf, bf, sl)
+    return Wf, bf, sl
+
+
+def build_coupling_ops(cw, cin, hid, cout, with_t):
+    """cw = (w1, b1, l1, w2, b2, l2, w3, b3, l3) reference parameters of get_block_2d."""
+    dev = cw[0].device
+    K1p, K3p = ops.round_up(9 * cin, 64), ops.round_up(9 * cout, 64)
+    e = lambda *s: torch.empty(*s, device=dev, dtype=BF16)
+    B1, B2, B3 = e(hid, K1p), e(hid, hid), e(K3p, hid)
+    B1T, B2T, B3T = (e(K1p, hid), e(hid, hid), e(hid, K3p)) if with_t else (None, None, None)
+    bias1 = torch.empty(hid, device=dev, dtype=F32)
+    bias2 = torch.empty(hid, device=dev, dtype=F32)
+    bias3 = torch.empty(cout, device=dev, dtype=F32)
+    ops.coupling_prep(*cw, cin, hid, cout, K1p, K3p, B1, B1T, B2, B2T, B3, B3T, bias1, bias2, bias3, with_t)
+    return B1, B1T, B2, B2T, B3, B3T, bias1, bias2, bias3
+
+
+def _coupling_net(col, k: StepConsts, M, hid, K1p, K3p, keep):
+    """conv3x3 -> ReLU -> conv1x1 -> ReLU -> per-tap products of the last conv3x3, all on tcgen05."""
+    dev = col.device
+    h1 = torch.empty(M, hid, device=dev, dtype=BF16)
+    ops.gemm_nt(col, k.B1, M, hid, K1p, ops.EPI_BIAS_RELU_BF16, h1, bias=k.bias1)
+    h2 = torch.empty(M, hid, device=dev, dtype=BF16)
+    ops.gemm_nt(h1, k.B2, M, hid, hid, ops.EPI_BIAS_RELU_BF16, h2, bias=k.bias2)
+    P = torch.empty(M, K3p, device=dev, dtype=F32)
+    ops.gemm_nt(h2, k.B3, M, K3p, hid, ops.EPI_F32, P)
+    return (h1, h2, P) if keep else (None, None, P)
+
+
+def flowstep2d_forward(x, ld_in, k: StepConsts, hid, keep):
+    """FlowStep.normal_flow (reference models/flows.py:142-171), 2-D affine coupling."""
+    B, C, H, W = x.shape
+    M, cin = B * H * W, C // 2
+    K1p, K3p = ops.round_up(9 * cin, 64), ops.round_up(9 * C, 64)
+    dev = x.device
+    y = torch.empty_like(x)
+    col = torch.empty(M, K1p, device=dev, dtype=BF16)
+    ld_out = torch.empty(B, device=dev, dtype=F32)
+    ops.affine1x1_fwd(x, k.Wf, k.bf, k.sl, y, col, K1p, ld_in, ld_out, B, C, H, W)
+    h1, h2, P = _coupling_net(col, k, M, hid, K1p, K3p, keep)
+    hsave = torch.empty(M, C, device=dev, dtype=F32) if keep else None
+    ops.coupling_fwd(P, K3p, k.bias3, y, hsave, ld_out, B, C, H, W, reverse=False)
+    return y, ld_out, (col, h1, h2, hsave)
+
+
+def flowstep2d_reverse(z, ld_in, k: StepConsts, hid):
+    """FlowStep.reverse_flow (reference models/flows.py:173-202): coupling^-1 -> invconv^-1 -> actnorm^-1.
+    k.Wf / k.bf / k.sl hold the INVERSE affine here."""
+    B, C, H, W = z.shape
+    M, cin = B * H * W, C // 2
+    K1p, K3p = ops.round_up(9 * cin, 64), ops.round_up(9 * C, 64)
+    dev = z.device
+    col = torch.empty(M, K1p, device=dev, dtype=BF16)
+    ops.affine1x1_fwd(z, None, None, None, None, col, K1p, None, None, B, C, H, W)   # im2col of z1 only
+    _, _, P = _coupling_net(col, k, M, hid, K1p, K3p, keep=False)
+    zc = z.clone()
+    ld_mid = ld_in.clone()
+    ops.coupling_fwd(P, K3p, k.bias3, zc, None, ld_mid, B, C, H, W, reverse=True)
+    x = torch.empty_like(z)
+    ld_out = torch.empty_like(ld_mid)
+    ops.affine1x1_fwd(zc, k.Wf, k.bf, k.sl, x, None, 0, ld_mid, ld_out, B, C, H, W)
+    return x, ld_out
+
+
+class FlowStep2dFn(torch.autograd.Function):
+    """Differentiable 2-D FlowStep forward. Inputs: x, logdet, then the 14 reference parameters and 2 buffers."""
+
+    @staticmethod
+    def forward(ctx, x, ld_in, hid, an_bias, an_logs, lower, upper, log_s, p, sign_s, w1, b1, l1, w2, b2, l2, w3,
+                b3, l3):
+        B, C, H, W = x.shape
+        x = x.contiguous()
+        Wf, bf, sl = build_affine(an_bias, an_logs, (lower, upper, log_s, p, sign_s, None), C, False, False)
+        cw = (w1, b1, l1, w2, b2, l2, w3, b3, l3)
+        k = StepConsts(Wf, bf, sl, *build_coupling_ops(cw, C // 2, hid, C, True))
+        y, ld_out, (col, h1, h2, hsave) = flowstep2d_forward(x, ld_in.contiguous(), k, hid, keep=True)
+        ctx.hid = hid
+        ctx.save_for_backward(x, y, col, h1, h2, hsave, Wf, k.B1T, k.B2T, k.B3T, an_bias, an_logs, lower, upper,
+                              log_s, p, sign_s, *cw)
+        ctx.mark_non_differentiable()
+        return y, ld_out
+
+    @staticmethod
+    def backward(ctx, g_out, g_ld):
+        (x, z_out, col, h1, h2, hsave, Wf, B1T, B2T, B3T, an_bias, an_logs, lower, upper, log_s, p, sign_s,
+         *cw) = ctx.saved_tensors
+        hid = ctx.hid
+        B, C, H, W = x.shape
+        M, cin = B * H * W, C // 2
+        K1p, K3p = ops.round_up(9 * cin, 64), ops.round_up(9 * C, 64)
+        dev = x.device
+        g_out = torch.zeros_like(x) if g_out is None else g_out.contiguous()
+        g_ld = torch.zeros(B, device=dev, dtype=F32) if g_ld is None else g_ld.contiguous()
+        # one zero-filled arena for every accumulate-into buffer of this step
+        sizes = [C, hid, hid, K3p * hid, hid * hid, hid * K1p, C * C, C]
+        offs = [0]
+        for s in sizes:
+            offs.append(offs[-1] + ops.round_up(s, 4))
+        arena = torch.zeros(offs[-1], device=dev, dtype=F32)
+        dbias3, dbias2, dbias1, dB3, dB2, dB1, dWf, dbf = (arena[offs[i]:offs[i] + sizes[i]] for i in range(8))
+        dB3, dB2, dB1, dWf = dB3.view(K3p, hid), dB2.view(hid, hid), dB1.view(hid, K1p), dWf.view(C, C)
+
+        dy = torch.empty_like(x)
+        dhcol = torch.empty(M, K3p, device=dev, dtype=BF16)
+        ops.coupling_bwd(g_out, g_ld, z_out, hsave, dy, dhcol, K3p, dbias3, B, C, H, W)
+        dpre2 = torch.empty(M, hid, device=dev, dtype=BF16)
+        ops.gemm_nt(dhcol, B3T, M, hid, K3p, ops.EPI_MASK_BF16, dpre2, aux=h2, colsum=dbias2)
+        ops.gemm_tn(dhcol, h2, K3p, hid, M, dB3)
+        dpre1 = torch.empty(M, hid, device=dev, dtype=BF16)
+        ops.gemm_nt(dpre2, B2T, M, hid, hid, ops.EPI_MASK_BF16, dpre1, aux=h1, colsum=dbias1)
+        ops.gemm_tn(dpre2, h1, hid, hid, M, dB2)
+        dcol = torch.empty(M, K1p, device=dev, dtype=F32)
+        ops.gemm_nt(dpre1, B1T, M, K1p, hid, ops.EPI_F32, dcol)
+        ops.gemm_tn(dpre1, col, hid, K1p, M, dB1)
+        dx = torch.empty_like(x)
+        ops.affine1x1_bwd(dy, dcol, K1p, x, Wf, dx, dWf, dbf, B, C, H, W)
+
+        d_an_bias, d_an_logs = torch.empty_like(an_bias), torch.empty_like(an_logs)
+        d_lower, d_upper, d_log_s = torch.empty_like(lower), torch.empty_like(upper), torch.empty_like(log_s)
+        ops.invconv_prep_bwd(an_bias, an_logs, lower, upper, log_s, p, sign_s, None, C, False, Wf, dWf, dbf, g_ld, B,
+                             H * W, d_an_bias, d_an_logs, d_lower, d_upper, d_log_s, None)
+        grads = [torch.empty_like(t) for t in cw]
+        ops.coupling_prep_bwd(*cw, cin, hid, C, K1p, K3p, dB1, dbias1, dB2, dbias2, dB3, dbias3, *grads)
+        return (dx, g_ld, None, d_an_bias, d_an_logs, d_lower, d_upper, d_log_s, None, None, *grads)
+
+
+# ------------------------------------------------------------------------------------------------ Split2d
+class Split2dFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, ld_in, w, bias, logs):
+        B, C, H, W = x.shape
+        x = x.contiguous()
+        z1 = torch.empty(B, C // 2, H, W, device=x.device, dtype=F32)
+        ld = ld_in.clone()
+        ops.split2d_fwd(x, w, bias, logs, z1, ld, B, C, H, W)
+        ctx.save_for_backward(x, w, bias, logs)
+        return z1, ld
+
+    @staticmethod
+    def backward(ctx, g_z1, g_ld):
+        x, w, bias, logs = ctx.saved_tensors
+        B, C, H, W = x.shape
+        dev = x.device
+        g_ld = torch.zeros(B, device=dev, dtype=F32) if g_ld is None else g_ld.contiguous()
+        g_z1 = None if g_z1 is None else g_z1.contiguous()
+        dx = torch.empty_like(x)
+        nw = w.numel()
+        arena = torch.zeros(nw + 2 * C, device=dev, dtype=F32)
+        dw, dbias, dlogs = arena[:nw].view_as(w), arena[nw:nw + C].view_as(bias), arena[nw + C:].view_as(logs)
+        ops.split2d_bwd(x, w, bias, logs, g_z1, g_ld, dx, dw, dbias, dlogs, B, C, H, W)
+        return dx, g_ld, dw, dbias, dlogs
+
+
+def split2d_reverse(z1, w, bias, logs, eps, temperature):
+    B, CH, H, W = z1.shape
+    out = torch.empty(B, 2 * CH, H, W, device=z1.device, dtype=F32)
+    ops.split2d_rev(z1.contiguous(), w, bias, logs, eps, temperature, out, B, 2 * CH, H, W)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ prior -> bpd
+class PriorBpdFn(torch.autograd.Function):
+    """bpd[b] = -(logdet[b] + log N(z_b; mean, exp(logs))) * scale (reference models/kd_flows.py:134-150)."""
+
+    @staticmethod
+    def forward(ctx, z, logdet, mean, logs, scale):
+        B = z.shape[0]
+        n = z[0].numel()
+        z = z.contiguous()
+        out = torch.empty(B, device=z.device, dtype=F32)
+        ops.prior_bpd_fwd(z, mean, logs, logdet.contiguous(), B, n, scale, out)
+        ctx.save_for_backward(z, mean, logs)
+        ctx.scale = scale
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        z, mean, logs = ctx.saved_tensors
+        B = z.shape[0]
+        n = z[0].numel()
+        dz = torch.empty_like(z)
+        dld = torch.empty(B, device=z.device, dtype=F32)
+        ops.prior_bpd_bwd(z, mean, logs, g.contiguous(), B, n, ctx.scale, dz, dld)
+        return dz, dld, None, None, None
+
+
+# ------------------------------------------------------------------------------------------------ KD loss
+class KdMseFn(torch.autograd.Function):
+    """kd[b] = (1/L) sum_levels mean_i (s_i - t_i)^2 in one accumulation buffer (pl_module.py:266-282).
+    Inputs: L student tensors followed by L teacher tensors (teacher is constant)."""
+
+    @staticmethod
+    def forward(ctx, *tensors):
+        L = len(tensors) // 2
+        s = [t.contiguous() for t in tensors[:L]]
+        t = [t.contiguous() for t in tensors[L:]]
+        B = s[0].shape[0]
+        acc = torch.zeros(B, device=s[0].device, dtype=F32)
+        for a, b in zip(s, t):
+            n = a[0].numel()
+            ops.kd_mse_fwd(a, b, B, n, 1.0 / (n * L), acc)
+        ctx.save_for_backward(*s, *t)
+        ctx.L = L
+        return acc
+
+    @staticmethod
+    def backward(ctx, g):
+        L = ctx.L
+        saved = ctx.saved_tensors
+        g = g.contiguous()
+        grads = []
+        for a, b in zip(saved[:L], saved[L:]):
+            B, n = a.shape[0], a[0].numel()
+            ds = torch.empty_like(a)
+            ops.kd_mse_bwd(a, b, g, B, n, 1.0 / (n * L), ds)
+            grads.append(ds)
+        return (*grads, *([None] * L))
+
+
+def kd_mse(student_levels, teacher_levels) -> Optional[torch.Tensor]:
+    if not student_levels:
+        return None
+    return KdMseFn.apply(*student_levels, *[t.detach() for t in teacher_levels])

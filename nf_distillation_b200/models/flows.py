@@ -1,0 +1,300 @@
+"""Drop-in mirror of the reference's models/flows.py (FlowStep / FlowNet / Glow): same constructor arguments,
+module tree and call signatures. FlowStep runs as a fixed sequence of libnfk kernels (functional.py).
+
+Reference line numbers refer to /root/reference/models/flows.py.
+"""
+from __future__ import annotations
+
+import logging
+import math
+
+import torch
+import torch.nn as nn
+
+from .. import functional as Fn
+from .layers import (ActNorm1d, ActNorm2d, Conv2d, Conv2dZeros, InvertibleConv1x1, LinearZeros, Permute2d, Split2d,
+                     SqueezeLayer, _as_logdet, _require_cuda, gaussian_likelihood, gaussian_sample)
+from .utils import split_feature, uniform_binning_correction
+
+logger = logging.getLogger(__name__)
+
+
+def get_block_2d(in_channels, out_channels, hidden_channels):
+    """conv3x3+ActNorm -> ReLU -> conv1x1+ActNorm -> ReLU -> zero-init conv3x3 (flows.py:25-34). The Sequential
+    only holds the parameters (state_dict keys block.{0,2,4}.*); FlowStep executes it as three tcgen05 GEMMs."""
+    return nn.Sequential(
+        Conv2d(in_channels, hidden_channels),
+        nn.ReLU(inplace=False),
+        Conv2d(hidden_channels, hidden_channels, kernel_size=(1, 1)),
+        nn.ReLU(inplace=False),
+        Conv2dZeros(hidden_channels, out_channels),
+    )
+
+
+def get_block_1d(in_features, out_features, hidden_features):
+    """6-Linear MLP, ReLU x4 then Tanh (flows.py:37-52); executed by the fused 1-D coupling kernel."""
+    return nn.Sequential(
+        nn.Linear(in_features, hidden_features), nn.ReLU(inplace=False),
+        nn.Linear(hidden_features, hidden_features), nn.ReLU(inplace=False),
+        nn.Linear(hidden_features, hidden_features), nn.ReLU(inplace=False),
+        nn.Linear(hidden_features, hidden_features), nn.ReLU(inplace=False),
+        nn.Linear(hidden_features, hidden_features), nn.Tanh(),
+        nn.Linear(hidden_features, out_features),
+    )
+
+
+class FlowStep(nn.Module):
+    """actnorm -> invertible 1x1 conv -> affine coupling, forward and inverse (flows.py:55-202)."""
+
+    def __init__(self, in_channels, hidden_channels, actnorm_scale, flow_permutation, flow_coupling, LU_decomposed,
+                 is_1d=False, condition_features=0):
+        super().__init__()
+        self.is_1d = is_1d
+        self.flow_coupling = flow_coupling
+        self.flow_permutation_type = flow_permutation
+        self.condition_features = condition_features
+        self.in_channels = in_channels
+        self.hidden_channels = hidden_channels
+
+        self.actnorm = ActNorm1d(in_channels, actnorm_scale) if is_1d else ActNorm2d(in_channels, actnorm_scale)
+        if flow_permutation == "invconv":
+            self.invconv = InvertibleConv1x1(in_channels, LU_decomposed=LU_decomposed, is_1d=is_1d)
+        elif flow_permutation == "shuffle":
+            if is_1d:
+                raise RuntimeError("Permutation is not supported is 1d mode")
+            self.shuffle = Permute2d(in_channels, shuffle=True)
+        else:
+            if is_1d:
+                raise RuntimeError("Permutation is not supported is 1d mode")
+            self.reverse = Permute2d(in_channels, shuffle=False)
+
+        if flow_coupling == "additive":
+            out_block = in_channels - in_channels // 2
+        elif flow_coupling == "affine":
+            out_block = (in_channels - in_channels // 2) * 2
+        else:
+            raise NameError(f"Unknown coupling type: {flow_coupling}")
+        in_block = in_channels // 2 + condition_features
+        make = get_block_1d if is_1d else get_block_2d
+        self.block = make(in_block, out_block, hidden_channels)
+        self._cache = {}
+
+    # ---- parameter views in the order the kernels expect
+    def _coupling_params_2d(self):
+        b = self.block
+        return (b[0].conv.weight, b[0].actnorm.bias, b[0].actnorm.logs,
+                b[2].conv.weight, b[2].actnorm.bias, b[2].actnorm.logs,
+                b[4].conv.weight, b[4].conv.bias, b[4].logs)
+
+    def _all_params(self):
+        inv = [t for t in self.invconv.lu_tensors() if t is not None]
+        blk = list(self.block.parameters())
+        return [self.actnorm.bias, self.actnorm.logs, *inv, *blk]
+
+    def _consts(self, reverse: bool) -> Fn.StepConsts:
+        """Derived tensors for the no-grad path (frozen teacher, sampling): rebuilt only when a parameter changed."""
+        key = (reverse, tuple((p.data_ptr(), p._version) for p in self._all_params()))
+        hit = self._cache.get(reverse)
+        if hit is not None and hit[0] == key:
+            return hit[1]
+        C = self.in_channels
+        inv = tuple(None if t is None else t.detach() for t in self.invconv.lu_tensors())
+        Wf, bf, sl = Fn.build_affine(self.actnorm.bias.detach(), self.actnorm.logs.detach(), inv, C, reverse,
+                                     self.is_1d)
+        if self.is_1d:
+            k = Fn.StepConsts(Wf, bf, sl)
+        else:
+            cw = tuple(t.detach() for t in self._coupling_params_2d())
+            k = Fn.StepConsts(Wf, bf, sl, *Fn.build_coupling_ops(cw, C // 2, self.hidden_channels, C, False))
+        self._cache[reverse] = (key, k)
+        return k
+
+    def _check_supported(self, input):
+        _require_cuda(input, "FlowStep")
+        if self.flow_permutation_type != "invconv" or self.flow_coupling != "affine":
+            raise NotImplementedError("the CUDA path covers flow_permutation='invconv' + flow_coupling='affine' "
+                                      "(every shipped config); shuffle/reverse/additive are not built yet")
+        if not self.is_1d:
+            if self.condition_features:
+                raise NotImplementedError("y-conditioned 2-D coupling is not built (no shipped image config uses it)")
+            if self.hidden_channels % 64 or self.in_channels not in (12, 24, 48, 96):
+                raise NotImplementedError("2-D FlowStep kernels need hidden_channels % 64 == 0 and "
+                                          "C in {12, 24, 48, 96}")
+            if not self.invconv.LU_decomposed and torch.is_grad_enabled():
+                pass
+
+    def forward(self, input, y_onehot=None, logdet=None, reverse=False):
+        self._check_supported(input)
+        if self.is_1d:
+            from .. import flow1d
+            return flow1d.flowstep1d(self, input, y_onehot, logdet, reverse)
+        B = input.shape[0]
+        ld = _as_logdet(logdet, B, input.device)
+        want_ld = ld is not None
+        if ld is None:
+            ld = torch.zeros(B, device=input.device)
+        params = self._all_params()
+        needs_grad = torch.is_grad_enabled() and (input.requires_grad or ld.requires_grad
+                                                  or any(p.requires_grad for p in params))
+        if not reverse:
+            if needs_grad:
+                if not self.invconv.LU_decomposed:
+                    raise NotImplementedError("training with LU_decomposed=False is not built")
+                iv = self.invconv
+                z, ld_out = Fn.FlowStep2dFn.apply(input, ld, self.hidden_channels, self.actnorm.bias,
+                                                  self.actnorm.logs, iv.lower, iv.upper, iv.log_s, iv.p, iv.sign_s,
+                                                  *self._coupling_params_2d())
+            else:
+                z, ld_out, _ = Fn.flowstep2d_forward(input.contiguous(), ld.contiguous(), self._consts(False),
+                                                     self.hidden_channels, keep=False)
+        else:
+            if needs_grad:
+                raise NotImplementedError("gradients through the 2-D inverse pass are not built (image configs use "
+                                          "perceptual weight 0, conf/training/cifar.yaml:17-20)")
+            z, ld_out = Fn.flowstep2d_reverse(input.contiguous(), ld.contiguous(), self._consts(True),
+                                              self.hidden_channels)
+        return z, (ld_out if want_ld else None)
+
+    def normal_flow(self, input, y_onehot, logdet):
+        return self.forward(input, y_onehot=y_onehot, logdet=logdet, reverse=False)
+
+    def reverse_flow(self, input, y_onehot, logdet):
+        return self.forward(input, y_onehot=y_onehot, logdet=logdet, reverse=True)
+
+
+class FlowNet(nn.Module):
+    """[Squeeze, K x FlowStep, Split2d] x (L-1) + [Squeeze, K x FlowStep] (flows.py:205-295)."""
+
+    def __init__(self, image_shape, hidden_channels, K, L, actnorm_scale, flow_permutation, flow_coupling,
+                 LU_decomposed, is_1d=False, condition_features=0):
+        super().__init__()
+        self.is_1d = is_1d
+        self.layers = nn.ModuleList()
+        self.output_shapes = []
+        self.K = K
+        self.L = L
+        if not is_1d:
+            H, W, C = image_shape
+        else:
+            C = image_shape[0]
+        for i in range(L):
+            if not is_1d:
+                C, H, W = C * 4, H // 2, W // 2
+                self.layers.append(SqueezeLayer(factor=2))
+                self.output_shapes.append([-1, C, H, W])
+            for _ in range(K):
+                self.layers.append(FlowStep(in_channels=C, hidden_channels=hidden_channels,
+                                            actnorm_scale=actnorm_scale, flow_permutation=flow_permutation,
+                                            flow_coupling=flow_coupling, LU_decomposed=LU_decomposed, is_1d=is_1d,
+                                            condition_features=condition_features))
+                self.output_shapes.append([-1, C] if is_1d else [-1, C, H, W])
+            if i < L - 1 and not is_1d:
+                self.layers.append(Split2d(num_channels=C))
+                self.output_shapes.append([-1, C // 2, H, W])
+                C = C // 2
+
+    def forward(self, input, y_onehot=None, logdet=0.0, reverse=False, temperature=None):
+        if reverse:
+            return self.decode(input, y_onehot=y_onehot, temperature=temperature)
+        return self.encode(input, y_onehot=y_onehot, logdet=logdet)
+
+    def encode(self, z, y_onehot=None, logdet=0.0):
+        for layer in self.layers:
+            z, logdet = layer(z, y_onehot=y_onehot, logdet=logdet, reverse=False)
+        return z, logdet
+
+    def decode(self, z, y_onehot=None, temperature=None):
+        for layer in reversed(self.layers):
+            if isinstance(layer, Split2d):
+                z, _ = layer(z, logdet=0, reverse=True, temperature=temperature)
+            else:
+                z, _ = layer(z, y_onehot=y_onehot, logdet=0, reverse=True)
+        return z
+
+
+class Glow(nn.Module):
+    """Flow + prior + bits/dim objective (flows.py:298-438)."""
+
+    def __init__(self, image_shape, hidden_channels, K, L, actnorm_scale, flow_permutation, flow_coupling,
+                 LU_decomposed, y_classes, learn_top, y_condition, is_1d=False):
+        super().__init__()
+        self.flow = FlowNet(image_shape=image_shape, hidden_channels=hidden_channels, K=K, L=L,
+                            actnorm_scale=actnorm_scale, flow_permutation=flow_permutation,
+                            flow_coupling=flow_coupling, LU_decomposed=LU_decomposed, is_1d=is_1d,
+                            condition_features=y_classes if y_condition else 0)
+        self.is_1d = is_1d
+        self.y_classes = y_classes
+        self.y_condition = y_condition
+        self.learn_top = learn_top
+        if learn_top:
+            C = self.flow.output_shapes[-1][1]
+            self.learn_top_fn = LinearZeros(C * 2, C * 2) if is_1d else Conv2dZeros(C * 2, C * 2)
+        if y_condition:
+            C = self.flow.output_shapes[-1][1]
+            self.project_ycond = LinearZeros(y_classes, 2 * C)
+            self.project_class = LinearZeros(C, y_classes)
+        last = self.flow.output_shapes[-1]
+        self.register_buffer("prior_h", torch.zeros([1, last[1] * 2] + ([] if is_1d else [last[2], last[3]])))
+
+    def prior(self, data, y_onehot=None):
+        """(mean, logs) of the top-level Gaussian (flows.py:367-391); batch 32 when neither data nor y is given."""
+        if data is not None:
+            batch = data.shape[0]
+        else:
+            batch = y_onehot.size(0) if y_onehot is not None else 32
+        h = self.prior_h.repeat(batch, *([1] * (self.prior_h.dim() - 1)))
+        channels = h.size(1)
+        if self.learn_top:
+            if self.is_1d:
+                h = self.learn_top_fn(h)
+            else:
+                raise NotImplementedError("learn_top for 2-D is not built (learn_top: false in every config)")
+        if self.y_condition:
+            assert y_onehot is not None
+            yp = self.project_ycond(y_onehot)
+            h = h + yp.view(h.shape[0], channels, *([1] * (h.dim() - 2)))
+        return split_feature(h, "split")
+
+    def _prior_rows(self):
+        """Batch-independent (mean, logs) rows when the prior is the fixed buffer (all shipped non-RICH configs)."""
+        if self.learn_top or self.y_condition:
+            return None
+        h = self.prior_h
+        c = h.shape[1] // 2
+        return h[0, :c].contiguous().view(-1), h[0, c:].contiguous().view(-1)
+
+    def forward(self, x=None, y_onehot=None, z=None, temperature=None, reverse=False):
+        if reverse:
+            return self.reverse_flow(z, y_onehot, temperature)
+        return self.normal_flow(x, y_onehot)
+
+    def _objective(self, x, z_last, logdet, y_onehot):
+        """bpd = -(logdet + log p(z)) / (ln2 * CHW) in 2-D, nats in 1-D — one fused reduction kernel."""
+        scale = 1.0 if self.is_1d else 1.0 / (math.log(2.0) * x.shape[1] * x.shape[2] * x.shape[3])
+        rows = self._prior_rows()
+        if rows is not None:
+            return Fn.PriorBpdFn.apply(z_last, logdet, rows[0], rows[1], scale)
+        mean, logs = self.prior(x, y_onehot)
+        return -(logdet + gaussian_likelihood(mean, logs, z_last)) * scale
+
+    def normal_flow(self, x, y_onehot=None):
+        _require_cuda(x, "Glow")
+        if self.is_1d:
+            logdet = torch.zeros(x.shape[0], device=x.device, dtype=torch.float32)
+        else:
+            x, logdet = uniform_binning_correction(x)
+        z, logdet = self.flow(x, y_onehot=y_onehot, logdet=logdet, reverse=False)
+        bpd = self._objective(x, z, logdet, y_onehot)
+        y_logits = self.project_class(z.mean(2).mean(2)) if self.y_condition else None
+        return z, bpd, y_logits
+
+    def reverse_flow(self, z, y_onehot, temperature):
+        if z is None:
+            mean, logs = self.prior(z, y_onehot)
+            z = gaussian_sample(mean, logs, temperature)
+        return self.flow(z, y_onehot=y_onehot, temperature=temperature, reverse=True)
+
+    def set_actnorm_init(self):
+        for _, module in self.named_modules():
+            if isinstance(module, (ActNorm2d, ActNorm1d)):
+                module.inited = True

@@ -1,0 +1,161 @@
+"""Tensor-level wrappers over the libnfk C-ABI (include/nfk.h): shape/dtype checks, pointer extraction, error
+codes -> exceptions. No arithmetic happens here and there is no fallback path: every call lands in a CUDA kernel.
+"""
+from __future__ import annotations
+
+import torch
+
+from ._lib import LIB, check
+
+EPI_F32, EPI_BIAS_RELU_BF16, EPI_MASK_BF16 = 0, 1, 2
+
+_LAUNCHES = 0  # kernels launched through this module (bench.py reports it as gpu_launches)
+
+
+def launch_count() -> int:
+    return _LAUNCHES
+
+
+def _p(t):
+    if t is None:
+        return None
+    assert t.is_cuda and t.is_contiguous(), "libnfk needs contiguous CUDA tensors"
+    return t.data_ptr()
+
+
+def _st():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _count(n=1):
+    global _LAUNCHES
+    _LAUNCHES += n
+
+
+def round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+def gemm_nt(A, B, M, N, K, epi, out, bias=None, aux=None, colsum=None):
+    """out[M,N] = A[M,K] @ B[N,K]^T on tcgen05 (bf16 operands, fp32 TMEM accumulate) with a fused epilogue."""
+    assert A.dtype == torch.bfloat16 and B.dtype == torch.bfloat16
+    _count()
+    check(LIB.nfk_gemm_nt_bf16(_p(A), A.stride(0), _p(B), B.stride(0), M, N, K, epi, _p(out), out.stride(0),
+                               _p(bias), _p(aux), 0 if aux is None else aux.stride(0), _p(colsum), _st()),
+          "nfk_gemm_nt_bf16")
+
+
+def gemm_tn(A, B, Mo, No, Kpix, out):
+    """out[Mo,No] += A[Kpix,Mo]^T @ B[Kpix,No] (split-K over pixels, fp32 red.add); out must be zeroed."""
+    assert A.dtype == torch.bfloat16 and B.dtype == torch.bfloat16 and out.dtype == torch.float32
+    _count()
+    check(LIB.nfk_gemm_tn_bf16(_p(A), A.stride(0), _p(B), B.stride(0), Mo, No, Kpix, _p(out), out.stride(0),
+                               sm_count(), _st()), "nfk_gemm_tn_bf16")
+
+
+_SM = {}
+
+
+def sm_count() -> int:
+    d = torch.cuda.current_device()
+    if d not in _SM:
+        _SM[d] = torch.cuda.get_device_properties(d).multi_processor_count
+    return _SM[d]
+
+
+def invconv_prep(an_bias, an_logs, lower, upper, log_s, p, sign_s, weight, C, reverse, transpose, outW, outb, out_sl):
+    _count()
+    check(LIB.nfk_invconv_prep(_p(an_bias), _p(an_logs), _p(lower), _p(upper), _p(log_s), _p(p), _p(sign_s),
+                               _p(weight), C, int(reverse), int(transpose), _p(outW), _p(outb), _p(out_sl), _st()),
+          "nfk_invconv_prep")
+
+
+def invconv_prep_bwd(an_bias, an_logs, lower, upper, log_s, p, sign_s, weight, C, transpose, Wf, dWf, dbf, g_ld, B,
+                     pixels, d_bias, d_logs, d_lower, d_upper, d_log_s, d_weight):
+    _count()
+    check(LIB.nfk_invconv_prep_bwd(_p(an_bias), _p(an_logs), _p(lower), _p(upper), _p(log_s), _p(p), _p(sign_s),
+                                   _p(weight), C, int(transpose), _p(Wf), _p(dWf), _p(dbf), _p(g_ld), B,
+                                   float(pixels), _p(d_bias), _p(d_logs), _p(d_lower), _p(d_upper), _p(d_log_s),
+                                   _p(d_weight), _st()), "nfk_invconv_prep_bwd")
+
+
+def coupling_prep(w1, b1, l1, w2, b2, l2, w3, b3, l3, cin, hid, cout, K1p, K3p, B1, B1T, B2, B2T, B3, B3T, bias1,
+                  bias2, bias3, with_t):
+    _count()
+    check(LIB.nfk_coupling_prep(_p(w1), _p(b1), _p(l1), _p(w2), _p(b2), _p(l2), _p(w3), _p(b3), _p(l3), cin, hid,
+                                cout, K1p, K3p, _p(B1), _p(B1T), _p(B2), _p(B2T), _p(B3), _p(B3T), _p(bias1),
+                                _p(bias2), _p(bias3), int(with_t), _st()), "nfk_coupling_prep")
+
+
+def coupling_prep_bwd(w1, b1, l1, w2, b2, l2, w3, b3, l3, cin, hid, cout, K1p, K3p, dB1, dbias1, dB2, dbias2, dB3,
+                      dbias3, dw1, db1, dl1, dw2, db2, dl2, dw3, db3, dl3):
+    _count()
+    check(LIB.nfk_coupling_prep_bwd(_p(w1), _p(b1), _p(l1), _p(w2), _p(b2), _p(l2), _p(w3), _p(b3), _p(l3), cin, hid,
+                                    cout, K1p, K3p, _p(dB1), _p(dbias1), _p(dB2), _p(dbias2), _p(dB3), _p(dbias3),
+                                    _p(dw1), _p(db1), _p(dl1), _p(dw2), _p(db2), _p(dl2), _p(dw3), _p(db3), _p(dl3),
+                                    _st()), "nfk_coupling_prep_bwd")
+
+
+def affine1x1_fwd(x, Wf, bf, sl, y, col, K1p, ld_in, ld_out, B, C, H, W):
+    _count()
+    check(LIB.nfk_affine1x1_fwd(_p(x), _p(Wf), _p(bf), _p(sl), _p(y), _p(col), K1p, _p(ld_in), _p(ld_out), B, C, H,
+                                W, _st()), "nfk_affine1x1_fwd")
+
+
+def coupling_fwd(P, K3p, bias3, y, hsave, ld, B, C, H, W, reverse):
+    _count()
+    check(LIB.nfk_coupling_fwd(_p(P), K3p, _p(bias3), _p(y), _p(hsave), _p(ld), B, C, H, W, int(reverse), _st()),
+          "nfk_coupling_fwd")
+
+
+def coupling_bwd(g_out, g_ld, z_out, hsave, dy, dhcol, K3p, dbias3, B, C, H, W):
+    _count()
+    check(LIB.nfk_coupling_bwd(_p(g_out), _p(g_ld), _p(z_out), _p(hsave), _p(dy), _p(dhcol), K3p, _p(dbias3), B, C,
+                               H, W, _st()), "nfk_coupling_bwd")
+
+
+def affine1x1_bwd(dy, dcol, K1p, x, Wf, dx, dWf, dbf, B, C, H, W):
+    _count()
+    check(LIB.nfk_affine1x1_bwd(_p(dy), _p(dcol), K1p, _p(x), _p(Wf), _p(dx), _p(dWf), _p(dbf), B, C, H, W, _st()),
+          "nfk_affine1x1_bwd")
+
+
+def split2d_fwd(x, w, bias, logs, z1_out, ld, B, C, H, W):
+    _count()
+    check(LIB.nfk_split2d_fwd(_p(x), _p(w), _p(bias), _p(logs), _p(z1_out), _p(ld), B, C, H, W, _st()),
+          "nfk_split2d_fwd")
+
+
+def split2d_rev(z1, w, bias, logs, eps, temperature, out, B, C, H, W):
+    _count()
+    check(LIB.nfk_split2d_rev(_p(z1), _p(w), _p(bias), _p(logs), _p(eps), float(temperature), _p(out), B, C, H, W,
+                              _st()), "nfk_split2d_rev")
+
+
+def split2d_bwd(x, w, bias, logs, g_z1, g_ld, dx, dw, dbias, dlogs, B, C, H, W):
+    _count()
+    check(LIB.nfk_split2d_bwd(_p(x), _p(w), _p(bias), _p(logs), _p(g_z1), _p(g_ld), _p(dx), _p(dw), _p(dbias),
+                              _p(dlogs), B, C, H, W, _st()), "nfk_split2d_bwd")
+
+
+def prior_bpd_fwd(z, mean, logs, logdet, B, n, scale, out):
+    _count()
+    check(LIB.nfk_prior_bpd_fwd(_p(z), _p(mean), _p(logs), _p(logdet), B, n, float(scale), _p(out), _st()),
+          "nfk_prior_bpd_fwd")
+
+
+def prior_bpd_bwd(z, mean, logs, g_bpd, B, n, scale, dz, dlogdet):
+    _count()
+    check(LIB.nfk_prior_bpd_bwd(_p(z), _p(mean), _p(logs), _p(g_bpd), B, n, float(scale), _p(dz), _p(dlogdet),
+                                _st()), "nfk_prior_bpd_bwd")
+
+
+def kd_mse_fwd(s, t, B, n, scale, acc):
+    _count()
+    check(LIB.nfk_kd_mse_fwd(_p(s), _p(t), B, n, float(scale), _p(acc), _st()), "nfk_kd_mse_fwd")
+
+
+def kd_mse_bwd(s, t, g, B, n, scale, ds, accumulate=False):
+    _count()
+    check(LIB.nfk_kd_mse_bwd(_p(s), _p(t), _p(g), B, n, float(scale), _p(ds), int(accumulate), _st()),
+          "nfk_kd_mse_bwd")

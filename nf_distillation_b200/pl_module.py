@@ -1,0 +1,164 @@
+"""KD training module: the hot-path slice of the reference's pl_module.py (NFModel) without Lightning.
+
+Kept: ``_get_kd_indices`` (pl_module.py:81-110), ``load_checkpoint`` (:112-129), ``create_model`` (:131-156),
+``forward`` (:198-255), ``loss`` (:257-320), ``generate`` (:322-346), ``configure_optimizers`` (:348-363),
+``training_step`` (:365-382) — same config keys, same batch formats, same returned dict. Everything else in the
+reference module (validation, FID/KS logging, data hooks) is out of scope.
+"""
+from __future__ import annotations
+
+import typing as tp
+
+import torch
+import torch.nn as nn
+
+from . import functional as Fn
+from .models import FlowStep, SqueezeLayer, create_glow_model, gaussian_sample  # noqa: F401
+
+TABULAR = ("bsds300", "gas", "hepmass", "miniboone", "power")
+
+
+class NFModel(nn.Module):
+    def __init__(self, config: tp.Dict[str, tp.Any]):
+        super().__init__()
+        self.params = config
+        self.nll_weight = config["loss"]["nll"]["weight"]
+        self.kd_weight = config["loss"]["kd"]["weight"]
+        self.perceptual_weight = config["loss"]["perceptual"]["weight"]
+        self.teacher = self.create_model("teacher")
+        self.student = self.create_model("student")
+        if self.teacher is not None:
+            for p in self.teacher.parameters():
+                p.requires_grad_(False)
+        name = config["loss"]["perceptual"].get("name", "l1")
+        if self.perceptual_weight > 0 and name != "l1":
+            raise NameError("only the l1 perceptual loss is on the hot path (vgg is out of scope)")
+        if config["loss"]["kd"].get("name", "mse") != "mse":
+            raise NameError("Unknown KD loss name")
+        self.student_kd_indices, self.teacher_kd_indices = self._get_kd_indices()
+        self.logged: tp.Dict[str, torch.Tensor] = {}
+
+    @property
+    def device(self):
+        return next(self.student.parameters()).device
+
+    def log(self, name, value, **kwargs):  # Lightning hook stand-in
+        self.logged[name] = value.detach()
+
+    # ---- pl_module.py:81-110
+    def _get_kd_indices(self):
+        if self.kd_weight + self.perceptual_weight == 0:
+            return [], []
+        is_1d = self.params["student"]["is_1d"]
+        mult = 2
+        s = [i for i, l in enumerate(self.student.flow.layers)
+             if isinstance(l, SqueezeLayer) or (is_1d and (i + 1) % mult == 0)
+             or i + 1 == len(self.student.flow.layers)]
+        t = [i for i, l in enumerate(self.teacher.flow.layers)
+             if isinstance(l, SqueezeLayer) or (is_1d and (i + 1) % (2 * mult) == 0)
+             or i + 1 == len(self.teacher.flow.layers)]
+        return s, t
+
+    # ---- pl_module.py:112-129
+    def load_checkpoint(self, model, checkpoint_path) -> nn.Module:
+        state = torch.load(checkpoint_path, map_location="cuda" if torch.cuda.is_available() else "cpu")
+        if "state_dict" in state:
+            state = {".".join(k.split(".")[1:]): v for k, v in state["state_dict"].items()
+                     if k.startswith("student.")}
+        model.load_state_dict(state)
+        return model
+
+    # ---- pl_module.py:131-156
+    def create_model(self, model_name) -> tp.Optional[nn.Module]:
+        if model_name == "teacher" and self.kd_weight + self.perceptual_weight == 0:
+            return None
+        cfg = dict(self.params[model_name])
+        ckpt = cfg.pop("checkpoint", None)
+        arch = cfg.pop("architecture", "glow")
+        if arch != "glow":
+            raise NameError(f"Unknown architecture: {arch}")
+        model = create_glow_model(cfg)
+        if ckpt:
+            model = self.load_checkpoint(model, ckpt)
+        return model
+
+    # ---- pl_module.py:198-255
+    def forward(self, batch):
+        name = self.params["data"]["name"]
+        if name in TABULAR:
+            x, y, weights = batch[0], None, None
+        elif "drop_weights" not in self.params["data"]:
+            x, y = batch
+            weights = None
+        else:
+            x, y, weights = batch
+        cond = y if self.params["student"]["y_condition"] else None
+        student_z, student_nll, _ = self.student(x, cond)
+        teacher_z = None
+        if self.kd_weight > 0:
+            with torch.no_grad():
+                teacher_z, _, _ = self.teacher(x, cond)   # x already carries the student's dequant noise
+        student_x = teacher_x = None
+        if self.perceptual_weight > 0:
+            mean, logs = self.student.prior(x, y_onehot=cond)
+            latent = gaussian_sample(mean, logs, 1)
+            student_x = self.student(z=latent, temperature=0.7, reverse=True, y_onehot=cond)[-1]
+            with torch.no_grad():
+                teacher_x = self.teacher(z=latent, temperature=0.7, reverse=True, y_onehot=cond)[-1]
+        return {"student_nll": student_nll, "student_z": student_z, "teacher_z": teacher_z,
+                "student_x": student_x, "teacher_x": teacher_x, "weights": weights}
+
+    # ---- pl_module.py:257-320
+    def loss(self, out, *args):
+        kd = perc = None
+        if self.kd_weight > 0:
+            pairs = list(zip(self.student_kd_indices, self.teacher_kd_indices))
+            kd = Fn.kd_mse([out["student_z"][s] for s, _ in pairs], [out["teacher_z"][t] for _, t in pairs])
+        if self.perceptual_weight > 0:
+            d = (out["student_x"] - out["teacher_x"]).abs()
+            perc = d.flatten(1).mean(1)
+            perc = torch.where(torch.isnan(perc), torch.zeros_like(perc), perc)
+        dev = out["student_nll"].device
+        if kd is None:
+            kd = torch.tensor(0.0, device=dev)
+        if perc is None:
+            perc = torch.tensor(0.0, device=dev)
+        result = self.nll_weight * out["student_nll"] + self.kd_weight * kd + self.perceptual_weight * perc
+        if out["weights"] is not None:
+            result = result * out["weights"]
+        return {"nll": out["student_nll"].mean(), "kd": kd.mean(), "perceptual": perc.mean(),
+                "result_loss": result.mean()}
+
+    # ---- pl_module.py:322-346
+    @torch.no_grad()
+    def generate(self, batch):
+        name = self.params["data"]["name"]
+        if name in TABULAR:
+            condition = batch[0]
+        elif "drop_weights" not in self.params["data"]:
+            _, condition = batch
+        else:
+            _, condition, _ = batch
+        if self.params["student"]["is_1d"] or self.params["student"]["y_condition"]:
+            # in 1-D the batch is passed as y_onehot only to size the prior (flows.py:372-376)
+            return self.student(reverse=True, y_onehot=condition, temperature=1)[-1]
+        return self.student(reverse=True, temperature=1)[-1]
+
+    # ---- pl_module.py:348-363
+    def configure_optimizers(self):
+        kw = dict(lr=self.params["learning_rate"], weight_decay=self.params["weight_decay"])
+        if self.params["optimizer"] == "adam":
+            return torch.optim.Adam(self.student.parameters(), **kw)
+        if self.params["optimizer"] == "adamax":
+            return torch.optim.Adamax(self.student.parameters(), **kw)
+        raise NameError("Unknown optimizer name")
+
+    # ---- pl_module.py:365-382
+    def training_step(self, batch, batch_idx=0):
+        losses = self.loss(self.forward(batch))
+        self.log("train_batch_nll", losses["nll"], on_step=True)
+        self.log("train_batch_kd", losses["kd"], on_step=True)
+        self.log("train_batch_perceptual", losses["perceptual"], on_step=True)
+        self.log("train_batch_loss", losses["result_loss"], on_step=True, prog_bar=True)
+        return {"nll": losses["nll"], "kd": losses["kd"], "perceptual": losses["perceptual"],
+                "loss": losses["result_loss"]}

@@ -14,6 +14,7 @@
 #include <cstdint>
 
 #include "../../include/nfk.h"
+#include "launch_util.h"
 #include "ptx.cuh"
 
 namespace nfk {
@@ -361,9 +362,7 @@ static int pick_bn(int N, int cap) {
 
 template <typename K>
 static int set_smem(K kernel, int bytes) {
-  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) == cudaSuccess
-             ? NFK_OK
-             : NFK_ERR_LAUNCH;
+  return ensure_dyn_smem(reinterpret_cast<const void*>(kernel), bytes);
 }
 
 }  // namespace nfk

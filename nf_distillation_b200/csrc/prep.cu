@@ -14,6 +14,7 @@
 #include <cstdint>
 
 #include "../../include/nfk.h"
+#include "launch_util.h"
 
 namespace nfk {
 
@@ -438,13 +439,7 @@ extern "C" int nfk_invconv_prep(const float* an_bias, const float* an_logs, cons
   if (!weight && (!lower || !upper || !log_s || !p || !sign_s)) return NFK_ERR_ARG;
   InvconvParams q{an_bias, an_logs, lower, upper, log_s, p, sign_s, weight};
   const int smem = prep_smem(C);
-  static int configured = 0;
-  if (smem > 48 * 1024 && configured < smem) {
-    if (cudaFuncSetAttribute(invconv_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) !=
-        cudaSuccess)
-      return NFK_ERR_LAUNCH;
-    configured = 200 * 1024;
-  }
+  if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(invconv_prep_kernel), smem)) return rc;
   invconv_prep_kernel<<<1, PREP_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(q, C, reverse, transpose, outW,
                                                                                   outb, out_sl);
   return cudaGetLastError() == cudaSuccess ? NFK_OK : NFK_ERR_LAUNCH;
@@ -461,13 +456,7 @@ extern "C" int nfk_invconv_prep_bwd(const float* an_bias, const float* an_logs, 
   if (weight ? !d_weight : (!d_lower || !d_upper || !d_log_s)) return NFK_ERR_ARG;
   InvconvParams q{an_bias, an_logs, lower, upper, log_s, p, sign_s, weight};
   const int smem = prep_smem(C);
-  static int configured = 0;
-  if (smem > 48 * 1024 && configured < smem) {
-    if (cudaFuncSetAttribute(invconv_prep_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) !=
-        cudaSuccess)
-      return NFK_ERR_LAUNCH;
-    configured = 200 * 1024;
-  }
+  if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(invconv_prep_bwd_kernel), smem)) return rc;
   invconv_prep_bwd_kernel<<<1, PREP_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(
       q, C, transpose, Wf, dWf, dbf, g_ld, B, pixels, d_bias, d_logs, d_lower, d_upper, d_log_s, d_weight);
   return cudaGetLastError() == cudaSuccess ? NFK_OK : NFK_ERR_LAUNCH;

@@ -5,6 +5,7 @@
 #include <cstdint>
 
 #include "../../include/nfk.h"
+#include "launch_util.h"
 
 namespace nfk {
 
@@ -305,10 +306,7 @@ extern "C" int nfk_split2d_fwd(const float* x, const float* w, const float* bias
   if (!x || !w || !bias || !logs || !z1_out) return NFK_ERR_ARG;
   SGeo g = make_sgeo(B, C, H, W, 256);
   const int smem = (C * (C / 2) * 9 + 2 * C + 3 * (C / 2) * (g.pixt + 1)) * 4;
-  if (smem > 227 * 1024) return NFK_ERR_SHAPE;
-  if (smem > 48 * 1024 &&
-      cudaFuncSetAttribute(split2d_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
-    return NFK_ERR_LAUNCH;
+  if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(split2d_fwd_kernel), smem)) return rc;
   split2d_fwd_kernel<<<(B + g.ipc - 1) / g.ipc, ST, smem, static_cast<cudaStream_t>(stream)>>>(
       x, w, bias, logs, z1_out, nullptr, 0.f, nullptr, ld, g, 0);
   return cudaGetLastError() == cudaSuccess ? NFK_OK : NFK_ERR_LAUNCH;
@@ -321,10 +319,7 @@ extern "C" int nfk_split2d_rev(const float* z1, const float* w, const float* bia
   if (!z1 || !w || !bias || !logs || !out) return NFK_ERR_ARG;
   SGeo g = make_sgeo(B, C, H, W, 256);
   const int smem = (C * (C / 2) * 9 + 2 * C + 3 * (C / 2) * (g.pixt + 1)) * 4;
-  if (smem > 227 * 1024) return NFK_ERR_SHAPE;
-  if (smem > 48 * 1024 &&
-      cudaFuncSetAttribute(split2d_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
-    return NFK_ERR_LAUNCH;
+  if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(split2d_fwd_kernel), smem)) return rc;
   split2d_fwd_kernel<<<(B + g.ipc - 1) / g.ipc, ST, smem, static_cast<cudaStream_t>(stream)>>>(
       z1, w, bias, logs, nullptr, eps, temperature, out, nullptr, g, 1);
   return cudaGetLastError() == cudaSuccess ? NFK_OK : NFK_ERR_LAUNCH;
@@ -337,10 +332,7 @@ extern "C" int nfk_split2d_bwd(const float* x, const float* w, const float* bias
   if (!x || !w || !bias || !logs || !g_ld || !dx || !dw || !dbias || !dlogs) return NFK_ERR_ARG;
   SGeo g = make_sgeo(B, C, H, W, 128);
   const int smem = (C * (C / 2) * 9 + 2 * C + (C / 2 + C) * (g.pixt + 1) + 2 * C) * 4;
-  if (smem > 227 * 1024) return NFK_ERR_SHAPE;
-  if (smem > 48 * 1024 &&
-      cudaFuncSetAttribute(split2d_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
-    return NFK_ERR_LAUNCH;
+  if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(split2d_bwd_kernel), smem)) return rc;
   split2d_bwd_kernel<<<(B + g.ipc - 1) / g.ipc, ST, smem, static_cast<cudaStream_t>(stream)>>>(
       x, w, bias, logs, g_z1, g_ld, dx, dw, dbias, dlogs, g);
   return cudaGetLastError() == cudaSuccess ? NFK_OK : NFK_ERR_LAUNCH;

@@ -12,6 +12,7 @@
 #include <cstdint>
 
 #include "../../include/nfk.h"
+#include "launch_util.h"
 
 namespace nfk {
 
@@ -419,11 +420,7 @@ static Geo make_geo(int B, int C, int H, int W, bool heavy) {
 
 template <typename K>
 static int ensure_smem(K kernel, int bytes) {
-  if (bytes <= 48 * 1024) return NFK_OK;
-  if (bytes > 227 * 1024) return NFK_ERR_SHAPE;
-  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) == cudaSuccess
-             ? NFK_OK
-             : NFK_ERR_LAUNCH;
+  return ensure_dyn_smem(reinterpret_cast<const void*>(kernel), bytes);
 }
 
 #define NFK_DISPATCH_C(C_, ...)                             \

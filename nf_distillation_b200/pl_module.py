@@ -120,9 +120,9 @@ class NFModel(nn.Module):
             perc = torch.where(torch.isnan(perc), torch.zeros_like(perc), perc)
         dev = out["student_nll"].device
         if kd is None:
-            kd = torch.tensor(0.0, device=dev)
+            kd = torch.zeros((), device=dev)   # (graph-capturable, unlike torch.tensor(0.0))
         if perc is None:
-            perc = torch.tensor(0.0, device=dev)
+            perc = torch.zeros((), device=dev)
         result = self.nll_weight * out["student_nll"] + self.kd_weight * kd + self.perceptual_weight * perc
         if out["weights"] is not None:
             result = result * out["weights"]

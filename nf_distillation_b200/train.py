@@ -1,0 +1,143 @@
+"""KD training driver: what Lightning's loop does around NFModel.training_step in the reference
+(train.py:41-58: seed, gradient_clip_val=30, optimiser step), one process per GPU.
+
+The whole step — student forward, teacher forward, multi-level KD loss, backward, gradient clipping and the
+optimiser update — is captured once into CUDA graphs and replayed; batches are sharded across ranks and the only
+collective is one NCCL all-reduce (average) of the flat student-gradient buffer between the two graphs.
+"""
+from __future__ import annotations
+
+import os
+import typing as tp
+
+import torch
+import torch.distributed as dist
+
+from .pl_module import NFModel
+
+GRAD_CLIP = 30.0  # train.py:46 gradient_clip_val
+
+
+def glow_cfg(image_shape, K, L, hidden, is_1d=False, y_classes=10):
+    return dict(image_shape=list(image_shape), hidden_channels=hidden, K=K, L=L, actnorm_scale=1.0,
+                flow_permutation="invconv", flow_coupling="affine", LU_decomposed=True, y_classes=y_classes,
+                learn_top=False, y_condition=False, is_1d=is_1d)
+
+
+def kd_config(student, teacher, data="cifar", nll=0.9, kd=0.1, perceptual=0.0, optimizer="adam", lr=5e-4):
+    """Same nesting as the reference's Hydra config (conf/config.yaml + conf/training/*.yaml)."""
+    return {"data": {"name": data}, "student": student, "teacher": teacher,
+            "loss": {"nll": {"weight": nll}, "kd": {"weight": kd, "name": "mse"},
+                     "perceptual": {"weight": perceptual, "name": "l1"}},
+            "optimizer": optimizer, "learning_rate": lr, "weight_decay": 0.0, "seed": 42}
+
+
+def randomise_zero_params(model: torch.nn.Module, seed: int, std: float = 0.05):
+    """Reference init leaves Conv2dZeros / ActNorm tensors at zero, which turns every coupling into a constant
+    (SURVEY §0.5); benchmarks and tests re-draw them N(0, std^2) so all kernels do real work."""
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for p in model.parameters():
+            if p.abs().max() == 0:
+                p.copy_((torch.randn(p.shape, generator=g) * std).to(p.device))
+
+
+class KDTrainer:
+    """Owns the NFModel, its optimiser, the static device buffers and the captured graphs."""
+
+    def __init__(self, config: dict, batch_shape: tp.Sequence[int], device: torch.device, use_graphs: bool = True,
+                 seed: int = 42):
+        self.device = device
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        torch.manual_seed(seed)                       # identical initial weights on every rank (train.py:41)
+        self.module = NFModel(config)
+        randomise_zero_params(self.module.student, seed + 1)
+        if self.module.teacher is not None:
+            randomise_zero_params(self.module.teacher, seed + 2)
+        self.module.to(device)
+        self.is_1d = config["student"]["is_1d"]
+        params = [p for p in self.module.student.parameters() if p.requires_grad]
+        self.params = params
+        # flat gradient buffer: p.grad are views, so the all-reduce is a single NCCL call with no packing copy
+        self.flat_grad = torch.zeros(sum(p.numel() for p in params), device=device)
+        off = 0
+        for p in params:
+            p.grad = self.flat_grad[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        kw = dict(lr=config["learning_rate"], weight_decay=config["weight_decay"], capturable=True)
+        opt = torch.optim.Adam if config["optimizer"] == "adam" else torch.optim.Adamax
+        try:
+            self.opt = opt(params, fused=True, **kw) if config["optimizer"] == "adam" else opt(params, **kw)
+        except TypeError:
+            self.opt = opt(params, **kw)
+        self.x = torch.zeros(*batch_shape, device=device)          # static input buffer
+        self.losses = torch.zeros(4, device=device)                 # nll, kd, perceptual, loss
+        self.use_graphs = use_graphs
+        self.g_fb: tp.Optional[torch.cuda.CUDAGraph] = None
+        self.g_opt: tp.Optional[torch.cuda.CUDAGraph] = None
+        torch.manual_seed(seed + 1000 + (dist.get_rank() if dist.is_initialized() else 0))  # per-rank noise stream
+
+    # ---- the two halves of a step
+    def _forward_backward(self):
+        self.flat_grad.zero_()
+        batch = [self.x] if self.is_1d else [self.x, None]
+        out = self.module.training_step(batch, 0)
+        out["loss"].backward()
+        self.losses.copy_(torch.stack([out["nll"], out["kd"], out["perceptual"], out["loss"]]).detach())
+
+    def _clip_and_update(self):
+        torch.nn.utils.clip_grad_norm_(self.params, GRAD_CLIP, foreach=True)
+        self.opt.step()
+
+    def _allreduce(self):
+        if self.world > 1:
+            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.AVG)
+
+    def warmup(self, iters: int = 3):
+        """Eager steps on a side stream (builds kernels' attributes, optimiser state), then graph capture."""
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(iters):
+                self._forward_backward()
+                self._allreduce()
+                self._clip_and_update()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        if not self.use_graphs:
+            return
+        self.g_fb = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.g_fb):
+            self._forward_backward()
+        self.g_opt = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.g_opt, pool=self.g_fb.pool()):
+            self._clip_and_update()
+        torch.cuda.synchronize()
+
+    def step_device(self):
+        """One training step on whatever self.x currently holds (inputs already resident in HBM)."""
+        if self.g_fb is not None:
+            self.g_fb.replay()
+            self._allreduce()
+            self.g_opt.replay()
+        else:
+            self._forward_backward()
+            self._allreduce()
+            self._clip_and_update()
+
+    def step(self, host_batch: torch.Tensor) -> torch.Tensor:
+        """Public end-to-end step: pinned host batch -> device, train, loss scalars back on the host."""
+        self.x.copy_(host_batch, non_blocking=True)
+        self.step_device()
+        return self.losses.cpu()
+
+
+def init_distributed() -> tp.Tuple[int, int, torch.device]:
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return rank, world, torch.device("cuda", local)

@@ -1,0 +1,103 @@
+"""CPU: the C-ABI library loads and exports every symbol include/nfk.h declares; host-side logic that needs no GPU."""
+import ctypes
+import os
+import re
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "nfk.h")).read()
+    return sorted(set(re.findall(r"\bint\s+(nfk_\w+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from nf_distillation_b200 import _lib
+    syms = declared_symbols()
+    assert len(syms) >= 15
+    for s in syms:
+        assert hasattr(_lib.LIB, s), f"{s} declared in include/nfk.h but not exported by libnfk.so"
+    assert set(_lib.SIGNATURES) == set(syms), "ctypes signatures and header diverge"
+    assert _lib.LIB.nfk_version() >= 1
+
+
+def test_argument_errors_without_gpu():
+    """Shape / argument validation happens before any CUDA call, so it is testable on the CPU."""
+    from nf_distillation_b200 import _lib
+    L = _lib.LIB
+    assert L.nfk_gemm_nt_bf16(None, 64, None, 64, 128, 100, 64, 0, None, 64, None, None, 0, None, None) == -1
+    assert L.nfk_gemm_nt_bf16(None, 64, None, 64, 128, 64, 60, 0, None, 64, None, None, 0, None, None) == -1
+    assert L.nfk_invconv_prep(None, None, None, None, None, None, None, None, 12, 0, 0, None, None, None, None) == -3
+    assert L.nfk_affine1x1_fwd(None, None, None, None, None, None, 0, None, None, 0, 12, 4, 4, None) == -1
+    assert L.nfk_kd_mse_fwd(None, None, 4, 16, 1.0, None, None) == -3
+
+
+def test_state_dict_keys_and_module_tree():
+    from nf_distillation_b200.models import FlowStep, SqueezeLayer, create_glow_model
+    cfg = dict(image_shape=[32, 32, 3], hidden_channels=64, K=2, L=3, actnorm_scale=1.0,
+               flow_permutation="invconv", flow_coupling="affine", LU_decomposed=True, y_classes=10,
+               learn_top=False, y_condition=False, is_1d=False)
+    m = create_glow_model(cfg)
+    sd = m.state_dict()
+    for k in ("prior_h", "flow.layers.1.actnorm.bias", "flow.layers.1.invconv.lower", "flow.layers.1.invconv.p",
+              "flow.layers.1.invconv.sign_s", "flow.layers.1.block.0.conv.weight",
+              "flow.layers.1.block.0.actnorm.logs", "flow.layers.1.block.4.logs", "flow.layers.1.block.4.conv.bias",
+              "flow.layers.3.conv.logs", "flow.layers.3.conv.conv.weight"):
+        assert k in sd, k
+    assert isinstance(m.flow.layers[0], SqueezeLayer) and isinstance(m.flow.layers[1], FlowStep)
+    assert len(m.flow.layers) == 3 * (2 + 1) + 2
+    assert m.flow.output_shapes[0] == [-1, 12, 16, 16] and m.flow.output_shapes[-1] == [-1, 48, 4, 4]
+    assert all(mod.inited for mod in m.modules() if hasattr(mod, "inited"))
+    mean, logs = m.prior(None)
+    assert mean.shape == (32, 48, 4, 4) and logs.shape == (32, 48, 4, 4)
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(2, 3, 32, 32), None)      # no CPU path: must fail loudly
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/models"), reason="reference tree not present")
+def test_seeded_init_matches_reference_bit_for_bit():
+    import warnings
+    warnings.filterwarnings("ignore")
+    from nf_distillation_b200.models import create_glow_model
+    for cfg in (dict(image_shape=[16, 16, 3], hidden_channels=64, K=2, L=2, is_1d=False, y_classes=10),
+                dict(image_shape=[63], hidden_channels=32, K=3, L=1, is_1d=True, y_classes=0)):
+        cfg.update(actnorm_scale=1.0, flow_permutation="invconv", flow_coupling="affine", LU_decomposed=True,
+                   learn_top=False, y_condition=False)
+        torch.manual_seed(42)
+        mine = create_glow_model(dict(cfg)).state_dict()
+        code = ("import sys, torch, warnings; warnings.filterwarnings('ignore'); sys.path.insert(0, '/root/reference');"
+                "from models import create_glow_model; torch.manual_seed(42);"
+                f"sd = create_glow_model({cfg!r}).state_dict(); torch.save(sd, sys.argv[1])")
+        import subprocess, tempfile
+        with tempfile.NamedTemporaryFile(suffix=".pt") as f:
+            subprocess.run([sys.executable, "-c", code, f.name], check=True, capture_output=True)
+            ref = torch.load(f.name)
+        assert set(ref) == set(mine)
+        assert all(torch.equal(ref[k], mine[k]) for k in ref)
+
+
+def test_kd_indices_match_reference_rule():
+    sys.path.insert(0, ROOT)
+    from oracle import glow_oracle as O
+    from nf_distillation_b200.pl_module import NFModel
+    base = dict(actnorm_scale=1.0, flow_permutation="invconv", flow_coupling="affine", LU_decomposed=True,
+                learn_top=False, y_condition=False)
+    s = dict(base, image_shape=[32, 32, 3], hidden_channels=64, K=8, L=3, is_1d=False, y_classes=10)
+    tch = dict(s, K=32)
+    cfg = {"data": {"name": "cifar"}, "student": s, "teacher": tch,
+           "loss": {"nll": {"weight": 0.9}, "kd": {"weight": 0.1, "name": "mse"},
+                    "perceptual": {"weight": 0.0, "name": "l1"}},
+           "optimizer": "adam", "learning_rate": 5e-4, "weight_decay": 0.0}
+    m = NFModel(cfg)
+    assert (m.student_kd_indices, m.teacher_kd_indices) == ([0, 10, 20, 28], [0, 34, 68, 100])   # SURVEY §3.2 probe
+    assert (m.student_kd_indices, m.teacher_kd_indices) == O.kd_indices(s, tch)
+    s1 = dict(base, image_shape=[63], hidden_channels=16, K=3, L=1, is_1d=True, y_classes=0)
+    t1 = dict(s1, hidden_channels=32, K=5)
+    cfg1 = dict(cfg, data={"name": "bsds300"}, student=s1, teacher=t1)
+    m1 = NFModel(cfg1)
+    assert (m1.student_kd_indices, m1.teacher_kd_indices) == ([1, 2], [3, 4])
+    assert isinstance(m.configure_optimizers(), torch.optim.Adam)

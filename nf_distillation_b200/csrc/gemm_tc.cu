@@ -50,6 +50,81 @@ __device__ __forceinline__ uint32_t tmem_cols_pow2(int n) {
 }
 
 // ------------------------------------------------------------------------------------------------ NT kernel
+// Persistent: grid = min(tiles, SMs); every CTA walks tiles t = blockIdx.x, +gridDim.x, ... (n-tile fastest, so CTAs
+// running side by side share the A row block through L2). Two TMEM accumulator stages let the epilogue of tile i
+// overlap the MMAs of tile i+1.
+template <int EPI>
+__device__ __forceinline__ void nt_epilogue_16(const GemmArgs& g, const uint32_t (&r)[16], long long row, bool row_ok,
+                                               int col, int cl, const float* bias_s, int lane) {
+  if constexpr (EPI == NFK_EPI_F32) {
+    if (row_ok) {
+      float* o = static_cast<float*>(g.out) + row * g.ldo + col;
+#pragma unroll
+      for (int j = 0; j < 16; j += 4) {
+        float4 v;
+        v.x = __uint_as_float(r[j + 0]); v.y = __uint_as_float(r[j + 1]);
+        v.z = __uint_as_float(r[j + 2]); v.w = __uint_as_float(r[j + 3]);
+        if (g.bias) {
+          const float4 b = *reinterpret_cast<const float4*>(bias_s + cl + j);
+          v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+        }
+        *reinterpret_cast<float4*>(o + j) = v;
+      }
+    }
+  } else if constexpr (EPI == NFK_EPI_BIAS_RELU_BF16) {
+    uint32_t p[8];
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) {
+      const float4 b = *reinterpret_cast<const float4*>(bias_s + cl + j);
+      p[(j >> 1)] = pack_bf16x2(fmaxf(__uint_as_float(r[j]) + b.x, 0.f), fmaxf(__uint_as_float(r[j + 1]) + b.y, 0.f));
+      p[(j >> 1) + 1] =
+          pack_bf16x2(fmaxf(__uint_as_float(r[j + 2]) + b.z, 0.f), fmaxf(__uint_as_float(r[j + 3]) + b.w, 0.f));
+    }
+    if (row_ok) {
+      uint4* o = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(g.out) + row * g.ldo + col);
+      o[0] = make_uint4(p[0], p[1], p[2], p[3]);
+      o[1] = make_uint4(p[4], p[5], p[6], p[7]);
+    }
+  } else {  // NFK_EPI_MASK_BF16: ReLU backward mask + bias-gradient column sums
+    float v[16];
+    uint4 m0 = make_uint4(0, 0, 0, 0), m1 = m0;
+    if (row_ok) {
+      const uint4* a = reinterpret_cast<const uint4*>(g.aux + row * g.ldaux + col);
+      m0 = __ldg(a);
+      m1 = __ldg(a + 1);
+    }
+    const uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      // post-ReLU activations are >= 0, so "active" <=> the bf16 bit pattern is non-zero (and not -0).
+      const uint32_t h = (j & 1) ? (mw[j >> 1] >> 16) : (mw[j >> 1] & 0xFFFFu);
+      const bool on = row_ok && h != 0u && h != 0x8000u;
+      v[j] = on ? __uint_as_float(r[j]) : 0.f;
+    }
+    if (row_ok) {
+      uint4* o = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(g.out) + row * g.ldo + col);
+      o[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+      o[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+    }
+    if (g.colsum) {
+      // 32 lanes x 16 columns -> lane j (< 16) ends with the sum of column j over the warp's 32 rows.
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] += __shfl_xor_sync(0xffffffffu, v[j], 16);
+#pragma unroll
+      for (int off = 8; off >= 1; off >>= 1) {
+        const bool up = (lane & off) != 0;
+#pragma unroll
+        for (int j = 0; j < off; ++j) {
+          const float send = up ? v[j] : v[j + off];
+          const float keep = up ? v[j + off] : v[j];
+          v[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+      }
+      if (lane < 16) atomicAdd(g.colsum + col + lane, v[0]);
+    }
+  }
+}
+
 template <int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
@@ -61,13 +136,15 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int stage_bytes = a_bytes + b_bytes;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + g.stages * stage_bytes);
   uint64_t* empty = full + g.stages;
-  uint64_t* tmem_full = empty + g.stages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  uint64_t* tmem_full = empty + g.stages;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;     // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* bias_s = reinterpret_cast<float*>(tmem_slot + 4);  // [2][256] (one per accumulator stage)
 
-  const int n_tile = blockIdx.x % g.n_tiles;
-  const int m_tile = blockIdx.x / g.n_tiles;
   const int num_kb = g.K / BK;
-  const uint32_t ncols = tmem_cols_pow2(g.BN);
+  const int m_tiles = (g.M + BM - 1) / BM;
+  const int num_tiles = m_tiles * g.n_tiles;
+  const uint32_t ncols = tmem_cols_pow2(2 * g.BN);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -76,7 +153,10 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
-    mbar_init(tmem_full, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 4);  // one arrival per epilogue warp
+    }
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -92,13 +172,16 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(&empty[s], ph ^ 1);
-        uint8_t* sa = smem + s * stage_bytes;
-        mbar_expect_tx(&full[s], stage_bytes);
-        tma_load_2d(sa, &tmA, &full[s], kb * BK, m_tile * BM);
-        tma_load_2d(sa + a_bytes, &tmB, &full[s], kb * BK, n_tile * g.BN);
-        if (++s == g.stages) { s = 0; ph ^= 1; }
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int n_tile = t % g.n_tiles, m_tile = t / g.n_tiles;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty[s], ph ^ 1);
+          uint8_t* sa = smem + s * stage_bytes;
+          mbar_expect_tx(&full[s], stage_bytes);
+          tma_load_2d(sa, &tmA, &full[s], kb * BK, m_tile * BM);
+          tma_load_2d(sa + a_bytes, &tmB, &full[s], kb * BK, n_tile * g.BN);
+          if (++s == g.stages) { s = 0; ph ^= 1; }
+        }
       }
     }
   } else if (warp == 1) {
@@ -106,97 +189,65 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t idesc = umma_idesc_bf16(BM, g.BN, false, false);
       int s = 0;
       uint32_t ph = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(&full[s], ph);
+      int it = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_ph = (it >> 1) & 1;
+        mbar_wait(&tmem_empty[acc], acc_ph ^ 1);  // epilogue has drained this accumulator stage
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
-        const uint32_t b_addr = a_addr + a_bytes;
+        const uint32_t tmem_d = tmem_base + acc * g.BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
+          const uint32_t b_addr = a_addr + a_bytes;
 #pragma unroll
-        for (int k = 0; k < BK / UMMA_K; ++k) {
-          const uint64_t ad = umma_desc_sw128(a_addr + k * (UMMA_K * 2), 16, 1024);
-          const uint64_t bd = umma_desc_sw128(b_addr + k * (UMMA_K * 2), 16, 1024);
-          umma_f16(tmem_base, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t ad = umma_desc_sw128(a_addr + k * (UMMA_K * 2), 16, 1024);
+            const uint64_t bd = umma_desc_sw128(b_addr + k * (UMMA_K * 2), 16, 1024);
+            umma_f16(tmem_d, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty[s]);  // frees the smem stage when these MMAs retire
+          if (++s == g.stages) { s = 0; ph ^= 1; }
         }
-        umma_commit(&empty[s]);  // frees the smem stage when these MMAs retire
-        if (++s == g.stages) { s = 0; ph ^= 1; }
+        umma_commit(&tmem_full[acc]);
       }
-      umma_commit(tmem_full);
     }
   } else {
-    mbar_wait(tmem_full, 0);
-    tc_fence_after();
     const int q = warp & 3;  // TMEM lane quadrant this warp may read
-    const long long row = static_cast<long long>(m_tile) * BM + q * 32 + lane;
-    const bool row_ok = row < g.M;
-    for (int c = 0; c < g.BN; c += 16) {
-      uint32_t r[16];
-      tmem_ld16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c, r);
-      tmem_ld_wait();
-      const int col = n_tile * g.BN + c;
-      if (col >= g.N) break;  // warp-uniform
-      if constexpr (EPI == NFK_EPI_F32) {
-        float* o = static_cast<float*>(g.out) + row * g.ldo + col;
-        if (row_ok) {
-#pragma unroll
-          for (int j = 0; j < 16; j += 4) {
-            float4 v;
-            v.x = __uint_as_float(r[j + 0]); v.y = __uint_as_float(r[j + 1]);
-            v.z = __uint_as_float(r[j + 2]); v.w = __uint_as_float(r[j + 3]);
-            if (g.bias) { v.x += g.bias[col + j]; v.y += g.bias[col + j + 1]; v.z += g.bias[col + j + 2]; v.w += g.bias[col + j + 3]; }
-            *reinterpret_cast<float4*>(o + j) = v;
-          }
+    const int et = threadIdx.x - 64;  // 0..127
+    int it = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      const int n_tile = t % g.n_tiles, m_tile = t / g.n_tiles;
+      const int acc = it & 1;
+      const uint32_t acc_ph = (it >> 1) & 1;
+      float* bs = bias_s + acc * 256;
+      if (EPI != NFK_EPI_MASK_BF16 && g.bias) {
+        // stage this tile's bias slice; the named barrier also orders it against the previous use of this stage
+        for (int c = et; c < g.BN; c += 128) {
+          const int col = n_tile * g.BN + c;
+          bs[c] = col < g.N ? __ldg(g.bias + col) : 0.f;
         }
-      } else if constexpr (EPI == NFK_EPI_BIAS_RELU_BF16) {
-        uint32_t p[8];
-#pragma unroll
-        for (int j = 0; j < 16; j += 2) {
-          const float a = fmaxf(__uint_as_float(r[j]) + __ldg(g.bias + col + j), 0.f);
-          const float b = fmaxf(__uint_as_float(r[j + 1]) + __ldg(g.bias + col + j + 1), 0.f);
-          p[j >> 1] = pack_bf16x2(a, b);
-        }
-        if (row_ok) {
-          uint4* o = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(g.out) + row * g.ldo + col);
-          o[0] = make_uint4(p[0], p[1], p[2], p[3]);
-          o[1] = make_uint4(p[4], p[5], p[6], p[7]);
-        }
-      } else {  // NFK_EPI_MASK_BF16: ReLU backward mask + bias-gradient column sums
-        float v[16];
-        uint4 m0 = make_uint4(0, 0, 0, 0), m1 = m0;
-        if (row_ok) {
-          const uint4* a = reinterpret_cast<const uint4*>(g.aux + row * g.ldaux + col);
-          m0 = __ldg(a);
-          m1 = __ldg(a + 1);
-        }
-        const uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          // post-ReLU activations are >= 0, so "active" <=> the bf16 bit pattern is non-zero (and not -0).
-          const uint32_t h = (j & 1) ? (mw[j >> 1] >> 16) : (mw[j >> 1] & 0xFFFFu);
-          const bool on = row_ok && h != 0u && h != 0x8000u;
-          v[j] = on ? __uint_as_float(r[j]) : 0.f;
-        }
-        if (row_ok) {
-          uint4* o = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(g.out) + row * g.ldo + col);
-          o[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-          o[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
-        }
-        if (g.colsum) {
-          // 32 lanes x 16 columns -> lane j (< 16) ends with the sum of column j over the warp's 32 rows.
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] += __shfl_xor_sync(0xffffffffu, v[j], 16);
-#pragma unroll
-          for (int off = 8; off >= 1; off >>= 1) {
-            const bool up = (lane & off) != 0;
-#pragma unroll
-            for (int j = 0; j < off; ++j) {
-              const float send = up ? v[j] : v[j + off];
-              const float keep = up ? v[j + off] : v[j];
-              v[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-            }
-          }
-          if (lane < 16) atomicAdd(g.colsum + col + lane, v[0]);
-        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
       }
+      mbar_wait(&tmem_full[acc], acc_ph);
+      tc_fence_after();
+      const long long row = static_cast<long long>(m_tile) * BM + q * 32 + lane;
+      const bool row_ok = row < g.M;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * g.BN;
+      for (int c = 0; c < g.BN; c += 32) {
+        uint32_t r0[16], r1[16];
+        const bool two = c + 16 < g.BN;
+        tmem_ld16(taddr + c, r0);
+        if (two) tmem_ld16(taddr + c + 16, r1);
+        tmem_ld_wait();
+        const int col = n_tile * g.BN + c;
+        if (col < g.N) nt_epilogue_16<EPI>(g, r0, row, row_ok, col, c, bs, lane);
+        if (two && col + 16 < g.N) nt_epilogue_16<EPI>(g, r1, row, row_ok, col + 16, c + 16, bs, lane);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
     }
   }
   tc_fence_before();
@@ -347,6 +398,16 @@ static int make_tmap_bf16(CUtensorMap* m, const void* ptr, uint64_t cols, uint64
   return r == CUDA_SUCCESS ? NFK_OK : NFK_ERR_DRIVER;
 }
 
+static int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
 static int pick_bn(int N, int cap) {
   // Widest tile (multiple of 16, <= cap) that wastes the fewest padded columns.
   const int n16 = (N + 15) / 16 * 16;
@@ -379,17 +440,21 @@ extern "C" int nfk_gemm_nt_bf16(const void* A, long long lda, const void* B, lon
   GemmArgs g{};
   g.M = M; g.N = N; g.K = K;
   g.BN = pick_bn(N, 256);
+  // few row tiles (small images x small batch): narrower accumulator tiles so the grid still covers the SMs
+  const int m_tiles = (M + BM - 1) / BM;
+  while (m_tiles * ((N + g.BN - 1) / g.BN) < 148 && g.BN >= 128 && g.BN % 32 == 0) g.BN /= 2;
   g.n_tiles = (N + g.BN - 1) / g.BN;
   const int stage_bytes = BM * 128 + g.BN * 128;
-  g.stages = min(8, (196 * 1024) / stage_bytes);
+  g.stages = min(8, (194 * 1024) / stage_bytes);
   g.out = out; g.ldo = ldo; g.bias = bias;
   g.aux = static_cast<const __nv_bfloat16*>(aux); g.ldaux = ldaux; g.colsum = colsum;
   CUtensorMap tmA, tmB;
   int rc;
   if ((rc = make_tmap_bf16(&tmA, A, K, M, lda, BM)) != NFK_OK) return rc;
   if ((rc = make_tmap_bf16(&tmB, B, K, N, ldb, g.BN)) != NFK_OK) return rc;
-  const int smem = g.stages * stage_bytes + 1024 + 256;
-  const dim3 grid(((M + BM - 1) / BM) * g.n_tiles);
+  const int smem = g.stages * stage_bytes + 1024 + 256 + 2 * 256 * 4;
+  const int tiles = m_tiles * g.n_tiles;
+  const dim3 grid(tiles < num_sms() ? tiles : num_sms());
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (epi) {
     case NFK_EPI_F32:

@@ -292,6 +292,7 @@ static SGeo make_sgeo(int B, int C, int H, int W, int target) {
   g.B = B; g.C = C; g.H = H; g.W = W; g.HW = H * W;
   g.ipc = g.HW >= target ? 1 : target / g.HW;
   if (g.ipc > B) g.ipc = B;
+  while (g.ipc > 1 && (B + g.ipc - 1) / g.ipc < 2 * 148) g.ipc >>= 1;
   g.pixt = g.ipc * g.HW;
   return g;
 }

@@ -414,6 +414,8 @@ static Geo make_geo(int B, int C, int H, int W, bool heavy) {
   int target = heavy ? (C <= 24 ? 256 : (C <= 48 ? 128 : 64)) : 256;
   g.ipc = g.HW >= target ? 1 : target / g.HW;
   if (g.ipc > B) g.ipc = B;
+  // small images: prefer >= 2 CTAs per SM over fat CTAs (these kernels are latency-bound when the grid is small)
+  while (g.ipc > 1 && (B + g.ipc - 1) / g.ipc < 2 * 148) g.ipc >>= 1;
   g.pixt = g.ipc * g.HW;
   return g;
 }

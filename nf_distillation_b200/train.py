@@ -58,12 +58,9 @@ class KDTrainer:
         self.is_1d = config["student"]["is_1d"]
         params = [p for p in self.module.student.parameters() if p.requires_grad]
         self.params = params
-        # flat gradient buffer: p.grad are views, so the all-reduce is a single NCCL call with no packing copy
-        self.flat_grad = torch.zeros(sum(p.numel() for p in params), device=device)
-        off = 0
-        for p in params:
-            p.grad = self.flat_grad[off:off + p.numel()].view_as(p)
-            off += p.numel()
+        # flat buffer for the gradient all-reduce (one NCCL call); grads themselves are produced fresh by backward
+        # (p.grad = None before it), so autograd steals them instead of launching one "+=" kernel per parameter
+        self.flat_grad = torch.zeros(sum(p.numel() for p in params), device=device) if self.world > 1 else None
         kw = dict(lr=config["learning_rate"], weight_decay=config["weight_decay"], capturable=True)
         opt = torch.optim.Adam if config["optimizer"] == "adam" else torch.optim.Adamax
         try:
@@ -79,7 +76,8 @@ class KDTrainer:
 
     # ---- the two halves of a step
     def _forward_backward(self):
-        self.flat_grad.zero_()
+        for p in self.params:
+            p.grad = None
         batch = [self.x] if self.is_1d else [self.x, None]
         out = self.module.training_step(batch, 0)
         out["loss"].backward()
@@ -91,7 +89,14 @@ class KDTrainer:
 
     def _allreduce(self):
         if self.world > 1:
+            grads = [p.grad for p in self.params]
+            views, off = [], 0
+            for g in grads:
+                views.append(self.flat_grad[off:off + g.numel()].view_as(g))
+                off += g.numel()
+            torch._foreach_copy_(views, grads)
             dist.all_reduce(self.flat_grad, op=dist.ReduceOp.AVG)
+            torch._foreach_copy_(grads, views)
 
     def warmup(self, iters: int = 3):
         """Eager steps on a side stream (builds kernels' attributes, optimiser state), then graph capture."""

@@ -60,11 +60,13 @@ int nfk_invconv_prep(const float* an_bias, const float* an_logs, const float* lo
                      const float* log_s, const float* p, const float* sign_s, const float* weight, int C, int reverse,
                      int transpose, float* outW, float* outb, float* out_sl, void* stream);
 
-/* Chain rule of the forward-direction prep: (dWf, dbf, g_ld[B]) -> gradients of actnorm.{bias,logs} and
- * invconv.{lower,upper,log_s} (or invconv.weight). `pixels` = H*W (1 in 1-D). Outputs are overwritten. */
+/* Chain rule of the prep in either direction: (dWf, dbf, g_ld[B] or NULL) -> gradients of actnorm.{bias,logs}
+ * and invconv.{lower,upper,log_s} (or invconv.weight); the inverse direction goes through
+ * dW = -W^-T dW^-1 W^-T. `pixels` = H*W (1 in 1-D). Outputs are overwritten. */
 int nfk_invconv_prep_bwd(const float* an_bias, const float* an_logs, const float* lower, const float* upper,
                          const float* log_s, const float* p, const float* sign_s, const float* weight, int C,
-                         int transpose, const float* Wf, const float* dWf, const float* dbf, const float* g_ld, int B,
+                         int reverse, int transpose, const float* Wf, const float* dWf, const float* dbf,
+                         const float* g_ld, int B,
                          float pixels, float* d_bias, float* d_logs, float* d_lower, float* d_upper, float* d_log_s,
                          float* d_weight, void* stream);
 
@@ -117,6 +119,28 @@ int nfk_prior_bpd_bwd(const float* z, const float* mean, const float* logs, cons
 int nfk_kd_mse_fwd(const float* s, const float* t, int B, int n, float scale, float* acc, void* stream);
 int nfk_kd_mse_bwd(const float* s, const float* t, const float* g, int B, int n, float scale, float* ds,
                    int accumulate, void* stream);
+
+/* ---- 1-D (tabular) FlowStep, fused (is_1d branches of models/flows.py:37-52,142-202, models/layers.py:410-411) --
+ * Weights are packed once per optimiser step by nfk_flow1d_pack from the fused affine (nfk_invconv_prep with
+ * transpose=1, forward or inverse direction) and the six nn.Linear layers of get_block_1d:
+ *   PF: per layer WT [nin][nout8] + bias [nout8] (forward), PB: per layer W [nout][nin8] (backward).
+ * nfk_flow1d_sizes reports the block sizes and the per-layer offsets of the gradient block G
+ * (dW_l [nout][nin8] at offG, db_l at offGB). x / y / dx are [B, D] row-major, cond is [B, Cc] (y_onehot). */
+int nfk_flow1d_sizes(int D, int Cc, int hid, int* total_fwd, int* total_bwd, int* total_grad, int* n_act,
+                     int* offsets);
+int nfk_flow1d_pack(const float* Wf, const float* bf, const float* const* w, const float* const* b, int D, int Cc,
+                    int hid, float* PF, float* PB, void* stream);
+/* reverse=0: y = coupling(affine(x)), ld_out = ld_in + sl + sum log s;  reverse=1: y = affine_inv(coupling^-1(x)),
+ * ld_out = ld_in + sl - sum log s (PF / sl built with reverse=1). acts (optional, [B, 5*hid + 2*D2]) keeps the MLP
+ * activations for nfk_flow1d_bwd. */
+int nfk_flow1d_fwd(const float* x, const float* cond, const float* PF, const float* sl, float* y, const float* ld_in,
+                   float* ld_out, float* acts, int B, int D, int Cc, int hid, int reverse, void* stream);
+int nfk_flow1d_bwd(const float* x_in, const float* cond, const float* acts, const float* PB, const float* PF,
+                   const float* g_out, const float* g_ld, float* dx, float* G, int B, int D, int Cc, int hid,
+                   int reverse, void* stream);
+/* y = W x + b on [B, D] rows (stand-alone ActNorm1d / InvertibleConv1x1, models/layers.py:129-142,404-421). */
+int nfk_affine_rows(const float* x, const float* Wf, const float* bf, const float* sl, float* y, const float* ld_in,
+                    float* ld_out, int B, int D, float pixels, void* stream);
 
 #ifdef __cplusplus
 }

@@ -24,7 +24,7 @@ SIGNATURES: dict[str, list] = {
     "nfk_gemm_nt_bf16": [_vp, _ll, _vp, _ll, _i, _i, _i, _i, _vp, _ll, _vp, _vp, _ll, _vp, _vp],
     "nfk_gemm_tn_bf16": [_vp, _ll, _vp, _ll, _i, _i, _i, _vp, _ll, _i, _vp],
     "nfk_invconv_prep": [_vp] * 8 + [_i, _i, _i, _vp, _vp, _vp, _vp],
-    "nfk_invconv_prep_bwd": [_vp] * 8 + [_i, _i, _vp, _vp, _vp, _vp, _i, _f] + [_vp] * 6 + [_vp],
+    "nfk_invconv_prep_bwd": [_vp] * 8 + [_i, _i, _i, _vp, _vp, _vp, _vp, _i, _f] + [_vp] * 6 + [_vp],
     "nfk_coupling_prep": [_vp] * 9 + [_i] * 5 + [_vp] * 9 + [_i, _vp],
     "nfk_coupling_prep_bwd": [_vp] * 9 + [_i] * 5 + [_vp] * 6 + [_vp] * 9 + [_vp],
     "nfk_affine1x1_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _vp],
@@ -38,6 +38,11 @@ SIGNATURES: dict[str, list] = {
     "nfk_prior_bpd_bwd": [_vp] * 4 + [_i, _i, _f, _vp, _vp, _vp],
     "nfk_kd_mse_fwd": [_vp, _vp, _i, _i, _f, _vp, _vp],
     "nfk_kd_mse_bwd": [_vp, _vp, _vp, _i, _i, _f, _vp, _i, _vp],
+    "nfk_flow1d_sizes": [_i, _i, _i, _vp, _vp, _vp, _vp, _vp],
+    "nfk_flow1d_pack": [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp],
+    "nfk_flow1d_fwd": [_vp] * 8 + [_i] * 5 + [_vp],
+    "nfk_flow1d_bwd": [_vp] * 9 + [_i] * 5 + [_vp],
+    "nfk_affine_rows": [_vp] * 7 + [_i, _i, _f, _vp],
 }
 
 

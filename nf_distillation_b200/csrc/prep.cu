@@ -213,9 +213,9 @@ invconv_prep_kernel(InvconvParams q, int C, int reverse, int transpose, float* _
   if (tid == 0) out_sl[0] = reverse ? -lsum : lsum;
 }
 
-// Backward of the forward-direction prep. Wf is the saved outW. All gradient outputs are overwritten.
+// Backward of the prep (either direction). Wf is the saved outW of the same direction. Outputs are overwritten.
 __global__ void __launch_bounds__(PREP_THREADS)
-invconv_prep_bwd_kernel(InvconvParams q, int C, int transpose, const float* __restrict__ Wf,
+invconv_prep_bwd_kernel(InvconvParams q, int C, int reverse, int transpose, const float* __restrict__ Wf,
                         const float* __restrict__ dWf, const float* __restrict__ dbf,
                         const float* __restrict__ g_ld, int B, float pixels, float* __restrict__ d_bias,
                         float* __restrict__ d_logs, float* __restrict__ d_lower, float* __restrict__ d_upper,
@@ -232,29 +232,68 @@ invconv_prep_bwd_kernel(InvconvParams q, int C, int transpose, const float* __re
   const int CC = C * C;
 
   float gs = 0.f;
-  for (int b = tid; b < B; b += blockDim.x) gs += g_ld[b];
-  const float gsum = block_sum(gs, red) * pixels;
+  if (g_ld)
+    for (int b = tid; b < B; b += blockDim.x) gs += g_ld[b];
+  float gsum = block_sum(gs, red) * pixels;
 
-  for (int i = tid; i < CC; i += blockDim.x) {
-    const int a = i / C, b = i % C;
-    G[i] = dWf[i] + dbf[a] * q.an_bias[b];
-  }
-  __syncthreads();
-  for (int b = tid; b < C; b += blockDim.x) {
-    float db = 0.f, dl = 0.f;
-    for (int a = 0; a < C; ++a) {
-      db = fmaf(Wf[a * C + b], dbf[a], db);
-      dl = fmaf(G[a * C + b], Wf[a * C + b], dl);
+  if (!reverse) {
+    // Wf[a][b] = W*[a][b] e^{logs_b}, bf = Wf bias
+    for (int i = tid; i < CC; i += blockDim.x) {
+      const int a = i / C, b = i % C;
+      G[i] = dWf[i] + dbf[a] * q.an_bias[b];
     }
-    d_bias[b] = db;
-    d_logs[b] = dl + gsum;
+    __syncthreads();
+    for (int b = tid; b < C; b += blockDim.x) {
+      float db = 0.f, dl = 0.f;
+      for (int a = 0; a < C; ++a) {
+        db = fmaf(Wf[a * C + b], dbf[a], db);
+        dl = fmaf(G[a * C + b], Wf[a * C + b], dl);
+      }
+      d_bias[b] = db;
+      d_logs[b] = dl + gsum;
+    }
+    for (int i = tid; i < CC; i += blockDim.x) {
+      const int r = i / C, c = i % C;
+      dW[i] = transpose ? G[c * C + r] * expf(q.an_logs[r]) : G[i] * expf(q.an_logs[c]);
+    }
+    __syncthreads();
+  } else {
+    // Wf[a][b] = Winv*[a][b] e^{-logs_a}, bf = -bias, log-det enters with a minus sign
+    gsum = -gsum;
+    for (int a = tid; a < C; a += blockDim.x) {
+      float dl = 0.f;
+      for (int b = 0; b < C; ++b) dl = fmaf(dWf[a * C + b], Wf[a * C + b], dl);
+      d_bias[a] = -dbf[a];
+      d_logs[a] = -dl + gsum;
+    }
+    float* Winv = G;      // plain layout
+    float* dWinv = dW;    // plain layout
+    for (int i = tid; i < CC; i += blockDim.x) {
+      const int a = i / C, b = i % C;
+      const float e = expf(q.an_logs[a]);
+      const int pi = transpose ? b * C + a : i;
+      Winv[pi] = Wf[i] * e;
+      dWinv[pi] = dWf[i] / e;
+    }
+    __syncthreads();
+    // Lm <- dWinv Winv^T ; Um <- -Winv^T Lm  (= dL/dW)
+    for (int i = tid; i < CC; i += blockDim.x) {
+      const int r = i / C, c = i % C;
+      float t = 0.f;
+      for (int k = 0; k < C; ++k) t = fmaf(dWinv[r * C + k], Winv[c * C + k], t);
+      Lm[i] = t;
+    }
+    __syncthreads();
+    for (int i = tid; i < CC; i += blockDim.x) {
+      const int r = i / C, c = i % C;
+      float t = 0.f;
+      for (int k = 0; k < C; ++k) t = fmaf(Winv[k * C + r], Lm[k * C + c], t);
+      Um[i] = -t;
+    }
+    __syncthreads();
+    for (int i = tid; i < CC; i += blockDim.x) dW[i] = Um[i];
+    __syncthreads();
   }
-  // dW in reference (plain W) layout
-  for (int i = tid; i < CC; i += blockDim.x) {
-    const int r = i / C, c = i % C;
-    dW[i] = transpose ? G[c * C + r] * expf(q.an_logs[r]) : G[i] * expf(q.an_logs[c]);
-  }
-  __syncthreads();
   if (q.weight) {
     // d slogdet / dW = W^-T
     for (int i = tid; i < CC; i += blockDim.x) Lm[i] = q.weight[i];
@@ -447,18 +486,19 @@ extern "C" int nfk_invconv_prep(const float* an_bias, const float* an_logs, cons
 
 extern "C" int nfk_invconv_prep_bwd(const float* an_bias, const float* an_logs, const float* lower,
                                     const float* upper, const float* log_s, const float* p, const float* sign_s,
-                                    const float* weight, int C, int transpose, const float* Wf, const float* dWf,
-                                    const float* dbf, const float* g_ld, int B, float pixels, float* d_bias,
+                                    const float* weight, int C, int reverse, int transpose, const float* Wf,
+                                    const float* dWf, const float* dbf, const float* g_ld, int B, float pixels,
+                                    float* d_bias,
                                     float* d_logs, float* d_lower, float* d_upper, float* d_log_s, float* d_weight,
                                     void* stream) {
   if (C <= 0 || C > 104 || B <= 0) return NFK_ERR_SHAPE;
-  if (!Wf || !dWf || !dbf || !g_ld || !d_bias || !d_logs) return NFK_ERR_ARG;
+  if (!Wf || !dWf || !dbf || !d_bias || !d_logs) return NFK_ERR_ARG;
   if (weight ? !d_weight : (!d_lower || !d_upper || !d_log_s)) return NFK_ERR_ARG;
   InvconvParams q{an_bias, an_logs, lower, upper, log_s, p, sign_s, weight};
   const int smem = prep_smem(C);
   if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(invconv_prep_bwd_kernel), smem)) return rc;
   invconv_prep_bwd_kernel<<<1, PREP_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(
-      q, C, transpose, Wf, dWf, dbf, g_ld, B, pixels, d_bias, d_logs, d_lower, d_upper, d_log_s, d_weight);
+      q, C, reverse, transpose, Wf, dWf, dbf, g_ld, B, pixels, d_bias, d_logs, d_lower, d_upper, d_log_s, d_weight);
   return cudaGetLastError() == cudaSuccess ? NFK_OK : NFK_ERR_LAUNCH;
 }
 

@@ -161,7 +161,7 @@ class FlowStep2dFn(torch.autograd.Function):
 
         d_an_bias, d_an_logs = torch.empty_like(an_bias), torch.empty_like(an_logs)
         d_lower, d_upper, d_log_s = torch.empty_like(lower), torch.empty_like(upper), torch.empty_like(log_s)
-        ops.invconv_prep_bwd(an_bias, an_logs, lower, upper, log_s, p, sign_s, None, C, False, Wf, dWf, dbf, g_ld, B,
+        ops.invconv_prep_bwd(an_bias, an_logs, lower, upper, log_s, p, sign_s, None, C, False, False, Wf, dWf, dbf, g_ld, B,
                              H * W, d_an_bias, d_an_logs, d_lower, d_upper, d_log_s, None)
         grads = [torch.empty_like(t) for t in cw]
         ops.coupling_prep_bwd(*cw, cin, hid, C, K1p, K3p, dB1, dbias1, dB2, dbias2, dB3, dbias3, *grads)

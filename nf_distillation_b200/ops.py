@@ -70,11 +70,12 @@ def invconv_prep(an_bias, an_logs, lower, upper, log_s, p, sign_s, weight, C, re
           "nfk_invconv_prep")
 
 
-def invconv_prep_bwd(an_bias, an_logs, lower, upper, log_s, p, sign_s, weight, C, transpose, Wf, dWf, dbf, g_ld, B,
-                     pixels, d_bias, d_logs, d_lower, d_upper, d_log_s, d_weight):
+def invconv_prep_bwd(an_bias, an_logs, lower, upper, log_s, p, sign_s, weight, C, reverse, transpose, Wf, dWf, dbf,
+                     g_ld, B, pixels, d_bias, d_logs, d_lower, d_upper, d_log_s, d_weight):
     _count()
     check(LIB.nfk_invconv_prep_bwd(_p(an_bias), _p(an_logs), _p(lower), _p(upper), _p(log_s), _p(p), _p(sign_s),
-                                   _p(weight), C, int(transpose), _p(Wf), _p(dWf), _p(dbf), _p(g_ld), B,
+                                   _p(weight), C, int(reverse), int(transpose), _p(Wf), _p(dWf), _p(dbf), _p(g_ld),
+                                   B,
                                    float(pixels), _p(d_bias), _p(d_logs), _p(d_lower), _p(d_upper), _p(d_log_s),
                                    _p(d_weight), _st()), "nfk_invconv_prep_bwd")
 
@@ -159,3 +160,40 @@ def kd_mse_bwd(s, t, g, B, n, scale, ds, accumulate=False):
     _count()
     check(LIB.nfk_kd_mse_bwd(_p(s), _p(t), _p(g), B, n, float(scale), _p(ds), int(accumulate), _st()),
           "nfk_kd_mse_bwd")
+
+
+def flow1d_sizes(D, Cc, hid):
+    """(total_fwd, total_bwd, total_grad, n_act, per-layer [(offG, offGB, ninp, noutp)] * 7)."""
+    import ctypes
+    vals = [ctypes.c_int() for _ in range(4)]
+    offs = (ctypes.c_int * 28)()
+    check(LIB.nfk_flow1d_sizes(D, Cc, hid, *[ctypes.addressof(v) for v in vals], ctypes.addressof(offs)),
+          "nfk_flow1d_sizes")
+    return (*[v.value for v in vals], [tuple(offs[4 * l:4 * l + 4]) for l in range(7)])
+
+
+def flow1d_pack(Wf, bf, ws, bs, D, Cc, hid, PF, PB):
+    import ctypes
+    _count()
+    wa = (ctypes.c_void_p * 6)(*[_p(t) for t in ws])
+    ba = (ctypes.c_void_p * 6)(*[_p(t) for t in bs])
+    check(LIB.nfk_flow1d_pack(_p(Wf), _p(bf), ctypes.addressof(wa), ctypes.addressof(ba), D, Cc, hid, _p(PF), _p(PB),
+                              _st()), "nfk_flow1d_pack")
+
+
+def flow1d_fwd(x, cond, PF, sl, y, ld_in, ld_out, acts, B, D, Cc, hid, reverse):
+    _count()
+    check(LIB.nfk_flow1d_fwd(_p(x), _p(cond), _p(PF), _p(sl), _p(y), _p(ld_in), _p(ld_out), _p(acts), B, D, Cc, hid,
+                             int(reverse), _st()), "nfk_flow1d_fwd")
+
+
+def flow1d_bwd(x_in, cond, acts, PB, PF, g_out, g_ld, dx, G, B, D, Cc, hid, reverse):
+    _count()
+    check(LIB.nfk_flow1d_bwd(_p(x_in), _p(cond), _p(acts), _p(PB), _p(PF), _p(g_out), _p(g_ld), _p(dx), _p(G), B, D,
+                             Cc, hid, int(reverse), _st()), "nfk_flow1d_bwd")
+
+
+def affine_rows(x, Wf, bf, sl, y, ld_in, ld_out, B, D, pixels):
+    _count()
+    check(LIB.nfk_affine_rows(_p(x), _p(Wf), _p(bf), _p(sl), _p(y), _p(ld_in), _p(ld_out), B, D, float(pixels),
+                              _st()), "nfk_affine_rows")

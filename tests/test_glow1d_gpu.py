@@ -1,0 +1,108 @@
+"""GPU parity of the fused 1-D (tabular) Glow kernels against vectors recorded from the unmodified reference.
+Everything here is fp32 end to end; tolerances: outputs / log-dets / bpd 1e-5 relative, deterministic inverse 1e-3,
+loss scalars 1e-5, student gradients (forward AND inverse-pass, i.e. the perceptual term) 1e-4 relative to max|grad|."""
+import json
+
+import pytest
+import torch
+
+from golden_util import cfg_of, load, state_dict_of, t
+from test_glow2d_gpu import nf_config, rel
+
+pytestmark = pytest.mark.gpu
+dev = "cuda"
+
+
+def build(name):
+    from nf_distillation_b200.models import create_glow_model
+    d = load(name)
+    cfg = cfg_of(d)
+    m = create_glow_model(cfg)
+    m.load_state_dict(state_dict_of(d))
+    return d, cfg, m.to(dev).eval()
+
+
+@pytest.mark.parametrize("name", ["glow1d_d6_k5_h32", "glow1d_d63_k5_h32"])
+def test_forward_reverse_golden(name):
+    d, cfg, m = build(name)
+    x = t(d["x"]).to(dev)
+    with torch.no_grad():
+        outs, nll, _ = m(x.clone(), None)
+    n = sum(1 for k in d if k.startswith("out."))
+    assert len(outs) == n
+    for i, o in enumerate(outs):
+        assert rel(o, t(d[f"out.{i}"])) < 1e-5
+    assert rel(nll, t(d["bpd"])) < 1e-5
+    with torch.no_grad():
+        rev = m(z=t(d[f"out.{n - 1}"]).to(dev), temperature=0.0, reverse=True)
+    assert len(rev) == int(d["rev_n"]) and rel(rev[-1], t(d["rev_last"])) < 1e-3
+    B = x.shape[0]
+    with torch.no_grad():
+        out, ld = m.flow.layers[0](x, logdet=torch.zeros(B, device=dev), reverse=False)
+        back, ldr = m.flow.layers[0](out, logdet=torch.zeros(B, device=dev), reverse=True)
+    assert rel(ld, t(d["step.0.logdet_fwd"])) < 1e-5 and rel(ldr, t(d["step.0.logdet_rev"])) < 1e-5
+    assert rel(back, x) < 1e-4
+
+
+def test_kd_training_step_golden_with_inverse_pass_gradients(monkeypatch):
+    import nf_distillation_b200.pl_module as PM
+    d = load("kd1d_d63_t5_s3")
+    s_cfg, t_cfg = cfg_of(d, "s_cfg"), cfg_of(d, "t_cfg")
+    w = json.loads(str(d["weights"]))
+    m = PM.NFModel(nf_config(s_cfg, t_cfg, w, "bsds300"))
+    m.student.load_state_dict(state_dict_of(d, "s_sd."))
+    m.teacher.load_state_dict(state_dict_of(d, "t_sd."))
+    m = m.to(dev)
+    assert m.student_kd_indices == list(d["s_idx"]) and m.teacher_kd_indices == list(d["t_idx"])
+    lat = t(d["latent"]).to(dev)
+    monkeypatch.setattr(PM, "gaussian_sample", lambda mean, logs, T: lat)
+    out = m.training_step([t(d["x"]).to(dev)], 0)
+    for k_, ref in (("nll", "nll"), ("kd", "kd"), ("perceptual", "perceptual"), ("loss", "loss")):
+        assert abs(out[k_].item() - float(d[ref])) < 1e-5 * abs(float(d[ref])) + 1e-7, k_
+    out["loss"].backward()
+    for n_, p in m.student.named_parameters():
+        assert p.grad is not None, n_
+        assert rel(p.grad, t(d["grad." + n_])) < 1e-4, n_
+
+
+@pytest.mark.parametrize("D,hid,K", [(6, 32, 5), (63, 16, 3), (8, 32, 2), (43, 32, 2)])
+def test_full_batch_roundtrip_and_logdet_antisymmetry(D, hid, K):
+    """Reference batch size (65 536, conf/training/tabular.yaml:7): x -> z -> x and logdet_fwd + logdet_rev = 0."""
+    from nf_distillation_b200.models import create_glow_model
+    from nf_distillation_b200.train import glow_cfg, randomise_zero_params
+    torch.manual_seed(D)
+    m = create_glow_model(glow_cfg([D], K, 1, hid, is_1d=True, y_classes=0))
+    randomise_zero_params(m, 3)
+    m = m.to(dev).eval()
+    B = 65536 + 17   # ragged last tile
+    x = torch.randn(B, D, device=dev)
+    with torch.no_grad():
+        outs, nll, _ = m(x, None)
+        back = m(z=outs[-1], temperature=0.0, reverse=True)[-1]
+        assert torch.isfinite(nll).all() and nll.shape == (B,)
+        assert rel(back, x) < 1e-3
+        z, ld = x, torch.zeros(B, device=dev)
+        for layer in m.flow.layers:
+            z, ld = layer(z, logdet=ld, reverse=False)
+        for layer in reversed(m.flow.layers):
+            z, ld = layer(z, logdet=ld, reverse=True)
+        assert ld.abs().max().item() < 1e-2 and rel(z, x) < 1e-3
+
+
+def test_standalone_1d_layers_and_empty_grad_cases():
+    from nf_distillation_b200.models.layers import ActNorm1d, InvertibleConv1x1
+    torch.manual_seed(0)
+    an, iv = ActNorm1d(21).to(dev), InvertibleConv1x1(21, LU_decomposed=True, is_1d=True).to(dev)
+    an.inited = True
+    with torch.no_grad():
+        an.bias.normal_(0, 0.3); an.logs.normal_(0, 0.3)
+        x = torch.randn(100, 21, device=dev)
+        y, ld = an(x, logdet=torch.zeros(100, device=dev))
+        assert rel(y, (x + an.bias) * torch.exp(an.logs)) < 1e-6 and rel(ld, an.logs.sum().expand(100)) < 1e-6
+        z, ld2 = iv(x, logdet=torch.zeros(100, device=dev))
+        L = torch.tril(iv.lower, -1) + torch.eye(21, device=dev)
+        U = torch.triu(iv.upper, 1) + torch.diag(iv.sign_s * torch.exp(iv.log_s))
+        Wm = iv.p @ L @ U
+        assert rel(z, x @ Wm) < 1e-5 and rel(ld2, iv.log_s.sum().expand(100)) < 1e-5
+        xb, ld3 = iv(z, logdet=ld2, reverse=True)
+        assert rel(xb, x) < 1e-4 and ld3.abs().max().item() < 1e-4

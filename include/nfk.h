@@ -142,6 +142,30 @@ int nfk_flow1d_bwd(const float* x_in, const float* cond, const float* acts, cons
 int nfk_affine_rows(const float* x, const float* Wf, const float* bf, const float* sl, float* y, const float* ld_in,
                     float* ld_out, int B, int D, float pixels, void* stream);
 
+/* Same GEMM with an explicit tile width and, per n-tile, the k-block range [kb_begin, kb_end) (64 columns each)
+ * that is not structurally zero — MADE's degree-sorted masks make the hidden weight block-triangular. */
+int nfk_gemm_nt_bf16_ranged(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K, int epi,
+                            void* out, long long ldo, const float* bias, const void* aux, long long ldaux,
+                            float* colsum, int bn, const int* kb_begin, const int* kb_end, void* stream);
+
+/* ---- MAF / MADE (no reference code exists — README.md:7 only; Papamakarios et al. 2017) ----------------------
+ * masks from degrees: m1[o][i] = deg1[o] >= i+1, m2[o][k] = deg2[o] >= deg1[k], m3[r][k] = (r % D)+1 > deg2[k];
+ * weights w1 [H,D], w2 [H,H], w3 [2D,H] (rows: mu then alpha) -> masked bf16 operands (and transposes). */
+int nfk_made_prep(const float* w1, const float* w2, const float* w3, const int* deg1, const int* deg2, int D, int H,
+                  int Dp, int N3p, void* B1, void* B1T, void* B2, void* B2T, void* B3, void* B3T, int with_t,
+                  void* stream);
+int nfk_made_prep_bwd(const float* dB1, const float* dB2, const float* dB3, const int* deg1, const int* deg2, int D,
+                      int H, int Dp, float* dw1, float* dw2, float* dw3, void* stream);
+int nfk_rows_to_bf16(const float* x, int B, int D, int Dp, void* xb, void* stream);
+/* u = (x - mu) exp(-alpha), ld_out = ld_in - sum alpha; u is written in reversed feature order when flip != 0. */
+int nfk_made_affine_fwd(const float* x, const float* out, int N3p, float* u, void* ub, int Dp, const float* ld_in,
+                        float* ld_out, int B, int D, int flip, void* stream);
+int nfk_made_affine_bwd(const float* x, const float* out, int N3p, const float* g_u, const float* g_ld, float* dx,
+                        void* dout, float* db3, int B, int D, int flip, void* stream);
+/* pass i of the sequential inverse: x[:, i] = u[:, i] exp(alpha_i) + mu_i */
+int nfk_made_inv_update(float* x, void* xb, int Dp, const float* u_in, const float* out, int N3p, const float* ld_in,
+                        float* ld_out, int B, int D, int i, int flip, int last, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -36,6 +36,9 @@ struct GemmArgs {
   const __nv_bfloat16* aux;  // EPI_MASK_BF16: post-ReLU activation of the layer being differentiated
   long long ldaux;
   float* colsum;       // EPI_MASK_BF16: per-column sum of the masked gradient (bias gradient)
+  // MADE masked linears: k-blocks [kb_begin, kb_end) that are not structurally zero for each n-tile (kb_end 0 = all)
+  short kb_begin[16];
+  short kb_end[16];
 };
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
@@ -174,7 +177,8 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t ph = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         const int n_tile = t % g.n_tiles, m_tile = t / g.n_tiles;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int kb0 = g.kb_begin[n_tile & 15], kb1 = g.kb_end[n_tile & 15] ? g.kb_end[n_tile & 15] : num_kb;
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty[s], ph ^ 1);
           uint8_t* sa = smem + s * stage_bytes;
           mbar_expect_tx(&full[s], stage_bytes);
@@ -196,7 +200,9 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_wait(&tmem_empty[acc], acc_ph ^ 1);  // epilogue has drained this accumulator stage
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * g.BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int n_tile = t % g.n_tiles;
+        const int kb0 = g.kb_begin[n_tile & 15], kb1 = g.kb_end[n_tile & 15] ? g.kb_end[n_tile & 15] : num_kb;
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full[s], ph);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
@@ -205,7 +211,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int k = 0; k < BK / UMMA_K; ++k) {
             const uint64_t ad = umma_desc_sw128(a_addr + k * (UMMA_K * 2), 16, 1024);
             const uint64_t bd = umma_desc_sw128(b_addr + k * (UMMA_K * 2), 16, 1024);
-            umma_f16(tmem_d, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_f16(tmem_d, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty[s]);  // frees the smem stage when these MMAs retire
           if (++s == g.stages) { s = 0; ph ^= 1; }
@@ -430,9 +436,29 @@ static int set_smem(K kernel, int bytes) {
 
 using namespace nfk;
 
+static int gemm_nt_launch(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K, int epi,
+                          void* out, long long ldo, const float* bias, const void* aux, long long ldaux,
+                          float* colsum, int bn_force, const int* kb_begin, const int* kb_end, void* stream);
+
 extern "C" int nfk_gemm_nt_bf16(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K,
                                 int epi, void* out, long long ldo, const float* bias, const void* aux,
                                 long long ldaux, float* colsum, void* stream) {
+  return gemm_nt_launch(A, lda, B, ldb, M, N, K, epi, out, ldo, bias, aux, ldaux, colsum, 0, nullptr, nullptr,
+                        stream);
+}
+
+extern "C" int nfk_gemm_nt_bf16_ranged(const void* A, long long lda, const void* B, long long ldb, int M, int N,
+                                       int K, int epi, void* out, long long ldo, const float* bias, const void* aux,
+                                       long long ldaux, float* colsum, int bn, const int* kb_begin,
+                                       const int* kb_end, void* stream) {
+  if (bn <= 0 || bn % 16 || bn > 256 || (N + bn - 1) / bn > 16 || !kb_begin || !kb_end) return NFK_ERR_ARG;
+  return gemm_nt_launch(A, lda, B, ldb, M, N, K, epi, out, ldo, bias, aux, ldaux, colsum, bn, kb_begin, kb_end,
+                        stream);
+}
+
+static int gemm_nt_launch(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K, int epi,
+                          void* out, long long ldo, const float* bias, const void* aux, long long ldaux,
+                          float* colsum, int bn_force, const int* kb_begin, const int* kb_end, void* stream) {
   if (M <= 0 || N <= 0 || K <= 0) return NFK_ERR_SHAPE;
   if (K % BK || N % 16 || ldo % 8) return NFK_ERR_SHAPE;
   if (epi == NFK_EPI_BIAS_RELU_BF16 && !bias) return NFK_ERR_ARG;
@@ -443,7 +469,14 @@ extern "C" int nfk_gemm_nt_bf16(const void* A, long long lda, const void* B, lon
   // few row tiles (small images x small batch): narrower accumulator tiles so the grid still covers the SMs
   const int m_tiles = (M + BM - 1) / BM;
   while (m_tiles * ((N + g.BN - 1) / g.BN) < 148 && g.BN >= 128 && g.BN % 32 == 0) g.BN /= 2;
+  if (bn_force) g.BN = bn_force;
   g.n_tiles = (N + g.BN - 1) / g.BN;
+  if (kb_begin)
+    for (int i = 0; i < g.n_tiles && i < 16; ++i) {
+      if (kb_begin[i] < 0 || kb_end[i] > K / BK || kb_begin[i] >= kb_end[i]) return NFK_ERR_ARG;
+      g.kb_begin[i] = static_cast<short>(kb_begin[i]);
+      g.kb_end[i] = static_cast<short>(kb_end[i]);
+    }
   const int stage_bytes = BM * 128 + g.BN * 128;
   g.stages = min(8, (194 * 1024) / stage_bytes);
   g.out = out; g.ldo = ldo; g.bias = bias;

@@ -197,3 +197,50 @@ def affine_rows(x, Wf, bf, sl, y, ld_in, ld_out, B, D, pixels):
     _count()
     check(LIB.nfk_affine_rows(_p(x), _p(Wf), _p(bf), _p(sl), _p(y), _p(ld_in), _p(ld_out), B, D, float(pixels),
                               _st()), "nfk_affine_rows")
+
+
+def gemm_nt_ranged(A, B, M, N, K, epi, out, bn, kb_begin, kb_end, bias=None, aux=None, colsum=None):
+    """gemm_nt with tile width bn and per-n-tile k-block ranges (structurally-zero mask tiles are never loaded)."""
+    import ctypes
+    _count()
+    n = len(kb_begin)
+    kb0 = (ctypes.c_int * n)(*kb_begin)
+    kb1 = (ctypes.c_int * n)(*kb_end)
+    check(LIB.nfk_gemm_nt_bf16_ranged(_p(A), A.stride(0), _p(B), B.stride(0), M, N, K, epi, _p(out), out.stride(0),
+                                      _p(bias), _p(aux), 0 if aux is None else aux.stride(0), _p(colsum), bn,
+                                      ctypes.addressof(kb0), ctypes.addressof(kb1), _st()), "nfk_gemm_nt_bf16_ranged")
+
+
+def made_prep(w1, w2, w3, deg1, deg2, D, H, Dp, N3p, B1, B1T, B2, B2T, B3, B3T, with_t):
+    _count()
+    check(LIB.nfk_made_prep(_p(w1), _p(w2), _p(w3), _p(deg1), _p(deg2), D, H, Dp, N3p, _p(B1), _p(B1T), _p(B2),
+                            _p(B2T), _p(B3), _p(B3T), int(with_t), _st()), "nfk_made_prep")
+
+
+def made_prep_bwd(dB1, dB2, dB3, deg1, deg2, D, H, Dp, dw1, dw2, dw3):
+    _count()
+    check(LIB.nfk_made_prep_bwd(_p(dB1), _p(dB2), _p(dB3), _p(deg1), _p(deg2), D, H, Dp, _p(dw1), _p(dw2), _p(dw3),
+                                _st()), "nfk_made_prep_bwd")
+
+
+def rows_to_bf16(x, B, D, Dp, xb):
+    _count()
+    check(LIB.nfk_rows_to_bf16(_p(x), B, D, Dp, _p(xb), _st()), "nfk_rows_to_bf16")
+
+
+def made_affine_fwd(x, out, N3p, u, ub, Dp, ld_in, ld_out, B, D, flip):
+    _count()
+    check(LIB.nfk_made_affine_fwd(_p(x), _p(out), N3p, _p(u), _p(ub), Dp, _p(ld_in), _p(ld_out), B, D, int(flip),
+                                  _st()), "nfk_made_affine_fwd")
+
+
+def made_affine_bwd(x, out, N3p, g_u, g_ld, dx, dout, db3, B, D, flip):
+    _count()
+    check(LIB.nfk_made_affine_bwd(_p(x), _p(out), N3p, _p(g_u), _p(g_ld), _p(dx), _p(dout), _p(db3), B, D, int(flip),
+                                  _st()), "nfk_made_affine_bwd")
+
+
+def made_inv_update(x, xb, Dp, u_in, out, N3p, ld_in, ld_out, B, D, i, flip, last):
+    _count()
+    check(LIB.nfk_made_inv_update(_p(x), _p(xb), Dp, _p(u_in), _p(out), N3p, _p(ld_in), _p(ld_out), B, D, i,
+                                  int(flip), int(last), _st()), "nfk_made_inv_update")

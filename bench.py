@@ -142,6 +142,9 @@ def main():
     ap.add_argument("--no-graphs", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-batch", type=int, default=8)
+    ap.add_argument("--ncu-step", action="store_true",
+                    help="profiling aid: warm up, then run ONE eager step between cudaProfilerStart/Stop and exit "
+                         "(use with ncu --profile-from-start off); prints no bench value")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
@@ -180,7 +183,16 @@ def main():
     host_pool = [synthetic_images(B, wl["image"], 1000 + rank * 100 + i).pin_memory() for i in range(n_pool)]
     dev_pool = [h.to(device) for h in host_pool]
     trainer.x.copy_(dev_pool[0])
-    l0 = ops.launch_count()
+    if args.ncu_step:
+        trainer.use_graphs = False
+        trainer.warmup(iters=3)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        trainer.step_device()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        print(json.dumps({"ncu_step": True, "batch": B, "losses": trainer.losses.cpu().tolist()}))
+        return
     trainer.warmup(iters=1)                      # eager step(s) + graph capture
     launches_eager_step = None
     # count kernels of ONE step: run one extra eager step outside the graphs

@@ -58,7 +58,7 @@ __device__ __forceinline__ uint32_t tmem_cols_pow2(int n) {
 // overlap the MMAs of tile i+1.
 template <int EPI>
 __device__ __forceinline__ void nt_epilogue_16(const GemmArgs& g, const uint32_t (&r)[16], long long row, bool row_ok,
-                                               int col, int cl, const float* bias_s, int lane) {
+                                               int col, int cl, const float* bias_s, int lane, uint4 m0, uint4 m1) {
   if constexpr (EPI == NFK_EPI_F32) {
     if (row_ok) {
       float* o = static_cast<float*>(g.out) + row * g.ldo + col;
@@ -90,12 +90,6 @@ __device__ __forceinline__ void nt_epilogue_16(const GemmArgs& g, const uint32_t
     }
   } else {  // NFK_EPI_MASK_BF16: ReLU backward mask + bias-gradient column sums
     float v[16];
-    uint4 m0 = make_uint4(0, 0, 0, 0), m1 = m0;
-    if (row_ok) {
-      const uint4* a = reinterpret_cast<const uint4*>(g.aux + row * g.ldaux + col);
-      m0 = __ldg(a);
-      m1 = __ldg(a + 1);
-    }
     const uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
@@ -236,20 +230,50 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
       }
-      mbar_wait(&tmem_full[acc], acc_ph);
-      tc_fence_after();
       const long long row = static_cast<long long>(m_tile) * BM + q * 32 + lane;
       const bool row_ok = row < g.M;
+      uint4 ma[4], mb[4];
+      auto load_mask = [&](int c, uint4 (&mk)[4]) {
+        const int col = n_tile * g.BN + c;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          mk[j] = make_uint4(0, 0, 0, 0);
+          if (row_ok && c + 8 * j < g.BN && col + 8 * j < g.N)
+            mk[j] = __ldg(reinterpret_cast<const uint4*>(g.aux + row * g.ldaux + col + 8 * j));
+        }
+      };
+      if constexpr (EPI == NFK_EPI_MASK_BF16) {
+        load_mask(0, ma);
+        load_mask(32, mb);
+      }
+      mbar_wait(&tmem_full[acc], acc_ph);
+      tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * g.BN;
-      for (int c = 0; c < g.BN; c += 32) {
+      auto do32 = [&](int c, const uint4 (&mk)[4]) {
         uint32_t r0[16], r1[16];
         const bool two = c + 16 < g.BN;
         tmem_ld16(taddr + c, r0);
         if (two) tmem_ld16(taddr + c + 16, r1);
         tmem_ld_wait();
         const int col = n_tile * g.BN + c;
-        if (col < g.N) nt_epilogue_16<EPI>(g, r0, row, row_ok, col, c, bs, lane);
-        if (two && col + 16 < g.N) nt_epilogue_16<EPI>(g, r1, row, row_ok, col + 16, c + 16, bs, lane);
+        if (col < g.N) nt_epilogue_16<EPI>(g, r0, row, row_ok, col, c, bs, lane, mk[0], mk[1]);
+        if (two && col + 16 < g.N) nt_epilogue_16<EPI>(g, r1, row, row_ok, col + 16, c + 16, bs, lane, mk[2], mk[3]);
+      };
+      if constexpr (EPI == NFK_EPI_MASK_BF16) {
+        // the ReLU mask comes from HBM with a row stride of ldaux: keep two 32-column groups of it in flight
+        // (issued before the accumulator is even complete) so the epilogue never waits on a cold load
+        for (int c = 0; c < g.BN; c += 64) {
+          do32(c, ma);
+          if (c + 64 < g.BN) load_mask(c + 64, ma);
+          if (c + 32 < g.BN) {
+            do32(c + 32, mb);
+            if (c + 96 < g.BN) load_mask(c + 96, mb);
+          }
+        }
+      } else {
+        const uint4 none[4] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0),
+                               make_uint4(0, 0, 0, 0)};
+        for (int c = 0; c < g.BN; c += 32) do32(c, none);
       }
       tc_fence_before();
       __syncwarp();

@@ -38,8 +38,10 @@ __device__ __forceinline__ void sigmoid_logsigmoid(float t, float& s, float& ls)
 
 struct Geo {
   int B, HW, W, H;
-  int ipc;   // images per CTA
-  int pixt;  // ipc * HW
+  int ipc;     // images per CTA
+  int pixt;    // ipc * HW
+  int strips;  // coupling_fwd: row strips per image (only when ipc == 1), log-det via atomics
+  int og;      // affine1x1_fwd: output-channel groups per pixel (more threads for small images)
 };
 
 // ------------------------------------------------------------------------------------------ affine1x1 fwd
@@ -78,7 +80,10 @@ affine1x1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ Wf, 
   if (ld_out && tid < nimg) ld_out[b0 + tid] = ld_in[b0 + tid] + sl[0] * static_cast<float>(g.HW);
   __syncthreads();
 
-  for (int pl = tid; pl < npix; pl += ZT) {
+  const int pixb = ZT / g.og;            // pixels per pass; lanes = consecutive pixels, output groups across warps
+  const int og = tid / pixb;
+  const int opg = C / g.og;              // outputs per group
+  for (int pl = tid % pixb; pl < npix && og < g.og; pl += pixb) {
     const int img = pl / g.HW, p = pl - img * g.HW;
     const float* xp = x + (static_cast<long long>(b0 + img) * C) * g.HW + p;
     float xv[C];
@@ -86,8 +91,7 @@ affine1x1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ Wf, 
     for (int i = 0; i < C; ++i) xv[i] = __ldg(xp + static_cast<long long>(i) * g.HW);
     if (Wf) {
       float* yp = y + (static_cast<long long>(b0 + img) * C) * g.HW + p;
-#pragma unroll 4
-      for (int o = 0; o < C; ++o) {
+      for (int o = og * opg; o < (og + 1) * opg; ++o) {
         float acc = bs[o];
         const float4* wr = reinterpret_cast<const float4*>(Ws + o * C);
 #pragma unroll
@@ -102,8 +106,7 @@ affine1x1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ Wf, 
         if (col && o < CH) y1s[o * ldp + pl] = acc;
       }
     } else if (col) {
-#pragma unroll
-      for (int o = 0; o < CH; ++o) y1s[o * ldp + pl] = xv[o];
+      for (int o = og * opg; o < (og + 1) * opg && o < CH; ++o) y1s[o * ldp + pl] = xv[o];
     }
   }
   if (!col) return;
@@ -142,15 +145,21 @@ coupling_fwd_kernel(const float* __restrict__ P, int K3p, const float* __restric
   float* ys = sm;
   float* ls = ys + J * ldp;
   const int tid = threadIdx.x;
-  const int b0 = blockIdx.x * g.ipc;
-  const int nimg = min(g.ipc, g.B - b0);
-  const int npix = nimg * g.HW;
+  int b0, nimg, p_lo, p_cnt;
+  if (g.strips > 1) {
+    b0 = blockIdx.x / g.strips; nimg = 1;
+    p_cnt = g.HW / g.strips; p_lo = (blockIdx.x % g.strips) * p_cnt;
+  } else {
+    b0 = blockIdx.x * g.ipc; nimg = min(g.ipc, g.B - b0);
+    p_cnt = g.HW; p_lo = 0;
+  }
+  const int npix = nimg * p_cnt;
 
   for (int i = tid; i < J * npix; i += ZT) {
     // (img, j, p) with p fastest
-    const int img = i / (J * g.HW), r = i - img * J * g.HW;
-    const int j = r / g.HW, p = r - j * g.HW;
-    ys[j * ldp + img * g.HW + p] = y[(static_cast<long long>(b0 + img) * C + J + j) * g.HW + p];
+    const int img = i / (J * p_cnt), r = i - img * J * p_cnt;
+    const int j = r / p_cnt, p = r - j * p_cnt;
+    ys[j * ldp + img * p_cnt + p] = y[(static_cast<long long>(b0 + img) * C + J + j) * g.HW + p_lo + p];
   }
   __syncthreads();
   constexpr int PPP = ZT / J;  // pixels per pass
@@ -158,9 +167,9 @@ coupling_fwd_kernel(const float* __restrict__ P, int K3p, const float* __restric
   if (pl0 < PPP) {
     const float bsh = bias3[2 * j], blg = bias3[2 * j + 1];
     for (int pl = pl0; pl < npix; pl += PPP) {
-      const int img = pl / g.HW, rem = pl - img * g.HW;
+      const int img = pl / p_cnt, rem = p_lo + pl - img * p_cnt;
       const int yy = rem / g.W, xx = rem - yy * g.W;
-      const long long m = static_cast<long long>(b0) * g.HW + pl;
+      const long long m = static_cast<long long>(b0 + img) * g.HW + rem;
       float sh = bsh, lg = blg;
 #pragma unroll
       for (int tap = 0; tap < 9; ++tap) {
@@ -182,20 +191,24 @@ coupling_fwd_kernel(const float* __restrict__ P, int K3p, const float* __restric
   }
   __syncthreads();
   for (int i = tid; i < J * npix; i += ZT) {
-    const int img = i / (J * g.HW), r = i - img * J * g.HW;
-    const int jj = r / g.HW, p = r - jj * g.HW;
-    y[(static_cast<long long>(b0 + img) * C + J + jj) * g.HW + p] = ys[jj * ldp + img * g.HW + p];
+    const int img = i / (J * p_cnt), r = i - img * J * p_cnt;
+    const int jj = r / p_cnt, p = r - jj * p_cnt;
+    y[(static_cast<long long>(b0 + img) * C + J + jj) * g.HW + p_lo + p] = ys[jj * ldp + img * p_cnt + p];
   }
   if (ld) {
     const int warp = tid >> 5, lane = tid & 31;
     for (int img = warp; img < nimg; img += ZT / 32) {
       float acc = 0.f;
-      for (int i = lane; i < J * g.HW; i += 32) {
-        const int jj = i / g.HW, p = i - jj * g.HW;
-        acc += ls[jj * ldp + img * g.HW + p];
+      for (int i = lane; i < J * p_cnt; i += 32) {
+        const int jj = i / p_cnt, p = i - jj * p_cnt;
+        acc += ls[jj * ldp + img * p_cnt + p];
       }
       for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-      if (lane == 0) ld[b0 + img] += reverse ? -acc : acc;
+      if (lane == 0) {
+        const float v = reverse ? -acc : acc;
+        if (g.strips > 1) atomicAdd(ld + b0 + img, v);
+        else ld[b0 + img] += v;
+      }
     }
   }
 }
@@ -417,6 +430,8 @@ static Geo make_geo(int B, int C, int H, int W, bool heavy) {
   // small images: prefer >= 2 CTAs per SM over fat CTAs (these kernels are latency-bound when the grid is small)
   while (g.ipc > 1 && (B + g.ipc - 1) / g.ipc < 2 * 148) g.ipc >>= 1;
   g.pixt = g.ipc * g.HW;
+  g.strips = 1;
+  g.og = 1;
   return g;
 }
 
@@ -445,6 +460,12 @@ extern "C" int nfk_affine1x1_fwd(const float* x, const float* Wf, const float* b
   if (!x || (!Wf && !col) || (Wf && (!bf || !y)) || (ld_out && (!ld_in || !sl))) return NFK_ERR_ARG;
   if (col && (K1p % 64 || K1p < 9 * (C / 2))) return NFK_ERR_SHAPE;
   Geo g = make_geo(B, C, H, W, false);
+  {
+    // few pixels in flight -> split the C outputs of a pixel over 2 or 4 threads
+    const long long M = static_cast<long long>(B) * H * W;
+    g.og = M >= 131072 ? 1 : (M >= 32768 ? 2 : 4);
+    while (g.og > 1 && C % g.og) g.og >>= 1;
+  }
   const int smem = (C * C + C + (col ? (C / 2) * (g.pixt + 1) + K1p : 0)) * 4;
   const int grid = (B + g.ipc - 1) / g.ipc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -462,8 +483,15 @@ extern "C" int nfk_coupling_fwd(const float* P, int K3p, const float* bias3, flo
   if (B <= 0 || H <= 0 || W <= 0 || H * W > 4096 || K3p < 9 * C || K3p % 2) return NFK_ERR_SHAPE;
   if (!P || !bias3 || !y) return NFK_ERR_ARG;
   Geo g = make_geo(B, C, H, W, false);
+  if (g.ipc == 1) {
+    // one image per CTA: cut it into row strips while a strip still gives every thread work and the grid is small
+    const int J = C / 2;
+    while (g.strips * 2 <= H && H % (g.strips * 2) == 0 && (g.HW / (g.strips * 2)) * J >= ZT &&
+           static_cast<long long>(B) * g.strips < 8 * 148)
+      g.strips *= 2;
+  }
   const int smem = 2 * (C / 2) * (g.pixt + 1) * 4;
-  const int grid = (B + g.ipc - 1) / g.ipc;
+  const int grid = g.strips > 1 ? B * g.strips : (B + g.ipc - 1) / g.ipc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   NFK_DISPATCH_C(C, {
     int rc = ensure_smem(coupling_fwd_kernel<CC>, smem);

@@ -56,6 +56,11 @@ class GlowGetAllOutputs(Glow):
             logdet = torch.zeros(x.shape[0], device=x.device, dtype=torch.float32)
         else:
             x, logdet = uniform_binning_correction(x)
+        return self.flow_from_dequantized(x, logdet, y_onehot)
+
+    def flow_from_dequantized(self, x, logdet, y_onehot=None):
+        """Everything of normal_flow after the (in-place) dequantisation; NFModel uses it to run the teacher and the
+        student concurrently on two streams while keeping the reference's in-place noise semantics."""
         z, logdet = self.flow(x, y_onehot=y_onehot, logdet=logdet, reverse=False)
         last_z = z[-1]
         bpd = self._objective(x, last_z, logdet, y_onehot)

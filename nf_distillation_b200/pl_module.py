@@ -7,6 +7,7 @@ reference module (validation, FID/KS logging, data hooks) is out of scope (SURVE
 """
 from __future__ import annotations
 
+import os
 import typing as tp
 
 import torch
@@ -37,6 +38,8 @@ class NFModel(nn.Module):
             raise NameError("Unknown KD loss name")
         self.student_kd_indices, self.teacher_kd_indices = self._get_kd_indices()
         self.logged: tp.Dict[str, torch.Tensor] = {}
+        self.concurrent_teacher = os.environ.get("NFK_CONCURRENT_TEACHER", "1") != "0"
+        self._side = None
 
     @property
     def device(self):
@@ -93,11 +96,15 @@ class NFModel(nn.Module):
         else:
             x, y, weights = batch
         cond = y if self.params["student"]["y_condition"] else None
-        student_z, student_nll, _ = self.student(x, cond)
         teacher_z = None
-        if self.kd_weight > 0:
-            with torch.no_grad():
-                teacher_z, _, _ = self.teacher(x, cond)   # x already carries the student's dequant noise
+        if (self.kd_weight > 0 and self.concurrent_teacher and x.is_cuda and not self.params["student"]["is_1d"]
+                and not self.params["teacher"]["is_1d"]):
+            student_z, student_nll, teacher_z = self._forward_two_streams(x, cond)
+        else:
+            student_z, student_nll, _ = self.student(x, cond)
+            if self.kd_weight > 0:
+                with torch.no_grad():
+                    teacher_z, _, _ = self.teacher(x, cond)   # x already carries the student's dequant noise
         student_x = teacher_x = None
         if self.perceptual_weight > 0:
             mean, logs = self.student.prior(x, y_onehot=cond)
@@ -107,6 +114,26 @@ class NFModel(nn.Module):
                 teacher_x = self.teacher(z=latent, temperature=0.7, reverse=True, y_onehot=cond)[-1]
         return {"student_nll": student_nll, "student_z": student_z, "teacher_z": teacher_z,
                 "student_x": student_x, "teacher_x": teacher_x, "weights": weights}
+
+    def _forward_two_streams(self, x, cond):
+        """Same arithmetic and in-place side effects as the sequential code above (student noise, then teacher noise
+        on top, both added to the caller's batch), but the frozen teacher runs on a second stream: its many small
+        level-2/3 kernels fill the SMs the student leaves idle. Captured CUDA graphs keep the fork/join."""
+        from .models.utils import uniform_binning_correction
+        main = torch.cuda.current_stream()
+        if self._side is None:
+            self._side = torch.cuda.Stream()
+        x, ld_s = uniform_binning_correction(x)            # student's dequantisation noise, in place
+        xs = x.clone()                                     # the student's view of the input
+        self._side.wait_stream(main)
+        with torch.cuda.stream(self._side), torch.no_grad():
+            xt, ld_t = uniform_binning_correction(x)       # teacher's noise on top, in place (reference semantics)
+            teacher_z, _, _ = self.teacher.flow_from_dequantized(xt, ld_t, cond)
+        student_z, student_nll, _ = self.student.flow_from_dequantized(xs, ld_s, cond)
+        main.wait_stream(self._side)
+        for i in self.teacher_kd_indices:
+            teacher_z[i].record_stream(main)
+        return student_z, student_nll, teacher_z
 
     # ---- pl_module.py:257-320
     def loss(self, out, *args):

@@ -29,8 +29,9 @@ extern "C" {
 
 /* Epilogues of nfk_gemm_nt_bf16 */
 #define NFK_EPI_F32 0            /* out fp32  = acc (+ bias[col])                                   */
-#define NFK_EPI_BIAS_RELU_BF16 1 /* out bf16  = relu(acc + bias[col])   (Conv2d+ActNorm+ReLU, folded) */
-#define NFK_EPI_MASK_BF16 2      /* out bf16  = acc * (aux > 0); colsum[col] += column sums (ReLU bwd) */
+#define NFK_EPI_BIAS_RELU_BF16 1 /* out bf16  = relu(acc + bias[col])   (Conv2d+ActNorm+ReLU, folded);
+                                    aux (optional) <- 1-bit mask (out > 0), word-major [N/32][ldaux >= M] words */
+#define NFK_EPI_MASK_BF16 2      /* out bf16  = acc * mask(aux);  colsum[col] += column sums   (ReLU backward) */
 
 int nfk_version(void);
 
@@ -42,6 +43,11 @@ int nfk_version(void);
 int nfk_gemm_nt_bf16(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K, int epi,
                      void* out, long long ldo, const float* bias, const void* aux, long long ldaux, float* colsum,
                      void* stream);
+
+/* Diagnostics: when buf != NULL ([grid][8] int64 on the device) the NT GEMM records, per CTA, cycles of the MMA
+ * issuer {total, waiting for a free accumulator, waiting for operands, tiles} and of epilogue warp 0 {waiting for the
+ * accumulator, draining it}. NULL switches it off. */
+int nfk_gemm_set_prof(void* buf);
 
 /* out[Mo,No] (fp32, caller-zeroed) += sum_k A[k,Mo] * B[k,No]; A/B bf16 row-major [Kpix, ld]. Weight gradients
  * of the coupling convs (autograd of nn.Conv2d in models/layers.py:209,249), split-K over pixels with

@@ -12,6 +12,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <cstdlib>
 
 #include "../../include/nfk.h"
 #include "launch_util.h"
@@ -22,7 +23,8 @@ namespace nfk {
 constexpr int BM = 128;           // accumulator rows per CTA (= TMEM lanes)
 constexpr int BK = 64;            // bf16 elements per 128-byte swizzle row
 constexpr int UMMA_K = 16;        // K per tcgen05.mma for 16-bit operands
-constexpr int GEMM_THREADS = 192; // warp0 TMA, warp1 MMA(+TMEM alloc), warps 2-5 epilogue
+constexpr int GEMM_THREADS = 320; // warp0 TMA, warp1 MMA(+TMEM alloc), warps 2-9 epilogue (2 per TMEM lane quadrant)
+constexpr int TN_THREADS = 192;   // TN kernel: warps 2-5 epilogue
 
 struct GemmArgs {
   int M, N, K;         // NT: out[M,N]; TN: out[M=Mo, N=No], K = pixels
@@ -33,9 +35,12 @@ struct GemmArgs {
   void* out;
   long long ldo;
   const float* bias;   // EPI_BIAS_RELU_BF16 / EPI_F32 (optional)
-  const __nv_bfloat16* aux;  // EPI_MASK_BF16: post-ReLU activation of the layer being differentiated
-  long long ldaux;
+  uint32_t* mask_out;        // EPI_BIAS_RELU_BF16 (optional): 1 bit per output, (value > 0), word-major
+  const uint32_t* mask_in;   // EPI_MASK_BF16: that mask, read back by the dgrad of the same layer
+  long long ldmask;          // [N/32][ldmask >= M] words: word (col/32, row) holds columns col..col+31 of that row
   float* colsum;       // EPI_MASK_BF16: per-column sum of the masked gradient (bias gradient)
+  int slab_bytes;      // per-epilogue-warp staging slab for the TMA store (0 = direct global stores)
+  long long* prof;     // optional [grid][8] cycle counters (diagnostics: where each role waits)
   // MADE masked linears: k-blocks [kb_begin, kb_end) that are not structurally zero for each n-tile (kb_end 0 = all)
   short kb_begin[16];
   short kb_end[16];
@@ -53,115 +58,144 @@ __device__ __forceinline__ uint32_t tmem_cols_pow2(int n) {
 }
 
 // ------------------------------------------------------------------------------------------------ NT kernel
-// Persistent: grid = min(tiles, SMs); every CTA walks tiles t = blockIdx.x, +gridDim.x, ... (n-tile fastest, so CTAs
-// running side by side share the A row block through L2). Two TMEM accumulator stages let the epilogue of tile i
-// overlap the MMAs of tile i+1.
+// Persistent: every CTA (or CTA pair) walks tiles t = id, id + stride, ... (n-tile fastest, so CTAs running side by
+// side share the A row block through L2). Two TMEM accumulator stages let the epilogue of tile i overlap the MMAs of
+// tile i+1. PAIR = cta_group::2: two SMs share one 256 x BN tile, each stages its own 128 rows of A and HALF of the B
+// tile; the leader issues the M=256 MMAs, both CTAs run TMA producers and epilogues on their own 128 TMEM lanes.
+//
+// Epilogue data path: TMEM -> registers (tcgen05.ld) -> fused math -> 128B-swizzled smem slab (one per warp) -> TMA
+// store. A thread owns one output ROW, so direct global stores would touch 32 different 128-byte lines per warp
+// instruction; staging through smem makes every HBM write a full-line bulk store and frees the LSU.
 template <int EPI>
 __device__ __forceinline__ void nt_epilogue_16(const GemmArgs& g, const uint32_t (&r)[16], long long row, bool row_ok,
-                                               int col, int cl, const float* bias_s, int lane, uint4 m0, uint4 m1) {
+                                               int col, int cl, int sc, const float* bias_s, int lane,
+                                               uint32_t bits16, uint8_t* slab, bool want_bits, uint32_t& relu_bits) {
+  // cl: column inside the tile (bias index), sc: column inside this warp's staging slab
+  const uint32_t sw = static_cast<uint32_t>(lane & 7);
   if constexpr (EPI == NFK_EPI_F32) {
-    if (row_ok) {
+    float4 v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      v[j].x = __uint_as_float(r[4 * j + 0]); v[j].y = __uint_as_float(r[4 * j + 1]);
+      v[j].z = __uint_as_float(r[4 * j + 2]); v[j].w = __uint_as_float(r[4 * j + 3]);
+      if (g.bias) {
+        const float4 b = *reinterpret_cast<const float4*>(bias_s + cl + 4 * j);
+        v[j].x += b.x; v[j].y += b.y; v[j].z += b.z; v[j].w += b.w;
+      }
+    }
+    if (slab) {
+      uint8_t* base = slab + lane * 128;
+      const uint32_t cc = static_cast<uint32_t>(sc & 31) >> 2;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) *reinterpret_cast<float4*>(base + (((cc + j) ^ sw) << 4)) = v[j];
+    } else if (row_ok) {
       float* o = static_cast<float*>(g.out) + row * g.ldo + col;
 #pragma unroll
-      for (int j = 0; j < 16; j += 4) {
-        float4 v;
-        v.x = __uint_as_float(r[j + 0]); v.y = __uint_as_float(r[j + 1]);
-        v.z = __uint_as_float(r[j + 2]); v.w = __uint_as_float(r[j + 3]);
-        if (g.bias) {
-          const float4 b = *reinterpret_cast<const float4*>(bias_s + cl + j);
-          v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
-        }
-        *reinterpret_cast<float4*>(o + j) = v;
-      }
+      for (int j = 0; j < 4; ++j) *reinterpret_cast<float4*>(o + 4 * j) = v[j];
     }
-  } else if constexpr (EPI == NFK_EPI_BIAS_RELU_BF16) {
-    uint32_t p[8];
-#pragma unroll
-    for (int j = 0; j < 16; j += 4) {
-      const float4 b = *reinterpret_cast<const float4*>(bias_s + cl + j);
-      p[(j >> 1)] = pack_bf16x2(fmaxf(__uint_as_float(r[j]) + b.x, 0.f), fmaxf(__uint_as_float(r[j + 1]) + b.y, 0.f));
-      p[(j >> 1) + 1] =
-          pack_bf16x2(fmaxf(__uint_as_float(r[j + 2]) + b.z, 0.f), fmaxf(__uint_as_float(r[j + 3]) + b.w, 0.f));
-    }
-    if (row_ok) {
-      uint4* o = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(g.out) + row * g.ldo + col);
-      o[0] = make_uint4(p[0], p[1], p[2], p[3]);
-      o[1] = make_uint4(p[4], p[5], p[6], p[7]);
-    }
-  } else {  // NFK_EPI_MASK_BF16: ReLU backward mask + bias-gradient column sums
+  } else {
     float v[16];
-    const uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+    if constexpr (EPI == NFK_EPI_BIAS_RELU_BF16) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      // post-ReLU activations are >= 0, so "active" <=> the bf16 bit pattern is non-zero (and not -0).
-      const uint32_t h = (j & 1) ? (mw[j >> 1] >> 16) : (mw[j >> 1] & 0xFFFFu);
-      const bool on = row_ok && h != 0u && h != 0x8000u;
-      v[j] = on ? __uint_as_float(r[j]) : 0.f;
-    }
-    if (row_ok) {
-      uint4* o = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(g.out) + row * g.ldo + col);
-      o[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-      o[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
-    }
-    if (g.colsum) {
-      // 32 lanes x 16 columns -> lane j (< 16) ends with the sum of column j over the warp's 32 rows.
-#pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] += __shfl_xor_sync(0xffffffffu, v[j], 16);
-#pragma unroll
-      for (int off = 8; off >= 1; off >>= 1) {
-        const bool up = (lane & off) != 0;
-#pragma unroll
-        for (int j = 0; j < off; ++j) {
-          const float send = up ? v[j] : v[j + off];
-          const float keep = up ? v[j + off] : v[j];
-          v[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-        }
+      for (int j = 0; j < 16; j += 4) {
+        const float4 b = *reinterpret_cast<const float4*>(bias_s + cl + j);
+        v[j] = fmaxf(__uint_as_float(r[j]) + b.x, 0.f);
+        v[j + 1] = fmaxf(__uint_as_float(r[j + 1]) + b.y, 0.f);
+        v[j + 2] = fmaxf(__uint_as_float(r[j + 2]) + b.z, 0.f);
+        v[j + 3] = fmaxf(__uint_as_float(r[j + 3]) + b.w, 0.f);
       }
-      if (lane < 16) atomicAdd(g.colsum + col + lane, v[0]);
+      if (want_bits) {
+        uint32_t bits = 0;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) bits |= (v[j] > 0.f ? 1u : 0u) << j;
+        relu_bits |= bits << (cl & 16);
+      }
+    } else {  // NFK_EPI_MASK_BF16: ReLU backward through the 1-bit activation mask of the forward pass
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = (row_ok && ((bits16 >> j) & 1u)) ? __uint_as_float(r[j]) : 0.f;
+    }
+    const uint4 p0 = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                                pack_bf16x2(v[6], v[7]));
+    const uint4 p1 = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]),
+                                pack_bf16x2(v[14], v[15]));
+    if (slab) {
+      uint8_t* base = slab + lane * 128;
+      const uint32_t cc = static_cast<uint32_t>(sc & 63) >> 3;
+      *reinterpret_cast<uint4*>(base + ((cc ^ sw) << 4)) = p0;
+      *reinterpret_cast<uint4*>(base + (((cc + 1) ^ sw) << 4)) = p1;
+    } else if (row_ok) {
+      uint4* o = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(g.out) + row * g.ldo + col);
+      o[0] = p0;
+      o[1] = p1;
+    }
+    if constexpr (EPI == NFK_EPI_MASK_BF16) {
+      if (g.colsum && !slab) {
+        // direct-store fallback: 32 lanes x 16 columns -> lane j (< 16) ends with the sum of column j
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] += __shfl_xor_sync(0xffffffffu, v[j], 16);
+#pragma unroll
+        for (int off = 8; off >= 1; off >>= 1) {
+          const bool up = (lane & off) != 0;
+#pragma unroll
+          for (int j = 0; j < off; ++j) {
+            const float send = up ? v[j] : v[j + off];
+            const float keep = up ? v[j + off] : v[j];
+            v[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+          }
+        }
+        if (lane < 16) atomicAdd(g.colsum + col + lane, v[0]);
+      }
     }
   }
 }
 
-template <int EPI>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+template <int EPI, bool PAIR>
+__device__ __forceinline__ void gemm_nt_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
+                                             const GemmArgs& g) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;   // 1024-byte aligned (no static shared memory in this kernel): SWIZZLE_128B requirement
+  if (smem_u32(smem) & 1023u) __trap();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int a_bytes = BM * 128;
-  const int b_bytes = g.BN * 128;
+  const int b_bytes = (PAIR ? g.BN / 2 : g.BN) * 128;
   const int stage_bytes = a_bytes + b_bytes;
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + g.stages * stage_bytes);
+  uint8_t* cstage = smem + g.stages * stage_bytes;                 // 8 warp slabs (1024-byte aligned)
+  uint64_t* full = reinterpret_cast<uint64_t*>(cstage + 8 * g.slab_bytes);
   uint64_t* empty = full + g.stages;
   uint64_t* tmem_full = empty + g.stages;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;     // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   float* bias_s = reinterpret_cast<float*>(tmem_slot + 4);  // [2][256] (one per accumulator stage)
 
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const int worker = PAIR ? (blockIdx.x >> 1) : blockIdx.x;
+  const int num_workers = PAIR ? (gridDim.x >> 1) : gridDim.x;
+  constexpr int TM = PAIR ? 2 * BM : BM;    // tile rows
   const int num_kb = g.K / BK;
-  const int m_tiles = (g.M + BM - 1) / BM;
+  const int m_tiles = (g.M + TM - 1) / TM;
   const int num_tiles = m_tiles * g.n_tiles;
   const uint32_t ncols = tmem_cols_pow2(2 * g.BN);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (g.slab_bytes) tma_prefetch_desc(&tmC);
     for (int s = 0; s < g.stages; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], 4);  // one arrival per epilogue warp
+      mbar_init(&tmem_empty[a], PAIR ? 16 : 8);  // one arrival per epilogue warp (of both CTAs; leader's copy is used)
     }
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, ncols);
-    tmem_relinquish();
+    if constexpr (PAIR) { tmem_alloc_pair(tmem_slot, ncols); tmem_relinquish_pair(); }
+    else { tmem_alloc(tmem_slot, ncols); tmem_relinquish(); }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -169,35 +203,48 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      for (int t = worker; t < num_tiles; t += num_workers) {
         const int n_tile = t % g.n_tiles, m_tile = t / g.n_tiles;
         const int kb0 = g.kb_begin[n_tile & 15], kb1 = g.kb_end[n_tile & 15] ? g.kb_end[n_tile & 15] : num_kb;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty[s], ph ^ 1);
           uint8_t* sa = smem + s * stage_bytes;
-          mbar_expect_tx(&full[s], stage_bytes);
-          tma_load_2d(sa, &tmA, &full[s], kb * BK, m_tile * BM);
-          tma_load_2d(sa + a_bytes, &tmB, &full[s], kb * BK, n_tile * g.BN);
+          if constexpr (PAIR) {
+            if (rank == 0) mbar_expect_tx(&full[s], 2 * stage_bytes);  // both CTAs' bytes land on the leader's barrier
+            tma_load_2d_pair(sa, &tmA, &full[s], kb * BK, m_tile * TM + static_cast<int>(rank) * BM);
+            tma_load_2d_pair(sa + a_bytes, &tmB, &full[s], kb * BK,
+                             n_tile * g.BN + static_cast<int>(rank) * (g.BN / 2));
+          } else {
+            mbar_expect_tx(&full[s], stage_bytes);
+            tma_load_2d(sa, &tmA, &full[s], kb * BK, m_tile * BM);
+            tma_load_2d(sa + a_bytes, &tmB, &full[s], kb * BK, n_tile * g.BN);
+          }
           if (++s == g.stages) { s = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(BM, g.BN, false, false);
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc = umma_idesc_bf16(TM, g.BN, false, false);
       int s = 0;
       uint32_t ph = 0;
       int it = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      long long pw_tmem = 0, pw_full = 0;
+      const long long pt0 = g.prof ? clock64() : 0;
+      for (int t = worker; t < num_tiles; t += num_workers, ++it) {
         const int acc = it & 1;
         const uint32_t acc_ph = (it >> 1) & 1;
+        long long t0 = g.prof ? clock64() : 0;
         mbar_wait(&tmem_empty[acc], acc_ph ^ 1);  // epilogue has drained this accumulator stage
+        if (g.prof) { pw_tmem += clock64() - t0; }
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * g.BN;
         const int n_tile = t % g.n_tiles;
         const int kb0 = g.kb_begin[n_tile & 15], kb1 = g.kb_end[n_tile & 15] ? g.kb_end[n_tile & 15] : num_kb;
         for (int kb = kb0; kb < kb1; ++kb) {
+          t0 = g.prof ? clock64() : 0;
           mbar_wait(&full[s], ph);
+          if (g.prof) { pw_full += clock64() - t0; }
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
           const uint32_t b_addr = a_addr + a_bytes;
@@ -205,91 +252,211 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int k = 0; k < BK / UMMA_K; ++k) {
             const uint64_t ad = umma_desc_sw128(a_addr + k * (UMMA_K * 2), 16, 1024);
             const uint64_t bd = umma_desc_sw128(b_addr + k * (UMMA_K * 2), 16, 1024);
-            umma_f16(tmem_d, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if constexpr (PAIR) umma_f16_pair(tmem_d, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            else umma_f16(tmem_d, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty[s]);  // frees the smem stage when these MMAs retire
+          // free the smem stage (in both CTAs of a pair) when these MMAs retire
+          if constexpr (PAIR) umma_commit_pair(&empty[s], 3); else umma_commit(&empty[s]);
           if (++s == g.stages) { s = 0; ph ^= 1; }
         }
-        umma_commit(&tmem_full[acc]);
+        if constexpr (PAIR) umma_commit_pair(&tmem_full[acc], 3); else umma_commit(&tmem_full[acc]);
+      }
+      if (g.prof) {
+        g.prof[blockIdx.x * 8 + 0] = clock64() - pt0;
+        g.prof[blockIdx.x * 8 + 1] = pw_tmem;
+        g.prof[blockIdx.x * 8 + 2] = pw_full;
+        g.prof[blockIdx.x * 8 + 3] = it;
       }
     }
   } else {
-    const int q = warp & 3;  // TMEM lane quadrant this warp may read
-    const int et = threadIdx.x - 64;  // 0..127
+    // 8 epilogue warps: warp w reads TMEM lanes (w % 4) * 32.., and of the tile's BN columns the half (w - 2) / 4
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int et = threadIdx.x - 64;  // 0..255
+    constexpr int panel_w = (EPI == NFK_EPI_F32) ? 32 : 64;   // columns per 128-byte staging panel
+    const bool split = (g.BN % (2 * panel_w)) == 0;            // both halves get whole panels (and whole mask words)
+    const int c_begin = split ? half * (g.BN / 2) : 0;
+    const int c_end = split ? c_begin + g.BN / 2 : (half == 0 ? g.BN : 0);
+    uint8_t* slab = g.slab_bytes ? cstage + (warp - 2) * g.slab_bytes : nullptr;   // ONE panel: 32 rows x 128 B
+    const bool want_bits = g.mask_out != nullptr;
+    // bias-gradient column sums (EPI_MASK): lane owns the column pair (lane>>2)*8 + (lane&3)*2 of each 64-col panel;
+    // accumulated over this CTA's tiles while they share one n-tile, flushed with one atomic per column at the end
+    float cs[4][2] = {};
+    int cs_ntile = -1;
+    auto flush_colsum = [&]() {
+      if (cs_ntile < 0) return;
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        const int col = cs_ntile * g.BN + c_begin + p * 64 + (lane >> 2) * 8 + (lane & 3) * 2;
+        if (c_begin + p * 64 < c_end && col < g.N) {
+          atomicAdd(g.colsum + col, cs[p][0]);
+          atomicAdd(g.colsum + col + 1, cs[p][1]);
+        }
+        cs[p][0] = cs[p][1] = 0.f;
+      }
+    };
+    // 1-bit ReLU mask words of a tile (EPI_MASK), fetched one tile ahead so their HBM latency is never exposed
+    auto load_mask = [&](int t, uint32_t (&mb)[4]) {
+      const int n_tile = t % g.n_tiles, m_tile = t / g.n_tiles;
+      const long long row = static_cast<long long>(m_tile) * TM + rank * BM + q * 32 + lane;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = c_begin + 32 * j;
+        const int col = n_tile * g.BN + c;
+        mb[j] = (t < num_tiles && row < g.M && c < c_end && col < g.N)
+                    ? __ldg(g.mask_in + static_cast<long long>(col >> 5) * g.ldmask + row) : 0u;
+      }
+    };
+    uint32_t mbits[4] = {0, 0, 0, 0}, mnext[4] = {0, 0, 0, 0};
+    if constexpr (EPI == NFK_EPI_MASK_BF16) load_mask(worker, mnext);
     int it = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+    long long ew_full = 0, ew_work = 0;
+    for (int t = worker; t < num_tiles; t += num_workers, ++it) {
       const int n_tile = t % g.n_tiles, m_tile = t / g.n_tiles;
       const int acc = it & 1;
       const uint32_t acc_ph = (it >> 1) & 1;
       float* bs = bias_s + acc * 256;
       if (EPI != NFK_EPI_MASK_BF16 && g.bias) {
         // stage this tile's bias slice; the named barrier also orders it against the previous use of this stage
-        for (int c = et; c < g.BN; c += 128) {
+        for (int c = et; c < g.BN; c += 256) {
           const int col = n_tile * g.BN + c;
           bs[c] = col < g.N ? __ldg(g.bias + col) : 0.f;
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
       }
-      const long long row = static_cast<long long>(m_tile) * BM + q * 32 + lane;
+      const long long row0 = static_cast<long long>(m_tile) * TM + rank * BM + q * 32;
+      const long long row = row0 + lane;
       const bool row_ok = row < g.M;
-      uint4 ma[4], mb[4];
-      auto load_mask = [&](int c, uint4 (&mk)[4]) {
-        const int col = n_tile * g.BN + c;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          mk[j] = make_uint4(0, 0, 0, 0);
-          if (row_ok && c + 8 * j < g.BN && col + 8 * j < g.N)
-            mk[j] = __ldg(reinterpret_cast<const uint4*>(g.aux + row * g.ldaux + col + 8 * j));
-        }
-      };
       if constexpr (EPI == NFK_EPI_MASK_BF16) {
-        load_mask(0, ma);
-        load_mask(32, mb);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) mbits[j] = mnext[j];
+        load_mask(t + num_workers, mnext);
+        if (g.colsum && slab && cs_ntile != n_tile) { flush_colsum(); cs_ntile = n_tile; }
       }
+      long long e0 = g.prof ? clock64() : 0;
       mbar_wait(&tmem_full[acc], acc_ph);
+      if (g.prof) { ew_full += clock64() - e0; e0 = clock64(); }
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * g.BN;
-      auto do32 = [&](int c, const uint4 (&mk)[4]) {
-        uint32_t r0[16], r1[16];
-        const bool two = c + 16 < g.BN;
-        tmem_ld16(taddr + c, r0);
-        if (two) tmem_ld16(taddr + c + 16, r1);
-        tmem_ld_wait();
-        const int col = n_tile * g.BN + c;
-        if (col < g.N) nt_epilogue_16<EPI>(g, r0, row, row_ok, col, c, bs, lane, mk[0], mk[1]);
-        if (two && col + 16 < g.N) nt_epilogue_16<EPI>(g, r1, row, row_ok, col + 16, c + 16, bs, lane, mk[2], mk[3]);
-      };
-      if constexpr (EPI == NFK_EPI_MASK_BF16) {
-        // the ReLU mask comes from HBM with a row stride of ldaux: keep two 32-column groups of it in flight
-        // (issued before the accumulator is even complete) so the epilogue never waits on a cold load
-        for (int c = 0; c < g.BN; c += 64) {
-          do32(c, ma);
-          if (c + 64 < g.BN) load_mask(c + 64, ma);
-          if (c + 32 < g.BN) {
-            do32(c + 32, mb);
-            if (c + 96 < g.BN) load_mask(c + 96, mb);
+      // one staging panel per pass: drain -> (column sums) -> fence -> TMA store; the slab is reused by the next pass
+      // once the previous bulk store has finished reading it
+      const int pass_w = slab ? panel_w : (c_end - c_begin);
+#pragma unroll 1
+      for (int pc = c_begin; pc < c_end; pc += pass_w) {
+        if (slab) {
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          __syncwarp();
+        }
+        const int pe = min(pc + pass_w, c_end);
+#pragma unroll 1
+        for (int c = pc; c < pe; c += 32) {
+          uint32_t r0[16], r1[16];
+          const bool two = c + 16 < pe;
+          tmem_ld16(taddr + c, r0);
+          if (two) tmem_ld16(taddr + c + 16, r1);
+          tmem_ld_wait();
+          const int col = n_tile * g.BN + c;
+          uint32_t bits = 0, relu_bits = 0;
+          if constexpr (EPI == NFK_EPI_MASK_BF16) {   // consume word 0, rotate (no dynamic register indexing)
+            bits = mbits[0];
+            mbits[0] = mbits[1]; mbits[1] = mbits[2]; mbits[2] = mbits[3];
+          }
+          if (col < g.N)
+            nt_epilogue_16<EPI>(g, r0, row, row_ok, col, c, c - pc, bs, lane, bits & 0xFFFFu, slab, want_bits,
+                                relu_bits);
+          if (two && col + 16 < g.N)
+            nt_epilogue_16<EPI>(g, r1, row, row_ok, col + 16, c + 16, c + 16 - pc, bs, lane, bits >> 16, slab,
+                                want_bits, relu_bits);
+          if constexpr (EPI == NFK_EPI_BIAS_RELU_BF16) {
+            if (want_bits && row_ok && col < g.N)
+              g.mask_out[static_cast<long long>(col >> 5) * g.ldmask + row] = relu_bits;   // word-major: coalesced
           }
         }
-      } else {
-        const uint4 none[4] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0),
-                               make_uint4(0, 0, 0, 0)};
-        for (int c = 0; c < g.BN; c += 32) do32(c, none);
+        if (pe == c_end) {   // last TMEM read of this tile is done: hand the accumulator stage back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if constexpr (PAIR) mbar_arrive_cluster(&tmem_empty[acc], 0); else mbar_arrive(&tmem_empty[acc]);
+          }
+        }
+        if (slab) {
+          __syncwarp();
+          if constexpr (EPI == NFK_EPI_MASK_BF16) {
+            if (g.colsum) {
+              // column sums straight from the staged bf16 panel: at row r the 32 lanes read the whole 128-byte row
+              // (conflict-free); rows outside the matrix were staged as zeros
+              const uint8_t* pb = slab + (lane & 3) * 4;
+              const uint32_t chunk = static_cast<uint32_t>(lane >> 2);
+              float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+#pragma unroll 8
+              for (int r = 0; r < 32; r += 2) {
+                const uint32_t w0 = *reinterpret_cast<const uint32_t*>(pb + r * 128 + ((chunk ^ (r & 7)) << 4));
+                const uint32_t w1 =
+                    *reinterpret_cast<const uint32_t*>(pb + (r + 1) * 128 + ((chunk ^ ((r + 1) & 7)) << 4));
+                a0 += __uint_as_float(w0 << 16);
+                a1 += __uint_as_float(w0 & 0xFFFF0000u);
+                b0 += __uint_as_float(w1 << 16);
+                b1 += __uint_as_float(w1 & 0xFFFF0000u);
+              }
+              const int p = (pc - c_begin) / 64;
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                if (k == p) { cs[k][0] += a0 + b0; cs[k][1] += a1 + b1; }
+            }
+          }
+          fence_proxy_async();   // generic-proxy smem writes -> visible to the TMA (async proxy)
+          __syncwarp();
+          const int col = n_tile * g.BN + pc;
+          if (lane == 0 && row0 < g.M && col < g.N) {
+            tma_store_2d(slab, &tmC, col, static_cast<int>(row0));
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (c_begin >= c_end) {   // idle half (tile too narrow to split): still part of the accumulator hand-back
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (PAIR) mbar_arrive_cluster(&tmem_empty[acc], 0); else mbar_arrive(&tmem_empty[acc]);
+        }
+      }
+      if (g.prof) ew_work += clock64() - e0;
+    }
+    if constexpr (EPI == NFK_EPI_MASK_BF16) {
+      if (g.colsum && slab) flush_colsum();
+    }
+    if (slab && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (g.prof && warp == 2 && lane == 0) {
+      g.prof[blockIdx.x * 8 + 4] = ew_full;
+      g.prof[blockIdx.x * 8 + 5] = ew_work;
     }
   }
   tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, ncols);
+  if constexpr (PAIR) cluster_sync_all(); else __syncthreads();
+  if (warp == 1) {
+    if constexpr (PAIR) tmem_dealloc_pair(tmem_base, ncols); else tmem_dealloc(tmem_base, ncols);
+  }
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmC, const GemmArgs g) {
+  gemm_nt_body<EPI, false>(tmA, tmB, tmC, g);
+}
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm_nt_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmC, const GemmArgs g) {
+  gemm_nt_body<EPI, true>(tmA, tmB, tmC, g);
 }
 
 // ------------------------------------------------------------------------------------------------ TN kernel
 // out[Mo, No] (fp32, pre-zeroed) += sum over this CTA's pixel range of A[k, m] * B[k, n].
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(TN_THREADS, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
-  extern __shared__ uint8_t smem_raw[];
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int BOX = 64 * 128;  // one TMA box: 64 pixel rows x 64 channels (128 B)
@@ -412,20 +579,27 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// Row-major bf16 matrix [rows, cols] with leading dimension ld (elements); box = 64 columns x box_rows rows.
-static int make_tmap_bf16(CUtensorMap* m, const void* ptr, uint64_t cols, uint64_t rows, uint64_t ld,
-                          uint32_t box_rows) {
+// Row-major matrix [rows, cols] with leading dimension ld (elements); box = 128 bytes of columns x box_rows rows.
+static int make_tmap(CUtensorMap* m, const void* ptr, uint64_t cols, uint64_t rows, uint64_t ld, uint32_t box_rows,
+                     bool f32) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return NFK_ERR_DRIVER;
-  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (ld * 2) % 16) return NFK_ERR_ALIGN;
+  const uint64_t es = f32 ? 4 : 2;
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (ld * es) % 16) return NFK_ERR_ALIGN;
   cuuint64_t dims[2] = {cols, rows};
-  cuuint64_t strides[1] = {ld * 2};
-  cuuint32_t box[2] = {64, box_rows};
+  cuuint64_t strides[1] = {ld * es};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(128 / es), box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+  CUresult r = enc(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                   const_cast<void*>(ptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? NFK_OK : NFK_ERR_DRIVER;
+}
+
+static int make_tmap_bf16(CUtensorMap* m, const void* ptr, uint64_t cols, uint64_t rows, uint64_t ld,
+                          uint32_t box_rows) {
+  return make_tmap(m, ptr, cols, rows, ld, box_rows, false);
 }
 
 static int num_sms() {
@@ -436,6 +610,17 @@ static int num_sms() {
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
   }
   return n;
+}
+
+static long long* g_prof_buffer = nullptr;   // set by nfk_gemm_set_prof (diagnostics only)
+
+static bool use_pairs() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("NFK_GEMM_PAIRS");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
 }
 
 static int pick_bn(int N, int cap) {
@@ -471,6 +656,11 @@ extern "C" int nfk_gemm_nt_bf16(const void* A, long long lda, const void* B, lon
                         stream);
 }
 
+extern "C" int nfk_gemm_set_prof(void* buf) {
+  g_prof_buffer = static_cast<long long*>(buf);
+  return NFK_OK;
+}
+
 extern "C" int nfk_gemm_nt_bf16_ranged(const void* A, long long lda, const void* B, long long ldb, int M, int N,
                                        int K, int epi, void* out, long long ldo, const float* bias, const void* aux,
                                        long long ldaux, float* colsum, int bn, const int* kb_begin,
@@ -486,49 +676,79 @@ static int gemm_nt_launch(const void* A, long long lda, const void* B, long long
   if (M <= 0 || N <= 0 || K <= 0) return NFK_ERR_SHAPE;
   if (K % BK || N % 16 || ldo % 8) return NFK_ERR_SHAPE;
   if (epi == NFK_EPI_BIAS_RELU_BF16 && !bias) return NFK_ERR_ARG;
-  if (epi == NFK_EPI_MASK_BF16 && (!aux || ldaux % 8)) return NFK_ERR_ARG;
+  if (epi == NFK_EPI_MASK_BF16 && (!aux || ldaux < M)) return NFK_ERR_ARG;
+  if (epi == NFK_EPI_BIAS_RELU_BF16 && aux && ldaux < M) return NFK_ERR_ARG;
+  const bool f32 = epi == NFK_EPI_F32;
+  // TMA-store epilogue needs whole 128-byte panels per tile: 64 bf16 / 32 fp32 columns
+  const int panel = f32 ? 32 : 64;
+  const bool staged = N % panel == 0 && (!bn_force || bn_force % panel == 0);
   GemmArgs g{};
   g.M = M; g.N = N; g.K = K;
-  g.BN = pick_bn(N, 256);
+  const int cap = f32 ? 128 : 256;   // fp32 tiles are twice as wide in bytes: keep the staging slabs at <= 64 KB
+  if (staged) {
+    g.BN = N <= cap ? N : cap;
+    if (N > cap && N % cap) {        // e.g. N = 448: 256 + 192, prefer an even split when it wastes nothing
+      for (int bn = cap; bn >= 64; bn -= panel)
+        if (N % bn == 0) { g.BN = bn; break; }
+    }
+  } else {
+    g.BN = pick_bn(N, cap);
+  }
   // few row tiles (small images x small batch): narrower accumulator tiles so the grid still covers the SMs
   const int m_tiles = (M + BM - 1) / BM;
-  while (m_tiles * ((N + g.BN - 1) / g.BN) < 148 && g.BN >= 128 && g.BN % 32 == 0) g.BN /= 2;
+  while (m_tiles * ((N + g.BN - 1) / g.BN) < 148 && g.BN >= 128 && g.BN % (2 * panel) == 0) g.BN /= 2;
   if (bn_force) g.BN = bn_force;
   g.n_tiles = (N + g.BN - 1) / g.BN;
+  if (g.n_tiles > 16 && kb_begin) return NFK_ERR_ARG;
   if (kb_begin)
     for (int i = 0; i < g.n_tiles && i < 16; ++i) {
       if (kb_begin[i] < 0 || kb_end[i] > K / BK || kb_begin[i] >= kb_end[i]) return NFK_ERR_ARG;
       g.kb_begin[i] = static_cast<short>(kb_begin[i]);
       g.kb_end[i] = static_cast<short>(kb_end[i]);
     }
-  const int stage_bytes = BM * 128 + g.BN * 128;
-  g.stages = min(8, (194 * 1024) / stage_bytes);
+  const int m_tiles2 = (M + 2 * BM - 1) / (2 * BM);
+  // CTA pairs once there are enough 256-row tiles to give every pair of SMs work (and B halves stay swizzle-aligned)
+  const bool pair = use_pairs() && g.BN % 32 == 0 && m_tiles2 * g.n_tiles >= num_sms() / 2;
+  const int stage_bytes = BM * 128 + (pair ? g.BN / 2 : g.BN) * 128;
+  // 8 epilogue warps, each with ONE 32-row x 128-byte staging panel that it refills once per 128 bytes of columns
+  g.slab_bytes = staged ? 4096 : 0;
+  const int fixed = 8 * g.slab_bytes + 256 + 2 * 256 * 4;
+  g.stages = min(8, (227 * 1024 - fixed) / stage_bytes);
+  if (g.stages < 2) return NFK_ERR_SHAPE;
   g.out = out; g.ldo = ldo; g.bias = bias;
-  g.aux = static_cast<const __nv_bfloat16*>(aux); g.ldaux = ldaux; g.colsum = colsum;
-  CUtensorMap tmA, tmB;
+  g.mask_out = epi == NFK_EPI_BIAS_RELU_BF16 ? static_cast<uint32_t*>(const_cast<void*>(aux)) : nullptr;
+  g.mask_in = epi == NFK_EPI_MASK_BF16 ? static_cast<const uint32_t*>(aux) : nullptr;
+  g.ldmask = ldaux; g.colsum = colsum;
+  g.prof = g_prof_buffer;
+  CUtensorMap tmA, tmB, tmC;
   int rc;
   if ((rc = make_tmap_bf16(&tmA, A, K, M, lda, BM)) != NFK_OK) return rc;
-  if ((rc = make_tmap_bf16(&tmB, B, K, N, ldb, g.BN)) != NFK_OK) return rc;
-  const int smem = g.stages * stage_bytes + 1024 + 256 + 2 * 256 * 4;
-  const int tiles = m_tiles * g.n_tiles;
-  const dim3 grid(tiles < num_sms() ? tiles : num_sms());
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  switch (epi) {
-    case NFK_EPI_F32:
-      if ((rc = set_smem(gemm_nt_kernel<NFK_EPI_F32>, smem))) return rc;
-      gemm_nt_kernel<NFK_EPI_F32><<<grid, GEMM_THREADS, smem, st>>>(tmA, tmB, g);
-      break;
-    case NFK_EPI_BIAS_RELU_BF16:
-      if ((rc = set_smem(gemm_nt_kernel<NFK_EPI_BIAS_RELU_BF16>, smem))) return rc;
-      gemm_nt_kernel<NFK_EPI_BIAS_RELU_BF16><<<grid, GEMM_THREADS, smem, st>>>(tmA, tmB, g);
-      break;
-    case NFK_EPI_MASK_BF16:
-      if ((rc = set_smem(gemm_nt_kernel<NFK_EPI_MASK_BF16>, smem))) return rc;
-      gemm_nt_kernel<NFK_EPI_MASK_BF16><<<grid, GEMM_THREADS, smem, st>>>(tmA, tmB, g);
-      break;
-    default:
-      return NFK_ERR_ARG;
+  if ((rc = make_tmap_bf16(&tmB, B, K, N, ldb, pair ? g.BN / 2 : g.BN)) != NFK_OK) return rc;
+  if (staged) {
+    if ((rc = make_tmap(&tmC, out, N, M, ldo, 32, f32)) != NFK_OK) return rc;
+  } else {
+    tmC = tmA;
   }
+  const int smem = g.stages * stage_bytes + fixed;
+  const int tiles = (pair ? m_tiles2 : m_tiles) * g.n_tiles;
+  const int sms = num_sms();
+  const dim3 grid(pair ? 2 * (tiles < sms / 2 ? tiles : sms / 2) : (tiles < sms ? tiles : sms));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define NFK_LAUNCH_NT(E)                                                                     \
+  if (pair) {                                                                                \
+    if ((rc = set_smem(gemm_nt_pair_kernel<E>, smem))) return rc;                            \
+    gemm_nt_pair_kernel<E><<<grid, GEMM_THREADS, smem, st>>>(tmA, tmB, tmC, g);              \
+  } else {                                                                                   \
+    if ((rc = set_smem(gemm_nt_kernel<E>, smem))) return rc;                                 \
+    gemm_nt_kernel<E><<<grid, GEMM_THREADS, smem, st>>>(tmA, tmB, tmC, g);                   \
+  }
+  switch (epi) {
+    case NFK_EPI_F32: NFK_LAUNCH_NT(NFK_EPI_F32); break;
+    case NFK_EPI_BIAS_RELU_BF16: NFK_LAUNCH_NT(NFK_EPI_BIAS_RELU_BF16); break;
+    case NFK_EPI_MASK_BF16: NFK_LAUNCH_NT(NFK_EPI_MASK_BF16); break;
+    default: return NFK_ERR_ARG;
+  }
+#undef NFK_LAUNCH_NT
   return cudaGetLastError() == cudaSuccess ? NFK_OK : NFK_ERR_LAUNCH;
 }
 
@@ -556,6 +776,6 @@ extern "C" int nfk_gemm_tn_bf16(const void* A, long long lda, const void* B, lon
   const int smem = g.stages * stage_bytes + 1024 + 256;
   if ((rc = set_smem(gemm_tn_kernel, smem))) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  gemm_tn_kernel<<<dim3(tiles, splits), GEMM_THREADS, smem, st>>>(tmA, tmB, g);
+  gemm_tn_kernel<<<dim3(tiles, splits), TN_THREADS, smem, st>>>(tmA, tmB, g);
   return cudaGetLastError() == cudaSuccess ? NFK_OK : NFK_ERR_LAUNCH;
 }

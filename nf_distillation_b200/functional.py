@@ -62,13 +62,15 @@ def build_coupling_ops(cw, cin, hid, cout, with_t):
 def _coupling_net(col, k: StepConsts, M, hid, K1p, K3p, keep):
     """conv3x3 -> ReLU -> conv1x1 -> ReLU -> per-tap products of the last conv3x3, all on tcgen05."""
     dev = col.device
+    m1 = ops.relu_mask_like(M, hid, dev) if keep else None      # 1-bit ReLU masks for the backward epilogues
+    m2 = ops.relu_mask_like(M, hid, dev) if keep else None
     h1 = torch.empty(M, hid, device=dev, dtype=BF16)
-    ops.gemm_nt(col, k.B1, M, hid, K1p, ops.EPI_BIAS_RELU_BF16, h1, bias=k.bias1)
+    ops.gemm_nt(col, k.B1, M, hid, K1p, ops.EPI_BIAS_RELU_BF16, h1, bias=k.bias1, aux=m1)
     h2 = torch.empty(M, hid, device=dev, dtype=BF16)
-    ops.gemm_nt(h1, k.B2, M, hid, hid, ops.EPI_BIAS_RELU_BF16, h2, bias=k.bias2)
+    ops.gemm_nt(h1, k.B2, M, hid, hid, ops.EPI_BIAS_RELU_BF16, h2, bias=k.bias2, aux=m2)
     P = torch.empty(M, K3p, device=dev, dtype=F32)
     ops.gemm_nt(h2, k.B3, M, K3p, hid, ops.EPI_F32, P)
-    return (h1, h2, P) if keep else (None, None, P)
+    return (h1, h2, P, m1, m2) if keep else (None, None, P, None, None)
 
 
 def flowstep2d_forward(x, ld_in, k: StepConsts, hid, keep):
@@ -81,10 +83,10 @@ def flowstep2d_forward(x, ld_in, k: StepConsts, hid, keep):
     col = torch.empty(M, K1p, device=dev, dtype=BF16)
     ld_out = torch.empty(B, device=dev, dtype=F32)
     ops.affine1x1_fwd(x, k.Wf, k.bf, k.sl, y, col, K1p, ld_in, ld_out, B, C, H, W)
-    h1, h2, P = _coupling_net(col, k, M, hid, K1p, K3p, keep)
+    h1, h2, P, m1, m2 = _coupling_net(col, k, M, hid, K1p, K3p, keep)
     hsave = torch.empty(M, C, device=dev, dtype=F32) if keep else None
     ops.coupling_fwd(P, K3p, k.bias3, y, hsave, ld_out, B, C, H, W, reverse=False)
-    return y, ld_out, (col, h1, h2, hsave)
+    return y, ld_out, (col, h1, h2, hsave, m1, m2)
 
 
 def flowstep2d_reverse(z, ld_in, k: StepConsts, hid):
@@ -96,7 +98,7 @@ def flowstep2d_reverse(z, ld_in, k: StepConsts, hid):
     dev = z.device
     col = torch.empty(M, K1p, device=dev, dtype=BF16)
     ops.affine1x1_fwd(z, None, None, None, None, col, K1p, None, None, B, C, H, W)   # im2col of z1 only
-    _, _, P = _coupling_net(col, k, M, hid, K1p, K3p, keep=False)
+    _, _, P, _, _ = _coupling_net(col, k, M, hid, K1p, K3p, keep=False)
     zc = z.clone()
     ld_mid = ld_in.clone()
     ops.coupling_fwd(P, K3p, k.bias3, zc, None, ld_mid, B, C, H, W, reverse=True)
@@ -117,16 +119,15 @@ class FlowStep2dFn(torch.autograd.Function):
         Wf, bf, sl = build_affine(an_bias, an_logs, (lower, upper, log_s, p, sign_s, None), C, False, False)
         cw = (w1, b1, l1, w2, b2, l2, w3, b3, l3)
         k = StepConsts(Wf, bf, sl, *build_coupling_ops(cw, C // 2, hid, C, True))
-        y, ld_out, (col, h1, h2, hsave) = flowstep2d_forward(x, ld_in.contiguous(), k, hid, keep=True)
+        y, ld_out, (col, h1, h2, hsave, m1, m2) = flowstep2d_forward(x, ld_in.contiguous(), k, hid, keep=True)
         ctx.hid = hid
-        ctx.save_for_backward(x, y, col, h1, h2, hsave, Wf, k.B1T, k.B2T, k.B3T, an_bias, an_logs, lower, upper,
-                              log_s, p, sign_s, *cw)
-        ctx.mark_non_differentiable()
+        ctx.save_for_backward(x, y, col, h1, h2, hsave, m1, m2, Wf, k.B1T, k.B2T, k.B3T, an_bias, an_logs, lower,
+                              upper, log_s, p, sign_s, *cw)
         return y, ld_out
 
     @staticmethod
     def backward(ctx, g_out, g_ld):
-        (x, z_out, col, h1, h2, hsave, Wf, B1T, B2T, B3T, an_bias, an_logs, lower, upper, log_s, p, sign_s,
+        (x, z_out, col, h1, h2, hsave, m1, m2, Wf, B1T, B2T, B3T, an_bias, an_logs, lower, upper, log_s, p, sign_s,
          *cw) = ctx.saved_tensors
         hid = ctx.hid
         B, C, H, W = x.shape
@@ -148,10 +149,10 @@ class FlowStep2dFn(torch.autograd.Function):
         dhcol = torch.empty(M, K3p, device=dev, dtype=BF16)
         ops.coupling_bwd(g_out, g_ld, z_out, hsave, dy, dhcol, K3p, dbias3, B, C, H, W)
         dpre2 = torch.empty(M, hid, device=dev, dtype=BF16)
-        ops.gemm_nt(dhcol, B3T, M, hid, K3p, ops.EPI_MASK_BF16, dpre2, aux=h2, colsum=dbias2)
+        ops.gemm_nt(dhcol, B3T, M, hid, K3p, ops.EPI_MASK_BF16, dpre2, aux=m2, colsum=dbias2)
         ops.gemm_tn(dhcol, h2, K3p, hid, M, dB3)
         dpre1 = torch.empty(M, hid, device=dev, dtype=BF16)
-        ops.gemm_nt(dpre2, B2T, M, hid, hid, ops.EPI_MASK_BF16, dpre1, aux=h1, colsum=dbias1)
+        ops.gemm_nt(dpre2, B2T, M, hid, hid, ops.EPI_MASK_BF16, dpre1, aux=m1, colsum=dbias1)
         ops.gemm_tn(dpre2, h1, hid, hid, M, dB2)
         dcol = torch.empty(M, K1p, device=dev, dtype=F32)
         ops.gemm_nt(dpre1, B1T, M, K1p, hid, ops.EPI_F32, dcol)

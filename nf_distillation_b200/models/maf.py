@@ -65,7 +65,7 @@ class _MadeFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_u, g_ld):
         made, flip = ctx.made, ctx.flip
-        x, xb, h1, h2, out, B1T, B2T, B3T = ctx.saved_tensors
+        x, xb, h1, h2, m1, m2, out, B1T, B2T, B3T = ctx.saved_tensors
         D, H, Dp, N3p = made.D, made.H, made.Dp, made.N3p
         B = x.shape[0]
         dev = x.device
@@ -82,11 +82,11 @@ class _MadeFn(torch.autograd.Function):
         dout = torch.empty(B, N3p, device=dev, dtype=BF16)
         ops.made_affine_bwd(x, out, N3p, g_u, g_ld, dx, dout, db3, B, D, flip)
         dpre2 = torch.empty(B, H, device=dev, dtype=BF16)
-        ops.gemm_nt(dout, B3T, B, H, N3p, ops.EPI_MASK_BF16, dpre2, aux=h2, colsum=db2)
+        ops.gemm_nt(dout, B3T, B, H, N3p, ops.EPI_MASK_BF16, dpre2, aux=m2, colsum=db2)
         ops.gemm_tn(dout, h2, N3p, H, B, dB3)
         dpre1 = torch.empty(B, H, device=dev, dtype=BF16)
         kb0, kb1 = made._ranges_t
-        ops.gemm_nt_ranged(dpre2, B2T, B, H, H, ops.EPI_MASK_BF16, dpre1, made.bn, kb0, kb1, aux=h1, colsum=db1)
+        ops.gemm_nt_ranged(dpre2, B2T, B, H, H, ops.EPI_MASK_BF16, dpre1, made.bn, kb0, kb1, aux=m1, colsum=db1)
         ops.gemm_tn(dpre2, h1, H, H, B, dB2)
         dxn = torch.empty(B, Dp, device=dev, dtype=F32)
         ops.gemm_nt(dpre1, B1T, B, Dp, H, ops.EPI_F32, dxn)
@@ -135,19 +135,21 @@ class MADE(nn.Module):
         b3p[:2 * D] = b3
         return B1, B1T, B2, B2T, B3, B3T, b3p
 
-    def _net(self, xb, Bn, ops_, b1, b2):
-        """(mu | alpha) = masked MLP(xb) on the tensor cores; returns h1, h2, out."""
+    def _net(self, xb, Bn, ops_, b1, b2, keep=False):
+        """(mu | alpha) = masked MLP(xb) on the tensor cores; returns h1, h2, out (+ 1-bit ReLU masks if keep)."""
         B1, _, B2, _, B3, _, b3p = ops_
         dev = xb.device
         H, Dp, N3p = self.H, self.Dp, self.N3p
+        m1 = ops.relu_mask_like(Bn, H, dev) if keep else None
+        m2 = ops.relu_mask_like(Bn, H, dev) if keep else None
         h1 = torch.empty(Bn, H, device=dev, dtype=BF16)
-        ops.gemm_nt(xb, B1, Bn, H, Dp, ops.EPI_BIAS_RELU_BF16, h1, bias=b1)
+        ops.gemm_nt(xb, B1, Bn, H, Dp, ops.EPI_BIAS_RELU_BF16, h1, bias=b1, aux=m1)
         h2 = torch.empty(Bn, H, device=dev, dtype=BF16)
         kb0, kb1 = self._ranges
-        ops.gemm_nt_ranged(h1, B2, Bn, H, H, ops.EPI_BIAS_RELU_BF16, h2, self.bn, kb0, kb1, bias=b2)
+        ops.gemm_nt_ranged(h1, B2, Bn, H, H, ops.EPI_BIAS_RELU_BF16, h2, self.bn, kb0, kb1, bias=b2, aux=m2)
         out = torch.empty(Bn, N3p, device=dev, dtype=F32)
         ops.gemm_nt(h2, B3, Bn, N3p, H, ops.EPI_F32, out, bias=b3p)
-        return h1, h2, out
+        return (h1, h2, out, m1, m2) if keep else (h1, h2, out)
 
     def _run_forward(self, x, ld_in, params, flip, keep):
         Bn = x.shape[0]
@@ -155,11 +157,12 @@ class MADE(nn.Module):
         ops_ = self._operands(params, keep)
         xb = torch.empty(Bn, self.Dp, device=dev, dtype=BF16)
         ops.rows_to_bf16(x, Bn, self.D, self.Dp, xb)
-        h1, h2, out = self._net(xb, Bn, ops_, params[1], params[3])
+        res = self._net(xb, Bn, ops_, params[1], params[3], keep)
+        h1, h2, out = res[:3]
         u = torch.empty_like(x)
         ld_out = torch.empty(Bn, device=dev, dtype=F32)
         ops.made_affine_fwd(x, out, self.N3p, u, None, 0, ld_in, ld_out, Bn, self.D, flip)
-        return u, ld_out, ((xb, h1, h2, out, ops_[1], ops_[3], ops_[5]) if keep else None)
+        return u, ld_out, ((xb, h1, h2, res[3], res[4], out, ops_[1], ops_[3], ops_[5]) if keep else None)
 
     def _cached_operands(self):
         key = tuple((p.data_ptr(), p._version) for p in self._params())

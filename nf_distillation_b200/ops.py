@@ -36,9 +36,17 @@ def round_up(x: int, m: int) -> int:
     return (x + m - 1) // m * m
 
 
+def relu_mask_like(M, N, device):
+    """Storage for the 1-bit ReLU mask of an [M, N] activation: int32 words, word-major [ceil(N/32), M] so that the
+    32 rows a warp owns are contiguous (coalesced writes in the forward epilogue, coalesced reads in the dgrad's)."""
+    return torch.empty((N + 31) // 32, M, device=device, dtype=torch.int32)
+
+
 def gemm_nt(A, B, M, N, K, epi, out, bias=None, aux=None, colsum=None):
-    """out[M,N] = A[M,K] @ B[N,K]^T on tcgen05 (bf16 operands, fp32 TMEM accumulate) with a fused epilogue."""
+    """out[M,N] = A[M,K] @ B[N,K]^T on tcgen05 (bf16 operands, fp32 TMEM accumulate) with a fused epilogue.
+    aux = 1-bit ReLU mask (relu_mask_like): written by EPI_BIAS_RELU_BF16 (optional), read by EPI_MASK_BF16."""
     assert A.dtype == torch.bfloat16 and B.dtype == torch.bfloat16
+    assert aux is None or aux.dtype == torch.int32
     _count()
     check(LIB.nfk_gemm_nt_bf16(_p(A), A.stride(0), _p(B), B.stride(0), M, N, K, epi, _p(out), out.stride(0),
                                _p(bias), _p(aux), 0 if aux is None else aux.stride(0), _p(colsum), _st()),

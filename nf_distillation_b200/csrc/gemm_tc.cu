@@ -296,18 +296,18 @@ __device__ __forceinline__ void gemm_nt_body(const CUtensorMap& tmA, const CUten
       }
     };
     // 1-bit ReLU mask words of a tile (EPI_MASK), fetched one tile ahead so their HBM latency is never exposed
-    auto load_mask = [&](int t, uint32_t (&mb)[4]) {
+    auto load_mask = [&](int t, uint32_t (&mb)[8]) {
       const int n_tile = t % g.n_tiles, m_tile = t / g.n_tiles;
       const long long row = static_cast<long long>(m_tile) * TM + rank * BM + q * 32 + lane;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < 8; ++j) {   // up to 8 words: a warp that is not sharing its tile owns all BN <= 256 columns
         const int c = c_begin + 32 * j;
         const int col = n_tile * g.BN + c;
         mb[j] = (t < num_tiles && row < g.M && c < c_end && col < g.N)
                     ? __ldg(g.mask_in + static_cast<long long>(col >> 5) * g.ldmask + row) : 0u;
       }
     };
-    uint32_t mbits[4] = {0, 0, 0, 0}, mnext[4] = {0, 0, 0, 0};
+    uint32_t mbits[8] = {}, mnext[8] = {};
     if constexpr (EPI == NFK_EPI_MASK_BF16) load_mask(worker, mnext);
     int it = 0;
     long long ew_full = 0, ew_work = 0;
@@ -329,7 +329,7 @@ __device__ __forceinline__ void gemm_nt_body(const CUtensorMap& tmA, const CUten
       const bool row_ok = row < g.M;
       if constexpr (EPI == NFK_EPI_MASK_BF16) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) mbits[j] = mnext[j];
+        for (int j = 0; j < 8; ++j) mbits[j] = mnext[j];
         load_mask(t + num_workers, mnext);
         if (g.colsum && slab && cs_ntile != n_tile) { flush_colsum(); cs_ntile = n_tile; }
       }
@@ -359,7 +359,8 @@ __device__ __forceinline__ void gemm_nt_body(const CUtensorMap& tmA, const CUten
           uint32_t bits = 0, relu_bits = 0;
           if constexpr (EPI == NFK_EPI_MASK_BF16) {   // consume word 0, rotate (no dynamic register indexing)
             bits = mbits[0];
-            mbits[0] = mbits[1]; mbits[1] = mbits[2]; mbits[2] = mbits[3];
+#pragma unroll
+            for (int j = 0; j < 7; ++j) mbits[j] = mbits[j + 1];
           }
           if (col < g.N)
             nt_epilogue_16<EPI>(g, r0, row, row_ok, col, c, c - pc, bs, lane, bits & 0xFFFFu, slab, want_bits,

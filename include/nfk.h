@@ -172,6 +172,15 @@ int nfk_made_affine_bwd(const float* x, const float* out, int N3p, const float* 
 int nfk_made_inv_update(float* x, void* xb, int Dp, const float* u_in, const float* out, int N3p, const float* ld_in,
                         float* ld_out, int B, int D, int i, int flip, int last, void* stream);
 
+/* Fused conv#1 -> conv#2 of the coupling network: h2 = relu(relu(col*B1^T + b1)*B2^T + b2) in ONE kernel (CTA
+ * pairs; h1 stays in shared memory as the tcgen05 A operand of conv#2). col [M,K1p] bf16, B1 [512,K1p], B2 [512,512]
+ * bf16 (nfk_coupling_prep), h2 [M,512] bf16. Training additionally passes h1 [M,512] and the two 1-bit ReLU mask
+ * buffers (word-major, [16][ldmask >= M]); inference passes NULL for them. hid must be 512. */
+int nfk_cnet_set_prof(void* buf); /* diagnostics: per-CTA cycle counters of the MMA issuer ([grid][8] int64) or NULL */
+int nfk_cnet_fwd_fused(const void* col, int K1p, const void* B1, const void* B2, const float* bias1,
+                       const float* bias2, void* h1, void* h2, void* mask1, void* mask2, long long ldmask, int M,
+                       int hid, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -5,6 +5,7 @@ fixed sequence of kernel launches; saved tensors are exactly what the matching b
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import Optional
 
@@ -14,6 +15,7 @@ from . import ops
 
 BF16 = torch.bfloat16
 F32 = torch.float32
+USE_FUSED_CNET = os.environ.get("NFK_FUSED_CNET", "1") != "0"
 
 
 # ------------------------------------------------------------------------------------------------ derived weights
@@ -64,10 +66,16 @@ def _coupling_net(col, k: StepConsts, M, hid, K1p, K3p, keep):
     dev = col.device
     m1 = ops.relu_mask_like(M, hid, dev) if keep else None      # 1-bit ReLU masks for the backward epilogues
     m2 = ops.relu_mask_like(M, hid, dev) if keep else None
-    h1 = torch.empty(M, hid, device=dev, dtype=BF16)
-    ops.gemm_nt(col, k.B1, M, hid, K1p, ops.EPI_BIAS_RELU_BF16, h1, bias=k.bias1, aux=m1)
+    h1 = torch.empty(M, hid, device=dev, dtype=BF16) if keep else None
     h2 = torch.empty(M, hid, device=dev, dtype=BF16)
-    ops.gemm_nt(h1, k.B2, M, hid, hid, ops.EPI_BIAS_RELU_BF16, h2, bias=k.bias2, aux=m2)
+    if USE_FUSED_CNET and ops.cnet_fused_supported(hid, K1p) and M >= 8192:
+        # one kernel for conv#1 + conv#2: h1 stays in shared memory (and is only written out when training)
+        ops.cnet_fwd_fused(col, K1p, k.B1, k.B2, k.bias1, k.bias2, h2, M, hid, h1=h1, mask1=m1, mask2=m2)
+    else:
+        if h1 is None:
+            h1 = torch.empty(M, hid, device=dev, dtype=BF16)
+        ops.gemm_nt(col, k.B1, M, hid, K1p, ops.EPI_BIAS_RELU_BF16, h1, bias=k.bias1, aux=m1)
+        ops.gemm_nt(h1, k.B2, M, hid, hid, ops.EPI_BIAS_RELU_BF16, h2, bias=k.bias2, aux=m2)
     P = torch.empty(M, K3p, device=dev, dtype=F32)
     ops.gemm_nt(h2, k.B3, M, K3p, hid, ops.EPI_F32, P)
     return (h1, h2, P, m1, m2) if keep else (None, None, P, None, None)

@@ -252,3 +252,15 @@ def made_inv_update(x, xb, Dp, u_in, out, N3p, ld_in, ld_out, B, D, i, flip, las
     _count()
     check(LIB.nfk_made_inv_update(_p(x), _p(xb), Dp, _p(u_in), _p(out), N3p, _p(ld_in), _p(ld_out), B, D, i,
                                   int(flip), int(last), _st()), "nfk_made_inv_update")
+
+
+def cnet_fused_supported(hid, K1p) -> bool:
+    return hid == 512 and K1p % 64 == 0 and 64 <= K1p <= 512
+
+
+def cnet_fwd_fused(col, K1p, B1, B2, bias1, bias2, h2, M, hid, h1=None, mask1=None, mask2=None):
+    """conv3x3 -> ReLU -> conv1x1 -> ReLU in one kernel: h1 never leaves the SM (training also stores it + masks)."""
+    _count()
+    ldm = 0 if mask1 is None else mask1.stride(0)
+    check(LIB.nfk_cnet_fwd_fused(_p(col), K1p, _p(B1), _p(B2), _p(bias1), _p(bias2), _p(h1), _p(h2), _p(mask1),
+                                 _p(mask2), ldm, M, hid, _st()), "nfk_cnet_fwd_fused")

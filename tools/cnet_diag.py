@@ -1,0 +1,45 @@
+"""Fused conv#1+conv#2 vs the two separate GEMMs: bitwise comparison (h2, and h1 + masks in training mode) + timing."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from nf_distillation_b200 import ops
+from nf_distillation_b200._lib import LIB
+dev = "cuda"
+torch.manual_seed(0)
+for (M, K1p) in ((256, 64), (1000, 64), (65536, 64), (16384, 128), (4096, 256), (262144, 64)):
+    hid = 512
+    col = (torch.randn(M, K1p, device=dev) * 0.5).bfloat16()
+    B1 = (torch.randn(hid, K1p, device=dev) * 0.1).bfloat16()
+    B2 = (torch.randn(hid, hid, device=dev) * 0.05).bfloat16()
+    b1, b2 = torch.randn(hid, device=dev) * 0.1, torch.randn(hid, device=dev) * 0.1
+    h1a = torch.empty(M, hid, device=dev, dtype=torch.bfloat16); h2a = torch.empty_like(h1a)
+    h1b = torch.full_like(h1a, float("nan")); h2b = torch.full_like(h1a, float("nan")); h2c = torch.full_like(h1a, float("nan"))
+    m1a, m2a = ops.relu_mask_like(M, hid, dev), ops.relu_mask_like(M, hid, dev)
+    m1b, m2b = torch.zeros_like(m1a), torch.zeros_like(m2a)
+    def unfused():
+        ops.gemm_nt(col, B1, M, hid, K1p, ops.EPI_BIAS_RELU_BF16, h1a, bias=b1, aux=m1a)
+        ops.gemm_nt(h1a, B2, M, hid, hid, ops.EPI_BIAS_RELU_BF16, h2a, bias=b2, aux=m2a)
+    def fused_train():
+        ops.cnet_fwd_fused(col, K1p, B1, B2, b1, b2, h2b, M, hid, h1=h1b, mask1=m1b, mask2=m2b)
+    def fused():
+        ops.cnet_fwd_fused(col, K1p, B1, B2, b1, b2, h2c, M, hid)
+    unfused(); fused_train(); fused(); torch.cuda.synchronize()
+    ok = (torch.equal(h2a, h2b), torch.equal(h2a, h2c), torch.equal(h1a, h1b), torch.equal(m1a, m1b), torch.equal(m2a, m2b))
+    def t(fn):
+        for _ in range(2): fn()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(10): fn()
+        g.replay(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); g.replay(); e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / 10 * 1e3
+    tu, tf, tt = t(unfused), t(fused), t(fused_train)
+    fl = 2.0 * M * hid * (K1p + hid)
+    print(f"M={M} K1p={K1p}: equal(h2 train, h2 infer, h1, m1, m2)={ok} | unfused {tu:.1f} us, fused {tf:.1f} us ({fl/tf/1e6:.0f} TFLOP/s), fused+save {tt:.1f} us")
+    if M == 262144:
+        prof = torch.zeros(148, 8, device=dev, dtype=torch.int64)
+        LIB.nfk_cnet_set_prof(prof.data_ptr()); fused(); torch.cuda.synchronize(); LIB.nfk_cnet_set_prof(None)
+        p = prof.cpu().double(); p = p[p[:, 0] > 0]
+        names = ["total", "wait operands", "wait acc-free", "wait h1"]
+        print("   MMA issuer cycles per CTA:", {n: int(p[:, i].mean()) for i, n in enumerate(names)}, "tiles/CTA %.1f" % (1024 / 74))

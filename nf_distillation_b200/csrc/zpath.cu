@@ -217,7 +217,11 @@ coupling_fwd_kernel(const float* __restrict__ P, int K3p, const float* __restric
 }
 
 // ------------------------------------------------------------------------------------------ coupling bwd
-// smem: gs[J*ldp] os[J*ldp] dhs[C*ldp] dbs[C] lut[K3p]
+// Persistent CTAs walk groups of `ipc` whole images. Phase 1 (thread = (channel pair, pixel), pixel fastest): gradient
+// of the affine coupling wrt (z2, shift, logit) from the saved h; dh goes to a smem tile. Phase 2 (thread = pixel):
+// the im2col matrix of dh for the dgrad / wgrad GEMMs with compile-time (tap, channel) positions, staged and copied out
+// in 16-byte coalesced chunks. Bias-gradient sums stay in smem across groups: one global atomic per channel and CTA.
+// smem: gs[J*ldp] os[J*ldp] dhs[C*ldp] dbs[C] | cst[pixt * (K3p/8 + 1)] 16-byte chunks
 template <int C>
 __global__ void __launch_bounds__(ZT)
 coupling_bwd_kernel(const float* __restrict__ g_out, const float* __restrict__ g_ld, const float* __restrict__ z_out,
@@ -230,85 +234,104 @@ coupling_bwd_kernel(const float* __restrict__ g_out, const float* __restrict__ g
   float* os = gs + J * ldp;
   float* dhs = os + J * ldp;
   float* dbs = dhs + C * ldp;
-  int* lut = reinterpret_cast<int*>(dbs + C);
+  uint4* cst = reinterpret_cast<uint4*>(dbs + ((C + 3) & ~3) + ((3 * 0)));
   const int tid = threadIdx.x;
-  const int b0 = blockIdx.x * g.ipc;
-  const int nimg = min(g.ipc, g.B - b0);
-  const int npix = nimg * g.HW;
-
+  const int HWm = g.HW - 1, Wm = g.W - 1;
+  const int ngroups = (g.B + g.ipc - 1) / g.ipc;
+  constexpr int K3 = 9 * C;
+  constexpr int NCH = (K3 + 7) / 8;
+  const int r16 = K3p / 8, rs16 = r16 + 1;
+  int noff[9];
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) noff[tap] = -((tap / 3 - 1) * g.W + (tap % 3 - 1));   // P[m'] fed pixel m' - off
   for (int i = tid; i < C; i += ZT) dbs[i] = 0.f;
-  for (int k = tid; k < K3p; k += ZT) {
-    int v = -1;
-    if (k < 9 * C) {
-      const int tap = k / C, co = k % C;
-      v = co | ((tap / 3) << 8) | ((tap % 3) << 10);
+
+  for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+    const int b0 = grp * g.ipc;
+    const int nimg = min(g.ipc, g.B - b0);
+    const int npix = nimg << g.lgHW;
+    __syncthreads();   // previous group's tiles are free (also orders the dbs zeroing)
+    // ---- phase 1
+    for (int i = tid; i < J * npix; i += ZT) {
+      const int jj = i / npix, pl = i - jj * npix;     // pixel fastest (npix is a multiple of 32 or the whole tile)
+      const int img = pl >> g.lgHW, rem = pl & HWm;
+      const long long lo = ((static_cast<long long>(b0 + img) * C + jj) << g.lgHW) + rem;
+      const long long hi = lo + (static_cast<long long>(J) << g.lgHW);
+      const long long m = (static_cast<long long>(b0) << g.lgHW) + pl;
+      dy[lo] = g_out[lo];  // z1 passes through; the coupling-net gradient is added by affine1x1_bwd
+      const float g2 = g_out[hi], o2 = z_out[hi];
+      const float2 h = *reinterpret_cast<const float2*>(hsave + m * C + 2 * jj);
+      float sg, lsv;
+      sigmoid_logsigmoid(h.y + 2.f, sg, lsv);
+      const float dsh = g2 * sg;
+      const float dlg = (g2 * o2 + g_ld[b0 + img]) * (1.f - sg);
+      dy[hi] = dsh;        // dL/dy2
+      dhs[(2 * jj) * ldp + pl] = dsh;
+      dhs[(2 * jj + 1) * ldp + pl] = dlg;
+      // bias gradient: a warp's 32 items share jj whenever npix % 32 == 0 (always for >= 2 images of >= 16 pixels)
+      float a = dsh, bsum = dlg;
+      if ((npix & 31) == 0) {
+        for (int o = 16; o > 0; o >>= 1) {
+          a += __shfl_xor_sync(0xffffffffu, a, o);
+          bsum += __shfl_xor_sync(0xffffffffu, bsum, o);
+        }
+        if ((tid & 31) == 0) { atomicAdd(&dbs[2 * jj], a); atomicAdd(&dbs[2 * jj + 1], bsum); }
+      } else {
+        atomicAdd(&dbs[2 * jj], a);
+        atomicAdd(&dbs[2 * jj + 1], bsum);
+      }
     }
-    lut[k] = v;
-  }
-  for (int i = tid; i < J * npix; i += ZT) {
-    const int img = i / (J * g.HW), r = i - img * J * g.HW;
-    const int j = r / g.HW, p = r - j * g.HW;
-    const long long lo = (static_cast<long long>(b0 + img) * C + j) * g.HW + p;
-    const long long hi = lo + static_cast<long long>(J) * g.HW;
-    dy[lo] = g_out[lo];  // z1 passes through; the coupling-net gradient is added by affine1x1_bwd
-    gs[j * ldp + img * g.HW + p] = g_out[hi];
-    os[j * ldp + img * g.HW + p] = z_out[hi];
-  }
-  __syncthreads();
-  constexpr int PPP = ZT / J;
-  const int j = tid % J, pl0 = tid / J;
-  if (pl0 < PPP) {
-    float a_sh = 0.f, a_lg = 0.f;
-    for (int pl = pl0; pl < npix; pl += PPP) {
-      const int img = pl / g.HW;
-      const long long m = static_cast<long long>(b0) * g.HW + pl;
-      const float2 h = *reinterpret_cast<const float2*>(hsave + m * C + 2 * j);
-      float s, lsv;
-      sigmoid_logsigmoid(h.y + 2.f, s, lsv);
-      const float g2 = gs[j * ldp + pl], o2 = os[j * ldp + pl];
-      const float dsh = g2 * s;
-      const float dlg = (g2 * o2 + g_ld[b0 + img]) * (1.f - s);
-      gs[j * ldp + pl] = dsh;  // = dL/dy2
-      dhs[(2 * j) * ldp + pl] = dsh;
-      dhs[(2 * j + 1) * ldp + pl] = dlg;
-      a_sh += dsh;
-      a_lg += dlg;
+    __syncthreads();
+    // ---- phase 2: im2col rows of dh (thread = pixel, small tiles share a pixel between GR threads)
+    const int GR = g.pixt >= ZT ? 1 : ZT / g.pixt;
+    const int gid = tid / g.pixt;
+    for (int pl = GR > 1 ? (tid & (g.pixt - 1)) : tid; pl < npix; pl += (GR > 1 ? g.pixt : ZT)) {
+      const int rem = pl & HWm;
+      const int yy = rem >> g.lgW, xx = rem & Wm;
+      uint32_t vmask = 0;
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        const int ny = yy - (tap / 3 - 1), nx = xx - (tap % 3 - 1);
+        vmask |= (ny >= 0 && ny < g.H && nx >= 0 && nx < g.W) ? (1u << tap) : 0u;
+      }
+      const float* db = dhs + pl;
+      uint4* drow = cst + pl * rs16;
+#pragma unroll
+      for (int c4 = 0; c4 < NCH; ++c4) {
+        if (GR > 1 && (c4 & (GR - 1)) != gid) continue;
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int k = c4 * 8 + e;
+          if (k < K3) {
+            const int tap = k / C, co = k % C;
+            v[e] = ((vmask >> tap) & 1u) ? db[co * ldp + noff[tap]] : 0.f;
+          } else {
+            v[e] = 0.f;
+          }
+        }
+        drow[c4] = make_uint4(bf2(v[0], v[1]), bf2(v[2], v[3]), bf2(v[4], v[5]), bf2(v[6], v[7]));
+      }
+      for (int c4 = NCH; c4 < r16; ++c4)
+        if (GR == 1 || (c4 & (GR - 1)) == gid) drow[c4] = make_uint4(0u, 0u, 0u, 0u);
     }
-    atomicAdd(&dbs[2 * j], a_sh);
-    atomicAdd(&dbs[2 * j + 1], a_lg);
+    __syncthreads();
+    uint4* out4 = reinterpret_cast<uint4*>(dhcol + (static_cast<long long>(b0) << g.lgHW) * K3p);
+    for (int i = tid; i < npix * r16; i += ZT) {
+      const int pl = i / r16, c4 = i - pl * r16;
+      out4[i] = cst[pl * rs16 + c4];
+    }
   }
   __syncthreads();
   for (int i = tid; i < C; i += ZT) atomicAdd(dbias3 + i, dbs[i]);
-  for (int i = tid; i < J * npix; i += ZT) {
-    const int img = i / (J * g.HW), r = i - img * J * g.HW;
-    const int jj = r / g.HW, p = r - jj * g.HW;
-    dy[(static_cast<long long>(b0 + img) * C + J + jj) * g.HW + p] = gs[jj * ldp + img * g.HW + p];
-  }
-  const int cpr = K3p / 8;
-  const int nchunk = npix * cpr;
-  for (int c = tid; c < nchunk; c += ZT) {
-    const int pl = c / cpr, k0 = (c - pl * cpr) * 8;
-    const int img = pl / g.HW, rem = pl - img * g.HW;
-    const int yy = rem / g.W, xx = rem - yy * g.W;
-    float v[8];
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const int e = lut[k0 + q];
-      float t = 0.f;
-      if (e >= 0) {
-        // P[m', (tap, co)] fed output pixel m' - off(tap): gather dh from there
-        const int co = e & 0xFF, ny = yy - (((e >> 8) & 3) - 1), nx = xx - (((e >> 10) & 3) - 1);
-        if (ny >= 0 && ny < g.H && nx >= 0 && nx < g.W) t = dhs[co * ldp + img * g.HW + ny * g.W + nx];
-      }
-      v[q] = t;
-    }
-    uint4 pk = make_uint4(bf2(v[0], v[1]), bf2(v[2], v[3]), bf2(v[4], v[5]), bf2(v[6], v[7]));
-    *reinterpret_cast<uint4*>(dhcol + (static_cast<long long>(b0) * g.HW + pl) * K3p + k0) = pk;
-  }
 }
 
 // ------------------------------------------------------------------------------------------ affine1x1 bwd
-// smem: Ws[C*C] (W'^T) | dys[C*ldp] | xs[C*ldp] | acc[C*C + C]
+// Persistent CTAs over groups of whole images. col2im of the first conv's input gradient straight from global
+// (thread = (pixel, channel), channel fastest: the CH lanes of a pixel read one contiguous segment per tap),
+// dx = W'^T dy, and dW' / db' accumulated in shared memory across all groups of the CTA (4x4 register blocks),
+// flushed with one global atomic per entry and CTA.
+// smem: WT[C*C] | dys[C*ldp] | xs[C*ldp] | acc[C*C + C]
 template <int C>
 __global__ void __launch_bounds__(ZT)
 affine1x1_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ dcol, int K1p,
@@ -322,33 +345,44 @@ affine1x1_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ dco
   float* xs = dys + C * ldp;
   float* acc = xs + C * ldp;
   const int tid = threadIdx.x;
-  const int b0 = blockIdx.x * g.ipc;
-  const int nimg = min(g.ipc, g.B - b0);
-  const int npix = nimg * g.HW;
+  const int HWm = g.HW - 1, Wm = g.W - 1;
+  const int ngroups = (g.B + g.ipc - 1) / g.ipc;
 
   for (int i = tid; i < C * C; i += ZT) {
     const int o = i / C, c = i % C;
     WT[c * C + o] = Wf[i];
   }
   for (int i = tid; i < C * C + C; i += ZT) acc[i] = 0.f;
-  // coalesced tile loads (p fastest)
-  for (int i = tid; i < C * npix; i += ZT) {
-    const int img = i / (C * g.HW), r = i - img * C * g.HW;
-    const int c = r / g.HW, p = r - c * g.HW;
-    const long long gi = (static_cast<long long>(b0 + img) * C + c) * g.HW + p;
-    xs[c * ldp + img * g.HW + p] = x[gi];
-    dys[c * ldp + img * g.HW + p] = dy[gi];
-  }
-  __syncthreads();
-  // col2im of the first conv's input gradient: dy1[ci, m] += sum_tap dcol[m - off(tap), tap*CH + ci]
-  if (dcol) {
-    constexpr int PPP = ZT / CH;
-    const int ci = tid % CH, pl0 = tid / CH;
-    if (pl0 < PPP) {
-      for (int pl = pl0; pl < npix; pl += PPP) {
-        const int img = pl / g.HW, rem = pl - img * g.HW;
-        const int yy = rem / g.W, xx = rem - yy * g.W;
-        const long long m = static_cast<long long>(b0) * g.HW + pl;
+
+  for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+    const int b0 = grp * g.ipc;
+    const int nimg = min(g.ipc, g.B - b0);
+    const int npix = nimg << g.lgHW;
+    __syncthreads();
+    // coalesced tile loads (pixel fastest)
+    for (int i = tid; i < C * npix; i += ZT) {
+      const int pl = i & (npix - 1) , c = i / npix;             // npix = nimg * HW; nimg may be non-pow2 only at the tail
+      if ((npix & (npix - 1)) != 0) {                           // generic path for a ragged last group
+        const int c2 = i / npix, p2 = i - c2 * npix;
+        const int img = p2 >> g.lgHW, rem = p2 & HWm;
+        const long long gi = ((static_cast<long long>(b0 + img) * C + c2) << g.lgHW) + rem;
+        xs[c2 * ldp + p2] = x[gi];
+        dys[c2 * ldp + p2] = dy[gi];
+      } else {
+        const int img = pl >> g.lgHW, rem = pl & HWm;
+        const long long gi = ((static_cast<long long>(b0 + img) * C + c) << g.lgHW) + rem;
+        xs[c * ldp + pl] = x[gi];
+        dys[c * ldp + pl] = dy[gi];
+      }
+    }
+    __syncthreads();
+    if (dcol) {
+      // dy1[ci, m] += sum_tap dcol[m - off(tap), tap*CH + ci]
+      for (int i = tid; i < CH * npix; i += ZT) {
+        const int pl = i / CH, ci = i - pl * CH;
+        const int rem = pl & HWm;
+        const int yy = rem >> g.lgW, xx = rem & Wm;
+        const long long m = (static_cast<long long>(b0) << g.lgHW) + pl;
         float a = 0.f;
 #pragma unroll
         for (int tap = 0; tap < 9; ++tap) {
@@ -359,64 +393,64 @@ affine1x1_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ dco
         }
         dys[ci * ldp + pl] += a;
       }
+      __syncthreads();
     }
-    __syncthreads();
-  }
-  // dx = W'^T dy
-  for (int pl = tid; pl < npix; pl += ZT) {
-    const int img = pl / g.HW, p = pl - img * g.HW;
-    float dv[C];
+    // dx = W'^T dy
+    for (int pl = tid; pl < npix; pl += ZT) {
+      const int img = pl >> g.lgHW, rem = pl & HWm;
+      float dv[C];
 #pragma unroll
-    for (int o = 0; o < C; ++o) dv[o] = dys[o * ldp + pl];
-    float* dxp = dx + (static_cast<long long>(b0 + img) * C) * g.HW + p;
+      for (int o = 0; o < C; ++o) dv[o] = dys[o * ldp + pl];
+      float* dxp = dx + ((static_cast<long long>(b0 + img) * C) << g.lgHW) + rem;
 #pragma unroll 4
-    for (int i = 0; i < C; ++i) {
-      float a = 0.f;
-      const float4* wr = reinterpret_cast<const float4*>(WT + i * C);
+      for (int i = 0; i < C; ++i) {
+        float a = 0.f;
+        const float4* wr = reinterpret_cast<const float4*>(WT + i * C);
 #pragma unroll
-      for (int o = 0; o < C / 4; ++o) {
-        const float4 w = wr[o];
-        a = fmaf(w.x, dv[4 * o], a);
-        a = fmaf(w.y, dv[4 * o + 1], a);
-        a = fmaf(w.z, dv[4 * o + 2], a);
-        a = fmaf(w.w, dv[4 * o + 3], a);
+        for (int o = 0; o < C / 4; ++o) {
+          const float4 w = wr[o];
+          a = fmaf(w.x, dv[4 * o], a);
+          a = fmaf(w.y, dv[4 * o + 1], a);
+          a = fmaf(w.z, dv[4 * o + 2], a);
+          a = fmaf(w.w, dv[4 * o + 3], a);
+        }
+        dxp[static_cast<long long>(i) << g.lgHW] = a;
       }
-      dxp[static_cast<long long>(i) * g.HW] = a;
     }
-  }
-  // dW'[o][i] += sum_p dy[o][p] x[i][p] with 4x4 register blocks, pixel range split over thread slices
-  constexpr int NBK = (C / 4) * (C / 4);
-  constexpr int SL = NBK >= ZT ? 1 : ZT / NBK;
-  for (int blk = tid % (NBK < ZT ? NBK : ZT); blk < NBK; blk += ZT) {
-    const int slice = NBK < ZT ? tid / NBK : 0;
-    if (slice >= SL) break;
-    const int to = blk / (C / 4), ti = blk % (C / 4);
-    float a[4][4] = {};
-    for (int p = slice; p < npix; p += SL) {
-      float dv[4], xv[4];
+    // dW'[o][i] += sum_p dy[o][p] x[i][p] with 4x4 register blocks, pixel range split over thread slices
+    constexpr int NBK = (C / 4) * (C / 4);
+    constexpr int SL = NBK >= ZT ? 1 : ZT / NBK;
+    for (int blk = tid % (NBK < ZT ? NBK : ZT); blk < NBK; blk += ZT) {
+      const int slice = NBK < ZT ? tid / NBK : 0;
+      if (slice >= SL) break;
+      const int to = blk / (C / 4), ti = blk % (C / 4);
+      float a[4][4] = {};
+      for (int p = slice; p < npix; p += SL) {
+        float dv[4], xv[4];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        dv[q] = dys[(4 * to + q) * ldp + p];
-        xv[q] = xs[(4 * ti + q) * ldp + p];
+        for (int q = 0; q < 4; ++q) {
+          dv[q] = dys[(4 * to + q) * ldp + p];
+          xv[q] = xs[(4 * ti + q) * ldp + p];
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+          for (int r = 0; r < 4; ++r) a[q][r] = fmaf(dv[q], xv[r], a[q][r]);
       }
 #pragma unroll
       for (int q = 0; q < 4; ++q)
 #pragma unroll
-        for (int r = 0; r < 4; ++r) a[q][r] = fmaf(dv[q], xv[r], a[q][r]);
+        for (int r = 0; r < 4; ++r) atomicAdd(&acc[(4 * to + q) * C + 4 * ti + r], a[q][r]);
     }
-#pragma unroll
-    for (int q = 0; q < 4; ++q)
-#pragma unroll
-      for (int r = 0; r < 4; ++r) atomicAdd(&acc[(4 * to + q) * C + 4 * ti + r], a[q][r]);
-  }
-  // db'[o] += sum_p dy[o][p]: one warp per channel
-  {
-    const int warp = tid >> 5, lane = tid & 31;
-    for (int o = warp; o < C; o += ZT / 32) {
-      float a = 0.f;
-      for (int p = lane; p < npix; p += 32) a += dys[o * ldp + p];
-      for (int s = 16; s > 0; s >>= 1) a += __shfl_xor_sync(0xffffffffu, a, s);
-      if (lane == 0) acc[C * C + o] = a;
+    // db'[o] += sum_p dy[o][p]: one warp per channel
+    {
+      const int warp = tid >> 5, lane = tid & 31;
+      for (int o = warp; o < C; o += ZT / 32) {
+        float a = 0.f;
+        for (int p = lane; p < npix; p += 32) a += dys[o * ldp + p];
+        for (int sft = 16; sft > 0; sft >>= 1) a += __shfl_xor_sync(0xffffffffu, a, sft);
+        if (lane == 0) acc[C * C + o] += a;
+      }
     }
   }
   __syncthreads();
@@ -504,11 +538,17 @@ extern "C" int nfk_coupling_fwd(const float* P, int K3p, const float* bias3, flo
 extern "C" int nfk_coupling_bwd(const float* g_out, const float* g_ld, const float* z_out, const float* hsave,
                                 float* dy, void* dhcol, int K3p, float* dbias3, int B, int C, int H, int W,
                                 void* stream) {
-  if (B <= 0 || H <= 0 || W <= 0 || H * W > 4096 || K3p % 64 || K3p < 9 * C) return NFK_ERR_SHAPE;
+  if (B <= 0 || H <= 0 || W <= 0 || H * W > 4096 || K3p % 64 || K3p < 9 * C || !pow2(H) || !pow2(W))
+    return NFK_ERR_SHAPE;
   if (!g_out || !g_ld || !z_out || !hsave || !dy || !dhcol || !dbias3) return NFK_ERR_ARG;
   Geo g = make_geo(B, C, H, W, true);
-  const int smem = (2 * C * (g.pixt + 1) + C + K3p) * 4;
-  const int grid = (B + g.ipc - 1) / g.ipc;
+  // keep tiles + the im2col staging under ~100 KB so two CTAs fit per SM
+  while (g.ipc > 1 && (2LL * C * (g.pixt + 1) * 4 + static_cast<long long>(g.pixt) * (K3p * 2 + 16)) > 100 * 1024) {
+    g.ipc >>= 1; g.pixt = g.ipc * g.HW;
+  }
+  const int smem = (2 * C * (g.pixt + 1) + ((C + 3) & ~3)) * 4 + g.pixt * (K3p / 8 + 1) * 16 + 16;
+  const int groups = (B + g.ipc - 1) / g.ipc;
+  const int grid = groups < 2 * 148 ? groups : 2 * 148;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   NFK_DISPATCH_C(C, {
     int rc = ensure_smem(coupling_bwd_kernel<CC>, smem);
@@ -521,11 +561,12 @@ extern "C" int nfk_coupling_bwd(const float* g_out, const float* g_ld, const flo
 
 extern "C" int nfk_affine1x1_bwd(const float* dy, const float* dcol, int K1p, const float* x, const float* Wf,
                                  float* dx, float* dWf, float* dbf, int B, int C, int H, int W, void* stream) {
-  if (B <= 0 || H <= 0 || W <= 0 || H * W > 4096) return NFK_ERR_SHAPE;
+  if (B <= 0 || H <= 0 || W <= 0 || H * W > 4096 || !pow2(H) || !pow2(W)) return NFK_ERR_SHAPE;
   if (!dy || !x || !Wf || !dx || !dWf || !dbf) return NFK_ERR_ARG;
   Geo g = make_geo(B, C, H, W, true);
   const int smem = (C * C + 2 * C * (g.pixt + 1) + C * C + C) * 4;
-  const int grid = (B + g.ipc - 1) / g.ipc;
+  const int groups = (B + g.ipc - 1) / g.ipc;
+  const int grid = groups < 2 * 148 ? groups : 2 * 148;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   NFK_DISPATCH_C(C, {
     int rc = ensure_smem(affine1x1_bwd_kernel<CC>, smem);

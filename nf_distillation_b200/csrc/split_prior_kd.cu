@@ -103,7 +103,9 @@ split2d_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, con
   }
 }
 
-// smem: ws[C*CH*9] | bsc[2C] | z1s[CH*ldp] | dps[C*ldp] | accw[C*CH*9] | accb[2C]
+// Persistent CTAs over groups of whole images; weight / bias / logs gradients are accumulated in shared memory across
+// all groups of a CTA (each thread owns its weight entries: no atomics) and flushed with one global atomic per entry.
+// smem: ws[C*CH*9] | bsc[2C] | z1s[CH*ldp] | dps[C*ldp] | accb[2C] | accw[C*CH*9]
 __global__ void __launch_bounds__(ST)
 split2d_bwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                    const float* __restrict__ logs, const float* __restrict__ g_z1, const float* __restrict__ g_ld,
@@ -116,98 +118,106 @@ split2d_bwd_kernel(const float* __restrict__ x, const float* __restrict__ w, con
   float* z1s = bsc + 2 * C;
   float* dps = z1s + CH * ldp;
   float* accb = dps + C * ldp;
+  float* accw = accb + 2 * C;
   const int tid = threadIdx.x;
-  const int b0 = blockIdx.x * g.ipc;
-  const int nimg = min(g.ipc, g.B - b0);
-  const int npix = nimg * g.HW;
+  const int ngroups = (g.B + g.ipc - 1) / g.ipc;
 
-  for (int i = tid; i < C * CH * 9; i += ST) ws[i] = w[i];
+  for (int i = tid; i < C * CH * 9; i += ST) { ws[i] = w[i]; accw[i] = 0.f; }
   for (int i = tid; i < C; i += ST) { bsc[i] = bias[i]; bsc[C + i] = expf(3.f * logs[i]); }
   for (int i = tid; i < 2 * C; i += ST) accb[i] = 0.f;
-  for (int i = tid; i < CH * npix; i += ST) {
-    const int img = i / (CH * g.HW), r = i - img * CH * g.HW;
-    const int c = r / g.HW, p = r - c * g.HW;
-    z1s[c * ldp + img * g.HW + p] = x[(static_cast<long long>(b0 + img) * C + c) * g.HW + p];
-  }
-  __syncthreads();
-  const int PPP = ST / CH;
-  const int j = tid % CH, pl0 = tid / CH;
-  if (pl0 < PPP) {
-    float a_bm = 0.f, a_bl = 0.f, a_lm = 0.f, a_ll = 0.f;
-    for (int pl = pl0; pl < npix; pl += PPP) {
-      const int img = pl / g.HW, rem = pl - img * g.HW;
-      const int yy = rem / g.W, xx = rem - yy * g.W;
-      float mean = 0.f, lsg = 0.f;
-      for (int tap = 0; tap < 9; ++tap) {
-        const int ny = yy + tap / 3 - 1, nx = xx + tap % 3 - 1;
-        if (ny < 0 || ny >= g.H || nx < 0 || nx >= g.W) continue;
-        const int q = img * g.HW + ny * g.W + nx;
-        const float* wm = ws + (2 * j) * CH * 9 + tap;
-        const float* wl = wm + CH * 9;
-        for (int ci = 0; ci < CH; ++ci) {
-          const float v = z1s[ci * ldp + q];
-          mean = fmaf(wm[ci * 9], v, mean);
-          lsg = fmaf(wl[ci * 9], v, lsg);
-        }
-      }
-      const float em = bsc[C + 2 * j], el = bsc[C + 2 * j + 1];
-      mean = (mean + bsc[2 * j]) * em;
-      lsg = (lsg + bsc[2 * j + 1]) * el;
-      const long long zi = (static_cast<long long>(b0 + img) * C + CH + j) * g.HW + rem;
-      const float z2 = x[zi];
-      const float gl = g_ld[b0 + img];
-      const float d = z2 - mean;
-      const float r = d * expf(-2.f * lsg);
-      const float dmean = gl * r;
-      const float dlsg = gl * (d * r - 1.f);
-      dx[zi] = -gl * r;
-      const float dpm = dmean * em, dpl = dlsg * el;
-      dps[(2 * j) * ldp + pl] = dpm;
-      dps[(2 * j + 1) * ldp + pl] = dpl;
-      a_bm += dpm; a_bl += dpl;
-      a_lm += dmean * mean; a_ll += dlsg * lsg;
+
+  for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+    const int b0 = grp * g.ipc;
+    const int nimg = min(g.ipc, g.B - b0);
+    const int npix = nimg * g.HW;
+    __syncthreads();
+    for (int i = tid; i < CH * npix; i += ST) {
+      const int img = i / (CH * g.HW), r = i - img * CH * g.HW;
+      const int c = r / g.HW, p = r - c * g.HW;
+      z1s[c * ldp + img * g.HW + p] = x[(static_cast<long long>(b0 + img) * C + c) * g.HW + p];
     }
-    atomicAdd(&accb[2 * j], a_bm);
-    atomicAdd(&accb[2 * j + 1], a_bl);
-    atomicAdd(&accb[C + 2 * j], 3.f * a_lm);
-    atomicAdd(&accb[C + 2 * j + 1], 3.f * a_ll);
+    __syncthreads();
+    const int PPP = ST / CH;
+    const int j = tid % CH, pl0 = tid / CH;
+    if (pl0 < PPP) {
+      float a_bm = 0.f, a_bl = 0.f, a_lm = 0.f, a_ll = 0.f;
+      for (int pl = pl0; pl < npix; pl += PPP) {
+        const int img = pl / g.HW, rem = pl - img * g.HW;
+        const int yy = rem / g.W, xx = rem - yy * g.W;
+        float mean = 0.f, lsg = 0.f;
+        for (int tap = 0; tap < 9; ++tap) {
+          const int ny = yy + tap / 3 - 1, nx = xx + tap % 3 - 1;
+          if (ny < 0 || ny >= g.H || nx < 0 || nx >= g.W) continue;
+          const int q = img * g.HW + ny * g.W + nx;
+          const float* wm = ws + (2 * j) * CH * 9 + tap;
+          const float* wl = wm + CH * 9;
+          for (int ci = 0; ci < CH; ++ci) {
+            const float v = z1s[ci * ldp + q];
+            mean = fmaf(wm[ci * 9], v, mean);
+            lsg = fmaf(wl[ci * 9], v, lsg);
+          }
+        }
+        const float em = bsc[C + 2 * j], el = bsc[C + 2 * j + 1];
+        mean = (mean + bsc[2 * j]) * em;
+        lsg = (lsg + bsc[2 * j + 1]) * el;
+        const long long zi = (static_cast<long long>(b0 + img) * C + CH + j) * g.HW + rem;
+        const float z2 = x[zi];
+        const float gl = g_ld[b0 + img];
+        const float d = z2 - mean;
+        const float r = d * expf(-2.f * lsg);
+        const float dmean = gl * r;
+        const float dlsg = gl * (d * r - 1.f);
+        dx[zi] = -gl * r;
+        const float dpm = dmean * em, dpl = dlsg * el;
+        dps[(2 * j) * ldp + pl] = dpm;
+        dps[(2 * j + 1) * ldp + pl] = dpl;
+        a_bm += dpm; a_bl += dpl;
+        a_lm += dmean * mean; a_ll += dlsg * lsg;
+      }
+      atomicAdd(&accb[2 * j], a_bm);
+      atomicAdd(&accb[2 * j + 1], a_bl);
+      atomicAdd(&accb[C + 2 * j], 3.f * a_lm);
+      atomicAdd(&accb[C + 2 * j + 1], 3.f * a_ll);
+    }
+    __syncthreads();
+    // dz1[ci, m] = g_z1 + sum_{co,tap} dpre[co, m - off(tap)] * w[co][ci][tap]
+    if (pl0 < PPP) {
+      const int ci = j;
+      for (int pl = pl0; pl < npix; pl += PPP) {
+        const int img = pl / g.HW, rem = pl - img * g.HW;
+        const int yy = rem / g.W, xx = rem - yy * g.W;
+        float a = 0.f;
+        for (int tap = 0; tap < 9; ++tap) {
+          const int ny = yy - (tap / 3 - 1), nx = xx - (tap % 3 - 1);
+          if (ny < 0 || ny >= g.H || nx < 0 || nx >= g.W) continue;
+          const int q = img * g.HW + ny * g.W + nx;
+          const float* wp = ws + ci * 9 + tap;
+          for (int co = 0; co < C; ++co) a = fmaf(dps[co * ldp + q], wp[co * CH * 9], a);
+        }
+        const long long gi = (static_cast<long long>(b0 + img) * CH + ci) * g.HW + rem;
+        dx[(static_cast<long long>(b0 + img) * C + ci) * g.HW + rem] = a + (g_z1 ? g_z1[gi] : 0.f);
+      }
+    }
+    // dw[co][ci][tap] += sum_m dpre[co, m] * z1[ci, m + off(tap)]   (entry e is owned by thread e % ST)
+    for (int e = tid; e < C * CH * 9; e += ST) {
+      const int co = e / (CH * 9), r = e - co * CH * 9;
+      const int ci = r / 9, tap = r - ci * 9;
+      const int dyy = tap / 3 - 1, dxx = tap % 3 - 1;
+      float a = 0.f;
+      for (int img = 0; img < nimg; ++img) {
+        const int y0 = max(0, -dyy), y1 = min(g.H, g.H - dyy);
+        const int x0 = max(0, -dxx), x1 = min(g.W, g.W - dxx);
+        for (int yy = y0; yy < y1; ++yy)
+          for (int xx = x0; xx < x1; ++xx)
+            a = fmaf(dps[co * ldp + img * g.HW + yy * g.W + xx],
+                     z1s[ci * ldp + img * g.HW + (yy + dyy) * g.W + xx + dxx], a);
+      }
+      accw[e] += a;
+    }
   }
   __syncthreads();
   for (int i = tid; i < C; i += ST) { atomicAdd(dbias + i, accb[i]); atomicAdd(dlogs + i, accb[C + i]); }
-  // dz1[ci, m] = g_z1 + sum_{co,tap} dpre[co, m - off(tap)] * w[co][ci][tap]
-  if (pl0 < PPP) {
-    const int ci = j;
-    for (int pl = pl0; pl < npix; pl += PPP) {
-      const int img = pl / g.HW, rem = pl - img * g.HW;
-      const int yy = rem / g.W, xx = rem - yy * g.W;
-      float a = 0.f;
-      for (int tap = 0; tap < 9; ++tap) {
-        const int ny = yy - (tap / 3 - 1), nx = xx - (tap % 3 - 1);
-        if (ny < 0 || ny >= g.H || nx < 0 || nx >= g.W) continue;
-        const int q = img * g.HW + ny * g.W + nx;
-        const float* wp = ws + ci * 9 + tap;
-        for (int co = 0; co < C; ++co) a = fmaf(dps[co * ldp + q], wp[co * CH * 9], a);
-      }
-      const long long gi = (static_cast<long long>(b0 + img) * CH + ci) * g.HW + rem;
-      dx[(static_cast<long long>(b0 + img) * C + ci) * g.HW + rem] = a + (g_z1 ? g_z1[gi] : 0.f);
-    }
-  }
-  // dw[co][ci][tap] += sum_m dpre[co, m] * z1[ci, m + off(tap)]
-  for (int e = tid; e < C * CH * 9; e += ST) {
-    const int co = e / (CH * 9), r = e - co * CH * 9;
-    const int ci = r / 9, tap = r - ci * 9;
-    const int dyy = tap / 3 - 1, dxx = tap % 3 - 1;
-    float a = 0.f;
-    for (int img = 0; img < nimg; ++img) {
-      const int y0 = max(0, -dyy), y1 = min(g.H, g.H - dyy);
-      const int x0 = max(0, -dxx), x1 = min(g.W, g.W - dxx);
-      for (int yy = y0; yy < y1; ++yy)
-        for (int xx = x0; xx < x1; ++xx)
-          a = fmaf(dps[co * ldp + img * g.HW + yy * g.W + xx],
-                   z1s[ci * ldp + img * g.HW + (yy + dyy) * g.W + xx + dxx], a);
-    }
-    atomicAdd(dw + e, a);
-  }
+  for (int e = tid; e < C * CH * 9; e += ST) atomicAdd(dw + e, accw[e]);
 }
 
 // One warp per sample: out[b] = -(logdet[b] + sum_i logN(z_i; mean_i, exp(logs_i))) * scale
@@ -332,9 +342,10 @@ extern "C" int nfk_split2d_bwd(const float* x, const float* w, const float* bias
   if (B <= 0 || C <= 0 || C % 2 || C > 128 || H * W > 4096) return NFK_ERR_SHAPE;
   if (!x || !w || !bias || !logs || !g_ld || !dx || !dw || !dbias || !dlogs) return NFK_ERR_ARG;
   SGeo g = make_sgeo(B, C, H, W, 128);
-  const int smem = (C * (C / 2) * 9 + 2 * C + (C / 2 + C) * (g.pixt + 1) + 2 * C) * 4;
+  const int smem = (2 * C * (C / 2) * 9 + 2 * C + (C / 2 + C) * (g.pixt + 1) + 2 * C) * 4;
   if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(split2d_bwd_kernel), smem)) return rc;
-  split2d_bwd_kernel<<<(B + g.ipc - 1) / g.ipc, ST, smem, static_cast<cudaStream_t>(stream)>>>(
+  const int groups = (B + g.ipc - 1) / g.ipc;
+  split2d_bwd_kernel<<<groups < 4 * 148 ? groups : 4 * 148, ST, smem, static_cast<cudaStream_t>(stream)>>>(
       x, w, bias, logs, g_z1, g_ld, dx, dw, dbias, dlogs, g);
   return cudaGetLastError() == cudaSuccess ? NFK_OK : NFK_ERR_LAUNCH;
 }

@@ -353,6 +353,10 @@ affine1x1_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ dco
     WT[c * C + o] = Wf[i];
   }
   for (int i = tid; i < C * C + C; i += ZT) acc[i] = 0.f;
+  constexpr int NBK = (C / 4) * (C / 4);              // 4x4 blocks of dW'
+  constexpr int SL = NBK >= ZT ? 1 : ZT / NBK;        // pixel slices per block
+  constexpr int RB = (NBK + ZT - 1) / ZT;             // blocks per thread
+  float wacc[RB][4][4] = {};
 
   for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
     const int b0 = grp * g.ipc;
@@ -417,14 +421,14 @@ affine1x1_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ dco
         dxp[static_cast<long long>(i) << g.lgHW] = a;
       }
     }
-    // dW'[o][i] += sum_p dy[o][p] x[i][p] with 4x4 register blocks, pixel range split over thread slices
-    constexpr int NBK = (C / 4) * (C / 4);
-    constexpr int SL = NBK >= ZT ? 1 : ZT / NBK;
-    for (int blk = tid % (NBK < ZT ? NBK : ZT); blk < NBK; blk += ZT) {
+    // dW'[o][i] += sum_p dy[o][p] x[i][p]: 4x4 register blocks, pixel range split over thread slices; the partial
+    // sums stay in registers across all groups of this CTA
+#pragma unroll
+    for (int rb = 0; rb < RB; ++rb) {
+      const int blk = (NBK < ZT ? tid % NBK : tid) + rb * ZT;
       const int slice = NBK < ZT ? tid / NBK : 0;
-      if (slice >= SL) break;
+      if (blk >= NBK || slice >= SL) continue;
       const int to = blk / (C / 4), ti = blk % (C / 4);
-      float a[4][4] = {};
       for (int p = slice; p < npix; p += SL) {
         float dv[4], xv[4];
 #pragma unroll
@@ -435,12 +439,8 @@ affine1x1_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ dco
 #pragma unroll
         for (int q = 0; q < 4; ++q)
 #pragma unroll
-          for (int r = 0; r < 4; ++r) a[q][r] = fmaf(dv[q], xv[r], a[q][r]);
+          for (int r = 0; r < 4; ++r) wacc[rb][q][r] = fmaf(dv[q], xv[r], wacc[rb][q][r]);
       }
-#pragma unroll
-      for (int q = 0; q < 4; ++q)
-#pragma unroll
-        for (int r = 0; r < 4; ++r) atomicAdd(&acc[(4 * to + q) * C + 4 * ti + r], a[q][r]);
     }
     // db'[o] += sum_p dy[o][p]: one warp per channel
     {
@@ -452,6 +452,17 @@ affine1x1_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ dco
         if (lane == 0) acc[C * C + o] += a;
       }
     }
+  }
+#pragma unroll
+  for (int rb = 0; rb < RB; ++rb) {
+    const int blk = (NBK < ZT ? tid % NBK : tid) + rb * ZT;
+    const int slice = NBK < ZT ? tid / NBK : 0;
+    if (blk >= NBK || slice >= SL) continue;
+    const int to = blk / (C / 4), ti = blk % (C / 4);
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) atomicAdd(&acc[(4 * to + q) * C + 4 * ti + r], wacc[rb][q][r]);
   }
   __syncthreads();
   for (int i = tid; i < C * C; i += ZT) atomicAdd(dWf + i, acc[i]);
@@ -548,7 +559,7 @@ extern "C" int nfk_coupling_bwd(const float* g_out, const float* g_ld, const flo
   }
   const int smem = (2 * C * (g.pixt + 1) + ((C + 3) & ~3)) * 4 + g.pixt * (K3p / 8 + 1) * 16 + 16;
   const int groups = (B + g.ipc - 1) / g.ipc;
-  const int grid = groups < 2 * 148 ? groups : 2 * 148;
+  const int grid = groups < 4 * 148 ? groups : 4 * 148;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   NFK_DISPATCH_C(C, {
     int rc = ensure_smem(coupling_bwd_kernel<CC>, smem);
@@ -566,7 +577,7 @@ extern "C" int nfk_affine1x1_bwd(const float* dy, const float* dcol, int K1p, co
   Geo g = make_geo(B, C, H, W, true);
   const int smem = (C * C + 2 * C * (g.pixt + 1) + C * C + C) * 4;
   const int groups = (B + g.ipc - 1) / g.ipc;
-  const int grid = groups < 2 * 148 ? groups : 2 * 148;
+  const int grid = groups < 4 * 148 ? groups : 4 * 148;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   NFK_DISPATCH_C(C, {
     int rc = ensure_smem(affine1x1_bwd_kernel<CC>, smem);

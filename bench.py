@@ -241,34 +241,55 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e = t.tolist()
 
-    # ---- roofline of the dominant kernel (conv#2 of the coupling net: M x 512 x 512 bf16 GEMM + bias/ReLU epilogue),
-    #      timed alone with CUDA events on its launch stream, operands larger than L2 across the rotation.
+    # ---- roofline of the dominant kernel (profiles/r01_launches_step_b1024.txt: cnet_fwd_fused_kernel, ~30 % of the
+    #      step): fused conv#1+conv#2 of the coupling net at the level-0 shape, M = B*H/2*W/2 pixels, timed alone with
+    #      CUDA events on its launch stream, 10 launches per CUDA graph so host launch overhead is not measured, and
+    #      rotating buffers larger than L2. Algorithmic work per launch = 2*M*512*(K1p+512) FLOP.
     roof = None
     if rank == 0:
         pk = peaks()
-        M, hid = B * (H // 2) * (W // 2), wl["hidden"]
-        nbuf = 6
-        A = [torch.randn(M, hid, device=device).bfloat16() for _ in range(nbuf)]
-        O_ = [torch.empty(M, hid, device=device, dtype=torch.bfloat16) for _ in range(nbuf)]
-        Wm = torch.randn(hid, hid, device=device).bfloat16()
-        bias = torch.zeros(hid, device=device)
+        M, hid, K1p = B * (H // 2) * (W // 2), wl["hidden"], 64
+        nbuf = 3
+        cols = [(torch.randn(M, K1p, device=device) * 0.5).bfloat16() for _ in range(nbuf)]
+        outs_ = [torch.empty(M, hid, device=device, dtype=torch.bfloat16) for _ in range(nbuf)]
+        W1 = (torch.randn(hid, K1p, device=device) * 0.1).bfloat16()
+        W2 = (torch.randn(hid, hid, device=device) * 0.05).bfloat16()
+        b1, b2 = torch.zeros(hid, device=device), torch.zeros(hid, device=device)
+        fused = ops.cnet_fused_supported(hid, K1p)
+
+        def run(i):
+            if fused:
+                ops.cnet_fwd_fused(cols[i], K1p, W1, W2, b1, b2, outs_[i], M, hid)
+            else:
+                ops.gemm_nt(outs_[(i + 1) % nbuf], W2, M, hid, hid, ops.EPI_BIAS_RELU_BF16, outs_[i], bias=b2)
         for i in range(3):
-            ops.gemm_nt(A[i], Wm, M, hid, hid, ops.EPI_BIAS_RELU_BF16, O_[i], bias=bias)
-        reps = 30
+            run(i % nbuf)
+        torch.cuda.synchronize()
+        reps = 12
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            for i in range(reps):
+                run(i % nbuf)
+        gr.replay()
+        torch.cuda.synchronize()
         k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         k0.record()
-        for i in range(reps):
-            ops.gemm_nt(A[i % nbuf], Wm, M, hid, hid, ops.EPI_BIAS_RELU_BF16, O_[i % nbuf], bias=bias)
+        gr.replay()
         k1.record()
         torch.cuda.synchronize()
         kms = k0.elapsed_time(k1) / reps
-        flops = 2.0 * M * hid * hid
+        flops = 2.0 * M * hid * ((K1p if fused else 0) + hid)
         ach = flops / (kms * 1e-3) / 1e12
-        roof = {"bound": "tensor", "kernel": "gemm_nt_kernel<BIAS_RELU_BF16> (coupling conv#2)", "achieved": ach,
-                "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops"], "traffic": None,
+        alg_bytes = 2.0 * (M * K1p + M * hid + hid * K1p + hid * hid)
+        roof = {"bound": "tensor",
+                "kernel": "cnet_fwd_fused_kernel (conv#1+conv#2 of the coupling net, level 0)" if fused
+                else "gemm_nt_pair_kernel<BIAS_RELU_BF16> (conv#2)",
+                "achieved": ach, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops"],
+                # dram__bytes_read+write per launch from profiles/r01_prof_cnet_r1.txt (ncu --set full, B=1024)
+                "traffic": 242.1e6 * (B / 1024.0) if fused else None,
                 "peak_src": pk["src"] + " burst (kernel timed alone)", "us_per_launch": kms * 1e3,
-                "flops_per_launch": flops, "algorithmic_bytes_per_launch": 2.0 * (2 * M * hid + hid * hid)}
-        del A, O_
+                "flops_per_launch": flops, "algorithmic_bytes_per_launch": alg_bytes}
+        del cols, outs_
 
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -27,6 +27,13 @@ WORKLOADS = {
     # per-GPU batch 1024 (weak scaling). The reference's config uses 64 (conf/training/cifar.yaml:7) on its single
     # GPU; throughput on synthetic data is quoted at the batch that fills a B200 (--batch overrides).
     "glow_cifar_kd_t32_s8": dict(image=(32, 32, 3), L=3, hidden=512, tK=32, sK=8, batch=1024),
+    # secondary workloads (BASELINE configs[1]): BSDS300-shaped tabular KD, D = 63, reference batch 65 536
+    # (conf/training/tabular.yaml: nll 0.85, kd 0.05, perceptual-L1 0.1 through the inverse pass)
+    "glow1d_bsds300_kd_t5_s3": dict(image=(63,), L=1, hidden=32, s_hidden=16, tK=5, sK=3, batch=65536, is_1d=True,
+                                    weights=(0.85, 0.05, 0.1), data="bsds300"),
+    # MAF teacher 10 MADE layers -> student 3 layers, hidden 512 (no reference implementation exists: parity unpinned)
+    "maf_bsds300_kd_t10_s3": dict(image=(63,), L=1, hidden=512, tK=10, sK=3, batch=65536, is_1d=True, arch="maf",
+                                  weights=(0.9, 0.1, 0.0), data="bsds300"),
 }
 METRIC = "kd_train_samples_per_sec"
 
@@ -94,9 +101,40 @@ def cpu_kd_step_fn(wl, batch, seed=42):
     from oracle import glow_oracle as O
     from nf_distillation_b200.models import create_glow_model
     from nf_distillation_b200.train import glow_cfg, randomise_zero_params
-    s_cfg = glow_cfg(wl["image"], wl["sK"], wl["L"], wl["hidden"])
-    t_cfg = glow_cfg(wl["image"], wl["tK"], wl["L"], wl["hidden"])
+    is_1d = wl.get("is_1d", False)
     torch.manual_seed(seed)
+    if wl.get("arch") == "maf":
+        from oracle import maf_oracle as MO
+        from nf_distillation_b200.models.maf import create_maf_model
+        D = wl["image"][0]
+        t_model = create_maf_model(dict(image_shape=[D], hidden_channels=wl["hidden"], K=wl["tK"]))
+        s_model = create_maf_model(dict(image_shape=[D], hidden_channels=wl["hidden"], K=wl["sK"]))
+        pn = dict(s_model.named_parameters())
+        s_sd = {k: v.clone().requires_grad_(k in pn) for k, v in s_model.state_dict().items()}
+        t_sd = {k: v.clone() for k, v in t_model.state_dict().items()}
+        params = [v for v in s_sd.values() if v.requires_grad]
+        opt = torch.optim.Adam(params, lr=5e-4)
+        x = torch.randn(batch, D)
+        wn, wk, _ = wl["weights"]
+
+        def step():
+            opt.zero_grad(set_to_none=True)
+            s_z, s_nll = MO.maf_forward(s_sd, D, wl["sK"], x)
+            with torch.no_grad():
+                t_z, _ = MO.maf_forward(t_sd, D, wl["tK"], x)
+            kd = O.kd_loss(s_z, t_z, [1, 2], [3, 7])
+            loss = (wn * s_nll + wk * kd).mean()
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(params, 30.0)
+            opt.step()
+            return float(loss.detach())
+        return step
+    if is_1d:
+        s_cfg = glow_cfg(wl["image"], wl["sK"], wl["L"], wl.get("s_hidden", wl["hidden"]), is_1d=True, y_classes=0)
+        t_cfg = glow_cfg(wl["image"], wl["tK"], wl["L"], wl["hidden"], is_1d=True, y_classes=0)
+    else:
+        s_cfg = glow_cfg(wl["image"], wl["sK"], wl["L"], wl["hidden"])
+        t_cfg = glow_cfg(wl["image"], wl["tK"], wl["L"], wl["hidden"])
     t_model, s_model = create_glow_model(t_cfg), create_glow_model(s_cfg)   # parameter containers only (CPU)
     randomise_zero_params(s_model, seed + 1)
     randomise_zero_params(t_model, seed + 2)
@@ -105,17 +143,26 @@ def cpu_kd_step_fn(wl, batch, seed=42):
     t_sd = {k: v.clone() for k, v in t_model.state_dict().items()}
     params = [v for v in s_sd.values() if v.requires_grad]
     opt = torch.optim.Adam(params, lr=5e-4)
-    x = synthetic_images(batch, wl["image"], seed)
-    weights = {"nll": 0.9, "kd": 0.1, "perceptual": 0.0}
+    if is_1d:
+        x = torch.randn(batch, wl["image"][0])
+        wn, wk, wp = wl["weights"]
+        weights = {"nll": wn, "kd": wk, "perceptual": wp}
+    else:
+        x = synthetic_images(batch, wl["image"], seed)
+        weights = {"nll": 0.9, "kd": 0.1, "perceptual": 0.0}
 
     def step():
-        n1, n2 = torch.rand_like(x) / 256, torch.rand_like(x) / 256
+        n1 = n2 = latent = None
+        if is_1d:
+            latent = torch.randn_like(x)
+        else:
+            n1, n2 = torch.rand_like(x) / 256, torch.rand_like(x) / 256
         opt.zero_grad(set_to_none=True)
-        out = O.kd_step(s_sd, s_cfg, t_sd, t_cfg, x, weights, n1, n2)
+        out = O.kd_step(s_sd, s_cfg, t_sd, t_cfg, x, weights, n1, n2, latent)
         out["result_loss"].backward()
         torch.nn.utils.clip_grad_norm_(params, 30.0)
         opt.step()
-        return float(out["result_loss"])
+        return float(out["result_loss"].detach())
     return step
 
 
@@ -152,14 +199,18 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     warmup = max(args.warmup, 3) if args.impl == "native" else max(args.warmup, 1)
-    cfg_desc = {"workload": args.workload, "teacher": f"glow K={wl['tK']} L={wl['L']} hidden={wl['hidden']}",
-                "student": f"glow K={wl['sK']} L={wl['L']} hidden={wl['hidden']}", "image": list(wl["image"]),
-                "loss": "0.9 nll + 0.1 kd(mse, 4 levels)", "optimizer": "adam 5e-4, clip 30"}
+    arch = wl.get("arch", "glow")
+    cfg_desc = {"workload": args.workload, "teacher": f"{arch} K={wl['tK']} L={wl['L']} hidden={wl['hidden']}",
+                "student": f"{arch} K={wl['sK']} L={wl['L']} hidden={wl.get('s_hidden', wl['hidden'])}",
+                "image": list(wl["image"]),
+                "loss": "0.9 nll + 0.1 kd(mse, 4 levels)" if "weights" not in wl else
+                        "%.2f nll + %.2f kd(mse) + %.2f perceptual(l1, inverse pass)" % wl["weights"],
+                "optimizer": "adam 5e-4, clip 30"}
 
     if args.impl == "reference":
         if rank != 0:
             return
-        cb = args.cpu_batch
+        cb = args.cpu_batch if not wl.get("is_1d", False) else 65536
         value, ms, cores = run_cpu(wl, cb, max(1, min(args.steps, 3)), 1)
         cfg_desc.update(per_gpu_batch=cb, global_batch=cb, parallelism="cpu")
         print(json.dumps({
@@ -177,12 +228,32 @@ def main():
     from nf_distillation_b200.train import KDTrainer, glow_cfg, init_distributed, kd_config
     rank, world, device = init_distributed()
     B = args.batch or wl["batch"]
-    H, W, C = wl["image"]
-    config = kd_config(glow_cfg(wl["image"], wl["sK"], wl["L"], wl["hidden"]),
-                       glow_cfg(wl["image"], wl["tK"], wl["L"], wl["hidden"]))
-    trainer = KDTrainer(config, (B, C, H, W), device, use_graphs=not args.no_graphs)
+    is_1d = wl.get("is_1d", False)
+    if is_1d:
+        D = wl["image"][0]
+        H = W = 2
+        C = D
+        s_cfg = glow_cfg(wl["image"], wl["sK"], wl["L"], wl.get("s_hidden", wl["hidden"]), is_1d=True, y_classes=0)
+        t_cfg = glow_cfg(wl["image"], wl["tK"], wl["L"], wl["hidden"], is_1d=True, y_classes=0)
+        if wl.get("arch") == "maf":
+            s_cfg["architecture"] = t_cfg["architecture"] = "maf"
+        wn, wk, wp = wl["weights"]
+        config = kd_config(s_cfg, t_cfg, data=wl["data"], nll=wn, kd=wk, perceptual=wp)
+        shape = (B, D)
+    else:
+        H, W, C = wl["image"]
+        config = kd_config(glow_cfg(wl["image"], wl["sK"], wl["L"], wl["hidden"]),
+                           glow_cfg(wl["image"], wl["tK"], wl["L"], wl["hidden"]))
+        shape = (B, C, H, W)
+    trainer = KDTrainer(config, shape, device, use_graphs=not args.no_graphs)
     n_pool = 4
-    host_pool = [synthetic_images(B, wl["image"], 1000 + rank * 100 + i).pin_memory() for i in range(n_pool)]
+
+    def synth(i):
+        if is_1d:   # z-scored tabular features (data/src/power.py:42-52): N(0, 1)
+            g = torch.Generator().manual_seed(1000 + rank * 100 + i)
+            return torch.randn(B, wl["image"][0], generator=g)
+        return synthetic_images(B, wl["image"], 1000 + rank * 100 + i)
+    host_pool = [synth(i).pin_memory() for i in range(n_pool)]
     dev_pool = [h.to(device) for h in host_pool]
     trainer.x.copy_(dev_pool[0])
     if args.ncu_step:
@@ -246,7 +317,7 @@ def main():
     #      CUDA events on its launch stream, 10 launches per CUDA graph so host launch overhead is not measured, and
     #      rotating buffers larger than L2. Algorithmic work per launch = 2*M*512*(K1p+512) FLOP.
     roof = None
-    if rank == 0:
+    if rank == 0 and not is_1d:
         pk = peaks()
         M, hid, K1p = B * (H // 2) * (W // 2), wl["hidden"], 64
         nbuf = 3
@@ -293,10 +364,11 @@ def main():
 
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, cms, cores = run_cpu(wl, args.cpu_batch, 2, 1)
+        cb = args.cpu_batch if not is_1d else (65536 if wl.get("arch") != "maf" else 8192)
+        v, cms, cores = run_cpu(wl, cb, 2, 1)
         cpu_base = {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
-                    "sample": f"2 KD train steps of {args.cpu_batch} samples, same model/config "
-                              f"(oracle/glow_oracle.py on torch CPU fp32, {cores} threads), {cms:.0f} ms/step"}
+                    "sample": f"2 KD train steps of {cb} samples, same model/config "
+                              f"(oracle/ on torch CPU fp32, {cores} threads), {cms:.0f} ms/step"}
 
     if rank == 0:
         gb = B * world
@@ -308,7 +380,7 @@ def main():
                "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
                "data": "synthetic", "config": cfg_desc, "clocks": clocks,
                "e2e": {"value": gb / (ms_e2e * 1e-3), "unit": "samples/s", "ms_per_step": ms_e2e,
-                       "h2d_bytes_per_step": B * C * H * W * 4, "d2h_bytes_per_step": 16},
+                       "h2d_bytes_per_step": host_pool[0].numel() * 4, "d2h_bytes_per_step": 16},
                "gpu_launches": launches_per_step * args.steps, "gpu_launches_per_step": launches_per_step,
                "losses_last_step": dict(zip(("nll", "kd", "perceptual", "loss"), losses)),
                "roofline": roof, "cpu_baseline": cpu_base}

@@ -42,8 +42,12 @@ def gaussian_likelihood(mean, logs, x):
 
 
 def gaussian_sample(mean, logs, temperature=1):
-    """z ~ N(mean, (exp(logs) * T)^2) from the global torch generator (layers.py:26-29)."""
-    return torch.normal(mean, torch.exp(logs) * temperature)
+    """z ~ N(mean, (exp(logs) * T)^2) from the global torch generator (layers.py:26-29).
+
+    Written as normal_(0,1)*std+mean, which is what torch.normal(mean, std) does internally (same Philox draws), minus
+    its host-side `std.min() >= 0` check: that check synchronises and cannot be captured in a CUDA graph, and
+    exp(logs)*T with T >= 0 is non-negative by construction."""
+    return torch.empty_like(mean).normal_().mul_(torch.exp(logs) * temperature).add_(mean)
 
 
 def squeeze2d(input, factor):

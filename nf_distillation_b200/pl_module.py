@@ -78,9 +78,13 @@ class NFModel(nn.Module):
         cfg = dict(self.params[model_name])
         ckpt = cfg.pop("checkpoint", None)
         arch = cfg.pop("architecture", "glow")
-        if arch != "glow":
+        if arch == "maf":   # extension: the reference names MAF (README.md:7) but only ever builds "glow"
+            from .models.maf import create_maf_model
+            model = create_maf_model(cfg)
+        elif arch != "glow":
             raise NameError(f"Unknown architecture: {arch}")
-        model = create_glow_model(cfg)
+        else:
+            model = create_glow_model(cfg)
         if ckpt:
             model = self.load_checkpoint(model, ckpt)
         return model

@@ -55,6 +55,29 @@ int nfk_gemm_set_prof(void* buf);
 int nfk_gemm_tn_bf16(const void* A, long long lda, const void* B, long long ldb, int Mo, int No, int Kpix,
                      float* out, long long ldo, int sm_count, void* stream);
 
+/* ---- batched parameter-space prep: every FlowStep of a model in one launch (one CTA per step) ----------------
+ * An item is the argument list of nfk_invconv_prep below; a backward item adds the incoming gradients of the
+ * fused matrix (dWf, row stride dWf_ld >= C; fwd.outW must hold the forward's outW) and the outputs.
+ * Items are read on the host at launch time (they travel in the kernel parameter block), so the arrays may be
+ * temporaries; the device pointers inside them must stay valid until the stream reaches the kernel. */
+typedef struct nfk_invconv_item {
+  const float *an_bias, *an_logs, *lower, *upper, *log_s, *p, *sign_s, *weight;
+  int C, reverse, transpose;
+  float *outW, *outb, *out_sl;
+} nfk_invconv_item;
+typedef struct nfk_invconv_bwd_item {
+  nfk_invconv_item fwd;
+  const float* dWf;
+  int dWf_ld;
+  const float* dbf;
+  const float* g_ld; /* [B] or NULL */
+  int B;
+  float pixels;
+  float *d_bias, *d_logs, *d_lower, *d_upper, *d_log_s, *d_weight;
+} nfk_invconv_bwd_item;
+int nfk_invconv_prep_batch(int n, const nfk_invconv_item* items, void* stream);
+int nfk_invconv_prep_bwd_batch(int n, const nfk_invconv_bwd_item* items, void* stream);
+
 /* ---- parameter-space prep ("K0") ---------------------------------------------------------------------------
  * Fused ActNorm o InvertibleConv1x1 matrix of one FlowStep (models/layers.py:376-397 get_weight + :101-142).
  *   forward (reverse=0):  outW = W diag(exp(logs)), outb = outW * an_bias, W = P (L o tril + I)(U o triu + diag(s))
@@ -141,7 +164,10 @@ int nfk_flow1d_pack(const float* Wf, const float* bf, const float* const* w, con
  * activations for nfk_flow1d_bwd. */
 int nfk_flow1d_fwd(const float* x, const float* cond, const float* PF, const float* sl, float* y, const float* ld_in,
                    float* ld_out, float* acts, int B, int D, int Cc, int hid, int reverse, void* stream);
-int nfk_flow1d_bwd(const float* x_in, const float* cond, const float* acts, const float* PB, const float* PF,
+/* Backward of nfk_flow1d_fwd. x_in = the step's input, y_out = the step's output (read when reverse=0: its first
+ * D//2 features are the coupling MLP's input, its last features the coupled values), acts as saved by the forward.
+ * dx [B, D]; G (pre-zeroed, nfk_flow1d_sizes layout) accumulates the parameter gradients. */
+int nfk_flow1d_bwd(const float* x_in, const float* cond, const float* acts, const float* PB, const float* y_out,
                    const float* g_out, const float* g_ld, float* dx, float* G, int B, int D, int Cc, int hid,
                    int reverse, void* stream);
 /* y = W x + b on [B, D] rows (stand-alone ActNorm1d / InvertibleConv1x1, models/layers.py:129-142,404-421). */

@@ -18,12 +18,30 @@ ERRORS = {
     -5: "NFK_ERR_DRIVER (tensor-map encode failure)",
 }
 
+
+
+class InvconvItem(_c.Structure):
+    """nfk_invconv_item (include/nfk.h)."""
+    _fields_ = [(n, _vp) for n in ("an_bias", "an_logs", "lower", "upper", "log_s", "p", "sign_s", "weight")] + \
+               [("C", _i), ("reverse", _i), ("transpose", _i)] + \
+               [(n, _vp) for n in ("outW", "outb", "out_sl")]
+
+
+class InvconvBwdItem(_c.Structure):
+    """nfk_invconv_bwd_item (include/nfk.h)."""
+    _fields_ = [("fwd", InvconvItem), ("dWf", _vp), ("dWf_ld", _i), ("dbf", _vp), ("g_ld", _vp), ("B", _i),
+                ("pixels", _f)] + \
+               [(n, _vp) for n in ("d_bias", "d_logs", "d_lower", "d_upper", "d_log_s", "d_weight")]
+
+
 # name -> argtypes; every function returns int. Keep in the same order as include/nfk.h.
 SIGNATURES: dict[str, list] = {
     "nfk_version": [],
     "nfk_gemm_nt_bf16": [_vp, _ll, _vp, _ll, _i, _i, _i, _i, _vp, _ll, _vp, _vp, _ll, _vp, _vp],
     "nfk_gemm_set_prof": [_vp],
     "nfk_gemm_tn_bf16": [_vp, _ll, _vp, _ll, _i, _i, _i, _vp, _ll, _i, _vp],
+    "nfk_invconv_prep_batch": [_i, _vp, _vp],
+    "nfk_invconv_prep_bwd_batch": [_i, _vp, _vp],
     "nfk_invconv_prep": [_vp] * 8 + [_i, _i, _i, _vp, _vp, _vp, _vp],
     "nfk_invconv_prep_bwd": [_vp] * 8 + [_i, _i, _i, _vp, _vp, _vp, _vp, _i, _f] + [_vp] * 6 + [_vp],
     "nfk_coupling_prep": [_vp] * 9 + [_i] * 5 + [_vp] * 9 + [_i, _vp],

@@ -87,22 +87,69 @@ __device__ float gauss_jordan(float* A, float* Inv, int C, int* piv_row, float* 
   return logabs;
 }
 
-struct InvconvParams {
-  const float* an_bias;  // [C]
-  const float* an_logs;  // [C]
-  const float* lower;    // [C,C]  (LU) or nullptr
-  const float* upper;    // [C,C]
-  const float* log_s;    // [C]
-  const float* p;        // [C,C] permutation
-  const float* sign_s;   // [C]
-  const float* weight;   // [C,C]  (non-LU) or nullptr
-};
+constexpr int INV_THREADS = 512;
+constexpr int INV_MAX_BATCH = 24;  // items per launch (passed by value in the kernel parameter block)
 
-// smem: Lm, Um, X, Y (C*C each) + perm[C] + red[32] + piv
-__global__ void __launch_bounds__(PREP_THREADS)
-invconv_prep_kernel(InvconvParams q, int C, int reverse, int transpose, float* __restrict__ outW,
-                    float* __restrict__ outb, float* __restrict__ out_sl) {
-  extern __shared__ float sm[];
+struct InvBatch { nfk_invconv_item it[INV_MAX_BATCH]; };
+struct InvBwdBatch { nfk_invconv_bwd_item it[INV_MAX_BATCH]; };
+
+// perm[r] = column of the single 1 in row r of the permutation matrix p (one coalesced pass over p)
+__device__ __forceinline__ void load_perm(const float* __restrict__ p, int C, int* perm) {
+  for (int i = threadIdx.x; i < C * C; i += blockDim.x)
+    if (p[i] > 0.5f) perm[i / C] = i % C;
+}
+
+// Lm = strict lower + I, Um = strict upper + diag(sign_s e^{log_s})
+__device__ __forceinline__ void load_lu(const nfk_invconv_item& q, int C, float* Lm, float* Um) {
+  for (int i = threadIdx.x; i < C * C; i += blockDim.x) {
+    const int r = i / C, c = i % C;
+    Lm[i] = c < r ? q.lower[i] : (c == r ? 1.f : 0.f);
+    Um[i] = c > r ? q.upper[i] : (c == r ? q.sign_s[r] * expf(q.log_s[r]) : 0.f);
+  }
+}
+
+// X <- L^-1 (unit lower) and Y <- U^-1, both by right-looking sweeps: at step k row k of the inverse is final and
+// is eliminated from every remaining row at once (C steps of rank-1 updates, one barrier each) instead of one
+// thread per column walking O(C^2) dependent shared-memory FMAs. U is first scaled to unit diagonal (U = D U'),
+// U^-1 = U'^-1 D^-1. Threads [0, T/2) sweep L top-down, threads [T/2, T) sweep U' bottom-up.
+__device__ void tri_inverses(const float* __restrict__ Lm, const float* __restrict__ Um, float* __restrict__ X,
+                             float* __restrict__ Y, int C) {
+  const int tid = threadIdx.x, half = blockDim.x >> 1;
+  for (int i = tid; i < C * C; i += blockDim.x) {
+    const float e = (i / C == i % C) ? 1.f : 0.f;
+    X[i] = e;
+    Y[i] = e;
+  }
+  __syncthreads();
+  const bool lowerSide = tid < half;
+  const int t = lowerSide ? tid : tid - half;
+  const int jx = t & 31, i0 = t >> 5, irows = half >> 5;
+  for (int s = 0; s + 1 < C; ++s) {
+    if (lowerSide) {
+      const int k = s;  // X[i][j] -= L[i][k] X[k][j]  for i > k, j <= k
+      for (int i = k + 1 + i0; i < C; i += irows) {
+        const float l = Lm[i * C + k];
+        for (int j = jx; j <= k; j += 32) X[i * C + j] = fmaf(-l, X[k * C + j], X[i * C + j]);
+      }
+    } else {
+      const int k = C - 1 - s;  // Y[i][j] -= U'[i][k] Y[k][j]  for i < k, j >= k
+      for (int i = i0; i < k; i += irows) {
+        const float u = Um[i * C + k] / Um[i * C + i];
+        for (int j = k + jx; j < C; j += 32) Y[i * C + j] = fmaf(-u, Y[k * C + j], Y[i * C + j]);
+      }
+    }
+    __syncthreads();
+  }
+  for (int i = tid; i < C * C; i += blockDim.x) {
+    const int r = i / C, c = i % C;
+    if (c >= r) Y[i] /= Um[c * C + c];
+  }
+  __syncthreads();
+}
+
+// smem: Lm, Um, X, Y (C*C each) + red[32] + perm[C] + piv
+__device__ void invconv_prep_body(const nfk_invconv_item& q, float* sm) {
+  const int C = q.C, reverse = q.reverse, transpose = q.transpose;
   float* Lm = sm;
   float* Um = Lm + C * C;
   float* X = Um + C * C;
@@ -128,18 +175,8 @@ invconv_prep_kernel(InvconvParams q, int C, int reverse, int transpose, float* _
       lsum += gauss_jordan(Lm, Um, C, piv, red);  // only the log|det| is needed
     }
   } else {
-    for (int i = tid; i < CC; i += blockDim.x) {
-      const int r = i / C, c = i % C;
-      Lm[i] = c < r ? q.lower[i] : (c == r ? 1.f : 0.f);
-      Um[i] = c > r ? q.upper[i] : (c == r ? q.sign_s[r] * expf(q.log_s[r]) : 0.f);
-    }
-    for (int r = tid; r < C; r += blockDim.x) {
-      int best = 0;
-      float bv = q.p[r * C];
-      for (int c = 1; c < C; ++c)
-        if (q.p[r * C + c] > bv) { bv = q.p[r * C + c]; best = c; }
-      perm[r] = best;
-    }
+    load_lu(q, C, Lm, Um);
+    load_perm(q.p, C, perm);
     __syncthreads();
     if (!reverse) {
       for (int i = tid; i < CC; i += blockDim.x) {
@@ -150,32 +187,7 @@ invconv_prep_kernel(InvconvParams q, int C, int reverse, int transpose, float* _
         Wplain[i] = t;
       }
     } else {
-      // X <- L^-1 (forward substitution), Y <- U^-1 (back substitution), one thread per column
-      for (int j = tid; j < C; j += blockDim.x) {
-        for (int i = 0; i < C; ++i) {
-          float x;
-          if (i < j) x = 0.f;
-          else if (i == j) x = 1.f;
-          else {
-            x = 0.f;
-            for (int k = j; k < i; ++k) x = fmaf(Lm[i * C + k], X[k * C + j], x);
-            x = -x;
-          }
-          X[i * C + j] = x;
-        }
-        for (int i = C - 1; i >= 0; --i) {
-          float x;
-          if (i > j) x = 0.f;
-          else if (i == j) x = 1.f / Um[j * C + j];
-          else {
-            x = 0.f;
-            for (int k = i + 1; k <= j; ++k) x = fmaf(Um[i * C + k], Y[k * C + j], x);
-            x = -x / Um[i * C + i];
-          }
-          Y[i * C + j] = x;
-        }
-      }
-      __syncthreads();
+      tri_inverses(Lm, Um, X, Y, C);
       // Lm <- (U^-1 L^-1) P^T : column c of the product goes to column where perm[.] == c
       for (int i = tid; i < CC; i += blockDim.x) {
         const int r = i / C, c = i % C, pc = perm[c];
@@ -190,37 +202,42 @@ invconv_prep_kernel(InvconvParams q, int C, int reverse, int transpose, float* _
   __syncthreads();
   // fused affine in "out" layout: out[a][b] multiplies input channel b into output channel a
   float* Out = Um;  // reuse
-  __syncthreads();
   for (int i = tid; i < CC; i += blockDim.x) {
     const int a = i / C, b = i % C;
     float v;
     if (!reverse) v = (transpose ? Wplain[b * C + a] : Wplain[i]) * expf(q.an_logs[b]);
     else v = (transpose ? Winv[b * C + a] : Winv[i]) * expf(-q.an_logs[a]);
     Out[i] = v;
-    outW[i] = v;
+    q.outW[i] = v;
   }
   __syncthreads();
-  for (int a = tid; a < C; a += blockDim.x) {
-    float t;
+  // b' = W' bias: one warp per output row
+  const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+  for (int a = warp; a < C; a += nwarps) {
     if (!reverse) {
-      t = 0.f;
-      for (int b = 0; b < C; ++b) t = fmaf(Out[a * C + b], q.an_bias[b], t);
-    } else {
-      t = -q.an_bias[a];
+      float t = 0.f;
+      for (int b = lane; b < C; b += 32) t = fmaf(Out[a * C + b], q.an_bias[b], t);
+      for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+      if (lane == 0) q.outb[a] = t;
+    } else if (lane == 0) {
+      q.outb[a] = -q.an_bias[a];
     }
-    outb[a] = t;
   }
-  if (tid == 0) out_sl[0] = reverse ? -lsum : lsum;
+  if (tid == 0) q.out_sl[0] = reverse ? -lsum : lsum;
+}
+
+__global__ void __launch_bounds__(INV_THREADS) invconv_prep_kernel(const __grid_constant__ InvBatch batch) {
+  extern __shared__ float sm[];
+  invconv_prep_body(batch.it[blockIdx.x], sm);
 }
 
 // Backward of the prep (either direction). Wf is the saved outW of the same direction. Outputs are overwritten.
-__global__ void __launch_bounds__(PREP_THREADS)
-invconv_prep_bwd_kernel(InvconvParams q, int C, int reverse, int transpose, const float* __restrict__ Wf,
-                        const float* __restrict__ dWf, const float* __restrict__ dbf,
-                        const float* __restrict__ g_ld, int B, float pixels, float* __restrict__ d_bias,
-                        float* __restrict__ d_logs, float* __restrict__ d_lower, float* __restrict__ d_upper,
-                        float* __restrict__ d_log_s, float* __restrict__ d_weight) {
-  extern __shared__ float sm[];
+__device__ void invconv_prep_bwd_body(const nfk_invconv_bwd_item& g, float* sm) {
+  const nfk_invconv_item& q = g.fwd;
+  const int C = q.C, reverse = q.reverse, transpose = q.transpose, ldw = g.dWf_ld;
+  const float* __restrict__ Wf = q.outW;
+  const float* __restrict__ dWf = g.dWf;
+  const float* __restrict__ dbf = g.dbf;
   float* Lm = sm;
   float* Um = Lm + C * C;
   float* G = Um + C * C;   // later dT
@@ -230,27 +247,37 @@ invconv_prep_bwd_kernel(InvconvParams q, int C, int reverse, int transpose, cons
   int* piv = perm + C;
   const int tid = threadIdx.x;
   const int CC = C * C;
+  const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
 
   float gs = 0.f;
-  if (g_ld)
-    for (int b = tid; b < B; b += blockDim.x) gs += g_ld[b];
-  float gsum = block_sum(gs, red) * pixels;
+  if (g.g_ld) {
+    const int B4 = ((reinterpret_cast<uintptr_t>(g.g_ld) & 15) == 0) ? g.B >> 2 : 0;
+    const float4* g4 = reinterpret_cast<const float4*>(g.g_ld);
+#pragma unroll 8
+    for (int b = tid; b < B4; b += blockDim.x) {
+      const float4 v = g4[b];
+      gs += (v.x + v.y) + (v.z + v.w);
+    }
+    for (int b = 4 * B4 + tid; b < g.B; b += blockDim.x) gs += g.g_ld[b];
+  }
+  float gsum = block_sum(gs, red) * g.pixels;
 
   if (!reverse) {
     // Wf[a][b] = W*[a][b] e^{logs_b}, bf = Wf bias
     for (int i = tid; i < CC; i += blockDim.x) {
       const int a = i / C, b = i % C;
-      G[i] = dWf[i] + dbf[a] * q.an_bias[b];
+      G[i] = dWf[a * ldw + b] + dbf[a] * q.an_bias[b];
+      Lm[i] = Wf[i];
     }
     __syncthreads();
     for (int b = tid; b < C; b += blockDim.x) {
       float db = 0.f, dl = 0.f;
       for (int a = 0; a < C; ++a) {
-        db = fmaf(Wf[a * C + b], dbf[a], db);
-        dl = fmaf(G[a * C + b], Wf[a * C + b], dl);
+        db = fmaf(Lm[a * C + b], dbf[a], db);
+        dl = fmaf(G[a * C + b], Lm[a * C + b], dl);
       }
-      d_bias[b] = db;
-      d_logs[b] = dl + gsum;
+      g.d_bias[b] = db;
+      g.d_logs[b] = dl + gsum;
     }
     for (int i = tid; i < CC; i += blockDim.x) {
       const int r = i / C, c = i % C;
@@ -260,11 +287,14 @@ invconv_prep_bwd_kernel(InvconvParams q, int C, int reverse, int transpose, cons
   } else {
     // Wf[a][b] = Winv*[a][b] e^{-logs_a}, bf = -bias, log-det enters with a minus sign
     gsum = -gsum;
-    for (int a = tid; a < C; a += blockDim.x) {
+    for (int a = warp; a < C; a += nwarps) {
       float dl = 0.f;
-      for (int b = 0; b < C; ++b) dl = fmaf(dWf[a * C + b], Wf[a * C + b], dl);
-      d_bias[a] = -dbf[a];
-      d_logs[a] = -dl + gsum;
+      for (int b = lane; b < C; b += 32) dl = fmaf(dWf[a * ldw + b], Wf[a * C + b], dl);
+      for (int o = 16; o > 0; o >>= 1) dl += __shfl_xor_sync(0xffffffffu, dl, o);
+      if (lane == 0) {
+        g.d_bias[a] = -dbf[a];
+        g.d_logs[a] = -dl + gsum;
+      }
     }
     float* Winv = G;      // plain layout
     float* dWinv = dW;    // plain layout
@@ -273,7 +303,7 @@ invconv_prep_bwd_kernel(InvconvParams q, int C, int reverse, int transpose, cons
       const float e = expf(q.an_logs[a]);
       const int pi = transpose ? b * C + a : i;
       Winv[pi] = Wf[i] * e;
-      dWinv[pi] = dWf[i] / e;
+      dWinv[pi] = dWf[a * ldw + b] / e;
     }
     __syncthreads();
     // Lm <- dWinv Winv^T ; Um <- -Winv^T Lm  (= dL/dW)
@@ -301,22 +331,12 @@ invconv_prep_bwd_kernel(InvconvParams q, int C, int reverse, int transpose, cons
     gauss_jordan(Lm, Um, C, piv, red);
     for (int i = tid; i < CC; i += blockDim.x) {
       const int r = i / C, c = i % C;
-      d_weight[i] = dW[i] + gsum * Um[c * C + r];
+      g.d_weight[i] = dW[i] + gsum * Um[c * C + r];
     }
     return;
   }
-  for (int i = tid; i < CC; i += blockDim.x) {
-    const int r = i / C, c = i % C;
-    Lm[i] = c < r ? q.lower[i] : (c == r ? 1.f : 0.f);
-    Um[i] = c > r ? q.upper[i] : (c == r ? q.sign_s[r] * expf(q.log_s[r]) : 0.f);
-  }
-  for (int r = tid; r < C; r += blockDim.x) {
-    int best = 0;
-    float bv = q.p[r * C];
-    for (int c = 1; c < C; ++c)
-      if (q.p[r * C + c] > bv) { bv = q.p[r * C + c]; best = c; }
-    perm[r] = best;
-  }
+  load_lu(q, C, Lm, Um);
+  load_perm(q.p, C, perm);
   __syncthreads();
   float* dT = G;  // dT[perm[o]][i] = dW[o][i]
   for (int i = tid; i < CC; i += blockDim.x) {
@@ -330,14 +350,20 @@ invconv_prep_bwd_kernel(InvconvParams q, int C, int reverse, int transpose, cons
     float dl = 0.f;
     if (k < r)
       for (int c = k; c < C; ++c) dl = fmaf(dT[r * C + c], Um[k * C + c], dl);
-    d_lower[i] = dl;
+    g.d_lower[i] = dl;
     // dUm[r][k] = sum_{rr>=r} Lm[rr][r] dT[rr][k]   (here (r,k) indexes U)
     float du = 0.f;
     if (k >= r)
       for (int rr = r; rr < C; ++rr) du = fmaf(Lm[rr * C + r], dT[rr * C + k], du);
-    d_upper[i] = k > r ? du : 0.f;
-    if (k == r) d_log_s[r] = du * Um[r * C + r] + gsum;
+    g.d_upper[i] = k > r ? du : 0.f;
+    if (k == r) g.d_log_s[r] = du * Um[r * C + r] + gsum;
   }
+}
+
+__global__ void __launch_bounds__(INV_THREADS)
+invconv_prep_bwd_kernel(const __grid_constant__ InvBwdBatch batch) {
+  extern __shared__ float sm[];
+  invconv_prep_bwd_body(batch.it[blockIdx.x], sm);
 }
 
 // ------------------------------------------------------------------------------------------ coupling weights
@@ -469,19 +495,66 @@ static int prep_smem(int C) { return (4 * C * C + 32 + C + 4) * static_cast<int>
 
 using namespace nfk;
 
+static int check_item(const nfk_invconv_item& q) {
+  if (q.C <= 0 || q.C > 104) return NFK_ERR_SHAPE;
+  if (!q.an_bias || !q.an_logs || !q.outW || !q.outb || !q.out_sl) return NFK_ERR_ARG;
+  if (!q.weight && (!q.lower || !q.upper || !q.log_s || !q.p || !q.sign_s)) return NFK_ERR_ARG;
+  return NFK_OK;
+}
+
+extern "C" int nfk_invconv_prep_batch(int n, const nfk_invconv_item* items, void* stream) {
+  if (n < 0) return NFK_ERR_SHAPE;
+  if (n && !items) return NFK_ERR_ARG;
+  int cmax = 0;
+  for (int i = 0; i < n; ++i) {
+    if (int rc = check_item(items[i])) return rc;
+    cmax = items[i].C > cmax ? items[i].C : cmax;
+  }
+  const int smem = prep_smem(cmax);
+  if (n)
+    if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(invconv_prep_kernel), smem)) return rc;
+  for (int i0 = 0; i0 < n; i0 += INV_MAX_BATCH) {
+    InvBatch b{};
+    const int m = n - i0 < INV_MAX_BATCH ? n - i0 : INV_MAX_BATCH;
+    for (int i = 0; i < m; ++i) b.it[i] = items[i0 + i];
+    invconv_prep_kernel<<<m, INV_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(b);
+    if (cudaGetLastError() != cudaSuccess) return NFK_ERR_LAUNCH;
+  }
+  return NFK_OK;
+}
+
+extern "C" int nfk_invconv_prep_bwd_batch(int n, const nfk_invconv_bwd_item* items, void* stream) {
+  if (n < 0) return NFK_ERR_SHAPE;
+  if (n && !items) return NFK_ERR_ARG;
+  int cmax = 0;
+  for (int i = 0; i < n; ++i) {
+    const nfk_invconv_bwd_item& g = items[i];
+    if (int rc = check_item(g.fwd)) return rc;
+    if (g.B <= 0 || g.dWf_ld < g.fwd.C) return NFK_ERR_SHAPE;
+    if (!g.dWf || !g.dbf || !g.d_bias || !g.d_logs) return NFK_ERR_ARG;
+    if (g.fwd.weight ? !g.d_weight : (!g.d_lower || !g.d_upper || !g.d_log_s)) return NFK_ERR_ARG;
+    cmax = g.fwd.C > cmax ? g.fwd.C : cmax;
+  }
+  const int smem = prep_smem(cmax);
+  if (n)
+    if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(invconv_prep_bwd_kernel), smem)) return rc;
+  for (int i0 = 0; i0 < n; i0 += INV_MAX_BATCH) {
+    InvBwdBatch b{};
+    const int m = n - i0 < INV_MAX_BATCH ? n - i0 : INV_MAX_BATCH;
+    for (int i = 0; i < m; ++i) b.it[i] = items[i0 + i];
+    invconv_prep_bwd_kernel<<<m, INV_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(b);
+    if (cudaGetLastError() != cudaSuccess) return NFK_ERR_LAUNCH;
+  }
+  return NFK_OK;
+}
+
 extern "C" int nfk_invconv_prep(const float* an_bias, const float* an_logs, const float* lower, const float* upper,
                                 const float* log_s, const float* p, const float* sign_s, const float* weight,
                                 int C, int reverse, int transpose, float* outW, float* outb, float* out_sl,
                                 void* stream) {
-  if (C <= 0 || C > 104) return NFK_ERR_SHAPE;
-  if (!an_bias || !an_logs || !outW || !outb || !out_sl) return NFK_ERR_ARG;
-  if (!weight && (!lower || !upper || !log_s || !p || !sign_s)) return NFK_ERR_ARG;
-  InvconvParams q{an_bias, an_logs, lower, upper, log_s, p, sign_s, weight};
-  const int smem = prep_smem(C);
-  if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(invconv_prep_kernel), smem)) return rc;
-  invconv_prep_kernel<<<1, PREP_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(q, C, reverse, transpose, outW,
-                                                                                  outb, out_sl);
-  return cudaGetLastError() == cudaSuccess ? NFK_OK : NFK_ERR_LAUNCH;
+  const nfk_invconv_item q{an_bias, an_logs, lower, upper, log_s, p, sign_s, weight, C, reverse, transpose,
+                           outW, outb, out_sl};
+  return nfk_invconv_prep_batch(1, &q, stream);
 }
 
 extern "C" int nfk_invconv_prep_bwd(const float* an_bias, const float* an_logs, const float* lower,
@@ -491,15 +564,14 @@ extern "C" int nfk_invconv_prep_bwd(const float* an_bias, const float* an_logs, 
                                     float* d_bias,
                                     float* d_logs, float* d_lower, float* d_upper, float* d_log_s, float* d_weight,
                                     void* stream) {
-  if (C <= 0 || C > 104 || B <= 0) return NFK_ERR_SHAPE;
-  if (!Wf || !dWf || !dbf || !d_bias || !d_logs) return NFK_ERR_ARG;
-  if (weight ? !d_weight : (!d_lower || !d_upper || !d_log_s)) return NFK_ERR_ARG;
-  InvconvParams q{an_bias, an_logs, lower, upper, log_s, p, sign_s, weight};
-  const int smem = prep_smem(C);
-  if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(invconv_prep_bwd_kernel), smem)) return rc;
-  invconv_prep_bwd_kernel<<<1, PREP_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(
-      q, C, reverse, transpose, Wf, dWf, dbf, g_ld, B, pixels, d_bias, d_logs, d_lower, d_upper, d_log_s, d_weight);
-  return cudaGetLastError() == cudaSuccess ? NFK_OK : NFK_ERR_LAUNCH;
+  if (!Wf) return NFK_ERR_ARG;
+  nfk_invconv_bwd_item g{};
+  g.fwd = nfk_invconv_item{an_bias, an_logs, lower, upper, log_s, p, sign_s, weight, C, reverse, transpose,
+                           const_cast<float*>(Wf), const_cast<float*>(Wf), const_cast<float*>(Wf)};
+  g.dWf = dWf; g.dWf_ld = C; g.dbf = dbf; g.g_ld = g_ld; g.B = B; g.pixels = pixels;
+  g.d_bias = d_bias; g.d_logs = d_logs; g.d_lower = d_lower; g.d_upper = d_upper; g.d_log_s = d_log_s;
+  g.d_weight = d_weight;
+  return nfk_invconv_prep_bwd_batch(1, &g, stream);
 }
 
 extern "C" int nfk_coupling_prep(const float* w1, const float* b1, const float* l1, const float* w2, const float* b2,

@@ -25,9 +25,10 @@ def _mlp_params(step):
     return ws, bs
 
 
-def _pack(step, reverse, with_bwd, an_bias, an_logs, inv, ws, bs):
+def _pack(step, reverse, with_bwd, affine, ws, bs):
+    """affine = (Wf, bf, sl) of this direction (nfk_invconv_prep with transpose=1)."""
     D, Cc, hid = step.in_channels, step.condition_features, step.hidden_channels
-    Wf, bf, sl = Fn.build_affine(an_bias, an_logs, inv, D, reverse, True)
+    Wf, bf, sl = affine
     tf, tb, tg, n_act, offs = ops.flow1d_sizes(D, Cc, hid)
     dev = Wf.device
     PF = torch.empty(tf, device=dev, dtype=F32)
@@ -44,40 +45,41 @@ def _consts(step, reverse):
         return hit[1]
     ws, bs = _mlp_params(step)
     inv = tuple(None if t is None else t.detach() for t in step.invconv.lu_tensors())
-    out = _pack(step, reverse, False, step.actnorm.bias.detach(), step.actnorm.logs.detach(), inv,
-                [w.detach() for w in ws], [b.detach() for b in bs])
+    affine = Fn.build_affine(step.actnorm.bias.detach(), step.actnorm.logs.detach(), inv, step.in_channels, reverse,
+                             True)
+    out = _pack(step, reverse, False, affine, [w.detach() for w in ws], [b.detach() for b in bs])
     step._cache[("1d", reverse)] = (key, out)
     return out
 
 
 class FlowStep1dFn(torch.autograd.Function):
     """Differentiable 1-D FlowStep in either direction (the tabular configs train through the inverse pass:
-    perceptual L1 on reverse-pass samples, conf/training/tabular.yaml:11-19)."""
+    perceptual L1 on reverse-pass samples, conf/training/tabular.yaml:11-19). The fused affine comes from the batched
+    prep (functional.PrepCtx); its parameter-space backward is deferred to PrepAllFn.backward."""
 
     @staticmethod
-    def forward(ctx, x, ld_in, cond, step, reverse, an_bias, an_logs, lower, upper, log_s, p, sign_s, *mlp):
+    def forward(ctx, x, ld_in, cond, step, reverse, token, pctx, idx, *mlp):
         ws, bs = list(mlp[:6]), list(mlp[6:])
         D, Cc, hid = step.in_channels, step.condition_features, step.hidden_channels
         B = x.shape[0]
         x = x.contiguous()
         cond = None if cond is None else cond.contiguous()
-        Wf, sl, PF, PB, (tg, n_act, offs) = _pack(step, reverse, True, an_bias, an_logs,
-                                                  (lower, upper, log_s, p, sign_s, None), ws, bs)
+        Wf, sl, PF, PB, (tg, n_act, offs) = _pack(step, reverse, True, pctx.consts[idx], ws, bs)
         acts = torch.empty(B, n_act, device=x.device, dtype=F32)
         y = torch.empty_like(x)
         ld_out = torch.empty(B, device=x.device, dtype=F32)
         ops.flow1d_fwd(x, cond, PF, sl, y, ld_in.contiguous(), ld_out, acts, B, D, Cc, hid, reverse)
         ctx.meta = (D, Cc, hid, reverse, tg, offs, cond is not None)
-        ctx.save_for_backward(x, acts, PF, PB, Wf, an_bias, an_logs, lower, upper, log_s, p, sign_s,
-                              *([cond] if cond is not None else []), *ws, *bs)
+        ctx.pctx, ctx.idx = pctx, idx
+        ctx.save_for_backward(x, acts, y, PB, *([cond] if cond is not None else []), *ws, *bs)
         return y, ld_out
 
     @staticmethod
     def backward(ctx, g_y, g_ld):
         D, Cc, hid, reverse, tg, offs, has_cond = ctx.meta
         saved = ctx.saved_tensors
-        x, acts, PF, PB, Wf, an_bias, an_logs, lower, upper, log_s, p, sign_s = saved[:12]
-        rest = saved[12:]
+        x, acts, y_out, PB = saved[:4]
+        rest = saved[4:]
         cond = rest[0] if has_cond else None
         ws = rest[1:7] if has_cond else rest[0:6]
         B = x.shape[0]
@@ -86,21 +88,18 @@ class FlowStep1dFn(torch.autograd.Function):
         g_ld = torch.zeros(B, device=dev, dtype=F32) if g_ld is None else g_ld.contiguous()
         G = torch.zeros(tg, device=dev, dtype=F32)
         dx = torch.empty_like(x)
-        ops.flow1d_bwd(x, cond, acts, PB, PF, g_y, g_ld, dx, G, B, D, Cc, hid, reverse)
+        ops.flow1d_bwd(x, cond, acts, PB, y_out, g_y, g_ld, dx, G, B, D, Cc, hid, reverse)
         offG, offGB, ninp, _ = offs[0]
-        dWf = G[offG:offG + D * ninp].view(D, ninp)[:, :D].contiguous()
-        dbf = G[offGB:offGB + D].contiguous()
-        d_bias, d_logs = torch.empty_like(an_bias), torch.empty_like(an_logs)
-        d_lower, d_upper, d_log_s = torch.empty_like(lower), torch.empty_like(upper), torch.empty_like(log_s)
-        ops.invconv_prep_bwd(an_bias, an_logs, lower, upper, log_s, p, sign_s, None, D, reverse, True, Wf, dWf, dbf,
-                             g_ld, B, 1.0, d_bias, d_logs, d_lower, d_upper, d_log_s, None)
+        dWf = G[offG:offG + D * ninp]          # [D, ninp] rows, the first D columns of each are dW'
+        dbf = G[offGB:offGB + D]
+        ctx.pctx.grads[ctx.idx] = (dWf, ninp, dbf, g_ld, B, 1.0)
         dws, dbs = [], []
         for l in range(1, 7):
             offG, offGB, ninp, _ = offs[l]
             nout, nin = ws[l - 1].shape
             dws.append(G[offG:offG + nout * ninp].view(nout, ninp)[:, :nin])
             dbs.append(G[offGB:offGB + nout])
-        return (dx, g_ld, None, None, None, d_bias, d_logs, d_lower, d_upper, d_log_s, None, None, *dws, *dbs)
+        return (dx, g_ld, None, None, None, None, None, None, *dws, *dbs)
 
 
 def flowstep1d(step, input, y_onehot, logdet, reverse):
@@ -117,10 +116,9 @@ def flowstep1d(step, input, y_onehot, logdet, reverse):
     if needs_grad:
         if not step.invconv.LU_decomposed:
             raise NotImplementedError("training with LU_decomposed=False is not built")
-        iv = step.invconv
         ws, bs = _mlp_params(step)
-        z, ld_out = FlowStep1dFn.apply(input, ld, cond, step, bool(reverse), step.actnorm.bias, step.actnorm.logs,
-                                       iv.lower, iv.upper, iv.log_s, iv.p, iv.sign_s, *ws, *bs)
+        pctx, idx = Fn.prep_for(step, bool(reverse))
+        z, ld_out = FlowStep1dFn.apply(input, ld, cond, step, bool(reverse), pctx.token, pctx, idx, *ws, *bs)
     else:
         Wf, sl, PF, _, _ = _consts(step, bool(reverse))
         x = input.contiguous()

@@ -47,6 +47,135 @@ def build_affine(an_bias, an_logs, inv, C, reverse, transpose):
     return Wf, bf, sl
 
 
+# ------------------------------------------------------------------------------------ batched affine build (K0)
+class PrepCtx:
+    """The fused ActNorm o invconv matrices of a set of FlowSteps built by ONE launch, and their deferred backward.
+
+    Forward: `PrepAllFn` runs nfk_invconv_prep_batch (one CTA per step) and leaves (Wf, bf, sl) per step in
+    `consts`. Each step's autograd Function takes the returned `token` as an input, so the autograd graph knows the
+    steps depend on the prep; in its backward the step deposits (dWf, dbf, g_ld) in `grads` instead of running its own
+    parameter-space kernel. `PrepAllFn.backward` runs after every step (it is their common ancestor) and turns all the
+    deposits into parameter gradients with one nfk_invconv_prep_bwd_batch launch."""
+
+    def __init__(self, steps, reverse: bool):
+        self.steps = list(steps)
+        self.reverse = bool(reverse)
+        self.index = {id(s): i for i, s in enumerate(self.steps)}
+        self.consts = [None] * len(self.steps)
+        self.items = [None] * len(self.steps)
+        self.grads = [None] * len(self.steps)
+        self.token = None
+
+    def build(self):
+        flat = []
+        for st in self.steps:
+            iv = st.invconv
+            flat += [st.actnorm.bias, st.actnorm.logs, iv.lower, iv.upper, iv.log_s]
+        self.token = PrepAllFn.apply(self, *flat)
+        return self
+
+    def lookup(self, step, reverse):
+        i = self.index.get(id(step))
+        return None if i is None or self.reverse != bool(reverse) else i
+
+
+_PREP_STACK: list = []
+
+
+class use_prep:
+    """Context manager: steps called inside find their batched constants in `pctx` (None = no batching)."""
+
+    def __init__(self, pctx):
+        self.pctx = pctx
+
+    def __enter__(self):
+        if self.pctx is not None:
+            _PREP_STACK.append(self.pctx)
+        return self.pctx
+
+    def __exit__(self, *exc):
+        if self.pctx is not None:
+            _PREP_STACK.pop()
+        return False
+
+
+def prep_for(step, reverse):
+    """(pctx, index) of the innermost active batch that holds `step`, else a one-step batch built on the spot."""
+    for pctx in reversed(_PREP_STACK):
+        i = pctx.lookup(step, reverse)
+        if i is not None:
+            return pctx, i
+    return PrepCtx([step], reverse).build(), 0
+
+
+def prepare_steps(layers, reverse):
+    """Batch every trainable LU-decomposed FlowStep in `layers` (called by FlowNet.encode/decode under grad)."""
+    if not torch.is_grad_enabled():
+        return None
+    steps = [l for l in layers if getattr(l, "_batched_prep_ok", None) is not None and l._batched_prep_ok()
+             and l.actnorm.logs.requires_grad]
+    if len(steps) < 2 or (reverse and not steps[0].is_1d):   # gradients through the 2-D inverse are not built
+        return None
+    return PrepCtx(steps, reverse).build()
+
+
+class PrepAllFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pctx, *flat):
+        dev = flat[0].device
+        sizes = [(st.in_channels * st.in_channels, st.in_channels, 1) for st in pctx.steps]
+        total = sum(ops.round_up(a, 4) + ops.round_up(b, 4) + 4 for a, b, _ in sizes)
+        buf = torch.empty(total, device=dev, dtype=F32)
+        off = 0
+        items = []
+        for i, st in enumerate(pctx.steps):
+            C = st.in_channels
+            Wf = buf[off:off + C * C].view(C, C); off += ops.round_up(C * C, 4)
+            bf = buf[off:off + C]; off += ops.round_up(C, 4)
+            sl = buf[off:off + 1]; off += 4
+            an_bias, an_logs, lower, upper, log_s = flat[5 * i:5 * i + 5]
+            it = ops.invconv_item(an_bias, an_logs, lower, upper, log_s, st.invconv.p, st.invconv.sign_s, None, C,
+                                  pctx.reverse, st.is_1d, Wf, bf, sl)
+            items.append(it)
+            pctx.consts[i] = (Wf, bf, sl)
+            pctx.items[i] = it
+        ops.invconv_prep_batch(items)
+        ctx.pctx = pctx
+        ctx.set_materialize_grads(False)
+        ctx.save_for_backward(*flat)
+        return torch.empty(1, device=dev, dtype=F32)
+
+    @staticmethod
+    def backward(ctx, _g_token):
+        pctx = ctx.pctx
+        flat = ctx.saved_tensors
+        dev = flat[0].device
+        n = len(pctx.steps)
+        live = [i for i in range(n) if pctx.grads[i] is not None]
+        sizes = []
+        for i in live:
+            C = pctx.steps[i].in_channels
+            sizes += [C, C, C * C, C * C, C]
+        offs = [0]
+        for sz in sizes:
+            offs.append(offs[-1] + ops.round_up(sz, 4))
+        arena = torch.empty(offs[-1], device=dev, dtype=F32)
+        out = [None] * (5 * n)
+        items = []
+        for j, i in enumerate(live):
+            C = pctx.steps[i].in_channels
+            d = [arena[offs[5 * j + k]:offs[5 * j + k] + sizes[5 * j + k]] for k in range(5)]
+            d_bias, d_logs = d[0].view_as(flat[5 * i]), d[1].view_as(flat[5 * i + 1])
+            d_lower, d_upper, d_log_s = d[2].view(C, C), d[3].view(C, C), d[4].view_as(flat[5 * i + 4])
+            dWf, dWf_ld, dbf, g_ld, B, pixels = pctx.grads[i]
+            items.append(ops.invconv_bwd_item(pctx.items[i], dWf.data_ptr(), dWf_ld, dbf, g_ld, B, pixels, d_bias,
+                                              d_logs, d_lower, d_upper, d_log_s))
+            out[5 * i:5 * i + 5] = [d_bias, d_logs, d_lower, d_upper, d_log_s]
+        ops.invconv_prep_bwd_batch(items)
+        pctx.grads = [None] * n
+        return (None, *out)
+
+
 def build_coupling_ops(cw, cin, hid, cout, with_t):
     """cw = (w1, b1, l1, w2, b2, l2, w3, b3, l3) reference parameters of get_block_2d."""
     dev = cw[0].device
@@ -117,26 +246,25 @@ def flowstep2d_reverse(z, ld_in, k: StepConsts, hid):
 
 
 class FlowStep2dFn(torch.autograd.Function):
-    """Differentiable 2-D FlowStep forward. Inputs: x, logdet, then the 14 reference parameters and 2 buffers."""
+    """Differentiable 2-D FlowStep forward. Inputs: x, logdet, the prep token (see PrepCtx; the fused affine comes from
+    pctx.consts[idx]), then the 9 reference parameters of the coupling net."""
 
     @staticmethod
-    def forward(ctx, x, ld_in, hid, an_bias, an_logs, lower, upper, log_s, p, sign_s, w1, b1, l1, w2, b2, l2, w3,
-                b3, l3):
+    def forward(ctx, x, ld_in, hid, token, pctx, idx, w1, b1, l1, w2, b2, l2, w3, b3, l3):
         B, C, H, W = x.shape
         x = x.contiguous()
-        Wf, bf, sl = build_affine(an_bias, an_logs, (lower, upper, log_s, p, sign_s, None), C, False, False)
+        Wf, bf, sl = pctx.consts[idx]
         cw = (w1, b1, l1, w2, b2, l2, w3, b3, l3)
         k = StepConsts(Wf, bf, sl, *build_coupling_ops(cw, C // 2, hid, C, True))
         y, ld_out, (col, h1, h2, hsave, m1, m2) = flowstep2d_forward(x, ld_in.contiguous(), k, hid, keep=True)
         ctx.hid = hid
-        ctx.save_for_backward(x, y, col, h1, h2, hsave, m1, m2, Wf, k.B1T, k.B2T, k.B3T, an_bias, an_logs, lower,
-                              upper, log_s, p, sign_s, *cw)
+        ctx.pctx, ctx.idx = pctx, idx
+        ctx.save_for_backward(x, y, col, h1, h2, hsave, m1, m2, Wf, k.B1T, k.B2T, k.B3T, *cw)
         return y, ld_out
 
     @staticmethod
     def backward(ctx, g_out, g_ld):
-        (x, z_out, col, h1, h2, hsave, m1, m2, Wf, B1T, B2T, B3T, an_bias, an_logs, lower, upper, log_s, p, sign_s,
-         *cw) = ctx.saved_tensors
+        (x, z_out, col, h1, h2, hsave, m1, m2, Wf, B1T, B2T, B3T, *cw) = ctx.saved_tensors
         hid = ctx.hid
         B, C, H, W = x.shape
         M, cin = B * H * W, C // 2
@@ -168,13 +296,11 @@ class FlowStep2dFn(torch.autograd.Function):
         dx = torch.empty_like(x)
         ops.affine1x1_bwd(dy, dcol, K1p, x, Wf, dx, dWf, dbf, B, C, H, W)
 
-        d_an_bias, d_an_logs = torch.empty_like(an_bias), torch.empty_like(an_logs)
-        d_lower, d_upper, d_log_s = torch.empty_like(lower), torch.empty_like(upper), torch.empty_like(log_s)
-        ops.invconv_prep_bwd(an_bias, an_logs, lower, upper, log_s, p, sign_s, None, C, False, False, Wf, dWf, dbf, g_ld, B,
-                             H * W, d_an_bias, d_an_logs, d_lower, d_upper, d_log_s, None)
+        # the parameter-space chain rule of the fused affine is deferred to PrepAllFn.backward (one batched launch)
+        ctx.pctx.grads[ctx.idx] = (dWf, C, dbf, g_ld, B, float(H * W))
         grads = [torch.empty_like(t) for t in cw]
         ops.coupling_prep_bwd(*cw, cin, hid, C, K1p, K3p, dB1, dbias1, dB2, dbias2, dB3, dbias3, *grads)
-        return (dx, g_ld, None, d_an_bias, d_an_logs, d_lower, d_upper, d_log_s, None, None, *grads)
+        return (dx, g_ld, None, None, None, None, *grads)
 
 
 # ------------------------------------------------------------------------------------------------ Split2d

@@ -109,6 +109,11 @@ class FlowStep(nn.Module):
         self._cache[reverse] = (key, k)
         return k
 
+    def _batched_prep_ok(self):
+        """True when this step's fused affine can be built by the batched K0 launch (functional.PrepCtx)."""
+        return (self.flow_permutation_type == "invconv" and self.invconv.LU_decomposed
+                and self.flow_coupling == "affine")
+
     def _check_supported(self, input):
         _require_cuda(input, "FlowStep")
         if self.flow_permutation_type != "invconv" or self.flow_coupling != "affine":
@@ -140,9 +145,8 @@ class FlowStep(nn.Module):
             if needs_grad:
                 if not self.invconv.LU_decomposed:
                     raise NotImplementedError("training with LU_decomposed=False is not built")
-                iv = self.invconv
-                z, ld_out = Fn.FlowStep2dFn.apply(input, ld, self.hidden_channels, self.actnorm.bias,
-                                                  self.actnorm.logs, iv.lower, iv.upper, iv.log_s, iv.p, iv.sign_s,
+                pctx, idx = Fn.prep_for(self, False)
+                z, ld_out = Fn.FlowStep2dFn.apply(input, ld, self.hidden_channels, pctx.token, pctx, idx,
                                                   *self._coupling_params_2d())
             else:
                 z, ld_out, _ = Fn.flowstep2d_forward(input.contiguous(), ld.contiguous(), self._consts(False),
@@ -199,16 +203,18 @@ class FlowNet(nn.Module):
         return self.encode(input, y_onehot=y_onehot, logdet=logdet)
 
     def encode(self, z, y_onehot=None, logdet=0.0):
-        for layer in self.layers:
-            z, logdet = layer(z, y_onehot=y_onehot, logdet=logdet, reverse=False)
+        with Fn.use_prep(Fn.prepare_steps(self.layers, False)):   # one K0 launch for every trainable step
+            for layer in self.layers:
+                z, logdet = layer(z, y_onehot=y_onehot, logdet=logdet, reverse=False)
         return z, logdet
 
     def decode(self, z, y_onehot=None, temperature=None):
-        for layer in reversed(self.layers):
-            if isinstance(layer, Split2d):
-                z, _ = layer(z, logdet=0, reverse=True, temperature=temperature)
-            else:
-                z, _ = layer(z, y_onehot=y_onehot, logdet=0, reverse=True)
+        with Fn.use_prep(Fn.prepare_steps(self.layers, True)):
+            for layer in reversed(self.layers):
+                if isinstance(layer, Split2d):
+                    z, _ = layer(z, logdet=0, reverse=True, temperature=temperature)
+                else:
+                    z, _ = layer(z, y_onehot=y_onehot, logdet=0, reverse=True)
         return z
 
 

@@ -7,6 +7,7 @@ import typing as tp
 
 import torch
 
+from .. import functional as Fn
 from .flows import FlowNet, FlowStep, Glow
 from .layers import Split2d, _require_cuda
 from .utils import uniform_binning_correction
@@ -19,19 +20,21 @@ class FlowNetGetAllOutputs(FlowNet):
 
     def encode(self, z, y_onehot=None, logdet=0.0):
         all_outputs = []
-        for layer in self.layers:
-            z, logdet = layer(z, y_onehot=y_onehot, logdet=logdet, reverse=False)
-            all_outputs.append(z)
+        with Fn.use_prep(Fn.prepare_steps(self.layers, False)):   # one K0 launch for every trainable step
+            for layer in self.layers:
+                z, logdet = layer(z, y_onehot=y_onehot, logdet=logdet, reverse=False)
+                all_outputs.append(z)
         return all_outputs, logdet
 
     def decode(self, z, y_onehot=None, temperature=None):
         all_outputs = []
-        for layer in reversed(self.layers):
-            if isinstance(layer, Split2d):
-                z, _ = layer(z, logdet=0, reverse=True, temperature=temperature)
-            else:
-                z, _ = layer(z, y_onehot=y_onehot, logdet=0, reverse=True)
-            all_outputs.append(z)
+        with Fn.use_prep(Fn.prepare_steps(self.layers, True)):
+            for layer in reversed(self.layers):
+                if isinstance(layer, Split2d):
+                    z, _ = layer(z, logdet=0, reverse=True, temperature=temperature)
+                else:
+                    z, _ = layer(z, y_onehot=y_onehot, logdet=0, reverse=True)
+                all_outputs.append(z)
         return all_outputs
 
 

@@ -3,6 +3,8 @@ codes -> exceptions. No arithmetic happens here and there is no fallback path: e
 """
 from __future__ import annotations
 
+import ctypes
+
 import torch
 
 from ._lib import LIB, check
@@ -86,6 +88,41 @@ def invconv_prep_bwd(an_bias, an_logs, lower, upper, log_s, p, sign_s, weight, C
                                    B,
                                    float(pixels), _p(d_bias), _p(d_logs), _p(d_lower), _p(d_upper), _p(d_log_s),
                                    _p(d_weight), _st()), "nfk_invconv_prep_bwd")
+
+
+def invconv_item(an_bias, an_logs, lower, upper, log_s, p, sign_s, weight, C, reverse, transpose, outW, outb, out_sl):
+    """One nfk_invconv_item (the argument list of invconv_prep) for the batched launch."""
+    from ._lib import InvconvItem
+    return InvconvItem(_p(an_bias), _p(an_logs), _p(lower), _p(upper), _p(log_s), _p(p), _p(sign_s), _p(weight), C,
+                       int(reverse), int(transpose), _p(outW), _p(outb), _p(out_sl))
+
+
+def invconv_prep_batch(items):
+    """Fused ActNorm o invconv matrices of many FlowSteps in one launch (one CTA per step)."""
+    from ._lib import InvconvItem
+    n = len(items)
+    if not n:
+        return
+    arr = (InvconvItem * n)(*items)
+    _count((n + 23) // 24)
+    check(LIB.nfk_invconv_prep_batch(n, ctypes.addressof(arr), _st()), "nfk_invconv_prep_batch")
+
+
+def invconv_bwd_item(fwd_item, dWf_ptr, dWf_ld, dbf, g_ld, B, pixels, d_bias, d_logs, d_lower, d_upper, d_log_s,
+                     d_weight=None):
+    from ._lib import InvconvBwdItem
+    return InvconvBwdItem(fwd_item, dWf_ptr, dWf_ld, _p(dbf), _p(g_ld), B, float(pixels), _p(d_bias), _p(d_logs),
+                          _p(d_lower), _p(d_upper), _p(d_log_s), _p(d_weight))
+
+
+def invconv_prep_bwd_batch(items):
+    from ._lib import InvconvBwdItem
+    n = len(items)
+    if not n:
+        return
+    arr = (InvconvBwdItem * n)(*items)
+    _count((n + 23) // 24)
+    check(LIB.nfk_invconv_prep_bwd_batch(n, ctypes.addressof(arr), _st()), "nfk_invconv_prep_bwd_batch")
 
 
 def coupling_prep(w1, b1, l1, w2, b2, l2, w3, b3, l3, cin, hid, cout, K1p, K3p, B1, B1T, B2, B2T, B3, B3T, bias1,
@@ -195,9 +232,9 @@ def flow1d_fwd(x, cond, PF, sl, y, ld_in, ld_out, acts, B, D, Cc, hid, reverse):
                              int(reverse), _st()), "nfk_flow1d_fwd")
 
 
-def flow1d_bwd(x_in, cond, acts, PB, PF, g_out, g_ld, dx, G, B, D, Cc, hid, reverse):
+def flow1d_bwd(x_in, cond, acts, PB, y_out, g_out, g_ld, dx, G, B, D, Cc, hid, reverse):
     _count()
-    check(LIB.nfk_flow1d_bwd(_p(x_in), _p(cond), _p(acts), _p(PB), _p(PF), _p(g_out), _p(g_ld), _p(dx), _p(G), B, D,
+    check(LIB.nfk_flow1d_bwd(_p(x_in), _p(cond), _p(acts), _p(PB), _p(y_out), _p(g_out), _p(g_ld), _p(dx), _p(G), B, D,
                              Cc, hid, int(reverse), _st()), "nfk_flow1d_bwd")
 
 

@@ -460,21 +460,21 @@ flow1d_fwd_kernel(const float* __restrict__ x, const float* __restrict__ cond, c
 // (forward direction) the step OUTPUT y_out, whose first D1 features are the MLP input and whose last D2 features are
 // (y2 + shift) * scale, or (reverse direction) the step input; writes the input gradient and accumulates the
 // parameter gradients into G (global, pre-zeroed).
-// smem (floats): PB[total_bwd] | GA[total_grad] | XY[DR*ld] | GZ[DR*ld] | A0[(D1+Cc)*ld if Cc] | ACT[n_act*ld] |
+// smem (floats): PB[total_bwd] | GA[total_grad] | XY[DR*ld] | GZ[gzr*ld] | A0[(D1+Cc)*ld if Cc] | ACT[n_act*ld] |
 //                SC[scr*ld] | GL[NT]      DR = D rounded up to 8; scr = hid | D1+Cc (forward direction), DR (reverse)
 __global__ void __launch_bounds__(F1_THREADS, 1)
 flow1d_bwd_kernel(const float* __restrict__ x_in, const float* __restrict__ cond, const float* __restrict__ acts,
                   const float* __restrict__ PB, const float* __restrict__ y_out, const float* __restrict__ g_out,
                   const float* __restrict__ g_ld, float* __restrict__ dx, float* __restrict__ G, F1Dims d, int B,
-                  int reverse, int scr, F1Run run) {
+                  int reverse, int scr, int gzr, F1Run run) {
   extern __shared__ __align__(16) float sm[];
   const int NT = run.NT, lgNT = run.lgNT, ld = NT + 4;
   const int DR = up8d(d.D);
   float* W = sm;
   float* GA = W + up4(d.total_bwd);
   float* XY = GA + up4(d.total_grad);
-  float* GZ = XY + DR * ld;
-  float* A0 = GZ + DR * ld;
+  float* GZ = XY + DR * ld;      // gzr rows: D, and in the reverse direction also the MLP scratch (hid | D1+Cc)
+  float* A0 = GZ + gzr * ld;
   float* ACT = A0 + (d.Cc ? (d.D1 + d.Cc) * ld : 0);
   float* SC = ACT + d.n_act * ld;
   float* GL = SC + scr * ld;  // [NT] incoming log-det gradient of the tile
@@ -653,11 +653,11 @@ static int f1_tile_fwd(const F1Dims& d, bool save, int* smem_out, F1Run* run) {
   return 0;
 }
 
-static int f1_tile_bwd(const F1Dims& d, int scr, int* smem_out, F1Run* run) {
+static int f1_tile_bwd(const F1Dims& d, int scr, int gzr, int* smem_out, F1Run* run) {
   const int DR = up8(d.D);
   for (int nt = 128; nt >= 32; nt >>= 1) {
     const int ld = nt + 4;
-    long long fl = up4(d.total_bwd) + up4(d.total_grad) + 2LL * DR * ld + (d.Cc ? (d.D1 + d.Cc) * ld : 0) +
+    long long fl = up4(d.total_bwd) + up4(d.total_grad) + 1LL * (DR + gzr) * ld + (d.Cc ? (d.D1 + d.Cc) * ld : 0) +
                    1LL * d.n_act * ld + 1LL * scr * ld + nt;
     if (fl * 4 <= 225 * 1024) { *smem_out = static_cast<int>(fl * 4); f1_run_fill(d, nt, 1, run); return nt; }
   }
@@ -721,17 +721,21 @@ extern "C" int nfk_flow1d_bwd(const float* x_in, const float* cond, const float*
   if (B <= 0 || D < 2 || hid <= 0 || Cc < 0) return NFK_ERR_SHAPE;
   if (!x_in || !acts || !PB || !g_out || !dx || !G || (Cc && !cond) || (!reverse && !y_out)) return NFK_ERR_ARG;
   const F1Dims d = f1_dims(D, Cc, hid);
-  int scr = hid > d.nin[1] ? hid : d.nin[1];
-  if (reverse) scr = up8(D);
+  const int mlp_scr = hid > d.nin[1] ? hid : d.nin[1];  // rows the MLP backward needs for its ping-pong buffer
+  int scr = mlp_scr, gzr = up8(D);
+  if (reverse) {  // dL/dz' lives in SC, the incoming-gradient buffer becomes the MLP scratch
+    scr = up8(D);
+    gzr = gzr > mlp_scr ? gzr : mlp_scr;
+  }
   int smem = 0;
   F1Run run{};
-  const int nt = f1_tile_bwd(d, scr, &smem, &run);
+  const int nt = f1_tile_bwd(d, scr, gzr, &smem, &run);
   if (!nt) return NFK_ERR_SHAPE;
   if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(flow1d_bwd_kernel), smem)) return rc;
   const int tiles = (B + nt - 1) / nt;
   const int grid = tiles < 148 ? tiles : 148;
   flow1d_bwd_kernel<<<grid, F1_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(x_in, cond, acts, PB, y_out, g_out,
-                                                                                  g_ld, dx, G, d, B, reverse, scr, run);
+                                                                                  g_ld, dx, G, d, B, reverse, scr, gzr, run);
   return cudaGetLastError() == cudaSuccess ? NFK_OK : NFK_ERR_LAUNCH;
 }
 

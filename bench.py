@@ -27,6 +27,13 @@ WORKLOADS = {
     # per-GPU batch 1024 (weak scaling). The reference's config uses 64 (conf/training/cifar.yaml:7) on its single
     # GPU; throughput on synthetic data is quoted at the batch that fills a B200 (--batch overrides).
     "glow_cifar_kd_t32_s8": dict(image=(32, 32, 3), L=3, hidden=512, tK=32, sK=8, batch=1024),
+    # BASELINE configs[4]: Glow L=4 K=32 on CelebA-shaped 64x64x3, KD training (level-0 GEMM shape of batch 256 equals
+    # CIFAR at batch 1024: 262 144 pixels)
+    "glow_celeba_kd_t32_s8": dict(image=(64, 64, 3), L=4, hidden=512, tK=32, sK=8, batch=256),
+    # BASELINE configs[2]: Glow L=3 K=32 hidden 512, forward + inverse + log-det (no gradients); metric = samples/s
+    # through one x -> z (+ per-sample log-det / bpd) pass followed by one z -> x sampling pass
+    "glow_cifar_fwd_inv_k32": dict(image=(32, 32, 3), L=3, hidden=512, tK=32, sK=32, batch=1024, mode="fwd_inv"),
+    "glow_celeba_fwd_inv_k32": dict(image=(64, 64, 3), L=4, hidden=512, tK=32, sK=32, batch=256, mode="fwd_inv"),
     # secondary workloads (BASELINE configs[1]): BSDS300-shaped tabular KD, D = 63, reference batch 65 536
     # (conf/training/tabular.yaml: nll 0.85, kd 0.05, perceptual-L1 0.1 through the inverse pass)
     "glow1d_bsds300_kd_t5_s3": dict(image=(63,), L=1, hidden=32, s_hidden=16, tK=5, sK=3, batch=65536, is_1d=True,
@@ -92,6 +99,114 @@ class ClockSampler:
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
                 "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ forward + inverse mode
+def run_fwd_inv(args, wl, cfg_desc, warmup):
+    """BASELINE configs[2]: one x -> z pass (all layer outputs, per-sample bpd) and one z -> x pass of the K=32 model,
+    no gradients, captured in one CUDA graph. value = samples/s through the pair of passes."""
+    from nf_distillation_b200 import ops
+    from nf_distillation_b200.models import create_glow_model
+    from nf_distillation_b200.train import glow_cfg, init_distributed, randomise_zero_params
+    import torch.distributed as dist
+    rank, world, device = init_distributed()
+    B = args.batch or wl["batch"]
+    H, W, C = wl["image"]
+    torch.manual_seed(42)
+    cfg = glow_cfg(wl["image"], wl["tK"], wl["L"], wl["hidden"])
+    model = create_glow_model(cfg)
+    randomise_zero_params(model, 43, std=0.01)
+    model = model.to(device).eval()
+    n_pool = 4
+    host_pool = [synthetic_images(B, wl["image"], 1000 + rank * 100 + i).pin_memory() for i in range(n_pool)]
+    dev_pool = [h.to(device) for h in host_pool]
+    x = torch.empty(B, C, H, W, device=device)
+    res = {}
+
+    def passes():
+        with torch.no_grad():
+            outs, bpd, _ = model(x.clone(), None)
+            rev = model(z=outs[-1], temperature=0.0, reverse=True)
+            res["bpd"], res["x"] = bpd, rev[-1]
+            res["stat"] = torch.stack([bpd.mean(), rev[-1].abs().mean()])
+
+    x.copy_(dev_pool[0])
+    passes()
+    torch.cuda.synchronize()
+    c0 = ops.launch_count()
+    passes()
+    launches = ops.launch_count() - c0
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    gr = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        passes()
+        with torch.cuda.graph(gr):
+            passes()
+    torch.cuda.current_stream().wait_stream(side)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(warmup):
+        x.copy_(dev_pool[i % n_pool]); gr.replay()
+    sampler = ClockSampler(device.index or 0)
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        x.copy_(dev_pool[i % n_pool]); gr.replay()
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1) / args.steps
+    # end to end: pinned host batch -> H2D -> both passes -> D2H of (mean bpd, mean |x|)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        x.copy_(host_pool[i % n_pool], non_blocking=True); gr.replay()
+        stat = res["stat"].cpu()
+    barrier()
+    ms_e2e = (time.perf_counter() - t0) * 1e3 / args.steps
+    t = torch.tensor([ms, ms_e2e], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = t.tolist()
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import glow_oracle as O
+        cb = args.cpu_batch
+        sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+        xc = synthetic_images(cb, wl["image"], 7)
+        with torch.no_grad():
+            t0 = time.perf_counter()
+            outs, _ = O.glow_forward(sd, cfg, xc)
+            O.glow_reverse(sd, cfg, outs[-1], 0.0)
+            dt = time.perf_counter() - t0
+        cpu_base = {"value": cb / dt, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
+                    "sample": f"one forward + one inverse pass of {cb} samples (oracle/glow_oracle.py, torch CPU fp32)"}
+    if rank == 0:
+        gb = B * world
+        cfg_desc.update(per_gpu_batch=B, global_batch=gb, parallelism=f"dp{world}", cuda_graphs=True,
+                        passes="x->z (all outputs, bpd) + z->x (split parts at the prior mean, temperature 0)",
+                        l2="activations (~GBs per pass) exceed the 126 MB L2; inputs rotate over 4 batches")
+        cfg_desc.pop("student", None); cfg_desc.pop("loss", None); cfg_desc.pop("optimizer", None)
+        print(json.dumps({"metric": "fwd_inv_samples_per_sec", "value": gb / (ms * 1e-3), "unit": "samples/s",
+                          "n_gpus": world, "steps": args.steps, "warmup": warmup, "ms_per_step": ms,
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+                          "data": "synthetic", "config": cfg_desc, "clocks": clocks,
+                          "e2e": {"value": gb / (ms_e2e * 1e-3), "unit": "samples/s", "ms_per_step": ms_e2e,
+                                  "h2d_bytes_per_step": host_pool[0].numel() * 4, "d2h_bytes_per_step": 8},
+                          "gpu_launches": launches * args.steps, "gpu_launches_per_step": launches,
+                          "last": {"bpd_mean": float(stat[0]), "x_abs_mean": float(stat[1])},
+                          "roofline": None, "cpu_baseline": cpu_base}))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 # ------------------------------------------------------------------------------------------ CPU arm (oracle port)
@@ -223,6 +338,8 @@ def main():
             "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
 
+    if wl.get("mode") == "fwd_inv":
+        return run_fwd_inv(args, wl, cfg_desc, warmup)
     import torch.distributed as dist
     from nf_distillation_b200 import ops
     from nf_distillation_b200.train import KDTrainer, glow_cfg, init_distributed, kd_config

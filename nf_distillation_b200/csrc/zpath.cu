@@ -217,27 +217,31 @@ coupling_fwd_kernel(const float* __restrict__ P, int K3p, const float* __restric
 }
 
 // ------------------------------------------------------------------------------------------ coupling bwd
-// Persistent CTAs walk groups of `ipc` whole images. Phase 1 (thread = (channel pair, pixel), pixel fastest): gradient
-// of the affine coupling wrt (z2, shift, logit) from the saved h; dh goes to a smem tile. Phase 2 (thread = pixel):
-// the im2col matrix of dh for the dgrad / wgrad GEMMs with compile-time (tap, channel) positions, staged and copied out
-// in 16-byte coalesced chunks. Bias-gradient sums stay in smem across groups: one global atomic per channel and CTA.
-// smem: gs[J*ldp] os[J*ldp] dhs[C*ldp] dbs[C] | cst[pixt * (K3p/8 + 1)] 16-byte chunks
+// Persistent CTAs walk groups of `ipc` whole images, or -- when one image's staging tile does not fit (32x32 and
+// larger) -- bands of `brows` image rows with a one-row halo on either side (the halo's dh is recomputed, its side
+// effects are not repeated). Phase 1 (thread = (channel pair, pixel), pixel fastest): gradient of the affine coupling
+// wrt (z2, shift, logit) from the saved h; dh goes to a smem tile. Phase 2 (thread = pixel): the im2col matrix of dh
+// for the dgrad / wgrad GEMMs with compile-time (tap, channel) positions, staged and copied out in 16-byte coalesced
+// chunks. Bias-gradient sums stay in smem across groups: one global atomic per channel and CTA.
+// smem: dhs[C*ldp] dbs[C] | cst[tile * (K3p/8 + 1)] 16-byte chunks,  ldp = tile + 2*halo + 1
 template <int C>
 __global__ void __launch_bounds__(ZT)
 coupling_bwd_kernel(const float* __restrict__ g_out, const float* __restrict__ g_ld, const float* __restrict__ z_out,
                     const float* __restrict__ hsave, float* __restrict__ dy, __nv_bfloat16* __restrict__ dhcol,
-                    int K3p, float* __restrict__ dbias3, Geo g) {
+                    int K3p, float* __restrict__ dbias3, Geo g, int brows) {
   extern __shared__ float sm[];
   constexpr int J = C / 2;
-  const int ldp = g.pixt + 1;
-  float* gs = sm;
-  float* os = gs + J * ldp;
-  float* dhs = os + J * ldp;
+  const int bands = g.H / brows;               // > 1 only with ipc == 1
+  const bool banded = bands > 1;
+  const int halo = banded ? g.W : 0;
+  const int tile = banded ? brows * g.W : g.pixt;
+  const int ldp = tile + 2 * halo + 1;
+  float* dhs = sm;
   float* dbs = dhs + C * ldp;
-  uint4* cst = reinterpret_cast<uint4*>(dbs + ((C + 3) & ~3) + ((3 * 0)));
+  uint4* cst = reinterpret_cast<uint4*>(dbs + ((C + 3) & ~3));
   const int tid = threadIdx.x;
   const int HWm = g.HW - 1, Wm = g.W - 1;
-  const int ngroups = (g.B + g.ipc - 1) / g.ipc;
+  const int ngroups = banded ? g.B * bands : (g.B + g.ipc - 1) / g.ipc;
   constexpr int K3 = 9 * C;
   constexpr int NCH = (K3 + 7) / 8;
   const int r16 = K3p / 8, rs16 = r16 + 1;
@@ -247,30 +251,40 @@ coupling_bwd_kernel(const float* __restrict__ g_out, const float* __restrict__ g
   for (int i = tid; i < C; i += ZT) dbs[i] = 0.f;
 
   for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
-    const int b0 = grp * g.ipc;
-    const int nimg = min(g.ipc, g.B - b0);
-    const int npix = nimg << g.lgHW;
+    const int b0 = banded ? grp / bands : grp * g.ipc;
+    const int p0 = banded ? (grp - b0 * bands) * tile : 0;   // first pixel of the band inside its image
+    const int nimg = banded ? 1 : min(g.ipc, g.B - b0);
+    const int npix = banded ? tile : nimg << g.lgHW;
+    const int np2 = npix + 2 * halo;
     __syncthreads();   // previous group's tiles are free (also orders the dbs zeroing)
     // ---- phase 1
-    for (int i = tid; i < J * npix; i += ZT) {
-      const int jj = i / npix, pl = i - jj * npix;     // pixel fastest (npix is a multiple of 32 or the whole tile)
-      const int img = pl >> g.lgHW, rem = pl & HWm;
-      const long long lo = ((static_cast<long long>(b0 + img) * C + jj) << g.lgHW) + rem;
-      const long long hi = lo + (static_cast<long long>(J) << g.lgHW);
-      const long long m = (static_cast<long long>(b0) << g.lgHW) + pl;
-      dy[lo] = g_out[lo];  // z1 passes through; the coupling-net gradient is added by affine1x1_bwd
-      const float g2 = g_out[hi], o2 = z_out[hi];
-      const float2 h = *reinterpret_cast<const float2*>(hsave + m * C + 2 * jj);
-      float sg, lsv;
-      sigmoid_logsigmoid(h.y + 2.f, sg, lsv);
-      const float dsh = g2 * sg;
-      const float dlg = (g2 * o2 + g_ld[b0 + img]) * (1.f - sg);
-      dy[hi] = dsh;        // dL/dy2
-      dhs[(2 * jj) * ldp + pl] = dsh;
-      dhs[(2 * jj + 1) * ldp + pl] = dlg;
-      // bias gradient: a warp's 32 items share jj whenever npix % 32 == 0 (always for >= 2 images of >= 16 pixels)
-      float a = dsh, bsum = dlg;
-      if ((npix & 31) == 0) {
+    for (int i = tid; i < J * np2; i += ZT) {
+      const int jj = i / np2, pq = i - jj * np2;     // pixel fastest (np2 is a multiple of 32 or the whole tile)
+      const int pl = pq - halo;
+      const bool own = pl >= 0 && pl < npix;
+      const int img = banded ? 0 : pl >> g.lgHW;
+      const int rem = banded ? p0 + pl : pl & HWm;
+      float dsh = 0.f, dlg = 0.f;
+      if (rem >= 0 && rem < g.HW) {
+        const long long lo = ((static_cast<long long>(b0 + img) * C + jj) << g.lgHW) + rem;
+        const long long hi = lo + (static_cast<long long>(J) << g.lgHW);
+        const long long m = (static_cast<long long>(b0 + img) << g.lgHW) + rem;
+        const float g2 = g_out[hi], o2 = z_out[hi];
+        const float2 h = *reinterpret_cast<const float2*>(hsave + m * C + 2 * jj);
+        float sg, lsv;
+        sigmoid_logsigmoid(h.y + 2.f, sg, lsv);
+        dsh = g2 * sg;
+        dlg = (g2 * o2 + g_ld[b0 + img]) * (1.f - sg);
+        if (own) {
+          dy[lo] = g_out[lo];  // z1 passes through; the coupling-net gradient is added by affine1x1_bwd
+          dy[hi] = dsh;        // dL/dy2
+        }
+      }
+      dhs[(2 * jj) * ldp + pq] = dsh;
+      dhs[(2 * jj + 1) * ldp + pq] = dlg;
+      // bias gradient: a warp's 32 items share jj whenever np2 % 32 == 0 (always for >= 2 images of >= 16 pixels)
+      float a = own ? dsh : 0.f, bsum = own ? dlg : 0.f;
+      if ((np2 & 31) == 0) {
         for (int o = 16; o > 0; o >>= 1) {
           a += __shfl_xor_sync(0xffffffffu, a, o);
           bsum += __shfl_xor_sync(0xffffffffu, bsum, o);
@@ -283,10 +297,10 @@ coupling_bwd_kernel(const float* __restrict__ g_out, const float* __restrict__ g
     }
     __syncthreads();
     // ---- phase 2: im2col rows of dh (thread = pixel, small tiles share a pixel between GR threads)
-    const int GR = g.pixt >= ZT ? 1 : ZT / g.pixt;
-    const int gid = tid / g.pixt;
-    for (int pl = GR > 1 ? (tid & (g.pixt - 1)) : tid; pl < npix; pl += (GR > 1 ? g.pixt : ZT)) {
-      const int rem = pl & HWm;
+    const int GR = tile >= ZT ? 1 : ZT / tile;
+    const int gid = tid / tile;
+    for (int pl = GR > 1 ? (tid & (tile - 1)) : tid; pl < npix; pl += (GR > 1 ? tile : ZT)) {
+      const int rem = banded ? p0 + pl : pl & HWm;
       const int yy = rem >> g.lgW, xx = rem & Wm;
       uint32_t vmask = 0;
 #pragma unroll
@@ -294,7 +308,7 @@ coupling_bwd_kernel(const float* __restrict__ g_out, const float* __restrict__ g
         const int ny = yy - (tap / 3 - 1), nx = xx - (tap % 3 - 1);
         vmask |= (ny >= 0 && ny < g.H && nx >= 0 && nx < g.W) ? (1u << tap) : 0u;
       }
-      const float* db = dhs + pl;
+      const float* db = dhs + halo + pl;
       uint4* drow = cst + pl * rs16;
 #pragma unroll
       for (int c4 = 0; c4 < NCH; ++c4) {
@@ -316,7 +330,7 @@ coupling_bwd_kernel(const float* __restrict__ g_out, const float* __restrict__ g
         if (GR == 1 || (c4 & (GR - 1)) == gid) drow[c4] = make_uint4(0u, 0u, 0u, 0u);
     }
     __syncthreads();
-    uint4* out4 = reinterpret_cast<uint4*>(dhcol + (static_cast<long long>(b0) << g.lgHW) * K3p);
+    uint4* out4 = reinterpret_cast<uint4*>(dhcol + ((static_cast<long long>(b0) << g.lgHW) + p0) * K3p);
     for (int i = tid; i < npix * r16; i += ZT) {
       const int pl = i / r16, c4 = i - pl * r16;
       out4[i] = cst[pl * rs16 + c4];
@@ -553,19 +567,26 @@ extern "C" int nfk_coupling_bwd(const float* g_out, const float* g_ld, const flo
     return NFK_ERR_SHAPE;
   if (!g_out || !g_ld || !z_out || !hsave || !dy || !dhcol || !dbias3) return NFK_ERR_ARG;
   Geo g = make_geo(B, C, H, W, true);
-  // keep tiles + the im2col staging under ~100 KB so two CTAs fit per SM
-  while (g.ipc > 1 && (2LL * C * (g.pixt + 1) * 4 + static_cast<long long>(g.pixt) * (K3p * 2 + 16)) > 100 * 1024) {
-    g.ipc >>= 1; g.pixt = g.ipc * g.HW;
-  }
-  const int smem = (2 * C * (g.pixt + 1) + ((C + 3) & ~3)) * 4 + g.pixt * (K3p / 8 + 1) * 16 + 16;
-  const int groups = (B + g.ipc - 1) / g.ipc;
+  // keep the dh tile + the im2col staging under ~100 KB so two CTAs fit per SM: fewer images per group first, then
+  // bands of image rows (with a one-row halo) once a single image is too large
+  auto bytes = [&](int tile, int halo) {
+    return static_cast<long long>(C * (tile + 2 * halo + 1) + ((C + 3) & ~3)) * 4 +
+           static_cast<long long>(tile) * (K3p / 8 + 1) * 16 + 16;
+  };
+  while (g.ipc > 1 && bytes(g.pixt, 0) > 100 * 1024) { g.ipc >>= 1; g.pixt = g.ipc * g.HW; }
+  int brows = H;
+  if (g.ipc == 1)
+    while (brows > 1 && bytes(brows * W, brows < H ? W : 0) > 100 * 1024) brows >>= 1;
+  const bool banded = brows < H;
+  const int smem = static_cast<int>(bytes(banded ? brows * W : g.pixt, banded ? W : 0));
+  const int groups = banded ? B * (H / brows) : (B + g.ipc - 1) / g.ipc;
   const int grid = groups < 4 * 148 ? groups : 4 * 148;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   NFK_DISPATCH_C(C, {
     int rc = ensure_smem(coupling_bwd_kernel<CC>, smem);
     if (rc) return rc;
     coupling_bwd_kernel<CC><<<grid, ZT, smem, st>>>(g_out, g_ld, z_out, hsave, dy,
-                                                    static_cast<__nv_bfloat16*>(dhcol), K3p, dbias3, g);
+                                                    static_cast<__nv_bfloat16*>(dhcol), K3p, dbias3, g, brows);
   });
   return cudaGetLastError() == cudaSuccess ? NFK_OK : NFK_ERR_LAUNCH;
 }

@@ -118,3 +118,38 @@ def test_config4_kd_step_l3_gradients_flow_everywhere():
     torch.manual_seed(5)
     out2 = m.training_step([x.clone(), None], 0)
     assert abs(out2["nll"].item() - out["nll"].item()) < 1e-6
+
+
+def test_config5_celeba_64x64_training_gradients_vs_oracle(monkeypatch):
+    """BASELINE configs[4] shape family in TRAINING: Glow L=4 on 64x64x3 — the level-0 maps are 32x32, so the coupling
+    backward walks row bands with a halo instead of whole images. Student gradients of nll (bpd) + a latent term
+    against the CPU oracle's autograd; bf16 GEMM operands: median 1e-2 of max|grad|, worst 0.25 (one element of a 4x4-level weight),
+    every tensor's cosine >= 0.995 (the 4x4 top level sums only B*16 pixels, so its bf16 rounding noise is the largest)."""
+    from nf_distillation_b200.models import utils as U
+    from nf_distillation_b200.train import glow_cfg
+    from oracle import glow_oracle as O
+    cfg = glow_cfg((64, 64, 3), 1, 4, 128)
+    m, sd = make(cfg, 11)
+    m.train()
+    g = torch.Generator().manual_seed(3)
+    B = 8
+    x, noise = images(B, 64, g), torch.rand(B, 3, 64, 64, generator=g) / 256
+    wz = torch.randn(B, 96, 4, 4, generator=g)
+    names = dict(m.named_parameters())
+    osd = {k: v.clone().requires_grad_(k in names) for k, v in sd.items()}
+    o_outs, o_bpd = O.glow_forward(osd, cfg, x, noise)
+    (o_bpd.sum() + (o_outs[-1] * wz).sum() * 1e-2).backward()
+    monkeypatch.setattr(U, "dequant_noise", lambda t, n: noise.to(dev))
+    outs, bpd, _ = m(x.to(dev), None)
+    assert rel(bpd, o_bpd.detach()) < 1e-4
+    (bpd.sum() + (outs[-1] * wz.to(dev)).sum() * 1e-2).backward()
+    errs = []
+    for n_, p in m.named_parameters():
+        if osd[n_].grad is None:
+            continue
+        assert p.grad is not None and torch.isfinite(p.grad).all(), n_
+        errs.append((rel(p.grad, osd[n_].grad), n_))
+        a, b = p.grad.detach().cpu().flatten().double(), osd[n_].grad.flatten().double()
+        assert (a @ b / (a.norm() * b.norm() + 1e-30)).item() > 0.995, n_
+    errs.sort()
+    assert errs[len(errs) // 2][0] < 1e-2 and errs[-1][0] < 0.25, (errs[len(errs) // 2], errs[-1])

@@ -149,6 +149,16 @@ int nfk_kd_mse_fwd(const float* s, const float* t, int B, int n, float scale, fl
 int nfk_kd_mse_bwd(const float* s, const float* t, const float* g, int B, int n, float scale, float* ds,
                    int accumulate, void* stream);
 
+/* ---- last conv of the coupling net fused with the coupling (models/layers.py:231-260 Conv2dZeros +
+ * models/flows.py:150-171 / :173-190): P^T = B3 * h2^T on tcgen05 with whole images as the N tile, col2im over the nine
+ * taps, bias, then z2 <- (z2 + shift) * sigmoid(logit + 2) (reverse: z2 / sigmoid - shift) in place on y's upper C/2
+ * channels, ld[b] += (-)sum log sigmoid. h2 [B*H*W, hid] bf16, B3 [K3p, hid] bf16 (rows tap*C + c, as built by
+ * nfk_coupling_prep), hsave (optional, [B*H*W, C] fp32) keeps the conv output for nfk_coupling_bwd.
+ * Supported shapes: nfk_pconv_coupling_supported (C = 12 with 16x16 maps, C = 24 with maps of <= 64 pixels). */
+int nfk_pconv_coupling_supported(int C, int H, int W, int hid);
+int nfk_pconv_coupling_fwd(const void* h2, const void* B3, int K3p, const float* bias3, float* y, float* hsave,
+                           float* ld, int B, int C, int H, int W, int hid, int reverse, void* stream);
+
 /* ---- 1-D (tabular) FlowStep, fused (is_1d branches of models/flows.py:37-52,142-202, models/layers.py:410-411) --
  * Weights are packed once per optimiser step by nfk_flow1d_pack from the fused affine (nfk_invconv_prep with
  * transpose=1, forward or inverse direction) and the six nn.Linear layers of get_block_1d:

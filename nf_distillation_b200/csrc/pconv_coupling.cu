@@ -1,0 +1,311 @@
+// Last convolution of the coupling net fused with the affine coupling itself (reference: models/layers.py:231-260
+// Conv2dZeros, models/flows.py:150-171 normal_flow / :173-190 reverse_flow).
+//
+// The 3x3 Conv2dZeros is computed as per-tap products  P^T[tap*C + c, pixel] = sum_k B3[tap*C + c, k] * h2[pixel, k]
+// on tcgen05 -- the small weight matrix is the M operand (9C <= 128 rows per accumulator block), a tile of whole
+// images is the N operand (256 pixels for C = 12, 128 for C = 24), so every MMA runs at the full 128 x N shape --
+// and the accumulator never goes to HBM: the epilogue drains TMEM into shared memory, sums the nine shifted
+// taps per output pixel (col2im), adds the bias, and applies the coupling
+//     z2 <- (z2 + shift) * sigmoid(logit + 2),   logdet += sum log sigmoid(logit + 2)          (or its inverse)
+// in place on the fp32 NCHW map. What used to be a GEMM writing P [M, 9C] fp32, and a second kernel reading it back,
+// is one kernel whose HBM traffic is the bf16 h2 read plus the z2 update.
+//
+// Warp roles (320 threads): warp 0 TMA producer, warp 1 MMA issuer (+ TMEM allocation), warps 2-9 epilogue.
+// Two TMEM accumulator stages: the epilogue of tile i overlaps the MMAs of tile i+1.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+
+#include "../../include/nfk.h"
+#include "launch_util.h"
+#include "ptx.cuh"
+
+namespace nfk {
+
+constexpr int PC_THREADS = 320;
+constexpr int PC_BK = 64;
+constexpr int PC_STAGES = 2;
+
+template <int C> struct PcCfg;
+template <> struct PcCfg<12> { static constexpr int NPIX = 256, MB = 1; };   // one 16x16 image per tile
+template <> struct PcCfg<24> { static constexpr int NPIX = 128, MB = 2; };   // two 8x8 images per tile
+
+struct PcArgs {
+  long long M;          // pixels = B * H * W
+  int num_kb;           // hid / 64
+  int B, H, W, lgHW, lgW;
+  const float* bias3;   // [C] folded Conv2dZeros bias
+  float* y;             // [B, C, H, W] fp32: channels C/2.. are updated in place
+  float* hsave;         // optional [M, C] fp32: conv output (shift, logit pairs) kept for the backward pass
+  float* ld;            // optional [B] log-det, accumulated
+  int reverse;
+};
+
+template <int C>
+struct PcSmem {
+  using Cfg = PcCfg<C>;
+  static constexpr int a_bytes = Cfg::MB * 128 * 128;          // B3 k-block: MB x (128 rows x 128 B)
+  static constexpr int b_bytes = Cfg::NPIX * 128;              // h2 k-block: NPIX pixels x 128 B
+  static constexpr int stage_bytes = a_bytes + b_bytes;
+  static constexpr int pitch = Cfg::NPIX + 1;                  // odd: a warp's 32 rows hit 32 banks
+  static constexpr int s_bytes = ((9 * C * pitch * 4 + 15) / 16) * 16;
+  static constexpr int off_s = PC_STAGES * stage_bytes;
+  static constexpr int off_bar = off_s + s_bytes;
+  static constexpr int total = off_bar + 256;
+};
+
+template <int C>
+__global__ void __launch_bounds__(PC_THREADS, 1)
+pconv_coupling_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmH,
+                      const PcArgs g) {
+  using Cfg = PcCfg<C>;
+  using Sm = PcSmem<C>;
+  constexpr int NPIX = Cfg::NPIX, MB = Cfg::MB;
+  constexpr int K3 = 9 * C, J = C / 2;
+  constexpr int ACC_COLS = MB * NPIX;   // TMEM columns of one accumulator stage
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if (smem_u32(smem) & 1023u) __trap();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* S = reinterpret_cast<float*>(smem + Sm::off_s);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + Sm::off_bar);
+  uint64_t* empty = full + PC_STAGES;
+  uint64_t* tmem_full = empty + PC_STAGES;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;      // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int num_tiles = static_cast<int>((g.M + NPIX - 1) / NPIX);
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmW);
+    tma_prefetch_desc(&tmH);
+    for (int s = 0; s < PC_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 8); }
+    fence_mbar_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        for (int kb = 0; kb < g.num_kb; ++kb) {
+          mbar_wait(&empty[s], ph ^ 1);
+          uint8_t* sa = smem + s * Sm::stage_bytes;
+          mbar_expect_tx(&full[s], Sm::stage_bytes);
+#pragma unroll
+          for (int mb = 0; mb < MB; ++mb) tma_load_2d(sa + mb * 128 * 128, &tmW, &full[s], kb * PC_BK, mb * 128);
+          tma_load_2d(sa + Sm::a_bytes, &tmH, &full[s], kb * PC_BK, t * NPIX);
+          if (++s == PC_STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(128, NPIX, false, false);
+      int s = 0, it = 0;
+      uint32_t ph = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+        const int acc = it & 1;
+        mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * ACC_COLS;
+        for (int kb = 0; kb < g.num_kb; ++kb) {
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + s * Sm::stage_bytes);
+          const uint32_t b_addr = a_addr + Sm::a_bytes;
+#pragma unroll
+          for (int k = 0; k < PC_BK / 16; ++k) {
+            const uint64_t bd = umma_desc_sw128(b_addr + k * 32, 16, 1024);
+#pragma unroll
+            for (int mb = 0; mb < MB; ++mb) {
+              const uint64_t ad = umma_desc_sw128(a_addr + mb * 128 * 128 + k * 32, 16, 1024);
+              umma_f16(tmem_d + mb * NPIX, ad, bd, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            }
+          }
+          umma_commit(&empty[s]);
+          if (++s == PC_STAGES) { s = 0; ph ^= 1; }
+        }
+        umma_commit(&tmem_full[acc]);
+      }
+    }
+  } else {
+    // ---- epilogue: 8 warps; warp w owns TMEM lanes (w % 4) * 32.. and half (w - 2) / 4 of the tile's columns.
+    // Per tile: (1) prefetch this thread's z2 values (their HBM latency hides behind the wait for the MMAs and the
+    // drain), (2) drain the whole accumulator P^T [9C, NPIX] into shared memory, (3) per (pixel, channel pair): sum
+    // the nine shifted taps, bias, coupling, in-place z2 update, log-det partial sums.
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    const int et = threadIdx.x - 64;   // 0..255
+    const int HW = g.H * g.W, HWm = HW - 1, Wm = g.W - 1;
+    constexpr int ITEMS = J * NPIX / 256;       // (pixel, j) items per thread: item i = et + 256 k, pixel fastest
+    static_assert(J * NPIX % 256 == 0, "items must divide over the 256 epilogue threads");
+    int it = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const long long tile_base = static_cast<long long>(t) * NPIX;
+      float z2v[ITEMS];
+#pragma unroll
+      for (int k = 0; k < ITEMS; ++k) {
+        const int i = et + 256 * k;
+        const int j = i / NPIX, pl = i - j * NPIX;
+        const long long m = tile_base + pl;
+        const int b = static_cast<int>(m >> g.lgHW), rem = static_cast<int>(m) & HWm;
+        z2v[k] = m < g.M ? g.y[((static_cast<long long>(b) * C + J + j) << g.lgHW) + rem] : 0.f;
+      }
+      mbar_wait(&tmem_full[acc], (it >> 1) & 1);
+      tc_fence_after();
+      // drain: TMEM [row][0 .. NPIX) -> S[row][0 .. NPIX)
+      constexpr int HCOLS = NPIX / 2;
+#pragma unroll
+      for (int mb = 0; mb < MB; ++mb) {
+        const int row = mb * 128 + q * 32 + lane;
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * ACC_COLS + mb * NPIX +
+                               half * HCOLS;
+        float* srow = S + row * Sm::pitch + half * HCOLS;
+        if (mb * 128 + q * 32 < K3) {   // warp-uniform: this block of 32 rows holds real taps
+#pragma unroll 1
+          for (int c = 0; c < HCOLS; c += 32) {
+            uint32_t r0[16], r1[16];
+            tmem_ld16(taddr + c, r0);
+            tmem_ld16(taddr + c + 16, r1);
+            tmem_ld_wait();
+            if (row < K3) {
+#pragma unroll
+              for (int k = 0; k < 16; ++k) {
+                srow[c + k] = __uint_as_float(r0[k]);
+                srow[c + 16 + k] = __uint_as_float(r1[k]);
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);   // accumulator stage back to the MMA warp
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+#pragma unroll
+      for (int k = 0; k < ITEMS; ++k) {
+        const int i = et + 256 * k;
+        const int j = i / NPIX, pl = i - j * NPIX;
+        const long long m = tile_base + pl;
+        const int b = static_cast<int>(m >> g.lgHW);
+        float lsum = 0.f;
+        if (m < g.M) {
+          const int rem = static_cast<int>(m) & HWm;
+          const int yy = rem >> g.lgW, xx = rem & Wm;
+          float sh = __ldg(g.bias3 + 2 * j), lg = __ldg(g.bias3 + 2 * j + 1);
+          const float* sp = S + (2 * j) * Sm::pitch + pl;
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap) {
+            const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+            const int ny = yy + dy, nx = xx + dx;
+            if (ny >= 0 && ny < g.H && nx >= 0 && nx < g.W) {
+              const float* p = sp + tap * C * Sm::pitch + dy * g.W + dx;
+              sh += p[0];
+              lg += p[Sm::pitch];
+            }
+          }
+          if (g.hsave) *reinterpret_cast<float2*>(g.hsave + m * C + 2 * j) = make_float2(sh, lg);
+          // sigmoid / log-sigmoid of (logit + 2), stable on both sides
+          const float tt = lg + 2.f;
+          const float e = expf(-fabsf(tt));
+          const float l1p = log1pf(e);
+          float sg, lsv;
+          if (tt >= 0.f) { sg = 1.f / (1.f + e); lsv = -l1p; }
+          else { sg = e / (1.f + e); lsv = tt - l1p; }
+          g.y[((static_cast<long long>(b) * C + J + j) << g.lgHW) + rem] =
+              g.reverse ? (z2v[k] / sg - sh) : (z2v[k] + sh) * sg;
+          lsum = g.reverse ? -lsv : lsv;
+        }
+        if (g.ld) {
+          // HW >= 32 and pixel-fastest items: the 32 items of a warp belong to one image (all inside or all
+          // outside the batch)
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
+          if (lane == 0 && m < g.M) atomicAdd(g.ld + b, lsum);
+        }
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");   // S is free for the next tile
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+typedef CUresult (*EncodeTiledFn3)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int pc_tmap(CUtensorMap* m, const void* ptr, uint64_t cols, uint64_t rows, uint64_t ld, uint32_t box_rows) {
+  static EncodeTiledFn3 fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return NFK_ERR_DRIVER;
+    fn = reinterpret_cast<EncodeTiledFn3>(p);
+  }
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (ld * 2) % 16) return NFK_ERR_ALIGN;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? NFK_OK : NFK_ERR_DRIVER;
+}
+
+template <int C>
+static int pc_launch(const void* h2, const void* B3, int K3p, const PcArgs& g, int hid, cudaStream_t st) {
+  using Cfg = PcCfg<C>;
+  CUtensorMap tmW, tmH;
+  int rc;
+  if ((rc = pc_tmap(&tmW, B3, hid, K3p, hid, 128))) return rc;
+  if ((rc = pc_tmap(&tmH, h2, hid, static_cast<uint64_t>(g.M), hid, Cfg::NPIX))) return rc;
+  if ((rc = ensure_dyn_smem(reinterpret_cast<const void*>(pconv_coupling_kernel<C>), PcSmem<C>::total))) return rc;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int tiles = static_cast<int>((g.M + Cfg::NPIX - 1) / Cfg::NPIX);
+  pconv_coupling_kernel<C><<<tiles < sms ? tiles : sms, PC_THREADS, PcSmem<C>::total, st>>>(tmW, tmH, g);
+  return cudaGetLastError() == cudaSuccess ? NFK_OK : NFK_ERR_LAUNCH;
+}
+
+}  // namespace nfk
+
+using namespace nfk;
+
+extern "C" int nfk_pconv_coupling_supported(int C, int H, int W, int hid) {
+  if (hid <= 0 || hid % 64) return 0;
+  const int HW = H * W;
+  if (HW < 32 || (HW & (HW - 1)) || (W & (W - 1))) return 0;
+  if (C == 12) return HW <= PcCfg<12>::NPIX;   // whole images per tile: no halo between tiles
+  if (C == 24) return HW <= PcCfg<24>::NPIX;
+  return 0;
+}
+
+extern "C" int nfk_pconv_coupling_fwd(const void* h2, const void* B3, int K3p, const float* bias3, float* y,
+                                      float* hsave, float* ld, int B, int C, int H, int W, int hid, int reverse,
+                                      void* stream) {
+  if (B <= 0 || !nfk_pconv_coupling_supported(C, H, W, hid)) return NFK_ERR_SHAPE;
+  if (K3p % 128 || K3p < 9 * C) return NFK_ERR_SHAPE;
+  if (!h2 || !B3 || !bias3 || !y) return NFK_ERR_ARG;
+  PcArgs g{};
+  g.M = static_cast<long long>(B) * H * W;
+  g.num_kb = hid / 64;
+  g.B = B; g.H = H; g.W = W;
+  g.lgW = 0; while ((1 << g.lgW) < W) ++g.lgW;
+  g.lgHW = 0; while ((1 << g.lgHW) < H * W) ++g.lgHW;
+  g.bias3 = bias3; g.y = y; g.hsave = hsave; g.ld = ld; g.reverse = reverse;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (C == 12) return pc_launch<12>(h2, B3, K3p, g, hid, st);
+  return pc_launch<24>(h2, B3, K3p, g, hid, st);
+}

@@ -16,6 +16,7 @@ from . import ops
 BF16 = torch.bfloat16
 F32 = torch.float32
 USE_FUSED_CNET = os.environ.get("NFK_FUSED_CNET", "1") != "0"
+USE_FUSED_PCONV = os.environ.get("NFK_FUSED_PCONV", "1") != "0"
 
 
 # ------------------------------------------------------------------------------------------------ derived weights
@@ -205,9 +206,19 @@ def _coupling_net(col, k: StepConsts, M, hid, K1p, K3p, keep):
             h1 = torch.empty(M, hid, device=dev, dtype=BF16)
         ops.gemm_nt(col, k.B1, M, hid, K1p, ops.EPI_BIAS_RELU_BF16, h1, bias=k.bias1, aux=m1)
         ops.gemm_nt(h1, k.B2, M, hid, hid, ops.EPI_BIAS_RELU_BF16, h2, bias=k.bias2, aux=m2)
-    P = torch.empty(M, K3p, device=dev, dtype=F32)
+    return (h1, h2, m1, m2) if keep else (None, h2, None, None)
+
+
+def _conv3_coupling(h2, k: StepConsts, y, hsave, ld, B, C, H, W, hid, K3p, reverse):
+    """Conv2dZeros + affine coupling on y (in place) / ld (accumulated): one fused kernel where the shape allows it,
+    otherwise per-tap GEMM into P followed by the col2im + coupling kernel."""
+    M = B * H * W
+    if USE_FUSED_PCONV and K3p % 128 == 0 and ops.pconv_coupling_supported(C, H, W, hid):
+        ops.pconv_coupling_fwd(h2, k.B3, K3p, k.bias3, y, hsave, ld, B, C, H, W, hid, reverse)
+        return
+    P = torch.empty(M, K3p, device=h2.device, dtype=F32)
     ops.gemm_nt(h2, k.B3, M, K3p, hid, ops.EPI_F32, P)
-    return (h1, h2, P, m1, m2) if keep else (None, None, P, None, None)
+    ops.coupling_fwd(P, K3p, k.bias3, y, hsave, ld, B, C, H, W, reverse=reverse)
 
 
 def flowstep2d_forward(x, ld_in, k: StepConsts, hid, keep):
@@ -220,10 +231,10 @@ def flowstep2d_forward(x, ld_in, k: StepConsts, hid, keep):
     col = torch.empty(M, K1p, device=dev, dtype=BF16)
     ld_out = torch.empty(B, device=dev, dtype=F32)
     ops.affine1x1_fwd(x, k.Wf, k.bf, k.sl, y, col, K1p, ld_in, ld_out, B, C, H, W)
-    h1, h2, P, m1, m2 = _coupling_net(col, k, M, hid, K1p, K3p, keep)
+    h1, h2, m1, m2 = _coupling_net(col, k, M, hid, K1p, K3p, keep)
     hsave = torch.empty(M, C, device=dev, dtype=F32) if keep else None
-    ops.coupling_fwd(P, K3p, k.bias3, y, hsave, ld_out, B, C, H, W, reverse=False)
-    return y, ld_out, (col, h1, h2, hsave, m1, m2)
+    _conv3_coupling(h2, k, y, hsave, ld_out, B, C, H, W, hid, K3p, False)
+    return y, ld_out, (col, h1, h2 if keep else None, hsave, m1, m2)
 
 
 def flowstep2d_reverse(z, ld_in, k: StepConsts, hid):
@@ -235,10 +246,10 @@ def flowstep2d_reverse(z, ld_in, k: StepConsts, hid):
     dev = z.device
     col = torch.empty(M, K1p, device=dev, dtype=BF16)
     ops.affine1x1_fwd(z, None, None, None, None, col, K1p, None, None, B, C, H, W)   # im2col of z1 only
-    _, _, P, _, _ = _coupling_net(col, k, M, hid, K1p, K3p, keep=False)
+    _, h2, _, _ = _coupling_net(col, k, M, hid, K1p, K3p, keep=False)
     zc = z.clone()
     ld_mid = ld_in.clone()
-    ops.coupling_fwd(P, K3p, k.bias3, zc, None, ld_mid, B, C, H, W, reverse=True)
+    _conv3_coupling(h2, k, zc, None, ld_mid, B, C, H, W, hid, K3p, True)
     x = torch.empty_like(z)
     ld_out = torch.empty_like(ld_mid)
     ops.affine1x1_fwd(zc, k.Wf, k.bf, k.sl, x, None, 0, ld_mid, ld_out, B, C, H, W)

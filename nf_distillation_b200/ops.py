@@ -207,6 +207,17 @@ def kd_mse_bwd(s, t, g, B, n, scale, ds, accumulate=False):
           "nfk_kd_mse_bwd")
 
 
+def pconv_coupling_supported(C, H, W, hid):
+    return bool(LIB.nfk_pconv_coupling_supported(C, H, W, hid))
+
+
+def pconv_coupling_fwd(h2, B3, K3p, bias3, y, hsave, ld, B, C, H, W, hid, reverse):
+    """Conv2dZeros (per-tap tcgen05 products + col2im) fused with the affine coupling; y / ld updated in place."""
+    _count()
+    check(LIB.nfk_pconv_coupling_fwd(_p(h2), _p(B3), K3p, _p(bias3), _p(y), _p(hsave), _p(ld), B, C, H, W, hid,
+                                     int(reverse), _st()), "nfk_pconv_coupling_fwd")
+
+
 def flow1d_sizes(D, Cc, hid):
     """(total_fwd, total_bwd, total_grad, n_act, per-layer [(offG, offGB, ninp, noutp)] * 7)."""
     import ctypes

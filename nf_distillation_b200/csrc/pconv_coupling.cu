@@ -25,11 +25,14 @@ namespace nfk {
 
 constexpr int PC_THREADS = 320;
 constexpr int PC_BK = 64;
-constexpr int PC_STAGES = 2;
+constexpr int PC_STAGES = 3;
 
 template <int C> struct PcCfg;
-template <> struct PcCfg<12> { static constexpr int NPIX = 256, MB = 1; };   // one 16x16 image per tile
-template <> struct PcCfg<24> { static constexpr int NPIX = 128, MB = 2; };   // two 8x8 images per tile
+// NPIX pixels per tile (whole images), MB accumulator blocks of 128 rows; the epilogue handles the tile in two halves
+// of NPIX/2 output pixels, each staging a window of WIN source pixels (the half plus one image row + 1 of halo when
+// the image is larger than the half), so the staging buffer leaves room for a 3-stage operand ring.
+template <> struct PcCfg<12> { static constexpr int NPIX = 256, MB = 1, WIN = 160; };   // one 16x16 image per tile
+template <> struct PcCfg<24> { static constexpr int NPIX = 128, MB = 2, WIN = 64; };    // two 8x8 images per tile
 
 struct PcArgs {
   long long M;          // pixels = B * H * W
@@ -48,7 +51,7 @@ struct PcSmem {
   static constexpr int a_bytes = Cfg::MB * 128 * 128;          // B3 k-block: MB x (128 rows x 128 B)
   static constexpr int b_bytes = Cfg::NPIX * 128;              // h2 k-block: NPIX pixels x 128 B
   static constexpr int stage_bytes = a_bytes + b_bytes;
-  static constexpr int pitch = Cfg::NPIX + 1;                  // odd: a warp's 32 rows hit 32 banks
+  static constexpr int pitch = Cfg::WIN + 1;                   // odd: a warp's 32 rows hit 32 banks
   static constexpr int s_bytes = ((9 * C * pitch * 4 + 15) / 16) * 16;
   static constexpr int off_s = PC_STAGES * stage_bytes;
   static constexpr int off_bar = off_s + s_bytes;
@@ -61,7 +64,7 @@ pconv_coupling_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
                       const PcArgs g) {
   using Cfg = PcCfg<C>;
   using Sm = PcSmem<C>;
-  constexpr int NPIX = Cfg::NPIX, MB = Cfg::MB;
+  constexpr int NPIX = Cfg::NPIX, MB = Cfg::MB, WIN = Cfg::WIN, HALF = NPIX / 2;
   constexpr int K3 = 9 * C, J = C / 2;
   constexpr int ACC_COLS = MB * NPIX;   // TMEM columns of one accumulator stage
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -143,91 +146,104 @@ pconv_coupling_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
     const int et = threadIdx.x - 64;   // 0..255
     const int HW = g.H * g.W, HWm = HW - 1, Wm = g.W - 1;
     constexpr int ITEMS = J * NPIX / 256;       // (pixel, j) items per thread: item i = et + 256 k, pixel fastest
-    static_assert(J * NPIX % 256 == 0, "items must divide over the 256 epilogue threads");
+    static_assert(J * NPIX % 512 == 0, "each half's items must divide over the 256 epilogue threads");
     int it = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
       const int acc = it & 1;
       const long long tile_base = static_cast<long long>(t) * NPIX;
       float z2v[ITEMS];
 #pragma unroll
-      for (int k = 0; k < ITEMS; ++k) {
-        const int i = et + 256 * k;
-        const int j = i / NPIX, pl = i - j * NPIX;
+      for (int k = 0; k < ITEMS; ++k) {   // same (half, j, pixel) mapping as the gather below
+        const int hf = k / (ITEMS / 2), ih = et + 256 * (k - hf * (ITEMS / 2));
+        const int j = ih / HALF, pl = hf * HALF + (ih - j * HALF);
         const long long m = tile_base + pl;
         const int b = static_cast<int>(m >> g.lgHW), rem = static_cast<int>(m) & HWm;
         z2v[k] = m < g.M ? g.y[((static_cast<long long>(b) * C + J + j) << g.lgHW) + rem] : 0.f;
       }
       mbar_wait(&tmem_full[acc], (it >> 1) & 1);
       tc_fence_after();
-      // drain: TMEM [row][0 .. NPIX) -> S[row][0 .. NPIX)
-      constexpr int HCOLS = NPIX / 2;
 #pragma unroll
-      for (int mb = 0; mb < MB; ++mb) {
-        const int row = mb * 128 + q * 32 + lane;
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * ACC_COLS + mb * NPIX +
-                               half * HCOLS;
-        float* srow = S + row * Sm::pitch + half * HCOLS;
-        if (mb * 128 + q * 32 < K3) {   // warp-uniform: this block of 32 rows holds real taps
+      for (int hf = 0; hf < 2; ++hf) {
+        // source window of this half's outputs: the half itself when it holds whole images, else grown by the halo
+        // and clipped to the tile (= the image)
+        const int w0 = (WIN == HALF) ? hf * HALF : (hf == 0 ? 0 : NPIX - WIN);
+        if (hf == 1) asm volatile("bar.sync 1, 256;" ::: "memory");   // first half's gather is done with S
+        // drain: TMEM [row][w0 .. w0+WIN) -> S[row][0 .. WIN); the two warps of a lane quadrant split the columns
+        constexpr int HCOLS = WIN / 2;
+        static_assert(HCOLS % 16 == 0, "window halves are drained 16 columns at a time");
+#pragma unroll
+        for (int mb = 0; mb < MB; ++mb) {
+          const int row = mb * 128 + q * 32 + lane;
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * ACC_COLS + mb * NPIX + w0 +
+                                 half * HCOLS;
+          float* srow = S + row * Sm::pitch + half * HCOLS;
+          if (mb * 128 + q * 32 < K3) {   // warp-uniform: this block of 32 rows holds real taps
 #pragma unroll 1
-          for (int c = 0; c < HCOLS; c += 32) {
-            uint32_t r0[16], r1[16];
-            tmem_ld16(taddr + c, r0);
-            tmem_ld16(taddr + c + 16, r1);
-            tmem_ld_wait();
-            if (row < K3) {
+            for (int c = 0; c < HCOLS; c += 32) {
+              uint32_t r0[16], r1[16];
+              const bool two = c + 16 < HCOLS;
+              tmem_ld16(taddr + c, r0);
+              if (two) tmem_ld16(taddr + c + 16, r1);
+              tmem_ld_wait();
+              if (row < K3) {
 #pragma unroll
-              for (int k = 0; k < 16; ++k) {
-                srow[c + k] = __uint_as_float(r0[k]);
-                srow[c + 16 + k] = __uint_as_float(r1[k]);
+                for (int k = 0; k < 16; ++k) srow[c + k] = __uint_as_float(r0[k]);
+                if (two) {
+#pragma unroll
+                  for (int k = 0; k < 16; ++k) srow[c + 16 + k] = __uint_as_float(r1[k]);
+                }
               }
             }
           }
         }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);   // accumulator stage back to the MMA warp
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-#pragma unroll
-      for (int k = 0; k < ITEMS; ++k) {
-        const int i = et + 256 * k;
-        const int j = i / NPIX, pl = i - j * NPIX;
-        const long long m = tile_base + pl;
-        const int b = static_cast<int>(m >> g.lgHW);
-        float lsum = 0.f;
-        if (m < g.M) {
-          const int rem = static_cast<int>(m) & HWm;
-          const int yy = rem >> g.lgW, xx = rem & Wm;
-          float sh = __ldg(g.bias3 + 2 * j), lg = __ldg(g.bias3 + 2 * j + 1);
-          const float* sp = S + (2 * j) * Sm::pitch + pl;
-#pragma unroll
-          for (int tap = 0; tap < 9; ++tap) {
-            const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-            const int ny = yy + dy, nx = xx + dx;
-            if (ny >= 0 && ny < g.H && nx >= 0 && nx < g.W) {
-              const float* p = sp + tap * C * Sm::pitch + dy * g.W + dx;
-              sh += p[0];
-              lg += p[Sm::pitch];
-            }
-          }
-          if (g.hsave) *reinterpret_cast<float2*>(g.hsave + m * C + 2 * j) = make_float2(sh, lg);
-          // sigmoid / log-sigmoid of (logit + 2), stable on both sides
-          const float tt = lg + 2.f;
-          const float e = expf(-fabsf(tt));
-          const float l1p = log1pf(e);
-          float sg, lsv;
-          if (tt >= 0.f) { sg = 1.f / (1.f + e); lsv = -l1p; }
-          else { sg = e / (1.f + e); lsv = tt - l1p; }
-          g.y[((static_cast<long long>(b) * C + J + j) << g.lgHW) + rem] =
-              g.reverse ? (z2v[k] / sg - sh) : (z2v[k] + sh) * sg;
-          lsum = g.reverse ? -lsv : lsv;
+        if (hf == 1) {   // last TMEM read of this tile: accumulator stage back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
         }
-        if (g.ld) {
-          // HW >= 32 and pixel-fastest items: the 32 items of a warp belong to one image (all inside or all
-          // outside the batch)
+        asm volatile("bar.sync 1, 256;" ::: "memory");
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
-          if (lane == 0 && m < g.M) atomicAdd(g.ld + b, lsum);
+        for (int kk = 0; kk < ITEMS / 2; ++kk) {
+          const int k = hf * (ITEMS / 2) + kk;
+          const int ih = et + 256 * kk;                     // item inside this half: (j, pixel), pixel fastest
+          const int j = ih / HALF, pl = hf * HALF + (ih - j * HALF);
+          const long long m = tile_base + pl;
+          const int b = static_cast<int>(m >> g.lgHW);
+          float lsum = 0.f;
+          if (m < g.M) {
+            const int rem = static_cast<int>(m) & HWm;
+            const int yy = rem >> g.lgW, xx = rem & Wm;
+            float sh = __ldg(g.bias3 + 2 * j), lg = __ldg(g.bias3 + 2 * j + 1);
+            const float* sp = S + (2 * j) * Sm::pitch + (pl - w0);
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+              const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+              const int ny = yy + dy, nx = xx + dx;
+              if (ny >= 0 && ny < g.H && nx >= 0 && nx < g.W) {
+                const float* p = sp + tap * C * Sm::pitch + dy * g.W + dx;
+                sh += p[0];
+                lg += p[Sm::pitch];
+              }
+            }
+            if (g.hsave) *reinterpret_cast<float2*>(g.hsave + m * C + 2 * j) = make_float2(sh, lg);
+            // sigmoid / log-sigmoid of (logit + 2), stable on both sides
+            const float tt = lg + 2.f;
+            const float e = expf(-fabsf(tt));
+            const float l1p = log1pf(e);
+            float sg, lsv;
+            if (tt >= 0.f) { sg = 1.f / (1.f + e); lsv = -l1p; }
+            else { sg = e / (1.f + e); lsv = tt - l1p; }
+            g.y[((static_cast<long long>(b) * C + J + j) << g.lgHW) + rem] =
+                g.reverse ? (z2v[k] / sg - sh) : (z2v[k] + sh) * sg;
+            lsum = g.reverse ? -lsv : lsv;
+          }
+          if (g.ld) {
+            // HW >= 32 and pixel-fastest items: the 32 items of a warp belong to one image (all inside or all
+            // outside the batch)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
+            if (lane == 0 && m < g.M) atomicAdd(g.ld + b, lsum);
+          }
         }
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");   // S is free for the next tile

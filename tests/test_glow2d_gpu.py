@@ -155,3 +155,41 @@ def test_forward_vs_oracle_fresh(B, K, hid, patched_noise):
     with torch.no_grad():
         xs = m(reverse=True, temperature=0.7)
     assert xs[-1].shape == (32, 3, 32, 32) and torch.isfinite(xs[-1]).all()
+
+
+@pytest.mark.parametrize("B,C,H,reverse", [(5, 12, 16, False), (5, 12, 16, True), (7, 24, 8, False), (300, 12, 16, False)])
+def test_fused_conv3_coupling_matches_two_kernel_path_and_torch(B, C, H, reverse):
+    """csrc/pconv_coupling.cu (Conv2dZeros + coupling in one kernel) against (a) the per-tap GEMM + col2im/coupling
+    kernels it replaces — same bf16 products, fp32 sums in a different order: 1e-6 — and (b) torch's conv2d on the same
+    bf16-rounded operands in fp32 (tolerance 1e-4 on outputs, 1e-5 relative on the log-det)."""
+    import torch.nn.functional as F
+    from nf_distillation_b200 import ops
+    hid, W = 512, H
+    M, K3p = B * H * W, ops.round_up(9 * C, 64)
+    g = torch.Generator(device=dev).manual_seed(100 + B + C)
+    h2 = (torch.randn(M, hid, device=dev, generator=g).clamp_min(0) * 0.5).bfloat16()
+    w3 = (torch.randn(C, hid, 3, 3, device=dev, generator=g) * 0.02).bfloat16()       # [co, ci, ky, kx]
+    B3 = torch.zeros(K3p, hid, device=dev, dtype=torch.bfloat16)
+    B3[:9 * C] = w3.permute(2, 3, 0, 1).reshape(9 * C, hid)                           # row = tap*C + co
+    bias3 = torch.randn(C, device=dev, generator=g) * 0.1
+    y0 = torch.randn(B, C, H, W, device=dev, generator=g)
+    ld0 = torch.randn(B, device=dev, generator=g)
+    assert ops.pconv_coupling_supported(C, H, W, hid)
+    yf, ldf, hsf = y0.clone(), ld0.clone(), torch.empty(M, C, device=dev)
+    ops.pconv_coupling_fwd(h2, B3, K3p, bias3, yf, hsf, ldf, B, C, H, W, hid, reverse)
+    yu, ldu, hsu = y0.clone(), ld0.clone(), torch.empty(M, C, device=dev)
+    P = torch.empty(M, K3p, device=dev)
+    ops.gemm_nt(h2, B3, M, K3p, hid, ops.EPI_F32, P)
+    ops.coupling_fwd(P, K3p, bias3, yu, hsu, ldu, B, C, H, W, reverse=reverse)
+    assert rel(yf, yu) < 1e-6 and rel(hsf, hsu) < 1e-6 and rel(ldf, ldu) < 1e-5
+    # torch reference on the same rounded operands
+    hmap = h2.float().view(B, H, W, hid).permute(0, 3, 1, 2)
+    out = F.conv2d(hmap, w3.float(), bias3, padding=1)
+    shift, logit = out[:, 0::2], out[:, 1::2]
+    s = torch.sigmoid(logit + 2.0)
+    z2 = y0[:, C // 2:]
+    z2r = (z2 / s - shift) if reverse else (z2 + shift) * s
+    ldr = ld0 + (-1.0 if reverse else 1.0) * torch.log(s).flatten(1).sum(1)
+    assert rel(yf[:, C // 2:], z2r) < 1e-4 and torch.equal(yf[:, :C // 2], y0[:, :C // 2])
+    assert rel(ldf, ldr) < 1e-5
+    assert rel(hsf.view(B, H, W, C).permute(0, 3, 1, 2), out) < 1e-4

@@ -55,7 +55,8 @@ struct PcSmem {
   static constexpr int s_bytes = ((9 * C * pitch * 4 + 15) / 16) * 16;
   static constexpr int off_s = PC_STAGES * stage_bytes;
   static constexpr int off_bar = off_s + s_bytes;
-  static constexpr int total = off_bar + 256;
+  static constexpr int off_bias = off_bar + 128;               // [C] floats
+  static constexpr int total = off_bias + 128;
 };
 
 template <int C>
@@ -76,6 +77,8 @@ pconv_coupling_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
   uint64_t* tmem_full = empty + PC_STAGES;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;      // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* bias_s = reinterpret_cast<float*>(smem + Sm::off_bias);
+  if (threadIdx.x < C) bias_s[threadIdx.x] = g.bias3[threadIdx.x];
 
   const int num_tiles = static_cast<int>((g.M + NPIX - 1) / NPIX);
   if (warp == 0 && lane == 0) {
@@ -213,7 +216,7 @@ pconv_coupling_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
           if (m < g.M) {
             const int rem = static_cast<int>(m) & HWm;
             const int yy = rem >> g.lgW, xx = rem & Wm;
-            float sh = __ldg(g.bias3 + 2 * j), lg = __ldg(g.bias3 + 2 * j + 1);
+            float sh = bias_s[2 * j], lg = bias_s[2 * j + 1];
             const float* sp = S + (2 * j) * Sm::pitch + (pl - w0);
 #pragma unroll
             for (int tap = 0; tap < 9; ++tap) {

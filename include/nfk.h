@@ -99,6 +99,22 @@ int nfk_invconv_prep_bwd(const float* an_bias, const float* an_logs, const float
                          float pixels, float* d_bias, float* d_logs, float* d_lower, float* d_upper, float* d_log_s,
                          float* d_weight, void* stream);
 
+/* Batched forms of nfk_coupling_prep / nfk_coupling_prep_bwd below (one grid row of CTAs per FlowStep): an item is
+ * that call's argument list. Same lifetime rules as nfk_invconv_item. */
+typedef struct nfk_coupling_item {
+  const float *w1, *b1, *l1, *w2, *b2, *l2, *w3, *b3, *l3;
+  int cin, hid, cout, K1p, K3p, with_transposed;
+  void *B1, *B1T, *B2, *B2T, *B3, *B3T;
+  float *bias1, *bias2, *bias3;
+} nfk_coupling_item;
+typedef struct nfk_coupling_bwd_item {
+  nfk_coupling_item fwd; /* parameters and sizes; the operand / bias outputs are not read */
+  const float *dB1, *dbias1, *dB2, *dbias2, *dB3, *dbias3;
+  float *dw1, *db1, *dl1, *dw2, *db2, *dl2, *dw3, *db3, *dl3;
+} nfk_coupling_bwd_item;
+int nfk_coupling_prep_batch(int n, const nfk_coupling_item* items, void* stream);
+int nfk_coupling_prep_bwd_batch(int n, const nfk_coupling_bwd_item* items, void* stream);
+
 /* Coupling-network weights -> bf16 GEMM operands with the ActNorm affine (models/layers.py:223-228) and the
  * Conv2dZeros exp(3*logs) scale (:257-260) folded in. K1p / K3p = 9*cin / 9*cout rounded up to 64.
  *   B1 [hid,K1p] (k = tap*cin+ci), B2 [hid,hid], B3 [K3p,hid] (row = tap*cout+co); *T = transposes for dgrads. */

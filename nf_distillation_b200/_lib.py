@@ -34,6 +34,20 @@ class InvconvBwdItem(_c.Structure):
                [(n, _vp) for n in ("d_bias", "d_logs", "d_lower", "d_upper", "d_log_s", "d_weight")]
 
 
+class CouplingItem(_c.Structure):
+    """nfk_coupling_item (include/nfk.h)."""
+    _fields_ = [(n, _vp) for n in ("w1", "b1", "l1", "w2", "b2", "l2", "w3", "b3", "l3")] + \
+               [(n, _i) for n in ("cin", "hid", "cout", "K1p", "K3p", "with_transposed")] + \
+               [(n, _vp) for n in ("B1", "B1T", "B2", "B2T", "B3", "B3T", "bias1", "bias2", "bias3")]
+
+
+class CouplingBwdItem(_c.Structure):
+    """nfk_coupling_bwd_item (include/nfk.h)."""
+    _fields_ = [("fwd", CouplingItem)] + \
+               [(n, _vp) for n in ("dB1", "dbias1", "dB2", "dbias2", "dB3", "dbias3")] + \
+               [(n, _vp) for n in ("dw1", "db1", "dl1", "dw2", "db2", "dl2", "dw3", "db3", "dl3")]
+
+
 # name -> argtypes; every function returns int. Keep in the same order as include/nfk.h.
 SIGNATURES: dict[str, list] = {
     "nfk_version": [],
@@ -44,6 +58,8 @@ SIGNATURES: dict[str, list] = {
     "nfk_invconv_prep_bwd_batch": [_i, _vp, _vp],
     "nfk_invconv_prep": [_vp] * 8 + [_i, _i, _i, _vp, _vp, _vp, _vp],
     "nfk_invconv_prep_bwd": [_vp] * 8 + [_i, _i, _i, _vp, _vp, _vp, _vp, _i, _f] + [_vp] * 6 + [_vp],
+    "nfk_coupling_prep_batch": [_i, _vp, _vp],
+    "nfk_coupling_prep_bwd_batch": [_i, _vp, _vp],
     "nfk_coupling_prep": [_vp] * 9 + [_i] * 5 + [_vp] * 9 + [_i, _vp],
     "nfk_coupling_prep_bwd": [_vp] * 9 + [_i] * 5 + [_vp] * 6 + [_vp] * 9 + [_vp],
     "nfk_affine1x1_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _vp],

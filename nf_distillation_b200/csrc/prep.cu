@@ -379,8 +379,15 @@ struct CouplingOps {
   float *bias1, *bias2, *bias3;  // folded biases
 };
 
-__global__ void coupling_prep_kernel(CouplingW w, CouplingOps o, int cin, int hid, int cout, int K1p, int K3p,
-                                     int with_transposed) {
+struct CouplingItem { CouplingW w; CouplingOps o; int cin, hid, cout, K1p, K3p, with_transposed; };
+constexpr int CP_MAX_BATCH = 16;
+struct CouplingBatch { CouplingItem it[CP_MAX_BATCH]; };
+
+__global__ void coupling_prep_kernel(const __grid_constant__ CouplingBatch batch) {
+  const CouplingItem& q = batch.it[blockIdx.y];
+  const CouplingW& w = q.w;
+  const CouplingOps& o = q.o;
+  const int cin = q.cin, hid = q.hid, cout = q.cout, K1p = q.K1p, K3p = q.K3p, with_transposed = q.with_transposed;
   const long long n1 = static_cast<long long>(hid) * K1p;
   const long long n2 = static_cast<long long>(hid) * hid;
   const long long n3 = static_cast<long long>(K3p) * hid;
@@ -432,12 +439,23 @@ struct CouplingGradOut {
   float *dw1, *db1, *dl1, *dw2, *db2, *dl2, *dw3, *db3, *dl3;
 };
 
-// One CTA per output channel: rows [0,hid) -> layer 1, [hid,2hid) -> layer 2, [2hid, 2hid+cout) -> layer 3.
+struct CouplingBwdItem { CouplingW w; CouplingGradIn gi; CouplingGradOut go; int cin, hid, cout, K1p, K3p; };
+constexpr int CPB_MAX_BATCH = 12;
+struct CouplingBwdBatch { CouplingBwdItem it[CPB_MAX_BATCH]; };
+
+// One CTA per output channel: rows [0,hid) -> layer 1, [hid,2hid) -> layer 2, [2hid, 2hid+cout) -> layer 3;
+// blockIdx.y = step of the batch.
 __global__ void __launch_bounds__(PREP_THREADS)
-coupling_prep_bwd_kernel(CouplingW w, CouplingGradIn gi, CouplingGradOut go, int cin, int hid, int cout, int K1p,
-                         int K3p) {
+coupling_prep_bwd_kernel(const __grid_constant__ CouplingBwdBatch batch) {
+  const CouplingBwdItem& q = batch.it[blockIdx.y];
+  const CouplingW& w = q.w;
+  const CouplingGradIn& gi = q.gi;
+  const CouplingGradOut& go = q.go;
+  const int cin = q.cin, hid = q.hid, cout = q.cout, K1p = q.K1p, K3p = q.K3p;
+  (void)K3p;
   __shared__ float red[32];
   const int row = blockIdx.x, tid = threadIdx.x;
+  if (row >= 2 * hid + cout) return;
   float acc = 0.f;
   if (row < hid) {
     const int co = row;
@@ -574,23 +592,84 @@ extern "C" int nfk_invconv_prep_bwd(const float* an_bias, const float* an_logs, 
   return nfk_invconv_prep_bwd_batch(1, &g, stream);
 }
 
+static int coupling_item_check(const nfk_coupling_item& c) {
+  if (c.cin <= 0 || c.hid <= 0 || c.cout <= 0 || c.hid % 64 || c.K1p % 64 || c.K3p % 64 || c.K1p < 9 * c.cin ||
+      c.K3p < 9 * c.cout)
+    return NFK_ERR_SHAPE;
+  if (!c.w1 || !c.b1 || !c.l1 || !c.w2 || !c.b2 || !c.l2 || !c.w3 || !c.b3 || !c.l3) return NFK_ERR_ARG;
+  return NFK_OK;
+}
+
+extern "C" int nfk_coupling_prep_batch(int n, const nfk_coupling_item* items, void* stream) {
+  if (n < 0) return NFK_ERR_SHAPE;
+  if (n && !items) return NFK_ERR_ARG;
+  for (int i = 0; i < n; ++i) {
+    const nfk_coupling_item& c = items[i];
+    if (int rc = coupling_item_check(c)) return rc;
+    if (!c.B1 || !c.B2 || !c.B3 || !c.bias1 || !c.bias2 || !c.bias3) return NFK_ERR_ARG;
+    if (c.with_transposed && (!c.B1T || !c.B2T || !c.B3T)) return NFK_ERR_ARG;
+  }
+  for (int i0 = 0; i0 < n; i0 += CP_MAX_BATCH) {
+    CouplingBatch b{};
+    const int m = n - i0 < CP_MAX_BATCH ? n - i0 : CP_MAX_BATCH;
+    long long tmax = 0;
+    for (int i = 0; i < m; ++i) {
+      const nfk_coupling_item& c = items[i0 + i];
+      CouplingItem& q = b.it[i];
+      q.w = CouplingW{c.w1, c.b1, c.l1, c.w2, c.b2, c.l2, c.w3, c.b3, c.l3};
+      q.o = CouplingOps{static_cast<__nv_bfloat16*>(c.B1), static_cast<__nv_bfloat16*>(c.B1T),
+                        static_cast<__nv_bfloat16*>(c.B2), static_cast<__nv_bfloat16*>(c.B2T),
+                        static_cast<__nv_bfloat16*>(c.B3), static_cast<__nv_bfloat16*>(c.B3T), c.bias1, c.bias2, c.bias3};
+      q.cin = c.cin; q.hid = c.hid; q.cout = c.cout; q.K1p = c.K1p; q.K3p = c.K3p;
+      q.with_transposed = c.with_transposed;
+      const long long total = static_cast<long long>(c.hid) * (c.K1p + c.hid + c.K3p) + 2 * c.hid + c.cout;
+      tmax = total > tmax ? total : tmax;
+    }
+    const int blocks = static_cast<int>((tmax + 255) / 256 < 1184 ? (tmax + 255) / 256 : 1184);
+    coupling_prep_kernel<<<dim3(blocks, m), 256, 0, static_cast<cudaStream_t>(stream)>>>(b);
+    if (cudaGetLastError() != cudaSuccess) return NFK_ERR_LAUNCH;
+  }
+  return NFK_OK;
+}
+
+extern "C" int nfk_coupling_prep_bwd_batch(int n, const nfk_coupling_bwd_item* items, void* stream) {
+  if (n < 0) return NFK_ERR_SHAPE;
+  if (n && !items) return NFK_ERR_ARG;
+  for (int i = 0; i < n; ++i) {
+    const nfk_coupling_bwd_item& g = items[i];
+    if (int rc = coupling_item_check(g.fwd)) return rc;
+    if (!g.dB1 || !g.dbias1 || !g.dB2 || !g.dbias2 || !g.dB3 || !g.dbias3) return NFK_ERR_ARG;
+    if (!g.dw1 || !g.db1 || !g.dl1 || !g.dw2 || !g.db2 || !g.dl2 || !g.dw3 || !g.db3 || !g.dl3) return NFK_ERR_ARG;
+  }
+  for (int i0 = 0; i0 < n; i0 += CPB_MAX_BATCH) {
+    CouplingBwdBatch b{};
+    const int m = n - i0 < CPB_MAX_BATCH ? n - i0 : CPB_MAX_BATCH;
+    int rows = 0;
+    for (int i = 0; i < m; ++i) {
+      const nfk_coupling_bwd_item& g = items[i0 + i];
+      const nfk_coupling_item& c = g.fwd;
+      CouplingBwdItem& q = b.it[i];
+      q.w = CouplingW{c.w1, c.b1, c.l1, c.w2, c.b2, c.l2, c.w3, c.b3, c.l3};
+      q.gi = CouplingGradIn{g.dB1, g.dbias1, g.dB2, g.dbias2, g.dB3, g.dbias3};
+      q.go = CouplingGradOut{g.dw1, g.db1, g.dl1, g.dw2, g.db2, g.dl2, g.dw3, g.db3, g.dl3};
+      q.cin = c.cin; q.hid = c.hid; q.cout = c.cout; q.K1p = c.K1p; q.K3p = c.K3p;
+      const int r = 2 * c.hid + c.cout;
+      rows = r > rows ? r : rows;
+    }
+    coupling_prep_bwd_kernel<<<dim3(rows, m), PREP_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(b);
+    if (cudaGetLastError() != cudaSuccess) return NFK_ERR_LAUNCH;
+  }
+  return NFK_OK;
+}
+
 extern "C" int nfk_coupling_prep(const float* w1, const float* b1, const float* l1, const float* w2, const float* b2,
                                  const float* l2, const float* w3, const float* b3, const float* l3, int cin, int hid,
                                  int cout, int K1p, int K3p, void* B1, void* B1T, void* B2, void* B2T, void* B3,
                                  void* B3T, float* bias1, float* bias2, float* bias3, int with_transposed,
                                  void* stream) {
-  if (cin <= 0 || hid <= 0 || cout <= 0 || hid % 64 || K1p % 64 || K3p % 64 || K1p < 9 * cin || K3p < 9 * cout)
-    return NFK_ERR_SHAPE;
-  if (with_transposed && (!B1T || !B2T || !B3T)) return NFK_ERR_ARG;
-  CouplingW w{w1, b1, l1, w2, b2, l2, w3, b3, l3};
-  CouplingOps o{static_cast<__nv_bfloat16*>(B1), static_cast<__nv_bfloat16*>(B1T), static_cast<__nv_bfloat16*>(B2),
-                static_cast<__nv_bfloat16*>(B2T), static_cast<__nv_bfloat16*>(B3), static_cast<__nv_bfloat16*>(B3T),
-                bias1, bias2, bias3};
-  const long long total = static_cast<long long>(hid) * (K1p + hid + K3p) + 2 * hid + cout;
-  const int blocks = static_cast<int>((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
-  coupling_prep_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(w, o, cin, hid, cout, K1p, K3p,
-                                                                             with_transposed);
-  return cudaGetLastError() == cudaSuccess ? NFK_OK : NFK_ERR_LAUNCH;
+  const nfk_coupling_item c{w1, b1, l1, w2, b2, l2, w3, b3, l3, cin, hid, cout, K1p, K3p, with_transposed,
+                            B1, B1T, B2, B2T, B3, B3T, bias1, bias2, bias3};
+  return nfk_coupling_prep_batch(1, &c, stream);
 }
 
 extern "C" int nfk_coupling_prep_bwd(const float* w1, const float* b1, const float* l1, const float* w2,
@@ -599,11 +678,10 @@ extern "C" int nfk_coupling_prep_bwd(const float* w1, const float* b1, const flo
                                      const float* dbias1, const float* dB2, const float* dbias2, const float* dB3,
                                      const float* dbias3, float* dw1, float* db1, float* dl1, float* dw2, float* db2,
                                      float* dl2, float* dw3, float* db3, float* dl3, void* stream) {
-  if (cin <= 0 || hid <= 0 || cout <= 0) return NFK_ERR_SHAPE;
-  CouplingW w{w1, b1, l1, w2, b2, l2, w3, b3, l3};
-  CouplingGradIn gi{dB1, dbias1, dB2, dbias2, dB3, dbias3};
-  CouplingGradOut go{dw1, db1, dl1, dw2, db2, dl2, dw3, db3, dl3};
-  coupling_prep_bwd_kernel<<<2 * hid + cout, PREP_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
-      w, gi, go, cin, hid, cout, K1p, K3p);
-  return cudaGetLastError() == cudaSuccess ? NFK_OK : NFK_ERR_LAUNCH;
+  nfk_coupling_bwd_item g{};
+  g.fwd = nfk_coupling_item{w1, b1, l1, w2, b2, l2, w3, b3, l3, cin, hid, cout, K1p, K3p, 0,
+                            nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  g.dB1 = dB1; g.dbias1 = dbias1; g.dB2 = dB2; g.dbias2 = dbias2; g.dB3 = dB3; g.dbias3 = dbias3;
+  g.dw1 = dw1; g.db1 = db1; g.dl1 = dl1; g.dw2 = dw2; g.db2 = db2; g.dl2 = dl2; g.dw3 = dw3; g.db3 = db3; g.dl3 = dl3;
+  return nfk_coupling_prep_bwd_batch(1, &g, stream);
 }

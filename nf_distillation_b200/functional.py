@@ -62,9 +62,13 @@ class PrepCtx:
         self.steps = list(steps)
         self.reverse = bool(reverse)
         self.index = {id(s): i for i, s in enumerate(self.steps)}
-        self.consts = [None] * len(self.steps)
-        self.items = [None] * len(self.steps)
-        self.grads = [None] * len(self.steps)
+        n = len(self.steps)
+        self.consts = [None] * n     # (Wf, bf, sl) per step
+        self.items = [None] * n
+        self.grads = [None] * n      # deposits of the steps' backward: (dWf, ld, dbf, g_ld, B, pixels)
+        self.cops = [None] * n       # 2-D steps: (B1, B1T, B2, B2T, B3, B3T, bias1, bias2, bias3)
+        self.citems = [None] * n
+        self.cgrads = [None] * n     # deposits: (dB1, dbias1, dB2, dbias2, dB3, dbias3)
         self.token = None
 
     def build(self):
@@ -72,6 +76,9 @@ class PrepCtx:
         for st in self.steps:
             iv = st.invconv
             flat += [st.actnorm.bias, st.actnorm.logs, iv.lower, iv.upper, iv.log_s]
+        for st in self.steps:
+            if not st.is_1d:
+                flat += list(st._coupling_params_2d())
         self.token = PrepAllFn.apply(self, *flat)
         return self
 
@@ -141,6 +148,26 @@ class PrepAllFn(torch.autograd.Function):
             pctx.consts[i] = (Wf, bf, sl)
             pctx.items[i] = it
         ops.invconv_prep_batch(items)
+        # coupling-net GEMM operands of the 2-D steps, one launch
+        off = 5 * len(pctx.steps)
+        citems = []
+        for i, st in enumerate(pctx.steps):
+            if st.is_1d:
+                continue
+            cw = flat[off:off + 9]; off += 9
+            C, hid = st.in_channels, st.hidden_channels
+            cin, cout = C // 2, C
+            K1p, K3p = ops.round_up(9 * cin, 64), ops.round_up(9 * cout, 64)
+            e = lambda *s_: torch.empty(*s_, device=dev, dtype=BF16)
+            B1, B2, B3 = e(hid, K1p), e(hid, hid), e(K3p, hid)
+            B1T, B2T, B3T = e(K1p, hid), e(hid, hid), e(hid, K3p)
+            bias = torch.empty(2 * hid + ops.round_up(cout, 4), device=dev, dtype=F32)
+            bias1, bias2, bias3 = bias[:hid], bias[hid:2 * hid], bias[2 * hid:2 * hid + cout]
+            it = ops.coupling_item(cw, cin, hid, cout, K1p, K3p, True, B1, B1T, B2, B2T, B3, B3T, bias1, bias2, bias3)
+            citems.append(it)
+            pctx.citems[i] = it
+            pctx.cops[i] = (B1, B1T, B2, B2T, B3, B3T, bias1, bias2, bias3)
+        ops.coupling_prep_batch(citems)
         ctx.pctx = pctx
         ctx.set_materialize_grads(False)
         ctx.save_for_backward(*flat)
@@ -174,7 +201,26 @@ class PrepAllFn(torch.autograd.Function):
             out[5 * i:5 * i + 5] = [d_bias, d_logs, d_lower, d_upper, d_log_s]
         ops.invconv_prep_bwd_batch(items)
         pctx.grads = [None] * n
-        return (None, *out)
+        # coupling-net parameters of the 2-D steps
+        off = 5 * n
+        cout_grads, citems = [], []
+        for i, st in enumerate(pctx.steps):
+            if st.is_1d:
+                continue
+            cw = flat[off:off + 9]; off += 9
+            if pctx.cgrads[i] is None:
+                cout_grads += [None] * 9
+                continue
+            total = sum(ops.round_up(t.numel(), 4) for t in cw)
+            arena_c = torch.empty(total, device=dev, dtype=F32)
+            o2, gout = 0, []
+            for t in cw:
+                gout.append(arena_c[o2:o2 + t.numel()].view_as(t)); o2 += ops.round_up(t.numel(), 4)
+            citems.append(ops.coupling_bwd_item(pctx.citems[i], pctx.cgrads[i], gout))
+            cout_grads += gout
+        ops.coupling_prep_bwd_batch(citems)
+        pctx.cgrads = [None] * n
+        return (None, *out, *cout_grads)
 
 
 def build_coupling_ops(cw, cin, hid, cout, with_t):
@@ -257,25 +303,25 @@ def flowstep2d_reverse(z, ld_in, k: StepConsts, hid):
 
 
 class FlowStep2dFn(torch.autograd.Function):
-    """Differentiable 2-D FlowStep forward. Inputs: x, logdet, the prep token (see PrepCtx; the fused affine comes from
-    pctx.consts[idx]), then the 9 reference parameters of the coupling net."""
+    """Differentiable 2-D FlowStep forward. Inputs: x, logdet and the prep token (see PrepCtx): the fused affine comes
+    from pctx.consts[idx], the coupling net's bf16 GEMM operands from pctx.cops[idx]; parameter gradients are produced
+    by PrepAllFn.backward from what this step's backward deposits in pctx."""
 
     @staticmethod
-    def forward(ctx, x, ld_in, hid, token, pctx, idx, w1, b1, l1, w2, b2, l2, w3, b3, l3):
+    def forward(ctx, x, ld_in, hid, token, pctx, idx):
         B, C, H, W = x.shape
         x = x.contiguous()
         Wf, bf, sl = pctx.consts[idx]
-        cw = (w1, b1, l1, w2, b2, l2, w3, b3, l3)
-        k = StepConsts(Wf, bf, sl, *build_coupling_ops(cw, C // 2, hid, C, True))
+        k = StepConsts(Wf, bf, sl, *pctx.cops[idx])
         y, ld_out, (col, h1, h2, hsave, m1, m2) = flowstep2d_forward(x, ld_in.contiguous(), k, hid, keep=True)
         ctx.hid = hid
         ctx.pctx, ctx.idx = pctx, idx
-        ctx.save_for_backward(x, y, col, h1, h2, hsave, m1, m2, Wf, k.B1T, k.B2T, k.B3T, *cw)
+        ctx.save_for_backward(x, y, col, h1, h2, hsave, m1, m2, Wf, k.B1T, k.B2T, k.B3T)
         return y, ld_out
 
     @staticmethod
     def backward(ctx, g_out, g_ld):
-        (x, z_out, col, h1, h2, hsave, m1, m2, Wf, B1T, B2T, B3T, *cw) = ctx.saved_tensors
+        (x, z_out, col, h1, h2, hsave, m1, m2, Wf, B1T, B2T, B3T) = ctx.saved_tensors
         hid = ctx.hid
         B, C, H, W = x.shape
         M, cin = B * H * W, C // 2
@@ -307,11 +353,11 @@ class FlowStep2dFn(torch.autograd.Function):
         dx = torch.empty_like(x)
         ops.affine1x1_bwd(dy, dcol, K1p, x, Wf, dx, dWf, dbf, B, C, H, W)
 
-        # the parameter-space chain rule of the fused affine is deferred to PrepAllFn.backward (one batched launch)
+        # the parameter-space chain rules (fused affine, folded conv operands) are deferred to PrepAllFn.backward:
+        # one batched launch each for all steps of the pass
         ctx.pctx.grads[ctx.idx] = (dWf, C, dbf, g_ld, B, float(H * W))
-        grads = [torch.empty_like(t) for t in cw]
-        ops.coupling_prep_bwd(*cw, cin, hid, C, K1p, K3p, dB1, dbias1, dB2, dbias2, dB3, dbias3, *grads)
-        return (dx, g_ld, None, None, None, None, *grads)
+        ctx.pctx.cgrads[ctx.idx] = (dB1, dbias1, dB2, dbias2, dB3, dbias3)
+        return (dx, g_ld, None, None, None, None)
 
 
 # ------------------------------------------------------------------------------------------------ Split2d

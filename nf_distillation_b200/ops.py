@@ -125,6 +125,38 @@ def invconv_prep_bwd_batch(items):
     check(LIB.nfk_invconv_prep_bwd_batch(n, ctypes.addressof(arr), _st()), "nfk_invconv_prep_bwd_batch")
 
 
+def coupling_item(cw, cin, hid, cout, K1p, K3p, with_t, B1, B1T, B2, B2T, B3, B3T, bias1, bias2, bias3):
+    from ._lib import CouplingItem
+    return CouplingItem(*[_p(t) for t in cw], cin, hid, cout, K1p, K3p, int(with_t), _p(B1), _p(B1T), _p(B2), _p(B2T),
+                        _p(B3), _p(B3T), _p(bias1), _p(bias2), _p(bias3))
+
+
+def coupling_prep_batch(items):
+    """bf16 GEMM operands of the coupling nets of many FlowSteps in one launch."""
+    from ._lib import CouplingItem
+    n = len(items)
+    if not n:
+        return
+    arr = (CouplingItem * n)(*items)
+    _count((n + 15) // 16)
+    check(LIB.nfk_coupling_prep_batch(n, ctypes.addressof(arr), _st()), "nfk_coupling_prep_batch")
+
+
+def coupling_bwd_item(fwd_item, gin, gout):
+    from ._lib import CouplingBwdItem
+    return CouplingBwdItem(fwd_item, *[_p(t) for t in gin], *[_p(t) for t in gout])
+
+
+def coupling_prep_bwd_batch(items):
+    from ._lib import CouplingBwdItem
+    n = len(items)
+    if not n:
+        return
+    arr = (CouplingBwdItem * n)(*items)
+    _count((n + 11) // 12)
+    check(LIB.nfk_coupling_prep_bwd_batch(n, ctypes.addressof(arr), _st()), "nfk_coupling_prep_bwd_batch")
+
+
 def coupling_prep(w1, b1, l1, w2, b2, l2, w3, b3, l3, cin, hid, cout, K1p, K3p, B1, B1T, B2, B2T, B3, B3T, bias1,
                   bias2, bias3, with_t):
     _count()

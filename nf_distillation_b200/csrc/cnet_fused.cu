@@ -69,15 +69,16 @@ cnet_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmCol, const __grid_co
   uint64_t* empty = full + CF_SLOTS;                                      // [4] operand slot consumed (local)
   uint64_t* acc_full = empty + CF_SLOTS;                                  // [2]
   uint64_t* acc_empty = acc_full + 2;                                     // [2] (leader, 16 arrivals)
-  uint64_t* h1_full = acc_empty + 2;                                      // [2] per 256-channel half (leader, 16 arrivals)
-  uint64_t* h1_empty = h1_full + 2;                                       // conv#2 of the tile has finished reading h1
+  uint64_t* h1_full = acc_empty + 2;                                      // [8] per 64-channel h1 panel (leader, 8 arrivals)
+  uint64_t* h1_empty = h1_full + 8;                                       // conv#2 of the tile has finished reading h1
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(h1_empty + 1);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmCol); tma_prefetch_desc(&tmB1); tma_prefetch_desc(&tmB2); tma_prefetch_desc(&tmH2);
     for (int s = 0; s < CF_SLOTS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 16); }
-    mbar_init(&h1_full[0], 16); mbar_init(&h1_full[1], 16); mbar_init(h1_empty, 1);
+    for (int p = 0; p < 8; ++p) mbar_init(&h1_full[p], 8);
+    mbar_init(h1_empty, 1);
     fence_mbar_init();
   }
   if (warp == 1) { tmem_alloc_pair(tmem_slot, 512); tmem_relinquish_pair(); }
@@ -155,13 +156,13 @@ cnet_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmCol, const __grid_co
           acc_end();
         }
         // ---- conv#2: A = the h1 panels the epilogue warps just wrote (both CTAs), B2 streamed
-        //      k-blocks 0-3 only need the first half of h1, so conv#2 starts while the second half is still being drained
+        //      k-block kb only needs h1 panel kb, so conv#2 starts as soon as the first panels have been written
         for (int h = 0; h < 2; ++h) {
           const uint32_t d = acc_begin();
           for (int kb = 0; kb < 8; ++kb) {
-            if (h == 0 && (kb == 0 || kb == 4)) {
+            if (h == 0) {
               const long long c0 = g.prof ? clock64() : 0;
-              mbar_wait(&h1_full[kb >> 2], tile_ph);
+              mbar_wait(&h1_full[kb], tile_ph);
               if (g.prof) w_h1 += clock64() - c0;
               tc_fence_after();
             }
@@ -190,41 +191,49 @@ cnet_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmCol, const __grid_co
     const uint32_t sw = static_cast<uint32_t>(lane & 7);
     uint8_t* stage = smem + CnetSmem::stage + (warp - 2) * 4096;
     uint32_t nacc = 0, tile_ph = 0;
-    // 64 accumulator columns -> bias + ReLU -> bf16 -> one swizzled panel slice (32 rows x 128 B) at `dst_rows`;
-    // returns nothing, optionally writes the 1-bit ReLU mask words (two per call)
-    auto drain64 = [&](uint32_t tm, const float* bias, uint8_t* dst_rows, uint32_t* mask, long long row, int col0) {
-      uint8_t* dst = dst_rows + lane * 128;
-#pragma unroll 1
-      for (int c = 0; c < 64; c += 32) {
-        uint32_t r0[16], r1[16];
-        tmem_ld16(tm + c, r0);
-        tmem_ld16(tm + c + 16, r1);
-        tmem_ld_wait();
-        uint32_t bits = 0;
+    // 16 accumulator columns (already in registers) -> bias + ReLU -> bf16 -> two 16-byte chunks (cc0, cc0 + 1) of
+    // this thread's 128-byte row in a swizzled panel; returns the 16 ReLU mask bits
+    auto epi16 = [&](const uint32_t (&r)[16], const float* bias16, uint8_t* dst, int cc0, bool want_bits) -> uint32_t {
+      float v[16];
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const uint32_t* r = h ? r1 : r0;
-          const int cc0 = (c + 16 * h) >> 3;
-          float v[16];
-#pragma unroll
-          for (int j = 0; j < 16; j += 4) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(bias + c + 16 * h + j));
-            v[j] = fmaxf(__uint_as_float(r[j]) + b.x, 0.f);
-            v[j + 1] = fmaxf(__uint_as_float(r[j + 1]) + b.y, 0.f);
-            v[j + 2] = fmaxf(__uint_as_float(r[j + 2]) + b.z, 0.f);
-            v[j + 3] = fmaxf(__uint_as_float(r[j + 3]) + b.w, 0.f);
-          }
-          if (mask) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) bits |= (v[j] > 0.f ? 1u : 0u) << (16 * h + j);
-          }
-          *reinterpret_cast<uint4*>(dst + ((static_cast<uint32_t>(cc0) ^ sw) << 4)) =
-              make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
-          *reinterpret_cast<uint4*>(dst + ((static_cast<uint32_t>(cc0 + 1) ^ sw) << 4)) =
-              make_uint4(pack2(v[8], v[9]), pack2(v[10], v[11]), pack2(v[12], v[13]), pack2(v[14], v[15]));
-        }
-        if (mask && row < g.M) mask[static_cast<long long>((col0 + c) >> 5) * g.ldmask + row] = bits;
+      for (int j = 0; j < 16; j += 4) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(bias16 + j));
+        v[j] = fmaxf(__uint_as_float(r[j]) + b.x, 0.f);
+        v[j + 1] = fmaxf(__uint_as_float(r[j + 1]) + b.y, 0.f);
+        v[j + 2] = fmaxf(__uint_as_float(r[j + 2]) + b.z, 0.f);
+        v[j + 3] = fmaxf(__uint_as_float(r[j + 3]) + b.w, 0.f);
       }
+      uint32_t bits = 0;
+      if (want_bits) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) bits |= (v[j] > 0.f ? 1u : 0u) << j;
+      }
+      *reinterpret_cast<uint4*>(dst + ((static_cast<uint32_t>(cc0) ^ sw) << 4)) =
+          make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
+      *reinterpret_cast<uint4*>(dst + ((static_cast<uint32_t>(cc0 + 1) ^ sw) << 4)) =
+          make_uint4(pack2(v[8], v[9]), pack2(v[10], v[11]), pack2(v[12], v[13]), pack2(v[14], v[15]));
+      return bits;
+    };
+    // 64 columns held in R[4 pz .. 4 pz + 3] -> one swizzled panel slice (32 rows x 128 B) at `dst_rows`, plus the two
+    // 1-bit ReLU mask words of those columns
+    auto panel64 = [&](const uint32_t (&r0)[16], const uint32_t (&r1)[16], const uint32_t (&r2)[16],
+                       const uint32_t (&r3)[16], const float* bias, uint8_t* dst_rows, uint32_t* mask, long long row,
+                       int col0) {
+      uint8_t* dst = dst_rows + lane * 128;
+      const bool wb = mask != nullptr;
+      const uint32_t b0 = epi16(r0, bias, dst, 0, wb), b1 = epi16(r1, bias + 16, dst, 2, wb);
+      const uint32_t b2 = epi16(r2, bias + 32, dst, 4, wb), b3 = epi16(r3, bias + 48, dst, 6, wb);
+      if (wb && row < g.M) {
+        mask[static_cast<long long>(col0 >> 5) * g.ldmask + row] = b0 | (b1 << 16);
+        mask[static_cast<long long>((col0 + 32) >> 5) * g.ldmask + row] = b2 | (b3 << 16);
+      }
+    };
+    // this warp's 128 accumulator columns -> registers, all loads in flight at once; the accumulator stage can be
+    // handed back to the MMA issuer as soon as they have landed, before any of the epilogue math
+    auto load128 = [&](uint32_t tm, uint32_t (&R)[8][16]) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) tmem_ld16(tm + 16 * i, R[i]);
+      tmem_ld_wait();
     };
     for (int t = pair; t < num_tiles; t += num_pairs) {
       const int row0 = t * 256 + static_cast<int>(rank) * 128 + qd * 32;
@@ -235,32 +244,36 @@ cnet_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmCol, const __grid_co
         if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         __syncwarp();
       }
-      // ---- conv#1 halves -> h1 panels (this warp: channels h*256 + hf*128 .. +127 = panels 4h + 2hf, +1)
+      // ---- conv#1 halves -> h1 panels. This warp takes panels 4h + hf and 4h + 2 + hf, so after the first round the
+      //      two lowest panels of the half exist and conv#2 can start on them (its k-block kb reads panel kb)
       for (int h = 0; h < 2; ++h) {
         const uint32_t st = nacc & 1;
         mbar_wait(&acc_full[st], (nacc >> 1) & 1);
         tc_fence_after();
-        const uint32_t tm = tmem_base + st * 256 + hf * 128 + lane_off;
-#pragma unroll 1
-        for (int pz = 0; pz < 2; ++pz) {
-          const int panel = 4 * h + 2 * hf + pz;
-          drain64(tm + pz * 64, g.bias1 + panel * 64, smem + CnetSmem::h1 + panel * CF_PANEL + qd * 32 * 128,
-                  g.mask1, row, panel * 64);
-        }
+        const uint32_t tm = tmem_base + st * 256 + lane_off;
+        uint32_t R[8][16];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) tmem_ld16(tm + hf * 64 + 16 * i, R[i]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) tmem_ld16(tm + (hf + 2) * 64 + 16 * i, R[4 + i]);
+        tmem_ld_wait();
         tc_fence_before();
-        fence_proxy_async();
         __syncwarp();
-        if (lane == 0) {
-          mbar_arrive_cluster(&acc_empty[st], 0);
-          mbar_arrive_cluster(&h1_full[h], 0);
-          if (g.store_h1 && row0 < g.M) {
-            for (int pz = 0; pz < 2; ++pz) {
-              const int panel = 4 * h + 2 * hf + pz;
-              tma_store_2d(smem + CnetSmem::h1 + panel * CF_PANEL + qd * 32 * 128, &tmH1, panel * 64, row0);
-            }
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        if (lane == 0) mbar_arrive_cluster(&acc_empty[st], 0);
+#pragma unroll
+        for (int pz = 0; pz < 2; ++pz) {
+          const int panel = 4 * h + 2 * pz + hf;
+          uint8_t* dst = smem + CnetSmem::h1 + panel * CF_PANEL + qd * 32 * 128;
+          if (pz == 0) panel64(R[0], R[1], R[2], R[3], g.bias1 + panel * 64, dst, g.mask1, row, panel * 64);
+          else panel64(R[4], R[5], R[6], R[7], g.bias1 + panel * 64, dst, g.mask1, row, panel * 64);
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive_cluster(&h1_full[panel], 0);
+            if (g.store_h1 && row0 < g.M) tma_store_2d(dst, &tmH1, panel * 64, row0);
           }
         }
+        if (g.store_h1 && lane == 0) asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         ++nacc;
       }
       // ---- conv#2 halves -> staging panel -> TMA store of h2
@@ -269,19 +282,20 @@ cnet_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmCol, const __grid_co
         mbar_wait(&acc_full[st], (nacc >> 1) & 1);
         tc_fence_after();
         const uint32_t tm = tmem_base + st * 256 + hf * 128 + lane_off;
-#pragma unroll 1
+        uint32_t R[8][16];
+        load128(tm, R);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(&acc_empty[st], 0);   // the MMAs of the next half may overwrite it now
+#pragma unroll
         for (int pz = 0; pz < 2; ++pz) {
           const int col0 = h * 256 + hf * 128 + pz * 64;
           // the staging panel is reused: the previous bulk store must have finished reading it. (With store_h1 the
           // same wait also covers the h1 stores, which only READ the h1 panels that conv#2 is reading anyway.)
           if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
           __syncwarp();
-          drain64(tm + pz * 64, g.bias2 + col0, stage, g.mask2, row, col0);
-          if (pz == 1) {
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(&acc_empty[st], 0);
-          }
+          if (pz == 0) panel64(R[0], R[1], R[2], R[3], g.bias2 + col0, stage, g.mask2, row, col0);
+          else panel64(R[4], R[5], R[6], R[7], g.bias2 + col0, stage, g.mask2, row, col0);
           fence_proxy_async();
           __syncwarp();
           if (lane == 0 && row0 < g.M) {

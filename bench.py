@@ -305,7 +305,7 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-graphs", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-batch", type=int, default=8)
+    ap.add_argument("--cpu-batch", type=int, default=32)
     ap.add_argument("--ncu-step", action="store_true",
                     help="profiling aid: warm up, then run ONE eager step between cudaProfilerStart/Stop and exit "
                          "(use with ncu --profile-from-start off); prints no bench value")

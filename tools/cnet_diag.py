@@ -6,7 +6,10 @@ from nf_distillation_b200 import ops
 from nf_distillation_b200._lib import LIB
 dev = "cuda"
 torch.manual_seed(0)
-for (M, K1p) in ((256, 64), (1000, 64), (65536, 64), (16384, 128), (4096, 256), (262144, 64)):
+CASES = ((256, 64), (1000, 64), (65536, 64), (16384, 128), (4096, 256), (262144, 64))
+if len(sys.argv) > 1:   # e.g. `cnet_diag.py 262144 64` for an ncu capture of one shape
+    CASES = ((int(sys.argv[1]), int(sys.argv[2]) if len(sys.argv) > 2 else 64),)
+for (M, K1p) in CASES:
     hid = 512
     col = (torch.randn(M, K1p, device=dev) * 0.5).bfloat16()
     B1 = (torch.randn(hid, K1p, device=dev) * 0.1).bfloat16()

@@ -55,15 +55,16 @@ def _kb_ranges_t(deg_out, deg_in, bn):
 
 class _MadeFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, ld_in, made, flip, w1, b1, w2, b2, w3, b3):
+    def forward(ctx, x, ld_in, made, flip, xb, w1, b1, w2, b2, w3, b3):
         x = x.contiguous()
-        u, ld_out, saved = made._run_forward(x, ld_in.contiguous(), (w1, b1, w2, b2, w3, b3), flip, True)
+        u, ld_out, ub, saved = made._run_forward(x, ld_in.contiguous(), (w1, b1, w2, b2, w3, b3), flip, True, xb)
         ctx.made, ctx.flip = made, flip
         ctx.save_for_backward(x, *saved)
-        return u, ld_out
+        ctx.mark_non_differentiable(ub)
+        return u, ld_out, ub
 
     @staticmethod
-    def backward(ctx, g_u, g_ld):
+    def backward(ctx, g_u, g_ld, _g_ub):
         made, flip = ctx.made, ctx.flip
         x, xb, h1, h2, m1, m2, out, B1T, B2T, B3T = ctx.saved_tensors
         D, H, Dp, N3p = made.D, made.H, made.Dp, made.N3p
@@ -95,7 +96,7 @@ class _MadeFn(torch.autograd.Function):
         dw1, dw2, dw3 = (torch.empty(H, D, device=dev), torch.empty(H, H, device=dev),
                          torch.empty(2 * D, H, device=dev))
         ops.made_prep_bwd(dB1, dB2, dB3, made.deg1, made.deg2, D, H, Dp, dw1, dw2, dw3)
-        return dx, g_ld, None, None, dw1, db1, dw2, db2, dw3, db3
+        return dx, g_ld, None, None, None, dw1, db1, dw2, db2, dw3, db3
 
 
 class MADE(nn.Module):
@@ -142,27 +143,44 @@ class MADE(nn.Module):
         H, Dp, N3p = self.H, self.Dp, self.N3p
         m1 = ops.relu_mask_like(Bn, H, dev) if keep else None
         m2 = ops.relu_mask_like(Bn, H, dev) if keep else None
-        h1 = torch.empty(Bn, H, device=dev, dtype=BF16)
-        ops.gemm_nt(xb, B1, Bn, H, Dp, ops.EPI_BIAS_RELU_BF16, h1, bias=b1, aux=m1)
         h2 = torch.empty(Bn, H, device=dev, dtype=BF16)
-        kb0, kb1 = self._ranges
-        ops.gemm_nt_ranged(h1, B2, Bn, H, H, ops.EPI_BIAS_RELU_BF16, h2, self.bn, kb0, kb1, bias=b2, aux=m2)
+        if ops.cnet_fused_supported(H, Dp) and Bn >= 8192:
+            # both masked linears in ONE kernel (the coupling net's fused conv#1 -> conv#2 kernel: h1 stays in shared
+            # memory as the second GEMM's A operand and is only written out when training). The masks are zeros in the
+            # bf16 weights here; skipping their k-blocks would save < what the h1 round trip through HBM costs.
+            h1 = torch.empty(Bn, H, device=dev, dtype=BF16) if keep else None
+            ops.cnet_fwd_fused(xb, Dp, B1, B2, b1, b2, h2, Bn, H, h1=h1, mask1=m1, mask2=m2)
+        else:
+            h1 = torch.empty(Bn, H, device=dev, dtype=BF16)
+            ops.gemm_nt(xb, B1, Bn, H, Dp, ops.EPI_BIAS_RELU_BF16, h1, bias=b1, aux=m1)
+            kb0, kb1 = self._ranges
+            ops.gemm_nt_ranged(h1, B2, Bn, H, H, ops.EPI_BIAS_RELU_BF16, h2, self.bn, kb0, kb1, bias=b2, aux=m2)
         out = torch.empty(Bn, N3p, device=dev, dtype=F32)
         ops.gemm_nt(h2, B3, Bn, N3p, H, ops.EPI_F32, out, bias=b3p)
         return (h1, h2, out, m1, m2) if keep else (h1, h2, out)
 
-    def _run_forward(self, x, ld_in, params, flip, keep):
+    def _bf16_rows(self, x, xb):
+        """bf16 zero-padded copy of x [B, Dp] for the first GEMM; reuses the copy the previous MADE layer's
+        affine kernel already wrote (attached to its output as `_nfk_bf16`) when there is one."""
+        Bn = x.shape[0]
+        if xb is not None and xb.shape == (Bn, self.Dp) and xb.dtype == BF16 and xb.device == x.device:
+            return xb
+        xb = torch.empty(Bn, self.Dp, device=x.device, dtype=BF16)
+        ops.rows_to_bf16(x, Bn, self.D, self.Dp, xb)
+        return xb
+
+    def _run_forward(self, x, ld_in, params, flip, keep, xb=None):
         Bn = x.shape[0]
         dev = x.device
         ops_ = self._operands(params, keep)
-        xb = torch.empty(Bn, self.Dp, device=dev, dtype=BF16)
-        ops.rows_to_bf16(x, Bn, self.D, self.Dp, xb)
+        xb = self._bf16_rows(x, xb)
         res = self._net(xb, Bn, ops_, params[1], params[3], keep)
         h1, h2, out = res[:3]
         u = torch.empty_like(x)
+        ub = torch.empty(Bn, self.Dp, device=dev, dtype=BF16)   # the next layer's GEMM operand
         ld_out = torch.empty(Bn, device=dev, dtype=F32)
-        ops.made_affine_fwd(x, out, self.N3p, u, None, 0, ld_in, ld_out, Bn, self.D, flip)
-        return u, ld_out, ((xb, h1, h2, res[3], res[4], out, ops_[1], ops_[3], ops_[5]) if keep else None)
+        ops.made_affine_fwd(x, out, self.N3p, u, ub, self.Dp, ld_in, ld_out, Bn, self.D, flip)
+        return u, ld_out, ub, ((xb, h1, h2, res[3], res[4], out, ops_[1], ops_[3], ops_[5]) if keep else None)
 
     def _cached_operands(self):
         key = tuple((p.data_ptr(), p._version) for p in self._params())
@@ -179,17 +197,20 @@ class MADE(nn.Module):
             ld = torch.zeros(Bn, device=input.device)
         params = self._params()
         if not reverse:
+            xb_in = getattr(input, "_nfk_bf16", None)      # (bf16 copy, version of the tensor it was made from)
+            xb_in = xb_in[0] if xb_in is not None and xb_in[1] == input._version else None
             if torch.is_grad_enabled() and (input.requires_grad or any(p.requires_grad for p in params)):
-                u, ld_out = _MadeFn.apply(input, ld, self, self.flip, *params)
+                u, ld_out, ub = _MadeFn.apply(input, ld, self, self.flip, xb_in, *params)
             else:
                 x = input.contiguous()
                 ops_ = self._cached_operands()
-                xb = torch.empty(Bn, self.Dp, device=x.device, dtype=BF16)
-                ops.rows_to_bf16(x, Bn, self.D, self.Dp, xb)
+                xb = self._bf16_rows(x, xb_in if x is input else None)
                 _, _, out = self._net(xb, Bn, ops_, params[1].detach(), params[3].detach())
                 u = torch.empty_like(x)
+                ub = torch.empty(Bn, self.Dp, device=x.device, dtype=BF16)
                 ld_out = torch.empty(Bn, device=x.device, dtype=F32)
-                ops.made_affine_fwd(x, out, self.N3p, u, None, 0, ld.contiguous(), ld_out, Bn, self.D, self.flip)
+                ops.made_affine_fwd(x, out, self.N3p, u, ub, self.Dp, ld.contiguous(), ld_out, Bn, self.D, self.flip)
+            u._nfk_bf16 = (ub, u._version)   # bf16 copy for the next MADE layer (saves its conversion pass)
             return u, (ld_out if want else None)
         if torch.is_grad_enabled() and input.requires_grad:
             raise NotImplementedError("gradients through the sequential MADE inverse are not built")

@@ -21,7 +21,7 @@ def rel(a, b):
     return ((a - b).abs().max() / (b.abs().max() + 1e-12)).item()
 
 
-@pytest.mark.parametrize("D,H,K,B", [(6, 512, 5, 300), (63, 512, 3, 257), (63, 192, 2, 64)])
+@pytest.mark.parametrize("D,H,K,B", [(6, 512, 5, 300), (63, 512, 3, 257), (63, 192, 2, 64), (63, 512, 2, 8229)])
 def test_maf_forward_inverse_backward_vs_paper_restatement(D, H, K, B):
     from nf_distillation_b200.models.maf import create_maf_model
     from oracle import maf_oracle as MO
@@ -38,11 +38,12 @@ def test_maf_forward_inverse_backward_vs_paper_restatement(D, H, K, B):
         for a, b in zip(outs, o_outs):
             assert rel(a, b) < 1e-3
         back = m(z=outs[-1], reverse=True)
-        assert len(back) == K and rel(back[-1], x) < 1e-5          # x -> z -> x
+        # x -> z -> x; fp32 cancellation in u*e^alpha + mu grows with the largest |mu| among B*D entries
+        assert len(back) == K and rel(back[-1], x) < (1e-5 if B < 4096 else 1e-4)
         # per-layer log-det antisymmetry
         z, ld = m.flow.layers[0](x.cuda(), logdet=torch.zeros(B, device="cuda"))
         xb, ld2 = m.flow.layers[0](z, logdet=ld, reverse=True)
-        assert ld2.abs().max().item() < 1e-3 * (ld.abs().max().item() + 1) and rel(xb, x) < 1e-5
+        assert ld2.abs().max().item() < 1e-3 * (ld.abs().max().item() + 1) and rel(xb, x) < (1e-5 if B < 4096 else 1e-4)
     # autoregressive property: d z_i / d x_j = 0 for j > i  (layer 0, un-flipped view)
     with torch.no_grad():
         x2 = x.clone()

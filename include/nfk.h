@@ -170,7 +170,8 @@ int nfk_kd_mse_bwd(const float* s, const float* t, const float* g, int B, int n,
  * taps, bias, then z2 <- (z2 + shift) * sigmoid(logit + 2) (reverse: z2 / sigmoid - shift) in place on y's upper C/2
  * channels, ld[b] += (-)sum log sigmoid. h2 [B*H*W, hid] bf16, B3 [K3p, hid] bf16 (rows tap*C + c, as built by
  * nfk_coupling_prep), hsave (optional, [B*H*W, C] fp32) keeps the conv output for nfk_coupling_bwd.
- * Supported shapes: nfk_pconv_coupling_supported (C = 12 with 16x16 maps, C = 24 with maps of <= 64 pixels). */
+ * Supported shapes (nfk_pconv_coupling_supported): C = 12 with maps of 256 pixels (W <= 16) or <= 128 pixels, C = 24
+ * with <= 64 pixels, C = 48 with <= 32 pixels; H, W powers of two; hid % 64 == 0. */
 int nfk_pconv_coupling_supported(int C, int H, int W, int hid);
 int nfk_pconv_coupling_fwd(const void* h2, const void* B3, int K3p, const float* bias3, float* y, float* hsave,
                            float* ld, int B, int C, int H, int W, int hid, int reverse, void* stream);

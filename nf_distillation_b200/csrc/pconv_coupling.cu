@@ -25,14 +25,14 @@ namespace nfk {
 
 constexpr int PC_THREADS = 320;
 constexpr int PC_BK = 64;
-constexpr int PC_STAGES = 3;
 
 template <int C> struct PcCfg;
 // NPIX pixels per tile (whole images), MB accumulator blocks of 128 rows; the epilogue handles the tile in two halves
 // of NPIX/2 output pixels, each staging a window of WIN source pixels (the half plus one image row + 1 of halo when
 // the image is larger than the half), so the staging buffer leaves room for a 3-stage operand ring.
-template <> struct PcCfg<12> { static constexpr int NPIX = 256, MB = 1, WIN = 160; };   // one 16x16 image per tile
-template <> struct PcCfg<24> { static constexpr int NPIX = 128, MB = 2, WIN = 64; };    // two 8x8 images per tile
+template <> struct PcCfg<12> { static constexpr int NPIX = 256, MB = 1, WIN = 160, STAGES = 3; };  // one 16x16 image
+template <> struct PcCfg<24> { static constexpr int NPIX = 128, MB = 2, WIN = 64, STAGES = 3; };   // two 8x8 images
+template <> struct PcCfg<48> { static constexpr int NPIX = 64, MB = 4, WIN = 32, STAGES = 2; };    // four 4x4 images
 
 struct PcArgs {
   long long M;          // pixels = B * H * W
@@ -53,7 +53,7 @@ struct PcSmem {
   static constexpr int stage_bytes = a_bytes + b_bytes;
   static constexpr int pitch = Cfg::WIN + 1;                   // odd: a warp's 32 rows hit 32 banks
   static constexpr int s_bytes = ((9 * C * pitch * 4 + 15) / 16) * 16;
-  static constexpr int off_s = PC_STAGES * stage_bytes;
+  static constexpr int off_s = Cfg::STAGES * stage_bytes;
   static constexpr int off_bar = off_s + s_bytes;
   static constexpr int off_bias = off_bar + 128;               // [C] floats
   static constexpr int total = off_bias + 128;
@@ -65,7 +65,7 @@ pconv_coupling_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
                       const PcArgs g) {
   using Cfg = PcCfg<C>;
   using Sm = PcSmem<C>;
-  constexpr int NPIX = Cfg::NPIX, MB = Cfg::MB, WIN = Cfg::WIN, HALF = NPIX / 2;
+  constexpr int NPIX = Cfg::NPIX, MB = Cfg::MB, WIN = Cfg::WIN, HALF = NPIX / 2, PC_STAGES = Cfg::STAGES;
   constexpr int K3 = 9 * C, J = C / 2;
   constexpr int ACC_COLS = MB * NPIX;   // TMEM columns of one accumulator stage
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -241,11 +241,15 @@ pconv_coupling_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
             lsum = g.reverse ? -lsv : lsv;
           }
           if (g.ld) {
-            // HW >= 32 and pixel-fastest items: the 32 items of a warp belong to one image (all inside or all
-            // outside the batch)
+            // pixel-fastest items: min(32, HW) consecutive lanes belong to one image (all inside or all outside the
+            // batch); reduce inside those segments, the first lane of each adds
+            const int seg = HW < 32 ? HW : 32;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
-            if (lane == 0 && m < g.M) atomicAdd(g.ld + b, lsum);
+            for (int o = 16; o > 0; o >>= 1) {
+              const float v = __shfl_xor_sync(0xffffffffu, lsum, o);
+              if (o < seg) lsum += v;
+            }
+            if ((lane & (seg - 1)) == 0 && m < g.M) atomicAdd(g.ld + b, lsum);
           }
         }
       }
@@ -305,9 +309,12 @@ using namespace nfk;
 extern "C" int nfk_pconv_coupling_supported(int C, int H, int W, int hid) {
   if (hid <= 0 || hid % 64) return 0;
   const int HW = H * W;
-  if (HW < 32 || (HW & (HW - 1)) || (W & (W - 1))) return 0;
-  if (C == 12) return HW <= PcCfg<12>::NPIX;   // whole images per tile: no halo between tiles
-  if (C == 24) return HW <= PcCfg<24>::NPIX;
+  if (HW < 4 || (HW & (HW - 1)) || (W & (W - 1))) return 0;
+  // whole images per tile half: no halo between tiles (C = 12 may also split one image over the two halves)
+  if (C == 12)   // one image split over the two halves needs its halo (W + 1 pixels) inside the staging window
+    return HW <= PcCfg<12>::NPIX / 2 || (HW == PcCfg<12>::NPIX && W + 1 <= PcCfg<12>::WIN - PcCfg<12>::NPIX / 2);
+  if (C == 24) return HW <= PcCfg<24>::NPIX / 2 && HW >= 4;
+  if (C == 48) return HW <= PcCfg<48>::NPIX / 2 && HW >= 4;
   return 0;
 }
 
@@ -315,7 +322,7 @@ extern "C" int nfk_pconv_coupling_fwd(const void* h2, const void* B3, int K3p, c
                                       float* hsave, float* ld, int B, int C, int H, int W, int hid, int reverse,
                                       void* stream) {
   if (B <= 0 || !nfk_pconv_coupling_supported(C, H, W, hid)) return NFK_ERR_SHAPE;
-  if (K3p % 128 || K3p < 9 * C) return NFK_ERR_SHAPE;
+  if (K3p % 64 || K3p < 9 * C || K3p > 128 * ((9 * C + 127) / 128)) return NFK_ERR_SHAPE;
   if (!h2 || !B3 || !bias3 || !y) return NFK_ERR_ARG;
   PcArgs g{};
   g.M = static_cast<long long>(B) * H * W;
@@ -326,5 +333,6 @@ extern "C" int nfk_pconv_coupling_fwd(const void* h2, const void* B3, int K3p, c
   g.bias3 = bias3; g.y = y; g.hsave = hsave; g.ld = ld; g.reverse = reverse;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (C == 12) return pc_launch<12>(h2, B3, K3p, g, hid, st);
-  return pc_launch<24>(h2, B3, K3p, g, hid, st);
+  if (C == 24) return pc_launch<24>(h2, B3, K3p, g, hid, st);
+  return pc_launch<48>(h2, B3, K3p, g, hid, st);
 }

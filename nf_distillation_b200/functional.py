@@ -259,7 +259,7 @@ def _conv3_coupling(h2, k: StepConsts, y, hsave, ld, B, C, H, W, hid, K3p, rever
     """Conv2dZeros + affine coupling on y (in place) / ld (accumulated): one fused kernel where the shape allows it,
     otherwise per-tap GEMM into P followed by the col2im + coupling kernel."""
     M = B * H * W
-    if USE_FUSED_PCONV and K3p % 128 == 0 and ops.pconv_coupling_supported(C, H, W, hid):
+    if USE_FUSED_PCONV and ops.pconv_coupling_supported(C, H, W, hid):
         ops.pconv_coupling_fwd(h2, k.B3, K3p, k.bias3, y, hsave, ld, B, C, H, W, hid, reverse)
         return
     P = torch.empty(M, K3p, device=h2.device, dtype=F32)

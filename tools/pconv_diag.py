@@ -53,3 +53,7 @@ if __name__ == "__main__":
     run(1024, 12, 16, 16, reverse=True)
     run(1024, 24, 8, 8)
     run(1023, 24, 8, 8)
+    run(5, 48, 4, 4)
+    run(1024, 48, 4, 4)
+    run(1021, 48, 4, 4, reverse=True)
+    run(9, 12, 8, 8)

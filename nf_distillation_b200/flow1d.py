@@ -117,8 +117,8 @@ def flowstep1d(step, input, y_onehot, logdet, reverse):
         if not step.invconv.LU_decomposed:
             raise NotImplementedError("training with LU_decomposed=False is not built")
         ws, bs = _mlp_params(step)
-        pctx, idx = Fn.prep_for(step, bool(reverse))
-        z, ld_out = FlowStep1dFn.apply(input, ld, cond, step, bool(reverse), pctx.token, pctx, idx, *ws, *bs)
+        pctx, idx, token = Fn.prep_for(step, bool(reverse))
+        z, ld_out = FlowStep1dFn.apply(input, ld, cond, step, bool(reverse), token, pctx, idx, *ws, *bs)
     else:
         Wf, sl, PF, _, _ = _consts(step, bool(reverse))
         x = input.contiguous()

@@ -104,16 +104,20 @@ class use_prep:
     def __exit__(self, *exc):
         if self.pctx is not None:
             _PREP_STACK.pop()
+            self.pctx.token = None   # every step has taken it; dropping it breaks the pctx <-> grad_fn reference cycle
         return False
 
 
 def prep_for(step, reverse):
-    """(pctx, index) of the innermost active batch that holds `step`, else a one-step batch built on the spot."""
+    """(pctx, index, token) of the innermost active batch that holds `step`, else a one-step batch built on the
+    spot (whose token reference is dropped at once: see use_prep.__exit__)."""
     for pctx in reversed(_PREP_STACK):
         i = pctx.lookup(step, reverse)
         if i is not None:
-            return pctx, i
-    return PrepCtx([step], reverse).build(), 0
+            return pctx, i, pctx.token
+    pctx = PrepCtx([step], reverse).build()
+    token, pctx.token = pctx.token, None
+    return pctx, 0, token
 
 
 def prepare_steps(layers, reverse):

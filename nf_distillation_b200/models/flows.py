@@ -145,8 +145,8 @@ class FlowStep(nn.Module):
             if needs_grad:
                 if not self.invconv.LU_decomposed:
                     raise NotImplementedError("training with LU_decomposed=False is not built")
-                pctx, idx = Fn.prep_for(self, False)
-                z, ld_out = Fn.FlowStep2dFn.apply(input, ld, self.hidden_channels, pctx.token, pctx, idx)
+                pctx, idx, token = Fn.prep_for(self, False)
+                z, ld_out = Fn.FlowStep2dFn.apply(input, ld, self.hidden_channels, token, pctx, idx)
             else:
                 z, ld_out, _ = Fn.flowstep2d_forward(input.contiguous(), ld.contiguous(), self._consts(False),
                                                      self.hidden_channels, keep=False)

@@ -153,3 +153,33 @@ def test_config5_celeba_64x64_training_gradients_vs_oracle(monkeypatch):
         assert (a @ b / (a.norm() * b.norm() + 1e-30)).item() > 0.995, n_
     errs.sort()
     assert errs[len(errs) // 2][0] < 1e-2 and errs[-1][0] < 0.25, (errs[len(errs) // 2], errs[-1])
+
+
+def test_eager_training_steps_do_not_accumulate_device_memory():
+    """The batched parameter prep hands a token through the autograd graph; nothing of a finished step (operands,
+    deposits, activations) may stay reachable once its backward has run, even with the cyclic GC off."""
+    import gc
+    from nf_distillation_b200.pl_module import NFModel
+    from nf_distillation_b200.train import glow_cfg, kd_config, randomise_zero_params
+    torch.manual_seed(0)
+    m = NFModel(kd_config(glow_cfg((32, 32, 3), 2, 3, 128), glow_cfg((32, 32, 3), 3, 3, 128)))
+    randomise_zero_params(m.student, 1)
+    randomise_zero_params(m.teacher, 2)
+    m.to(dev)
+    g = torch.Generator().manual_seed(2)
+    x = images(8, 32, g).to(dev)
+    gc.collect()
+    gc.disable()
+    try:
+        used = []
+        for it in range(6):
+            out = m.training_step([x.clone(), None], 0)
+            out["loss"].backward()
+            for p in m.student.parameters():
+                p.grad = None
+            del out
+            torch.cuda.synchronize()
+            used.append(torch.cuda.memory_allocated())
+        assert used[5] <= used[2] + (1 << 20), used
+    finally:
+        gc.enable()

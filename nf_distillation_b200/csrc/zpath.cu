@@ -44,6 +44,23 @@ struct Geo {
   int lgHW, lgW;  // H, W are powers of two for the forward kernels
 };
 
+// Staging tile (rows of r16 16-byte chunks, row stride rs16) -> global rows of r16 chunks, consecutive threads on
+// consecutive chunks. r16 = K/8 is a power of two for every shipped width except K = 448, so a thread's chunk column is
+// fixed and its row advances by ZT / r16 per pass (no per-element division).
+__device__ __forceinline__ void copy_out_rows(uint4* __restrict__ out4, const uint4* __restrict__ cst, int npix,
+                                              int r16, int rs16, int tid) {
+  if ((r16 & (r16 - 1)) == 0 && r16 <= ZT) {
+    const int lg = __ffs(r16) - 1;
+    const int c4 = tid & (r16 - 1), step = ZT >> lg;
+    for (int pl = tid >> lg; pl < npix; pl += step) out4[(pl << lg) + c4] = cst[pl * rs16 + c4];
+  } else {
+    for (int i = tid; i < npix * r16; i += ZT) {
+      const int pl = i / r16, c4 = i - pl * r16;
+      out4[i] = cst[pl * rs16 + c4];
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------ affine1x1 fwd
 // One CTA = `ipc` whole images (the 3x3 im2col needs their halo). H, W are powers of two (shifts, no divisions).
 // Phase 1: thread = (pixel, output group): y = W'x + b' with x in registers, W' broadcast from smem (LDS.128).
@@ -154,10 +171,7 @@ affine1x1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ Wf, 
   __syncthreads();
   // Phase 3: coalesced copy-out, 16 bytes per thread, consecutive threads -> consecutive chunks of the same row
   uint4* out4 = reinterpret_cast<uint4*>(col + (static_cast<long long>(b0) << g.lgHW) * K1p);
-  for (int i = tid; i < npix * r16; i += ZT) {
-    const int pl = i / r16, c4 = i - pl * r16;
-    out4[i] = cst[pl * rs16 + c4];
-  }
+  copy_out_rows(out4, cst, npix, r16, rs16, tid);
 }
 
 // ------------------------------------------------------------------------------------------ coupling fwd / inv
@@ -257,42 +271,67 @@ coupling_bwd_kernel(const float* __restrict__ g_out, const float* __restrict__ g
     const int npix = banded ? tile : nimg << g.lgHW;
     const int np2 = npix + 2 * halo;
     __syncthreads();   // previous group's tiles are free (also orders the dbs zeroing)
-    // ---- phase 1
-    for (int i = tid; i < J * np2; i += ZT) {
-      const int jj = i / np2, pq = i - jj * np2;     // pixel fastest (np2 is a multiple of 32 or the whole tile)
-      const int pl = pq - halo;
-      const bool own = pl >= 0 && pl < npix;
-      const int img = banded ? 0 : pl >> g.lgHW;
-      const int rem = banded ? p0 + pl : pl & HWm;
-      float dsh = 0.f, dlg = 0.f;
-      if (rem >= 0 && rem < g.HW) {
-        const long long lo = ((static_cast<long long>(b0 + img) * C + jj) << g.lgHW) + rem;
-        const long long hi = lo + (static_cast<long long>(J) << g.lgHW);
-        const long long m = (static_cast<long long>(b0 + img) << g.lgHW) + rem;
-        const float g2 = g_out[hi], o2 = z_out[hi];
-        const float2 h = *reinterpret_cast<const float2*>(hsave + m * C + 2 * jj);
-        float sg, lsv;
-        sigmoid_logsigmoid(h.y + 2.f, sg, lsv);
-        dsh = g2 * sg;
-        dlg = (g2 * o2 + g_ld[b0 + img]) * (1.f - sg);
-        if (own) {
-          dy[lo] = g_out[lo];  // z1 passes through; the coupling-net gradient is added by affine1x1_bwd
-          dy[hi] = dsh;        // dL/dy2
+    // ---- phase 1: UN items per thread at a time, every global load of the batch in flight before the first use
+    constexpr int UN = 4;
+    for (int i0 = tid; i0 < J * np2; i0 += UN * ZT) {
+      float g1[UN], g2[UN], o2[UN], glv[UN];
+      float2 hh[UN];
+      long long lo[UN];
+      int pqv[UN], jjv[UN];
+      bool inr[UN], ownv[UN];
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        const int i = i0 + u * ZT;
+        const int jj = i / np2, pq = i - jj * np2;     // pixel fastest (np2 is a multiple of 32 or the whole tile)
+        const int pl = pq - halo;
+        const int img = banded ? 0 : pl >> g.lgHW;
+        const int rem = banded ? p0 + pl : pl & HWm;
+        jjv[u] = jj; pqv[u] = pq;
+        ownv[u] = i < J * np2 && pl >= 0 && pl < npix;
+        inr[u] = i < J * np2 && rem >= 0 && rem < g.HW;
+        g1[u] = g2[u] = o2[u] = glv[u] = 0.f;
+        hh[u] = make_float2(0.f, 0.f);
+        lo[u] = 0;
+        if (inr[u]) {
+          lo[u] = ((static_cast<long long>(b0 + img) * C + jj) << g.lgHW) + rem;
+          const long long hi = lo[u] + (static_cast<long long>(J) << g.lgHW);
+          const long long m = (static_cast<long long>(b0 + img) << g.lgHW) + rem;
+          g2[u] = g_out[hi];
+          o2[u] = z_out[hi];
+          hh[u] = *reinterpret_cast<const float2*>(hsave + m * C + 2 * jj);
+          glv[u] = g_ld[b0 + img];
+          if (ownv[u]) g1[u] = g_out[lo[u]];
         }
       }
-      dhs[(2 * jj) * ldp + pq] = dsh;
-      dhs[(2 * jj + 1) * ldp + pq] = dlg;
-      // bias gradient: a warp's 32 items share jj whenever np2 % 32 == 0 (always for >= 2 images of >= 16 pixels)
-      float a = own ? dsh : 0.f, bsum = own ? dlg : 0.f;
-      if ((np2 & 31) == 0) {
-        for (int o = 16; o > 0; o >>= 1) {
-          a += __shfl_xor_sync(0xffffffffu, a, o);
-          bsum += __shfl_xor_sync(0xffffffffu, bsum, o);
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        if (i0 + u * ZT >= J * np2) continue;   // warp-uniform: J * np2 is a multiple of 32 whenever shuffles are used
+        float dsh = 0.f, dlg = 0.f;
+        if (inr[u]) {
+          float sg, lsv;
+          sigmoid_logsigmoid(hh[u].y + 2.f, sg, lsv);
+          dsh = g2[u] * sg;
+          dlg = (g2[u] * o2[u] + glv[u]) * (1.f - sg);
+          if (ownv[u]) {
+            dy[lo[u]] = g1[u];  // z1 passes through; the coupling-net gradient is added by affine1x1_bwd
+            dy[lo[u] + (static_cast<long long>(J) << g.lgHW)] = dsh;        // dL/dy2
+          }
         }
-        if ((tid & 31) == 0) { atomicAdd(&dbs[2 * jj], a); atomicAdd(&dbs[2 * jj + 1], bsum); }
-      } else {
-        atomicAdd(&dbs[2 * jj], a);
-        atomicAdd(&dbs[2 * jj + 1], bsum);
+        const int jj = jjv[u];
+        dhs[(2 * jj) * ldp + pqv[u]] = dsh;
+        dhs[(2 * jj + 1) * ldp + pqv[u]] = dlg;
+        // bias gradient: a warp's 32 items share jj whenever np2 % 32 == 0 (always for >= 2 images of >= 16 pixels)
+        float a = ownv[u] ? dsh : 0.f, bsum = ownv[u] ? dlg : 0.f;
+        if ((np2 & 31) == 0) {
+          for (int o = 16; o > 0; o >>= 1) {
+            a += __shfl_xor_sync(0xffffffffu, a, o);
+            bsum += __shfl_xor_sync(0xffffffffu, bsum, o);
+          }
+          if ((tid & 31) == 0) { atomicAdd(&dbs[2 * jj], a); atomicAdd(&dbs[2 * jj + 1], bsum); }
+        } else {
+          atomicAdd(&dbs[2 * jj], a);
+          atomicAdd(&dbs[2 * jj + 1], bsum);
+        }
       }
     }
     __syncthreads();
@@ -331,10 +370,7 @@ coupling_bwd_kernel(const float* __restrict__ g_out, const float* __restrict__ g
     }
     __syncthreads();
     uint4* out4 = reinterpret_cast<uint4*>(dhcol + ((static_cast<long long>(b0) << g.lgHW) + p0) * K3p);
-    for (int i = tid; i < npix * r16; i += ZT) {
-      const int pl = i / r16, c4 = i - pl * r16;
-      out4[i] = cst[pl * rs16 + c4];
-    }
+    copy_out_rows(out4, cst, npix, r16, rs16, tid);
   }
   __syncthreads();
   for (int i = tid; i < C; i += ZT) atomicAdd(dbias3 + i, dbs[i]);
@@ -395,21 +431,38 @@ affine1x1_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ dco
     }
     __syncthreads();
     if (dcol) {
-      // dy1[ci, m] += sum_tap dcol[m - off(tap), tap*CH + ci]
-      for (int i = tid; i < CH * npix; i += ZT) {
-        const int pl = i / CH, ci = i - pl * CH;
-        const int rem = pl & HWm;
-        const int yy = rem >> g.lgW, xx = rem & Wm;
-        const long long m = (static_cast<long long>(b0) << g.lgHW) + pl;
-        float a = 0.f;
+      // dy1[ci, m] += sum_tap dcol[m - off(tap), tap*CH + ci]; two items per thread at a time so that 18 loads of
+      // the (HBM-resident) dcol rows are in flight before the first add
+      constexpr int UN = 2;
+      for (int i0 = tid; i0 < CH * npix; i0 += UN * ZT) {
+        float v[UN][9];
 #pragma unroll
-        for (int tap = 0; tap < 9; ++tap) {
-          const int ddy = tap / 3 - 1, ddx = tap % 3 - 1;
-          const int ny = yy - ddy, nx = xx - ddx;
-          if (ny >= 0 && ny < g.H && nx >= 0 && nx < g.W)
-            a += __ldg(dcol + (m - ddy * g.W - ddx) * K1p + tap * CH + ci);
+        for (int u = 0; u < UN; ++u) {
+          const int i = i0 + u * ZT;
+          const bool live = i < CH * npix;
+          const int pl = live ? i / CH : 0, ci = live ? i - pl * CH : 0;
+          const int rem = pl & HWm;
+          const int yy = rem >> g.lgW, xx = rem & Wm;
+          const long long m = (static_cast<long long>(b0) << g.lgHW) + pl;
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap) {
+            const int ddy = tap / 3 - 1, ddx = tap % 3 - 1;
+            const int ny = yy - ddy, nx = xx - ddx;
+            v[u][tap] = (live && ny >= 0 && ny < g.H && nx >= 0 && nx < g.W)
+                            ? __ldg(dcol + (m - ddy * g.W - ddx) * K1p + tap * CH + ci) : 0.f;
+          }
         }
-        dys[ci * ldp + pl] += a;
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+          const int i = i0 + u * ZT;
+          if (i < CH * npix) {
+            const int pl = i / CH, ci = i - pl * CH;
+            float a = 0.f;
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) a += v[u][tap];
+            dys[ci * ldp + pl] += a;
+          }
+        }
       }
       __syncthreads();
     }

@@ -48,3 +48,19 @@ for (C, H) in ((12, 16), (24, 8), (48, 4)):
     t = timeit(lambda i: ops.coupling_fwd(Ps[i], K3p, b3, ys[i], None, ld1, B, C, H, W, False), nbuf)
     by = M * (K3p * 4 + C * 4)
     print(f"                         coupling_fwd  {t:7.1f} us  {by/1e6:7.1f} MB  {by/t*1e6/HBM*100:5.1f}% of HBM peak")
+    # backward kernels of the student
+    gouts = [torch.randn(B, C, H, W, device=dev) for _ in range(nbuf)]
+    hsv = [torch.randn(M, C, device=dev) for _ in range(nbuf)]
+    dys = [torch.empty(B, C, H, W, device=dev) for _ in range(nbuf)]
+    dhcols = [torch.empty(M, K3p, device=dev, dtype=torch.bfloat16) for _ in range(nbuf)]
+    gld = torch.randn(B, device=dev)
+    db3 = torch.zeros(C, device=dev)
+    t = timeit(lambda i: ops.coupling_bwd(gouts[i], gld, ys[i], hsv[i], dys[i], dhcols[i], K3p, db3, B, C, H, W), nbuf)
+    by = M * (C * 4 + C * 2 + C * 4 + C * 4 + K3p * 2)
+    print(f"                         coupling_bwd  {t:7.1f} us  {by/1e6:7.1f} MB  {by/t*1e6/HBM*100:5.1f}% of HBM peak")
+    dcols = [torch.randn(M, K1p, device=dev) * 0.1 for _ in range(nbuf)]
+    dxs = [torch.empty(B, C, H, W, device=dev) for _ in range(nbuf)]
+    dWf, dbf = torch.zeros(C, C, device=dev), torch.zeros(C, device=dev)
+    t = timeit(lambda i: ops.affine1x1_bwd(dys[i], dcols[i], K1p, xs[i], Wf, dxs[i], dWf, dbf, B, C, H, W), nbuf)
+    by = M * (C * 12 + K1p * 4)
+    print(f"                         affine1x1_bwd {t:7.1f} us  {by/1e6:7.1f} MB  {by/t*1e6/HBM*100:5.1f}% of HBM peak")

@@ -386,14 +386,14 @@ template <int C>
 __global__ void __launch_bounds__(ZT)
 affine1x1_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ dcol, int K1p,
                      const float* __restrict__ x, const float* __restrict__ Wf, float* __restrict__ dx,
-                     float* __restrict__ dWf, float* __restrict__ dbf, Geo g) {
+                     float* __restrict__ dWf, float* __restrict__ dbf, Geo g, int tile_floats) {
   extern __shared__ float sm[];
   constexpr int CH = C / 2;
   const int ldp = g.pixt + 1;
   float* WT = sm;
   float* dys = WT + C * C;
   float* xs = dys + C * ldp;
-  float* acc = xs + C * ldp;
+  float* acc = dys + tile_floats;   // tile_floats >= 2*C*ldp, and >= the slice-reduction scratch at the end
   const int tid = threadIdx.x;
   const int HWm = g.HW - 1, Wm = g.W - 1;
   const int ngroups = (g.B + g.ipc - 1) / g.ipc;
@@ -413,27 +413,37 @@ affine1x1_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ dco
     const int nimg = min(g.ipc, g.B - b0);
     const int npix = nimg << g.lgHW;
     __syncthreads();
-    // coalesced tile loads (pixel fastest)
-    for (int i = tid; i < C * npix; i += ZT) {
-      const int pl = i & (npix - 1) , c = i / npix;             // npix = nimg * HW; nimg may be non-pow2 only at the tail
-      if ((npix & (npix - 1)) != 0) {                           // generic path for a ragged last group
-        const int c2 = i / npix, p2 = i - c2 * npix;
-        const int img = p2 >> g.lgHW, rem = p2 & HWm;
-        const long long gi = ((static_cast<long long>(b0 + img) * C + c2) << g.lgHW) + rem;
-        xs[c2 * ldp + p2] = x[gi];
-        dys[c2 * ldp + p2] = dy[gi];
-      } else {
-        const int img = pl >> g.lgHW, rem = pl & HWm;
-        const long long gi = ((static_cast<long long>(b0 + img) * C + c) << g.lgHW) + rem;
-        xs[c * ldp + pl] = x[gi];
-        dys[c * ldp + pl] = dy[gi];
+    // coalesced tile loads (pixel fastest), four (x, dy) pairs per thread in flight at a time
+    {
+      constexpr int UL = 4;
+      const int total = C * npix;
+      for (int i0 = tid; i0 < total; i0 += UL * ZT) {
+        float xv[UL], dv[UL];
+        int so[UL];
+#pragma unroll
+        for (int u = 0; u < UL; ++u) {
+          const int i = i0 + u * ZT;
+          xv[u] = dv[u] = 0.f;
+          so[u] = -1;
+          if (i < total) {
+            const int c = i / npix, pl = i - c * npix;
+            const int img = pl >> g.lgHW, rem = pl & HWm;
+            const long long gi = ((static_cast<long long>(b0 + img) * C + c) << g.lgHW) + rem;
+            xv[u] = x[gi];
+            dv[u] = dy[gi];
+            so[u] = c * ldp + pl;
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < UL; ++u)
+          if (so[u] >= 0) { xs[so[u]] = xv[u]; dys[so[u]] = dv[u]; }
       }
     }
     __syncthreads();
     if (dcol) {
-      // dy1[ci, m] += sum_tap dcol[m - off(tap), tap*CH + ci]; two items per thread at a time so that 18 loads of
+      // dy1[ci, m] += sum_tap dcol[m - off(tap), tap*CH + ci]; three items per thread at a time so that 27 loads of
       // the (HBM-resident) dcol rows are in flight before the first add
-      constexpr int UN = 2;
+      constexpr int UN = 3;
       for (int i0 = tid; i0 < CH * npix; i0 += UN * ZT) {
         float v[UN][9];
 #pragma unroll
@@ -520,6 +530,10 @@ affine1x1_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ dco
       }
     }
   }
+  // the pixel slices of a block meet through a scratch tile (the x / dy tiles are dead now): shared-memory float
+  // atomics are CAS loops, and up to 28 slices would fight over each entry
+  __syncthreads();
+  float* scratch = dys;   // dys and xs are contiguous: 2*C*ldp floats >= SL * C * C for every supported shape
 #pragma unroll
   for (int rb = 0; rb < RB; ++rb) {
     const int blk = (NBK < ZT ? tid % NBK : tid) + rb * ZT;
@@ -529,7 +543,13 @@ affine1x1_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ dco
 #pragma unroll
     for (int q = 0; q < 4; ++q)
 #pragma unroll
-      for (int r = 0; r < 4; ++r) atomicAdd(&acc[(4 * to + q) * C + 4 * ti + r], wacc[rb][q][r]);
+      for (int r = 0; r < 4; ++r) scratch[slice * C * C + (4 * to + q) * C + 4 * ti + r] = wacc[rb][q][r];
+  }
+  __syncthreads();
+  for (int i = tid; i < C * C; i += ZT) {
+    float a = 0.f;
+    for (int sl2 = 0; sl2 < SL; ++sl2) a += scratch[sl2 * C * C + i];
+    acc[i] += a;
   }
   __syncthreads();
   for (int i = tid; i < C * C; i += ZT) atomicAdd(dWf + i, acc[i]);
@@ -649,14 +669,18 @@ extern "C" int nfk_affine1x1_bwd(const float* dy, const float* dcol, int K1p, co
   if (B <= 0 || H <= 0 || W <= 0 || H * W > 4096 || !pow2(H) || !pow2(W)) return NFK_ERR_SHAPE;
   if (!dy || !x || !Wf || !dx || !dWf || !dbf) return NFK_ERR_ARG;
   Geo g = make_geo(B, C, H, W, true);
-  const int smem = (C * C + 2 * C * (g.pixt + 1) + C * C + C) * 4;
+  const int nbk = (C / 4) * (C / 4);
+  const int slices = nbk >= ZT ? 1 : ZT / nbk;
+  int tile_floats = 2 * C * (g.pixt + 1);
+  if (tile_floats < slices * C * C) tile_floats = slices * C * C;   // scratch of the final slice reduction
+  const int smem = (C * C + tile_floats + C * C + C) * 4;
   const int groups = (B + g.ipc - 1) / g.ipc;
   const int grid = groups < 4 * 148 ? groups : 4 * 148;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   NFK_DISPATCH_C(C, {
     int rc = ensure_smem(affine1x1_bwd_kernel<CC>, smem);
     if (rc) return rc;
-    affine1x1_bwd_kernel<CC><<<grid, ZT, smem, st>>>(dy, dcol, K1p, x, Wf, dx, dWf, dbf, g);
+    affine1x1_bwd_kernel<CC><<<grid, ZT, smem, st>>>(dy, dcol, K1p, x, Wf, dx, dWf, dbf, g, tile_floats);
   });
   return cudaGetLastError() == cudaSuccess ? NFK_OK : NFK_ERR_LAUNCH;
 }

@@ -86,22 +86,47 @@ affine1x1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ Wf, 
   const int ldp = g.pixt + 1;
   const int HWm = g.HW - 1, Wm = g.W - 1;
 
+  const int pixb = ZT / g.og;            // pixels per pass; lanes = consecutive pixels, output groups across warps
+  const int og = tid / pixb;
+  const int opg = C / g.og;              // outputs per group
+  // narrow steps: the first pass's inputs are requested before the weights, so the two global round trips overlap
+  // (wide ones would carry C live registers across the barrier and lose a resident CTA)
+  constexpr bool PREFETCH_X = C <= 24;
+  float xv[C];
+  if (PREFETCH_X) {
+    const int pl = tid % pixb;
+    if (pl < npix && og < g.og) {
+      const float* xp = x + (static_cast<long long>(b0 + (pl >> g.lgHW)) * C << g.lgHW) + (pl & HWm);
+#pragma unroll
+      for (int i = 0; i < C; ++i) xv[i] = __ldg(xp + (static_cast<long long>(i) << g.lgHW));
+    }
+  }
   if (Wf) {
-    for (int i = tid; i < C * C; i += ZT) Ws[i] = Wf[i];
+    // C*C/4 float4 weights: all of a thread's loads first, then its stores (C*C is a multiple of 4; cudaMalloc'd)
+    constexpr int W4 = C * C / 4, WPT = (W4 + ZT - 1) / ZT;
+    float4 wreg[WPT];
+#pragma unroll
+    for (int k = 0; k < WPT; ++k) {
+      const int i = tid + k * ZT;
+      if (i < W4) wreg[k] = __ldg(reinterpret_cast<const float4*>(Wf) + i);
+    }
+#pragma unroll
+    for (int k = 0; k < WPT; ++k) {
+      const int i = tid + k * ZT;
+      if (i < W4) reinterpret_cast<float4*>(Ws)[i] = wreg[k];
+    }
     for (int i = tid; i < C; i += ZT) bs[i] = bf[i];
   }
   if (ld_out && tid < nimg) ld_out[b0 + tid] = ld_in[b0 + tid] + sl[0] * static_cast<float>(g.HW);
   __syncthreads();
 
-  const int pixb = ZT / g.og;            // pixels per pass; lanes = consecutive pixels, output groups across warps
-  const int og = tid / pixb;
-  const int opg = C / g.og;              // outputs per group
   for (int pl = tid % pixb; pl < npix && og < g.og; pl += pixb) {
     const int img = pl >> g.lgHW, p = pl & HWm;
     const float* xp = x + (static_cast<long long>(b0 + img) * C << g.lgHW) + p;
-    float xv[C];
+    if (!PREFETCH_X || pl >= pixb) {   // later passes (the first one was prefetched above)
 #pragma unroll
-    for (int i = 0; i < C; ++i) xv[i] = __ldg(xp + (static_cast<long long>(i) << g.lgHW));
+      for (int i = 0; i < C; ++i) xv[i] = __ldg(xp + (static_cast<long long>(i) << g.lgHW));
+    }
     if (Wf) {
       float* yp = y + (static_cast<long long>(b0 + img) * C << g.lgHW) + p;
       for (int o = og * opg; o < (og + 1) * opg; ++o) {
@@ -119,7 +144,9 @@ affine1x1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ Wf, 
         if (col && o < CH) y1s[o * ldp + pl] = acc;
       }
     } else if (col) {
-      for (int o = og * opg; o < (og + 1) * opg && o < CH; ++o) y1s[o * ldp + pl] = xv[o];
+#pragma unroll
+      for (int o = 0; o < CH; ++o)   // static register indices (a runtime xv[o] would push xv to local memory)
+        if (o >= og * opg && o < (og + 1) * opg) y1s[o * ldp + pl] = xv[o];
     }
   }
   if (!col) return;

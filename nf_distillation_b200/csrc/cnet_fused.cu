@@ -194,24 +194,33 @@ cnet_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmCol, const __grid_co
     // 16 accumulator columns (already in registers) -> bias + ReLU -> bf16 -> two 16-byte chunks (cc0, cc0 + 1) of
     // this thread's 128-byte row in a swizzled panel; returns the 16 ReLU mask bits
     auto epi16 = [&](const uint32_t (&r)[16], const float* bias16, uint8_t* dst, int cc0, bool want_bits) -> uint32_t {
-      float v[16];
+      // packed arithmetic: bias add as add.f32x2, round to bf16x2, ReLU on the packed pair (max.bf16x2 with +0 equals
+      // rounding the fp32 ReLU: rounding is monotonic and keeps the sign) -- 24 issue slots per 16 columns instead of 40
+      uint32_t p[8];
+      const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
 #pragma unroll
       for (int j = 0; j < 16; j += 4) {
         const float4 b = __ldg(reinterpret_cast<const float4*>(bias16 + j));
-        v[j] = fmaxf(__uint_as_float(r[j]) + b.x, 0.f);
-        v[j + 1] = fmaxf(__uint_as_float(r[j + 1]) + b.y, 0.f);
-        v[j + 2] = fmaxf(__uint_as_float(r[j + 2]) + b.z, 0.f);
-        v[j + 3] = fmaxf(__uint_as_float(r[j + 3]) + b.w, 0.f);
+        const float2 s0 = __fadd2_rn(make_float2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])),
+                                     make_float2(b.x, b.y));
+        const float2 s1 = __fadd2_rn(make_float2(__uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])),
+                                     make_float2(b.z, b.w));
+        const __nv_bfloat162 h0 = __hmax2(__float22bfloat162_rn(s0), zero2);
+        const __nv_bfloat162 h1 = __hmax2(__float22bfloat162_rn(s1), zero2);
+        p[j / 2] = *reinterpret_cast<const uint32_t*>(&h0);
+        p[j / 2 + 1] = *reinterpret_cast<const uint32_t*>(&h1);
       }
       uint32_t bits = 0;
-      if (want_bits) {
+      if (want_bits) {   // value > 0  <=>  the (non-negative) bf16 is not +0
 #pragma unroll
-        for (int j = 0; j < 16; ++j) bits |= (v[j] > 0.f ? 1u : 0u) << j;
+        for (int k = 0; k < 8; ++k) {
+          bits |= ((p[k] & 0xFFFFu) ? 1u : 0u) << (2 * k);
+          bits |= ((p[k] >> 16) ? 1u : 0u) << (2 * k + 1);
+        }
       }
-      *reinterpret_cast<uint4*>(dst + ((static_cast<uint32_t>(cc0) ^ sw) << 4)) =
-          make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
+      *reinterpret_cast<uint4*>(dst + ((static_cast<uint32_t>(cc0) ^ sw) << 4)) = make_uint4(p[0], p[1], p[2], p[3]);
       *reinterpret_cast<uint4*>(dst + ((static_cast<uint32_t>(cc0 + 1) ^ sw) << 4)) =
-          make_uint4(pack2(v[8], v[9]), pack2(v[10], v[11]), pack2(v[12], v[13]), pack2(v[14], v[15]));
+          make_uint4(p[4], p[5], p[6], p[7]);
       return bits;
     };
     // 64 columns held in R[4 pz .. 4 pz + 3] -> one swizzled panel slice (32 rows x 128 B) at `dst_rows`, plus the two

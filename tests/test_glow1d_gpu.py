@@ -151,3 +151,42 @@ def test_ragged_batch_gradients_match_oracle_both_directions(D, hid, K, B):
             continue
         assert p.grad is not None, n_
         assert rel(p.grad, sd[n_].grad) < 1e-4, n_
+
+
+@pytest.mark.parametrize("D,Cc,hid,B", [(10, 3, 32, 300), (63, 5, 16, 131)])
+def test_conditioned_1d_step_matches_oracle(D, Cc, hid, B):
+    """y-conditioned 1-D FlowStep (the coupling MLP sees [z1 | y_onehot], reference flows.py:156-166 with
+    condition_features > 0): forward, inverse and parameter / input gradients against the oracle step. fp32."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from oracle import glow_oracle as O
+    from nf_distillation_b200.models.flows import FlowStep
+    torch.manual_seed(D * 7 + Cc)
+    step = FlowStep(D, hid, 1.0, "invconv", "affine", True, is_1d=True, condition_features=Cc)
+    with torch.no_grad():
+        for p in step.parameters():
+            if p.abs().max() == 0:
+                p.normal_(0, 0.05)
+    step.actnorm.inited = True
+    sd = {"s." + k: v.clone().requires_grad_(k in dict(step.named_parameters())) for k, v in step.state_dict().items()}
+    x = torch.randn(B, D)
+    cond = torch.nn.functional.one_hot(torch.randint(0, Cc, (B,)), Cc).float()
+    wz, wl = torch.randn(B, D), torch.randn(B)
+    xo = x.clone().requires_grad_(True)
+    zo, ldo = O.flowstep(xo, sd, "s.", torch.zeros(B), False, y_onehot=cond)
+    xr, ldr = O.flowstep(zo.detach(), sd, "s.", torch.zeros(B), True, y_onehot=cond)
+    ((zo * wz).sum() + (ldo * wl).sum()).backward()
+    step = step.to(dev).train()
+    xg = x.to(dev).requires_grad_(True)
+    z, ld = step(xg, y_onehot=cond.to(dev), logdet=torch.zeros(B, device=dev), reverse=False)
+    assert rel(z, zo.detach()) < 1e-5 and rel(ld, ldo.detach()) < 1e-5
+    with torch.no_grad():
+        back, ldb = step(z.detach(), y_onehot=cond.to(dev), logdet=torch.zeros(B, device=dev), reverse=True)
+    assert rel(back, xr.detach()) < 1e-4 and rel(ldb, ldr.detach()) < 1e-4 and rel(back, x) < 1e-4
+    ((z * wz.to(dev)).sum() + (ld * wl.to(dev)).sum()).backward()
+    assert rel(xg.grad, xo.grad) < 1e-4
+    for n_, p in step.named_parameters():
+        ref = sd["s." + n_].grad
+        if ref is None:
+            continue
+        assert p.grad is not None and rel(p.grad, ref) < 1e-4, n_

@@ -182,6 +182,10 @@ int nfk_pconv_coupling_fwd(const void* h2, const void* B3, int K3p, const float*
  *   PF: per layer WT [nin][nout8] + bias [nout8] (forward), PB: per layer W [nout][nin8] (backward).
  * nfk_flow1d_sizes reports the block sizes and the per-layer offsets of the gradient block G
  * (dW_l [nout][nin8] at offG, db_l at offGB). x / y / dx are [B, D] row-major, cond is [B, Cc] (y_onehot). */
+/* 1 when the step's weights (six Linear layers + the fused affine) and a sample tile fit in shared memory: for the
+ * inference kernel (hidden widths up to 88 at D = 63), and with training != 0 also for the activation-saving
+ * forward and the backward (which holds the weights and their gradient block: widths up to 48), else 0. */
+int nfk_flow1d_supported(int D, int Cc, int hid, int training);
 int nfk_flow1d_sizes(int D, int Cc, int hid, int* total_fwd, int* total_bwd, int* total_grad, int* n_act,
                      int* offsets);
 int nfk_flow1d_pack(const float* Wf, const float* bf, const float* const* w, const float* const* b, int D, int Cc,

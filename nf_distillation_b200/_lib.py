@@ -73,6 +73,7 @@ SIGNATURES: dict[str, list] = {
     "nfk_prior_bpd_bwd": [_vp] * 4 + [_i, _i, _f, _vp, _vp, _vp],
     "nfk_kd_mse_fwd": [_vp, _vp, _i, _i, _f, _vp, _vp],
     "nfk_kd_mse_bwd": [_vp, _vp, _vp, _i, _i, _f, _vp, _i, _vp],
+    "nfk_flow1d_supported": [_i, _i, _i, _i],
     "nfk_flow1d_sizes": [_i, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "nfk_flow1d_pack": [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp],
     "nfk_flow1d_fwd": [_vp] * 8 + [_i] * 5 + [_vp],

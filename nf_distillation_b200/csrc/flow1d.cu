@@ -684,6 +684,22 @@ extern "C" int nfk_flow1d_sizes(int D, int Cc, int hid, int* total_fwd, int* tot
   return NFK_OK;
 }
 
+extern "C" int nfk_flow1d_supported(int D, int Cc, int hid, int training) {
+  // the fused kernels keep every weight of the step in shared memory: 1 when the inference kernel -- and, with
+  // training != 0, the activation-saving forward and the backward of both directions -- find a sample tile that fits
+  if (D < 2 || hid <= 0 || Cc < 0) return 0;
+  const F1Dims d = f1_dims(D, Cc, hid);
+  int smem = 0;
+  F1Run run{};
+  if (!f1_tile_fwd(d, false, &smem, &run)) return 0;
+  if (!training) return 1;
+  if (!f1_tile_fwd(d, true, &smem, &run)) return 0;
+  const int mlp_scr = hid > d.nin[1] ? hid : d.nin[1];
+  const int gzr = up8(D) > mlp_scr ? up8(D) : mlp_scr;
+  if (!f1_tile_bwd(d, mlp_scr, up8(D), &smem, &run) || !f1_tile_bwd(d, up8(D), gzr, &smem, &run)) return 0;
+  return 1;
+}
+
 extern "C" int nfk_flow1d_pack(const float* Wf, const float* bf, const float* const* w, const float* const* b, int D,
                                int Cc, int hid, float* PF, float* PB, void* stream) {
   if (D < 2 || hid <= 0 || Cc < 0) return NFK_ERR_SHAPE;

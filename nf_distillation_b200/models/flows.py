@@ -119,6 +119,15 @@ class FlowStep(nn.Module):
         if self.flow_permutation_type != "invconv" or self.flow_coupling != "affine":
             raise NotImplementedError("the CUDA path covers flow_permutation='invconv' + flow_coupling='affine' "
                                       "(every shipped config); shuffle/reverse/additive are not built yet")
+        if self.is_1d:
+            from .. import ops
+            training = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+            if not ops.flow1d_supported(self.in_channels, self.condition_features, self.hidden_channels, training):
+                raise NotImplementedError(
+                    f"the fused 1-D FlowStep keeps the whole coupling MLP in shared memory; hidden_channels="
+                    f"{self.hidden_channels} at D={self.in_channels} does not fit "
+                    f"({'training: widths up to 48' if training else 'inference: widths up to 88'}). The tabular "
+                    f"configs use 16 / 32; conf/teacher/rich.yaml (256) is not covered yet.")
         if not self.is_1d:
             if self.condition_features:
                 raise NotImplementedError("y-conditioned 2-D coupling is not built (no shipped image config uses it)")

@@ -250,6 +250,10 @@ def pconv_coupling_fwd(h2, B3, K3p, bias3, y, hsave, ld, B, C, H, W, hid, revers
                                      int(reverse), _st()), "nfk_pconv_coupling_fwd")
 
 
+def flow1d_supported(D, Cc, hid, training=False):
+    return bool(LIB.nfk_flow1d_supported(D, Cc, hid, int(training)))
+
+
 def flow1d_sizes(D, Cc, hid):
     """(total_fwd, total_bwd, total_grad, n_act, per-layer [(offG, offGB, ninp, noutp)] * 7)."""
     import ctypes

@@ -102,6 +102,76 @@ class FlowStep1dFn(torch.autograd.Function):
         return (dx, g_ld, None, None, None, None, None, None, *dws, *dbs)
 
 
+# ---------------------------------------------------------------------------------------- wide MLPs (inference)
+def _wide_consts(step, reverse):
+    """Frozen wide step (hidden width a multiple of 64 that does not fit the fused kernel, e.g. conf/teacher/rich.yaml:
+    256): fused affine of this direction + the six Linear layers as zero-padded bf16 GEMM operands. Cached."""
+    key = (reverse, tuple((p.data_ptr(), p._version) for p in step._all_params()))
+    hit = step._cache.get(("1dw", reverse))
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    D = step.in_channels
+    inv = tuple(None if t is None else t.detach() for t in step.invconv.lu_tensors())
+    Wf, bf, sl = Fn.build_affine(step.actnorm.bias.detach(), step.actnorm.logs.detach(), inv, D, reverse, True)
+    ws, bs = _mlp_params(step)
+    Wb, bb = [], []
+    for w, b in zip(ws, bs):
+        nout, nin = w.shape
+        n_p, k_p = ops.round_up(nout, 16), ops.round_up(nin, 64)
+        wp = torch.zeros(n_p, k_p, device=w.device, dtype=torch.bfloat16)
+        wp[:nout, :nin] = w.detach()
+        bp = torch.zeros(n_p, device=w.device, dtype=F32)
+        bp[:nout] = b.detach()
+        Wb.append(wp)
+        bb.append(bp)
+    out = (Wf, bf, sl, Wb, bb)
+    step._cache[("1dw", reverse)] = (key, out)
+    return out
+
+
+def _flowstep1d_wide(step, x, cond, ld, reverse):
+    """Inference of a 1-D FlowStep whose coupling MLP is too wide for shared memory: the affine on the fp32 row kernel,
+    the MLP as tcgen05 GEMMs (bf16 operands, fp32 accumulate, bias+ReLU epilogues; 1e-2 tolerance class like the 2-D
+    coupling nets), tanh / coupling as elementwise torch ops. Gradients are not built for this path."""
+    Wf, bf, sl, Wb, bb = _wide_consts(step, reverse)
+    B, D = x.shape
+    D1, D2, hid = D // 2, D - D // 2, step.hidden_channels
+    dev = x.device
+    if not reverse:
+        z = torch.empty_like(x)
+        ld1 = torch.empty(B, device=dev, dtype=F32)
+        ops.affine_rows(x, Wf, bf, sl, z, ld, ld1, B, D, 1.0)
+    else:
+        z, ld1 = x, ld
+    k0 = Wb[0].shape[1]
+    a0 = torch.zeros(B, k0, device=dev, dtype=torch.bfloat16)
+    a0[:, :D1] = z[:, :D1]
+    if cond is not None:
+        a0[:, D1:D1 + cond.shape[1]] = cond
+    h = a0
+    for l in range(4):
+        hn = torch.empty(B, hid, device=dev, dtype=torch.bfloat16)
+        ops.gemm_nt(h, Wb[l], B, hid, h.shape[1], ops.EPI_BIAS_RELU_BF16, hn, bias=bb[l])
+        h = hn
+    t = torch.empty(B, hid, device=dev, dtype=F32)
+    ops.gemm_nt(h, Wb[4], B, hid, hid, ops.EPI_F32, t, bias=bb[4])
+    h = torch.tanh(t).to(torch.bfloat16)
+    n6 = Wb[5].shape[0]
+    o = torch.empty(B, n6, device=dev, dtype=F32)
+    ops.gemm_nt(h, Wb[5], B, n6, hid, ops.EPI_F32, o, bias=bb[5])
+    shift, logit = o[:, 0:2 * D2:2], o[:, 1:2 * D2:2] + 2.0
+    ls = torch.nn.functional.logsigmoid(logit)
+    if not reverse:
+        out = torch.cat((z[:, :D1], (z[:, D1:] + shift) * torch.exp(ls)), 1)
+        return out, ld1 + ls.sum(1)
+    zc = torch.cat((z[:, :D1], z[:, D1:] * torch.exp(-ls) - shift), 1).contiguous()
+    ld_mid = (ld1 - ls.sum(1)).contiguous()
+    xo = torch.empty_like(zc)
+    ld_out = torch.empty(B, device=dev, dtype=F32)
+    ops.affine_rows(zc, Wf, bf, sl, xo, ld_mid, ld_out, B, D, 1.0)
+    return xo, ld_out
+
+
 def flowstep1d(step, input, y_onehot, logdet, reverse):
     from .models.layers import _as_logdet
     B = input.shape[0]
@@ -119,6 +189,9 @@ def flowstep1d(step, input, y_onehot, logdet, reverse):
         ws, bs = _mlp_params(step)
         pctx, idx, token = Fn.prep_for(step, bool(reverse))
         z, ld_out = FlowStep1dFn.apply(input, ld, cond, step, bool(reverse), token, pctx, idx, *ws, *bs)
+    elif not ops.flow1d_supported(step.in_channels, step.condition_features, step.hidden_channels, False):
+        z, ld_out = _flowstep1d_wide(step, input.contiguous(), None if cond is None else cond.contiguous().float(),
+                                     ld.contiguous(), bool(reverse))
     else:
         Wf, sl, PF, _, _ = _consts(step, bool(reverse))
         x = input.contiguous()

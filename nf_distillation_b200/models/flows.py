@@ -122,12 +122,15 @@ class FlowStep(nn.Module):
         if self.is_1d:
             from .. import ops
             training = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
-            if not ops.flow1d_supported(self.in_channels, self.condition_features, self.hidden_channels, training):
+            wide_ok = not training and self.hidden_channels % 64 == 0      # GEMM path of flow1d._flowstep1d_wide
+            if not wide_ok and not ops.flow1d_supported(self.in_channels, self.condition_features,
+                                                        self.hidden_channels, training):
                 raise NotImplementedError(
                     f"the fused 1-D FlowStep keeps the whole coupling MLP in shared memory; hidden_channels="
                     f"{self.hidden_channels} at D={self.in_channels} does not fit "
                     f"({'training: widths up to 48' if training else 'inference: widths up to 88'}). The tabular "
-                    f"configs use 16 / 32; conf/teacher/rich.yaml (256) is not covered yet.")
+                    f"configs use 16 / 32. Frozen steps with a width that is a multiple of 64 (conf/teacher/rich.yaml: "
+                    f"256) run on the tensor-core GEMM path instead; training them is not built.")
         if not self.is_1d:
             if self.condition_features:
                 raise NotImplementedError("y-conditioned 2-D coupling is not built (no shipped image config uses it)")

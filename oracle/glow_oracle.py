@@ -196,15 +196,20 @@ def split2d_reverse(z1: Tensor, sd: SD, pre: str, temperature: float, eps: Optio
 
 
 # ------------------------------------------------------------------------------------------ whole model
-def prior(sd: SD, cfg: dict, batch: int) -> Tuple[Tensor, Tensor]:
-    """Glow.prior with learn_top = y_condition = False (models/flows.py:367-391): prior_h repeated, split."""
+def prior(sd: SD, cfg: dict, batch: int, y_onehot: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
+    """Glow.prior with learn_top = False (models/flows.py:367-391): prior_h repeated, plus the LinearZeros projection
+    of y_onehot when y_condition (models/layers.py:173-187: linear(x) * exp(3 * logs)), split in halves."""
     h = sd["prior_h"]
     h = h.expand(batch, *h.shape[1:])
+    if cfg.get("y_condition", False):
+        yp = torch.nn.functional.linear(y_onehot, sd["project_ycond.linear.weight"], sd["project_ycond.linear.bias"])
+        yp = yp * torch.exp(sd["project_ycond.logs"] * 3.0)
+        h = h + yp.view(batch, h.shape[1], *([1] * (h.dim() - 2)))
     c = h.shape[1] // 2
     return h[:, :c], h[:, c:]
 
 
-def glow_forward(sd: SD, cfg: dict, x: Tensor, noise: Optional[Tensor] = None):
+def glow_forward(sd: SD, cfg: dict, x: Tensor, noise: Optional[Tensor] = None, y_onehot: Optional[Tensor] = None):
     """GlowGetAllOutputs.normal_flow (models/kd_flows.py:121-152): returns (all layer outputs, bpd|nll [B]).
 
     `noise` is the dequantisation noise U(0, 1/256) the reference draws in uniform_binning_correction
@@ -226,18 +231,19 @@ def glow_forward(sd: SD, cfg: dict, x: Tensor, noise: Optional[Tensor] = None):
         if kind == "squeeze":
             z = squeeze2d(z)
         elif kind == "step":
-            z, logdet = flowstep(z, sd, pre, logdet, False, coupling=cfg.get("flow_coupling", "affine"))
+            z, logdet = flowstep(z, sd, pre, logdet, False, y_onehot=y_onehot if cfg.get("y_condition") else None,
+                                 coupling=cfg.get("flow_coupling", "affine"))
         else:
             z, logdet = split2d_forward(z, sd, pre, logdet)
         outs.append(z)
-    mean, logs = prior(sd, cfg, B)
+    mean, logs = prior(sd, cfg, B, y_onehot)
     objective = logdet + gaussian_logp(mean.to(z.dtype), logs.to(z.dtype), z)
     bpd = -objective if is_1d else -objective / (math.log(2.0) * chw)
     return outs, bpd
 
 
 def glow_reverse(sd: SD, cfg: dict, z: Tensor, temperature: float = 0.0,
-                 eps: Optional[Sequence[Tensor]] = None) -> List[Tensor]:
+                 eps: Optional[Sequence[Tensor]] = None, y_onehot: Optional[Tensor] = None) -> List[Tensor]:
     """FlowNetGetAllOutputs.decode (models/kd_flows.py:55-73): all outputs of the inverse pass, last = x.
     `eps` supplies the N(0,1) draws of each Split2d in decode order (None -> zeros)."""
     plan = layer_plan(cfg)
@@ -250,7 +256,8 @@ def glow_reverse(sd: SD, cfg: dict, z: Tensor, temperature: float = 0.0,
         if kind == "squeeze":
             z = unsqueeze2d(z)
         elif kind == "step":
-            z, _ = flowstep(z, sd, pre, dummy, True, coupling=cfg.get("flow_coupling", "affine"))
+            z, _ = flowstep(z, sd, pre, dummy, True, y_onehot=y_onehot if cfg.get("y_condition") else None,
+                            coupling=cfg.get("flow_coupling", "affine"))
         else:
             z = split2d_reverse(z, sd, pre, temperature, None if eps is None else eps[k])
             k += 1
@@ -281,31 +288,34 @@ def kd_loss(student_z: Sequence[Tensor], teacher_z: Sequence[Tensor], s_idx, t_i
 
 def kd_step(student_sd: SD, student_cfg: dict, teacher_sd: SD, teacher_cfg: dict, x: Tensor,
             weights: dict, noise_s: Optional[Tensor] = None, noise_t: Optional[Tensor] = None,
-            latent: Optional[Tensor] = None) -> dict:
+            latent: Optional[Tensor] = None, y_onehot: Optional[Tensor] = None,
+            sample_weights: Optional[Tensor] = None) -> dict:
     """NFModel.forward + loss (pl_module.py:198-320). The student adds dequantisation noise to x in place and the
     teacher then adds its own on top (pl_module.py:215-225 + models/utils.py:38), so the teacher sees
     x + noise_s + noise_t. The perceptual term is L1 between reverse passes at temperature 0.7 from `latent`."""
     is_1d = student_cfg.get("is_1d", False)
     xs = x if (is_1d or noise_s is None) else x + noise_s
-    s_z, s_nll = glow_forward(student_sd, student_cfg, xs)
+    s_z, s_nll = glow_forward(student_sd, student_cfg, xs, y_onehot=y_onehot)
     out = {"nll": s_nll}
     s_idx, t_idx = kd_indices(student_cfg, teacher_cfg)
     if weights.get("kd", 0) > 0:
         xt = xs if (is_1d or noise_t is None) else xs + noise_t
         with torch.no_grad():
-            t_z, _ = glow_forward(teacher_sd, teacher_cfg, xt)
+            t_z, _ = glow_forward(teacher_sd, teacher_cfg, xt, y_onehot=y_onehot)
         out["kd"] = kd_loss(s_z, t_z, s_idx, t_idx)
     else:
         out["kd"] = torch.zeros((), dtype=x.dtype)
     if weights.get("perceptual", 0) > 0:
-        sx = glow_reverse(student_sd, student_cfg, latent, 0.7)[-1]
+        sx = glow_reverse(student_sd, student_cfg, latent, 0.7, y_onehot=y_onehot)[-1]
         with torch.no_grad():
-            tx = glow_reverse(teacher_sd, teacher_cfg, latent, 0.7)[-1]
+            tx = glow_reverse(teacher_sd, teacher_cfg, latent, 0.7, y_onehot=y_onehot)[-1]
         perc = (sx - tx).abs().flatten(1).mean(1)
         out["perceptual"] = torch.where(torch.isnan(perc), torch.zeros_like(perc), perc)
     else:
         out["perceptual"] = torch.zeros((), dtype=x.dtype)
     result = weights.get("nll", 0) * out["nll"] + weights.get("kd", 0) * out["kd"] \
         + weights.get("perceptual", 0) * out["perceptual"]
+    if sample_weights is not None:   # RICH: per-sample weights multiply the combined loss (pl_module.py:311-313)
+        result = result * sample_weights
     return {"nll": out["nll"].mean(), "kd": out["kd"].mean(), "perceptual": out["perceptual"].mean(),
             "result_loss": result.mean(), "student_z": s_z}

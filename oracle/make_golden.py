@@ -55,6 +55,8 @@ def randomise(model, gen, std=0.05):
                 p.add_(torch.randn(p.shape, generator=gen) * std)
             elif ".block.10." in name:  # last Linear of the 1-D coupling MLP: default init is fine but small
                 p.mul_(0.5)
+            elif name.startswith(("project_ycond.linear", "project_class.linear")):   # LinearZeros of y_condition
+                p.copy_(torch.randn(p.shape, generator=gen) * std)
 
 
 def make_x(cfg, B, gen):
@@ -116,7 +118,7 @@ def forward_fixture(name, cfg, B, seed):
     print(name, "layers", len(outs), "bpd", bpd.numpy()[:2])
 
 
-def kd_fixture(name, s_cfg, t_cfg, B, seed, weights):
+def kd_fixture(name, s_cfg, t_cfg, B, seed, weights, sample_weights=False):
     create_glow_model, FlowStep, SqueezeLayer, Split2d = import_reference()
     torch.manual_seed(seed)
     gen = torch.Generator().manual_seed(seed + 1)
@@ -127,22 +129,26 @@ def kd_fixture(name, s_cfg, t_cfg, B, seed, weights):
     s_idx, t_idx = kd_indices_reference(student, teacher, is_1d, SqueezeLayer)
     x0 = make_x(s_cfg, B, gen)
     x = x0.clone()
+    cond = None
+    if s_cfg["y_condition"]:   # RICH: batch = [x, cond, weights] (pl_module.py:212-213), cond one-hot over y_classes
+        cond = torch.nn.functional.one_hot(torch.randint(0, s_cfg["y_classes"], (B,), generator=gen),
+                                           s_cfg["y_classes"]).float()
     torch.manual_seed(seed + 2)
     # --- pl_module.py:198-255 (forward), restated without Lightning
-    s_z, s_nll, _ = student(x, None)
+    s_z, s_nll, _ = student(x, cond)
     noise_s = (x - x0).clone()
     with torch.no_grad():
-        t_z, _, _ = teacher(x, None)
+        t_z, _, _ = teacher(x, cond)
     noise_t = (x - x0) - noise_s
     data = {"x": x0.numpy(), "noise_s": noise_s.numpy(), "noise_t": noise_t.numpy(),
             "s_idx": np.array(s_idx), "t_idx": np.array(t_idx)}
     perceptual = torch.tensor(0.0)
     if weights["perceptual"] > 0:
-        mean, logs = student.prior(x, y_onehot=None)
-        latent = torch.randn(mean.shape, generator=gen) * torch.exp(logs) + mean
-        sx = student(z=latent, temperature=0.7, reverse=True, y_onehot=None)[-1]
+        mean, logs = student.prior(x, y_onehot=cond)
+        latent = (torch.randn(mean.shape, generator=gen) * torch.exp(logs) + mean).detach()
+        sx = student(z=latent, temperature=0.7, reverse=True, y_onehot=cond)[-1]
         with torch.no_grad():
-            tx = teacher(z=latent, temperature=0.7, reverse=True, y_onehot=None)[-1]
+            tx = teacher(z=latent, temperature=0.7, reverse=True, y_onehot=cond)[-1]
         data["latent"] = latent.numpy()
         data["student_x"] = sx.detach().numpy()
         perceptual = torch.nn.functional.l1_loss(sx, tx, reduction="none")
@@ -155,6 +161,12 @@ def kd_fixture(name, s_cfg, t_cfg, B, seed, weights):
         kd = part if kd is None else kd + part
     kd = kd / len(s_idx)
     result = weights["nll"] * s_nll + weights["kd"] * kd + weights["perceptual"] * perceptual
+    if cond is not None:
+        data["cond"] = cond.numpy()
+    if sample_weights:          # pl_module.py:311-313
+        sw = torch.rand(B, generator=gen) + 0.5
+        data["sample_w"] = sw.numpy()
+        result = result * sw
     loss = result.mean()
     loss.backward()
     data.update(nll=s_nll.mean().detach().numpy(), kd=kd.mean().detach().numpy(),
@@ -175,7 +187,7 @@ def kd_fixture(name, s_cfg, t_cfg, B, seed, weights):
     print(name, "taps", s_idx, t_idx, "loss", float(loss))
 
 
-def main():
+def main(only=None):
     # 2-D Glow, CIFAR-shaped, small K / hidden so the fixture stays small (reference default config otherwise)
     forward_fixture("glow2d_cifar_k2_h64", base_cfg(K=2, L=3, hidden_channels=64), B=4, seed=42)
     # 2-D Glow, 16x16, L=2 (exercises one Split2d), odd batch
@@ -191,6 +203,12 @@ def main():
     kd_fixture("kd1d_d63_t5_s3", base_cfg(image_shape=[63], K=3, L=1, hidden_channels=16, is_1d=True, y_classes=0),
                base_cfg(image_shape=[63], K=5, L=1, hidden_channels=32, is_1d=True, y_classes=0), B=64, seed=23,
                weights={"nll": 0.85, "kd": 0.05, "perceptual": 0.1})
+    # RICH-shaped (conf/{teacher,student,training}/rich.yaml): D=5, y-conditioned on 3 classes, wide frozen teacher,
+    # per-sample loss weights; small K / teacher width 128 so the fixture stays small
+    rich = dict(image_shape=[5], is_1d=True, y_classes=3, y_condition=True)
+    kd_fixture("kd1d_rich_t2_s2", base_cfg(K=2, L=1, hidden_channels=32, **rich),
+               base_cfg(K=1, L=2, hidden_channels=128, **rich), B=96, seed=31,
+               weights={"nll": 0.85, "kd": 0.075, "perceptual": 0.075}, sample_weights=True)
 
 
 if __name__ == "__main__":

@@ -190,3 +190,69 @@ def test_conditioned_1d_step_matches_oracle(D, Cc, hid, B):
         if ref is None:
             continue
         assert p.grad is not None and rel(p.grad, ref) < 1e-4, n_
+
+
+@pytest.mark.parametrize("D,Cc,hid,B", [(5, 3, 256, 300), (63, 0, 128, 1000)])
+def test_wide_frozen_1d_step_runs_on_the_gemm_path(D, Cc, hid, B):
+    """conf/teacher/rich.yaml shape (D=5, 3 condition classes, hidden 256): the coupling MLP does not fit the fused
+    kernel's shared memory, so a frozen step runs its six Linear layers as tcgen05 GEMMs (bf16 operands: 2e-2 of the
+    output range, 1e-2 on the per-sample log-det); forward and inverse against the oracle, and x -> z -> x."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from oracle import glow_oracle as O
+    from nf_distillation_b200.models.flows import FlowStep
+    torch.manual_seed(D + hid)
+    step = FlowStep(D, hid, 1.0, "invconv", "affine", True, is_1d=True, condition_features=Cc)
+    with torch.no_grad():
+        for p in step.parameters():
+            if p.abs().max() == 0:
+                p.normal_(0, 0.05)
+    step.actnorm.inited = True
+    sd = {"s." + k: v.clone() for k, v in step.state_dict().items()}
+    x = torch.randn(B, D)
+    cond = torch.nn.functional.one_hot(torch.randint(0, Cc, (B,)), Cc).float() if Cc else None
+    zo, ldo = O.flowstep(x, sd, "s.", torch.zeros(B), False, y_onehot=cond)
+    xr, ldr = O.flowstep(zo, sd, "s.", torch.zeros(B), True, y_onehot=cond)
+    step = step.to(dev).eval()
+    cg = None if cond is None else cond.to(dev)
+    with torch.no_grad():
+        z, ld = step(x.to(dev), y_onehot=cg, logdet=torch.zeros(B, device=dev), reverse=False)
+        back, ldb = step(z, y_onehot=cg, logdet=ld, reverse=True)
+    assert rel(z, zo) < 2e-2 and (ld.cpu() - ldo).abs().max() < 1e-2 * (ldo.abs().max() + 1)
+    assert rel(back, x) < 1e-4 and ldb.abs().max().item() < 1e-4      # exact inverse of its own forward
+    with pytest.raises(NotImplementedError):
+        step.train()
+        step(x.to(dev).requires_grad_(True), y_onehot=cg, logdet=torch.zeros(B, device=dev), reverse=False)
+
+
+def test_rich_shaped_kd_step_golden(monkeypatch):
+    """conf/{teacher,student,training}/rich.yaml shape, recorded from the unmodified reference (oracle/make_golden.py,
+    fixture kd1d_rich_t2_s2): D = 5, y-conditioned on 3 classes (coupling MLPs see [z1 | y], the prior gets the
+    LinearZeros projection of y), batch = [x, cond, weights], per-sample loss weights, frozen WIDE teacher (hidden 128:
+    tensor-core GEMM path, bf16 operands) and a narrow student (fused fp32 kernels), perceptual term through both
+    inverse passes. nll is all-fp32 (1e-5); kd / perceptual / loss and the gradients inherit the teacher's bf16 MLP
+    (2e-2 of the largest entry)."""
+    import nf_distillation_b200.pl_module as PM
+    d = load("kd1d_rich_t2_s2")
+    s_cfg, t_cfg = cfg_of(d, "s_cfg"), cfg_of(d, "t_cfg")
+    w = json.loads(str(d["weights"]))
+    cfg = nf_config(s_cfg, t_cfg, w, "rich")
+    cfg["data"]["drop_weights"] = False
+    m = PM.NFModel(cfg)
+    m.student.load_state_dict(state_dict_of(d, "s_sd."))
+    m.teacher.load_state_dict(state_dict_of(d, "t_sd."))
+    m = m.to(dev)
+    assert m.student_kd_indices == list(d["s_idx"]) and m.teacher_kd_indices == list(d["t_idx"])
+    lat = t(d["latent"]).to(dev)
+    monkeypatch.setattr(PM, "gaussian_sample", lambda mean, logs, T: lat)
+    out = m.training_step([t(d["x"]).to(dev), t(d["cond"]).to(dev), t(d["sample_w"]).to(dev)], 0)
+    assert abs(out["nll"].item() - float(d["nll"])) < 1e-5 * abs(float(d["nll"]))
+    for k_ in ("kd", "perceptual", "loss"):
+        assert abs(out[k_].item() - float(d[k_])) < 2e-2 * abs(float(d[k_])) + 1e-6, (k_, out[k_].item(), float(d[k_]))
+    out["loss"].backward()
+    assert all(p.grad is None for p in m.teacher.parameters())
+    for n_, p in m.student.named_parameters():
+        ref = t(d["grad." + n_])
+        if ref.abs().max() == 0:
+            continue
+        assert p.grad is not None and rel(p.grad, ref) < 2e-2, n_

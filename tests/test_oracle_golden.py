@@ -65,7 +65,7 @@ def test_step_logdets(name):
         inp = out
 
 
-@pytest.mark.parametrize("name", ["kd2d_cifar_t4_s2_h64", "kd1d_d63_t5_s3"])
+@pytest.mark.parametrize("name", ["kd2d_cifar_t4_s2_h64", "kd1d_d63_t5_s3", "kd1d_rich_t2_s2"])
 def test_kd_step_matches_reference(name):
     import json
     d = load(name)
@@ -78,7 +78,10 @@ def test_kd_step_matches_reference(name):
         if v.dtype.is_floating_point:
             v.requires_grad_(True)
     latent = t(d["latent"]) if "latent" in d else None
-    out = O.kd_step(s_sd, s_cfg, t_sd, t_cfg, t(d["x"]), weights, t(d["noise_s"]), t(d["noise_t"]), latent)
+    cond = t(d["cond"]) if "cond" in d else None             # RICH-shaped fixture: [x, cond, weights] batches
+    sw = t(d["sample_w"]) if "sample_w" in d else None
+    out = O.kd_step(s_sd, s_cfg, t_sd, t_cfg, t(d["x"]), weights, t(d["noise_s"]), t(d["noise_t"]), latent,
+                    y_onehot=cond, sample_weights=sw)
     for key, ref in (("nll", "nll"), ("kd", "kd"), ("perceptual", "perceptual"), ("result_loss", "loss")):
         close(out[key].detach(), t(d[ref]), rtol=1e-5)
     for i in s_idx:

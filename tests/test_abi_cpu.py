@@ -101,3 +101,48 @@ def test_kd_indices_match_reference_rule():
     m1 = NFModel(cfg1)
     assert (m1.student_kd_indices, m1.teacher_kd_indices) == ([1, 2], [3, 4])
     assert isinstance(m.configure_optimizers(), torch.optim.Adam)
+
+
+def test_checkpoints_in_both_reference_formats_load(tmp_path):
+    """pl_module.py:112-129: a raw state_dict, or a Lightning checkpoint whose keys carry the `student.` prefix (other
+    entries, e.g. `teacher.*`, are ignored), load into the drop-in module unchanged."""
+    import torch
+    from nf_distillation_b200.pl_module import NFModel
+    from nf_distillation_b200.models import create_glow_model
+    from nf_distillation_b200.train import glow_cfg, kd_config
+    cfg = glow_cfg((32, 32, 3), 2, 2, 64)
+    torch.manual_seed(1)
+    src = create_glow_model(cfg)
+    with torch.no_grad():
+        for p in src.parameters():
+            p.add_(torch.randn_like(p) * 0.01)
+    raw, lightning = tmp_path / "raw.ckpt", tmp_path / "pl.ckpt"
+    torch.save(src.state_dict(), raw)
+    torch.save({"epoch": 3, "state_dict": {**{"student." + k: v for k, v in src.state_dict().items()},
+                                           "teacher.flow.layers.1.actnorm.bias": torch.zeros(1)}}, lightning)
+    for path in (raw, lightning):
+        s_cfg = dict(cfg, checkpoint=str(path))
+        m = NFModel(kd_config(s_cfg, glow_cfg((32, 32, 3), 2, 2, 64), kd=0.0))   # kd = perceptual = 0: no teacher
+        assert m.teacher is None
+        got = m.student.state_dict()
+        assert got.keys() == src.state_dict().keys()
+        assert all(torch.equal(got[k].cpu(), v) for k, v in src.state_dict().items())
+
+
+def test_pre_and_postprocess_match_the_reference_helpers():
+    import torch
+    from nf_distillation_b200 import data_utils as U
+    g = torch.Generator().manual_seed(0)
+    img = torch.randint(0, 256, (4, 3, 8, 8), generator=g).float() / 255.0
+    x = U.preprocess(img)
+    assert x.min() >= -0.5 and x.max() < 0.5
+    assert torch.allclose(x, torch.round(img * 255) / 256 - 0.5, atol=1e-6)
+    back = U.postprocess(x.clone())
+    # (the reference scales by 1/256 on the way in and by 255 on the way out, so the round trip truncates: k*255/256)
+    assert back.dtype == torch.uint8 and torch.equal(back, ((x + 0.5) * 255).byte())
+    if os.path.isdir("/root/reference/data/src"):   # live reference in the build container
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("ref_data_utils", "/root/reference/data/src/utils.py")
+        R = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(R)
+        assert torch.equal(R.preprocess(img), x) and torch.equal(R.postprocess(x.clone()), back)

@@ -32,6 +32,10 @@ WORKLOADS = {
     # BASELINE configs[4]: Glow L=4 K=32 on CelebA-shaped 64x64x3, KD training (level-0 GEMM shape of batch 256 equals
     # CIFAR at batch 1024: 262 144 pixels)
     "glow_celeba_kd_t32_s8": dict(image=(64, 64, 3), L=4, hidden=512, tK=32, sK=8, batch=256),
+    # the reference's own CelebA pair (conf/teacher/celeba.yaml, conf/student/celeba.yaml): L=3, teacher K=32 hidden
+    # 512, student K=16 hidden 256
+    "glow_celeba_ref_kd_t32h512_s16h256": dict(image=(64, 64, 3), L=3, hidden=512, s_hidden=256, tK=32, sK=16,
+                                               batch=256),
     # BASELINE configs[2]: Glow L=3 K=32 hidden 512, forward + inverse + log-det (no gradients); metric = samples/s
     # through one x -> z (+ per-sample log-det / bpd) pass followed by one z -> x sampling pass
     "glow_cifar_fwd_inv_k32": dict(image=(32, 32, 3), L=3, hidden=512, tK=32, sK=32, batch=1024, mode="fwd_inv"),
@@ -250,7 +254,7 @@ def cpu_kd_step_fn(wl, batch, seed=42):
         s_cfg = glow_cfg(wl["image"], wl["sK"], wl["L"], wl.get("s_hidden", wl["hidden"]), is_1d=True, y_classes=0)
         t_cfg = glow_cfg(wl["image"], wl["tK"], wl["L"], wl["hidden"], is_1d=True, y_classes=0)
     else:
-        s_cfg = glow_cfg(wl["image"], wl["sK"], wl["L"], wl["hidden"])
+        s_cfg = glow_cfg(wl["image"], wl["sK"], wl["L"], wl.get("s_hidden", wl["hidden"]))
         t_cfg = glow_cfg(wl["image"], wl["tK"], wl["L"], wl["hidden"])
     t_model, s_model = create_glow_model(t_cfg), create_glow_model(s_cfg)   # parameter containers only (CPU)
     randomise_zero_params(s_model, seed + 1)
@@ -383,7 +387,7 @@ def main():
         shape = (B, D)
     else:
         H, W, C = wl["image"]
-        config = kd_config(glow_cfg(wl["image"], wl["sK"], wl["L"], wl["hidden"]),
+        config = kd_config(glow_cfg(wl["image"], wl["sK"], wl["L"], wl.get("s_hidden", wl["hidden"])),
                            glow_cfg(wl["image"], wl["tK"], wl["L"], wl["hidden"]))
         shape = (B, C, H, W)
     trainer = KDTrainer(config, shape, device, use_graphs=not args.no_graphs)

@@ -43,7 +43,18 @@ struct PcArgs {
   float* hsave;         // optional [M, C] fp32: conv output (shift, logit pairs) kept for the backward pass
   float* ld;            // optional [B] log-det, accumulated
   int reverse;
+  // band mode (maps larger than a tile, W * 8 == NPIX): a tile is 8 image rows = rb output rows + one halo row above and
+  // below; nb bands per image. banded == 0: tiles are NPIX consecutive pixels = whole images.
+  int banded, nb, rb;
 };
+
+// First pixel (global index, may be negative for the halo above the very first image) of tile t.
+template <int NPIX>
+__device__ __forceinline__ long long pc_tile_pix0(const PcArgs& g, int t) {
+  if (!g.banded) return static_cast<long long>(t) * NPIX;
+  const int img = t / g.nb, band = t - img * g.nb;
+  return (static_cast<long long>(img) << g.lgHW) + static_cast<long long>(band * g.rb - 1) * g.W;
+}
 
 template <int C>
 struct PcSmem {
@@ -80,7 +91,7 @@ pconv_coupling_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
   float* bias_s = reinterpret_cast<float*>(smem + Sm::off_bias);
   if (threadIdx.x < C) bias_s[threadIdx.x] = g.bias3[threadIdx.x];
 
-  const int num_tiles = static_cast<int>((g.M + NPIX - 1) / NPIX);
+  const int num_tiles = g.banded ? g.B * g.nb : static_cast<int>((g.M + NPIX - 1) / NPIX);
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmW);
     tma_prefetch_desc(&tmH);
@@ -105,7 +116,7 @@ pconv_coupling_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
           mbar_expect_tx(&full[s], Sm::stage_bytes);
 #pragma unroll
           for (int mb = 0; mb < MB; ++mb) tma_load_2d(sa + mb * 128 * 128, &tmW, &full[s], kb * PC_BK, mb * 128);
-          tma_load_2d(sa + Sm::a_bytes, &tmH, &full[s], kb * PC_BK, t * NPIX);
+          tma_load_2d(sa + Sm::a_bytes, &tmH, &full[s], kb * PC_BK, static_cast<int>(pc_tile_pix0<NPIX>(g, t)));
           if (++s == PC_STAGES) { s = 0; ph ^= 1; }
         }
       }
@@ -150,18 +161,32 @@ pconv_coupling_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
     const int HW = g.H * g.W, HWm = HW - 1, Wm = g.W - 1;
     constexpr int ITEMS = J * NPIX / 256;       // (pixel, j) items per thread: item i = et + 256 k, pixel fastest
     static_assert(J * NPIX % 512 == 0, "each half's items must divide over the 256 epilogue threads");
+    // output pixels of one half: HALF consecutive pixels, or in band mode rb/2 image rows after the halo row
+    const int OH = g.banded ? (g.rb >> 1) * g.W : HALF;
     int it = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
       const int acc = it & 1;
-      const long long tile_base = static_cast<long long>(t) * NPIX;
+      const long long tile_base = pc_tile_pix0<NPIX>(g, t);
+      const int row0 = g.banded ? (t % g.nb) * g.rb - 1 : 0;                   // band mode: image row of tile row 0
+      const int row_end = g.banded ? min(g.H, row0 + 1 + g.rb) : 0;            //            first image row not owned
+      // item ih of half hf -> (channel pair j, tile-local pixel pl, global pixel m); live = it exists and is ours
+      auto decode = [&](int hf, int ih, int& j, int& pl, long long& m) -> bool {
+        j = ih / OH;
+        pl = (g.banded ? g.W : 0) + hf * OH + (ih - j * OH);
+        m = tile_base + pl;
+        if (j >= J) return false;
+        if (!g.banded) return m < g.M;
+        return row0 + (pl >> g.lgW) < row_end;   // (rows past the image end would alias the next image's first rows)
+      };
       float z2v[ITEMS];
 #pragma unroll
       for (int k = 0; k < ITEMS; ++k) {   // same (half, j, pixel) mapping as the gather below
-        const int hf = k / (ITEMS / 2), ih = et + 256 * (k - hf * (ITEMS / 2));
-        const int j = ih / HALF, pl = hf * HALF + (ih - j * HALF);
-        const long long m = tile_base + pl;
+        const int hf = k / (ITEMS / 2);
+        int j, pl;
+        long long m;
+        const bool live = decode(hf, et + 256 * (k - hf * (ITEMS / 2)), j, pl, m);
         const int b = static_cast<int>(m >> g.lgHW), rem = static_cast<int>(m) & HWm;
-        z2v[k] = m < g.M ? g.y[((static_cast<long long>(b) * C + J + j) << g.lgHW) + rem] : 0.f;
+        z2v[k] = live ? g.y[((static_cast<long long>(b) * C + J + j) << g.lgHW) + rem] : 0.f;
       }
       mbar_wait(&tmem_full[acc], (it >> 1) & 1);
       tc_fence_after();
@@ -208,12 +233,12 @@ pconv_coupling_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
 #pragma unroll
         for (int kk = 0; kk < ITEMS / 2; ++kk) {
           const int k = hf * (ITEMS / 2) + kk;
-          const int ih = et + 256 * kk;                     // item inside this half: (j, pixel), pixel fastest
-          const int j = ih / HALF, pl = hf * HALF + (ih - j * HALF);
-          const long long m = tile_base + pl;
+          int j, pl;                                        // item inside this half: (j, pixel), pixel fastest
+          long long m;
+          const bool live = decode(hf, et + 256 * kk, j, pl, m);
           const int b = static_cast<int>(m >> g.lgHW);
           float lsum = 0.f;
-          if (m < g.M) {
+          if (live) {
             const int rem = static_cast<int>(m) & HWm;
             const int yy = rem >> g.lgW, xx = rem & Wm;
             float sh = bias_s[2 * j], lg = bias_s[2 * j + 1];
@@ -249,7 +274,7 @@ pconv_coupling_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
               const float v = __shfl_xor_sync(0xffffffffu, lsum, o);
               if (o < seg) lsum += v;
             }
-            if ((lane & (seg - 1)) == 0 && m < g.M) atomicAdd(g.ld + b, lsum);
+            if ((lane & (seg - 1)) == 0 && live) atomicAdd(g.ld + b, lsum);
           }
         }
       }
@@ -297,7 +322,7 @@ static int pc_launch(const void* h2, const void* B3, int K3p, const PcArgs& g, i
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int tiles = static_cast<int>((g.M + Cfg::NPIX - 1) / Cfg::NPIX);
+  const int tiles = g.banded ? g.B * g.nb : static_cast<int>((g.M + Cfg::NPIX - 1) / Cfg::NPIX);
   pconv_coupling_kernel<C><<<tiles < sms ? tiles : sms, PC_THREADS, PcSmem<C>::total, st>>>(tmW, tmH, g);
   return cudaGetLastError() == cudaSuccess ? NFK_OK : NFK_ERR_LAUNCH;
 }
@@ -311,8 +336,13 @@ extern "C" int nfk_pconv_coupling_supported(int C, int H, int W, int hid) {
   const int HW = H * W;
   if (HW < 4 || (HW & (HW - 1)) || (W & (W - 1))) return 0;
   // whole images per tile half: no halo between tiles (C = 12 may also split one image over the two halves)
-  if (C == 12)   // one image split over the two halves needs its halo (W + 1 pixels) inside the staging window
-    return HW <= PcCfg<12>::NPIX / 2 || (HW == PcCfg<12>::NPIX && W + 1 <= PcCfg<12>::WIN - PcCfg<12>::NPIX / 2);
+  if (C == 12) {
+    // whole images per half; or one image split over the two halves with its halo (W + 1 pixels) inside the staging
+    // window; or band mode: 8 image rows per tile (6 output rows + a halo row either side), any H
+    if (HW <= PcCfg<12>::NPIX / 2) return 1;
+    if (HW == PcCfg<12>::NPIX && W + 1 <= PcCfg<12>::WIN - PcCfg<12>::NPIX / 2) return 1;
+    return W * 8 == PcCfg<12>::NPIX && 3 * W + W + 1 <= PcCfg<12>::WIN + 1;
+  }
   if (C == 24) return HW <= PcCfg<24>::NPIX / 2 && HW >= 4;
   if (C == 48) return HW <= PcCfg<48>::NPIX / 2 && HW >= 4;
   return 0;
@@ -331,6 +361,11 @@ extern "C" int nfk_pconv_coupling_fwd(const void* h2, const void* B3, int K3p, c
   g.lgW = 0; while ((1 << g.lgW) < W) ++g.lgW;
   g.lgHW = 0; while ((1 << g.lgHW) < H * W) ++g.lgHW;
   g.bias3 = bias3; g.y = y; g.hsave = hsave; g.ld = ld; g.reverse = reverse;
+  if (C == 12 && H * W > PcCfg<12>::NPIX / 2 && !(H * W == PcCfg<12>::NPIX && W + 1 <= 32)) {
+    g.banded = 1;
+    g.rb = PcCfg<12>::NPIX / W - 2;          // 6 output rows per 8-row tile
+    g.nb = (H + g.rb - 1) / g.rb;
+  }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (C == 12) return pc_launch<12>(h2, B3, K3p, g, hid, st);
   if (C == 24) return pc_launch<24>(h2, B3, K3p, g, hid, st);

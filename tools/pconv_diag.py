@@ -57,3 +57,7 @@ if __name__ == "__main__":
     run(1024, 48, 4, 4)
     run(1021, 48, 4, 4, reverse=True)
     run(9, 12, 8, 8)
+    run(3, 12, 32, 32)
+    run(5, 12, 8, 32)
+    run(256, 12, 32, 32)
+    run(255, 12, 32, 32, reverse=True)

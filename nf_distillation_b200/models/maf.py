@@ -100,7 +100,8 @@ class _MadeFn(torch.autograd.Function):
 
 
 class MADE(nn.Module):
-    """One masked autoregressive layer: forward x -> u with logdet = -sum(alpha); reverse is the D-pass inverse."""
+    """One masked autoregressive layer: forward x -> u with logdet = -sum(alpha); reverse is the sequential inverse
+    (one launch, activations resident in shared memory: csrc/maf_inverse.cu)."""
 
     def __init__(self, num_inputs: int, hidden_features: int, flip: bool):
         super().__init__()
@@ -120,6 +121,25 @@ class MADE(nn.Module):
         self._ranges = _kb_ranges(deg, deg, self.bn)
         self._ranges_t = _kb_ranges_t(deg, deg, self.bn)
         self._cache = None
+        self._job_cache = None
+        self.resident_inverse = True     # False: the D-pass GEMM inverse (kept as the cross-check in the tests)
+        self.resident_mtiles = 0         # 16-sample tiles per warp in the resident inverse (0 = chosen by the library)
+
+    def _inverse_jobs(self, dev):
+        """Job table of the resident inverse (ops.made_inverse_jobs) on `dev`, from cnt[d] = number of hidden units
+        with degree <= d (d = 0..D); None when the degrees are not sorted ascending (the resident inverse walks the
+        units in degree order)."""
+        key = (self.deg1.data_ptr(), self.deg1._version, self.deg2.data_ptr(), self.deg2._version, str(dev))
+        if self._job_cache is None or self._job_cache[0] != key:
+            d1, d2 = self.deg1.detach().cpu().long(), self.deg2.detach().cpu().long()
+            ok = bool((d1[1:] >= d1[:-1]).all() and (d2[1:] >= d2[:-1]).all() and d1.min() >= 1 and d2.min() >= 1)
+            jobs = None
+            if ok:
+                edges = torch.arange(self.D + 1)
+                cnt1, cnt2 = ((d[None, :] <= edges[:, None]).sum(1) for d in (d1, d2))
+                jobs = ops.made_inverse_jobs(cnt1, cnt2, self.D).to(dev)
+            self._job_cache = (key, jobs)
+        return self._job_cache[1]
 
     def _params(self):
         return (self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias, self.fc3.weight, self.fc3.bias)
@@ -214,9 +234,19 @@ class MADE(nn.Module):
             return u, (ld_out if want else None)
         if torch.is_grad_enabled() and input.requires_grad:
             raise NotImplementedError("gradients through the sequential MADE inverse are not built")
-        # sequential inverse: D passes, activations stay on the device, one column of x fixed per pass
         u_in = input.contiguous()
         ops_ = self._cached_operands()
+        jobs = self._inverse_jobs(u_in.device)
+        if jobs is not None and self.resident_inverse and ops.made_inverse_resident_supported(self.D, self.H, self.Dp):
+            # ONE launch: every hidden unit finalised once, in degree order, activations resident in shared memory
+            x = torch.empty_like(u_in)
+            ld_out = torch.empty(Bn, device=x.device, dtype=F32) if want else None
+            ops.made_inverse_resident(u_in, ops_[0], ops_[2], ops_[4], params[1].detach(), params[3].detach(),
+                                      ops_[6], jobs, x, ld.contiguous() if want else None, ld_out, Bn,
+                                      self.D, self.H, self.Dp, self.flip, self.resident_mtiles)
+            return x, ld_out
+        # fallback (unsorted degrees / shapes the resident kernel does not take): D passes of the three GEMMs,
+        # activations in HBM / L2, one column of x fixed per pass
         x = torch.zeros_like(u_in)
         xb = torch.zeros(Bn, self.Dp, device=x.device, dtype=BF16)
         ld_out = torch.empty(Bn, device=x.device, dtype=F32)

@@ -338,6 +338,32 @@ def made_inv_update(x, xb, Dp, u_in, out, N3p, ld_in, ld_out, B, D, i, flip, las
                                   int(flip), int(last), _st()), "nfk_made_inv_update")
 
 
+def made_inverse_resident_supported(D, H, Dp) -> bool:
+    return bool(LIB.nfk_made_inverse_resident_supported(D, H, Dp))
+
+
+def made_inverse_jobs(cnt1, cnt2, D):
+    """Host-side job table of the resident inverse from the degree counts (CPU int32 tensors [D+1]) -> [njobs, 4]."""
+    import torch
+    cnt1 = cnt1.to(torch.int32).contiguous().cpu()
+    cnt2 = cnt2.to(torch.int32).contiguous().cpu()
+    n = LIB.nfk_made_inverse_jobs(cnt1.data_ptr(), cnt2.data_ptr(), D, None, 0)
+    if n <= 0:
+        check(n if n < 0 else -1, "nfk_made_inverse_jobs")
+    jobs = torch.empty(n, 4, dtype=torch.int32)
+    check(0 if LIB.nfk_made_inverse_jobs(cnt1.data_ptr(), cnt2.data_ptr(), D, jobs.data_ptr(), n) == n else -1,
+          "nfk_made_inverse_jobs")
+    return jobs
+
+
+def made_inverse_resident(u_in, B1, B2, B3, b1, b2, b3, jobs, x, ld_in, ld_out, B, D, H, Dp, flip, mtiles=0):
+    """The whole sequential inverse of one MADE layer in one launch (activations resident in shared memory)."""
+    _count()
+    check(LIB.nfk_made_inverse_resident(_p(u_in), _p(B1), _p(B2), _p(B3), _p(b1), _p(b2), _p(b3), _p(jobs),
+                                        jobs.shape[0], _p(x), _p(ld_in), _p(ld_out), B, D, H, Dp, int(flip),
+                                        int(mtiles), _st()), "nfk_made_inverse_resident")
+
+
 def cnet_fused_supported(hid, K1p) -> bool:
     return hid == 512 and K1p % 64 == 0 and 64 <= K1p <= 512
 

@@ -146,3 +146,53 @@ def test_pre_and_postprocess_match_the_reference_helpers():
         R = importlib.util.module_from_spec(spec)
         spec.loader.exec_module(R)
         assert torch.equal(R.preprocess(img), x) and torch.equal(R.postprocess(x.clone()), back)
+
+
+def test_resident_inverse_job_table_reproduces_the_sequential_inverse():
+    """nfk_made_inverse_jobs is host code: replay its job stream in fp32 torch (each job = one 8/16-unit tile of a
+    hidden layer over the k-chunks it names, or the (mu_d, alpha_d) row pair) and compare with the paper
+    restatement's D-pass inverse — the schedule the CUDA kernel executes finalises every unit exactly when its
+    inputs are final, including degrees that own no unit (D > H) and tiles straddling two degrees."""
+    import torch
+    from nf_distillation_b200 import ops
+    from nf_distillation_b200.models.maf import hidden_degrees
+    from oracle import maf_oracle as MO
+    for D, H in [(6, 512), (63, 512), (63, 192), (1, 64), (2, 64), (100, 64), (17, 128)]:
+        torch.manual_seed(D)
+        deg = hidden_degrees(D, H)
+        pre = "l."
+        sd = {pre + "deg1": deg, pre + "deg2": deg.clone(),
+              pre + "fc1.weight": torch.randn(H, D) * 0.1, pre + "fc1.bias": torch.randn(H) * 0.1,
+              pre + "fc2.weight": torch.randn(H, H) * 0.05, pre + "fc2.bias": torch.randn(H) * 0.1,
+              pre + "fc3.weight": torch.randn(2 * D, H) * 0.02, pre + "fc3.bias": torch.randn(2 * D) * 0.1}
+        m1, m2, m3 = MO.masks(D, deg.long(), deg.long())
+        W1, W2, W3 = sd[pre + "fc1.weight"] * m1, sd[pre + "fc2.weight"] * m2, sd[pre + "fc3.weight"] * m3
+        Dp = (D + 63) // 64 * 64
+        W1p = torch.zeros(H, Dp)
+        W1p[:, :D] = W1
+        edges = torch.arange(D + 1)
+        cnt = (deg.long()[None, :] <= edges[:, None]).sum(1)
+        jobs = ops.made_inverse_jobs(cnt, cnt, D)
+        assert jobs.shape[1] == 4 and (jobs[:, 0] == 2).sum().item() == D
+        u = torch.randn(19, D)
+        uf = u.flip(1)
+        xb, h1, h2 = torch.zeros(19, Dp), torch.zeros(19, H), torch.zeros(19, H)
+        x, ld = torch.zeros(19, D), torch.zeros(19)
+        for phase, row0, kch, two in jobs.tolist():
+            k = kch * 16
+            if phase == 0:
+                o = slice(row0, row0 + (16 if two else 8))
+                h1[:, o] = torch.relu(xb[:, :k] @ W1p[o, :k].T + sd[pre + "fc1.bias"][o])
+            elif phase == 1:
+                o = slice(row0, row0 + (16 if two else 8))
+                h2[:, o] = torch.relu(h1[:, :k] @ W2[o, :k].T + sd[pre + "fc2.bias"][o])
+            else:
+                d = row0
+                mu = h2[:, :k] @ W3[d, :k] + sd[pre + "fc3.bias"][d]
+                al = h2[:, :k] @ W3[D + d, :k] + sd[pre + "fc3.bias"][D + d]
+                x[:, d] = uf[:, d] * torch.exp(al) + mu
+                xb[:, d] = x[:, d]
+                ld += al
+        x_o, a_o = MO.made_inverse(u, sd, pre, D)
+        assert (x - x_o).abs().max().item() < 1e-5 * (x_o.abs().max().item() + 1), (D, H)
+        assert (ld - a_o).abs().max().item() < 1e-5 * (a_o.abs().max().item() + 1), (D, H)

@@ -2,8 +2,10 @@
 checker is this repo's own plain-PyTorch fp32 restatement of the paper (oracle/maf_oracle.py).
 
 Tolerances (masked linears run on bf16 tensor-core tiles with fp32 accumulation; the affine transform and log-det
-are fp32): outputs / nll 1e-3 relative to max, inverse round trip 1e-5 (the inverse reuses the same network, so it is
-consistent to fp32), input gradient 1e-2, parameter gradients: cosine similarity >= 0.999 and 0.1 of max|grad|
+are fp32): outputs / nll 1e-3 relative to max, inverse round trip 1e-4 (the inverse evaluates the same bf16 network; the resident
+kernel sums each pre-activation in a different order than the forward GEMM, so a hidden unit sitting on a bf16
+rounding boundary may round the other way — the D-pass GEMM inverse, bit-consistent with the forward, holds 1e-5 and
+the two inverses agree to 1e-4), input gradient 1e-2, parameter gradients: cosine similarity >= 0.999 and 0.1 of max|grad|
 (0.99 / 0.2 for the 64-sample case, where bf16 rounding of the few summed terms dominates)."""
 import os
 import sys
@@ -39,11 +41,23 @@ def test_maf_forward_inverse_backward_vs_paper_restatement(D, H, K, B):
             assert rel(a, b) < 1e-3
         back = m(z=outs[-1], reverse=True)
         # x -> z -> x; fp32 cancellation in u*e^alpha + mu grows with the largest |mu| among B*D entries
-        assert len(back) == K and rel(back[-1], x) < (1e-5 if B < 4096 else 1e-4)
+        assert len(back) == K and rel(back[-1], x) < 1e-4
         # per-layer log-det antisymmetry
         z, ld = m.flow.layers[0](x.cuda(), logdet=torch.zeros(B, device="cuda"))
         xb, ld2 = m.flow.layers[0](z, logdet=ld, reverse=True)
-        assert ld2.abs().max().item() < 1e-3 * (ld.abs().max().item() + 1) and rel(xb, x) < (1e-5 if B < 4096 else 1e-4)
+        assert ld2.abs().max().item() < 1e-3 * (ld.abs().max().item() + 1) and rel(xb, x) < 1e-4
+        # the resident one-launch inverse (both tile shapes) against the D-pass GEMM inverse it replaces
+        lay = m.flow.layers[0]
+        lay.resident_inverse = False
+        x_dp, ld_dp = lay(z, logdet=ld, reverse=True)
+        lay.resident_inverse = True
+        assert rel(x_dp, x) < (1e-5 if B < 4096 else 1e-4)
+        for mt in (1, 2):
+            lay.resident_mtiles = mt
+            x_r, ld_r = lay(z, logdet=ld, reverse=True)
+            assert rel(x_r, x_dp) < 1e-4, mt
+            assert (ld_r - ld_dp).abs().max().item() < 1e-3 * (ld.abs().max().item() + 1), mt
+        lay.resident_mtiles = 0
     # autoregressive property: d z_i / d x_j = 0 for j > i  (layer 0, un-flipped view)
     with torch.no_grad():
         x2 = x.clone()
@@ -63,6 +77,33 @@ def test_maf_forward_inverse_backward_vs_paper_restatement(D, H, K, B):
         ref = sdg[n].grad
         cs = torch.nn.functional.cosine_similarity(p.grad.flatten().cpu(), ref.flatten(), dim=0).item()
         assert cs > (0.999 if B >= 256 else 0.99) and rel(p.grad, ref) < (0.1 if B >= 256 else 0.2), (n, cs)
+
+
+@pytest.mark.parametrize("D,H,B,flip", [(1, 64, 33, True), (2, 64, 16, False), (100, 64, 50, True), (17, 128, 1, True),
+                                        (63, 512, 20000, True)])
+def test_resident_inverse_matches_paper_restatement(D, H, B, flip):
+    """One MADE layer, inverse only: the one-launch resident kernel against the fp32 restatement's D-pass inverse
+    (bf16 network vs fp32 network: 2e-3 of max|x|), at degenerate sizes (D = 1, D > H so some degrees own no hidden
+    unit, a single sample, a ragged last tile) and at a batch that fills every SM several times."""
+    from nf_distillation_b200.models.maf import MADE
+    from oracle import maf_oracle as MO
+    torch.manual_seed(D * 7 + H)
+    made = MADE(D, H, flip=flip)
+    with torch.no_grad():
+        made.fc3.bias.normal_(0, 0.1)
+    sd = {"l." + k: v.clone() for k, v in made.state_dict().items()}
+    u = torch.randn(B, D)
+    x_o, sum_alpha = MO.made_inverse(u, sd, "l.", D, flip=flip)
+    made = made.cuda()
+    with torch.no_grad():
+        ld0 = torch.randn(B, device="cuda")
+        for mt in (1, 2):
+            made.resident_mtiles = mt
+            x, ld = made(u.cuda(), logdet=ld0, reverse=True)
+            assert rel(x, x_o) < 2e-3, mt
+            assert ((ld - ld0).cpu() - sum_alpha).abs().max().item() < 2e-3 * (sum_alpha.abs().max().item() + 1), mt
+            x2, none = made(u.cuda(), logdet=None, reverse=True)
+            assert none is None and torch.equal(x2, x)
 
 
 def test_masked_tile_skipping_is_exact():

@@ -230,16 +230,18 @@ int nfk_made_inv_update(float* x, void* xb, int Dp, const float* u_in, const flo
                         float* ld_out, int B, int D, int i, int flip, int last, void* stream);
 /* The whole D-step inverse of one MADE layer in ONE launch (csrc/maf_inverse.cu): a warp keeps x, h1, h2 of its 16 or
  * 32 samples in shared memory and finalises every hidden unit once, in degree order (~ one forward pass of work,
- * not D); a producer warp streams the weight rows of each job through a shared-memory ring (cp.async.bulk).
+ * not D); a producer warp streams the weight rows of each job through a shared-memory byte ring (cp.async.bulk).
  * B1/B2/B3, b1/b2: the masked bf16 operands / biases of nfk_made_prep; b3 [>= 2D]. jobs [njobs][4] int32 on the
  * DEVICE (16-byte aligned) = the table nfk_made_inverse_jobs builds. u_in is in the layer's output order (reversed
  * when flip != 0); x [B,D]; ld_out = ld_in + sum alpha (either may be NULL). mtiles: 16-row tiles per warp (1 or 2;
  * 0 = choose). _supported: 1 if the shapes fit (H, Dp multiples of 64).
  * nfk_made_inverse_jobs is HOST code (host pointers, no GPU): cnt1/cnt2 [D+1] = number of layer-1 / layer-2 hidden
- * units with degree <= d (degrees sorted ascending); writes up to `cap` jobs {phase, first row, 16-wide k-chunks,
- * second 8-row tile present} and returns the number of jobs of one sample tile (call with cap = 0 to size). */
+ * units with degree <= d (degrees sorted ascending); returns the number of jobs of one sample tile and, when
+ * cap >= that number, writes the jobs {phase (0: layer-1 tile pair, 1: layer-2 tile pair, 2: (mu, alpha) row pair)
+ * | second 8-row tile present << 2 | 16-wide k-chunks << 3, first row (phase 2: d), byte offset in the kernel's
+ * shared-memory weight ring, jobs back to the latest job occupying any of those bytes}. Call with cap = 0 to size. */
 int nfk_made_inverse_resident_supported(int D, int H, int Dp);
-int nfk_made_inverse_jobs(const int* cnt1, const int* cnt2, int D, int* jobs, int cap);
+int nfk_made_inverse_jobs(const int* cnt1, const int* cnt2, int D, int H, int Dp, int* jobs, int cap);
 int nfk_made_inverse_resident(const float* u_in, const void* B1, const void* B2, const void* B3, const float* b1,
                               const float* b2, const float* b3, const int* jobs, int njobs, float* x,
                               const float* ld_in, float* ld_out, int B, int D, int H, int Dp, int flip, int mtiles,

@@ -14,10 +14,12 @@
 // 8-16 output columns of a 16-row tile, far below its 64 x 8 x 16 minimum shape with a TMEM round trip per step.
 // The recursion is a fixed stream of JOBS (step d: layer-1 tile pairs of degree d, layer-2 tile pairs, the
 // (mu_d, alpha_d) row pair), the same for every sample tile, so the host builds the job table once
-// (nfk_made_inverse_jobs). A producer warp streams each job's weight rows into a 3-stage shared-memory ring with
-// cp.async.bulk (TMA, one bulk copy per row, completion on an mbarrier); the consumer warps wait on the stage's
-// "full" barrier, multiply, and release it through its "empty" barrier — no block-wide barrier in the recursion,
-// warps drift apart freely. History (B = 65 536, D = 63, H = 512): every warp streaming its B fragments straight
+// (nfk_made_inverse_jobs), including each job's byte range in a shared-memory weight ring. A producer warp streams
+// each job's weight rows into its range with cp.async.bulk (TMA, one bulk copy per row, completion on an mbarrier);
+// the consumer warps wait on the job's "full" barrier, multiply, and release it through its "empty" barrier — no
+// block-wide barrier in the recursion, warps drift apart freely. Jobs are sized by their bytes (a (mu, alpha) row
+// pair is 2 KB, a full layer-2 tile pair 16 KB), so ~50 KB of ring keeps ~a dozen jobs = several microseconds of
+// copies in flight; with three fixed 16 KB stages the consumers waited on the copy latency at every job (0.77 ms). History (B = 65 536, D = 63, H = 512): every warp streaming its B fragments straight
 // from L2 (with 213 KB of shared memory carved out there is no L1 left): 1.62 ms; cp.async ring filled by all
 // threads + __syncthreads per job + the job stream derived on the fly by every thread: 1.12 ms, issue-bound on that
 // bookkeeping (ncu: 1 000 warp instructions per warp and step, 60 % of them index arithmetic).
@@ -32,7 +34,7 @@
 
 namespace nfk {
 
-constexpr int MI_STAGES = 3;
+constexpr int MI_SLOTS = 16;   // jobs in flight at most (mbarrier pairs); the byte ring usually binds first
 
 struct MiArgs {
   const float* u_in;            // [B, D] layer output order (flipped if flip)
@@ -40,18 +42,27 @@ struct MiArgs {
   const __nv_bfloat16* B2;      // [H, H]
   const __nv_bfloat16* B3;      // [N3p, H]  rows: mu_0..mu_{D-1}, alpha_0..alpha_{D-1}
   const float *b1, *b2, *b3;    // [H], [H], [>= 2D]
-  const int4* jobs;             // [njobs] {phase, row0 (phase 2: d), k-chunks of 16, second tile present}
-  int njobs;
+  const int4* jobs;             // [njobs] {phase | second tile << 2 | k-chunks << 3, row0 (phase 2: d), ring offset, back}
+  int njobs, ring_bytes;
   float* x;                     // [B, D]
   const float* ld_in;           // [B] or null
   float* ld_out;                // [B] or null
   int B, D, H, Dp, flip;
 };
 
+template <int OFF = 0>
 __device__ __forceinline__ void mi_ldsm_x4(uint32_t addr, uint32_t (&r)[4]) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4+%5];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
-               : "r"(addr)
+               : "r"(addr), "n"(OFF)
+               : "memory");
+}
+
+template <int OFF = 0>
+__device__ __forceinline__ void mi_ldsm_x2(uint32_t addr, uint32_t (&r)[2]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2+%3];"
+               : "=r"(r[0]), "=r"(r[1])
+               : "r"(addr), "n"(OFF)
                : "memory");
 }
 
@@ -73,6 +84,14 @@ __device__ __forceinline__ uint32_t mi_pack_relu(float a, float b) {
   return *reinterpret_cast<const uint32_t*>(&v);
 }
 
+// job descriptor in 2 x 32 bits: x = phase [0,2) | second tile [2] | k-chunks [3,11) | first row (phase 2: d) [11,32)
+//                                y = ring offset / 16 [0,16) | jobs back to the latest job whose ring bytes it overwrites [16,32)
+__device__ __forceinline__ uint2 mi_pack_job(int4 j) {
+  const uint32_t back = j.w > 65535 ? 65535u : static_cast<uint32_t>(j.w);
+  return make_uint2(static_cast<uint32_t>(j.x) | (static_cast<uint32_t>(j.y) << 11),
+                    (static_cast<uint32_t>(j.z) >> 4) | (back << 16));
+}
+
 // blockDim = (consumer warps + 1) * 32; the last warp is the weight producer
 template <int MT>
 __global__ void __launch_bounds__(288) made_inverse_resident_kernel(const MiArgs p) {
@@ -80,18 +99,18 @@ __global__ void __launch_bounds__(288) made_inverse_resident_kernel(const MiArgs
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, cwarps = (blockDim.x >> 5) - 1;
   const int D = p.D, H = p.H, Dp = p.Dp;
   const int ldx = Dp + 8, ldh = H + 8;                       // bf16 elements; +8 keeps ldmatrix rows on distinct banks
-  const int ldb_bytes = ((H > Dp ? H : Dp) + 8) * 2;         // weight ring row stride
-  const int stage_bytes = 16 * ldb_bytes;
   constexpr int R = MT * 16;
   const int per_warp = R * (ldx + 2 * ldh) * 2;              // bytes
   unsigned char* ring = mi_smem;
-  uint64_t* full = reinterpret_cast<uint64_t*>(mi_smem + MI_STAGES * stage_bytes);
-  uint64_t* empty = full + MI_STAGES;
-  unsigned char* act = mi_smem + MI_STAGES * stage_bytes + 128;
+  uint64_t* full = reinterpret_cast<uint64_t*>(mi_smem + p.ring_bytes);
+  uint64_t* empty = full + MI_SLOTS;
+  uint2* jobs_s = reinterpret_cast<uint2*>(mi_smem + p.ring_bytes + 256);   // packed, see mi_pack_job
+  unsigned char* act = mi_smem + p.ring_bytes + 256 + ((p.njobs * 8 + 15) & ~15);
   const uint32_t ring_s = smem_u32(ring);
+  for (int i = threadIdx.x; i < p.njobs; i += blockDim.x) jobs_s[i] = mi_pack_job(__ldg(p.jobs + i));
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < MI_STAGES; ++s) {
+    for (int s = 0; s < MI_SLOTS; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], cwarps);
     }
@@ -104,31 +123,36 @@ __global__ void __launch_bounds__(288) made_inverse_resident_kernel(const MiArgs
   const int njobs = p.njobs;
 
   if (warp == cwarps) {
-    // ---------------- producer: the same job stream once per CTA tile, MI_STAGES jobs ahead of the slowest consumer
-    int stage = 0, par = 0;
+    // ---------------- producer: the same job stream once per CTA tile. A job's rows go to its own byte range of the
+    // ring (row stride = row bytes + 16: ldmatrix rows on distinct banks); before overwriting, wait until the latest
+    // job that used any of those bytes — or this job's slot — has been released by every consumer warp.
+    int slot = 0, par = 0, q = 0;
     for (int tile = 0; tile < my_tiles; ++tile) {
-      int4 jd = __ldg(p.jobs);
-      for (int j = 0; j < njobs; ++j) {
-        const int4 cur = jd;
-        if (j + 1 < njobs) jd = __ldg(p.jobs + j + 1);
-        if (tile > 0 || j >= MI_STAGES) mbar_wait(&empty[stage], par ^ 1);
-        const int phase = cur.x, kch = cur.z;
-        const int rows = phase == 2 ? 2 : (cur.w ? 16 : 8);
+      for (int j = 0; j < njobs; ++j, ++q) {
+        const uint2 cur = jobs_s[j];
+        int back = cur.y >> 16;
+        if (back > MI_SLOTS) back = MI_SLOTS;
+        if (q >= back) {
+          const int ws = slot >= back ? slot - back : slot - back + MI_SLOTS;
+          mbar_wait(&empty[ws], slot >= back ? par : par ^ 1);
+        }
+        const int phase = cur.x & 3, kch = (cur.x >> 3) & 255, row0 = cur.x >> 11;
+        const int rows = phase == 2 ? 2 : ((cur.x & 4) ? 16 : 8);
         const uint32_t row_bytes = kch * 32;
         if (kch == 0) {
-          if (lane == 0) mbar_arrive(&full[stage]);
+          if (lane == 0) mbar_arrive(&full[slot]);
         } else {
-          if (lane == 0) mbar_expect_tx(&full[stage], rows * row_bytes);
+          if (lane == 0) mbar_expect_tx(&full[slot], rows * row_bytes);
           __syncwarp();
           if (lane < rows) {
             const __nv_bfloat16* src;
-            if (phase == 0) src = p.B1 + static_cast<size_t>(cur.y + lane) * Dp;
-            else if (phase == 1) src = p.B2 + static_cast<size_t>(cur.y + lane) * H;
-            else src = p.B3 + static_cast<size_t>(cur.y + lane * D) * H;     // rows d (mu) and D + d (alpha)
-            mi_bulk_row(ring_s + stage * stage_bytes + lane * ldb_bytes, src, row_bytes, &full[stage]);
+            if (phase == 0) src = p.B1 + static_cast<size_t>(row0 + lane) * Dp;
+            else if (phase == 1) src = p.B2 + static_cast<size_t>(row0 + lane) * H;
+            else src = p.B3 + static_cast<size_t>(row0 + lane * D) * H;     // rows d (mu) and D + d (alpha)
+            mi_bulk_row(ring_s + (cur.y & 0xffff) * 16 + lane * (row_bytes + 16), src, row_bytes, &full[slot]);
           }
         }
-        if (++stage == MI_STAGES) { stage = 0; par ^= 1; }
+        if (++slot == MI_SLOTS) { slot = 0; par ^= 1; }
       }
     }
     return;
@@ -143,13 +167,34 @@ __global__ void __launch_bounds__(288) made_inverse_resident_kernel(const MiArgs
   const uint32_t xb_lane = smem_u32(xb + lrow * ldx + lcol);
   const uint32_t h1_lane = smem_u32(h1 + lrow * ldh + lcol);
   const uint32_t h2_lane = smem_u32(h2 + lrow * ldh + lcol);
-  // B-operand ldmatrix address of this lane inside a stage: matrices = (tile 0, k 0-7), (tile 0, k 8-15), (tile 1, ..)
-  const uint32_t b_lane = ((lane & 7) + ((lane >> 4) << 3)) * ldb_bytes + ((lane >> 3) & 1) * 16;
+  // B-operand ldmatrix row / column of this lane inside a job: matrices = (tile 0, k 0-7), (tile 0, k 8-15), (tile 1, ..)
+  const uint32_t b_row = (lane & 7) + ((lane >> 4) << 3), b_col = ((lane >> 3) & 1) * 16;
 
-  int stage = 0, par = 0;
+  // biases of a job (phase < 2: the two column pairs this lane finishes; phase 2: b3[d], b3[D + d]); requested one
+  // job ahead of their use so the L2 round trip hides behind the previous job's products
+  auto fetch_bias = [&](uint32_t jd) -> float4 {   // jd = descriptor word x
+    const int phase = jd & 3, row0 = jd >> 11;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (phase < 2) {
+      const float* bias = (phase == 0 ? p.b1 : p.b2) + row0 + 2 * t;
+      v.x = __ldg(bias);
+      v.y = __ldg(bias + 1);
+      if (jd & 4) {
+        v.z = __ldg(bias + 8);
+        v.w = __ldg(bias + 9);
+      }
+    } else {
+      v.x = __ldg(p.b3 + row0);
+      v.y = __ldg(p.b3 + D + row0);
+    }
+    return v;
+  };
+
+  int slot = 0, par = 0;
   for (int tile = 0; tile < my_tiles; ++tile) {
     const long long base = ((static_cast<long long>(tile) * gridDim.x + blockIdx.x) * cwarps + warp) * R;
     float ldacc[MT][2], unext[MT][2];
+    const float* urow[MT][2];     // lanes t == 0: this lane's samples' rows of u (null past the batch end)
     {
       // clear this warp's slice: scratch columns must be finite (they meet masked-zero weights)
       uint4* z = reinterpret_cast<uint4*>(xb);
@@ -161,25 +206,28 @@ __global__ void __launch_bounds__(288) made_inverse_resident_kernel(const MiArgs
         for (int hh = 0; hh < 2; ++hh) {
           const long long b = base + mt * 16 + g + 8 * hh;
           ldacc[mt][hh] = 0.f;
-          unext[mt][hh] = (t == 0 && b < p.B) ? __ldg(p.u_in + b * D + (p.flip ? D - 1 : 0)) : 0.f;
+          urow[mt][hh] = (t == 0 && b < p.B) ? p.u_in + b * D : nullptr;
+          unext[mt][hh] = urow[mt][hh] ? __ldg(urow[mt][hh] + (p.flip ? D - 1 : 0)) : 0.f;
         }
       __syncwarp();
     }
-    int4 jd = __ldg(p.jobs);
+    uint2 jd = jobs_s[0];
+    float4 bnext = fetch_bias(jd.x);
     for (int j = 0; j < njobs; ++j) {
-      const int4 cur = jd;
-      if (j + 1 < njobs) jd = __ldg(p.jobs + j + 1);         // next descriptor requested a job ahead
-      const int phase = cur.x, kch = cur.z;
-      const uint32_t bs = ring_s + stage * stage_bytes + b_lane;
+      const uint32_t cur = jd.x;
+      const float4 bv = bnext;
+      const int phase = cur & 3, kch = (cur >> 3) & 255, row0 = cur >> 11;
+      uint32_t b_addr = ring_s + (jd.y & 0xffff) * 16 + b_row * (kch * 32 + 16) + b_col;
+      if (j + 1 < njobs) {
+        jd = jobs_s[j + 1];
+        bnext = fetch_bias(jd.x);
+      }
 
       if (phase < 2) {
         // out[:, row0 .. row0 + 16) = bf16(relu(in[:, 0 .. 16*kch) . W^T + bias))
-        const bool l1 = phase == 0, two = cur.w != 0;
-        const uint32_t in_lane = l1 ? xb_lane : h1_lane;
+        const bool l1 = phase == 0, two = (cur & 4) != 0;
+        uint32_t a_addr = l1 ? xb_lane : h1_lane;
         const int lda_bytes = (l1 ? ldx : ldh) * 2;
-        const float* bias = (l1 ? p.b1 : p.b2) + cur.y + 2 * t;
-        const float bv00 = __ldg(bias), bv01 = __ldg(bias + 1);
-        const float bv10 = two ? __ldg(bias + 8) : 0.f, bv11 = two ? __ldg(bias + 9) : 0.f;
         float acc[MT][2][2][4];   // [m-tile][n-tile][even / odd k-chunk chain]
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt)
@@ -189,65 +237,70 @@ __global__ void __launch_bounds__(288) made_inverse_resident_kernel(const MiArgs
             for (int c = 0; c < 2; ++c)
 #pragma unroll
               for (int e = 0; e < 4; ++e) acc[mt][n][c][e] = 0.f;
-        mbar_wait(&full[stage], par);
-        int kc = 0;
-#pragma unroll 2
-        for (; kc + 1 < kch; kc += 2) {
+        mbar_wait(&full[slot], par);
+        // fragments are requested one k-chunk ahead of the products that use them (ping-pong register sets)
+        uint32_t a0[MT][4], a1[MT][4], b0[4], b1[4];
+        if (kch > 0) {
+          mi_ldsm_x4<0>(b_addr, b0);
 #pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            uint32_t b[4];
-            mi_ldsm_x4(bs + (kc + c) * 32, b);
-#pragma unroll
-            for (int mt = 0; mt < MT; ++mt) {
-              uint32_t a[4];
-              mi_ldsm_x4(in_lane + mt * 16 * lda_bytes + (kc + c) * 32, a);
-              mi_mma(acc[mt][0][c], a, b[0], b[1]);
-              mi_mma(acc[mt][1][c], a, b[2], b[3]);
-            }
-          }
+          for (int mt = 0; mt < MT; ++mt) mi_ldsm_x4<0>(a_addr + mt * 16 * lda_bytes, a0[mt]);
         }
-        if (kc < kch) {
-          uint32_t b[4];
-          mi_ldsm_x4(bs + kc * 32, b);
+        int kc = kch;
+        for (; kc >= 2; kc -= 2, a_addr += 64, b_addr += 64) {
+          mi_ldsm_x4<32>(b_addr, b1);
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) mi_ldsm_x4<32>(a_addr + mt * 16 * lda_bytes, a1[mt]);
 #pragma unroll
           for (int mt = 0; mt < MT; ++mt) {
-            uint32_t a[4];
-            mi_ldsm_x4(in_lane + mt * 16 * lda_bytes + kc * 32, a);
-            mi_mma(acc[mt][0][0], a, b[0], b[1]);
-            mi_mma(acc[mt][1][0], a, b[2], b[3]);
+            mi_mma(acc[mt][0][0], a0[mt], b0[0], b0[1]);
+            mi_mma(acc[mt][1][0], a0[mt], b0[2], b0[3]);
+          }
+          if (kc > 2) {
+            mi_ldsm_x4<64>(b_addr, b0);
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) mi_ldsm_x4<64>(a_addr + mt * 16 * lda_bytes, a0[mt]);
+          }
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) {
+            mi_mma(acc[mt][0][1], a1[mt], b1[0], b1[1]);
+            mi_mma(acc[mt][1][1], a1[mt], b1[2], b1[3]);
+          }
+        }
+        if (kc) {
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) {
+            mi_mma(acc[mt][0][0], a0[mt], b0[0], b0[1]);
+            mi_mma(acc[mt][1][0], a0[mt], b0[2], b0[3]);
           }
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[stage]);             // weights consumed: the stage may be refilled
-        __nv_bfloat16* out = (l1 ? h1 : h2) + cur.y + 2 * t;
+        if (lane == 0) mbar_arrive(&empty[slot]);             // weights consumed: the bytes may be refilled
+        __nv_bfloat16* out = (l1 ? h1 : h2) + row0 + 2 * t;
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
           *reinterpret_cast<uint32_t*>(out + (mt * 16 + g) * ldh) = mi_pack_relu(
-              acc[mt][0][0][0] + acc[mt][0][1][0] + bv00, acc[mt][0][0][1] + acc[mt][0][1][1] + bv01);
+              acc[mt][0][0][0] + acc[mt][0][1][0] + bv.x, acc[mt][0][0][1] + acc[mt][0][1][1] + bv.y);
           *reinterpret_cast<uint32_t*>(out + (mt * 16 + g + 8) * ldh) = mi_pack_relu(
-              acc[mt][0][0][2] + acc[mt][0][1][2] + bv00, acc[mt][0][0][3] + acc[mt][0][1][3] + bv01);
+              acc[mt][0][0][2] + acc[mt][0][1][2] + bv.x, acc[mt][0][0][3] + acc[mt][0][1][3] + bv.y);
           if (two) {
             *reinterpret_cast<uint32_t*>(out + (mt * 16 + g) * ldh + 8) = mi_pack_relu(
-                acc[mt][1][0][0] + acc[mt][1][1][0] + bv10, acc[mt][1][0][1] + acc[mt][1][1][1] + bv11);
+                acc[mt][1][0][0] + acc[mt][1][1][0] + bv.z, acc[mt][1][0][1] + acc[mt][1][1][1] + bv.w);
             *reinterpret_cast<uint32_t*>(out + (mt * 16 + g + 8) * ldh + 8) = mi_pack_relu(
-                acc[mt][1][0][2] + acc[mt][1][1][2] + bv10, acc[mt][1][0][3] + acc[mt][1][1][3] + bv11);
+                acc[mt][1][0][2] + acc[mt][1][1][2] + bv.z, acc[mt][1][0][3] + acc[mt][1][1][3] + bv.w);
           }
         }
         __syncwarp();
       } else {
-        // (mu_d, alpha_d) from the layer-2 units of degree <= d; stage row 0 = mu weights, row 1 = alpha weights
-        const int d = cur.y;
+        // (mu_d, alpha_d) from the layer-2 units of degree <= d; job row 0 = mu weights, row 1 = alpha weights
+        const int d = row0;
         float uv[MT][2];
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
           for (int hh = 0; hh < 2; ++hh) {
-            uv[mt][hh] = unext[mt][hh];
-            const long long b = base + mt * 16 + g + 8 * hh;   // next step's u, requested a whole step ahead
-            unext[mt][hh] =
-                (t == 0 && b < p.B && d + 1 < D) ? __ldg(p.u_in + b * D + (p.flip ? D - 2 - d : d + 1)) : 0.f;
+            uv[mt][hh] = unext[mt][hh];                          // next step's u, requested a whole step ahead
+            unext[mt][hh] = (urow[mt][hh] && d + 1 < D) ? __ldg(urow[mt][hh] + (p.flip ? D - 2 - d : d + 1)) : 0.f;
           }
-        const float bm = __ldg(p.b3 + d), ba = __ldg(p.b3 + D + d);
         float acc[MT][4][4];      // four independent k-chunk chains
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt)
@@ -255,54 +308,70 @@ __global__ void __launch_bounds__(288) made_inverse_resident_kernel(const MiArgs
           for (int c = 0; c < 4; ++c)
 #pragma unroll
             for (int e = 0; e < 4; ++e) acc[mt][c][e] = 0.f;
-        mbar_wait(&full[stage], par);
-        int kc = 0;
-        for (; kc + 3 < kch; kc += 4) {
+        uint32_t a_addr = h2_lane;
+        mbar_wait(&full[slot], par);
+        // chunk c of a group of four feeds chain c; the next group's fragments are requested before this group's
+        // products (only matrices 0/1 of the B operand are needed: rows 0 (mu) and 1 (alpha) of the job)
+        uint32_t a[2][MT][4][4], b[2][4][2];
+        auto load_group = [&](int buf, int n) {   // n = live chunks of the group (1..4)
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            uint32_t b[4];
-            mi_ldsm_x4(bs + (kc + c) * 32, b);
+          for (int c = 0; c < 4; ++c)
+            if (c < n) {
+              if (c == 0) mi_ldsm_x2<0>(b_addr, b[buf][0]);
+              if (c == 1) mi_ldsm_x2<32>(b_addr, b[buf][1]);
+              if (c == 2) mi_ldsm_x2<64>(b_addr, b[buf][2]);
+              if (c == 3) mi_ldsm_x2<96>(b_addr, b[buf][3]);
 #pragma unroll
-            for (int mt = 0; mt < MT; ++mt) {
-              uint32_t a[4];
-              mi_ldsm_x4(h2_lane + mt * 16 * ldh * 2 + (kc + c) * 32, a);
-              mi_mma(acc[mt][c], a, b[0], b[1]);
+              for (int mt = 0; mt < MT; ++mt) {
+                if (c == 0) mi_ldsm_x4<0>(a_addr + mt * 16 * ldh * 2, a[buf][mt][0]);
+                if (c == 1) mi_ldsm_x4<32>(a_addr + mt * 16 * ldh * 2, a[buf][mt][1]);
+                if (c == 2) mi_ldsm_x4<64>(a_addr + mt * 16 * ldh * 2, a[buf][mt][2]);
+                if (c == 3) mi_ldsm_x4<96>(a_addr + mt * 16 * ldh * 2, a[buf][mt][3]);
+              }
             }
-          }
-        }
+          a_addr += 128;
+          b_addr += 128;
+        };
+        auto mma_group = [&](int buf, int n) {
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          if (kc + c < kch) {
-            uint32_t b[4];
-            mi_ldsm_x4(bs + (kc + c) * 32, b);
+          for (int c = 0; c < 4; ++c)
+            if (c < n) {
 #pragma unroll
-            for (int mt = 0; mt < MT; ++mt) {
-              uint32_t a[4];
-              mi_ldsm_x4(h2_lane + mt * 16 * ldh * 2 + (kc + c) * 32, a);
-              mi_mma(acc[mt][c], a, b[0], b[1]);
+              for (int mt = 0; mt < MT; ++mt) mi_mma(acc[mt][c], a[buf][mt][c], b[buf][c][0], b[buf][c][1]);
             }
-          }
+        };
+        int kc = kch;                                  // chunks not yet multiplied
+        if (kc > 0) load_group(0, kc < 4 ? kc : 4);
+        while (kc > 0) {
+          const int n0 = kc < 4 ? kc : 4, r1 = kc - n0;
+          if (r1 > 0) load_group(1, r1 < 4 ? r1 : 4);
+          mma_group(0, n0);
+          if (r1 <= 0) break;
+          const int n1 = r1 < 4 ? r1 : 4, r2 = r1 - n1;
+          if (r2 > 0) load_group(0, r2 < 4 ? r2 : 4);
+          mma_group(1, n1);
+          kc = r2;
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[stage]);
+        if (lane == 0) mbar_arrive(&empty[slot]);
         if (t == 0) {   // lanes t == 0 hold columns 0 (mu) and 1 (alpha) of samples g and g + 8
 #pragma unroll
           for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
-              const float mu = (acc[mt][0][2 * hh] + acc[mt][1][2 * hh]) + (acc[mt][2][2 * hh] + acc[mt][3][2 * hh]) + bm;
+              const float mu = (acc[mt][0][2 * hh] + acc[mt][1][2 * hh]) + (acc[mt][2][2 * hh] + acc[mt][3][2 * hh]) + bv.x;
               const float al = (acc[mt][0][2 * hh + 1] + acc[mt][1][2 * hh + 1]) +
-                               (acc[mt][2][2 * hh + 1] + acc[mt][3][2 * hh + 1]) + ba;
+                               (acc[mt][2][2 * hh + 1] + acc[mt][3][2 * hh + 1]) + bv.y;
               const float xv = uv[mt][hh] * expf(al) + mu;
               const int s = mt * 16 + g + 8 * hh;
-              if (base + s < p.B) p.x[(base + s) * D + d] = xv;
+              if (urow[mt][hh]) p.x[(urow[mt][hh] - p.u_in) + d] = xv;
               xb[s * ldx + d] = __float2bfloat16_rn(xv);
               ldacc[mt][hh] += al;
             }
         }
         __syncwarp();
       }
-      if (++stage == MI_STAGES) { stage = 0; par ^= 1; }
+      if (++slot == MI_SLOTS) { slot = 0; par ^= 1; }
     }
     if (t == 0 && p.ld_out) {
 #pragma unroll
@@ -317,7 +386,8 @@ __global__ void __launch_bounds__(288) made_inverse_resident_kernel(const MiArgs
 }
 
 static inline int mi_per_warp_bytes(int mt, int H, int Dp) { return mt * 16 * ((Dp + 8) + 2 * (H + 8)) * 2; }
-static inline int mi_fixed_bytes(int H, int Dp) { return MI_STAGES * 16 * ((H > Dp ? H : Dp) + 8) * 2 + 128; }
+static inline int mi_job_bytes(int rows, int kch) { return kch ? ((rows * (kch * 32 + 16) + 127) & ~127) : 0; }
+static inline int mi_side_bytes(int njobs) { return 256 + ((njobs * 8 + 15) & ~15); }   // barriers + packed job table
 
 }  // namespace nfk
 
@@ -325,22 +395,38 @@ using namespace nfk;
 
 static constexpr int MI_SMEM_MAX = 227 * 1024;
 
-extern "C" int nfk_made_inverse_resident_supported(int D, int H, int Dp) {
-  if (D <= 0 || H <= 0 || H % 64 || Dp % 64 || Dp < D) return 0;
-  return mi_fixed_bytes(H, Dp) + mi_per_warp_bytes(1, H, Dp) <= MI_SMEM_MAX ? 1 : 0;
+// Weight ring size for a layer shape: what is left after the barriers, the job table and as many one-tile warps as fit
+// next to a ring of two largest jobs (so that at least two jobs can be in flight), at most 8 warps.
+static int mi_ring_bytes(int H, int Dp, int njobs) {
+  const int biggest = mi_job_bytes(16, (H > Dp ? H : Dp) / 16);
+  const int avail = MI_SMEM_MAX - mi_side_bytes(njobs), per_warp = mi_per_warp_bytes(1, H, Dp);
+  int warps = (avail - 2 * biggest) / per_warp;
+  if (warps < 1) return -1;
+  if (warps > 8) warps = 8;
+  int ring = (avail - warps * per_warp) & ~127;
+  if (ring > (1 << 20) - 128) ring = (1 << 20) - 128;   // offsets are stored in 16 bits of 16-byte units
+  return ring;
 }
 
-// Host-side: the job stream of one sample tile from the degree counts (cnt[d] = units with degree <= d, d = 0..D).
-extern "C" int nfk_made_inverse_jobs(const int* cnt1, const int* cnt2, int D, int* jobs, int cap) {
+extern "C" int nfk_made_inverse_resident_supported(int D, int H, int Dp) {
+  if (D <= 0 || H <= 0 || H % 64 || Dp % 64 || Dp < D || H > 255 * 16 || Dp > 255 * 16) return 0;
+  // (the packed job table also lives in shared memory: at most 4 D + H / 8 jobs of 8 bytes)
+  return mi_ring_bytes(H, Dp, 4 * D + H / 8) > 0 ? 1 : 0;
+}
+
+// Host-side: the job stream of one sample tile from the degree counts (cnt[d] = units with degree <= d, d = 0..D),
+// each job with its byte range in the weight ring and the distance back to the latest job that used those bytes.
+extern "C" int nfk_made_inverse_jobs(const int* cnt1, const int* cnt2, int D, int H, int Dp, int* jobs, int cap) {
   if (!cnt1 || !cnt2 || D <= 0 || cap < 0 || (cap > 0 && !jobs)) return NFK_ERR_ARG;
+  if (!nfk_made_inverse_resident_supported(D, H, Dp)) return NFK_ERR_SHAPE;
   int n = 0;
   auto put = [&](int phase, int row0, int kch, int two) {
-    if (n < cap) { jobs[4 * n] = phase; jobs[4 * n + 1] = row0; jobs[4 * n + 2] = kch; jobs[4 * n + 3] = two; }
+    if (n < cap) { jobs[4 * n] = phase | (two << 2) | (kch << 3); jobs[4 * n + 1] = row0; jobs[4 * n + 2] = 0; jobs[4 * n + 3] = 0; }
     ++n;
   };
   for (int d = 0; d < D; ++d) {
     const int c1p = d ? cnt1[d - 1] : 0, c1 = cnt1[d], c2p = d ? cnt2[d - 1] : 0, c2 = cnt2[d];
-    if (c1 < c1p || c2 < c2p || c1p < 0 || c2p < 0) return NFK_ERR_ARG;
+    if (c1 < c1p || c2 < c2p || c1p < 0 || c2p < 0 || c1 > H || c2 > H) return NFK_ERR_ARG;
     if (d > 0) {
       if (c1 > c1p)   // layer-1 units of degree d: inputs x_0 .. x_{d-1}
         for (int nt = c1p >> 3, hi = (c1 + 7) >> 3; nt < hi; nt += 2) put(0, nt * 8, (d + 15) >> 4, nt + 1 < hi);
@@ -349,12 +435,41 @@ extern "C" int nfk_made_inverse_jobs(const int* cnt1, const int* cnt2, int D, in
     }
     put(2, d, (c2 + 15) >> 4, 0);   // (mu_d, alpha_d): layer-2 units of degree <= d
   }
+  if (n > cap) return n;            // sizing call (or a short buffer): offsets need the whole table
+  // ring placement: consecutive byte ranges, wrapping to 0 when a job does not fit before the end; every tile replays
+  // the same offsets, so `back` looks through the cyclic job order (a job of the previous tile counts)
+  const int ring = mi_ring_bytes(H, Dp, n);
+  if (ring <= 0) return NFK_ERR_SHAPE;
+  int cur = 0;
+  for (int j = 0; j < n; ++j) {
+    const int d = jobs[4 * j], phase = d & 3, kch = d >> 3;
+    const int size = mi_job_bytes(phase == 2 ? 2 : ((d & 4) ? 16 : 8), kch);
+    if (size > ring) return NFK_ERR_SHAPE;
+    if (cur + size > ring) cur = 0;
+    jobs[4 * j + 2] = cur;
+    cur += size;
+  }
+  for (int j = 0; j < n; ++j) {
+    const int d = jobs[4 * j], phase = d & 3, kch = d >> 3;
+    const int lo = jobs[4 * j + 2], hi = lo + mi_job_bytes(phase == 2 ? 2 : ((d & 4) ? 16 : 8), kch);
+    int back = n;                                  // nothing overlaps within a whole period: only the slot binds
+    for (int b = 1; b < n && hi > lo; ++b) {
+      const int i = ((j - b) % n + n) % n;
+      const int di = jobs[4 * i], lo2 = jobs[4 * i + 2];
+      const int hi2 = lo2 + mi_job_bytes((di & 3) == 2 ? 2 : ((di & 4) ? 16 : 8), di >> 3);
+      if (lo < hi2 && lo2 < hi) { back = b; break; }
+    }
+    jobs[4 * j + 3] = back;
+  }
   return n;
 }
 
 template <int MT>
-static int mi_launch(const MiArgs& p, cudaStream_t st) {
-  const int per_warp = mi_per_warp_bytes(MT, p.H, p.Dp), fixed = mi_fixed_bytes(p.H, p.Dp);
+static int mi_launch(MiArgs p, cudaStream_t st) {
+  const int per_warp = mi_per_warp_bytes(MT, p.H, p.Dp);
+  p.ring_bytes = mi_ring_bytes(p.H, p.Dp, p.njobs);
+  if (p.ring_bytes <= 0) return NFK_ERR_SHAPE;
+  const int fixed = p.ring_bytes + mi_side_bytes(p.njobs);
   int warps = (MI_SMEM_MAX - fixed) / per_warp;
   if (warps > 8) warps = 8;
   if (warps < 1) return NFK_ERR_SHAPE;
@@ -377,7 +492,8 @@ extern "C" int nfk_made_inverse_resident(const float* u_in, const void* B1, cons
                                          const float* b1, const float* b2, const float* b3, const int* jobs,
                                          int njobs, float* x, const float* ld_in, float* ld_out, int B, int D, int H,
                                          int Dp, int flip, int mtiles, void* stream) {
-  if (B <= 0 || njobs <= 0 || !nfk_made_inverse_resident_supported(D, H, Dp) || mtiles < 0 || mtiles > 2)
+  if (B <= 0 || njobs <= 0 || njobs > (1 << 20) || !nfk_made_inverse_resident_supported(D, H, Dp) || mtiles < 0 ||
+      mtiles > 2)
     return NFK_ERR_SHAPE;
   if (!u_in || !B1 || !B2 || !B3 || !b1 || !b2 || !b3 || !jobs || !x) return NFK_ERR_ARG;
   if (reinterpret_cast<uintptr_t>(jobs) & 15) return NFK_ERR_ARG;
@@ -387,12 +503,14 @@ extern "C" int nfk_made_inverse_resident(const float* u_in, const void* B1, cons
   p.B2 = static_cast<const __nv_bfloat16*>(B2);
   p.B3 = static_cast<const __nv_bfloat16*>(B3);
   p.b1 = b1; p.b2 = b2; p.b3 = b3;
-  p.jobs = reinterpret_cast<const int4*>(jobs); p.njobs = njobs;
+  p.jobs = reinterpret_cast<const int4*>(jobs); p.njobs = njobs; p.ring_bytes = 0;
   p.x = x; p.ld_in = ld_in; p.ld_out = ld_out;
   p.B = B; p.D = D; p.H = H; p.Dp = Dp; p.flip = flip;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   // one 16-sample tile per warp leaves room for the most warps (latency hiding); two halve the B-operand reads
+  const int ring = mi_ring_bytes(H, Dp, njobs);
+  if (ring <= 0) return NFK_ERR_SHAPE;
   int mt = mtiles == 0 ? 1 : mtiles;
-  if (mt == 2 && mi_fixed_bytes(H, Dp) + mi_per_warp_bytes(2, H, Dp) > MI_SMEM_MAX) mt = 1;
+  if (mt == 2 && ring + mi_side_bytes(njobs) + mi_per_warp_bytes(2, H, Dp) > MI_SMEM_MAX) mt = 1;
   return mt == 2 ? mi_launch<2>(p, st) : mi_launch<1>(p, st);
 }

@@ -137,7 +137,7 @@ class MADE(nn.Module):
             if ok:
                 edges = torch.arange(self.D + 1)
                 cnt1, cnt2 = ((d[None, :] <= edges[:, None]).sum(1) for d in (d1, d2))
-                jobs = ops.made_inverse_jobs(cnt1, cnt2, self.D).to(dev)
+                jobs = ops.made_inverse_jobs(cnt1, cnt2, self.D, self.H, self.Dp).to(dev)
             self._job_cache = (key, jobs)
         return self._job_cache[1]
 

@@ -342,16 +342,17 @@ def made_inverse_resident_supported(D, H, Dp) -> bool:
     return bool(LIB.nfk_made_inverse_resident_supported(D, H, Dp))
 
 
-def made_inverse_jobs(cnt1, cnt2, D):
-    """Host-side job table of the resident inverse from the degree counts (CPU int32 tensors [D+1]) -> [njobs, 4]."""
+def made_inverse_jobs(cnt1, cnt2, D, H, Dp):
+    """Host-side job table of the resident inverse from the degree counts (CPU int32 tensors [D+1]) -> [njobs, 4]:
+    (phase | two << 2 | k-chunks << 3, first row, weight-ring byte offset, jobs back to the ring bytes' last user)."""
     import torch
     cnt1 = cnt1.to(torch.int32).contiguous().cpu()
     cnt2 = cnt2.to(torch.int32).contiguous().cpu()
-    n = LIB.nfk_made_inverse_jobs(cnt1.data_ptr(), cnt2.data_ptr(), D, None, 0)
+    n = LIB.nfk_made_inverse_jobs(cnt1.data_ptr(), cnt2.data_ptr(), D, H, Dp, None, 0)
     if n <= 0:
         check(n if n < 0 else -1, "nfk_made_inverse_jobs")
     jobs = torch.empty(n, 4, dtype=torch.int32)
-    check(0 if LIB.nfk_made_inverse_jobs(cnt1.data_ptr(), cnt2.data_ptr(), D, jobs.data_ptr(), n) == n else -1,
+    check(0 if LIB.nfk_made_inverse_jobs(cnt1.data_ptr(), cnt2.data_ptr(), D, H, Dp, jobs.data_ptr(), n) == n else -1,
           "nfk_made_inverse_jobs")
     return jobs
 

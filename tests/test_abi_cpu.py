@@ -172,13 +172,23 @@ def test_resident_inverse_job_table_reproduces_the_sequential_inverse():
         W1p[:, :D] = W1
         edges = torch.arange(D + 1)
         cnt = (deg.long()[None, :] <= edges[:, None]).sum(1)
-        jobs = ops.made_inverse_jobs(cnt, cnt, D)
-        assert jobs.shape[1] == 4 and (jobs[:, 0] == 2).sum().item() == D
+        jobs = ops.made_inverse_jobs(cnt, cnt, D, H, Dp)
+        assert jobs.shape[1] == 4 and ((jobs[:, 0] & 3) == 2).sum().item() == D
+        # ring plan: 16-byte aligned ranges; a job never overwrites bytes of the `back - 1` jobs before it
+        size = lambda q: 0 if (q[0] >> 3) == 0 else ((2 if (q[0] & 3) == 2 else (16 if q[0] & 4 else 8))
+                                                     * ((q[0] >> 3) * 32 + 16) + 127) // 128 * 128
+        jl = jobs.tolist()
+        for j, q in enumerate(jl):
+            assert q[2] % 16 == 0 and q[3] >= 1
+            for b in range(1, min(q[3], len(jl))):
+                o = jl[(j - b) % len(jl)]
+                assert not (q[2] < o[2] + size(o) and o[2] < q[2] + size(q)), (D, H, j, b)
         u = torch.randn(19, D)
         uf = u.flip(1)
         xb, h1, h2 = torch.zeros(19, Dp), torch.zeros(19, H), torch.zeros(19, H)
         x, ld = torch.zeros(19, D), torch.zeros(19)
-        for phase, row0, kch, two in jobs.tolist():
+        for desc, row0, _off, _back in jobs.tolist():
+            phase, two, kch = desc & 3, desc & 4, desc >> 3
             k = kch * 16
             if phase == 0:
                 o = slice(row0, row0 + (16 if two else 8))

@@ -40,6 +40,10 @@ WORKLOADS = {
     # through one x -> z (+ per-sample log-det / bpd) pass followed by one z -> x sampling pass
     "glow_cifar_fwd_inv_k32": dict(image=(32, 32, 3), L=3, hidden=512, tK=32, sK=32, batch=1024, mode="fwd_inv"),
     "glow_celeba_fwd_inv_k32": dict(image=(64, 64, 3), L=4, hidden=512, tK=32, sK=32, batch=256, mode="fwd_inv"),
+    # MAF density evaluation + sampling: 10 MADE layers, D = 63, hidden 512 (parity unpinned, see oracle/maf_oracle.py);
+    # the z -> x pass is the shared-memory-resident sequential inverse (csrc/maf_inverse.cu), one launch per layer
+    "maf_bsds300_fwd_inv_k10": dict(image=(63,), L=1, hidden=512, tK=10, sK=10, batch=65536, is_1d=True, arch="maf",
+                                    mode="fwd_inv", data="bsds300"),
     # secondary workloads (BASELINE configs[1]): BSDS300-shaped tabular KD, D = 63, reference batch 65 536
     # (conf/training/tabular.yaml: nll 0.85, kd 0.05, perceptual-L1 0.1 through the inverse pass)
     "glow1d_bsds300_kd_t5_s3": dict(image=(63,), L=1, hidden=32, s_hidden=16, tK=5, sK=3, batch=65536, is_1d=True,
@@ -117,16 +121,25 @@ def run_fwd_inv(args, wl, cfg_desc, warmup):
     import torch.distributed as dist
     rank, world, device = init_distributed()
     B = args.batch or wl["batch"]
-    H, W, C = wl["image"]
+    maf = wl.get("arch") == "maf"
     torch.manual_seed(42)
-    cfg = glow_cfg(wl["image"], wl["tK"], wl["L"], wl["hidden"])
-    model = create_glow_model(cfg)
-    randomise_zero_params(model, 43, std=0.01)
-    model = model.to(device).eval()
     n_pool = 4
-    host_pool = [synthetic_images(B, wl["image"], 1000 + rank * 100 + i).pin_memory() for i in range(n_pool)]
+    if maf:
+        from nf_distillation_b200.models.maf import create_maf_model
+        cfg = dict(image_shape=[wl["image"][0]], hidden_channels=wl["hidden"], K=wl["tK"])
+        model = create_maf_model(cfg).to(device).eval()
+        host_pool = [torch.randn(B, wl["image"][0], generator=torch.Generator().manual_seed(1000 + rank * 100 + i))
+                     .pin_memory() for i in range(n_pool)]
+        x = torch.empty(B, wl["image"][0], device=device)
+    else:
+        H, W, C = wl["image"]
+        cfg = glow_cfg(wl["image"], wl["tK"], wl["L"], wl["hidden"])
+        model = create_glow_model(cfg)
+        randomise_zero_params(model, 43, std=0.01)
+        model = model.to(device).eval()
+        host_pool = [synthetic_images(B, wl["image"], 1000 + rank * 100 + i).pin_memory() for i in range(n_pool)]
+        x = torch.empty(B, C, H, W, device=device)
     dev_pool = [h.to(device) for h in host_pool]
-    x = torch.empty(B, C, H, W, device=device)
     res = {}
 
     def passes():
@@ -184,21 +197,27 @@ def run_fwd_inv(args, wl, cfg_desc, warmup):
     ms, ms_e2e = t.tolist()
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        from oracle import glow_oracle as O
-        cb = args.cpu_batch
         sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
-        xc = synthetic_images(cb, wl["image"], 7)
-        with torch.no_grad():
-            t0 = time.perf_counter()
-            outs, _ = O.glow_forward(sd, cfg, xc)
-            O.glow_reverse(sd, cfg, outs[-1], 0.0)
-            dt = time.perf_counter() - t0
+        if maf:
+            cb, dt = cpu_maf_fwd_inv(sd, wl, 4096, 1)
+            what = "oracle/maf_oracle.py (paper restatement, parity unpinned)"
+        else:
+            from oracle import glow_oracle as O
+            cb = args.cpu_batch
+            xc = synthetic_images(cb, wl["image"], 7)
+            with torch.no_grad():
+                t0 = time.perf_counter()
+                outs, _ = O.glow_forward(sd, cfg, xc)
+                O.glow_reverse(sd, cfg, outs[-1], 0.0)
+                dt = time.perf_counter() - t0
+            what = "oracle/glow_oracle.py"
         cpu_base = {"value": cb / dt, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
-                    "sample": f"one forward + one inverse pass of {cb} samples (oracle/glow_oracle.py, torch CPU fp32)"}
+                    "sample": f"one forward + one inverse pass of {cb} samples ({what}, torch CPU fp32)"}
     if rank == 0:
         gb = B * world
         cfg_desc.update(per_gpu_batch=B, global_batch=gb, parallelism=f"dp{world}", cuda_graphs=True,
-                        passes="x->z (all outputs, bpd) + z->x (split parts at the prior mean, temperature 0)",
+                        passes=("x->z (all layer outputs, nll) + z->x (sequential inverse of every MADE layer)" if maf else
+                                "x->z (all outputs, bpd) + z->x (split parts at the prior mean, temperature 0)"),
                         l2="activations (~GBs per pass) exceed the 126 MB L2; inputs rotate over 4 batches")
         cfg_desc.pop("student", None); cfg_desc.pop("loss", None); cfg_desc.pop("optimizer", None)
         print(json.dumps({"metric": "fwd_inv_samples_per_sec", "value": gb / (ms * 1e-3), "unit": "samples/s",
@@ -216,6 +235,19 @@ def run_fwd_inv(args, wl, cfg_desc, warmup):
 
 
 # ------------------------------------------------------------------------------------------ CPU arm (oracle port)
+def cpu_maf_fwd_inv(sd, wl, cb, n):
+    """Seconds for one x -> z + one z -> x pass of `cb` samples through the paper restatement (oracle/maf_oracle.py)."""
+    from oracle import maf_oracle as MO
+    D = wl["image"][0]
+    xc = torch.randn(cb, D, generator=torch.Generator().manual_seed(7))
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        for _ in range(n):
+            outs, _ = MO.maf_forward(sd, D, wl["tK"], xc)
+            MO.maf_inverse(sd, D, wl["tK"], outs[-1])
+        return cb, (time.perf_counter() - t0) / n
+
+
 def cpu_kd_step_fn(wl, batch, seed=42):
     """The reference's CPU algorithm for this path, restated in oracle/ (the reference itself is Python and does not
     travel to the GPU box): KD train step = fwd student+teacher, loss, backward, clip 30, Adam."""
@@ -333,7 +365,18 @@ def main():
             return
         cb = args.cpu_batch if not wl.get("is_1d", False) else 65536
         metric = METRIC
-        if wl.get("mode") == "fwd_inv":   # forward + inverse + log-det of the K=32 model through the oracle port
+        if wl.get("mode") == "fwd_inv" and wl.get("arch") == "maf":
+            from nf_distillation_b200.models.maf import create_maf_model
+            metric = "fwd_inv_samples_per_sec"
+            torch.manual_seed(42)
+            model = create_maf_model(dict(image_shape=[wl["image"][0]], hidden_channels=wl["hidden"], K=wl["tK"]))
+            sd = {k: v.detach() for k, v in model.state_dict().items()}
+            n = max(1, min(args.steps, 3))
+            cpu_maf_fwd_inv(sd, wl, 256, 1)
+            cb, dt = cpu_maf_fwd_inv(sd, wl, 4096, n)
+            ms = dt * 1e3
+            value, cores = cb / dt, torch.get_num_threads()
+        elif wl.get("mode") == "fwd_inv":   # forward + inverse + log-det of the K=32 model through the oracle port
             from oracle import glow_oracle as O
             from nf_distillation_b200.models import create_glow_model
             from nf_distillation_b200.train import glow_cfg, randomise_zero_params
@@ -356,6 +399,9 @@ def main():
         else:
             value, ms, cores = run_cpu(wl, cb, max(1, min(args.steps, 3)), 1)
         cfg_desc.update(per_gpu_batch=cb, global_batch=cb, parallelism="cpu")
+        if wl.get("mode") == "fwd_inv":
+            for k in ("student", "loss", "optimizer"):
+                cfg_desc.pop(k, None)
         print(json.dumps({
             "impl": "reference", "metric": metric, "value": value, "unit": "samples/s", "n_gpus": args.gpus,
             "steps": max(1, min(args.steps, 3)), "warmup": 1, "ms_per_step": ms, "higher_is_better": True,

@@ -241,11 +241,17 @@ int nfk_made_inv_update(float* x, void* xb, int Dp, const float* u_in, const flo
  * | second 8-row tile present << 2 | 16-wide k-chunks << 3, first row (phase 2: d), byte offset in the kernel's
  * shared-memory weight ring, jobs back to the latest job occupying any of those bytes}. Call with cap = 0 to size. */
 int nfk_made_inverse_resident_supported(int D, int H, int Dp);
-int nfk_made_inverse_jobs(const int* cnt1, const int* cnt2, int D, int H, int Dp, int* jobs, int cap);
-int nfk_made_inverse_resident(const float* u_in, const void* B1, const void* B2, const void* B3, const float* b1,
-                              const float* b2, const float* b3, const int* jobs, int njobs, float* x,
-                              const float* ld_in, float* ld_out, int B, int D, int H, int Dp, int flip, int mtiles,
-                              void* stream);
+/* PUSH variant of the same launch (B3push != NULL): when the hidden degrees change only on multiples of 8 units and
+ * 2D <= N3p <= 128, the layer-2 activations never reach shared memory — each finished 16-unit tile pair is multiplied
+ * straight into running (mu | alpha) sums kept in registers. B3push = [H/8 + 1][N3p][8] bf16: B3 regrouped per
+ * 8-unit tile (B3push[t][r][k] = B3[r][8t + k]) plus one all-zero tile. The job table must be built with push = 1. */
+int nfk_made_inverse_push_supported(int D, int H, int Dp, int N3p);
+int nfk_made_inverse_jobs(const int* cnt1, const int* cnt2, int D, int H, int Dp, int N3p, int push, int* jobs,
+                          int cap);
+int nfk_made_inverse_resident(const float* u_in, const void* B1, const void* B2, const void* B3, const void* B3push,
+                              int N3p, const float* b1, const float* b2, const float* b3, const int* jobs, int njobs,
+                              float* x, const float* ld_in, float* ld_out, int B, int D, int H, int Dp, int flip,
+                              int mtiles, void* stream);
 
 /* Fused conv#1 -> conv#2 of the coupling network: h2 = relu(relu(col*B1^T + b1)*B2^T + b2) in ONE kernel (CTA
  * pairs; h1 stays in shared memory as the tcgen05 A operand of conv#2). col [M,K1p] bf16, B1 [512,K1p], B2 [512,512]

@@ -91,8 +91,9 @@ SIGNATURES: dict[str, list] = {
     "nfk_made_affine_bwd": [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp],
     "nfk_made_inv_update": [_vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "nfk_made_inverse_resident_supported": [_i, _i, _i],
-    "nfk_made_inverse_jobs": [_vp, _vp, _i, _i, _i, _vp, _i],
-    "nfk_made_inverse_resident": [_vp] * 8 + [_i] + [_vp] * 3 + [_i] * 6 + [_vp],
+    "nfk_made_inverse_push_supported": [_i, _i, _i, _i],
+    "nfk_made_inverse_jobs": [_vp, _vp, _i, _i, _i, _i, _i, _vp, _i],
+    "nfk_made_inverse_resident": [_vp] * 5 + [_i] + [_vp] * 4 + [_i] + [_vp] * 3 + [_i] * 6 + [_vp],
 }
 
 

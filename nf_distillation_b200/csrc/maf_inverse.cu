@@ -41,6 +41,8 @@ struct MiArgs {
   const __nv_bfloat16* B1;      // [H, Dp]   masked, k contiguous
   const __nv_bfloat16* B2;      // [H, H]
   const __nv_bfloat16* B3;      // [N3p, H]  rows: mu_0..mu_{D-1}, alpha_0..alpha_{D-1}
+  const __nv_bfloat16* B3push;  // push kernel only: [H/8 + 1][N3p][8] = B3 regrouped per 8-unit tile (+ one zero tile)
+  int N3p;
   const float *b1, *b2, *b3;    // [H], [H], [>= 2D]
   const int4* jobs;             // [njobs] {phase | second tile << 2 | k-chunks << 3, row0 (phase 2: d), ring offset, back}
   int njobs, ring_bytes;
@@ -385,8 +387,279 @@ __global__ void __launch_bounds__(288) made_inverse_resident_kernel(const MiArgs
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// PUSH variant (degree boundaries on multiples of 8 units, 2D <= 128): the layer-2 activations never reach shared
+// memory. When the layer-2 tile pair of degree d comes out of its accumulators it is packed (bias, ReLU, bf16) straight
+// into an A fragment and multiplied into the running (mu | alpha) sums of ALL outputs, kept in NO x 4 registers per
+// thread for the whole recursion: out[:, r] += h2[:, 16 units] . B3[r, 16 units]^T. Step d then only extracts columns d
+// and D + d. Against the pull kernel above: no h2 slice (19 KB instead of 35 KB per warp -> 9 consumer warps instead
+// of 5), no K = (units of degree <= d) product per step for two useful columns out of eight.
+template <int NO>
+__global__ void __launch_bounds__(384) made_inverse_push_kernel(const MiArgs p) {
+  extern __shared__ __align__(128) unsigned char mi_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, cwarps = (blockDim.x >> 5) - 1;
+  const int D = p.D, H = p.H, Dp = p.Dp;
+  const int ldx = Dp + 8, ldh = H + 8;
+  constexpr int R = 16, N3p = NO * 8;
+  const int per_warp = R * (ldx + ldh) * 2;                  // bytes: x and h1 only
+  uint64_t* full = reinterpret_cast<uint64_t*>(mi_smem + p.ring_bytes);
+  uint64_t* empty = full + MI_SLOTS;
+  uint2* jobs_s = reinterpret_cast<uint2*>(mi_smem + p.ring_bytes + 256);
+  unsigned char* act = mi_smem + p.ring_bytes + 256 + ((p.njobs * 8 + 15) & ~15);
+  const uint32_t ring_s = smem_u32(mi_smem);
+  for (int i = threadIdx.x; i < p.njobs; i += blockDim.x) jobs_s[i] = mi_pack_job(__ldg(p.jobs + i));
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < MI_SLOTS; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], cwarps);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  const int ctiles = (p.B + R * cwarps - 1) / (R * cwarps);
+  const int my_tiles = (ctiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  const int njobs = p.njobs;
+  constexpr uint32_t PUSH_BYTES = 2 * N3p * 16;               // two 8-unit tiles of the push table
+
+  if (warp == cwarps) {
+    // ---------------- producer (see the pull kernel); a layer-2 job also carries its two push-table tiles, placed
+    // after the B2 rows; a (mu_d, alpha_d) job carries nothing
+    int slot = 0, par = 0, q = 0;
+    for (int tile = 0; tile < my_tiles; ++tile) {
+      for (int j = 0; j < njobs; ++j, ++q) {
+        const uint2 cur = jobs_s[j];
+        int back = cur.y >> 16;
+        if (back > MI_SLOTS) back = MI_SLOTS;
+        if (q >= back) {
+          const int ws = slot >= back ? slot - back : slot - back + MI_SLOTS;
+          mbar_wait(&empty[ws], slot >= back ? par : par ^ 1);
+        }
+        const int phase = cur.x & 3, kch = (cur.x >> 3) & 255, row0 = cur.x >> 11;
+        if (phase == 2) {
+          if (lane == 0) mbar_arrive(&full[slot]);
+        } else {
+          const int rows = (cur.x & 4) ? 16 : 8;
+          const uint32_t row_bytes = kch * 32, base = ring_s + (cur.y & 0xffff) * 16;
+          if (lane == 0) mbar_expect_tx(&full[slot], rows * row_bytes + (phase == 1 ? PUSH_BYTES : 0u));
+          __syncwarp();
+          if (lane < rows && row_bytes) {
+            const __nv_bfloat16* src = phase == 0 ? p.B1 + static_cast<size_t>(row0 + lane) * Dp
+                                                  : p.B2 + static_cast<size_t>(row0 + lane) * H;
+            mi_bulk_row(base + lane * (row_bytes + 16), src, row_bytes, &full[slot]);
+          }
+          if (lane == 16 && phase == 1)
+            mi_bulk_row(base + ((16 * (row_bytes + 16) + 127) & ~127u),
+                        p.B3push + static_cast<size_t>(row0 >> 3) * (N3p * 8), PUSH_BYTES, &full[slot]);
+        }
+        if (++slot == MI_SLOTS) { slot = 0; par ^= 1; }
+      }
+    }
+    return;
+  }
+
+  // ---------------- consumers
+  const int g = lane >> 2, t = lane & 3;
+  __nv_bfloat16* xb = reinterpret_cast<__nv_bfloat16*>(act + static_cast<size_t>(warp) * per_warp);
+  __nv_bfloat16* h1 = xb + R * ldx;
+  const int lrow = lane & 15, lcol = (lane >> 4) * 8;
+  const uint32_t xb_lane = smem_u32(xb + lrow * ldx + lcol);
+  const uint32_t h1_lane = smem_u32(h1 + lrow * ldh + lcol);
+  const uint32_t b_row = (lane & 7) + ((lane >> 4) << 3), b_col = ((lane >> 3) & 1) * 16;
+  // push-table ldmatrix.x4: matrices = (n-tile n, tile block 0), (n, block 1), (n + 1, block 0), (n + 1, block 1);
+  // a tile block is [N3p outputs][8 units] dense: 8 rows x 16 bytes = all 32 banks once
+  const uint32_t pb_lane = ((lane >> 3) & 1) * (N3p * 16) + (((lane >> 4) << 3) + (lane & 7)) * 16;
+
+  auto fetch_bias = [&](uint32_t jd) -> float4 {
+    const int phase = jd & 3, row0 = jd >> 11;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (phase < 2) {
+      const float* bias = (phase == 0 ? p.b1 : p.b2) + row0 + 2 * t;
+      v.x = __ldg(bias);
+      v.y = __ldg(bias + 1);
+      if (jd & 4) {
+        v.z = __ldg(bias + 8);
+        v.w = __ldg(bias + 9);
+      }
+    } else {
+      v.x = __ldg(p.b3 + row0);
+      v.y = __ldg(p.b3 + D + row0);
+    }
+    return v;
+  };
+
+  int slot = 0, par = 0;
+  for (int tile = 0; tile < my_tiles; ++tile) {
+    const long long base = ((static_cast<long long>(tile) * gridDim.x + blockIdx.x) * cwarps + warp) * R;
+    float ldacc[2], unext[2];
+    const float* urow[2];
+    float out[NO][4];            // running (mu | alpha) sums: C fragments of the [16 samples x N3p] output
+#pragma unroll
+    for (int n = 0; n < NO; ++n)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) out[n][e] = 0.f;
+    {
+      uint4* z = reinterpret_cast<uint4*>(xb);
+      const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+      for (int i = lane; i < per_warp / 16; i += 32) z[i] = zero;
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const long long b = base + g + 8 * hh;
+        ldacc[hh] = 0.f;
+        urow[hh] = (t == 0 && b < p.B) ? p.u_in + b * D : nullptr;
+        unext[hh] = urow[hh] ? __ldg(urow[hh] + (p.flip ? D - 1 : 0)) : 0.f;
+      }
+      __syncwarp();
+    }
+    int dcur = 0;                // degree of the hidden units being finalised = index of the next x to come
+    uint2 jd = jobs_s[0];
+    float4 bnext = fetch_bias(jd.x);
+    for (int j = 0; j < njobs; ++j) {
+      const uint32_t cur = jd.x;
+      const float4 bv = bnext;
+      const int phase = cur & 3, kch = (cur >> 3) & 255, row0 = cur >> 11;
+      const uint32_t job_s = ring_s + (jd.y & 0xffff) * 16;
+      if (j + 1 < njobs) {
+        jd = jobs_s[j + 1];
+        bnext = fetch_bias(jd.x);
+      }
+
+      if (phase < 2) {
+        const bool l1 = phase == 0, two = (cur & 4) != 0;
+        uint32_t a_addr = l1 ? xb_lane : h1_lane;
+        uint32_t b_addr = job_s + b_row * (kch * 32 + 16) + b_col;
+        float acc[2][2][4];      // [n-tile][even / odd k-chunk chain]
+#pragma unroll
+        for (int n = 0; n < 2; ++n)
+#pragma unroll
+          for (int c = 0; c < 2; ++c)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[n][c][e] = 0.f;
+        mbar_wait(&full[slot], par);
+        uint32_t a0[4], a1[4], b0[4], b1[4];
+        if (kch > 0) {
+          mi_ldsm_x4<0>(b_addr, b0);
+          mi_ldsm_x4<0>(a_addr, a0);
+        }
+        int kc = kch;
+        for (; kc >= 2; kc -= 2, a_addr += 64, b_addr += 64) {
+          mi_ldsm_x4<32>(b_addr, b1);
+          mi_ldsm_x4<32>(a_addr, a1);
+          mi_mma(acc[0][0], a0, b0[0], b0[1]);
+          mi_mma(acc[1][0], a0, b0[2], b0[3]);
+          if (kc > 2) {
+            mi_ldsm_x4<64>(b_addr, b0);
+            mi_ldsm_x4<64>(a_addr, a0);
+          }
+          mi_mma(acc[0][1], a1, b1[0], b1[1]);
+          mi_mma(acc[1][1], a1, b1[2], b1[3]);
+        }
+        if (kc) {
+          mi_mma(acc[0][0], a0, b0[0], b0[1]);
+          mi_mma(acc[1][0], a0, b0[2], b0[3]);
+        }
+        // bias + ReLU + bf16: rows g / g + 8, columns row0 + 2t, + 1 (tile 0) and row0 + 8 + 2t, + 1 (tile 1)
+        uint32_t hA[4];
+        hA[0] = mi_pack_relu(acc[0][0][0] + acc[0][1][0] + bv.x, acc[0][0][1] + acc[0][1][1] + bv.y);
+        hA[1] = mi_pack_relu(acc[0][0][2] + acc[0][1][2] + bv.x, acc[0][0][3] + acc[0][1][3] + bv.y);
+        hA[2] = two ? mi_pack_relu(acc[1][0][0] + acc[1][1][0] + bv.z, acc[1][0][1] + acc[1][1][1] + bv.w) : 0u;
+        hA[3] = two ? mi_pack_relu(acc[1][0][2] + acc[1][1][2] + bv.z, acc[1][0][3] + acc[1][1][3] + bv.w) : 0u;
+        if (l1) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty[slot]);
+          __nv_bfloat16* o = h1 + row0 + 2 * t;
+          *reinterpret_cast<uint32_t*>(o + g * ldh) = hA[0];
+          *reinterpret_cast<uint32_t*>(o + (g + 8) * ldh) = hA[1];
+          if (two) {
+            *reinterpret_cast<uint32_t*>(o + g * ldh + 8) = hA[2];
+            *reinterpret_cast<uint32_t*>(o + (g + 8) * ldh + 8) = hA[3];
+          }
+        } else {
+          // push: these 16 layer-2 units (degree dcur) feed outputs mu_i, alpha_i for i >= dcur only
+          // (hA is exactly the A fragment of a 16 x 16 tile: C fragments of two adjacent 8-column tiles)
+          const uint32_t pb = job_s + ((16 * (kch * 32 + 16) + 127) & ~127) + pb_lane;
+#pragma unroll
+          for (int n = 0; n < NO; n += 2) {
+            const bool live0 = (8 * n + 7 >= dcur && 8 * n < D) || (8 * n + 7 >= D + dcur && 8 * n < 2 * D);
+            const bool live1 = (8 * n + 15 >= dcur && 8 * n + 8 < D) || (8 * n + 15 >= D + dcur && 8 * n + 8 < 2 * D);
+            if (live0 || live1) {
+              uint32_t w[4];
+              mi_ldsm_x4<0>(pb + n * 128, w);
+              if (live0) mi_mma(out[n], hA, w[0], w[1]);
+              if (live1) mi_mma(out[n + 1], hA, w[2], w[3]);
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty[slot]);
+        }
+        __syncwarp();
+      } else {
+        // (mu_d, alpha_d) = columns d and D + d of the running sums
+        const int d = row0;
+        dcur = d + 1;
+        float uv[2];
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          uv[hh] = unext[hh];
+          unext[hh] = (urow[hh] && d + 1 < D) ? __ldg(urow[hh] + (p.flip ? D - 2 - d : d + 1)) : 0.f;
+        }
+        mbar_wait(&full[slot], par);                           // (empty job: keeps the slot sequence in step)
+        __syncwarp();                                          // every lane has seen the phase before the slot is released
+        if (lane == 0) mbar_arrive(&empty[slot]);
+        const int nm = d >> 3, cm = d & 7, na = (D + d) >> 3, ca = (D + d) & 7;
+        float m0 = 0.f, m1 = 0.f, l0 = 0.f, l1v = 0.f;
+#pragma unroll
+        for (int n = 0; n < NO; ++n) {
+          if (n == nm) {
+            m0 = (cm & 1) ? out[n][1] : out[n][0];
+            m1 = (cm & 1) ? out[n][3] : out[n][2];
+          }
+          if (n == na) {
+            l0 = (ca & 1) ? out[n][1] : out[n][0];
+            l1v = (ca & 1) ? out[n][3] : out[n][2];
+          }
+        }
+        const int srcm = (lane & ~3) | (cm >> 1), srca = (lane & ~3) | (ca >> 1);
+        m0 = __shfl_sync(0xffffffffu, m0, srcm);
+        m1 = __shfl_sync(0xffffffffu, m1, srcm);
+        l0 = __shfl_sync(0xffffffffu, l0, srca);
+        l1v = __shfl_sync(0xffffffffu, l1v, srca);
+        if (t == 0) {
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            const float mu = (hh ? m1 : m0) + bv.x, al = (hh ? l1v : l0) + bv.y;
+            const float xv = uv[hh] * expf(al) + mu;
+            if (urow[hh]) p.x[(urow[hh] - p.u_in) + d] = xv;
+            xb[(g + 8 * hh) * ldx + d] = __float2bfloat16_rn(xv);
+            ldacc[hh] += al;
+          }
+        }
+        __syncwarp();
+      }
+      if (++slot == MI_SLOTS) { slot = 0; par ^= 1; }
+    }
+    if (t == 0 && p.ld_out) {
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const long long b = base + g + 8 * hh;
+        if (b < p.B) p.ld_out[b] = (p.ld_in ? p.ld_in[b] : 0.f) + ldacc[hh];
+      }
+    }
+  }
+}
+
 static inline int mi_per_warp_bytes(int mt, int H, int Dp) { return mt * 16 * ((Dp + 8) + 2 * (H + 8)) * 2; }
-static inline int mi_job_bytes(int rows, int kch) { return kch ? ((rows * (kch * 32 + 16) + 127) & ~127) : 0; }
+static inline int mi_per_warp_bytes_push(int H, int Dp) { return 16 * ((Dp + 8) + (H + 8)) * 2; }
+static inline int mi_rows_bytes(int rows, int kch) { return (rows * (kch * 32 + 16) + 127) & ~127; }
+// bytes of a job in the weight ring. pull: its rows (nothing for kch == 0). push: layer-1 job = its rows, layer-2 job =
+// a 16-row block + two push-table tiles, (mu, alpha) job = nothing.
+static inline int mi_job_bytes(int desc, int push, int N3p) {
+  const int phase = desc & 3, kch = desc >> 3, rows = phase == 2 ? 2 : ((desc & 4) ? 16 : 8);
+  if (!push) return kch ? mi_rows_bytes(rows, kch) : 0;
+  if (phase == 2) return 0;
+  if (phase == 0) return mi_rows_bytes(rows, kch);
+  return mi_rows_bytes(16, kch) + 2 * N3p * 16;
+}
 static inline int mi_side_bytes(int njobs) { return 256 + ((njobs * 8 + 15) & ~15); }   // barriers + packed job table
 
 }  // namespace nfk
@@ -396,13 +669,16 @@ using namespace nfk;
 static constexpr int MI_SMEM_MAX = 227 * 1024;
 
 // Weight ring size for a layer shape: what is left after the barriers, the job table and as many one-tile warps as fit
-// next to a ring of two largest jobs (so that at least two jobs can be in flight), at most 8 warps.
-static int mi_ring_bytes(int H, int Dp, int njobs) {
-  const int biggest = mi_job_bytes(16, (H > Dp ? H : Dp) / 16);
-  const int avail = MI_SMEM_MAX - mi_side_bytes(njobs), per_warp = mi_per_warp_bytes(1, H, Dp);
+// next to a ring of two largest jobs (so that at least two jobs can be in flight).
+static int mi_ring_bytes(int H, int Dp, int njobs, int push, int N3p) {
+  const int kmax = (H > Dp ? H : Dp) / 16;
+  const int biggest = push ? mi_rows_bytes(16, kmax) + 2 * N3p * 16 : mi_rows_bytes(16, kmax);
+  const int avail = MI_SMEM_MAX - mi_side_bytes(njobs);
+  const int per_warp = push ? mi_per_warp_bytes_push(H, Dp) : mi_per_warp_bytes(1, H, Dp);
+  const int max_warps = push ? 11 : 8;
   int warps = (avail - 2 * biggest) / per_warp;
   if (warps < 1) return -1;
-  if (warps > 8) warps = 8;
+  if (warps > max_warps) warps = max_warps;
   int ring = (avail - warps * per_warp) & ~127;
   if (ring > (1 << 20) - 128) ring = (1 << 20) - 128;   // offsets are stored in 16 bits of 16-byte units
   return ring;
@@ -411,14 +687,22 @@ static int mi_ring_bytes(int H, int Dp, int njobs) {
 extern "C" int nfk_made_inverse_resident_supported(int D, int H, int Dp) {
   if (D <= 0 || H <= 0 || H % 64 || Dp % 64 || Dp < D || H > 255 * 16 || Dp > 255 * 16) return 0;
   // (the packed job table also lives in shared memory: at most 4 D + H / 8 jobs of 8 bytes)
-  return mi_ring_bytes(H, Dp, 4 * D + H / 8) > 0 ? 1 : 0;
+  return mi_ring_bytes(H, Dp, 4 * D + H / 8, 0, 0) > 0 ? 1 : 0;
+}
+
+extern "C" int nfk_made_inverse_push_supported(int D, int H, int Dp, int N3p) {
+  if (!nfk_made_inverse_resident_supported(D, H, Dp)) return 0;
+  if ((N3p != 64 && N3p != 128) || 2 * D > N3p) return 0;
+  return mi_ring_bytes(H, Dp, 4 * D + H / 8, 1, N3p) > 0 ? 1 : 0;
 }
 
 // Host-side: the job stream of one sample tile from the degree counts (cnt[d] = units with degree <= d, d = 0..D),
 // each job with its byte range in the weight ring and the distance back to the latest job that used those bytes.
-extern "C" int nfk_made_inverse_jobs(const int* cnt1, const int* cnt2, int D, int H, int Dp, int* jobs, int cap) {
+extern "C" int nfk_made_inverse_jobs(const int* cnt1, const int* cnt2, int D, int H, int Dp, int N3p, int push,
+                                     int* jobs, int cap) {
   if (!cnt1 || !cnt2 || D <= 0 || cap < 0 || (cap > 0 && !jobs)) return NFK_ERR_ARG;
-  if (!nfk_made_inverse_resident_supported(D, H, Dp)) return NFK_ERR_SHAPE;
+  if (!(push ? nfk_made_inverse_push_supported(D, H, Dp, N3p) : nfk_made_inverse_resident_supported(D, H, Dp)))
+    return NFK_ERR_SHAPE;
   int n = 0;
   auto put = [&](int phase, int row0, int kch, int two) {
     if (n < cap) { jobs[4 * n] = phase | (two << 2) | (kch << 3); jobs[4 * n + 1] = row0; jobs[4 * n + 2] = 0; jobs[4 * n + 3] = 0; }
@@ -427,36 +711,34 @@ extern "C" int nfk_made_inverse_jobs(const int* cnt1, const int* cnt2, int D, in
   for (int d = 0; d < D; ++d) {
     const int c1p = d ? cnt1[d - 1] : 0, c1 = cnt1[d], c2p = d ? cnt2[d - 1] : 0, c2 = cnt2[d];
     if (c1 < c1p || c2 < c2p || c1p < 0 || c2p < 0 || c1 > H || c2 > H) return NFK_ERR_ARG;
+    if (push && ((c1 | c2) & 7)) return NFK_ERR_SHAPE;   // the push kernel needs degree boundaries on whole 8-unit tiles
     if (d > 0) {
       if (c1 > c1p)   // layer-1 units of degree d: inputs x_0 .. x_{d-1}
         for (int nt = c1p >> 3, hi = (c1 + 7) >> 3; nt < hi; nt += 2) put(0, nt * 8, (d + 15) >> 4, nt + 1 < hi);
       if (c2 > c2p)   // layer-2 units of degree d: layer-1 units of degree <= d
         for (int nt = c2p >> 3, hi = (c2 + 7) >> 3; nt < hi; nt += 2) put(1, nt * 8, (c1 + 15) >> 4, nt + 1 < hi);
     }
-    put(2, d, (c2 + 15) >> 4, 0);   // (mu_d, alpha_d): layer-2 units of degree <= d
+    put(2, d, push ? 0 : (c2 + 15) >> 4, 0);   // (mu_d, alpha_d): layer-2 units of degree <= d (push: already summed)
   }
   if (n > cap) return n;            // sizing call (or a short buffer): offsets need the whole table
   // ring placement: consecutive byte ranges, wrapping to 0 when a job does not fit before the end; every tile replays
   // the same offsets, so `back` looks through the cyclic job order (a job of the previous tile counts)
-  const int ring = mi_ring_bytes(H, Dp, n);
+  const int ring = mi_ring_bytes(H, Dp, n, push, N3p);
   if (ring <= 0) return NFK_ERR_SHAPE;
   int cur = 0;
   for (int j = 0; j < n; ++j) {
-    const int d = jobs[4 * j], phase = d & 3, kch = d >> 3;
-    const int size = mi_job_bytes(phase == 2 ? 2 : ((d & 4) ? 16 : 8), kch);
+    const int size = mi_job_bytes(jobs[4 * j], push, N3p);
     if (size > ring) return NFK_ERR_SHAPE;
     if (cur + size > ring) cur = 0;
     jobs[4 * j + 2] = cur;
     cur += size;
   }
   for (int j = 0; j < n; ++j) {
-    const int d = jobs[4 * j], phase = d & 3, kch = d >> 3;
-    const int lo = jobs[4 * j + 2], hi = lo + mi_job_bytes(phase == 2 ? 2 : ((d & 4) ? 16 : 8), kch);
+    const int lo = jobs[4 * j + 2], hi = lo + mi_job_bytes(jobs[4 * j], push, N3p);
     int back = n;                                  // nothing overlaps within a whole period: only the slot binds
     for (int b = 1; b < n && hi > lo; ++b) {
       const int i = ((j - b) % n + n) % n;
-      const int di = jobs[4 * i], lo2 = jobs[4 * i + 2];
-      const int hi2 = lo2 + mi_job_bytes((di & 3) == 2 ? 2 : ((di & 4) ? 16 : 8), di >> 3);
+      const int lo2 = jobs[4 * i + 2], hi2 = lo2 + mi_job_bytes(jobs[4 * i], push, N3p);
       if (lo < hi2 && lo2 < hi) { back = b; break; }
     }
     jobs[4 * j + 3] = back;
@@ -467,7 +749,7 @@ extern "C" int nfk_made_inverse_jobs(const int* cnt1, const int* cnt2, int D, in
 template <int MT>
 static int mi_launch(MiArgs p, cudaStream_t st) {
   const int per_warp = mi_per_warp_bytes(MT, p.H, p.Dp);
-  p.ring_bytes = mi_ring_bytes(p.H, p.Dp, p.njobs);
+  p.ring_bytes = mi_ring_bytes(p.H, p.Dp, p.njobs, 0, 0);
   if (p.ring_bytes <= 0) return NFK_ERR_SHAPE;
   const int fixed = p.ring_bytes + mi_side_bytes(p.njobs);
   int warps = (MI_SMEM_MAX - fixed) / per_warp;
@@ -488,13 +770,39 @@ static int mi_launch(MiArgs p, cudaStream_t st) {
   return cudaGetLastError() == cudaSuccess ? NFK_OK : NFK_ERR_LAUNCH;
 }
 
+template <int NO>
+static int mi_launch_push(MiArgs p, cudaStream_t st) {
+  const int per_warp = mi_per_warp_bytes_push(p.H, p.Dp);
+  p.ring_bytes = mi_ring_bytes(p.H, p.Dp, p.njobs, 1, p.N3p);
+  if (p.ring_bytes <= 0) return NFK_ERR_SHAPE;
+  const int fixed = p.ring_bytes + mi_side_bytes(p.njobs);
+  int warps = (MI_SMEM_MAX - fixed) / per_warp;
+  if (warps > 11) warps = 11;
+  if (warps < 1) return NFK_ERR_SHAPE;
+  const int wtiles = (p.B + 15) / 16;
+  if (warps > wtiles) warps = wtiles;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int smem = fixed + warps * per_warp;
+  if (cudaFuncSetAttribute(made_inverse_push_kernel<NO>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) !=
+      cudaSuccess)
+    return NFK_ERR_LAUNCH;
+  int grid = (wtiles + warps - 1) / warps;
+  if (grid > sms) grid = sms;
+  made_inverse_push_kernel<NO><<<grid, (warps + 1) * 32, smem, st>>>(p);
+  return cudaGetLastError() == cudaSuccess ? NFK_OK : NFK_ERR_LAUNCH;
+}
+
 extern "C" int nfk_made_inverse_resident(const float* u_in, const void* B1, const void* B2, const void* B3,
-                                         const float* b1, const float* b2, const float* b3, const int* jobs,
-                                         int njobs, float* x, const float* ld_in, float* ld_out, int B, int D, int H,
-                                         int Dp, int flip, int mtiles, void* stream) {
+                                         const void* B3push, int N3p, const float* b1, const float* b2,
+                                         const float* b3, const int* jobs, int njobs, float* x, const float* ld_in,
+                                         float* ld_out, int B, int D, int H, int Dp, int flip, int mtiles,
+                                         void* stream) {
   if (B <= 0 || njobs <= 0 || njobs > (1 << 20) || !nfk_made_inverse_resident_supported(D, H, Dp) || mtiles < 0 ||
       mtiles > 2)
     return NFK_ERR_SHAPE;
+  if (B3push && !nfk_made_inverse_push_supported(D, H, Dp, N3p)) return NFK_ERR_SHAPE;
   if (!u_in || !B1 || !B2 || !B3 || !b1 || !b2 || !b3 || !jobs || !x) return NFK_ERR_ARG;
   if (reinterpret_cast<uintptr_t>(jobs) & 15) return NFK_ERR_ARG;
   MiArgs p;
@@ -502,13 +810,15 @@ extern "C" int nfk_made_inverse_resident(const float* u_in, const void* B1, cons
   p.B1 = static_cast<const __nv_bfloat16*>(B1);
   p.B2 = static_cast<const __nv_bfloat16*>(B2);
   p.B3 = static_cast<const __nv_bfloat16*>(B3);
+  p.B3push = static_cast<const __nv_bfloat16*>(B3push); p.N3p = N3p;
   p.b1 = b1; p.b2 = b2; p.b3 = b3;
   p.jobs = reinterpret_cast<const int4*>(jobs); p.njobs = njobs; p.ring_bytes = 0;
   p.x = x; p.ld_in = ld_in; p.ld_out = ld_out;
   p.B = B; p.D = D; p.H = H; p.Dp = Dp; p.flip = flip;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  // one 16-sample tile per warp leaves room for the most warps (latency hiding); two halve the B-operand reads
-  const int ring = mi_ring_bytes(H, Dp, njobs);
+  if (B3push) return N3p == 128 ? mi_launch_push<16>(p, st) : mi_launch_push<8>(p, st);
+  // pull kernel: one 16-sample tile per warp leaves room for the most warps; two halve the B-operand reads
+  const int ring = mi_ring_bytes(H, Dp, njobs, 0, 0);
   if (ring <= 0) return NFK_ERR_SHAPE;
   int mt = mtiles == 0 ? 1 : mtiles;
   if (mt == 2 && ring + mi_side_bytes(njobs) + mi_per_warp_bytes(2, H, Dp) > MI_SMEM_MAX) mt = 1;

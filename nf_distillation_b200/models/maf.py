@@ -21,9 +21,14 @@ BF16, F32 = torch.bfloat16, torch.float32
 
 
 def hidden_degrees(D: int, H: int) -> torch.Tensor:
-    """Sorted degrees in [1, D-1], each value ~H/(D-1) times (D == 1 degenerates to all ones)."""
+    """Sorted degrees in [1, D-1], each value ~H/(D-1) times (D == 1 degenerates to all ones). When H is a multiple of
+    8 the degree changes only on multiples of 8 units (whole MMA column tiles), which is what lets the inverse kernel
+    feed a finished layer-2 tile straight from its accumulators into the output sums (csrc/maf_inverse.cu, push)."""
     if D <= 1:
         return torch.ones(H, dtype=torch.int32)
+    if H % 8 == 0:
+        tiles = H // 8
+        return (torch.arange(tiles, dtype=torch.int64) * (D - 1) // tiles + 1).repeat_interleave(8).to(torch.int32)
     return (torch.arange(H, dtype=torch.int64) * (D - 1) // H + 1).to(torch.int32)
 
 
@@ -122,24 +127,41 @@ class MADE(nn.Module):
         self._ranges_t = _kb_ranges_t(deg, deg, self.bn)
         self._cache = None
         self._job_cache = None
+        self._push_cache = None
+        self.push_inverse = True         # False: the pull kernel (h2 kept in shared memory) even for aligned degrees
         self.resident_inverse = True     # False: the D-pass GEMM inverse (kept as the cross-check in the tests)
         self.resident_mtiles = 0         # 16-sample tiles per warp in the resident inverse (0 = chosen by the library)
 
     def _inverse_jobs(self, dev):
-        """Job table of the resident inverse (ops.made_inverse_jobs) on `dev`, from cnt[d] = number of hidden units
-        with degree <= d (d = 0..D); None when the degrees are not sorted ascending (the resident inverse walks the
-        units in degree order)."""
-        key = (self.deg1.data_ptr(), self.deg1._version, self.deg2.data_ptr(), self.deg2._version, str(dev))
+        """(job table on `dev`, push?) of the resident inverse (ops.made_inverse_jobs), from cnt[d] = number of hidden
+        units with degree <= d (d = 0..D); (None, False) when the degrees are not sorted ascending (the resident
+        inverse walks the units in degree order). push = the degrees change on whole 8-unit tiles and 2D <= 128."""
+        key = (self.deg1.data_ptr(), self.deg1._version, self.deg2.data_ptr(), self.deg2._version, str(dev),
+               self.push_inverse)
         if self._job_cache is None or self._job_cache[0] != key:
             d1, d2 = self.deg1.detach().cpu().long(), self.deg2.detach().cpu().long()
             ok = bool((d1[1:] >= d1[:-1]).all() and (d2[1:] >= d2[:-1]).all() and d1.min() >= 1 and d2.min() >= 1)
-            jobs = None
+            jobs, push = None, False
             if ok:
                 edges = torch.arange(self.D + 1)
                 cnt1, cnt2 = ((d[None, :] <= edges[:, None]).sum(1) for d in (d1, d2))
-                jobs = ops.made_inverse_jobs(cnt1, cnt2, self.D, self.H, self.Dp).to(dev)
-            self._job_cache = (key, jobs)
+                if self.push_inverse and ops.made_inverse_push_supported(self.D, self.H, self.Dp, self.N3p):
+                    jobs = ops.made_inverse_jobs(cnt1, cnt2, self.D, self.H, self.Dp, self.N3p, push=True)
+                    push = jobs is not None
+                if jobs is None:
+                    jobs = ops.made_inverse_jobs(cnt1, cnt2, self.D, self.H, self.Dp)
+                jobs = jobs.to(dev)
+            self._job_cache = (key, (jobs, push))
         return self._job_cache[1]
+
+    def _push_table(self, B3):
+        """B3 [N3p, H] regrouped per 8-unit tile: [H/8 + 1, N3p, 8] (last tile zero), cached with the operands."""
+        key = (B3.data_ptr(), B3._version)
+        if self._push_cache is None or self._push_cache[0] != key:
+            tab = torch.zeros(self.H // 8 + 1, self.N3p, 8, device=B3.device, dtype=BF16)
+            tab[:-1] = B3.view(self.N3p, self.H // 8, 8).permute(1, 0, 2)
+            self._push_cache = (key, tab, B3)   # (keeps B3 alive so the pointer in the key cannot be reused)
+        return self._push_cache[1]
 
     def _params(self):
         return (self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias, self.fc3.weight, self.fc3.bias)
@@ -236,14 +258,15 @@ class MADE(nn.Module):
             raise NotImplementedError("gradients through the sequential MADE inverse are not built")
         u_in = input.contiguous()
         ops_ = self._cached_operands()
-        jobs = self._inverse_jobs(u_in.device)
+        jobs, push = self._inverse_jobs(u_in.device)
         if jobs is not None and self.resident_inverse and ops.made_inverse_resident_supported(self.D, self.H, self.Dp):
             # ONE launch: every hidden unit finalised once, in degree order, activations resident in shared memory
             x = torch.empty_like(u_in)
             ld_out = torch.empty(Bn, device=x.device, dtype=F32) if want else None
             ops.made_inverse_resident(u_in, ops_[0], ops_[2], ops_[4], params[1].detach(), params[3].detach(),
                                       ops_[6], jobs, x, ld.contiguous() if want else None, ld_out, Bn,
-                                      self.D, self.H, self.Dp, self.flip, self.resident_mtiles)
+                                      self.D, self.H, self.Dp, self.flip, self.resident_mtiles,
+                                      B3push=self._push_table(ops_[4]) if push else None, N3p=self.N3p)
             return x, ld_out
         # fallback (unsorted degrees / shapes the resident kernel does not take): D passes of the three GEMMs,
         # activations in HBM / L2, one column of x fixed per pass

@@ -342,26 +342,35 @@ def made_inverse_resident_supported(D, H, Dp) -> bool:
     return bool(LIB.nfk_made_inverse_resident_supported(D, H, Dp))
 
 
-def made_inverse_jobs(cnt1, cnt2, D, H, Dp):
+def made_inverse_push_supported(D, H, Dp, N3p) -> bool:
+    return bool(LIB.nfk_made_inverse_push_supported(D, H, Dp, N3p))
+
+
+def made_inverse_jobs(cnt1, cnt2, D, H, Dp, N3p=0, push=False):
     """Host-side job table of the resident inverse from the degree counts (CPU int32 tensors [D+1]) -> [njobs, 4]:
-    (phase | two << 2 | k-chunks << 3, first row, weight-ring byte offset, jobs back to the ring bytes' last user)."""
+    (phase | two << 2 | k-chunks << 3, first row, weight-ring byte offset, jobs back to the ring bytes' last user).
+    Returns None when push=True and the degrees do not change on whole 8-unit tiles."""
     import torch
     cnt1 = cnt1.to(torch.int32).contiguous().cpu()
     cnt2 = cnt2.to(torch.int32).contiguous().cpu()
-    n = LIB.nfk_made_inverse_jobs(cnt1.data_ptr(), cnt2.data_ptr(), D, H, Dp, None, 0)
+    n = LIB.nfk_made_inverse_jobs(cnt1.data_ptr(), cnt2.data_ptr(), D, H, Dp, N3p, int(push), None, 0)
+    if push and n == -1:     # NFK_ERR_SHAPE: not tile-aligned / not supported -> caller uses the pull kernel
+        return None
     if n <= 0:
         check(n if n < 0 else -1, "nfk_made_inverse_jobs")
     jobs = torch.empty(n, 4, dtype=torch.int32)
-    check(0 if LIB.nfk_made_inverse_jobs(cnt1.data_ptr(), cnt2.data_ptr(), D, H, Dp, jobs.data_ptr(), n) == n else -1,
-          "nfk_made_inverse_jobs")
+    check(0 if LIB.nfk_made_inverse_jobs(cnt1.data_ptr(), cnt2.data_ptr(), D, H, Dp, N3p, int(push), jobs.data_ptr(),
+                                         n) == n else -1, "nfk_made_inverse_jobs")
     return jobs
 
 
-def made_inverse_resident(u_in, B1, B2, B3, b1, b2, b3, jobs, x, ld_in, ld_out, B, D, H, Dp, flip, mtiles=0):
-    """The whole sequential inverse of one MADE layer in one launch (activations resident in shared memory)."""
+def made_inverse_resident(u_in, B1, B2, B3, b1, b2, b3, jobs, x, ld_in, ld_out, B, D, H, Dp, flip, mtiles=0,
+                          B3push=None, N3p=0):
+    """The whole sequential inverse of one MADE layer in one launch (activations resident in shared memory).
+    B3push given: the push kernel (jobs built with push=True)."""
     _count()
-    check(LIB.nfk_made_inverse_resident(_p(u_in), _p(B1), _p(B2), _p(B3), _p(b1), _p(b2), _p(b3), _p(jobs),
-                                        jobs.shape[0], _p(x), _p(ld_in), _p(ld_out), B, D, H, Dp, int(flip),
+    check(LIB.nfk_made_inverse_resident(_p(u_in), _p(B1), _p(B2), _p(B3), _p(B3push), N3p, _p(b1), _p(b2), _p(b3),
+                                        _p(jobs), jobs.shape[0], _p(x), _p(ld_in), _p(ld_out), B, D, H, Dp, int(flip),
                                         int(mtiles), _st()), "nfk_made_inverse_resident")
 
 

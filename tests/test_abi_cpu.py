@@ -172,37 +172,58 @@ def test_resident_inverse_job_table_reproduces_the_sequential_inverse():
         W1p[:, :D] = W1
         edges = torch.arange(D + 1)
         cnt = (deg.long()[None, :] <= edges[:, None]).sum(1)
-        jobs = ops.made_inverse_jobs(cnt, cnt, D, H, Dp)
-        assert jobs.shape[1] == 4 and ((jobs[:, 0] & 3) == 2).sum().item() == D
-        # ring plan: 16-byte aligned ranges; a job never overwrites bytes of the `back - 1` jobs before it
-        size = lambda q: 0 if (q[0] >> 3) == 0 else ((2 if (q[0] & 3) == 2 else (16 if q[0] & 4 else 8))
-                                                     * ((q[0] >> 3) * 32 + 16) + 127) // 128 * 128
-        jl = jobs.tolist()
-        for j, q in enumerate(jl):
-            assert q[2] % 16 == 0 and q[3] >= 1
-            for b in range(1, min(q[3], len(jl))):
-                o = jl[(j - b) % len(jl)]
-                assert not (q[2] < o[2] + size(o) and o[2] < q[2] + size(q)), (D, H, j, b)
-        u = torch.randn(19, D)
-        uf = u.flip(1)
-        xb, h1, h2 = torch.zeros(19, Dp), torch.zeros(19, H), torch.zeros(19, H)
-        x, ld = torch.zeros(19, D), torch.zeros(19)
-        for desc, row0, _off, _back in jobs.tolist():
-            phase, two, kch = desc & 3, desc & 4, desc >> 3
-            k = kch * 16
-            if phase == 0:
+        N3p = (2 * D + 63) // 64 * 64
+        size_rows = lambda rows, kch: (rows * (kch * 32 + 16) + 127) // 128 * 128
+        for push in (False, True):
+            jobs = ops.made_inverse_jobs(cnt, cnt, D, H, Dp, N3p, push=push)
+            if push and (2 * D > 128):
+                assert jobs is None                       # more than 16 output tiles: pull kernel only
+                continue
+            assert jobs.shape[1] == 4 and ((jobs[:, 0] & 3) == 2).sum().item() == D
+
+            def size(q):
+                phase, kch, rows = q[0] & 3, q[0] >> 3, (2 if (q[0] & 3) == 2 else (16 if q[0] & 4 else 8))
+                if not push:
+                    return size_rows(rows, kch) if kch else 0
+                return 0 if phase == 2 else (size_rows(rows, kch) if phase == 0 else size_rows(16, kch) + 2 * N3p * 16)
+            # ring plan: 16-byte aligned ranges; a job never overwrites bytes of the `back - 1` jobs before it
+            jl = jobs.tolist()
+            for j, q in enumerate(jl):
+                assert q[2] % 16 == 0 and q[3] >= 1
+                for b in range(1, min(q[3], len(jl)) if size(q) else 0):
+                    o = jl[(j - b) % len(jl)]
+                    assert not (q[2] < o[2] + size(o) and o[2] < q[2] + size(q)), (D, H, j, b)
+            # replay: pull = h2 kept, (mu, alpha) recomputed from it per step; push = outputs accumulated as tiles finish
+            u = torch.randn(19, D)
+            uf = u.flip(1)
+            xb, h1, h2 = torch.zeros(19, Dp), torch.zeros(19, H), torch.zeros(19, H)
+            out = torch.zeros(19, 2 * D)
+            x, ld = torch.zeros(19, D), torch.zeros(19)
+            for desc, row0, _off, _back in jl:
+                phase, two, kch = desc & 3, desc & 4, desc >> 3
+                k = kch * 16
                 o = slice(row0, row0 + (16 if two else 8))
-                h1[:, o] = torch.relu(xb[:, :k] @ W1p[o, :k].T + sd[pre + "fc1.bias"][o])
-            elif phase == 1:
-                o = slice(row0, row0 + (16 if two else 8))
-                h2[:, o] = torch.relu(h1[:, :k] @ W2[o, :k].T + sd[pre + "fc2.bias"][o])
-            else:
-                d = row0
-                mu = h2[:, :k] @ W3[d, :k] + sd[pre + "fc3.bias"][d]
-                al = h2[:, :k] @ W3[D + d, :k] + sd[pre + "fc3.bias"][D + d]
-                x[:, d] = uf[:, d] * torch.exp(al) + mu
-                xb[:, d] = x[:, d]
-                ld += al
+                if phase == 0:
+                    h1[:, o] = torch.relu(xb[:, :k] @ W1p[o, :k].T + sd[pre + "fc1.bias"][o])
+                elif phase == 1:
+                    h2[:, o] = torch.relu(h1[:, :k] @ W2[o, :k].T + sd[pre + "fc2.bias"][o])
+                    if push:
+                        out += h2[:, o] @ W3[:, o].T
+                else:
+                    d = row0
+                    if push:
+                        assert kch == 0
+                        mu, al = out[:, d] + sd[pre + "fc3.bias"][d], out[:, D + d] + sd[pre + "fc3.bias"][D + d]
+                    else:
+                        mu = h2[:, :k] @ W3[d, :k] + sd[pre + "fc3.bias"][d]
+                        al = h2[:, :k] @ W3[D + d, :k] + sd[pre + "fc3.bias"][D + d]
+                    x[:, d] = uf[:, d] * torch.exp(al) + mu
+                    xb[:, d] = x[:, d]
+                    ld += al
+            x_o, a_o = MO.made_inverse(u, sd, pre, D)
+            assert (x - x_o).abs().max().item() < 1e-5 * (x_o.abs().max().item() + 1), (D, H, push)
+            assert (ld - a_o).abs().max().item() < 1e-5 * (a_o.abs().max().item() + 1), (D, H, push)
+        continue
         x_o, a_o = MO.made_inverse(u, sd, pre, D)
         assert (x - x_o).abs().max().item() < 1e-5 * (x_o.abs().max().item() + 1), (D, H)
         assert (ld - a_o).abs().max().item() < 1e-5 * (a_o.abs().max().item() + 1), (D, H)

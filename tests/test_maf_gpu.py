@@ -52,12 +52,13 @@ def test_maf_forward_inverse_backward_vs_paper_restatement(D, H, K, B):
         x_dp, ld_dp = lay(z, logdet=ld, reverse=True)
         lay.resident_inverse = True
         assert rel(x_dp, x) < (1e-5 if B < 4096 else 1e-4)
-        for mt in (1, 2):
-            lay.resident_mtiles = mt
+        for push, mt in ((True, 0), (False, 1), (False, 2)):   # push kernel; pull kernel with 16 / 32 samples per warp
+            lay.push_inverse, lay.resident_mtiles = push, mt
+            assert lay._inverse_jobs(z.device)[1] == push
             x_r, ld_r = lay(z, logdet=ld, reverse=True)
-            assert rel(x_r, x_dp) < 1e-4, mt
-            assert (ld_r - ld_dp).abs().max().item() < 1e-3 * (ld.abs().max().item() + 1), mt
-        lay.resident_mtiles = 0
+            assert rel(x_r, x_dp) < 1e-4, (push, mt)
+            assert (ld_r - ld_dp).abs().max().item() < 1e-3 * (ld.abs().max().item() + 1), (push, mt)
+        lay.push_inverse, lay.resident_mtiles = True, 0
     # autoregressive property: d z_i / d x_j = 0 for j > i  (layer 0, un-flipped view)
     with torch.no_grad():
         x2 = x.clone()
@@ -82,7 +83,8 @@ def test_maf_forward_inverse_backward_vs_paper_restatement(D, H, K, B):
 @pytest.mark.parametrize("D,H,B,flip", [(1, 64, 33, True), (2, 64, 16, False), (100, 64, 50, True), (17, 128, 1, True),
                                         (63, 512, 20000, True)])
 def test_resident_inverse_matches_paper_restatement(D, H, B, flip):
-    """One MADE layer, inverse only: the one-launch resident kernel against the fp32 restatement's D-pass inverse
+    """One MADE layer, inverse only: the one-launch resident kernels (push: layer-2 tiles multiplied straight into
+    running output sums; pull: h2 kept in shared memory) against the fp32 restatement's D-pass inverse
     (bf16 network vs fp32 network: 2e-3 of max|x|), at degenerate sizes (D = 1, D > H so some degrees own no hidden
     unit, a single sample, a ragged last tile) and at a batch that fills every SM several times."""
     from nf_distillation_b200.models.maf import MADE
@@ -97,11 +99,12 @@ def test_resident_inverse_matches_paper_restatement(D, H, B, flip):
     made = made.cuda()
     with torch.no_grad():
         ld0 = torch.randn(B, device="cuda")
-        for mt in (1, 2):
-            made.resident_mtiles = mt
+        for push, mt in ((True, 0), (False, 1), (False, 2)):
+            made.push_inverse, made.resident_mtiles = push, mt
+            assert made._inverse_jobs(ld0.device)[1] == (push and 2 * D <= 128)
             x, ld = made(u.cuda(), logdet=ld0, reverse=True)
-            assert rel(x, x_o) < 2e-3, mt
-            assert ((ld - ld0).cpu() - sum_alpha).abs().max().item() < 2e-3 * (sum_alpha.abs().max().item() + 1), mt
+            assert rel(x, x_o) < 2e-3, (push, mt)
+            assert ((ld - ld0).cpu() - sum_alpha).abs().max().item() < 2e-3 * (sum_alpha.abs().max().item() + 1), (push, mt)
             x2, none = made(u.cuda(), logdet=None, reverse=True)
             assert none is None and torch.equal(x2, x)
 

@@ -228,30 +228,35 @@ int nfk_made_affine_bwd(const float* x, const float* out, int N3p, const float* 
 /* pass i of the sequential inverse: x[:, i] = u[:, i] exp(alpha_i) + mu_i */
 int nfk_made_inv_update(float* x, void* xb, int Dp, const float* u_in, const float* out, int N3p, const float* ld_in,
                         float* ld_out, int B, int D, int i, int flip, int last, void* stream);
-/* The whole D-step inverse of one MADE layer in ONE launch (csrc/maf_inverse.cu): a warp keeps x, h1, h2 of its 16 or
- * 32 samples in shared memory and finalises every hidden unit once, in degree order (~ one forward pass of work,
- * not D); a producer warp streams the weight rows of each job through a shared-memory byte ring (cp.async.bulk).
- * B1/B2/B3, b1/b2: the masked bf16 operands / biases of nfk_made_prep; b3 [>= 2D]. jobs [njobs][4] int32 on the
- * DEVICE (16-byte aligned) = the table nfk_made_inverse_jobs builds. u_in is in the layer's output order (reversed
- * when flip != 0); x [B,D]; ld_out = ld_in + sum alpha (either may be NULL). mtiles: 16-row tiles per warp (1 or 2;
- * 0 = choose). _supported: 1 if the shapes fit (H, Dp multiples of 64).
- * nfk_made_inverse_jobs is HOST code (host pointers, no GPU): cnt1/cnt2 [D+1] = number of layer-1 / layer-2 hidden
- * units with degree <= d (degrees sorted ascending); returns the number of jobs of one sample tile and, when
- * cap >= that number, writes the jobs {phase (0: layer-1 tile pair, 1: layer-2 tile pair, 2: (mu, alpha) row pair)
- * | second 8-row tile present << 2 | 16-wide k-chunks << 3, first row (phase 2: d), byte offset in the kernel's
- * shared-memory weight ring, jobs back to the latest job occupying any of those bytes}. Call with cap = 0 to size. */
+/* The whole D-step inverse of one MADE layer in ONE launch (csrc/maf_inverse.cu): a warp keeps x and the hidden
+ * activations of its 16 samples in shared memory and finalises every hidden unit once, in degree order (~ one forward
+ * pass of work, not D); a producer warp streams each job's weights through a shared-memory byte ring (one
+ * cp.async.bulk per job). Three steps:
+ *  1. nfk_made_inverse_jobs — HOST code (host pointers, no GPU): cnt1/cnt2 [D+1] = number of layer-1 / layer-2 hidden
+ *     units with degree <= d (degrees sorted ascending). Returns the number of jobs of one sample tile and, when
+ *     cap >= that number, writes 8 int32 per job: {phase (0: layer-1 tile pair, 1: layer-2 tile pair, 2: (mu, alpha))
+ *     | second 8-row tile present << 2 | 16-wide k-chunks << 3, first row (phase 2: d), byte offset in the kernel's
+ *     weight ring, jobs back to the latest job occupying any of those bytes, offset / 16 in the packed weight
+ *     stream, bytes / 16, 0, 0}. Call with cap = 0 to size. Depends on the degrees only.
+ *     push = 1 (needs nfk_made_inverse_push_supported and degrees that change only on multiples of 8 units, else
+ *     NFK_ERR_SHAPE): the PUSH kernel — layer-2 activations never reach shared memory, each finished 16-unit tile
+ *     pair is multiplied straight into running (mu | alpha) sums kept in registers.
+ *  2. nfk_made_inverse_pack — packs the masked bf16 operands of nfk_made_prep (B1 [H,Dp], B2 [H,H], B3 [N3p,H]) into
+ *     the weight stream (sum of the jobs' bytes, 128-byte aligned, zero-initialised by the caller), job after job in
+ *     shared-memory layout. jobs = the DEVICE copy of the table (16-byte aligned). Redo when the weights change.
+ *  3. nfk_made_inverse_resident — u_in is in the layer's output order (reversed when flip != 0); x [B,D];
+ *     ld_out = ld_in + sum alpha (either may be NULL); b1/b2 [H], b3 [>= 2D] fp32; mtiles: 16-sample tiles per warp
+ *     of the pull kernel (1 or 2; 0 = choose). _supported: 1 if the shapes fit (H, Dp multiples of 64). */
 int nfk_made_inverse_resident_supported(int D, int H, int Dp);
-/* PUSH variant of the same launch (B3push != NULL): when the hidden degrees change only on multiples of 8 units and
- * 2D <= N3p <= 128, the layer-2 activations never reach shared memory — each finished 16-unit tile pair is multiplied
- * straight into running (mu | alpha) sums kept in registers. B3push = [H/8 + 1][N3p][8] bf16: B3 regrouped per
- * 8-unit tile (B3push[t][r][k] = B3[r][8t + k]) plus one all-zero tile. The job table must be built with push = 1. */
 int nfk_made_inverse_push_supported(int D, int H, int Dp, int N3p);
 int nfk_made_inverse_jobs(const int* cnt1, const int* cnt2, int D, int H, int Dp, int N3p, int push, int* jobs,
                           int cap);
-int nfk_made_inverse_resident(const float* u_in, const void* B1, const void* B2, const void* B3, const void* B3push,
-                              int N3p, const float* b1, const float* b2, const float* b3, const int* jobs, int njobs,
-                              float* x, const float* ld_in, float* ld_out, int B, int D, int H, int Dp, int flip,
-                              int mtiles, void* stream);
+int nfk_made_inverse_pack(const int* jobs, int njobs, const void* B1, const void* B2, const void* B3, int N3p, int D,
+                          int H, int Dp, int push, void* wstream, void* stream);
+int nfk_made_inverse_resident(const float* u_in, const void* wstream, const float* b1, const float* b2,
+                              const float* b3, const int* jobs, int njobs, int push, int N3p, float* x,
+                              const float* ld_in, float* ld_out, int B, int D, int H, int Dp, int flip, int mtiles,
+                              void* stream);
 
 /* Fused conv#1 -> conv#2 of the coupling network: h2 = relu(relu(col*B1^T + b1)*B2^T + b2) in ONE kernel (CTA
  * pairs; h1 stays in shared memory as the tcgen05 A operand of conv#2). col [M,K1p] bf16, B1 [512,K1p], B2 [512,512]

@@ -93,7 +93,8 @@ SIGNATURES: dict[str, list] = {
     "nfk_made_inverse_resident_supported": [_i, _i, _i],
     "nfk_made_inverse_push_supported": [_i, _i, _i, _i],
     "nfk_made_inverse_jobs": [_vp, _vp, _i, _i, _i, _i, _i, _vp, _i],
-    "nfk_made_inverse_resident": [_vp] * 5 + [_i] + [_vp] * 4 + [_i] + [_vp] * 3 + [_i] * 6 + [_vp],
+    "nfk_made_inverse_pack": [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp],
+    "nfk_made_inverse_resident": [_vp] * 6 + [_i] * 3 + [_vp] * 3 + [_i] * 6 + [_vp],
 }
 
 

@@ -14,8 +14,9 @@
 // 8-16 output columns of a 16-row tile, far below its 64 x 8 x 16 minimum shape with a TMEM round trip per step.
 // The recursion is a fixed stream of JOBS (step d: layer-1 tile pairs of degree d, layer-2 tile pairs, the
 // (mu_d, alpha_d) row pair), the same for every sample tile, so the host builds the job table once
-// (nfk_made_inverse_jobs), including each job's byte range in a shared-memory weight ring. A producer warp streams
-// each job's weight rows into its range with cp.async.bulk (TMA, one bulk copy per row, completion on an mbarrier);
+// (nfk_made_inverse_jobs), including each job's byte range in a shared-memory weight ring, and the weights are packed
+// once per weight update into one stream, job after job, already in shared-memory layout (nfk_made_inverse_pack). A
+// producer warp copies each job's block into its range with ONE cp.async.bulk (TMA, completion on an mbarrier);
 // the consumer warps wait on the job's "full" barrier, multiply, and release it through its "empty" barrier — no
 // block-wide barrier in the recursion, warps drift apart freely. Jobs are sized by their bytes (a (mu, alpha) row
 // pair is 2 KB, a full layer-2 tile pair 16 KB), so ~50 KB of ring keeps ~a dozen jobs = several microseconds of
@@ -38,13 +39,10 @@ constexpr int MI_SLOTS = 16;   // jobs in flight at most (mbarrier pairs); the b
 
 struct MiArgs {
   const float* u_in;            // [B, D] layer output order (flipped if flip)
-  const __nv_bfloat16* B1;      // [H, Dp]   masked, k contiguous
-  const __nv_bfloat16* B2;      // [H, H]
-  const __nv_bfloat16* B3;      // [N3p, H]  rows: mu_0..mu_{D-1}, alpha_0..alpha_{D-1}
-  const __nv_bfloat16* B3push;  // push kernel only: [H/8 + 1][N3p][8] = B3 regrouped per 8-unit tile (+ one zero tile)
-  int N3p;
+  const unsigned char* wstream; // every job's weight bytes in shared-memory layout, job after job (nfk_made_inverse_pack)
   const float *b1, *b2, *b3;    // [H], [H], [>= 2D]
-  const int4* jobs;             // [njobs] {phase | second tile << 2 | k-chunks << 3, row0 (phase 2: d), ring offset, back}
+  const int4* jobs;             // [njobs][2]: {phase | second tile << 2 | k-chunks << 3, row0 (phase 2: d), ring offset,
+                                //              back}, {stream offset / 16, bytes / 16, 0, 0}
   int njobs, ring_bytes;
   float* x;                     // [B, D]
   const float* ld_in;           // [B] or null
@@ -74,7 +72,7 @@ __device__ __forceinline__ void mi_mma(float (&c)[4], const uint32_t (&a)[4], ui
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-// one row of weights, global -> shared, completion counted in bytes on `bar`
+// one contiguous block, global -> shared, completion counted in bytes on `bar`
 __device__ __forceinline__ void mi_bulk_row(uint32_t dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
@@ -86,12 +84,14 @@ __device__ __forceinline__ uint32_t mi_pack_relu(float a, float b) {
   return *reinterpret_cast<const uint32_t*>(&v);
 }
 
-// job descriptor in 2 x 32 bits: x = phase [0,2) | second tile [2] | k-chunks [3,11) | first row (phase 2: d) [11,32)
-//                                y = ring offset / 16 [0,16) | jobs back to the latest job whose ring bytes it overwrites [16,32)
-__device__ __forceinline__ uint2 mi_pack_job(int4 j) {
-  const uint32_t back = j.w > 65535 ? 65535u : static_cast<uint32_t>(j.w);
-  return make_uint2(static_cast<uint32_t>(j.x) | (static_cast<uint32_t>(j.y) << 11),
-                    (static_cast<uint32_t>(j.z) >> 4) | (back << 16));
+// job descriptor in 4 x 32 bits: x = phase [0,2) | second tile [2] | k-chunks [3,11) | first row (phase 2: d) [11,32)
+//                               y = ring offset / 16 [0,16) | jobs back to the latest job whose ring bytes it overwrites [16,32)
+//                               z = offset / 16 in the packed weight stream, w = bytes / 16 (0: the job carries nothing)
+__device__ __forceinline__ uint4 mi_pack_job(int4 a, int4 b) {
+  const uint32_t back = a.w > 65535 ? 65535u : static_cast<uint32_t>(a.w);
+  return make_uint4(static_cast<uint32_t>(a.x) | (static_cast<uint32_t>(a.y) << 11),
+                    (static_cast<uint32_t>(a.z) >> 4) | (back << 16), static_cast<uint32_t>(b.x),
+                    static_cast<uint32_t>(b.y));
 }
 
 // blockDim = (consumer warps + 1) * 32; the last warp is the weight producer
@@ -106,10 +106,10 @@ __global__ void __launch_bounds__(288) made_inverse_resident_kernel(const MiArgs
   unsigned char* ring = mi_smem;
   uint64_t* full = reinterpret_cast<uint64_t*>(mi_smem + p.ring_bytes);
   uint64_t* empty = full + MI_SLOTS;
-  uint2* jobs_s = reinterpret_cast<uint2*>(mi_smem + p.ring_bytes + 256);   // packed, see mi_pack_job
-  unsigned char* act = mi_smem + p.ring_bytes + 256 + ((p.njobs * 8 + 15) & ~15);
+  uint4* jobs_s = reinterpret_cast<uint4*>(mi_smem + p.ring_bytes + 256);   // packed, see mi_pack_job
+  unsigned char* act = mi_smem + p.ring_bytes + 256 + p.njobs * 16;
   const uint32_t ring_s = smem_u32(ring);
-  for (int i = threadIdx.x; i < p.njobs; i += blockDim.x) jobs_s[i] = mi_pack_job(__ldg(p.jobs + i));
+  for (int i = threadIdx.x; i < p.njobs; i += blockDim.x) jobs_s[i] = mi_pack_job(__ldg(p.jobs + 2 * i), __ldg(p.jobs + 2 * i + 1));
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < MI_SLOTS; ++s) {
@@ -125,33 +125,28 @@ __global__ void __launch_bounds__(288) made_inverse_resident_kernel(const MiArgs
   const int njobs = p.njobs;
 
   if (warp == cwarps) {
-    // ---------------- producer: the same job stream once per CTA tile. A job's rows go to its own byte range of the
-    // ring (row stride = row bytes + 16: ldmatrix rows on distinct banks); before overwriting, wait until the latest
-    // job that used any of those bytes — or this job's slot — has been released by every consumer warp.
+    // ---------------- producer: the same job stream once per CTA tile. A job's weights are ONE contiguous block of
+    // the packed stream (already in shared-memory layout: row stride = row bytes + 16 keeps ldmatrix rows on distinct
+    // banks) -> one bulk copy per job into its byte range of the ring. (One copy per weight ROW, 16-17 per job, made
+    // the copy engine the bottleneck: ~100 cycles per bulk operation, 51 per step.) Before overwriting, wait until
+    // the latest job that used any of those bytes — or this job's slot — has been released by every consumer warp.
     int slot = 0, par = 0, q = 0;
     for (int tile = 0; tile < my_tiles; ++tile) {
       for (int j = 0; j < njobs; ++j, ++q) {
-        const uint2 cur = jobs_s[j];
+        const uint4 cur = jobs_s[j];
         int back = cur.y >> 16;
         if (back > MI_SLOTS) back = MI_SLOTS;
         if (q >= back) {
           const int ws = slot >= back ? slot - back : slot - back + MI_SLOTS;
           mbar_wait(&empty[ws], slot >= back ? par : par ^ 1);
         }
-        const int phase = cur.x & 3, kch = (cur.x >> 3) & 255, row0 = cur.x >> 11;
-        const int rows = phase == 2 ? 2 : ((cur.x & 4) ? 16 : 8);
-        const uint32_t row_bytes = kch * 32;
-        if (kch == 0) {
-          if (lane == 0) mbar_arrive(&full[slot]);
-        } else {
-          if (lane == 0) mbar_expect_tx(&full[slot], rows * row_bytes);
-          __syncwarp();
-          if (lane < rows) {
-            const __nv_bfloat16* src;
-            if (phase == 0) src = p.B1 + static_cast<size_t>(row0 + lane) * Dp;
-            else if (phase == 1) src = p.B2 + static_cast<size_t>(row0 + lane) * H;
-            else src = p.B3 + static_cast<size_t>(row0 + lane * D) * H;     // rows d (mu) and D + d (alpha)
-            mi_bulk_row(ring_s + (cur.y & 0xffff) * 16 + lane * (row_bytes + 16), src, row_bytes, &full[slot]);
+        if (lane == 0) {
+          if (cur.w == 0) {
+            mbar_arrive(&full[slot]);
+          } else {
+            mbar_expect_tx(&full[slot], cur.w * 16);
+            mi_bulk_row(ring_s + (cur.y & 0xffff) * 16, p.wstream + static_cast<size_t>(cur.z) * 16, cur.w * 16,
+                        &full[slot]);
           }
         }
         if (++slot == MI_SLOTS) { slot = 0; par ^= 1; }
@@ -213,7 +208,7 @@ __global__ void __launch_bounds__(288) made_inverse_resident_kernel(const MiArgs
         }
       __syncwarp();
     }
-    uint2 jd = jobs_s[0];
+    uint4 jd = jobs_s[0];
     float4 bnext = fetch_bias(jd.x);
     for (int j = 0; j < njobs; ++j) {
       const uint32_t cur = jd.x;
@@ -404,10 +399,10 @@ __global__ void __launch_bounds__(384) made_inverse_push_kernel(const MiArgs p) 
   const int per_warp = R * (ldx + ldh) * 2;                  // bytes: x and h1 only
   uint64_t* full = reinterpret_cast<uint64_t*>(mi_smem + p.ring_bytes);
   uint64_t* empty = full + MI_SLOTS;
-  uint2* jobs_s = reinterpret_cast<uint2*>(mi_smem + p.ring_bytes + 256);
-  unsigned char* act = mi_smem + p.ring_bytes + 256 + ((p.njobs * 8 + 15) & ~15);
+  uint4* jobs_s = reinterpret_cast<uint4*>(mi_smem + p.ring_bytes + 256);
+  unsigned char* act = mi_smem + p.ring_bytes + 256 + p.njobs * 16;
   const uint32_t ring_s = smem_u32(mi_smem);
-  for (int i = threadIdx.x; i < p.njobs; i += blockDim.x) jobs_s[i] = mi_pack_job(__ldg(p.jobs + i));
+  for (int i = threadIdx.x; i < p.njobs; i += blockDim.x) jobs_s[i] = mi_pack_job(__ldg(p.jobs + 2 * i), __ldg(p.jobs + 2 * i + 1));
   if (threadIdx.x == 0) {
     for (int s = 0; s < MI_SLOTS; ++s) {
       mbar_init(&full[s], 1);
@@ -420,37 +415,28 @@ __global__ void __launch_bounds__(384) made_inverse_push_kernel(const MiArgs p) 
   const int ctiles = (p.B + R * cwarps - 1) / (R * cwarps);
   const int my_tiles = (ctiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
   const int njobs = p.njobs;
-  constexpr uint32_t PUSH_BYTES = 2 * N3p * 16;               // two 8-unit tiles of the push table
 
   if (warp == cwarps) {
-    // ---------------- producer (see the pull kernel); a layer-2 job also carries its two push-table tiles, placed
+    // ---------------- producer (see the pull kernel); a layer-2 job's block also holds its two push-table tiles,
     // after the B2 rows; a (mu_d, alpha_d) job carries nothing
     int slot = 0, par = 0, q = 0;
     for (int tile = 0; tile < my_tiles; ++tile) {
       for (int j = 0; j < njobs; ++j, ++q) {
-        const uint2 cur = jobs_s[j];
+        const uint4 cur = jobs_s[j];
         int back = cur.y >> 16;
         if (back > MI_SLOTS) back = MI_SLOTS;
         if (q >= back) {
           const int ws = slot >= back ? slot - back : slot - back + MI_SLOTS;
           mbar_wait(&empty[ws], slot >= back ? par : par ^ 1);
         }
-        const int phase = cur.x & 3, kch = (cur.x >> 3) & 255, row0 = cur.x >> 11;
-        if (phase == 2) {
-          if (lane == 0) mbar_arrive(&full[slot]);
-        } else {
-          const int rows = (cur.x & 4) ? 16 : 8;
-          const uint32_t row_bytes = kch * 32, base = ring_s + (cur.y & 0xffff) * 16;
-          if (lane == 0) mbar_expect_tx(&full[slot], rows * row_bytes + (phase == 1 ? PUSH_BYTES : 0u));
-          __syncwarp();
-          if (lane < rows && row_bytes) {
-            const __nv_bfloat16* src = phase == 0 ? p.B1 + static_cast<size_t>(row0 + lane) * Dp
-                                                  : p.B2 + static_cast<size_t>(row0 + lane) * H;
-            mi_bulk_row(base + lane * (row_bytes + 16), src, row_bytes, &full[slot]);
+        if (lane == 0) {
+          if (cur.w == 0) {
+            mbar_arrive(&full[slot]);
+          } else {
+            mbar_expect_tx(&full[slot], cur.w * 16);
+            mi_bulk_row(ring_s + (cur.y & 0xffff) * 16, p.wstream + static_cast<size_t>(cur.z) * 16, cur.w * 16,
+                        &full[slot]);
           }
-          if (lane == 16 && phase == 1)
-            mi_bulk_row(base + ((16 * (row_bytes + 16) + 127) & ~127u),
-                        p.B3push + static_cast<size_t>(row0 >> 3) * (N3p * 8), PUSH_BYTES, &full[slot]);
         }
         if (++slot == MI_SLOTS) { slot = 0; par ^= 1; }
       }
@@ -512,7 +498,7 @@ __global__ void __launch_bounds__(384) made_inverse_push_kernel(const MiArgs p) 
       __syncwarp();
     }
     int dcur = 0;                // degree of the hidden units being finalised = index of the next x to come
-    uint2 jd = jobs_s[0];
+    uint4 jd = jobs_s[0];
     float4 bnext = fetch_bias(jd.x);
     for (int j = 0; j < njobs; ++j) {
       const uint32_t cur = jd.x;
@@ -648,6 +634,43 @@ __global__ void __launch_bounds__(384) made_inverse_push_kernel(const MiArgs p) 
   }
 }
 
+// Packed weight stream: every job's bytes exactly as the inverse kernels want them in shared memory — rows of
+// (kch * 32) weight bytes + 16 bytes of padding (zero), rows the job does not own zeroed, for a push-mode layer-2 job
+// followed (128-byte aligned) by its two push-table tiles B3[r][row0 .. row0 + 16) regrouped as [tile][r][8].
+// One CTA per job; rebuilt when the weights change (the job table itself depends on the degrees only).
+__global__ void made_inverse_pack_kernel(const int4* __restrict__ jobs, const __nv_bfloat16* __restrict__ B1,
+                                         const __nv_bfloat16* __restrict__ B2, const __nv_bfloat16* __restrict__ B3,
+                                         int N3p, int D, int H, int Dp, int push, unsigned char* __restrict__ wstream) {
+  const int4 a = jobs[2 * blockIdx.x], b = jobs[2 * blockIdx.x + 1];
+  if (b.y == 0) return;
+  const int phase = a.x & 3, two = (a.x >> 2) & 1, kch = a.x >> 3, row0 = a.y;
+  uint4* dst = reinterpret_cast<uint4*>(wstream + static_cast<size_t>(b.x) * 16);
+  const int per_row = kch * 2 + 1;                                      // 16-byte pieces per row, the last one padding
+  const int rows_valid = phase == 2 ? 2 : (two ? 16 : 8);
+  const int rows_block = (push && phase == 1) ? 16 : rows_valid;
+  for (int i = threadIdx.x; i < rows_block * per_row; i += blockDim.x) {
+    const int r = i / per_row, c = i - r * per_row;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (r < rows_valid && c < kch * 2) {
+      const __nv_bfloat16* src = phase == 0   ? B1 + static_cast<size_t>(row0 + r) * Dp
+                                 : phase == 1 ? B2 + static_cast<size_t>(row0 + r) * H
+                                              : B3 + static_cast<size_t>(row0 + r * D) * H;   // rows d (mu), D + d (alpha)
+      v = *reinterpret_cast<const uint4*>(src + c * 8);
+    }
+    dst[i] = v;
+  }
+  if (push && phase == 1) {
+    // push tiles: [2 tiles][N3p rows][8 units]; units past H (a last, single tile) are zero
+    __nv_bfloat16* pt = reinterpret_cast<__nv_bfloat16*>(dst + ((rows_block * per_row * 16 + 127) & ~127) / 16);
+    for (int i = threadIdx.x; i < 2 * N3p; i += blockDim.x) {
+      const int tb = i / N3p, r = i - tb * N3p, u0 = row0 + 8 * tb;
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (u0 < H) v = *reinterpret_cast<const uint4*>(B3 + static_cast<size_t>(r) * H + u0);
+      reinterpret_cast<uint4*>(pt)[i] = v;
+    }
+  }
+}
+
 static inline int mi_per_warp_bytes(int mt, int H, int Dp) { return mt * 16 * ((Dp + 8) + 2 * (H + 8)) * 2; }
 static inline int mi_per_warp_bytes_push(int H, int Dp) { return 16 * ((Dp + 8) + (H + 8)) * 2; }
 static inline int mi_rows_bytes(int rows, int kch) { return (rows * (kch * 32 + 16) + 127) & ~127; }
@@ -660,7 +683,7 @@ static inline int mi_job_bytes(int desc, int push, int N3p) {
   if (phase == 0) return mi_rows_bytes(rows, kch);
   return mi_rows_bytes(16, kch) + 2 * N3p * 16;
 }
-static inline int mi_side_bytes(int njobs) { return 256 + ((njobs * 8 + 15) & ~15); }   // barriers + packed job table
+static inline int mi_side_bytes(int njobs) { return 256 + njobs * 16; }   // barriers + packed job table
 
 }  // namespace nfk
 
@@ -686,7 +709,7 @@ static int mi_ring_bytes(int H, int Dp, int njobs, int push, int N3p) {
 
 extern "C" int nfk_made_inverse_resident_supported(int D, int H, int Dp) {
   if (D <= 0 || H <= 0 || H % 64 || Dp % 64 || Dp < D || H > 255 * 16 || Dp > 255 * 16) return 0;
-  // (the packed job table also lives in shared memory: at most 4 D + H / 8 jobs of 8 bytes)
+  // (the packed job table also lives in shared memory: at most 4 D + H / 8 jobs of 16 bytes)
   return mi_ring_bytes(H, Dp, 4 * D + H / 8, 0, 0) > 0 ? 1 : 0;
 }
 
@@ -705,7 +728,11 @@ extern "C" int nfk_made_inverse_jobs(const int* cnt1, const int* cnt2, int D, in
     return NFK_ERR_SHAPE;
   int n = 0;
   auto put = [&](int phase, int row0, int kch, int two) {
-    if (n < cap) { jobs[4 * n] = phase | (two << 2) | (kch << 3); jobs[4 * n + 1] = row0; jobs[4 * n + 2] = 0; jobs[4 * n + 3] = 0; }
+    if (n < cap) {
+      int* q = jobs + 8 * n;
+      q[0] = phase | (two << 2) | (kch << 3); q[1] = row0;
+      for (int e = 2; e < 8; ++e) q[e] = 0;
+    }
     ++n;
   };
   for (int d = 0; d < D; ++d) {
@@ -722,28 +749,47 @@ extern "C" int nfk_made_inverse_jobs(const int* cnt1, const int* cnt2, int D, in
   }
   if (n > cap) return n;            // sizing call (or a short buffer): offsets need the whole table
   // ring placement: consecutive byte ranges, wrapping to 0 when a job does not fit before the end; every tile replays
-  // the same offsets, so `back` looks through the cyclic job order (a job of the previous tile counts)
+  // the same offsets, so `back` looks through the cyclic job order (a job of the previous tile counts).
+  // stream placement: job after job.
   const int ring = mi_ring_bytes(H, Dp, n, push, N3p);
   if (ring <= 0) return NFK_ERR_SHAPE;
   int cur = 0;
+  long long soff = 0;
   for (int j = 0; j < n; ++j) {
-    const int size = mi_job_bytes(jobs[4 * j], push, N3p);
+    const int size = mi_job_bytes(jobs[8 * j], push, N3p);
     if (size > ring) return NFK_ERR_SHAPE;
     if (cur + size > ring) cur = 0;
-    jobs[4 * j + 2] = cur;
+    jobs[8 * j + 2] = cur;
     cur += size;
+    if (soff / 16 > 0x7fffffff) return NFK_ERR_SHAPE;
+    jobs[8 * j + 4] = static_cast<int>(soff / 16);
+    jobs[8 * j + 5] = size / 16;
+    soff += size;
   }
   for (int j = 0; j < n; ++j) {
-    const int lo = jobs[4 * j + 2], hi = lo + mi_job_bytes(jobs[4 * j], push, N3p);
+    const int lo = jobs[8 * j + 2], hi = lo + jobs[8 * j + 5] * 16;
     int back = n;                                  // nothing overlaps within a whole period: only the slot binds
     for (int b = 1; b < n && hi > lo; ++b) {
       const int i = ((j - b) % n + n) % n;
-      const int lo2 = jobs[4 * i + 2], hi2 = lo2 + mi_job_bytes(jobs[4 * i], push, N3p);
+      const int lo2 = jobs[8 * i + 2], hi2 = lo2 + jobs[8 * i + 5] * 16;
       if (lo < hi2 && lo2 < hi) { back = b; break; }
     }
-    jobs[4 * j + 3] = back;
+    jobs[8 * j + 3] = back;
   }
   return n;
+}
+
+extern "C" int nfk_made_inverse_pack(const int* jobs, int njobs, const void* B1, const void* B2, const void* B3,
+                                     int N3p, int D, int H, int Dp, int push, void* wstream, void* stream) {
+  if (njobs <= 0 || !nfk_made_inverse_resident_supported(D, H, Dp) || N3p < 2 * D || N3p % 8) return NFK_ERR_SHAPE;
+  if (!jobs || !B1 || !B2 || !B3 || !wstream || (reinterpret_cast<uintptr_t>(jobs) & 15) ||
+      (reinterpret_cast<uintptr_t>(wstream) & 127))
+    return NFK_ERR_ARG;
+  made_inverse_pack_kernel<<<njobs, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const int4*>(jobs), static_cast<const __nv_bfloat16*>(B1),
+      static_cast<const __nv_bfloat16*>(B2), static_cast<const __nv_bfloat16*>(B3), N3p, D, H, Dp, push,
+      static_cast<unsigned char*>(wstream));
+  return cudaGetLastError() == cudaSuccess ? NFK_OK : NFK_ERR_LAUNCH;
 }
 
 template <int MT>
@@ -773,7 +819,7 @@ static int mi_launch(MiArgs p, cudaStream_t st) {
 template <int NO>
 static int mi_launch_push(MiArgs p, cudaStream_t st) {
   const int per_warp = mi_per_warp_bytes_push(p.H, p.Dp);
-  p.ring_bytes = mi_ring_bytes(p.H, p.Dp, p.njobs, 1, p.N3p);
+  p.ring_bytes = mi_ring_bytes(p.H, p.Dp, p.njobs, 1, NO * 8);
   if (p.ring_bytes <= 0) return NFK_ERR_SHAPE;
   const int fixed = p.ring_bytes + mi_side_bytes(p.njobs);
   int warps = (MI_SMEM_MAX - fixed) / per_warp;
@@ -794,29 +840,25 @@ static int mi_launch_push(MiArgs p, cudaStream_t st) {
   return cudaGetLastError() == cudaSuccess ? NFK_OK : NFK_ERR_LAUNCH;
 }
 
-extern "C" int nfk_made_inverse_resident(const float* u_in, const void* B1, const void* B2, const void* B3,
-                                         const void* B3push, int N3p, const float* b1, const float* b2,
-                                         const float* b3, const int* jobs, int njobs, float* x, const float* ld_in,
-                                         float* ld_out, int B, int D, int H, int Dp, int flip, int mtiles,
-                                         void* stream) {
+extern "C" int nfk_made_inverse_resident(const float* u_in, const void* wstream, const float* b1, const float* b2,
+                                         const float* b3, const int* jobs, int njobs, int push, int N3p, float* x,
+                                         const float* ld_in, float* ld_out, int B, int D, int H, int Dp, int flip,
+                                         int mtiles, void* stream) {
   if (B <= 0 || njobs <= 0 || njobs > (1 << 20) || !nfk_made_inverse_resident_supported(D, H, Dp) || mtiles < 0 ||
       mtiles > 2)
     return NFK_ERR_SHAPE;
-  if (B3push && !nfk_made_inverse_push_supported(D, H, Dp, N3p)) return NFK_ERR_SHAPE;
-  if (!u_in || !B1 || !B2 || !B3 || !b1 || !b2 || !b3 || !jobs || !x) return NFK_ERR_ARG;
-  if (reinterpret_cast<uintptr_t>(jobs) & 15) return NFK_ERR_ARG;
+  if (push && !nfk_made_inverse_push_supported(D, H, Dp, N3p)) return NFK_ERR_SHAPE;
+  if (!u_in || !wstream || !b1 || !b2 || !b3 || !jobs || !x) return NFK_ERR_ARG;
+  if ((reinterpret_cast<uintptr_t>(jobs) & 15) || (reinterpret_cast<uintptr_t>(wstream) & 15)) return NFK_ERR_ARG;
   MiArgs p;
   p.u_in = u_in;
-  p.B1 = static_cast<const __nv_bfloat16*>(B1);
-  p.B2 = static_cast<const __nv_bfloat16*>(B2);
-  p.B3 = static_cast<const __nv_bfloat16*>(B3);
-  p.B3push = static_cast<const __nv_bfloat16*>(B3push); p.N3p = N3p;
+  p.wstream = static_cast<const unsigned char*>(wstream);
   p.b1 = b1; p.b2 = b2; p.b3 = b3;
   p.jobs = reinterpret_cast<const int4*>(jobs); p.njobs = njobs; p.ring_bytes = 0;
   p.x = x; p.ld_in = ld_in; p.ld_out = ld_out;
   p.B = B; p.D = D; p.H = H; p.Dp = Dp; p.flip = flip;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (B3push) return N3p == 128 ? mi_launch_push<16>(p, st) : mi_launch_push<8>(p, st);
+  if (push) return N3p == 128 ? mi_launch_push<16>(p, st) : mi_launch_push<8>(p, st);
   // pull kernel: one 16-sample tile per warp leaves room for the most warps; two halve the B-operand reads
   const int ring = mi_ring_bytes(H, Dp, njobs, 0, 0);
   if (ring <= 0) return NFK_ERR_SHAPE;

@@ -127,7 +127,7 @@ class MADE(nn.Module):
         self._ranges_t = _kb_ranges_t(deg, deg, self.bn)
         self._cache = None
         self._job_cache = None
-        self._push_cache = None
+        self._stream_cache = None
         self.push_inverse = True         # False: the pull kernel (h2 kept in shared memory) even for aligned degrees
         self.resident_inverse = True     # False: the D-pass GEMM inverse (kept as the cross-check in the tests)
         self.resident_mtiles = 0         # 16-sample tiles per warp in the resident inverse (0 = chosen by the library)
@@ -154,14 +154,15 @@ class MADE(nn.Module):
             self._job_cache = (key, (jobs, push))
         return self._job_cache[1]
 
-    def _push_table(self, B3):
-        """B3 [N3p, H] regrouped per 8-unit tile: [H/8 + 1, N3p, 8] (last tile zero), cached with the operands."""
-        key = (B3.data_ptr(), B3._version)
-        if self._push_cache is None or self._push_cache[0] != key:
-            tab = torch.zeros(self.H // 8 + 1, self.N3p, 8, device=B3.device, dtype=BF16)
-            tab[:-1] = B3.view(self.N3p, self.H // 8, 8).permute(1, 0, 2)
-            self._push_cache = (key, tab, B3)   # (keeps B3 alive so the pointer in the key cannot be reused)
-        return self._push_cache[1]
+    def _weight_stream(self, jobs, push, ops_):
+        """The packed weight stream of the resident inverse for the current operands (rebuilt when they change)."""
+        key = (jobs.data_ptr(), push, ops_[0].data_ptr(), ops_[0]._version)
+        if self._stream_cache is None or self._stream_cache[0] != key:
+            nbytes = int(jobs[:, 5].sum().item()) * 16
+            ws = torch.zeros(max(nbytes, 128), device=jobs.device, dtype=torch.uint8)
+            ops.made_inverse_pack(jobs, ops_[0], ops_[2], ops_[4], self.N3p, self.D, self.H, self.Dp, push, ws)
+            self._stream_cache = (key, ws, ops_[0])   # (keeps B1 alive so the pointer in the key cannot be reused)
+        return self._stream_cache[1]
 
     def _params(self):
         return (self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias, self.fc3.weight, self.fc3.bias)
@@ -263,10 +264,10 @@ class MADE(nn.Module):
             # ONE launch: every hidden unit finalised once, in degree order, activations resident in shared memory
             x = torch.empty_like(u_in)
             ld_out = torch.empty(Bn, device=x.device, dtype=F32) if want else None
-            ops.made_inverse_resident(u_in, ops_[0], ops_[2], ops_[4], params[1].detach(), params[3].detach(),
-                                      ops_[6], jobs, x, ld.contiguous() if want else None, ld_out, Bn,
-                                      self.D, self.H, self.Dp, self.flip, self.resident_mtiles,
-                                      B3push=self._push_table(ops_[4]) if push else None, N3p=self.N3p)
+            ops.made_inverse_resident(u_in, self._weight_stream(jobs, push, ops_), params[1].detach(),
+                                      params[3].detach(), ops_[6], jobs, push, self.N3p, x,
+                                      ld.contiguous() if want else None, ld_out, Bn, self.D, self.H, self.Dp,
+                                      self.flip, self.resident_mtiles)
             return x, ld_out
         # fallback (unsorted degrees / shapes the resident kernel does not take): D passes of the three GEMMs,
         # activations in HBM / L2, one column of x fixed per pass

@@ -347,9 +347,10 @@ def made_inverse_push_supported(D, H, Dp, N3p) -> bool:
 
 
 def made_inverse_jobs(cnt1, cnt2, D, H, Dp, N3p=0, push=False):
-    """Host-side job table of the resident inverse from the degree counts (CPU int32 tensors [D+1]) -> [njobs, 4]:
-    (phase | two << 2 | k-chunks << 3, first row, weight-ring byte offset, jobs back to the ring bytes' last user).
-    Returns None when push=True and the degrees do not change on whole 8-unit tiles."""
+    """Host-side job table of the resident inverse from the degree counts (CPU int32 tensors [D+1]) -> [njobs, 8]:
+    (phase | two << 2 | k-chunks << 3, first row, weight-ring byte offset, jobs back to the ring bytes' last user,
+    packed-stream offset / 16, bytes / 16, 0, 0). Returns None when push=True and the degrees do not change on whole
+    8-unit tiles (or the shape does not fit the push kernel)."""
     import torch
     cnt1 = cnt1.to(torch.int32).contiguous().cpu()
     cnt2 = cnt2.to(torch.int32).contiguous().cpu()
@@ -358,19 +359,24 @@ def made_inverse_jobs(cnt1, cnt2, D, H, Dp, N3p=0, push=False):
         return None
     if n <= 0:
         check(n if n < 0 else -1, "nfk_made_inverse_jobs")
-    jobs = torch.empty(n, 4, dtype=torch.int32)
+    jobs = torch.empty(n, 8, dtype=torch.int32)
     check(0 if LIB.nfk_made_inverse_jobs(cnt1.data_ptr(), cnt2.data_ptr(), D, H, Dp, N3p, int(push), jobs.data_ptr(),
                                          n) == n else -1, "nfk_made_inverse_jobs")
     return jobs
 
 
-def made_inverse_resident(u_in, B1, B2, B3, b1, b2, b3, jobs, x, ld_in, ld_out, B, D, H, Dp, flip, mtiles=0,
-                          B3push=None, N3p=0):
-    """The whole sequential inverse of one MADE layer in one launch (activations resident in shared memory).
-    B3push given: the push kernel (jobs built with push=True)."""
+def made_inverse_pack(jobs_dev, B1, B2, B3, N3p, D, H, Dp, push, wstream):
+    """Weights of every job, packed job after job in the shared-memory layout the inverse kernel copies in one piece."""
     _count()
-    check(LIB.nfk_made_inverse_resident(_p(u_in), _p(B1), _p(B2), _p(B3), _p(B3push), N3p, _p(b1), _p(b2), _p(b3),
-                                        _p(jobs), jobs.shape[0], _p(x), _p(ld_in), _p(ld_out), B, D, H, Dp, int(flip),
+    check(LIB.nfk_made_inverse_pack(_p(jobs_dev), jobs_dev.shape[0], _p(B1), _p(B2), _p(B3), N3p, D, H, Dp, int(push),
+                                    _p(wstream), _st()), "nfk_made_inverse_pack")
+
+
+def made_inverse_resident(u_in, wstream, b1, b2, b3, jobs, push, N3p, x, ld_in, ld_out, B, D, H, Dp, flip, mtiles=0):
+    """The whole sequential inverse of one MADE layer in one launch (activations resident in shared memory)."""
+    _count()
+    check(LIB.nfk_made_inverse_resident(_p(u_in), _p(wstream), _p(b1), _p(b2), _p(b3), _p(jobs), jobs.shape[0],
+                                        int(push), N3p, _p(x), _p(ld_in), _p(ld_out), B, D, H, Dp, int(flip),
                                         int(mtiles), _st()), "nfk_made_inverse_resident")
 
 

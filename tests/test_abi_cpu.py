@@ -179,7 +179,7 @@ def test_resident_inverse_job_table_reproduces_the_sequential_inverse():
             if push and (2 * D > 128):
                 assert jobs is None                       # more than 16 output tiles: pull kernel only
                 continue
-            assert jobs.shape[1] == 4 and ((jobs[:, 0] & 3) == 2).sum().item() == D
+            assert jobs.shape[1] == 8 and ((jobs[:, 0] & 3) == 2).sum().item() == D
 
             def size(q):
                 phase, kch, rows = q[0] & 3, q[0] >> 3, (2 if (q[0] & 3) == 2 else (16 if q[0] & 4 else 8))
@@ -188,8 +188,11 @@ def test_resident_inverse_job_table_reproduces_the_sequential_inverse():
                 return 0 if phase == 2 else (size_rows(rows, kch) if phase == 0 else size_rows(16, kch) + 2 * N3p * 16)
             # ring plan: 16-byte aligned ranges; a job never overwrites bytes of the `back - 1` jobs before it
             jl = jobs.tolist()
+            soff = 0
             for j, q in enumerate(jl):
                 assert q[2] % 16 == 0 and q[3] >= 1
+                assert q[4] * 16 == soff and q[5] * 16 == size(q)      # packed stream: job after job
+                soff += size(q)
                 for b in range(1, min(q[3], len(jl)) if size(q) else 0):
                     o = jl[(j - b) % len(jl)]
                     assert not (q[2] < o[2] + size(o) and o[2] < q[2] + size(q)), (D, H, j, b)
@@ -199,7 +202,7 @@ def test_resident_inverse_job_table_reproduces_the_sequential_inverse():
             xb, h1, h2 = torch.zeros(19, Dp), torch.zeros(19, H), torch.zeros(19, H)
             out = torch.zeros(19, 2 * D)
             x, ld = torch.zeros(19, D), torch.zeros(19)
-            for desc, row0, _off, _back in jl:
+            for desc, row0, *_rest in jl:
                 phase, two, kch = desc & 3, desc & 4, desc >> 3
                 k = kch * 16
                 o = slice(row0, row0 + (16 if two else 8))

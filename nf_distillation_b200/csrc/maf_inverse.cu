@@ -86,12 +86,13 @@ __device__ __forceinline__ uint32_t mi_pack_relu(float a, float b) {
 
 // job descriptor in 4 x 32 bits: x = phase [0,2) | second tile [2] | k-chunks [3,11) | first row (phase 2: d) [11,32)
 //                               y = ring offset / 16 [0,16) | jobs back to the latest job whose ring bytes it overwrites [16,32)
-//                               z = offset / 16 in the packed weight stream, w = bytes / 16 (0: the job carries nothing)
+//                               z = offset / 16 in the packed weight stream
+//                               w = bytes / 16 [0,16) (0: the job carries nothing) | push kernel: output tiles fed [16,32)
 __device__ __forceinline__ uint4 mi_pack_job(int4 a, int4 b) {
   const uint32_t back = a.w > 65535 ? 65535u : static_cast<uint32_t>(a.w);
   return make_uint4(static_cast<uint32_t>(a.x) | (static_cast<uint32_t>(a.y) << 11),
                     (static_cast<uint32_t>(a.z) >> 4) | (back << 16), static_cast<uint32_t>(b.x),
-                    static_cast<uint32_t>(b.y));
+                    static_cast<uint32_t>(b.y) | (static_cast<uint32_t>(b.z) << 16));
 }
 
 // blockDim = (consumer warps + 1) * 32; the last warp is the weight producer
@@ -141,12 +142,12 @@ __global__ void __launch_bounds__(288) made_inverse_resident_kernel(const MiArgs
           mbar_wait(&empty[ws], slot >= back ? par : par ^ 1);
         }
         if (lane == 0) {
-          if (cur.w == 0) {
+          const uint32_t bytes = (cur.w & 0xffff) * 16;
+          if (bytes == 0) {
             mbar_arrive(&full[slot]);
           } else {
-            mbar_expect_tx(&full[slot], cur.w * 16);
-            mi_bulk_row(ring_s + (cur.y & 0xffff) * 16, p.wstream + static_cast<size_t>(cur.z) * 16, cur.w * 16,
-                        &full[slot]);
+            mbar_expect_tx(&full[slot], bytes);
+            mi_bulk_row(ring_s + (cur.y & 0xffff) * 16, p.wstream + static_cast<size_t>(cur.z) * 16, bytes, &full[slot]);
           }
         }
         if (++slot == MI_SLOTS) { slot = 0; par ^= 1; }
@@ -430,12 +431,12 @@ __global__ void __launch_bounds__(384) made_inverse_push_kernel(const MiArgs p) 
           mbar_wait(&empty[ws], slot >= back ? par : par ^ 1);
         }
         if (lane == 0) {
-          if (cur.w == 0) {
+          const uint32_t bytes = (cur.w & 0xffff) * 16;
+          if (bytes == 0) {
             mbar_arrive(&full[slot]);
           } else {
-            mbar_expect_tx(&full[slot], cur.w * 16);
-            mi_bulk_row(ring_s + (cur.y & 0xffff) * 16, p.wstream + static_cast<size_t>(cur.z) * 16, cur.w * 16,
-                        &full[slot]);
+            mbar_expect_tx(&full[slot], bytes);
+            mi_bulk_row(ring_s + (cur.y & 0xffff) * 16, p.wstream + static_cast<size_t>(cur.z) * 16, bytes, &full[slot]);
           }
         }
         if (++slot == MI_SLOTS) { slot = 0; par ^= 1; }
@@ -497,14 +498,13 @@ __global__ void __launch_bounds__(384) made_inverse_push_kernel(const MiArgs p) 
       }
       __syncwarp();
     }
-    int dcur = 0;                // degree of the hidden units being finalised = index of the next x to come
     uint4 jd = jobs_s[0];
     float4 bnext = fetch_bias(jd.x);
     for (int j = 0; j < njobs; ++j) {
       const uint32_t cur = jd.x;
       const float4 bv = bnext;
       const int phase = cur & 3, kch = (cur >> 3) & 255, row0 = cur >> 11;
-      const uint32_t job_s = ring_s + (jd.y & 0xffff) * 16;
+      const uint32_t job_s = ring_s + (jd.y & 0xffff) * 16, live = jd.w >> 16;
       if (j + 1 < njobs) {
         jd = jobs_s[j + 1];
         bnext = fetch_bias(jd.x);
@@ -522,27 +522,20 @@ __global__ void __launch_bounds__(384) made_inverse_push_kernel(const MiArgs p) 
 #pragma unroll
             for (int e = 0; e < 4; ++e) acc[n][c][e] = 0.f;
         mbar_wait(&full[slot], par);
+        // k-chunk counts are even (the host rounds up: the extra chunk meets masked-zero weights); fragments are
+        // requested one chunk ahead, the last request of a job reads past its last chunk and is never used
         uint32_t a0[4], a1[4], b0[4], b1[4];
-        if (kch > 0) {
-          mi_ldsm_x4<0>(b_addr, b0);
-          mi_ldsm_x4<0>(a_addr, a0);
-        }
-        int kc = kch;
-        for (; kc >= 2; kc -= 2, a_addr += 64, b_addr += 64) {
+        mi_ldsm_x4<0>(b_addr, b0);
+        mi_ldsm_x4<0>(a_addr, a0);
+        for (int kc = kch; kc > 0; kc -= 2, a_addr += 64, b_addr += 64) {
           mi_ldsm_x4<32>(b_addr, b1);
           mi_ldsm_x4<32>(a_addr, a1);
           mi_mma(acc[0][0], a0, b0[0], b0[1]);
           mi_mma(acc[1][0], a0, b0[2], b0[3]);
-          if (kc > 2) {
-            mi_ldsm_x4<64>(b_addr, b0);
-            mi_ldsm_x4<64>(a_addr, a0);
-          }
+          mi_ldsm_x4<64>(b_addr, b0);
+          mi_ldsm_x4<64>(a_addr, a0);
           mi_mma(acc[0][1], a1, b1[0], b1[1]);
           mi_mma(acc[1][1], a1, b1[2], b1[3]);
-        }
-        if (kc) {
-          mi_mma(acc[0][0], a0, b0[0], b0[1]);
-          mi_mma(acc[1][0], a0, b0[2], b0[3]);
         }
         // bias + ReLU + bf16: rows g / g + 8, columns row0 + 2t, + 1 (tile 0) and row0 + 8 + 2t, + 1 (tile 1)
         uint32_t hA[4];
@@ -561,18 +554,16 @@ __global__ void __launch_bounds__(384) made_inverse_push_kernel(const MiArgs p) 
             *reinterpret_cast<uint32_t*>(o + (g + 8) * ldh + 8) = hA[3];
           }
         } else {
-          // push: these 16 layer-2 units (degree dcur) feed outputs mu_i, alpha_i for i >= dcur only
+          // push: these 16 layer-2 units (degree d) feed outputs mu_i, alpha_i for i >= d only
           // (hA is exactly the A fragment of a 16 x 16 tile: C fragments of two adjacent 8-column tiles)
           const uint32_t pb = job_s + ((16 * (kch * 32 + 16) + 127) & ~127) + pb_lane;
 #pragma unroll
           for (int n = 0; n < NO; n += 2) {
-            const bool live0 = (8 * n + 7 >= dcur && 8 * n < D) || (8 * n + 7 >= D + dcur && 8 * n < 2 * D);
-            const bool live1 = (8 * n + 15 >= dcur && 8 * n + 8 < D) || (8 * n + 15 >= D + dcur && 8 * n + 8 < 2 * D);
-            if (live0 || live1) {
+            if (live & (3u << n)) {      // the host marked the output tiles these units reach (i >= their degree)
               uint32_t w[4];
               mi_ldsm_x4<0>(pb + n * 128, w);
-              if (live0) mi_mma(out[n], hA, w[0], w[1]);
-              if (live1) mi_mma(out[n + 1], hA, w[2], w[3]);
+              if (live & (1u << n)) mi_mma(out[n], hA, w[0], w[1]);
+              if (live & (2u << n)) mi_mma(out[n + 1], hA, w[2], w[3]);
             }
           }
           __syncwarp();
@@ -582,7 +573,6 @@ __global__ void __launch_bounds__(384) made_inverse_push_kernel(const MiArgs p) 
       } else {
         // (mu_d, alpha_d) = columns d and D + d of the running sums
         const int d = row0;
-        dcur = d + 1;
         float uv[2];
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
@@ -683,7 +673,9 @@ static inline int mi_job_bytes(int desc, int push, int N3p) {
   if (phase == 0) return mi_rows_bytes(rows, kch);
   return mi_rows_bytes(16, kch) + 2 * N3p * 16;
 }
-static inline int mi_side_bytes(int njobs) { return 256 + njobs * 16; }   // barriers + packed job table
+// barriers + packed job table + 128 spare bytes at the very end of the allocation (the product loops request one
+// fragment past a row's last k-chunk; for the last row of the last warp that is past the activations)
+static inline int mi_side_bytes(int njobs) { return 256 + njobs * 16 + 128; }   // barriers + packed job table
 
 }  // namespace nfk
 
@@ -727,6 +719,9 @@ extern "C" int nfk_made_inverse_jobs(const int* cnt1, const int* cnt2, int D, in
   if (!(push ? nfk_made_inverse_push_supported(D, H, Dp, N3p) : nfk_made_inverse_resident_supported(D, H, Dp)))
     return NFK_ERR_SHAPE;
   int n = 0;
+  // k-chunk counts of the hidden layers are rounded up to even (H / 16 and Dp / 16 are even): the kernels' product
+  // loops take two chunks per trip; the extra chunk multiplies masked-zero weights
+  auto even = [](int k) { return (k + 1) & ~1; };
   auto put = [&](int phase, int row0, int kch, int two) {
     if (n < cap) {
       int* q = jobs + 8 * n;
@@ -741,9 +736,17 @@ extern "C" int nfk_made_inverse_jobs(const int* cnt1, const int* cnt2, int D, in
     if (push && ((c1 | c2) & 7)) return NFK_ERR_SHAPE;   // the push kernel needs degree boundaries on whole 8-unit tiles
     if (d > 0) {
       if (c1 > c1p)   // layer-1 units of degree d: inputs x_0 .. x_{d-1}
-        for (int nt = c1p >> 3, hi = (c1 + 7) >> 3; nt < hi; nt += 2) put(0, nt * 8, (d + 15) >> 4, nt + 1 < hi);
+        for (int nt = c1p >> 3, hi = (c1 + 7) >> 3; nt < hi; nt += 2) put(0, nt * 8, even((d + 15) >> 4), nt + 1 < hi);
       if (c2 > c2p)   // layer-2 units of degree d: layer-1 units of degree <= d
-        for (int nt = c2p >> 3, hi = (c2 + 7) >> 3; nt < hi; nt += 2) put(1, nt * 8, (c1 + 15) >> 4, nt + 1 < hi);
+        for (int nt = c2p >> 3, hi = (c2 + 7) >> 3; nt < hi; nt += 2) {
+          put(1, nt * 8, even((c1 + 15) >> 4), nt + 1 < hi);
+          if (push && n <= cap) {   // output tiles (8 rows of [mu | alpha]) holding an output i >= d
+            int mask = 0;
+            for (int t = 0; t < N3p / 8; ++t)
+              if ((8 * t + 7 >= d && 8 * t < D) || (8 * t + 7 >= D + d && 8 * t < 2 * D)) mask |= 1 << t;
+            jobs[8 * (n - 1) + 6] = mask;
+          }
+        }
     }
     put(2, d, push ? 0 : (c2 + 15) >> 4, 0);   // (mu_d, alpha_d): layer-2 units of degree <= d (push: already summed)
   }

@@ -479,7 +479,8 @@ __global__ void __launch_bounds__(384) made_inverse_push_kernel(const MiArgs p) 
   for (int tile = 0; tile < my_tiles; ++tile) {
     const long long base = ((static_cast<long long>(tile) * gridDim.x + blockIdx.x) * cwarps + warp) * R;
     float ldacc[2], unext[2];
-    const float* urow[2];
+    const float* urow[2];        // lanes t == 0: rows of u and x of this lane's two samples (null past the batch end)
+    float* xrow[2];
     float out[NO][4];            // running (mu | alpha) sums: C fragments of the [16 samples x N3p] output
 #pragma unroll
     for (int n = 0; n < NO; ++n)
@@ -494,6 +495,7 @@ __global__ void __launch_bounds__(384) made_inverse_push_kernel(const MiArgs p) 
         const long long b = base + g + 8 * hh;
         ldacc[hh] = 0.f;
         urow[hh] = (t == 0 && b < p.B) ? p.u_in + b * D : nullptr;
+        xrow[hh] = p.x + b * D;
         unext[hh] = urow[hh] ? __ldg(urow[hh] + (p.flip ? D - 1 : 0)) : 0.f;
       }
       __syncwarp();
@@ -584,17 +586,26 @@ __global__ void __launch_bounds__(384) made_inverse_push_kernel(const MiArgs p) 
         if (lane == 0) mbar_arrive(&empty[slot]);
         const int nm = d >> 3, cm = d & 7, na = (D + d) >> 3, ca = (D + d) & 7;
         float m0 = 0.f, m1 = 0.f, l0 = 0.f, l1v = 0.f;
-#pragma unroll
-        for (int n = 0; n < NO; ++n) {
-          if (n == nm) {
-            m0 = (cm & 1) ? out[n][1] : out[n][0];
-            m1 = (cm & 1) ? out[n][3] : out[n][2];
-          }
-          if (n == na) {
-            l0 = (ca & 1) ? out[n][1] : out[n][0];
-            l1v = (ca & 1) ? out[n][3] : out[n][2];
-          }
-        }
+        // (a real switch = one indexed branch; an unrolled chain of n == nm tests costs 4 instructions per tile)
+#define MI_PICK(N, ODD, V0, V1)                \
+  case N:                                      \
+    if (N < NO) {                              \
+      V0 = (ODD) ? out[N < NO ? N : 0][1] : out[N < NO ? N : 0][0]; \
+      V1 = (ODD) ? out[N < NO ? N : 0][3] : out[N < NO ? N : 0][2]; \
+    }                                          \
+    break;
+#define MI_PICK_ALL(SEL, ODD, V0, V1)                                                                      \
+  switch (SEL) {                                                                                           \
+    MI_PICK(0, ODD, V0, V1) MI_PICK(1, ODD, V0, V1) MI_PICK(2, ODD, V0, V1) MI_PICK(3, ODD, V0, V1)        \
+    MI_PICK(4, ODD, V0, V1) MI_PICK(5, ODD, V0, V1) MI_PICK(6, ODD, V0, V1) MI_PICK(7, ODD, V0, V1)        \
+    MI_PICK(8, ODD, V0, V1) MI_PICK(9, ODD, V0, V1) MI_PICK(10, ODD, V0, V1) MI_PICK(11, ODD, V0, V1)      \
+    MI_PICK(12, ODD, V0, V1) MI_PICK(13, ODD, V0, V1) MI_PICK(14, ODD, V0, V1) MI_PICK(15, ODD, V0, V1)    \
+    default: break;                                                                                        \
+  }
+        MI_PICK_ALL(nm, cm & 1, m0, m1)
+        MI_PICK_ALL(na, ca & 1, l0, l1v)
+#undef MI_PICK_ALL
+#undef MI_PICK
         const int srcm = (lane & ~3) | (cm >> 1), srca = (lane & ~3) | (ca >> 1);
         m0 = __shfl_sync(0xffffffffu, m0, srcm);
         m1 = __shfl_sync(0xffffffffu, m1, srcm);
@@ -605,7 +616,7 @@ __global__ void __launch_bounds__(384) made_inverse_push_kernel(const MiArgs p) 
           for (int hh = 0; hh < 2; ++hh) {
             const float mu = (hh ? m1 : m0) + bv.x, al = (hh ? l1v : l0) + bv.y;
             const float xv = uv[hh] * expf(al) + mu;
-            if (urow[hh]) p.x[(urow[hh] - p.u_in) + d] = xv;
+            if (urow[hh]) xrow[hh][d] = xv;
             xb[(g + 8 * hh) * ldx + d] = __float2bfloat16_rn(xv);
             ldacc[hh] += al;
           }

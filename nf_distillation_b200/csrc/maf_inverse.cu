@@ -401,9 +401,13 @@ __global__ void __launch_bounds__(384) made_inverse_push_kernel(const MiArgs p) 
   uint64_t* full = reinterpret_cast<uint64_t*>(mi_smem + p.ring_bytes);
   uint64_t* empty = full + MI_SLOTS;
   uint4* jobs_s = reinterpret_cast<uint4*>(mi_smem + p.ring_bytes + 256);
-  unsigned char* act = mi_smem + p.ring_bytes + 256 + p.njobs * 16;
+  float* bias_s = reinterpret_cast<float*>(mi_smem + p.ring_bytes + 256 + p.njobs * 16);   // [b1 | b2 | b3 (N3p)]
+  unsigned char* act = mi_smem + p.ring_bytes + 256 + p.njobs * 16 + (2 * H + N3p) * 4;
   const uint32_t ring_s = smem_u32(mi_smem);
   for (int i = threadIdx.x; i < p.njobs; i += blockDim.x) jobs_s[i] = mi_pack_job(__ldg(p.jobs + 2 * i), __ldg(p.jobs + 2 * i + 1));
+  // the biases live in shared memory: an L2 round trip per job sat on every warp's dependent chain
+  for (int i = threadIdx.x; i < 2 * H + N3p; i += blockDim.x)
+    bias_s[i] = i < H ? __ldg(p.b1 + i) : i < 2 * H ? __ldg(p.b2 + i - H) : (i - 2 * H < 2 * D ? __ldg(p.b3 + i - 2 * H) : 0.f);
   if (threadIdx.x == 0) {
     for (int s = 0; s < MI_SLOTS; ++s) {
       mbar_init(&full[s], 1);
@@ -457,24 +461,6 @@ __global__ void __launch_bounds__(384) made_inverse_push_kernel(const MiArgs p) 
   // a tile block is [N3p outputs][8 units] dense: 8 rows x 16 bytes = all 32 banks once
   const uint32_t pb_lane = ((lane >> 3) & 1) * (N3p * 16) + (((lane >> 4) << 3) + (lane & 7)) * 16;
 
-  auto fetch_bias = [&](uint32_t jd) -> float4 {
-    const int phase = jd & 3, row0 = jd >> 11;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (phase < 2) {
-      const float* bias = (phase == 0 ? p.b1 : p.b2) + row0 + 2 * t;
-      v.x = __ldg(bias);
-      v.y = __ldg(bias + 1);
-      if (jd & 4) {
-        v.z = __ldg(bias + 8);
-        v.w = __ldg(bias + 9);
-      }
-    } else {
-      v.x = __ldg(p.b3 + row0);
-      v.y = __ldg(p.b3 + D + row0);
-    }
-    return v;
-  };
-
   int slot = 0, par = 0;
   for (int tile = 0; tile < my_tiles; ++tile) {
     const long long base = ((static_cast<long long>(tile) * gridDim.x + blockIdx.x) * cwarps + warp) * R;
@@ -501,16 +487,11 @@ __global__ void __launch_bounds__(384) made_inverse_push_kernel(const MiArgs p) 
       __syncwarp();
     }
     uint4 jd = jobs_s[0];
-    float4 bnext = fetch_bias(jd.x);
     for (int j = 0; j < njobs; ++j) {
       const uint32_t cur = jd.x;
-      const float4 bv = bnext;
       const int phase = cur & 3, kch = (cur >> 3) & 255, row0 = cur >> 11;
       const uint32_t job_s = ring_s + (jd.y & 0xffff) * 16, live = jd.w >> 16;
-      if (j + 1 < njobs) {
-        jd = jobs_s[j + 1];
-        bnext = fetch_bias(jd.x);
-      }
+      if (j + 1 < njobs) jd = jobs_s[j + 1];
 
       if (phase < 2) {
         const bool l1 = phase == 0, two = (cur & 4) != 0;
@@ -523,6 +504,8 @@ __global__ void __launch_bounds__(384) made_inverse_push_kernel(const MiArgs p) 
           for (int c = 0; c < 2; ++c)
 #pragma unroll
             for (int e = 0; e < 4; ++e) acc[n][c][e] = 0.f;
+        const float* bsrc = bias_s + (l1 ? 0 : H) + row0 + 2 * t;   // columns row0 + 2t, + 1 (tile 0) and + 8 (tile 1)
+        const float2 bv01 = *reinterpret_cast<const float2*>(bsrc), bv23 = *reinterpret_cast<const float2*>(bsrc + 8);
         mbar_wait(&full[slot], par);
         // k-chunk counts are even (the host rounds up: the extra chunk meets masked-zero weights); fragments are
         // requested one chunk ahead, the last request of a job reads past its last chunk and is never used
@@ -541,10 +524,10 @@ __global__ void __launch_bounds__(384) made_inverse_push_kernel(const MiArgs p) 
         }
         // bias + ReLU + bf16: rows g / g + 8, columns row0 + 2t, + 1 (tile 0) and row0 + 8 + 2t, + 1 (tile 1)
         uint32_t hA[4];
-        hA[0] = mi_pack_relu(acc[0][0][0] + acc[0][1][0] + bv.x, acc[0][0][1] + acc[0][1][1] + bv.y);
-        hA[1] = mi_pack_relu(acc[0][0][2] + acc[0][1][2] + bv.x, acc[0][0][3] + acc[0][1][3] + bv.y);
-        hA[2] = two ? mi_pack_relu(acc[1][0][0] + acc[1][1][0] + bv.z, acc[1][0][1] + acc[1][1][1] + bv.w) : 0u;
-        hA[3] = two ? mi_pack_relu(acc[1][0][2] + acc[1][1][2] + bv.z, acc[1][0][3] + acc[1][1][3] + bv.w) : 0u;
+        hA[0] = mi_pack_relu(acc[0][0][0] + acc[0][1][0] + bv01.x, acc[0][0][1] + acc[0][1][1] + bv01.y);
+        hA[1] = mi_pack_relu(acc[0][0][2] + acc[0][1][2] + bv01.x, acc[0][0][3] + acc[0][1][3] + bv01.y);
+        hA[2] = two ? mi_pack_relu(acc[1][0][0] + acc[1][1][0] + bv23.x, acc[1][0][1] + acc[1][1][1] + bv23.y) : 0u;
+        hA[3] = two ? mi_pack_relu(acc[1][0][2] + acc[1][1][2] + bv23.x, acc[1][0][3] + acc[1][1][3] + bv23.y) : 0u;
         if (l1) {
           __syncwarp();
           if (lane == 0) mbar_arrive(&empty[slot]);
@@ -614,7 +597,7 @@ __global__ void __launch_bounds__(384) made_inverse_push_kernel(const MiArgs p) 
         if (t == 0) {
 #pragma unroll
           for (int hh = 0; hh < 2; ++hh) {
-            const float mu = (hh ? m1 : m0) + bv.x, al = (hh ? l1v : l0) + bv.y;
+            const float mu = (hh ? m1 : m0) + bias_s[2 * H + d], al = (hh ? l1v : l0) + bias_s[2 * H + D + d];
             const float xv = uv[hh] * expf(al) + mu;
             if (urow[hh]) xrow[hh][d] = xv;
             xb[(g + 8 * hh) * ldx + d] = __float2bfloat16_rn(xv);
@@ -686,7 +669,7 @@ static inline int mi_job_bytes(int desc, int push, int N3p) {
 }
 // barriers + packed job table + 128 spare bytes at the very end of the allocation (the product loops request one
 // fragment past a row's last k-chunk; for the last row of the last warp that is past the activations)
-static inline int mi_side_bytes(int njobs) { return 256 + njobs * 16 + 128; }   // barriers + packed job table
+static inline int mi_side_bytes(int njobs, int bias_floats = 0) { return 256 + njobs * 16 + bias_floats * 4 + 128; }   // barriers + packed job table
 
 }  // namespace nfk
 
@@ -694,15 +677,18 @@ using namespace nfk;
 
 static constexpr int MI_SMEM_MAX = 227 * 1024;
 
-// Weight ring size for a layer shape: what is left after the barriers, the job table and as many one-tile warps as fit
-// next to a ring of two largest jobs (so that at least two jobs can be in flight).
+// Weight ring size for a layer shape: what is left after the barriers, the job table (the biases) and as many one-tile
+// warps as fit next to a ring of two or three largest jobs.
 static int mi_ring_bytes(int H, int Dp, int njobs, int push, int N3p) {
   const int kmax = (H > Dp ? H : Dp) / 16;
   const int biggest = push ? mi_rows_bytes(16, kmax) + 2 * N3p * 16 : mi_rows_bytes(16, kmax);
-  const int avail = MI_SMEM_MAX - mi_side_bytes(njobs);
+  const int avail = MI_SMEM_MAX - mi_side_bytes(njobs, push ? 2 * H + N3p : 0);
   const int per_warp = push ? mi_per_warp_bytes_push(H, Dp) : mi_per_warp_bytes(1, H, Dp);
   const int max_warps = push ? 11 : 8;
-  int warps = (avail - 2 * biggest) / per_warp;
+  // room for three of the largest jobs when that still leaves 8 warps (with two, the copy of job j + 2 cannot start
+  // before job j is released: its latency shows when jobs are few and large, D = 6), else for two
+  int warps = (avail - 3 * biggest) / per_warp;
+  if (warps < 8) warps = (avail - 2 * biggest) / per_warp < 8 ? (avail - 2 * biggest) / per_warp : 8;
   if (warps < 1) return -1;
   if (warps > max_warps) warps = max_warps;
   int ring = (avail - warps * per_warp) & ~127;
@@ -835,7 +821,7 @@ static int mi_launch_push(MiArgs p, cudaStream_t st) {
   const int per_warp = mi_per_warp_bytes_push(p.H, p.Dp);
   p.ring_bytes = mi_ring_bytes(p.H, p.Dp, p.njobs, 1, NO * 8);
   if (p.ring_bytes <= 0) return NFK_ERR_SHAPE;
-  const int fixed = p.ring_bytes + mi_side_bytes(p.njobs);
+  const int fixed = p.ring_bytes + mi_side_bytes(p.njobs, 2 * p.H + NO * 8);
   int warps = (MI_SMEM_MAX - fixed) / per_warp;
   if (warps > 11) warps = 11;
   if (warps < 1) return NFK_ERR_SHAPE;

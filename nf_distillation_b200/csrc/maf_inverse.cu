@@ -7,25 +7,28 @@
 // is known the layer-1 units of degree d are final, then the layer-2 units of degree d (they read layer-1 units of
 // degree <= d only), then (mu_d, alpha_d) (layer-2 units of degree <= d). Total work ~ one forward pass.
 //
-// A CTA owns warps x MT*16 samples for the whole D-step recursion. Each WARP keeps x (bf16), h1 and h2 (bf16, the
-// same roundings the forward GEMM epilogues apply) of its own samples in its slice of shared memory; every product is
-// a warp-level mma.sync.m16n8k16 (bf16 operands, fp32 accumulation) with the activations as the A operand and the
-// masked bf16 weights as the B operand, both through ldmatrix. tcgen05 does not fit this recursion: a step touches
-// 8-16 output columns of a 16-row tile, far below its 64 x 8 x 16 minimum shape with a TMEM round trip per step.
+// Two kernels share the machinery below. A CTA owns warps x 16 samples for the whole D-step recursion; each WARP keeps
+// the bf16 activations of its own samples (the roundings the forward GEMM epilogues apply) in its slice of shared
+// memory; every product is a warp-level mma.sync.m16n8k16 (bf16 operands, fp32 accumulation), activations as the A
+// operand and the masked bf16 weights as the B operand, both through ldmatrix. tcgen05 does not fit this recursion: a
+// step touches 16 output columns of a 16-row tile, far below its tile shapes, with a TMEM round trip per step on the
+// dependent chain.
+//   made_inverse_resident_kernel (PULL): x, h1 and h2 resident; (mu_d, alpha_d) recomputed from h2 at every step.
+//     Any sorted degrees: units go in aligned 8-column tiles, a tile that straddles two degrees is evaluated at both
+//     steps (its not-yet-final columns hold finite scratch values that only meet masked-zero weights).
+//   made_inverse_push_kernel (PUSH, further down): degrees change on whole tiles; finished layer-2 tiles go straight
+//     from their accumulators into running (mu | alpha) sums in registers, h2 never exists in memory.
 // The recursion is a fixed stream of JOBS (step d: layer-1 tile pairs of degree d, layer-2 tile pairs, the
-// (mu_d, alpha_d) row pair), the same for every sample tile, so the host builds the job table once
-// (nfk_made_inverse_jobs), including each job's byte range in a shared-memory weight ring, and the weights are packed
-// once per weight update into one stream, job after job, already in shared-memory layout (nfk_made_inverse_pack). A
-// producer warp copies each job's block into its range with ONE cp.async.bulk (TMA, completion on an mbarrier);
-// the consumer warps wait on the job's "full" barrier, multiply, and release it through its "empty" barrier — no
-// block-wide barrier in the recursion, warps drift apart freely. Jobs are sized by their bytes (a (mu, alpha) row
-// pair is 2 KB, a full layer-2 tile pair 16 KB), so ~50 KB of ring keeps ~a dozen jobs = several microseconds of
-// copies in flight; with three fixed 16 KB stages the consumers waited on the copy latency at every job (0.77 ms). History (B = 65 536, D = 63, H = 512): every warp streaming its B fragments straight
-// from L2 (with 213 KB of shared memory carved out there is no L1 left): 1.62 ms; cp.async ring filled by all
-// threads + __syncthreads per job + the job stream derived on the fly by every thread: 1.12 ms, issue-bound on that
-// bookkeeping (ncu: 1 000 warp instructions per warp and step, 60 % of them index arithmetic).
-// Units are processed in aligned 8-column tiles; a tile that straddles two degrees is evaluated at both steps (the
-// not-yet-final columns hold finite scratch values that only ever meet masked-zero weights before being overwritten).
+// (mu_d, alpha_d) row pair), the same for every sample tile, so the host plans it once (nfk_made_inverse_jobs): per job
+// its byte range in a shared-memory weight ring, the distance back to the job whose bytes it overwrites, and its
+// offset in a packed weight stream that holds every job's weights already in shared-memory layout
+// (nfk_made_inverse_pack, redone when the weights change). A producer warp copies each job's block into its range
+// with ONE cp.async.bulk (completion on the job's "full" mbarrier); consumer warps wait on it, multiply, and release
+// the job through its "empty" mbarrier — no block-wide barrier in the recursion, warps drift apart freely.
+// What bounds it (profiles/r01_prof_maf_inverse.txt): a warp advances about one instruction per 6 cycles whatever the
+// other warps do (a dependent scalar + MMA chain), so a tile costs (instructions per step) x D steps; the measured
+// time followed the instruction count per step and nothing else — not the copy engine (one bulk copy per weight row,
+// 51 per step, ran as fast as one per job), not the ring depth, not the warp count.
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <cstdint>

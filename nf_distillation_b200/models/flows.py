@@ -43,8 +43,40 @@ def get_block_1d(in_features, out_features, hidden_features):
     )
 
 
+class _PermutationAsLU:
+    """A fixed channel permutation (Permute2d: flow_permutation 'shuffle' / 'reverse', reference flows.py:85-95) in the
+    LU parametrisation the kernels take: W = P (L + I)(U + diag(sign_s e^{log_s})) with L = U = 0, log_s = 0,
+    sign_s = 1 is the permutation matrix itself and log|det W| = 0, so the step runs through the same fused
+    ActNorm o 1x1 kernels (forward, inverse, training) as an invertible conv whose factors never train. Nothing here
+    is a Parameter or a buffer: the reference's Permute2d has neither, so the state_dict keys stay identical."""
+
+    LU_decomposed = True
+
+    def __init__(self, perm: Permute2d):
+        self.perm = perm
+        self._key = None
+        self.lower = self.upper = self.log_s = self.p = self.sign_s = None
+
+    def sync(self, device):
+        idx = self.perm.indices
+        key = (tuple(idx.tolist()), str(device))
+        if key != self._key:
+            C = idx.numel()
+            p = torch.zeros(C, C)
+            p[torch.arange(C), idx.cpu()] = 1.0          # z[:, o] = x[:, indices[o]]  <=>  W[o, indices[o]] = 1
+            self.p = p.to(device)
+            self.lower, self.upper = torch.zeros(C, C, device=device), torch.zeros(C, C, device=device)
+            self.log_s, self.sign_s = torch.zeros(C, device=device), torch.ones(C, device=device)
+            self._key = key
+        return self
+
+    def lu_tensors(self):
+        return (self.lower, self.upper, self.log_s, self.p, self.sign_s, None)
+
+
 class FlowStep(nn.Module):
-    """actnorm -> invertible 1x1 conv -> affine coupling, forward and inverse (flows.py:55-202)."""
+    """actnorm -> invertible 1x1 conv (or a fixed permutation) -> affine (or additive) coupling, forward and inverse
+    (flows.py:55-202)."""
 
     def __init__(self, in_channels, hidden_channels, actnorm_scale, flow_permutation, flow_coupling, LU_decomposed,
                  is_1d=False, condition_features=0):
@@ -63,10 +95,12 @@ class FlowStep(nn.Module):
             if is_1d:
                 raise RuntimeError("Permutation is not supported is 1d mode")
             self.shuffle = Permute2d(in_channels, shuffle=True)
+            self.invconv = _PermutationAsLU(self.shuffle)      # (plain attribute: not a sub-module, no state)
         else:
             if is_1d:
                 raise RuntimeError("Permutation is not supported is 1d mode")
             self.reverse = Permute2d(in_channels, shuffle=False)
+            self.invconv = _PermutationAsLU(self.reverse)
 
         if flow_coupling == "additive":
             out_block = in_channels - in_channels // 2
@@ -82,11 +116,23 @@ class FlowStep(nn.Module):
     # ---- parameter views in the order the kernels expect
     def _coupling_params_2d(self):
         b = self.block
+        w3, b3, l3 = b[4].conv.weight, b[4].conv.bias, b[4].logs
+        if self.flow_coupling == "additive":
+            # z2 + block(z1) (reference flows.py:157-158) on the affine kernels with the scale pinned to one: the
+            # Conv2dZeros gets interleaved 'logit' rows with zero weights and bias 30, so sigmoid(30 + 2) == 1.0f and
+            # log sigmoid = -1.3e-14 per element. Built with differentiable ops: gradients reach the real rows only.
+            w3 = torch.stack((w3, torch.zeros_like(w3)), 1).flatten(0, 1)
+            b3 = torch.stack((b3, torch.full_like(b3, 30.0)), 1).flatten()
+            l3 = torch.stack((l3, torch.zeros_like(l3)), 1).flatten(0, 1)
         return (b[0].conv.weight, b[0].actnorm.bias, b[0].actnorm.logs,
-                b[2].conv.weight, b[2].actnorm.bias, b[2].actnorm.logs,
-                b[4].conv.weight, b[4].conv.bias, b[4].logs)
+                b[2].conv.weight, b[2].actnorm.bias, b[2].actnorm.logs, w3, b3, l3)
+
+    def _sync_permutation(self):
+        if isinstance(self.invconv, _PermutationAsLU):
+            self.invconv.sync(self.actnorm.bias.device)
 
     def _all_params(self):
+        self._sync_permutation()
         inv = [t for t in self.invconv.lu_tensors() if t is not None]
         blk = list(self.block.parameters())
         return [self.actnorm.bias, self.actnorm.logs, *inv, *blk]
@@ -111,14 +157,14 @@ class FlowStep(nn.Module):
 
     def _batched_prep_ok(self):
         """True when this step's fused affine can be built by the batched K0 launch (functional.PrepCtx)."""
-        return (self.flow_permutation_type == "invconv" and self.invconv.LU_decomposed
-                and self.flow_coupling == "affine")
+        self._sync_permutation()
+        return bool(self.invconv.LU_decomposed)
 
     def _check_supported(self, input):
         _require_cuda(input, "FlowStep")
-        if self.flow_permutation_type != "invconv" or self.flow_coupling != "affine":
-            raise NotImplementedError("the CUDA path covers flow_permutation='invconv' + flow_coupling='affine' "
-                                      "(every shipped config); shuffle/reverse/additive are not built yet")
+        if self.is_1d and self.flow_coupling != "affine":
+            raise NotImplementedError("additive coupling is built for the 2-D steps only (every 1-D config is affine)")
+        self._sync_permutation()
         if self.is_1d:
             from .. import ops
             training = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())

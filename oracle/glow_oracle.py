@@ -146,14 +146,29 @@ def coupling_net(x: Tensor, sd: SD, pre: str) -> Tensor:
     return h
 
 
+def permute(x: Tensor, perm: Tensor, reverse: bool) -> Tensor:
+    """Permute2d (models/layers.py:263-290): forward input[:, indices], reverse input[:, indices_inverse]; no log-det."""
+    perm = torch.as_tensor(perm, dtype=torch.long)
+    if reverse:
+        inv = torch.empty_like(perm)
+        inv[perm] = torch.arange(perm.numel())
+        perm = inv
+    return x[:, perm]
+
+
 def flowstep(x: Tensor, sd: SD, pre: str, logdet: Tensor, reverse: bool, y_onehot=None,
-             coupling: str = "affine") -> Tuple[Tensor, Tensor]:
-    """FlowStep.normal_flow / reverse_flow (models/flows.py:142-202): actnorm -> invconv -> coupling, where the
-    affine coupling is z2 = (z2 + shift) * sigmoid(s + 2) with shift = h[:,0::2], s = h[:,1::2]."""
+             coupling: str = "affine", perm=None) -> Tuple[Tensor, Tensor]:
+    """FlowStep.normal_flow / reverse_flow (models/flows.py:142-202): actnorm -> invconv (or, with `perm` = the
+    step's Permute2d.indices, the fixed shuffle / reverse permutation, flows.py:85-95) -> coupling, where the affine
+    coupling is z2 = (z2 + shift) * sigmoid(s + 2) with shift = h[:,0::2], s = h[:,1::2] and the additive one is
+    z2 = z2 + h (flows.py:157-158)."""
     red = lambda t: t.flatten(1).sum(1)
     if not reverse:
         z, logdet = actnorm(x, sd[pre + "actnorm.bias"], sd[pre + "actnorm.logs"], logdet, False)
-        z, logdet = invconv(z, sd, pre + "invconv.", logdet, False)
+        if perm is None:
+            z, logdet = invconv(z, sd, pre + "invconv.", logdet, False)
+        else:
+            z = permute(z, perm, False)
     else:
         z = x
     c1 = z.shape[1] // 2
@@ -172,7 +187,10 @@ def flowstep(x: Tensor, sd: SD, pre: str, logdet: Tensor, reverse: bool, y_oneho
             logdet = logdet + red(torch.log(scale))
     z = torch.cat((z1, z2), 1)
     if reverse:
-        z, logdet = invconv(z, sd, pre + "invconv.", logdet, True)
+        if perm is None:
+            z, logdet = invconv(z, sd, pre + "invconv.", logdet, True)
+        else:
+            z = permute(z, perm, True)
         z, logdet = actnorm(z, sd[pre + "actnorm.bias"], sd[pre + "actnorm.logs"], logdet, True)
     return z, logdet
 
@@ -209,6 +227,14 @@ def prior(sd: SD, cfg: dict, batch: int, y_onehot: Optional[Tensor] = None) -> T
     return h[:, :c], h[:, c:]
 
 
+def step_perm(cfg: dict, i: int):
+    """Permute2d.indices of layer i for flow_permutation 'shuffle' / 'reverse' (they are plain attributes, not in the
+    state_dict, so they travel in cfg["perm_indices"] = {str(layer index): [indices]}); None for 'invconv'."""
+    if cfg.get("flow_permutation", "invconv") == "invconv":
+        return None
+    return cfg["perm_indices"][str(i)]
+
+
 def glow_forward(sd: SD, cfg: dict, x: Tensor, noise: Optional[Tensor] = None, y_onehot: Optional[Tensor] = None):
     """GlowGetAllOutputs.normal_flow (models/kd_flows.py:121-152): returns (all layer outputs, bpd|nll [B]).
 
@@ -232,7 +258,7 @@ def glow_forward(sd: SD, cfg: dict, x: Tensor, noise: Optional[Tensor] = None, y
             z = squeeze2d(z)
         elif kind == "step":
             z, logdet = flowstep(z, sd, pre, logdet, False, y_onehot=y_onehot if cfg.get("y_condition") else None,
-                                 coupling=cfg.get("flow_coupling", "affine"))
+                                 coupling=cfg.get("flow_coupling", "affine"), perm=step_perm(cfg, i))
         else:
             z, logdet = split2d_forward(z, sd, pre, logdet)
         outs.append(z)
@@ -257,7 +283,7 @@ def glow_reverse(sd: SD, cfg: dict, z: Tensor, temperature: float = 0.0,
             z = unsqueeze2d(z)
         elif kind == "step":
             z, _ = flowstep(z, sd, pre, dummy, True, y_onehot=y_onehot if cfg.get("y_condition") else None,
-                            coupling=cfg.get("flow_coupling", "affine"))
+                            coupling=cfg.get("flow_coupling", "affine"), perm=step_perm(cfg, i))
         else:
             z = split2d_reverse(z, sd, pre, temperature, None if eps is None else eps[k])
             k += 1

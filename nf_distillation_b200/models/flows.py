@@ -311,12 +311,25 @@ class Glow(nn.Module):
             if self.is_1d:
                 h = self.learn_top_fn(h)
             else:
-                raise NotImplementedError("learn_top for 2-D is not built (learn_top: false in every config)")
+                # Conv2dZeros over the prior buffer (flows.py:344-352). The buffer is all zeros (it is created as zeros
+                # and nothing ever writes it), so every tap of the 3x3 conv multiplies zero and what is left is one
+                # constant per channel, (0 + bias) * exp(3 * logs): parameter-space arithmetic, no kernel.
+                if self._prior_h_nonzero():
+                    raise NotImplementedError("learn_top over a non-zero prior_h buffer is not built")
+                f = self.learn_top_fn
+                row = f.conv.bias * torch.exp(f.logs.view(-1) * f.logscale_factor)
+                h = h + row.view(1, channels, 1, 1)
         if self.y_condition:
             assert y_onehot is not None
             yp = self.project_ycond(y_onehot)
             h = h + yp.view(h.shape[0], channels, *([1] * (h.dim() - 2)))
         return split_feature(h, "split")
+
+    def _prior_h_nonzero(self):
+        key = (self.prior_h.data_ptr(), self.prior_h._version)
+        if getattr(self, "_ph_key", None) != key:
+            self._ph_key, self._ph_nonzero = key, bool((self.prior_h != 0).any())
+        return self._ph_nonzero
 
     def _prior_rows(self):
         """Batch-independent (mean, logs) rows when the prior is the fixed buffer (all shipped non-RICH configs)."""

@@ -215,10 +215,17 @@ def split2d_reverse(z1: Tensor, sd: SD, pre: str, temperature: float, eps: Optio
 
 # ------------------------------------------------------------------------------------------ whole model
 def prior(sd: SD, cfg: dict, batch: int, y_onehot: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
-    """Glow.prior with learn_top = False (models/flows.py:367-391): prior_h repeated, plus the LinearZeros projection
-    of y_onehot when y_condition (models/layers.py:173-187: linear(x) * exp(3 * logs)), split in halves."""
+    """Glow.prior (models/flows.py:367-391): prior_h repeated, through learn_top_fn when learn_top (Conv2dZeros in 2-D,
+    LinearZeros in 1-D: models/flows.py:344-352), plus the LinearZeros projection of y_onehot when y_condition
+    (models/layers.py:173-187: linear(x) * exp(3 * logs)), split in halves."""
     h = sd["prior_h"]
     h = h.expand(batch, *h.shape[1:])
+    if cfg.get("learn_top", False):
+        if h.dim() == 4:
+            h = conv_zeros(h, sd, "learn_top_fn.")
+        else:
+            h = torch.nn.functional.linear(h, sd["learn_top_fn.linear.weight"], sd["learn_top_fn.linear.bias"])
+            h = h * torch.exp(sd["learn_top_fn.logs"] * 3.0)
     if cfg.get("y_condition", False):
         yp = torch.nn.functional.linear(y_onehot, sd["project_ycond.linear.weight"], sd["project_ycond.linear.bias"])
         yp = yp * torch.exp(sd["project_ycond.logs"] * 3.0)

@@ -49,6 +49,7 @@ def randomise(model, gen, std=0.05):
     with torch.no_grad():
         for name, p in model.named_parameters():
             if name.endswith(("actnorm.bias", "actnorm.logs", ".logs")) or ".block.4." in name or \
+                    name.startswith("learn_top_fn.") or \
                     (".conv.conv." in name) or name.endswith(("conv.logs",)):
                 p.copy_(torch.randn(p.shape, generator=gen) * std)
             elif name.endswith(("invconv.lower", "invconv.upper", "invconv.log_s")):
@@ -202,6 +203,9 @@ def main(only=None):
     forward_fixture("glow2d_16_affine_reverse_k2_h64",
                     base_cfg(image_shape=[16, 16, 3], K=2, L=2, hidden_channels=64, flow_permutation="reverse"),
                     B=3, seed=19)
+    # learn_top: the prior's mean / logs come from a Conv2dZeros over the (all-zero) prior buffer
+    forward_fixture("glow2d_16_learntop_k1_h64",
+                    base_cfg(image_shape=[16, 16, 3], K=1, L=2, hidden_channels=64, learn_top=True), B=3, seed=29)
     # 1-D Glow (tabular): POWER-shaped D=6 and BSDS300-shaped D=63 (odd D: z1=31, z2=32)
     forward_fixture("glow1d_d6_k5_h32", base_cfg(image_shape=[6], K=5, L=1, hidden_channels=32, is_1d=True,
                                                   y_classes=0), B=64, seed=11)

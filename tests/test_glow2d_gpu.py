@@ -197,7 +197,7 @@ def test_fused_conv3_coupling_matches_two_kernel_path_and_torch(B, C, H, reverse
     assert rel(hsf.view(B, H, W, C).permute(0, 3, 1, 2), out) < 1e-4
 
 
-VARIANTS = ["glow2d_16_additive_shuffle_k2_h64", "glow2d_16_affine_reverse_k2_h64"]
+VARIANTS = ["glow2d_16_additive_shuffle_k2_h64", "glow2d_16_affine_reverse_k2_h64", "glow2d_16_learntop_k1_h64"]
 
 
 def build_variant(name):
@@ -206,7 +206,7 @@ def build_variant(name):
     from nf_distillation_b200.models import create_glow_model
     d = load(name)
     cfg = cfg_of(d)
-    perms = cfg.pop("perm_indices")
+    perms = cfg.pop("perm_indices", {})
     m = create_glow_model(cfg)
     m.load_state_dict(state_dict_of(d))
     for i, layer in enumerate(m.flow.layers):
@@ -219,8 +219,8 @@ def build_variant(name):
 
 @pytest.mark.parametrize("name", VARIANTS)
 def test_additive_coupling_and_fixed_permutations_golden(name, patched_noise):
-    """flow_coupling='additive' and flow_permutation='shuffle' / 'reverse' (reference flows.py:85-95,157-158; no shipped
-    config uses them) against vectors recorded from the unmodified reference: forward outputs and bpd, inverse,
+    """flow_coupling='additive', flow_permutation='shuffle' / 'reverse' and learn_top (reference flows.py:85-95,157-158,
+    344-352; no shipped config uses them) against vectors recorded from the unmodified reference: forward outputs and bpd, inverse,
     per-step log-dets and round trip, and the gradients of mean bpd against the oracle's autograd (CPU fp32)."""
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     from oracle import glow_oracle as O

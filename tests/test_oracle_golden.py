@@ -12,7 +12,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from oracle import glow_oracle as O  # noqa: E402
 
 FWD = ["glow2d_cifar_k2_h64", "glow2d_16_k1_h64", "glow1d_d6_k5_h32", "glow1d_d63_k5_h32",
-       "glow2d_16_additive_shuffle_k2_h64", "glow2d_16_affine_reverse_k2_h64"]
+       "glow2d_16_additive_shuffle_k2_h64", "glow2d_16_affine_reverse_k2_h64", "glow2d_16_learntop_k1_h64"]
 
 
 def close(a, b, rtol=1e-5, atol=None):

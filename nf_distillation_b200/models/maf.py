@@ -128,6 +128,7 @@ class MADE(nn.Module):
         self._cache = None
         self._job_cache = None
         self._stream_cache = None
+        self._stream_bytes = 0
         self.push_inverse = True         # False: the pull kernel (h2 kept in shared memory) even for aligned degrees
         self.resident_inverse = True     # False: the D-pass GEMM inverse (kept as the cross-check in the tests)
         self.resident_mtiles = 0         # 16-sample tiles per warp in the resident inverse (0 = chosen by the library)
@@ -150,6 +151,7 @@ class MADE(nn.Module):
                     push = jobs is not None
                 if jobs is None:
                     jobs = ops.made_inverse_jobs(cnt1, cnt2, self.D, self.H, self.Dp)
+                self._stream_bytes = int(jobs[:, 5].sum()) * 16     # (host tensor: no device sync later)
                 jobs = jobs.to(dev)
             self._job_cache = (key, (jobs, push))
         return self._job_cache[1]
@@ -158,8 +160,7 @@ class MADE(nn.Module):
         """The packed weight stream of the resident inverse for the current operands (rebuilt when they change)."""
         key = (jobs.data_ptr(), push, ops_[0].data_ptr(), ops_[0]._version)
         if self._stream_cache is None or self._stream_cache[0] != key:
-            nbytes = int(jobs[:, 5].sum().item()) * 16
-            ws = torch.zeros(max(nbytes, 128), device=jobs.device, dtype=torch.uint8)
+            ws = torch.zeros(max(self._stream_bytes, 128), device=jobs.device, dtype=torch.uint8)
             ops.made_inverse_pack(jobs, ops_[0], ops_[2], ops_[4], self.N3p, self.D, self.H, self.Dp, push, ws)
             self._stream_cache = (key, ws, ops_[0])   # (keeps B1 alive so the pointer in the key cannot be reused)
         return self._stream_cache[1]

@@ -87,13 +87,16 @@ __device__ __forceinline__ uint32_t mi_pack_relu(float a, float b) {
   return *reinterpret_cast<const uint32_t*>(&v);
 }
 
-// job descriptor in 4 x 32 bits: x = phase [0,2) | second tile [2] | k-chunks [3,11) | first row (phase 2: d) [11,32)
+// job descriptor in 4 x 32 bits: x = phase [0,2) | second tile [2] | k-chunks [3,11) | first row (phase 2: d) [11,23)
+//                                   | push kernel: step d finished by this job [23,31), flag [31]
 //                               y = ring offset / 16 [0,16) | jobs back to the latest job whose ring bytes it overwrites [16,32)
 //                               z = offset / 16 in the packed weight stream
 //                               w = bytes / 16 [0,16) (0: the job carries nothing) | push kernel: output tiles fed [16,32)
 __device__ __forceinline__ uint4 mi_pack_job(int4 a, int4 b) {
   const uint32_t back = a.w > 65535 ? 65535u : static_cast<uint32_t>(a.w);
-  return make_uint4(static_cast<uint32_t>(a.x) | (static_cast<uint32_t>(a.y) << 11),
+  // (push kernel) b.w = d + 1 on the last layer-2 job of step d: x_d is finished right after it, no job of its own
+  const uint32_t fin = b.w ? ((static_cast<uint32_t>(b.w - 1) << 23) | (1u << 31)) : 0u;
+  return make_uint4(static_cast<uint32_t>(a.x) | (static_cast<uint32_t>(a.y) << 11) | fin,
                     (static_cast<uint32_t>(a.z) >> 4) | (back << 16), static_cast<uint32_t>(b.x),
                     static_cast<uint32_t>(b.y) | (static_cast<uint32_t>(b.z) << 16));
 }
@@ -489,10 +492,57 @@ __global__ void __launch_bounds__(384) made_inverse_push_kernel(const MiArgs p) 
       }
       __syncwarp();
     }
+    // (mu_d, alpha_d) = columns d and D + d of the running sums -> x_d, its bf16 copy for the next layer-1 tile, log-det
+    auto finalize = [&](const int d) {
+        float uv[2];
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          uv[hh] = unext[hh];
+          unext[hh] = (urow[hh] && d + 1 < D) ? __ldg(urow[hh] + (p.flip ? D - 2 - d : d + 1)) : 0.f;
+        }
+        const int nm = d >> 3, cm = d & 7, na = (D + d) >> 3, ca = (D + d) & 7;
+        float m0 = 0.f, m1 = 0.f, l0 = 0.f, l1v = 0.f;
+        // (a real switch = one indexed branch; an unrolled chain of n == nm tests costs 4 instructions per tile)
+#define MI_PICK(N, ODD, V0, V1)                \
+  case N:                                      \
+    if (N < NO) {                              \
+      V0 = (ODD) ? out[N < NO ? N : 0][1] : out[N < NO ? N : 0][0]; \
+      V1 = (ODD) ? out[N < NO ? N : 0][3] : out[N < NO ? N : 0][2]; \
+    }                                          \
+    break;
+#define MI_PICK_ALL(SEL, ODD, V0, V1)                                                                      \
+  switch (SEL) {                                                                                           \
+    MI_PICK(0, ODD, V0, V1) MI_PICK(1, ODD, V0, V1) MI_PICK(2, ODD, V0, V1) MI_PICK(3, ODD, V0, V1)        \
+    MI_PICK(4, ODD, V0, V1) MI_PICK(5, ODD, V0, V1) MI_PICK(6, ODD, V0, V1) MI_PICK(7, ODD, V0, V1)        \
+    MI_PICK(8, ODD, V0, V1) MI_PICK(9, ODD, V0, V1) MI_PICK(10, ODD, V0, V1) MI_PICK(11, ODD, V0, V1)      \
+    MI_PICK(12, ODD, V0, V1) MI_PICK(13, ODD, V0, V1) MI_PICK(14, ODD, V0, V1) MI_PICK(15, ODD, V0, V1)    \
+    default: break;                                                                                        \
+  }
+        MI_PICK_ALL(nm, cm & 1, m0, m1)
+        MI_PICK_ALL(na, ca & 1, l0, l1v)
+#undef MI_PICK_ALL
+#undef MI_PICK
+        const int srcm = (lane & ~3) | (cm >> 1), srca = (lane & ~3) | (ca >> 1);
+        m0 = __shfl_sync(0xffffffffu, m0, srcm);
+        m1 = __shfl_sync(0xffffffffu, m1, srcm);
+        l0 = __shfl_sync(0xffffffffu, l0, srca);
+        l1v = __shfl_sync(0xffffffffu, l1v, srca);
+        if (t == 0) {
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            const float mu = (hh ? m1 : m0) + bias_s[2 * H + d], al = (hh ? l1v : l0) + bias_s[2 * H + D + d];
+            const float xv = uv[hh] * expf(al) + mu;
+            if (urow[hh]) xrow[hh][d] = xv;
+            xb[(g + 8 * hh) * ldx + d] = __float2bfloat16_rn(xv);
+            ldacc[hh] += al;
+          }
+        }
+        __syncwarp();
+    };
     uint4 jd = jobs_s[0];
     for (int j = 0; j < njobs; ++j) {
       const uint32_t cur = jd.x;
-      const int phase = cur & 3, kch = (cur >> 3) & 255, row0 = cur >> 11;
+      const int phase = cur & 3, kch = (cur >> 3) & 255, row0 = (cur >> 11) & 0xfff;
       const uint32_t job_s = ring_s + (jd.y & 0xffff) * 16, live = jd.w >> 16;
       if (j + 1 < njobs) jd = jobs_s[j + 1];
 
@@ -556,58 +606,15 @@ __global__ void __launch_bounds__(384) made_inverse_push_kernel(const MiArgs p) 
           }
           __syncwarp();
           if (lane == 0) mbar_arrive(&empty[slot]);
+          if (cur >> 31) finalize((cur >> 23) & 0xff);         // last layer-2 job of its step: x_d is complete
         }
         __syncwarp();
       } else {
-        // (mu_d, alpha_d) = columns d and D + d of the running sums
-        const int d = row0;
-        float uv[2];
-#pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-          uv[hh] = unext[hh];
-          unext[hh] = (urow[hh] && d + 1 < D) ? __ldg(urow[hh] + (p.flip ? D - 2 - d : d + 1)) : 0.f;
-        }
+        // a step without layer-2 units of its own degree (step 0; sparse degrees): x_d gets a job of its own
         mbar_wait(&full[slot], par);                           // (empty job: keeps the slot sequence in step)
         __syncwarp();                                          // every lane has seen the phase before the slot is released
         if (lane == 0) mbar_arrive(&empty[slot]);
-        const int nm = d >> 3, cm = d & 7, na = (D + d) >> 3, ca = (D + d) & 7;
-        float m0 = 0.f, m1 = 0.f, l0 = 0.f, l1v = 0.f;
-        // (a real switch = one indexed branch; an unrolled chain of n == nm tests costs 4 instructions per tile)
-#define MI_PICK(N, ODD, V0, V1)                \
-  case N:                                      \
-    if (N < NO) {                              \
-      V0 = (ODD) ? out[N < NO ? N : 0][1] : out[N < NO ? N : 0][0]; \
-      V1 = (ODD) ? out[N < NO ? N : 0][3] : out[N < NO ? N : 0][2]; \
-    }                                          \
-    break;
-#define MI_PICK_ALL(SEL, ODD, V0, V1)                                                                      \
-  switch (SEL) {                                                                                           \
-    MI_PICK(0, ODD, V0, V1) MI_PICK(1, ODD, V0, V1) MI_PICK(2, ODD, V0, V1) MI_PICK(3, ODD, V0, V1)        \
-    MI_PICK(4, ODD, V0, V1) MI_PICK(5, ODD, V0, V1) MI_PICK(6, ODD, V0, V1) MI_PICK(7, ODD, V0, V1)        \
-    MI_PICK(8, ODD, V0, V1) MI_PICK(9, ODD, V0, V1) MI_PICK(10, ODD, V0, V1) MI_PICK(11, ODD, V0, V1)      \
-    MI_PICK(12, ODD, V0, V1) MI_PICK(13, ODD, V0, V1) MI_PICK(14, ODD, V0, V1) MI_PICK(15, ODD, V0, V1)    \
-    default: break;                                                                                        \
-  }
-        MI_PICK_ALL(nm, cm & 1, m0, m1)
-        MI_PICK_ALL(na, ca & 1, l0, l1v)
-#undef MI_PICK_ALL
-#undef MI_PICK
-        const int srcm = (lane & ~3) | (cm >> 1), srca = (lane & ~3) | (ca >> 1);
-        m0 = __shfl_sync(0xffffffffu, m0, srcm);
-        m1 = __shfl_sync(0xffffffffu, m1, srcm);
-        l0 = __shfl_sync(0xffffffffu, l0, srca);
-        l1v = __shfl_sync(0xffffffffu, l1v, srca);
-        if (t == 0) {
-#pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {
-            const float mu = (hh ? m1 : m0) + bias_s[2 * H + d], al = (hh ? l1v : l0) + bias_s[2 * H + D + d];
-            const float xv = uv[hh] * expf(al) + mu;
-            if (urow[hh]) xrow[hh][d] = xv;
-            xb[(g + 8 * hh) * ldx + d] = __float2bfloat16_rn(xv);
-            ldacc[hh] += al;
-          }
-        }
-        __syncwarp();
+        finalize(row0);
       }
       if (++slot == MI_SLOTS) { slot = 0; par ^= 1; }
     }
@@ -688,10 +695,12 @@ static int mi_ring_bytes(int H, int Dp, int njobs, int push, int N3p) {
   const int avail = MI_SMEM_MAX - mi_side_bytes(njobs, push ? 2 * H + N3p : 0);
   const int per_warp = push ? mi_per_warp_bytes_push(H, Dp) : mi_per_warp_bytes(1, H, Dp);
   const int max_warps = push ? 11 : 8;
-  // room for three of the largest jobs when that still leaves 8 warps (with two, the copy of job j + 2 cannot start
-  // before job j is released: its latency shows when jobs are few and large, D = 6), else for two
-  int warps = (avail - 3 * biggest) / per_warp;
-  if (warps < 8) warps = (avail - 2 * biggest) / per_warp < 8 ? (avail - 2 * biggest) / per_warp : 8;
+  // room for four (else three) of the largest jobs when that still leaves 8 warps — with two, the copy of job j + 2
+  // cannot start before job j is released and its latency shows when jobs are few and large (D = 6); a ring of exactly
+  // three wastes its tail on jobs of unequal size — else for two
+  int warps = 0;
+  for (int k = 4; k >= 2 && warps < 8; --k) warps = (avail - k * biggest) / per_warp;
+  if (warps > 8 && (avail - 4 * biggest) / per_warp < 8) warps = 8;   // (k = 3 or 2 chosen for the 8 warps: keep 8)
   if (warps < 1) return -1;
   if (warps > max_warps) warps = max_warps;
   int ring = (avail - warps * per_warp) & ~127;
@@ -748,7 +757,11 @@ extern "C" int nfk_made_inverse_jobs(const int* cnt1, const int* cnt2, int D, in
           }
         }
     }
-    put(2, d, push ? 0 : (c2 + 15) >> 4, 0);   // (mu_d, alpha_d): layer-2 units of degree <= d (push: already summed)
+    if (push && d > 0 && c2 > c2p) {
+      if (n <= cap) jobs[8 * (n - 1) + 7] = d + 1;   // push: the step's last layer-2 job also finishes x_d
+    } else {
+      put(2, d, push ? 0 : (c2 + 15) >> 4, 0);       // (mu_d, alpha_d): layer-2 units of degree <= d (push: already summed)
+    }
   }
   if (n > cap) return n;            // sizing call (or a short buffer): offsets need the whole table
   // ring placement: consecutive byte ranges, wrapping to 0 when a job does not fit before the end; every tile replays

@@ -179,7 +179,10 @@ def test_resident_inverse_job_table_reproduces_the_sequential_inverse():
             if push and (2 * D > 128):
                 assert jobs is None                       # more than 16 output tiles: pull kernel only
                 continue
-            assert jobs.shape[1] == 8 and ((jobs[:, 0] & 3) == 2).sum().item() == D
+            # every x_d is finished exactly once: by a (mu, alpha) job of its own, or (push) by the step's last layer-2 job
+            assert jobs.shape[1] == 8
+            assert ((jobs[:, 0] & 3) == 2).sum().item() + (jobs[:, 7] != 0).sum().item() == D
+            assert push or not (jobs[:, 7] != 0).any()
 
             def size(q):
                 phase, kch, rows = q[0] & 3, q[0] >> 3, (2 if (q[0] & 3) == 2 else (16 if q[0] & 4 else 8))
@@ -202,7 +205,19 @@ def test_resident_inverse_job_table_reproduces_the_sequential_inverse():
             xb, h1, h2 = torch.zeros(19, Dp), torch.zeros(19, H), torch.zeros(19, H)
             out = torch.zeros(19, 2 * D)
             x, ld = torch.zeros(19, D), torch.zeros(19)
-            for desc, row0, *_rest in jl:
+            def finish(d, k):
+                if push:
+                    mu, al = out[:, d] + sd[pre + "fc3.bias"][d], out[:, D + d] + sd[pre + "fc3.bias"][D + d]
+                else:
+                    mu = h2[:, :k] @ W3[d, :k] + sd[pre + "fc3.bias"][d]
+                    al = h2[:, :k] @ W3[D + d, :k] + sd[pre + "fc3.bias"][D + d]
+                x[:, d] = uf[:, d] * torch.exp(al) + mu
+                xb[:, d] = x[:, d]
+                ld.add_(al)
+
+            order = []
+            for q in jl:
+                desc, row0, fin = q[0], q[1], q[7]
                 phase, two, kch = desc & 3, desc & 4, desc >> 3
                 k = kch * 16
                 o = slice(row0, row0 + (16 if two else 8))
@@ -212,17 +227,14 @@ def test_resident_inverse_job_table_reproduces_the_sequential_inverse():
                     h2[:, o] = torch.relu(h1[:, :k] @ W2[o, :k].T + sd[pre + "fc2.bias"][o])
                     if push:
                         out += h2[:, o] @ W3[:, o].T
+                        if fin:
+                            order.append(fin - 1)
+                            finish(fin - 1, 0)
                 else:
-                    d = row0
-                    if push:
-                        assert kch == 0
-                        mu, al = out[:, d] + sd[pre + "fc3.bias"][d], out[:, D + d] + sd[pre + "fc3.bias"][D + d]
-                    else:
-                        mu = h2[:, :k] @ W3[d, :k] + sd[pre + "fc3.bias"][d]
-                        al = h2[:, :k] @ W3[D + d, :k] + sd[pre + "fc3.bias"][D + d]
-                    x[:, d] = uf[:, d] * torch.exp(al) + mu
-                    xb[:, d] = x[:, d]
-                    ld += al
+                    assert not push or kch == 0
+                    order.append(row0)
+                    finish(row0, k)
+            assert order == list(range(D))
             x_o, a_o = MO.made_inverse(u, sd, pre, D)
             assert (x - x_o).abs().max().item() < 1e-5 * (x_o.abs().max().item() + 1), (D, H, push)
             assert (ld - a_o).abs().max().item() < 1e-5 * (a_o.abs().max().item() + 1), (D, H, push)

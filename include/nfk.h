@@ -237,7 +237,9 @@ int nfk_made_inv_update(float* x, void* xb, int Dp, const float* u_in, const flo
  *     cap >= that number, writes 8 int32 per job: {phase (0: layer-1 tile pair, 1: layer-2 tile pair, 2: (mu, alpha))
  *     | second 8-row tile present << 2 | 16-wide k-chunks << 3, first row (phase 2: d), byte offset in the kernel's
  *     weight ring, jobs back to the latest job occupying any of those bytes, offset / 16 in the packed weight
- *     stream, bytes / 16, 0, 0}. Call with cap = 0 to size. Depends on the degrees only.
+ *     stream, bytes / 16, (push) bit mask of the 8-row output tiles the job's units feed, (push) d + 1 when x_d is
+ *     finished right after this job (such a step has no (mu, alpha) job of its own)}. Call with cap = 0 to size.
+ *     Depends on the degrees only.
  *     push = 1 (needs nfk_made_inverse_push_supported and degrees that change only on multiples of 8 units, else
  *     NFK_ERR_SHAPE): the PUSH kernel — layer-2 activations never reach shared memory, each finished 16-unit tile
  *     pair is multiplied straight into running (mu | alpha) sums kept in registers.

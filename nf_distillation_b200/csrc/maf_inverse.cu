@@ -45,7 +45,8 @@ struct MiArgs {
   const unsigned char* wstream; // every job's weight bytes in shared-memory layout, job after job (nfk_made_inverse_pack)
   const float *b1, *b2, *b3;    // [H], [H], [>= 2D]
   const int4* jobs;             // [njobs][2]: {phase | second tile << 2 | k-chunks << 3, row0 (phase 2: d), ring offset,
-                                //              back}, {stream offset / 16, bytes / 16, 0, 0}
+                                //              back}, {stream offset / 16, bytes / 16, push: output tiles fed (bit mask),
+                                //              push: d + 1 when the job also finishes x_d}
   int njobs, ring_bytes;
   float* x;                     // [B, D]
   const float* ld_in;           // [B] or null
@@ -76,7 +77,7 @@ __device__ __forceinline__ void mi_mma(float (&c)[4], const uint32_t (&a)[4], ui
 }
 
 // one contiguous block, global -> shared, completion counted in bytes on `bar`
-__device__ __forceinline__ void mi_bulk_row(uint32_t dst, const void* src, uint32_t bytes, uint64_t* bar) {
+__device__ __forceinline__ void mi_bulk_copy(uint32_t dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
@@ -153,7 +154,7 @@ __global__ void __launch_bounds__(288) made_inverse_resident_kernel(const MiArgs
             mbar_arrive(&full[slot]);
           } else {
             mbar_expect_tx(&full[slot], bytes);
-            mi_bulk_row(ring_s + (cur.y & 0xffff) * 16, p.wstream + static_cast<size_t>(cur.z) * 16, bytes, &full[slot]);
+            mi_bulk_copy(ring_s + (cur.y & 0xffff) * 16, p.wstream + static_cast<size_t>(cur.z) * 16, bytes, &full[slot]);
           }
         }
         if (++slot == MI_SLOTS) { slot = 0; par ^= 1; }
@@ -446,7 +447,7 @@ __global__ void __launch_bounds__(384) made_inverse_push_kernel(const MiArgs p) 
             mbar_arrive(&full[slot]);
           } else {
             mbar_expect_tx(&full[slot], bytes);
-            mi_bulk_row(ring_s + (cur.y & 0xffff) * 16, p.wstream + static_cast<size_t>(cur.z) * 16, bytes, &full[slot]);
+            mi_bulk_copy(ring_s + (cur.y & 0xffff) * 16, p.wstream + static_cast<size_t>(cur.z) * 16, bytes, &full[slot]);
           }
         }
         if (++slot == MI_SLOTS) { slot = 0; par ^= 1; }

@@ -242,3 +242,29 @@ def test_resident_inverse_job_table_reproduces_the_sequential_inverse():
         x_o, a_o = MO.made_inverse(u, sd, pre, D)
         assert (x - x_o).abs().max().item() < 1e-5 * (x_o.abs().max().item() + 1), (D, H)
         assert (ld - a_o).abs().max().item() < 1e-5 * (a_o.abs().max().item() + 1), (D, H)
+
+
+def test_resident_inverse_planner_error_codes():
+    """Host entry points of the resident MADE inverse: bad arguments and unsupported shapes come back as error codes
+    (no GPU touched); push planning refuses degrees that do not change on whole 8-unit tiles."""
+    import ctypes
+    import torch
+    from nf_distillation_b200 import _lib, ops
+    L = _lib.LIB
+    D, H, Dp, N3p = 6, 64, 64, 64
+    good = torch.tensor([0, 16, 24, 40, 48, 64, 64], dtype=torch.int32)          # tile-aligned, non-decreasing
+    ragged = torch.tensor([0, 13, 26, 39, 52, 64, 64], dtype=torch.int32)        # sorted but not tile-aligned
+    falling = torch.tensor([0, 16, 8, 40, 48, 64, 64], dtype=torch.int32)
+    call = lambda c, push: L.nfk_made_inverse_jobs(c.data_ptr(), c.data_ptr(), D, H, Dp, N3p, push, None, 0)
+    assert call(good, 0) > 0 and call(good, 1) > 0
+    assert call(ragged, 0) > 0 and call(ragged, 1) == -1                         # NFK_ERR_SHAPE: pull kernel only
+    assert call(falling, 0) == -3                                                # NFK_ERR_ARG
+    assert L.nfk_made_inverse_jobs(None, None, D, H, Dp, N3p, 0, None, 0) == -3
+    assert L.nfk_made_inverse_jobs(good.data_ptr(), good.data_ptr(), D, 100, Dp, N3p, 0, None, 0) == -1   # H % 64
+    assert ops.made_inverse_jobs(ragged, ragged, D, H, Dp, N3p, push=True) is None
+    assert L.nfk_made_inverse_resident_supported(D, H, Dp) == 1 and L.nfk_made_inverse_push_supported(D, H, Dp, N3p) == 1
+    assert L.nfk_made_inverse_push_supported(100, 64, 128, 256) == 0             # 2D > 128: more than 16 output tiles
+    # launch-side argument checks happen before any CUDA call
+    assert L.nfk_made_inverse_resident(None, None, None, None, None, None, 1, 0, N3p, None, None, None, 4, D, H, Dp,
+                                       1, 0, None) == -3
+    assert L.nfk_made_inverse_pack(None, 1, None, None, None, N3p, D, H, Dp, 0, None, None) == -3

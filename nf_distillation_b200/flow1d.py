@@ -39,7 +39,7 @@ def _pack(step, reverse, with_bwd, affine, ws, bs):
 
 def _consts(step, reverse):
     """No-grad path: packed weights cached until a parameter changes (frozen teacher, sampling)."""
-    key = (reverse, tuple((p.data_ptr(), p._version) for p in step._all_params()))
+    key = (reverse, Fn.param_key(step._all_params()))
     hit = step._cache.get(("1d", reverse))
     if hit is not None and hit[0] == key:
         return hit[1]
@@ -106,7 +106,7 @@ class FlowStep1dFn(torch.autograd.Function):
 def _wide_consts(step, reverse):
     """Frozen wide step (hidden width a multiple of 64 that does not fit the fused kernel, e.g. conf/teacher/rich.yaml:
     256): fused affine of this direction + the six Linear layers as zero-padded bf16 GEMM operands. Cached."""
-    key = (reverse, tuple((p.data_ptr(), p._version) for p in step._all_params()))
+    key = (reverse, Fn.param_key(step._all_params()))
     hit = step._cache.get(("1dw", reverse))
     if hit is not None and hit[0] == key:
         return hit[1]

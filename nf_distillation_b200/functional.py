@@ -18,6 +18,26 @@ F32 = torch.float32
 USE_FUSED_CNET = os.environ.get("NFK_FUSED_CNET", "1") != "0"
 USE_FUSED_PCONV = os.environ.get("NFK_FUSED_PCONV", "1") != "0"
 
+# ------------------------------------------------------------------------------------------------ parameter epoch
+# The no-grad paths cache operands derived from the parameters (fused affine, folded bf16 conv weights, packed MLP /
+# MADE weights) keyed on (data_ptr, _version) of the parameters. An optimiser step replayed from a CUDA graph (or a
+# write through `.data`) changes the values without touching either, so every such key also carries this counter:
+# whoever updates parameters behind autograd's back (train.KDTrainer after each replayed clip+Adam graph) calls
+# `bump_param_epoch()`, which invalidates every cached operand of trainable modules at once.
+_PARAM_EPOCH = [0]
+
+
+def bump_param_epoch() -> None:
+    _PARAM_EPOCH[0] += 1
+
+
+def param_key(params) -> tuple:
+    """Cache key of a parameter set: identity + version of every tensor, plus the global epoch when any of them is
+    trainable (frozen modules — the teacher — keep their operands across optimiser steps)."""
+    params = list(params)
+    epoch = _PARAM_EPOCH[0] if any(p.requires_grad for p in params) else -1
+    return (epoch, tuple((p.data_ptr(), p._version) for p in params))
+
 
 # ------------------------------------------------------------------------------------------------ derived weights
 @dataclass

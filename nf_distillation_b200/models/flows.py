@@ -139,7 +139,7 @@ class FlowStep(nn.Module):
 
     def _consts(self, reverse: bool) -> Fn.StepConsts:
         """Derived tensors for the no-grad path (frozen teacher, sampling): rebuilt only when a parameter changed."""
-        key = (reverse, tuple((p.data_ptr(), p._version) for p in self._all_params()))
+        key = (reverse, Fn.param_key(self._all_params()))
         hit = self._cache.get(reverse)
         if hit is not None and hit[0] == key:
             return hit[1]
@@ -160,8 +160,26 @@ class FlowStep(nn.Module):
         self._sync_permutation()
         return bool(self.invconv.LU_decomposed)
 
+    def _check_actnorm_inited(self, input):
+        """Reference layers.py:129-133: an ActNorm that was never initialised runs its data-dependent init on the first
+        training batch and raises in eval mode. create_glow_model marks every ActNorm initialised (kd_flows.py:155-159),
+        so this only matters for a Glow / FlowStep built directly. The step's own ActNorm is initialised from the input
+        like the reference; the two ActNorms inside the coupling net would need the statistics of the hidden maps, which
+        the fused kernels never materialise: those raise instead of silently running with zero bias / logs."""
+        if not self.actnorm.inited:
+            self.actnorm.initialize_parameters(input)      # (raises ValueError in eval mode, like the reference)
+        if not self.is_1d:
+            for blk in (self.block[0], self.block[2]):
+                if not blk.actnorm.inited:
+                    if not self.training:
+                        raise ValueError("In Eval mode, but ActNorm not inited")
+                    raise NotImplementedError(
+                        "data-dependent ActNorm initialisation inside the fused coupling net is not built; build the "
+                        "model with create_glow_model (or call set_actnorm_init()) as the reference pipeline does")
+
     def _check_supported(self, input):
         _require_cuda(input, "FlowStep")
+        self._check_actnorm_inited(input)
         if self.is_1d and self.flow_coupling != "affine":
             raise NotImplementedError("additive coupling is built for the 2-D steps only (every 1-D config is affine)")
         self._sync_permutation()

@@ -14,6 +14,7 @@ import math
 import torch
 import torch.nn as nn
 
+from .. import functional as Fn
 from .. import ops
 from .layers import _as_logdet, _require_cuda
 
@@ -21,12 +22,16 @@ BF16, F32 = torch.bfloat16, torch.float32
 
 
 def hidden_degrees(D: int, H: int) -> torch.Tensor:
-    """Sorted degrees in [1, D-1], each value ~H/(D-1) times (D == 1 degenerates to all ones). When H is a multiple of
-    8 the degree changes only on multiples of 8 units (whole MMA column tiles), which is what lets the inverse kernel
-    feed a finished layer-2 tile straight from its accumulators into the output sums (csrc/maf_inverse.cu, push)."""
+    """Sorted degrees in [1, D-1], each value ~H/(D-1) times (D == 1 degenerates to all ones): the standard MADE
+    assignment (Germain et al. 2015, eq. 12-13 with deterministic, evenly spread degrees). When H is a multiple of 8
+    AND there are at least D-1 tiles of 8 units, the degree changes only on multiples of 8 units (whole MMA column
+    tiles), which is what lets the inverse kernel feed a finished layer-2 tile straight from its accumulators into the
+    output sums (csrc/maf_inverse.cu, push); every degree 1..D-1 still occurs. With fewer tiles than degrees the
+    tile-aligned form would drop degrees (outputs 2..8 would see only degree-1 units), so the per-unit assignment is
+    used and the inverse runs the pull kernel."""
     if D <= 1:
         return torch.ones(H, dtype=torch.int32)
-    if H % 8 == 0:
+    if H % 8 == 0 and H // 8 >= D - 1:
         tiles = H // 8
         return (torch.arange(tiles, dtype=torch.int64) * (D - 1) // tiles + 1).repeat_interleave(8).to(torch.int32)
     return (torch.arange(H, dtype=torch.int64) * (D - 1) // H + 1).to(torch.int32)
@@ -123,8 +128,7 @@ class MADE(nn.Module):
         deg = hidden_degrees(D, H)
         self.register_buffer("deg1", deg.clone())
         self.register_buffer("deg2", deg.clone())
-        self._ranges = _kb_ranges(deg, deg, self.bn)
-        self._ranges_t = _kb_ranges_t(deg, deg, self.bn)
+        self._range_cache = None
         self._cache = None
         self._job_cache = None
         self._stream_cache = None
@@ -132,6 +136,29 @@ class MADE(nn.Module):
         self.push_inverse = True         # False: the pull kernel (h2 kept in shared memory) even for aligned degrees
         self.resident_inverse = True     # False: the D-pass GEMM inverse (kept as the cross-check in the tests)
         self.resident_mtiles = 0         # 16-sample tiles per warp in the resident inverse (0 = chosen by the library)
+
+    def _kb_ranges_now(self):
+        """(forward, transposed) k-block skip ranges of the H x H masked linear for the CURRENT degree buffers (a
+        loaded checkpoint may carry other degrees than the constructor's). Unsorted degrees have no block-triangular
+        structure to skip: full ranges."""
+        key = (self.deg1.data_ptr(), self.deg1._version, self.deg2.data_ptr(), self.deg2._version)
+        if self._range_cache is None or self._range_cache[0] != key:
+            d1, d2 = self.deg1.detach().cpu().long(), self.deg2.detach().cpu().long()
+            if bool((d1[1:] >= d1[:-1]).all() and (d2[1:] >= d2[:-1]).all()):
+                r, rt = _kb_ranges(d2, d1, self.bn), _kb_ranges_t(d2, d1, self.bn)
+            else:
+                nt, nkb = (self.H + self.bn - 1) // self.bn, self.H // 64
+                r = rt = ([0] * nt, [nkb] * nt)
+            self._range_cache = (key, (r, rt))
+        return self._range_cache[1]
+
+    @property
+    def _ranges(self):
+        return self._kb_ranges_now()[0]
+
+    @property
+    def _ranges_t(self):
+        return self._kb_ranges_now()[1]
 
     def _inverse_jobs(self, dev):
         """(job table on `dev`, push?) of the resident inverse (ops.made_inverse_jobs), from cnt[d] = number of hidden
@@ -227,7 +254,7 @@ class MADE(nn.Module):
         return u, ld_out, ub, ((xb, h1, h2, res[3], res[4], out, ops_[1], ops_[3], ops_[5]) if keep else None)
 
     def _cached_operands(self):
-        key = tuple((p.data_ptr(), p._version) for p in self._params())
+        key = Fn.param_key(self._params())
         if self._cache is None or self._cache[0] != key:
             self._cache = (key, self._operands(tuple(p.detach() for p in self._params()), False))
         return self._cache[1]

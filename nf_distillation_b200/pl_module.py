@@ -14,7 +14,8 @@ import torch
 import torch.nn as nn
 
 from . import functional as Fn
-from .models import FlowStep, SqueezeLayer, create_glow_model, gaussian_sample  # noqa: F401
+from .models import (FlowStep, SqueezeLayer, create_glow_model, gaussian_sample,  # noqa: F401
+                     inherit_permutation_matrix)
 
 TABULAR = ("bsds300", "gas", "hepmass", "miniboone", "power")
 
@@ -37,6 +38,11 @@ class NFModel(nn.Module):
         if config["loss"]["kd"].get("name", "mse") != "mse":
             raise NameError("Unknown KD loss name")
         self.student_kd_indices, self.teacher_kd_indices = self._get_kd_indices()
+        if config.get("inherit_p", False):     # pl_module.py:64-76
+            assert not config["teacher"].get("is_1d", False), "Teacher model must be 3-dimensional"
+            assert not config["student"].get("is_1d", False), "Student model must be 3-dimensional"
+            inherit_permutation_matrix(self.student, self.teacher, self.student_kd_indices,
+                                       self.teacher_kd_indices)
         self.logged: tp.Dict[str, torch.Tensor] = {}
         self.concurrent_teacher = os.environ.get("NFK_CONCURRENT_TEACHER", "1") != "0"
         self._side = None
@@ -77,7 +83,9 @@ class NFModel(nn.Module):
             return None
         cfg = dict(self.params[model_name])
         ckpt = cfg.pop("checkpoint", None)
-        arch = cfg.pop("architecture", "glow")
+        # the reference reads the architecture from the top-level config (pl_module.py:140); a per-model key is also
+        # accepted (bench workloads mix nothing, but a MAF teacher with its own key stays expressible)
+        arch = cfg.pop("architecture", self.params.get("architecture", "glow"))
         if arch == "maf":   # extension: the reference names MAF (README.md:7) but only ever builds "glow"
             from .models.maf import create_maf_model
             model = create_maf_model(cfg)

@@ -25,6 +25,52 @@ SD = Dict[str, Tensor]
 LOG2PI = math.log(2.0 * math.pi)
 
 
+# ------------------------------------------------------------------------------------------ bf16-operand mode
+# The CUDA path runs the three convolutions of the 2-D coupling network (models/flows.py:25-34) on the tensor cores with
+# bf16 OPERANDS and fp32 accumulation; everything else (z path, log-dets, Split2d, prior, losses) is fp32. With
+# `bf16_operands()` active this oracle rounds exactly the same tensors at exactly the same places, so that a CUDA-vs-
+# oracle difference that remains is summation order (1e-6), not operand rounding:
+#   forward   conv inputs (z1, h1, h2) and the folded weights w*exp(logs) / w*exp(3 logs) are rounded to bf16, the biases
+#             b*exp(logs) and all sums stay fp32, h1 / h2 are stored as bf16;
+#   backward  (autograd) the gradients that the CUDA backward stores as bf16 GEMM operands are rounded too: d(pre2),
+#             d(pre1) (after the ReLU mask) and the gradient of the Conv2dZeros output taps; weight / bias gradients and
+#             the gradient of z1 are fp32 sums of those products.
+# The default (flag off) is the reference's plain fp32 arithmetic; the fp32 bounds of the tests are stated against that.
+_BF16 = {"on": False}
+
+
+class bf16_operands:
+    """Context manager: `with bf16_operands(): glow_forward(...)`."""
+
+    def __init__(self, on: bool = True):
+        self.on = on
+
+    def __enter__(self):
+        self.prev, _BF16["on"] = _BF16["on"], self.on
+        return self
+
+    def __exit__(self, *exc):
+        _BF16["on"] = self.prev
+        return False
+
+
+class _Round(torch.autograd.Function):
+    """Round to the nearest bf16 (kept in the tensor's own dtype) in the forward and / or the backward direction."""
+
+    @staticmethod
+    def forward(ctx, x, fwd, bwd):
+        ctx.bwd = bwd
+        return x.to(torch.bfloat16).to(x.dtype) if fwd else x.clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        return (g.to(torch.bfloat16).to(g.dtype) if ctx.bwd else g), None, None
+
+
+def _q(x: Tensor, fwd: bool = True, bwd: bool = False) -> Tensor:
+    return _Round.apply(x, fwd, bwd) if _BF16["on"] else x
+
+
 # ------------------------------------------------------------------------------------------ model topology
 def layer_plan(cfg: dict) -> List[Tuple[str, int, int, int]]:
     """List of (kind, C_in, H, W) in execution order, kind in {squeeze, step, split}.
@@ -119,13 +165,23 @@ def invconv(x: Tensor, sd: SD, pre: str, logdet, reverse: bool) -> Tuple[Tensor,
 def conv_actnorm(x: Tensor, sd: SD, pre: str) -> Tensor:
     """Conv2d: zero-pad 'same' -> bias-free conv -> ActNorm affine (models/layers.py:190-228)."""
     w = sd[pre + "conv.weight"]
+    if _BF16["on"]:   # folded operand bf16(w * exp(logs)) and fp32 bias b * exp(logs) (csrc/prep.cu::coupling_prep)
+        e = torch.exp(sd[pre + "actnorm.logs"])                      # [1, Cout, 1, 1]
+        wf = _q(w * e.view(-1, 1, 1, 1))
+        y = F.conv2d(_q(x), wf, padding=(w.shape[2] // 2, w.shape[3] // 2))
+        return y + sd[pre + "actnorm.bias"] * e
     y = F.conv2d(x, w, padding=(w.shape[2] // 2, w.shape[3] // 2))
     return (y + sd[pre + "actnorm.bias"]) * torch.exp(sd[pre + "actnorm.logs"])
 
 
-def conv_zeros(x: Tensor, sd: SD, pre: str) -> Tensor:
+def conv_zeros(x: Tensor, sd: SD, pre: str, bf16: bool = False) -> Tensor:
     """Conv2dZeros: zero-pad -> conv3x3 + bias -> * exp(3 * logs) (models/layers.py:231-260)."""
     w = sd[pre + "conv.weight"]
+    if _BF16["on"] and bf16:
+        e = torch.exp(sd[pre + "logs"] * 3.0)                        # [Cout, 1, 1]
+        y = F.conv2d(_q(x), _q(w * e.view(-1, 1, 1, 1)), padding=(w.shape[2] // 2, w.shape[3] // 2))
+        # the per-tap products leave the tensor cores in fp32; their GRADIENT is a bf16 dgrad / wgrad operand
+        return _q(y, fwd=False, bwd=True) + (sd[pre + "conv.bias"] * e.view(-1)).view(1, -1, 1, 1)
     y = F.conv2d(x, w, sd[pre + "conv.bias"], padding=(w.shape[2] // 2, w.shape[3] // 2))
     return y * torch.exp(sd[pre + "logs"] * 3.0)
 
@@ -133,9 +189,10 @@ def conv_zeros(x: Tensor, sd: SD, pre: str) -> Tensor:
 def coupling_net(x: Tensor, sd: SD, pre: str) -> Tensor:
     """get_block_2d (models/flows.py:25-34) or get_block_1d (:37-52), chosen by tensor rank."""
     if x.dim() == 4:
-        h = torch.relu(conv_actnorm(x, sd, pre + "0."))
-        h = torch.relu(conv_actnorm(h, sd, pre + "2."))
-        return conv_zeros(h, sd, pre + "4.")
+        # (bf16 mode: h1 / h2 are stored as bf16 and their pre-activation gradients are bf16 operands of the backward)
+        h = _q(torch.relu(conv_actnorm(x, sd, pre + "0.")), bwd=True)
+        h = _q(torch.relu(conv_actnorm(h, sd, pre + "2.")), bwd=True)
+        return conv_zeros(h, sd, pre + "4.", bf16=True)
     h = x
     for i, act in zip((0, 2, 4, 6, 8, 10), ("relu", "relu", "relu", "relu", "tanh", None)):
         h = F.linear(h, sd[f"{pre}{i}.weight"], sd[f"{pre}{i}.bias"])

@@ -176,8 +176,11 @@ def test_resident_inverse_job_table_reproduces_the_sequential_inverse():
         size_rows = lambda rows, kch: (rows * (kch * 32 + 16) + 127) // 128 * 128
         for push in (False, True):
             jobs = ops.made_inverse_jobs(cnt, cnt, D, H, Dp, N3p, push=push)
-            if push and (2 * D > 128):
-                assert jobs is None                       # more than 16 output tiles: pull kernel only
+            aligned = all(int(i + 1) % 8 == 0 for i in (deg[1:] != deg[:-1]).nonzero().flatten())
+            if push and (2 * D > 128 or not aligned):
+                # more than 16 output tiles, or degrees that change inside an 8-unit tile (hidden_degrees keeps the
+                # standard per-unit MADE assignment when there are fewer tiles than degrees): pull kernel only
+                assert jobs is None
                 continue
             # every x_d is finished exactly once: by a (mu, alpha) job of its own, or (push) by the step's last layer-2 job
             assert jobs.shape[1] == 8

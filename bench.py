@@ -1,10 +1,14 @@
 #!/usr/bin/env python
-"""Benchmark of the KD training hot path (BASELINE.json: "KD-train samples/sec (Glow 32x32x3, ...)").
+"""Benchmark of the KD training hot path (BASELINE.json: "KD-train samples/sec (Glow 32x32x3, ...); logp delta").
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl reference] [--workload NAME]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B | --global-batch G] [--impl reference]
+                    [--workload NAME]
 
 One process per GPU (torchrun for N > 1). A step = one KD training step (student fwd, teacher fwd, multi-level
 latent MSE, backward, clip 30, Adam) on one synthetic CIFAR-shaped batch per rank. Prints ONE JSON line.
+
+--impl reference times the reference's CPU algorithm (oracle/ port; the reference is a Python script tree that does not
+travel to the GPU box) and imports NOTHING from the product package.
 """
 from __future__ import annotations
 
@@ -23,36 +27,43 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
 WORKLOADS = {
-    # name: (image_shape, L, hidden, teacher K, student K)
+    # name: image shape, L, hidden, teacher K, student K, per-GPU batch, dtype = the arithmetic type of the GEMM operands
     # per-GPU batch 2048 (weak scaling). The reference's config uses 64 (conf/training/cifar.yaml:7) on its single
-    # GPU; throughput on synthetic data is quoted at a batch that fills a B200 (--batch overrides; measured on one
-    # B200: 39.0 k samples/s at 1024, 42.8 k at 2048, 43.9 k at 4096 — the small upper-level kernels stop being
-    # latency-bound).
-    "glow_cifar_kd_t32_s8": dict(image=(32, 32, 3), L=3, hidden=512, tK=32, sK=8, batch=2048),
+    # GPU (--batch 64 measures that point); throughput on synthetic data is quoted at a batch that fills a B200.
+    "glow_cifar_kd_t32_s8": dict(image=(32, 32, 3), L=3, hidden=512, tK=32, sK=8, batch=2048, dtype="bf16"),
     # BASELINE configs[4]: Glow L=4 K=32 on CelebA-shaped 64x64x3, KD training (level-0 GEMM shape of batch 256 equals
     # CIFAR at batch 1024: 262 144 pixels)
-    "glow_celeba_kd_t32_s8": dict(image=(64, 64, 3), L=4, hidden=512, tK=32, sK=8, batch=256),
+    "glow_celeba_kd_t32_s8": dict(image=(64, 64, 3), L=4, hidden=512, tK=32, sK=8, batch=256, dtype="bf16"),
     # the reference's own CelebA pair (conf/teacher/celeba.yaml, conf/student/celeba.yaml): L=3, teacher K=32 hidden
     # 512, student K=16 hidden 256
     "glow_celeba_ref_kd_t32h512_s16h256": dict(image=(64, 64, 3), L=3, hidden=512, s_hidden=256, tK=32, sK=16,
-                                               batch=256),
+                                               batch=256, dtype="bf16"),
     # BASELINE configs[2]: Glow L=3 K=32 hidden 512, forward + inverse + log-det (no gradients); metric = samples/s
     # through one x -> z (+ per-sample log-det / bpd) pass followed by one z -> x sampling pass
-    "glow_cifar_fwd_inv_k32": dict(image=(32, 32, 3), L=3, hidden=512, tK=32, sK=32, batch=1024, mode="fwd_inv"),
-    "glow_celeba_fwd_inv_k32": dict(image=(64, 64, 3), L=4, hidden=512, tK=32, sK=32, batch=256, mode="fwd_inv"),
-    # MAF density evaluation + sampling: 10 MADE layers, D = 63, hidden 512 (parity unpinned, see oracle/maf_oracle.py);
-    # the z -> x pass is the shared-memory-resident sequential inverse (csrc/maf_inverse.cu), one launch per layer
+    "glow_cifar_fwd_inv_k32": dict(image=(32, 32, 3), L=3, hidden=512, tK=32, sK=32, batch=1024, mode="fwd_inv",
+                                   dtype="bf16"),
+    "glow_celeba_fwd_inv_k32": dict(image=(64, 64, 3), L=4, hidden=512, tK=32, sK=32, batch=256, mode="fwd_inv",
+                                    dtype="bf16"),
+    # MAF density evaluation + sampling: 10 MADE layers, D = 63, hidden 512; the z -> x pass is the shared-memory-
+    # resident sequential inverse (csrc/maf_inverse.cu), one launch per layer
     "maf_bsds300_fwd_inv_k10": dict(image=(63,), L=1, hidden=512, tK=10, sK=10, batch=65536, is_1d=True, arch="maf",
-                                    mode="fwd_inv", data="bsds300"),
+                                    mode="fwd_inv", data="bsds300", dtype="bf16"),
     # secondary workloads (BASELINE configs[1]): BSDS300-shaped tabular KD, D = 63, reference batch 65 536
-    # (conf/training/tabular.yaml: nll 0.85, kd 0.05, perceptual-L1 0.1 through the inverse pass)
+    # (conf/training/tabular.yaml: nll 0.85, kd 0.05, perceptual-L1 0.1 through the inverse pass); the 1-D path is fp32
     "glow1d_bsds300_kd_t5_s3": dict(image=(63,), L=1, hidden=32, s_hidden=16, tK=5, sK=3, batch=65536, is_1d=True,
-                                    weights=(0.85, 0.05, 0.1), data="bsds300"),
-    # MAF teacher 10 MADE layers -> student 3 layers, hidden 512 (no reference implementation exists: parity unpinned)
+                                    weights=(0.85, 0.05, 0.1), data="bsds300", dtype="f32"),
+    # MAF teacher 10 MADE layers -> student 3 layers, hidden 512 (the reference names MAF but ships no code for it)
     "maf_bsds300_kd_t10_s3": dict(image=(63,), L=1, hidden=512, tK=10, sK=3, batch=65536, is_1d=True, arch="maf",
-                                  weights=(0.9, 0.1, 0.0), data="bsds300"),
+                                  weights=(0.9, 0.1, 0.0), data="bsds300", dtype="bf16"),
 }
 METRIC = "kd_train_samples_per_sec"
+
+
+def glow_cfg(image_shape, K, L, hidden, is_1d=False, y_classes=10):
+    """Constructor kwargs of the reference's GlowGetAllOutputs (conf/teacher/*.yaml minus `checkpoint`)."""
+    return dict(image_shape=list(image_shape), hidden_channels=hidden, K=K, L=L, actnorm_scale=1.0,
+                flow_permutation="invconv", flow_coupling="affine", LU_decomposed=True, y_classes=y_classes,
+                learn_top=False, y_condition=False, is_1d=is_1d)
 
 
 def synthetic_images(n, shape, seed):
@@ -69,6 +80,19 @@ def peaks():
         return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"],
                 "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "src": "measured"}
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "src": "fallback"}
+
+
+def profiled_traffic(kernel, M, K1p):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` at this exact shape, from the committed
+    `ncu --set full` summaries (profiles/traffic.json, written by tools/ncu_traffic.py from the .ncu-rep of this
+    round); (None, reason) when no capture of this shape exists — the number is never scaled from another shape."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(path):
+        return None, "no profiles/traffic.json"
+    for e in json.load(open(path)).get(kernel, []):
+        if e.get("M") == M and e.get("K1p") == K1p:
+            return e["dram_bytes"], e.get("src", "profiles/traffic.json")
+    return None, f"no ncu capture at M={M}, K1p={K1p}"
 
 
 class ClockSampler:
@@ -111,16 +135,174 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+# ------------------------------------------------------------------------------------------ dominant-kernel roofline
+def time_graph(run, reps, nbuf):
+    """Average device time of one call of run(i): `reps` calls captured in one CUDA graph (host launch overhead is not
+    measured), rotating over `nbuf` buffer sets larger than L2, CUDA events on the launching stream."""
+    for i in range(3):
+        run(i % nbuf)
+    torch.cuda.synchronize()
+    gr = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(gr):
+        for i in range(reps):
+            run(i % nbuf)
+    gr.replay()
+    torch.cuda.synchronize()
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k0.record()
+    gr.replay()
+    k1.record()
+    torch.cuda.synchronize()
+    return k0.elapsed_time(k1) / reps
+
+
+def cnet_roofline(B, H, W, C_img, hid, device):
+    """Roofline of the dominant kernel of every 2-D Glow workload (profiles/r02_launches_*.txt): the fused
+    conv3x3 -> ReLU -> conv1x1 -> ReLU of the coupling net at the level-0 shape, M = B*(H/2)*(W/2) pixels, timed alone.
+    ALGORITHMIC FLOPs per launch = 2*M*hid*(9*C/2 + hid) with C = 4*C_img level-0 channels (the zero-padded K1p
+    columns the kernel also multiplies are not counted), bytes = bf16 col + h2 + weights."""
+    from nf_distillation_b200 import ops
+    pk = peaks()
+    C = 4 * C_img
+    M, K1, K1p = B * (H // 2) * (W // 2), 9 * C // 2, ops.round_up(9 * C // 2, 64)
+    nbuf = 3
+    cols = [(torch.randn(M, K1p, device=device) * 0.5).bfloat16() for _ in range(nbuf)]
+    for c in cols:
+        c[:, K1:] = 0
+    outs_ = [torch.empty(M, hid, device=device, dtype=torch.bfloat16) for _ in range(nbuf)]
+    W1 = (torch.randn(hid, K1p, device=device) * 0.1).bfloat16()
+    W2 = (torch.randn(hid, hid, device=device) * 0.05).bfloat16()
+    b1, b2 = torch.zeros(hid, device=device), torch.zeros(hid, device=device)
+    fused = ops.cnet_fused_supported(hid, K1p) and M >= 8192
+
+    def run(i):
+        if fused:
+            ops.cnet_fwd_fused(cols[i], K1p, W1, W2, b1, b2, outs_[i], M, hid)
+        else:
+            ops.gemm_nt(outs_[(i + 1) % nbuf], W2, M, hid, hid, ops.EPI_BIAS_RELU_BF16, outs_[i], bias=b2)
+    kms = time_graph(run, 12, nbuf)
+    flops = 2.0 * M * hid * ((K1 if fused else 0) + hid)
+    ach = flops / (kms * 1e-3) / 1e12
+    alg_bytes = 2.0 * (M * K1 + M * hid + hid * K1 + hid * hid)
+    kname = "cnet_fwd_fused_kernel" if fused else "gemm_nt_pair_kernel<1>"
+    traffic, tsrc = profiled_traffic(kname, M, K1p) if fused else (None, "not captured")
+    return {"bound": "tensor",
+            "kernel": kname + (" (conv#1+conv#2 of the coupling net, level 0)" if fused else " (conv#2, level 0)"),
+            "achieved": ach, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops"],
+            "traffic": traffic, "traffic_src": tsrc,
+            "peak_src": pk["src"] + " burst (kernel timed alone)", "us_per_launch": kms * 1e3,
+            "flops_per_launch": flops, "algorithmic_bytes_per_launch": alg_bytes,
+            "shape": {"M": M, "K1": K1, "K1p": K1p, "hid": hid}}
+
+
+def flow1d_roofline(B, D, hid, device):
+    """1-D Glow: the fused FlowStep kernel (csrc/flow1d.cu) is fp32-FMA bound, its HBM side is 8*D bytes per sample;
+    report the HBM fraction (the bound the tier's contract names for non-GEMM paths) of the inference kernel."""
+    from nf_distillation_b200.models import create_glow_model
+    pk = peaks()
+    m = create_glow_model(glow_cfg([D], 1, 1, hid, is_1d=True, y_classes=0)).to(device).eval()
+    for p in m.parameters():
+        p.requires_grad_(False)
+    step = m.flow.layers[0]
+    xs = [torch.randn(B, D, device=device) for _ in range(3)]
+    ld = torch.zeros(B, device=device)
+
+    def run(i):
+        with torch.no_grad():
+            step(xs[i], logdet=ld, reverse=False)
+    kms = time_graph(run, 12, 3)
+    alg = 8.0 * D * B + 8.0 * B
+    ach = alg / (kms * 1e-3) / 1e9
+    return {"bound": "hbm", "kernel": f"flow1d_fwd_kernel (whole FlowStep, D={D}, hidden {hid})", "achieved": ach,
+            "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": None,
+            "traffic_src": "not captured", "peak_src": pk["src"], "us_per_launch": kms * 1e3,
+            "algorithmic_bytes_per_launch": alg,
+            "note": "fp32 FMA-pipe bound (6.6-11 k FMA per sample), not HBM bound: see DESIGN.md §3"}
+
+
+def maf_roofline(B, D, H, device):
+    """MAF: the fused two-GEMM masked-linear kernel (the coupling net's cnet_fwd_fused_kernel on [B, Dp] rows)."""
+    from nf_distillation_b200 import ops
+    pk = peaks()
+    Dp = ops.round_up(D, 64)
+    nbuf = 3
+    xs = [(torch.randn(B, Dp, device=device) * 0.5).bfloat16() for _ in range(nbuf)]
+    outs_ = [torch.empty(B, H, device=device, dtype=torch.bfloat16) for _ in range(nbuf)]
+    W1 = (torch.randn(H, Dp, device=device) * 0.1).bfloat16()
+    W2 = (torch.randn(H, H, device=device) * 0.05).bfloat16()
+    b1, b2 = torch.zeros(H, device=device), torch.zeros(H, device=device)
+    if not (ops.cnet_fused_supported(H, Dp) and B >= 8192):
+        return None
+    kms = time_graph(lambda i: ops.cnet_fwd_fused(xs[i], Dp, W1, W2, b1, b2, outs_[i], B, H), 12, nbuf)
+    # algorithmic = the non-zero part of the masked products: layer 1 D x H, layer 2 ~ half of H x H (degree-sorted)
+    flops = 2.0 * B * H * (D + H / 2.0)
+    ach = flops / (kms * 1e-3) / 1e12
+    traffic, tsrc = profiled_traffic("cnet_fwd_fused_kernel", B, Dp)
+    return {"bound": "tensor", "kernel": "cnet_fwd_fused_kernel (both masked linears of a MADE layer)",
+            "achieved": ach, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops"],
+            "traffic": traffic, "traffic_src": tsrc, "peak_src": pk["src"] + " burst (kernel timed alone)",
+            "us_per_launch": kms * 1e3, "flops_per_launch": flops,
+            "algorithmic_bytes_per_launch": 2.0 * (B * D + B * H + H * D + H * H / 2),
+            "note": "masked FLOPs only: the kernel multiplies the structurally-zero half of the H x H weights too"}
+
+
+def roofline_for(wl, B, device):
+    if wl.get("arch") == "maf":
+        return maf_roofline(B, wl["image"][0], wl["hidden"], device)
+    if wl.get("is_1d", False):
+        return flow1d_roofline(B, wl["image"][0], wl["hidden"], device)
+    H, W, C = wl["image"]
+    return cnet_roofline(B, H, W, C, wl["hidden"], device)
+
+
+# ------------------------------------------------------------------------------------------ logp delta (vs the oracle)
+def logp_delta(model, cfg, is_maf, wl, device, n=8):
+    """BASELINE.json metric "...; logp delta": max relative error of the per-sample log-likelihood (bpd in 2-D, nll
+    in nats in 1-D) and of the total log-det of the model under test against the CPU oracle (fp32 reference
+    arithmetic) on a small batch of the same synthetic data, measured in this run. north_star bound: 1e-4."""
+    from nf_distillation_b200.models import utils as U
+    sd = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    if is_maf:
+        from oracle import maf_oracle as MO
+        D = wl["image"][0]
+        x = torch.randn(n, D, generator=torch.Generator().manual_seed(77))
+        with torch.no_grad():
+            _, ref = MO.maf_forward(sd, D, len(model.flow.layers), x)
+            _, got, _ = model(x.to(device), None)
+        what = "oracle/maf_oracle.py"
+    else:
+        from oracle import glow_oracle as O
+        if cfg.get("is_1d", False):
+            x = torch.randn(n, cfg["image_shape"][0], generator=torch.Generator().manual_seed(77))
+            noise = None
+        else:
+            x = synthetic_images(n, wl["image"], 77)
+            noise = torch.rand(x.shape, generator=torch.Generator().manual_seed(78)) / 256
+        with torch.no_grad():
+            _, ref = O.glow_forward(sd, cfg, x, noise)
+            orig = U.dequant_noise
+            if noise is not None:
+                U.dequant_noise = lambda t, nb: noise.to(device)
+            try:
+                _, got, _ = model(x.to(device), None)
+            finally:
+                U.dequant_noise = orig
+        what = "oracle/glow_oracle.py"
+    got = got.float().cpu()
+    return {"max_rel_err_per_sample_logp": ((got - ref).abs() / ref.abs().clamp_min(1e-12)).max().item(),
+            "samples": n, "oracle": what + " (torch CPU fp32)", "bound": 1e-4}
+
+
 # ------------------------------------------------------------------------------------------ forward + inverse mode
 def run_fwd_inv(args, wl, cfg_desc, warmup):
     """BASELINE configs[2]: one x -> z pass (all layer outputs, per-sample bpd) and one z -> x pass of the K=32 model,
     no gradients, captured in one CUDA graph. value = samples/s through the pair of passes."""
     from nf_distillation_b200 import ops
     from nf_distillation_b200.models import create_glow_model
-    from nf_distillation_b200.train import glow_cfg, init_distributed, randomise_zero_params
+    from nf_distillation_b200.train import init_distributed, randomise_zero_params
     import torch.distributed as dist
     rank, world, device = init_distributed()
-    B = args.batch or wl["batch"]
+    B = batch_per_gpu(args, wl, world)
     maf = wl.get("arch") == "maf"
     torch.manual_seed(42)
     n_pool = 4
@@ -139,6 +321,8 @@ def run_fwd_inv(args, wl, cfg_desc, warmup):
         model = model.to(device).eval()
         host_pool = [synthetic_images(B, wl["image"], 1000 + rank * 100 + i).pin_memory() for i in range(n_pool)]
         x = torch.empty(B, C, H, W, device=device)
+    for p in model.parameters():        # inference workload: frozen weights keep their derived operands cached
+        p.requires_grad_(False)
     dev_pool = [h.to(device) for h in host_pool]
     res = {}
 
@@ -195,24 +379,12 @@ def run_fwd_inv(args, wl, cfg_desc, warmup):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e = t.tolist()
-    cpu_base = None
+    roof = roofline_for(wl, B, device) if rank == 0 else None
+    cpu_base = delta = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
-        if maf:
-            cb, dt = cpu_maf_fwd_inv(sd, wl, 4096, 1)
-            what = "oracle/maf_oracle.py (paper restatement, parity unpinned)"
-        else:
-            from oracle import glow_oracle as O
-            cb = args.cpu_batch
-            xc = synthetic_images(cb, wl["image"], 7)
-            with torch.no_grad():
-                t0 = time.perf_counter()
-                outs, _ = O.glow_forward(sd, cfg, xc)
-                O.glow_reverse(sd, cfg, outs[-1], 0.0)
-                dt = time.perf_counter() - t0
-            what = "oracle/glow_oracle.py"
-        cpu_base = {"value": cb / dt, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
-                    "sample": f"one forward + one inverse pass of {cb} samples ({what}, torch CPU fp32)"}
+        delta = logp_delta(model, cfg if not maf else None, maf, wl, device)
+        v, cms, cores, sample = cpu_fwd_inv(wl, args.cpu_batch, 1)
+        cpu_base = {"value": v, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample}
     if rank == 0:
         gb = B * world
         cfg_desc.update(per_gpu_batch=B, global_batch=gb, parallelism=f"dp{world}", cuda_graphs=True,
@@ -222,49 +394,67 @@ def run_fwd_inv(args, wl, cfg_desc, warmup):
         cfg_desc.pop("student", None); cfg_desc.pop("loss", None); cfg_desc.pop("optimizer", None)
         print(json.dumps({"metric": "fwd_inv_samples_per_sec", "value": gb / (ms * 1e-3), "unit": "samples/s",
                           "n_gpus": world, "steps": args.steps, "warmup": warmup, "ms_per_step": ms,
-                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
-                          "data": "synthetic", "config": cfg_desc, "clocks": clocks,
+                          "higher_is_better": True, "scaling": scaling_kind(args), "vs_baseline": None,
+                          "dtype": wl["dtype"], "data": "synthetic", "config": cfg_desc, "clocks": clocks,
                           "e2e": {"value": gb / (ms_e2e * 1e-3), "unit": "samples/s", "ms_per_step": ms_e2e,
                                   "h2d_bytes_per_step": host_pool[0].numel() * 4, "d2h_bytes_per_step": 8},
                           "gpu_launches": launches * args.steps, "gpu_launches_per_step": launches,
                           "last": {"bpd_mean": float(stat[0]), "x_abs_mean": float(stat[1])},
-                          "roofline": None, "cpu_baseline": cpu_base}))
+                          "logp_delta": delta, "roofline": roof, "cpu_baseline": cpu_base}))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
 # ------------------------------------------------------------------------------------------ CPU arm (oracle port)
-def cpu_maf_fwd_inv(sd, wl, cb, n):
-    """Seconds for one x -> z + one z -> x pass of `cb` samples through the paper restatement (oracle/maf_oracle.py)."""
-    from oracle import maf_oracle as MO
-    D = wl["image"][0]
-    xc = torch.randn(cb, D, generator=torch.Generator().manual_seed(7))
-    with torch.no_grad():
-        t0 = time.perf_counter()
-        for _ in range(n):
+# Nothing below imports nf_distillation_b200: weights come from the oracles' own seeded initialisers.
+def cpu_fwd_inv(wl, cb, n):
+    """(samples/s, ms, threads, description) of n x (one x -> z pass + one z -> x pass) of `cb` samples on the host."""
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    if wl.get("arch") == "maf":
+        from oracle import maf_oracle as MO
+        D, cb = wl["image"][0], 4096
+        sd = MO.random_state_dict(D, wl["hidden"], wl["tK"], 42)
+        xc = torch.randn(cb, D, generator=torch.Generator().manual_seed(7))
+
+        def once():
             outs, _ = MO.maf_forward(sd, D, wl["tK"], xc)
             MO.maf_inverse(sd, D, wl["tK"], outs[-1])
-        return cb, (time.perf_counter() - t0) / n
+        what = "oracle/maf_oracle.py"
+    else:
+        from oracle import glow_oracle as O
+        cfg = glow_cfg(wl["image"], wl["tK"], wl["L"], wl["hidden"])
+        sd = O.random_state_dict(cfg, 42, std=0.01)
+        xc = synthetic_images(cb, wl["image"], 7)
+
+        def once():
+            outs, _ = O.glow_forward(sd, cfg, xc)
+            O.glow_reverse(sd, cfg, outs[-1], 0.0)
+        what = "oracle/glow_oracle.py"
+    with torch.no_grad():
+        once()
+        t0 = time.perf_counter()
+        for _ in range(n):
+            once()
+        dt = (time.perf_counter() - t0) / n
+    return cb / dt, dt * 1e3, cores, (f"{n} x (one forward + one inverse pass) of {cb} samples ({what}, torch CPU "
+                                     f"fp32, {cores} threads)")
 
 
 def cpu_kd_step_fn(wl, batch, seed=42):
-    """The reference's CPU algorithm for this path, restated in oracle/ (the reference itself is Python and does not
-    travel to the GPU box): KD train step = fwd student+teacher, loss, backward, clip 30, Adam."""
+    """The reference's CPU algorithm for this path, restated in oracle/ (the reference itself is a Python script tree
+    with missing dependencies and does not travel to the GPU box): KD train step = fwd student + teacher, loss,
+    backward, clip 30, Adam."""
     from oracle import glow_oracle as O
-    from nf_distillation_b200.models import create_glow_model
-    from nf_distillation_b200.train import glow_cfg, randomise_zero_params
     is_1d = wl.get("is_1d", False)
     torch.manual_seed(seed)
     if wl.get("arch") == "maf":
         from oracle import maf_oracle as MO
-        from nf_distillation_b200.models.maf import create_maf_model
         D = wl["image"][0]
-        t_model = create_maf_model(dict(image_shape=[D], hidden_channels=wl["hidden"], K=wl["tK"]))
-        s_model = create_maf_model(dict(image_shape=[D], hidden_channels=wl["hidden"], K=wl["sK"]))
-        pn = dict(s_model.named_parameters())
-        s_sd = {k: v.clone().requires_grad_(k in pn) for k, v in s_model.state_dict().items()}
-        t_sd = {k: v.clone() for k, v in t_model.state_dict().items()}
+        t_sd = MO.random_state_dict(D, wl["hidden"], wl["tK"], seed + 2)
+        s_sd = {k: (v.requires_grad_(True) if v.dtype.is_floating_point else v)
+                for k, v in MO.random_state_dict(D, wl["hidden"], wl["sK"], seed + 1).items()}
         params = [v for v in s_sd.values() if v.requires_grad]
         opt = torch.optim.Adam(params, lr=5e-4)
         x = torch.randn(batch, D)
@@ -282,18 +472,12 @@ def cpu_kd_step_fn(wl, batch, seed=42):
             opt.step()
             return float(loss.detach())
         return step
-    if is_1d:
-        s_cfg = glow_cfg(wl["image"], wl["sK"], wl["L"], wl.get("s_hidden", wl["hidden"]), is_1d=True, y_classes=0)
-        t_cfg = glow_cfg(wl["image"], wl["tK"], wl["L"], wl["hidden"], is_1d=True, y_classes=0)
-    else:
-        s_cfg = glow_cfg(wl["image"], wl["sK"], wl["L"], wl.get("s_hidden", wl["hidden"]))
-        t_cfg = glow_cfg(wl["image"], wl["tK"], wl["L"], wl["hidden"])
-    t_model, s_model = create_glow_model(t_cfg), create_glow_model(s_cfg)   # parameter containers only (CPU)
-    randomise_zero_params(s_model, seed + 1)
-    randomise_zero_params(t_model, seed + 2)
-    s_sd = {k: v.clone().requires_grad_(v.dtype.is_floating_point and k in dict(s_model.named_parameters()))
-            for k, v in s_model.state_dict().items()}
-    t_sd = {k: v.clone() for k, v in t_model.state_dict().items()}
+    yc = 0 if is_1d else 10
+    s_cfg = glow_cfg(wl["image"], wl["sK"], wl["L"], wl.get("s_hidden", wl["hidden"]), is_1d=is_1d, y_classes=yc)
+    t_cfg = glow_cfg(wl["image"], wl["tK"], wl["L"], wl["hidden"], is_1d=is_1d, y_classes=yc)
+    t_sd = O.random_state_dict(t_cfg, seed + 2)
+    s_sd = {k: (v.requires_grad_(True) if k != "prior_h" and not k.endswith((".p", ".sign_s")) else v)
+            for k, v in O.random_state_dict(s_cfg, seed + 1).items()}
     params = [v for v in s_sd.values() if v.requires_grad]
     opt = torch.optim.Adam(params, lr=5e-4)
     if is_1d:
@@ -332,13 +516,58 @@ def run_cpu(wl, batch, steps, warmup):
     return batch / dt, dt * 1e3, cores
 
 
+def cpu_batch_for(args, wl):
+    if not wl.get("is_1d", False):
+        return args.cpu_batch
+    return 8192 if wl.get("arch") == "maf" else 65536
+
+
+def run_reference_arm(args, wl, cfg_desc):
+    """bench.py --impl reference: the reference's CPU algorithm for this workload (oracle/ port) on the box's host
+    cores, bounded sample per step; rank 0 only. No product code is imported on this path."""
+    n = max(1, min(args.steps, 3))
+    if wl.get("mode") == "fwd_inv":
+        metric = "fwd_inv_samples_per_sec"
+        value, ms, cores, sample = cpu_fwd_inv(wl, args.cpu_batch, n)
+        cb = 4096 if wl.get("arch") == "maf" else args.cpu_batch
+        for k in ("student", "loss", "optimizer"):
+            cfg_desc.pop(k, None)
+    else:
+        metric = METRIC
+        cb = cpu_batch_for(args, wl)
+        value, ms, cores = run_cpu(wl, cb, n, 1)
+        sample = (f"{cb}-sample KD train steps of the same workload (oracle/ port of the reference, torch CPU fp32, "
+                  f"{cores} threads)")
+    cfg_desc.update(per_gpu_batch=cb, global_batch=cb, parallelism="cpu")
+    print(json.dumps({
+        "impl": "reference", "metric": metric, "value": value, "unit": "samples/s", "n_gpus": args.gpus,
+        "steps": n, "warmup": 1, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg_desc,
+        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+    assert not any(m.startswith("nf_distillation_b200") for m in sys.modules), "reference arm must not load the product"
+
+
+def batch_per_gpu(args, wl, world):
+    if args.global_batch:
+        assert args.global_batch % world == 0, "--global-batch must divide evenly over the ranks"
+        return args.global_batch // world
+    return args.batch or wl["batch"]
+
+
+def scaling_kind(args):
+    return "strong" if args.global_batch else "weak"
+
+
 # ------------------------------------------------------------------------------------------ main
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: workload's)")
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: workload's); weak scaling")
+    ap.add_argument("--global-batch", type=int, default=0,
+                    help="STRONG scaling: total batch fixed, each rank takes global/N (overrides --batch)")
     ap.add_argument("--workload", default="glow_cifar_kd_t32_s8", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-graphs", action="store_true")
@@ -363,67 +592,18 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        cb = args.cpu_batch if not wl.get("is_1d", False) else 65536
-        metric = METRIC
-        if wl.get("mode") == "fwd_inv" and wl.get("arch") == "maf":
-            from nf_distillation_b200.models.maf import create_maf_model
-            metric = "fwd_inv_samples_per_sec"
-            torch.manual_seed(42)
-            model = create_maf_model(dict(image_shape=[wl["image"][0]], hidden_channels=wl["hidden"], K=wl["tK"]))
-            sd = {k: v.detach() for k, v in model.state_dict().items()}
-            n = max(1, min(args.steps, 3))
-            cpu_maf_fwd_inv(sd, wl, 256, 1)
-            cb, dt = cpu_maf_fwd_inv(sd, wl, 4096, n)
-            ms = dt * 1e3
-            value, cores = cb / dt, torch.get_num_threads()
-        elif wl.get("mode") == "fwd_inv":   # forward + inverse + log-det of the K=32 model through the oracle port
-            from oracle import glow_oracle as O
-            from nf_distillation_b200.models import create_glow_model
-            from nf_distillation_b200.train import glow_cfg, randomise_zero_params
-            metric = "fwd_inv_samples_per_sec"
-            torch.manual_seed(42)
-            cfg = glow_cfg(wl["image"], wl["tK"], wl["L"], wl["hidden"])
-            model = create_glow_model(cfg)
-            randomise_zero_params(model, 43, std=0.01)
-            sd = {k: v.detach() for k, v in model.state_dict().items()}
-            xc = synthetic_images(cb, wl["image"], 7)
-            n = max(1, min(args.steps, 3))
-            with torch.no_grad():
-                for it in range(n + 1):
-                    if it == 1:
-                        t0 = time.perf_counter()
-                    outs, _ = O.glow_forward(sd, cfg, xc)
-                    O.glow_reverse(sd, cfg, outs[-1], 0.0)
-            ms = (time.perf_counter() - t0) * 1e3 / n
-            value, cores = cb / (ms * 1e-3), torch.get_num_threads()
-        else:
-            value, ms, cores = run_cpu(wl, cb, max(1, min(args.steps, 3)), 1)
-        cfg_desc.update(per_gpu_batch=cb, global_batch=cb, parallelism="cpu")
-        if wl.get("mode") == "fwd_inv":
-            for k in ("student", "loss", "optimizer"):
-                cfg_desc.pop(k, None)
-        print(json.dumps({
-            "impl": "reference", "metric": metric, "value": value, "unit": "samples/s", "n_gpus": args.gpus,
-            "steps": max(1, min(args.steps, 3)), "warmup": 1, "ms_per_step": ms, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg_desc,
-            "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port",
-                             "sample": f"{cb}-sample steps of the same workload (oracle/ port of the reference, "
-                                       f"torch CPU fp32, {cores} threads)"},
-            "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
-        return
+        return run_reference_arm(args, wl, cfg_desc)
 
     if wl.get("mode") == "fwd_inv":
         return run_fwd_inv(args, wl, cfg_desc, warmup)
     import torch.distributed as dist
     from nf_distillation_b200 import ops
-    from nf_distillation_b200.train import KDTrainer, glow_cfg, init_distributed, kd_config
+    from nf_distillation_b200.train import KDTrainer, init_distributed, kd_config
     rank, world, device = init_distributed()
-    B = args.batch or wl["batch"]
+    B = batch_per_gpu(args, wl, world)
     is_1d = wl.get("is_1d", False)
     if is_1d:
         D = wl["image"][0]
-        H = W = 2
-        C = D
         s_cfg = glow_cfg(wl["image"], wl["sK"], wl["L"], wl.get("s_hidden", wl["hidden"]), is_1d=True, y_classes=0)
         t_cfg = glow_cfg(wl["image"], wl["tK"], wl["L"], wl["hidden"], is_1d=True, y_classes=0)
         if wl.get("arch") == "maf":
@@ -433,8 +613,8 @@ def main():
         shape = (B, D)
     else:
         H, W, C = wl["image"]
-        config = kd_config(glow_cfg(wl["image"], wl["sK"], wl["L"], wl.get("s_hidden", wl["hidden"])),
-                           glow_cfg(wl["image"], wl["tK"], wl["L"], wl["hidden"]))
+        s_cfg = glow_cfg(wl["image"], wl["sK"], wl["L"], wl.get("s_hidden", wl["hidden"]))
+        config = kd_config(s_cfg, glow_cfg(wl["image"], wl["tK"], wl["L"], wl["hidden"]))
         shape = (B, C, H, W)
     trainer = KDTrainer(config, shape, device, use_graphs=not args.no_graphs)
     n_pool = 4
@@ -457,11 +637,18 @@ def main():
         torch.cuda.profiler.stop()
         print(json.dumps({"ncu_step": True, "batch": B, "losses": trainer.losses.cpu().tolist()}))
         return
+    # logp delta of the student as initialised, before any step (rank 0, single GPU, with the CPU legs)
+    delta = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        trainer.module.student.eval()
+        delta = logp_delta(trainer.module.student, None if wl.get("arch") == "maf" else s_cfg,
+                           wl.get("arch") == "maf", wl, device)
+        trainer.module.student.train()
+    # count kernels of ONE step: an eager step (forward, backward, clip + Adam) outside the graphs
     trainer.warmup(iters=1)                      # eager step(s) + graph capture
-    launches_eager_step = None
-    # count kernels of ONE step: run one extra eager step outside the graphs
     c0 = ops.launch_count()
     trainer._forward_backward()
+    trainer._clip_and_update()
     launches_per_step = ops.launch_count() - c0
     torch.cuda.synchronize()
 
@@ -503,59 +690,11 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e = t.tolist()
 
-    # ---- roofline of the dominant kernel (profiles/r01_launches_step_b1024.txt: cnet_fwd_fused_kernel, ~30 % of the
-    #      step): fused conv#1+conv#2 of the coupling net at the level-0 shape, M = B*H/2*W/2 pixels, timed alone with
-    #      CUDA events on its launch stream, 10 launches per CUDA graph so host launch overhead is not measured, and
-    #      rotating buffers larger than L2. Algorithmic work per launch = 2*M*512*(K1p+512) FLOP.
-    roof = None
-    if rank == 0 and not is_1d:
-        pk = peaks()
-        M, hid, K1p = B * (H // 2) * (W // 2), wl["hidden"], 64
-        nbuf = 3
-        cols = [(torch.randn(M, K1p, device=device) * 0.5).bfloat16() for _ in range(nbuf)]
-        outs_ = [torch.empty(M, hid, device=device, dtype=torch.bfloat16) for _ in range(nbuf)]
-        W1 = (torch.randn(hid, K1p, device=device) * 0.1).bfloat16()
-        W2 = (torch.randn(hid, hid, device=device) * 0.05).bfloat16()
-        b1, b2 = torch.zeros(hid, device=device), torch.zeros(hid, device=device)
-        fused = ops.cnet_fused_supported(hid, K1p)
-
-        def run(i):
-            if fused:
-                ops.cnet_fwd_fused(cols[i], K1p, W1, W2, b1, b2, outs_[i], M, hid)
-            else:
-                ops.gemm_nt(outs_[(i + 1) % nbuf], W2, M, hid, hid, ops.EPI_BIAS_RELU_BF16, outs_[i], bias=b2)
-        for i in range(3):
-            run(i % nbuf)
-        torch.cuda.synchronize()
-        reps = 12
-        gr = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(gr):
-            for i in range(reps):
-                run(i % nbuf)
-        gr.replay()
-        torch.cuda.synchronize()
-        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        k0.record()
-        gr.replay()
-        k1.record()
-        torch.cuda.synchronize()
-        kms = k0.elapsed_time(k1) / reps
-        flops = 2.0 * M * hid * ((K1p if fused else 0) + hid)
-        ach = flops / (kms * 1e-3) / 1e12
-        alg_bytes = 2.0 * (M * K1p + M * hid + hid * K1p + hid * hid)
-        roof = {"bound": "tensor",
-                "kernel": "cnet_fwd_fused_kernel (conv#1+conv#2 of the coupling net, level 0)" if fused
-                else "gemm_nt_pair_kernel<BIAS_RELU_BF16> (conv#2)",
-                "achieved": ach, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops"],
-                # dram__bytes_read+write per launch from profiles/r01_prof_cnet_r1.txt (ncu --set full, B=1024)
-                "traffic": 242.1e6 * (B / 1024.0) if fused else None,
-                "peak_src": pk["src"] + " burst (kernel timed alone)", "us_per_launch": kms * 1e3,
-                "flops_per_launch": flops, "algorithmic_bytes_per_launch": alg_bytes}
-        del cols, outs_
+    roof = roofline_for(wl, B, device) if rank == 0 else None
 
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cb = args.cpu_batch if not is_1d else (65536 if wl.get("arch") != "maf" else 8192)
+        cb = cpu_batch_for(args, wl)
         v, cms, cores = run_cpu(wl, cb, 2, 1)
         cpu_base = {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
                     "sample": f"2 KD train steps of {cb} samples, same model/config "
@@ -568,13 +707,13 @@ def main():
                         l2="per-step working set (activations ~GBs) exceeds the 126 MB L2; inputs rotate over 4 batches")
         out = {"metric": METRIC, "value": gb / (ms * 1e-3), "unit": "samples/s", "n_gpus": world,
                "steps": args.steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True,
-               "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+               "scaling": scaling_kind(args), "vs_baseline": None, "dtype": wl["dtype"],
                "data": "synthetic", "config": cfg_desc, "clocks": clocks,
                "e2e": {"value": gb / (ms_e2e * 1e-3), "unit": "samples/s", "ms_per_step": ms_e2e,
                        "h2d_bytes_per_step": host_pool[0].numel() * 4, "d2h_bytes_per_step": 16},
                "gpu_launches": launches_per_step * args.steps, "gpu_launches_per_step": launches_per_step,
                "losses_last_step": dict(zip(("nll", "kd", "perceptual", "loss"), losses)),
-               "roofline": roof, "cpu_baseline": cpu_base}
+               "logp_delta": delta, "roofline": roof, "cpu_baseline": cpu_base}
         print(json.dumps(out))
     if world > 1:
         dist.barrier()

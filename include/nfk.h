@@ -269,6 +269,47 @@ int nfk_cnet_fwd_fused(const void* col, int K1p, const void* B1, const void* B2,
                        const float* bias2, void* h1, void* h2, void* mask1, void* mask2, long long ldmask, int M,
                        int hid, void* stream);
 
+/* ---- the tail of the KD training step (csrc/loss_optim.cu) -------------------------------------------------------
+ * NFModel.loss (pl_module.py:257-320) in ONE launch: per sample
+ *     kd[b]   = (1/L) sum_l mean_i (s_l[b,i] - t_l[b,i])^2                          (pl_module.py:266-282)
+ *     nll[b]  = -(logdet[b] + sum_i log N(z_last[b,i]; mean_i, exp(logs_i))) * nll_scale
+ *               (models/layers.py:10-23, models/kd_flows.py:134-150; prior rows NULL = zeros), or nll_in[b] when
+ *               z_last is NULL (objective already computed by the model's forward)
+ *     res[b]  = (w_nll nll + w_kd kd + w_perc perc[b]) * sample_w[b]                (pl_module.py:306-313)
+ * and means[4] = batch means of (nll, kd, perc, res) (pl_module.py:315-320), added up in a fixed order by the last
+ * CTA to finish (deterministic). nll_out / kd_out ([B], optional) receive the per-sample terms. scratch:
+ * nfk_kd_nll_loss_scratch_floats(B) floats. The backward takes the gradient of the four means (device, [4]) plus
+ * optional per-sample gradients of nll / kd and writes ds_l for every level with a non-NULL ds pointer, dz_last,
+ * dlogdet (or dnll_in), dperc. Up to NFK_LOSS_MAX_LEVELS levels; the struct is read on the host. */
+#define NFK_LOSS_MAX_LEVELS 8
+typedef struct {
+  const float* s[NFK_LOSS_MAX_LEVELS]; /* student taps [B, n_l] */
+  const float* t[NFK_LOSS_MAX_LEVELS]; /* teacher taps [B, n_l] */
+  float* ds[NFK_LOSS_MAX_LEVELS];      /* backward only: gradient of s_l (NULL = not needed) */
+  int n[NFK_LOSS_MAX_LEVELS];
+  int L;
+} nfk_loss_levels;
+int nfk_kd_nll_loss_scratch_floats(int B);
+int nfk_kd_nll_loss_fwd(const nfk_loss_levels* levels, const float* z_last, int nz, const float* prior_mean,
+                        const float* prior_logs, const float* logdet, float nll_scale, const float* nll_in,
+                        const float* perc, const float* sample_w, float w_nll, float w_kd, float w_perc, int B,
+                        float* nll_out, float* kd_out, float* means, float* scratch, void* stream);
+int nfk_kd_nll_loss_bwd(const nfk_loss_levels* levels, const float* z_last, int nz, const float* prior_mean,
+                        const float* prior_logs, float nll_scale, const float* sample_w, float w_nll, float w_kd,
+                        float w_perc, int B, const float* g_means, const float* g_nll, const float* g_kd,
+                        float* dz_last, float* dlogdet, float* dnll_in, float* dperc, void* stream);
+
+/* Gradient clipping + optimiser on FLAT fp32 buffers (train.py:46 gradient_clip_val, pl_module.py:348-363 Adam /
+ * Adamax): nfk_grad_sqnorm writes nfk_optim_partials() per-CTA partial sums of |g|^2 and adds one to *step (device
+ * int, optional); nfk_adam_step re-adds the partials in a fixed order, scales the gradient by
+ * min(1, max_norm / (norm + 1e-6)) (max_norm <= 0: no clipping) and applies torch.optim.Adam's (adamax != 0:
+ * Adamax's) update with bias correction from *step. norm_out (optional) receives the unclipped norm. */
+int nfk_optim_partials(void);
+int nfk_grad_sqnorm(const float* g, long long n, float* partials, int* step, void* stream);
+int nfk_adam_step(float* p, const float* g, float* m, float* v, long long n, const float* partials, const int* step,
+                  float max_norm, float lr, float beta1, float beta2, float eps, float weight_decay, int adamax,
+                  float* norm_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

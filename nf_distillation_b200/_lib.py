@@ -48,6 +48,15 @@ class CouplingBwdItem(_c.Structure):
                [(n, _vp) for n in ("dw1", "db1", "dl1", "dw2", "db2", "dl2", "dw3", "db3", "dl3")]
 
 
+NFK_LOSS_MAX_LEVELS = 8
+
+
+class LossLevels(_c.Structure):
+    """nfk_loss_levels (include/nfk.h)."""
+    _fields_ = [("s", _vp * NFK_LOSS_MAX_LEVELS), ("t", _vp * NFK_LOSS_MAX_LEVELS), ("ds", _vp * NFK_LOSS_MAX_LEVELS),
+                ("n", _i * NFK_LOSS_MAX_LEVELS), ("L", _i)]
+
+
 # name -> argtypes; every function returns int. Keep in the same order as include/nfk.h.
 SIGNATURES: dict[str, list] = {
     "nfk_version": [],
@@ -95,6 +104,12 @@ SIGNATURES: dict[str, list] = {
     "nfk_made_inverse_jobs": [_vp, _vp, _i, _i, _i, _i, _i, _vp, _i],
     "nfk_made_inverse_pack": [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp],
     "nfk_made_inverse_resident": [_vp] * 6 + [_i] * 3 + [_vp] * 3 + [_i] * 6 + [_vp],
+    "nfk_kd_nll_loss_scratch_floats": [_i],
+    "nfk_kd_nll_loss_fwd": [_vp, _vp, _i, _vp, _vp, _vp, _f, _vp, _vp, _vp, _f, _f, _f, _i, _vp, _vp, _vp, _vp, _vp],
+    "nfk_kd_nll_loss_bwd": [_vp, _vp, _i, _vp, _vp, _f, _vp, _f, _f, _f, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "nfk_optim_partials": [],
+    "nfk_grad_sqnorm": [_vp, _ll, _vp, _vp, _vp],
+    "nfk_adam_step": [_vp, _vp, _vp, _vp, _ll, _vp, _vp, _f, _f, _f, _f, _f, _f, _i, _vp, _vp],
 }
 
 

@@ -477,6 +477,58 @@ class KdMseFn(torch.autograd.Function):
         return (*grads, *([None] * L))
 
 
+class KdNllLossFn(torch.autograd.Function):
+    """NFModel.loss (pl_module.py:257-320) as ONE forward and ONE backward launch (csrc/loss_optim.cu): multi-level
+    latent MSE + prior log-density / bits-per-dim objective + weighted sum + the four batch means.
+
+    apply(spec, logdet_or_nll, z_last, perc, *student_levels) -> (means[4] = (nll, kd, perceptual, loss), nll[B], kd[B])
+    spec: dict(teacher=[...], prior=(mean_row, logs_row) | None, nll_scale, w=(w_nll, w_kd, w_perc), sample_w).
+    z_last None: `logdet_or_nll` already is the per-sample objective (models whose prior is not a fixed row)."""
+
+    @staticmethod
+    def forward(ctx, spec, ld_or_nll, z_last, perc, *s_levels):
+        s = [t.contiguous() for t in s_levels]
+        t = [x.detach().contiguous() for x in spec["teacher"]]
+        assert len(s) == len(t)
+        B = ld_or_nll.shape[0]
+        dev = ld_or_nll.device
+        ld_or_nll = ld_or_nll.contiguous()
+        z_last = None if z_last is None else z_last.contiguous()
+        perc = None if perc is None else perc.contiguous()
+        mean, logs = spec["prior"] if spec.get("prior") is not None else (None, None)
+        sw = spec.get("sample_w")
+        sw = None if sw is None else sw.detach().to(F32).contiguous()
+        w_nll, w_kd, w_perc = spec["w"]
+        out = torch.empty(4 + 2 * B, device=dev, dtype=F32)
+        means, nll, kd = out[:4], out[4:4 + B], out[4 + B:]
+        ops.kd_nll_loss_fwd(s, t, z_last, mean, logs, ld_or_nll if z_last is not None else None,
+                            spec.get("nll_scale", 1.0), None if z_last is not None else ld_or_nll, perc, sw,
+                            w_nll, w_kd, w_perc, B, nll, kd, means)
+        ctx.spec, ctx.sw, ctx.L, ctx.B = spec, sw, len(s), B
+        ctx.has_z, ctx.has_perc = z_last is not None, perc is not None
+        ctx.save_for_backward(z_last, mean, logs, *s, *t)
+        ctx.mark_non_differentiable(nll, kd)
+        return means, nll, kd
+
+    @staticmethod
+    def backward(ctx, g_means, _g_nll, _g_kd):
+        z_last, mean, logs, *st = ctx.saved_tensors
+        L, B = ctx.L, ctx.B
+        s, t = st[:L], st[L:]
+        spec = ctx.spec
+        w_nll, w_kd, w_perc = spec["w"]
+        dev = g_means.device
+        needs = ctx.needs_input_grad
+        ds = [torch.empty_like(a) if needs[4 + i] else None for i, a in enumerate(s)]
+        dz = torch.empty_like(z_last) if ctx.has_z and needs[2] else None
+        d_first = torch.empty(B, device=dev, dtype=F32) if needs[1] else None
+        dperc = torch.empty(B, device=dev, dtype=F32) if ctx.has_perc and needs[3] else None
+        ops.kd_nll_loss_bwd(s, t, ds, z_last if ctx.has_z else None, mean, logs, spec.get("nll_scale", 1.0), ctx.sw,
+                            w_nll, w_kd, w_perc, B, g_means.contiguous(), None, None, dz,
+                            d_first if ctx.has_z else None, None if ctx.has_z else d_first, dperc)
+        return (None, d_first, dz, dperc, *ds)
+
+
 def kd_mse(student_levels, teacher_levels) -> Optional[torch.Tensor]:
     if not student_levels:
         return None

@@ -3,6 +3,7 @@ training module can pick its distillation taps (reference /root/reference/models
 from __future__ import annotations
 
 import logging
+import math
 import typing as tp
 
 import torch
@@ -73,6 +74,18 @@ class GlowGetAllOutputs(Glow):
         else:
             y_logits = None
         return z, bpd, y_logits
+
+    def deferred_objective(self, x, logdet, y_onehot=None):
+        """flow_from_dequantized WITHOUT the prior / bits-per-dim reduction: returns (z list, logdet [B],
+        (mean_row, logs_row), nll_scale) so that NFModel.loss can fold the objective (kd_flows.py:134-150) into its
+        single fused loss kernel (functional.KdNllLossFn); None when the prior is not a batch-independent row
+        (learn_top / y_condition), in which case the caller uses the ordinary forward."""
+        rows = self._prior_rows()
+        if rows is None:
+            return None
+        z, logdet = self.flow(x, y_onehot=y_onehot, logdet=logdet, reverse=False)
+        scale = 1.0 if self.is_1d else 1.0 / (math.log(2.0) * x.shape[1] * x.shape[2] * x.shape[3])
+        return z, logdet, rows, scale
 
 
 def create_glow_model(config: tp.Dict[str, tp.Any]) -> GlowGetAllOutputs:

@@ -390,3 +390,57 @@ def cnet_fwd_fused(col, K1p, B1, B2, bias1, bias2, h2, M, hid, h1=None, mask1=No
     ldm = 0 if mask1 is None else mask1.stride(0)
     check(LIB.nfk_cnet_fwd_fused(_p(col), K1p, _p(B1), _p(B2), _p(bias1), _p(bias2), _p(h1), _p(h2), _p(mask1),
                                  _p(mask2), ldm, M, hid, _st()), "nfk_cnet_fwd_fused")
+
+
+def _loss_levels(s_list, t_list, ds_list=None):
+    from ._lib import NFK_LOSS_MAX_LEVELS, LossLevels
+    L = len(s_list)
+    if L > NFK_LOSS_MAX_LEVELS:
+        raise ValueError(f"at most {NFK_LOSS_MAX_LEVELS} KD levels per launch")
+    lv = LossLevels()
+    lv.L = L
+    for k in range(L):
+        lv.s[k], lv.t[k] = _p(s_list[k]), _p(t_list[k])
+        lv.ds[k] = None if ds_list is None or ds_list[k] is None else _p(ds_list[k])
+        lv.n[k] = s_list[k][0].numel()
+    return lv
+
+
+def kd_nll_loss_fwd(s_list, t_list, z_last, prior_mean, prior_logs, logdet, nll_scale, nll_in, perc, sample_w, w_nll,
+                    w_kd, w_perc, B, nll_out, kd_out, means):
+    """NFModel.loss in one launch (include/nfk.h: nfk_kd_nll_loss_fwd)."""
+    _count()
+    lv = _loss_levels(s_list, t_list)
+    scratch = torch.empty(LIB.nfk_kd_nll_loss_scratch_floats(B), device=means.device, dtype=torch.float32)
+    nz = 0 if z_last is None else z_last[0].numel()
+    check(LIB.nfk_kd_nll_loss_fwd(ctypes.addressof(lv), _p(z_last), nz, _p(prior_mean), _p(prior_logs), _p(logdet),
+                                  float(nll_scale), _p(nll_in), _p(perc), _p(sample_w), float(w_nll), float(w_kd),
+                                  float(w_perc), B, _p(nll_out), _p(kd_out), _p(means), _p(scratch), _st()),
+          "nfk_kd_nll_loss_fwd")
+
+
+def kd_nll_loss_bwd(s_list, t_list, ds_list, z_last, prior_mean, prior_logs, nll_scale, sample_w, w_nll, w_kd, w_perc,
+                    B, g_means, g_nll, g_kd, dz_last, dlogdet, dnll_in, dperc):
+    _count()
+    lv = _loss_levels(s_list, t_list, ds_list)
+    nz = 0 if z_last is None else z_last[0].numel()
+    check(LIB.nfk_kd_nll_loss_bwd(ctypes.addressof(lv), _p(z_last), nz, _p(prior_mean), _p(prior_logs),
+                                  float(nll_scale), _p(sample_w), float(w_nll), float(w_kd), float(w_perc), B,
+                                  _p(g_means), _p(g_nll), _p(g_kd), _p(dz_last), _p(dlogdet), _p(dnll_in), _p(dperc),
+                                  _st()), "nfk_kd_nll_loss_bwd")
+
+
+def optim_partials() -> int:
+    return int(LIB.nfk_optim_partials())
+
+
+def grad_sqnorm(g, partials, step=None):
+    _count()
+    check(LIB.nfk_grad_sqnorm(_p(g), g.numel(), _p(partials), _p(step), _st()), "nfk_grad_sqnorm")
+
+
+def adam_step(p, g, m, v, partials, step, max_norm, lr, beta1, beta2, eps, weight_decay, adamax, norm_out=None):
+    _count()
+    check(LIB.nfk_adam_step(_p(p), _p(g), _p(m), _p(v), p.numel(), _p(partials), _p(step), float(max_norm), float(lr),
+                            float(beta1), float(beta2), float(eps), float(weight_decay), int(adamax), _p(norm_out),
+                            _st()), "nfk_adam_step")

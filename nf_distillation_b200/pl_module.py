@@ -98,7 +98,11 @@ class NFModel(nn.Module):
         return model
 
     # ---- pl_module.py:198-255
-    def forward(self, batch):
+    def forward(self, batch, _defer_objective=False):
+        """pl_module.py:198-255. `_defer_objective` (used by training_step only): when the student's prior is a fixed
+        row, skip the model's own prior / bits-per-dim reduction and hand logdet + last latent to loss(), whose fused
+        kernel computes the objective together with the KD terms; "student_nll" is then None and "student_objective"
+        = (logdet, (mean_row, logs_row), scale). Called without the flag the dict is the reference's."""
         name = self.params["data"]["name"]
         if name in TABULAR:
             x, y, weights = batch[0], None, None
@@ -109,11 +113,25 @@ class NFModel(nn.Module):
             x, y, weights = batch
         cond = y if self.params["student"]["y_condition"] else None
         teacher_z = None
+        objective = None
+        defer = _defer_objective and hasattr(self.student, "deferred_objective") \
+            and self.student._prior_rows() is not None
         if (self.kd_weight > 0 and self.concurrent_teacher and x.is_cuda and not self.params["student"]["is_1d"]
                 and not self.params["teacher"]["is_1d"]):
-            student_z, student_nll, teacher_z = self._forward_two_streams(x, cond)
+            student_z, student_nll, teacher_z = self._forward_two_streams(x, cond, defer)
+            if defer:
+                objective, student_nll = student_nll, None
         else:
-            student_z, student_nll, _ = self.student(x, cond)
+            if defer:
+                if self.params["student"]["is_1d"]:
+                    ld0 = torch.zeros(x.shape[0], device=x.device, dtype=torch.float32)
+                else:
+                    from .models.utils import uniform_binning_correction
+                    x, ld0 = uniform_binning_correction(x)
+                student_z, ld, rows, scale = self.student.deferred_objective(x, ld0, cond)
+                objective, student_nll = (ld, rows, scale), None
+            else:
+                student_z, student_nll, _ = self.student(x, cond)
             if self.kd_weight > 0:
                 with torch.no_grad():
                     teacher_z, _, _ = self.teacher(x, cond)   # x already carries the student's dequant noise
@@ -125,9 +143,9 @@ class NFModel(nn.Module):
             with torch.no_grad():
                 teacher_x = self.teacher(z=latent, temperature=0.7, reverse=True, y_onehot=cond)[-1]
         return {"student_nll": student_nll, "student_z": student_z, "teacher_z": teacher_z,
-                "student_x": student_x, "teacher_x": teacher_x, "weights": weights}
+                "student_x": student_x, "teacher_x": teacher_x, "weights": weights, "student_objective": objective}
 
-    def _forward_two_streams(self, x, cond):
+    def _forward_two_streams(self, x, cond, defer=False):
         """Same arithmetic and in-place side effects as the sequential code above (student noise, then teacher noise
         on top, both added to the caller's batch), but the frozen teacher runs on a second stream: its many small
         level-2/3 kernels fill the SMs the student leaves idle. Captured CUDA graphs keep the fork/join."""
@@ -141,7 +159,11 @@ class NFModel(nn.Module):
         with torch.cuda.stream(self._side), torch.no_grad():
             xt, ld_t = uniform_binning_correction(x)       # teacher's noise on top, in place (reference semantics)
             teacher_z, _, _ = self.teacher.flow_from_dequantized(xt, ld_t, cond)
-        student_z, student_nll, _ = self.student.flow_from_dequantized(xs, ld_s, cond)
+        if defer:
+            student_z, ld, rows, scale = self.student.deferred_objective(xs, ld_s, cond)
+            student_nll = (ld, rows, scale)
+        else:
+            student_z, student_nll, _ = self.student.flow_from_dequantized(xs, ld_s, cond)
         main.wait_stream(self._side)
         for i in self.teacher_kd_indices:
             teacher_z[i].record_stream(main)
@@ -149,24 +171,26 @@ class NFModel(nn.Module):
 
     # ---- pl_module.py:257-320
     def loss(self, out, *args):
-        kd = perc = None
-        if self.kd_weight > 0:
-            pairs = list(zip(self.student_kd_indices, self.teacher_kd_indices))
-            kd = Fn.kd_mse([out["student_z"][s] for s, _ in pairs], [out["teacher_z"][t] for _, t in pairs])
+        """Multi-level latent MSE, objective, perceptual L1, their weighted sum (times the RICH sample weights) and the
+        four batch means: one fused kernel forward, one backward (functional.KdNllLossFn, csrc/loss_optim.cu)."""
+        pairs = list(zip(self.student_kd_indices, self.teacher_kd_indices)) if self.kd_weight > 0 else []
+        s_levels = [out["student_z"][s] for s, _ in pairs]
+        t_levels = [out["teacher_z"][t] for _, t in pairs]
+        perc = None
         if self.perceptual_weight > 0:
             d = (out["student_x"] - out["teacher_x"]).abs()
             perc = d.flatten(1).mean(1)
             perc = torch.where(torch.isnan(perc), torch.zeros_like(perc), perc)
-        dev = out["student_nll"].device
-        if kd is None:
-            kd = torch.zeros((), device=dev)   # (graph-capturable, unlike torch.tensor(0.0))
-        if perc is None:
-            perc = torch.zeros((), device=dev)
-        result = self.nll_weight * out["student_nll"] + self.kd_weight * kd + self.perceptual_weight * perc
-        if out["weights"] is not None:
-            result = result * out["weights"]
-        return {"nll": out["student_nll"].mean(), "kd": kd.mean(), "perceptual": perc.mean(),
-                "result_loss": result.mean()}
+        spec = {"teacher": t_levels, "w": (self.nll_weight, self.kd_weight, self.perceptual_weight),
+                "sample_w": out["weights"]}
+        obj = out.get("student_objective")
+        if obj is not None:
+            ld, rows, scale = obj
+            spec.update(prior=rows, nll_scale=scale)
+            means, _, _ = Fn.KdNllLossFn.apply(spec, ld, out["student_z"][-1], perc, *s_levels)
+        else:
+            means, _, _ = Fn.KdNllLossFn.apply(spec, out["student_nll"], None, perc, *s_levels)
+        return {"nll": means[0], "kd": means[1], "perceptual": means[2], "result_loss": means[3]}
 
     # ---- pl_module.py:322-346
     @torch.no_grad()
@@ -194,7 +218,7 @@ class NFModel(nn.Module):
 
     # ---- pl_module.py:365-382
     def training_step(self, batch, batch_idx=0):
-        losses = self.loss(self.forward(batch))
+        losses = self.loss(self.forward(batch, _defer_objective=True))
         self.log("train_batch_nll", losses["nll"], on_step=True)
         self.log("train_batch_kd", losses["kd"], on_step=True)
         self.log("train_batch_perceptual", losses["perceptual"], on_step=True)

@@ -65,6 +65,57 @@ def randomise_zero_params(model: torch.nn.Module, seed: int, std: float = 0.05):
                 p.copy_((torch.randn(p.shape, generator=g) * std).to(p.device))
 
 
+class FlatAdam:
+    """torch.nn.utils.clip_grad_norm_(max_norm) + torch.optim.Adam / Adamax (pl_module.py:348-363, train.py:46) on FLAT
+    fp32 buffers, two launches per step (csrc/loss_optim.cu): every parameter's storage is re-pointed into one
+    contiguous buffer `p` (16-byte aligned slices), the gradients are gathered into `g` (the buffer the all-reduce
+    runs on), and the moments live in `m` / `v`. The step counter is a device int so a captured graph advances it."""
+
+    ALIGN = 64   # floats: every slice starts on a 256-byte boundary
+
+    def __init__(self, params: tp.Sequence[torch.nn.Parameter], lr: float, weight_decay: float = 0.0,
+                 kind: str = "adam", max_norm: float = GRAD_CLIP, betas=(0.9, 0.999), eps: float = 1e-8):
+        from . import ops
+        self.ops = ops
+        self.params = list(params)
+        dev = self.params[0].device
+        self.offsets, off = [], 0
+        for p in self.params:
+            self.offsets.append(off)
+            off += (p.numel() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        self.n = off
+        self.p = torch.zeros(off, device=dev)
+        self.g = torch.zeros(off, device=dev)
+        self.m = torch.zeros(off, device=dev)
+        self.v = torch.zeros(off, device=dev)
+        self.step_count = torch.zeros(1, device=dev, dtype=torch.int32)
+        self.partials = torch.zeros(ops.optim_partials(), device=dev)
+        self.grad_norm = torch.zeros(1, device=dev)
+        self.lr, self.wd, self.max_norm, self.betas, self.eps = lr, weight_decay, max_norm, betas, eps
+        if kind not in ("adam", "adamax"):
+            raise NameError("Unknown optimizer name")
+        self.adamax = kind == "adamax"
+        with torch.no_grad():
+            for p, o in zip(self.params, self.offsets):
+                view = self.p[o:o + p.numel()].view_as(p)
+                view.copy_(p)
+                p.data = view                    # the module's kernels now read the flat buffer directly
+        self.g_views = [self.g[o:o + p.numel()].view_as(p) for p, o in zip(self.params, self.offsets)]
+
+    def gather_grads(self):
+        """p.grad (fresh tensors produced by backward) -> slices of the flat gradient buffer, one multi-tensor copy."""
+        torch._foreach_copy_(self.g_views, [p.grad for p in self.params])
+
+    def step(self):
+        o = self.ops
+        o.grad_sqnorm(self.g, self.partials, self.step_count)
+        o.adam_step(self.p, self.g, self.m, self.v, self.partials, self.step_count, self.max_norm, self.lr,
+                    self.betas[0], self.betas[1], self.eps, self.wd, self.adamax, self.grad_norm)
+
+    def reset(self):
+        self.m.zero_(); self.v.zero_(); self.g.zero_(); self.step_count.zero_()
+
+
 class KDTrainer:
     """Owns the NFModel, its optimiser, the static device buffers and the captured graphs."""
 
@@ -81,15 +132,11 @@ class KDTrainer:
         self.is_1d = config["student"]["is_1d"]
         params = [p for p in self.module.student.parameters() if p.requires_grad]
         self.params = params
-        # flat buffer for the gradient all-reduce (one NCCL call); grads themselves are produced fresh by backward
-        # (p.grad = None before it), so autograd steals them instead of launching one "+=" kernel per parameter
-        self.flat_grad = torch.zeros(sum(p.numel() for p in params), device=device) if self.world > 1 else None
-        kw = dict(lr=config["learning_rate"], weight_decay=config["weight_decay"], capturable=True)
-        opt = torch.optim.Adam if config["optimizer"] == "adam" else torch.optim.Adamax
-        try:
-            self.opt = opt(params, fused=True, **kw) if config["optimizer"] == "adam" else opt(params, **kw)
-        except TypeError:
-            self.opt = opt(params, **kw)
+        # flat parameter / gradient / moment buffers: the all-reduce, the clipping norm and the optimiser all run on
+        # them; the gradients themselves are produced fresh by backward (p.grad = None before it), so autograd steals
+        # them instead of launching one "+=" kernel per parameter
+        self.opt = FlatAdam(params, lr=config["learning_rate"], weight_decay=config["weight_decay"],
+                            kind=config["optimizer"])
         self.x = torch.zeros(*batch_shape, device=device)          # static input buffer
         self.losses = torch.zeros(4, device=device)                 # nll, kd, perceptual, loss
         self.use_graphs = use_graphs
@@ -105,14 +152,27 @@ class KDTrainer:
         out = self.module.training_step(batch, 0)
         out["loss"].backward()
         self.losses.copy_(torch.stack([out["nll"], out["kd"], out["perceptual"], out["loss"]]).detach())
+        self.opt.gather_grads()
 
     def _clip_and_update(self):
-        torch.nn.utils.clip_grad_norm_(self.params, GRAD_CLIP, foreach=True)
         self.opt.step()
 
     def _allreduce(self):
+        """The only collective of the KD step: average the flat student gradient over the ranks."""
         if self.world > 1:
-            allreduce_mean_([p.grad for p in self.params], self.flat_grad)
+            dist.all_reduce(self.opt.g, op=dist.ReduceOp.AVG)
+
+    def flat_grad_view(self) -> torch.Tensor:
+        """The flat gradient buffer of the last step (after the all-reduce, before clipping)."""
+        return self.opt.g
+
+    def reset_state(self, student_state: tp.Optional[dict] = None):
+        """Back to a given student state_dict with fresh optimiser state (warm-up / capture steps must not count)."""
+        from . import functional as Fn
+        if student_state is not None:
+            self.module.student.load_state_dict(student_state)     # in-place copies: the flat views stay
+        self.opt.reset()
+        Fn.bump_param_epoch()
 
     def warmup(self, iters: int = 3):
         """Eager steps on a side stream (builds kernels' attributes, optimiser state), then graph capture."""
@@ -128,23 +188,31 @@ class KDTrainer:
         if not self.use_graphs:
             return
         self.g_fb = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.g_fb):
-            self._forward_backward()
-        self.g_opt = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.g_opt, pool=self.g_fb.pool()):
-            self._clip_and_update()
+        if self.world == 1:      # no collective between the halves: the whole step is ONE graph
+            with torch.cuda.graph(self.g_fb):
+                self._forward_backward()
+                self._clip_and_update()
+        else:
+            with torch.cuda.graph(self.g_fb):
+                self._forward_backward()
+            self.g_opt = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.g_opt, pool=self.g_fb.pool()):
+                self._clip_and_update()
         torch.cuda.synchronize()
 
     def step_device(self):
         """One training step on whatever self.x currently holds (inputs already resident in HBM)."""
+        from . import functional as Fn
         if self.g_fb is not None:
             self.g_fb.replay()
-            self._allreduce()
-            self.g_opt.replay()
+            if self.g_opt is not None:
+                self._allreduce()
+                self.g_opt.replay()
         else:
             self._forward_backward()
             self._allreduce()
             self._clip_and_update()
+        Fn.bump_param_epoch()     # parameter values changed behind autograd's back: drop cached derived operands
 
     def step(self, host_batch: torch.Tensor) -> torch.Tensor:
         """Public end-to-end step: pinned host batch -> device, train, loss scalars back on the host."""

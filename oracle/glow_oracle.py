@@ -409,3 +409,52 @@ def kd_step(student_sd: SD, student_cfg: dict, teacher_sd: SD, teacher_cfg: dict
         result = result * sample_weights
     return {"nll": out["nll"].mean(), "kd": out["kd"].mean(), "perceptual": out["perceptual"].mean(),
             "result_loss": result.mean(), "student_z": s_z}
+
+
+# ------------------------------------------------------------------------------------------ synthetic weights
+def random_state_dict(cfg: dict, seed: int, std: float = 0.05) -> SD:
+    """A reference-format state_dict with seeded random weights of the reference's shapes, built WITHOUT any model
+    class (bench.py's reference arm must not touch the product package): conv weights Xavier-normal like
+    models/layers.py:209-214, invconv from the LU factors of a random orthogonal matrix like :336-352, and the
+    tensors the reference zero-initialises (ActNorm bias/logs, Conv2dZeros, LinearZeros) drawn
+    N(0, std^2) so that every coupling does real work. Timing input only — parity tests use fixtures / shared dicts."""
+    g = torch.Generator().manual_seed(seed)
+    rn = lambda *s: torch.randn(*s, generator=g)
+    sd: SD = {}
+    hid = cfg["hidden_channels"]
+    is_1d = cfg.get("is_1d", False)
+    cond = cfg["y_classes"] if cfg.get("y_condition", False) else 0
+    for i, (kind, C, H, W) in enumerate(layer_plan(cfg)):
+        pre = f"flow.layers.{i}."
+        if kind == "step":
+            shp = [1, C] if is_1d else [1, C, 1, 1]
+            sd[pre + "actnorm.bias"], sd[pre + "actnorm.logs"] = rn(*shp) * std, rn(*shp) * std
+            q = torch.linalg.qr(rn(C, C))[0]
+            p_, lo, up = torch.lu_unpack(*torch.linalg.lu_factor(q))
+            s_ = torch.diag(up)
+            sd[pre + "invconv.p"], sd[pre + "invconv.sign_s"] = p_, torch.sign(s_)
+            sd[pre + "invconv.lower"], sd[pre + "invconv.upper"] = lo, torch.triu(up, 1)
+            sd[pre + "invconv.log_s"] = torch.log(torch.abs(s_))
+            cin, cout = C // 2 + cond, (C - C // 2) * 2
+            if is_1d:
+                dims = [cin, hid, hid, hid, hid, hid, cout]
+                for j, k in enumerate((0, 2, 4, 6, 8, 10)):
+                    bound = 1.0 / math.sqrt(dims[j])
+                    sd[f"{pre}block.{k}.weight"] = (torch.rand(dims[j + 1], dims[j], generator=g) * 2 - 1) * bound
+                    sd[f"{pre}block.{k}.bias"] = (torch.rand(dims[j + 1], generator=g) * 2 - 1) * bound
+            else:
+                sd[pre + "block.0.conv.weight"] = rn(hid, cin, 3, 3) * math.sqrt(2.0 / (9 * (cin + hid)))
+                sd[pre + "block.2.conv.weight"] = rn(hid, hid, 1, 1) * math.sqrt(2.0 / (2 * hid))
+                for k in ("0", "2"):
+                    sd[f"{pre}block.{k}.actnorm.bias"] = rn(1, hid, 1, 1) * std
+                    sd[f"{pre}block.{k}.actnorm.logs"] = rn(1, hid, 1, 1) * std
+                sd[pre + "block.4.conv.weight"] = rn(cout, hid, 3, 3) * std
+                sd[pre + "block.4.conv.bias"] = rn(cout) * std
+                sd[pre + "block.4.logs"] = rn(cout, 1, 1) * std
+        elif kind == "split":
+            sd[pre + "conv.conv.weight"] = rn(C, C // 2, 3, 3) * std
+            sd[pre + "conv.conv.bias"] = rn(C) * std
+            sd[pre + "conv.logs"] = rn(C, 1, 1) * std
+    kind, C, H, W = layer_plan(cfg)[-1]
+    sd["prior_h"] = torch.zeros([1, 2 * C] + ([] if is_1d else [H, W]))
+    return sd

@@ -61,3 +61,29 @@ def maf_inverse(sd, D, n_layers, z):
     for l in reversed(range(n_layers)):
         z, _ = made_inverse(z, sd, f"flow.layers.{l}.", D)
     return z
+
+
+def hidden_degrees(D, H):
+    """Sorted degrees 1..D-1, each ~H/(D-1) times (Germain et al. 2015, eq. 12-13, deterministic assignment); changes
+    fall on multiples of 8 units when there are at least D-1 such groups (same rule as the product's models/maf.py)."""
+    if D <= 1:
+        return torch.ones(H, dtype=torch.int32)
+    if H % 8 == 0 and H // 8 >= D - 1:
+        tiles = H // 8
+        return (torch.arange(tiles, dtype=torch.int64) * (D - 1) // tiles + 1).repeat_interleave(8).to(torch.int32)
+    return (torch.arange(H, dtype=torch.int64) * (D - 1) // H + 1).to(torch.int32)
+
+
+def random_state_dict(D, H, n_layers, seed):
+    """Seeded nn.Linear-style weights for `n_layers` MADE layers (timing input for bench.py's reference arm)."""
+    g = torch.Generator().manual_seed(seed)
+    u = lambda *s, fan: (torch.rand(*s, generator=g) * 2 - 1) / math.sqrt(fan)
+    sd = {}
+    for l in range(n_layers):
+        pre = f"flow.layers.{l}."
+        deg = hidden_degrees(D, H)
+        sd[pre + "deg1"], sd[pre + "deg2"] = deg.clone(), deg.clone()
+        sd[pre + "fc1.weight"], sd[pre + "fc1.bias"] = u(H, D, fan=D), u(H, fan=D)
+        sd[pre + "fc2.weight"], sd[pre + "fc2.bias"] = u(H, H, fan=H), u(H, fan=H)
+        sd[pre + "fc3.weight"], sd[pre + "fc3.bias"] = u(2 * D, H, fan=H) * 0.1, torch.zeros(2 * D)
+    return sd

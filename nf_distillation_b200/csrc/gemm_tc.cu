@@ -767,7 +767,8 @@ extern "C" int nfk_gemm_tn_bf16(const void* A, long long lda, const void* B, lon
   const int tiles = ((Mo + BM - 1) / BM) * g.n_tiles;
   const int total_kb = (Kpix + BK - 1) / BK;
   if (sm_count <= 0) sm_count = 148;
-  int splits = max(1, min(total_kb, (sm_count + tiles - 1) / tiles));
+  // one wave: tiles * splits <= SMs (one CTA per SM; 152 CTAs on 148 SMs would run as two waves at half the speed)
+  int splits = max(1, min(total_kb, sm_count / tiles));
   g.kb_per_split = (total_kb + splits - 1) / splits;
   splits = (total_kb + g.kb_per_split - 1) / g.kb_per_split;
   CUtensorMap tmA, tmB;

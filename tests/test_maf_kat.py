@@ -78,30 +78,34 @@ def test_maf_oracle_jacobian_is_triangular_and_logdet_is_its_log_determinant():
 # ------------------------------------------------------------------------------------------------ GPU: the kernels
 @pytest.mark.gpu
 def test_cuda_maf_reproduces_the_hand_derived_known_answers():
-    """Forward u / per-layer outputs / log-det / nll and the sequential inverse of the CUDA path against the float64
-    closed forms. Every weight and input is exactly representable in bf16, so the tensor-core products are exact and
-    the tolerance is fp32 rounding of exp() and the affine: 2e-6 relative."""
+    """The CUDA path against the float64 closed forms. Layer 1: every weight and input is exactly representable in
+    bf16, so the tensor-core products are exact and what is left is fp32 rounding of exp() and the affine (2e-6) —
+    forward u, log-det, and both inverse kernels (whose recursion feeds back dyadic x_d, again exact). Layer 2 takes
+    layer 1's output, which bf16 rounds on its way into the masked GEMM: conditioner inputs carry 2^-9 relative
+    rounding, so the two-layer outputs / nll are held to 1e-2 / 2e-3."""
     from nf_distillation_b200.models.maf import create_maf_model
     d, sd = kat()
     m = create_maf_model(dict(image_shape=[3], hidden_channels=64, K=2))
     m.load_state_dict(sd)
     m = m.cuda().eval()
     x = t(d["x"]).float().cuda()
-    with torch.no_grad():
-        outs, nll, _ = m(x, None)
     rel = lambda a, b: ((a.double().cpu() - b).abs().max() / b.abs().max()).item()
-    assert rel(outs[0], t(d["out_layer1"])) < 2e-6
-    assert rel(outs[1], t(d["out_layer2"])) < 2e-6
-    assert rel(nll, t(d["nll"])) < 2e-6
-    for resident in (True, False):                      # shared-memory-resident inverse and the D-pass GEMM inverse
-        for layer in m.flow.layers:
-            layer.resident_inverse = resident
-        with torch.no_grad():
-            back = m(z=outs[1], reverse=True)[-1]
-        assert rel(back, t(d["x"])) < 5e-6, resident
+    layer1 = m.flow.layers[0]
+    with torch.no_grad():
+        u, ld = layer1(x, logdet=torch.zeros(x.shape[0], device="cuda"))
+        assert rel(u, t(d["out_layer1"])) < 2e-6 and rel(ld, t(d["logdet_layer1"])) < 2e-6
+        for resident in (True, False):                  # shared-memory-resident inverse and the D-pass GEMM inverse
+            layer1.resident_inverse = resident
+            back, ldb = layer1(t(d["out_layer1"]).float().cuda(), logdet=ld, reverse=True)
+            assert rel(back, t(d["x"])) < 5e-6, resident
+            assert ldb.abs().max().item() < 1e-5, resident          # logdet(fwd) + logdet(inverse) = 0
+        outs, nll, _ = m(x, None)
+        assert rel(outs[0], t(d["out_layer1"])) < 2e-6
+        assert rel(outs[1], t(d["out_layer2"])) < 1e-2 and rel(nll, t(d["nll"])) < 2e-3
+        assert rel(m(z=outs[1], reverse=True)[-1], t(d["x"])) < 1e-2
     # training path (activation-saving forward) gives the same numbers
     outs_t, nll_t, _ = m(x.clone().requires_grad_(True), None)
-    assert rel(nll_t.detach(), t(d["nll"])) < 2e-6
+    assert rel(outs_t[0].detach(), t(d["out_layer1"])) < 2e-6 and rel(nll_t.detach(), t(d["nll"])) < 2e-3
 
 
 @pytest.mark.gpu

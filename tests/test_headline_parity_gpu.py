@@ -107,7 +107,8 @@ def test_flowstep_hidden512_forward_backward_all_fused_variants(C, H, B):
     # ---- training mode: the same kernel also stores h1 and the two ReLU masks
     xg = x.to(dev).requires_grad_(True)
     zt, ldt = st(xg, logdet=ld0.to(dev), reverse=False)
-    assert torch.equal(zt.detach(), zi) and torch.equal(ldt.detach(), ldi), "training and inference kernels must agree bit for bit"
+    assert torch.equal(zt.detach(), zi), "training and inference kernels must agree bit for bit"
+    assert rel(ldt, ldi) < 1e-6      # (per-sample log-det partial sums meet in fp32 atomics: order is not fixed)
     ((zt * wz.to(dev)).sum() + (ldt * wl.to(dev)).sum()).backward()
     assert rel(xg.grad, dx16) < BOUND_GRAD_BF16 and rel(xg.grad, dx32) < 5e-2
     worst16 = worst32 = 0.0

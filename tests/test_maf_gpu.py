@@ -54,7 +54,10 @@ def test_maf_forward_inverse_backward_vs_paper_restatement(D, H, K, B):
         assert rel(x_dp, x) < (1e-5 if B < 4096 else 1e-4)
         for push, mt in ((True, 0), (False, 1), (False, 2)):   # push kernel; pull kernel with 16 / 32 samples per warp
             lay.push_inverse, lay.resident_mtiles = push, mt
-            assert lay._inverse_jobs(z.device)[1] == push
+            # the push kernel needs degree changes on whole 8-unit tiles; with fewer tiles than degrees (H/8 < D-1)
+            # the module keeps the standard per-unit MADE assignment and every request lands on the pull kernel
+            aligned = H // 8 >= D - 1
+            assert lay._inverse_jobs(z.device)[1] == (push and aligned)
             x_r, ld_r = lay(z, logdet=ld, reverse=True)
             assert rel(x_r, x_dp) < 1e-4, (push, mt)
             assert (ld_r - ld_dp).abs().max().item() < 1e-3 * (ld.abs().max().item() + 1), (push, mt)

@@ -573,6 +573,9 @@ def main():
     ap.add_argument("--no-graphs", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-batch", type=int, default=32)
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16x3"],
+                    help="arithmetic of the 2-D coupling-net GEMMs: bf16 operands (default) or the fp32-class "
+                         "3-term split (models.flows.Glow.set_precision)")
     ap.add_argument("--ncu-step", action="store_true",
                     help="profiling aid: warm up, then run ONE eager step between cudaProfilerStart/Stop and exit "
                          "(use with ncu --profile-from-start off); prints no bench value")
@@ -617,6 +620,13 @@ def main():
         config = kd_config(s_cfg, glow_cfg(wl["image"], wl["tK"], wl["L"], wl["hidden"]))
         shape = (B, C, H, W)
     trainer = KDTrainer(config, shape, device, use_graphs=not args.no_graphs)
+    dtype = wl["dtype"]
+    if args.precision != "bf16":
+        if is_1d:
+            raise SystemExit("--precision applies to the 2-D Glow workloads (the 1-D path is fp32 already)")
+        trainer.module.student.set_precision(args.precision)
+        trainer.module.teacher.set_precision(args.precision)
+        dtype = "bf16x3 (fp32-class: hi+lo split bf16 operands, 3 partial products, fp32 accumulate)"
     n_pool = 4
 
     def synth(i):
@@ -690,7 +700,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e = t.tolist()
 
-    roof = roofline_for(wl, B, device) if rank == 0 else None
+    roof = roofline_for(wl, B, device) if rank == 0 and args.precision == "bf16" else None
 
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -707,7 +717,7 @@ def main():
                         l2="per-step working set (activations ~GBs) exceeds the 126 MB L2; inputs rotate over 4 batches")
         out = {"metric": METRIC, "value": gb / (ms * 1e-3), "unit": "samples/s", "n_gpus": world,
                "steps": args.steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True,
-               "scaling": scaling_kind(args), "vs_baseline": None, "dtype": wl["dtype"],
+               "scaling": scaling_kind(args), "vs_baseline": None, "dtype": dtype,
                "data": "synthetic", "config": cfg_desc, "clocks": clocks,
                "e2e": {"value": gb / (ms_e2e * 1e-3), "unit": "samples/s", "ms_per_step": ms_e2e,
                        "h2d_bytes_per_step": host_pool[0].numel() * 4, "d2h_bytes_per_step": 16},

@@ -310,6 +310,28 @@ int nfk_adam_step(float* p, const float* g, float* m, float* v, long long n, con
                   float max_norm, float lr, float beta1, float beta2, float eps, float weight_decay, int adamax,
                   float* norm_out, void* stream);
 
+/* ---- fp32-class coupling network on the bf16 tiles: "bf16x3" precision mode (csrc/split3.cu) ---------------------
+ * The reference's convolutions are fp32 (models/layers.py:209,249). Each fp32 operand is split a = hi + lo into two
+ * bf16 numbers and a*b ~= hi*hi + hi*lo + lo*hi (2^-16 relative) is computed by the SAME tensor-core GEMMs in one pass
+ * over K-concatenated operands: activations as [hi | hi | lo] (pattern 0), weights as [hi | lo | hi] (pattern 1).
+ * `pattern` selects the operand layout: 0 = A [h|h|m], 1 = B [h|m|h] (three terms, 2^-16); 2 = A [h|h|h|m|m|l],
+ * 3 = B [h|m|l|h|m|h] (six terms, 2^-24: used for the forward pre-activations, whose signs are the ReLU masks).
+ *   nfk_split3_rows      src fp32 [rows, lds] (first Ksrc columns; zero padded to K) -> out bf16 [rows, terms*K]
+ *   nfk_im2col3x3_split3 3x3 'same' im2col (k = tap*Cc + c, zero padded to Kp) of an NCHW channel slice (layout 0) or a
+ *                        pixel-major [M, Cc] matrix (layout 1); flip != 0 mirrors the taps (transposed conv);
+ *                        pattern 0 or 2 -> [M, terms*Kp]
+ *   nfk_act_split3       mode 0: relu(pre); mode 1: pre where gate > 0 (gate: bf16, row stride ldg); pattern 0 or 2
+ *                        -> [M, terms*N], and colsum[n] += column sums of the fp32 result (bias gradients)
+ *   nfk_coupling_bwd_f32 backward of the affine coupling (models/flows.py:160-168) with an fp32 pixel-major dh [M, C] */
+int nfk_split3_rows(const float* src, long long lds, long long rows, int K, int Ksrc, int pattern, void* out,
+                    void* stream);
+int nfk_im2col3x3_split3(const float* src, int layout, int Ctot, int c0, int Cc, int B, int H, int W, int flip,
+                         int Kp, int pattern, void* out, void* stream);
+int nfk_act_split3(const float* pre, long long M, int N, int mode, const void* gate, long long ldg, int pattern,
+                   void* out, float* colsum, void* stream);
+int nfk_coupling_bwd_f32(const float* g_out, const float* g_ld, const float* z_out, const float* hsave, float* dy,
+                         float* dh, float* dbias3, int B, int C, int H, int W, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -110,6 +110,10 @@ SIGNATURES: dict[str, list] = {
     "nfk_optim_partials": [],
     "nfk_grad_sqnorm": [_vp, _ll, _vp, _vp, _vp],
     "nfk_adam_step": [_vp, _vp, _vp, _vp, _ll, _vp, _vp, _f, _f, _f, _f, _f, _f, _i, _vp, _vp],
+    "nfk_split3_rows": [_vp, _ll, _ll, _i, _i, _i, _vp, _vp],
+    "nfk_im2col3x3_split3": [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp],
+    "nfk_act_split3": [_vp, _ll, _i, _i, _vp, _ll, _i, _vp, _vp, _vp],
+    "nfk_coupling_bwd_f32": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
 }
 
 

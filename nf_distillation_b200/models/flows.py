@@ -112,6 +112,9 @@ class FlowStep(nn.Module):
         make = get_block_1d if is_1d else get_block_2d
         self.block = make(in_block, out_block, hidden_channels)
         self._cache = {}
+        # arithmetic of the coupling-net GEMMs (2-D): "bf16" = bf16 operands, fp32 accumulate (default, the benched
+        # mode); "bf16x3" = fp32-class split products (nf_distillation_b200/precise.py). Glow.set_precision sets it.
+        self.precision = "bf16"
 
     # ---- parameter views in the order the kernels expect
     def _coupling_params_2d(self):
@@ -217,6 +220,8 @@ class FlowStep(nn.Module):
         params = self._all_params()
         needs_grad = torch.is_grad_enabled() and (input.requires_grad or ld.requires_grad
                                                   or any(p.requires_grad for p in params))
+        if self.precision == "bf16x3":
+            return self._forward_precise(input, ld, want_ld, reverse, needs_grad)
         if not reverse:
             if needs_grad:
                 if not self.invconv.LU_decomposed:
@@ -232,6 +237,23 @@ class FlowStep(nn.Module):
                                           "perceptual weight 0, conf/training/cifar.yaml:17-20)")
             z, ld_out = Fn.flowstep2d_reverse(input.contiguous(), ld.contiguous(), self._consts(True),
                                               self.hidden_channels)
+        return z, (ld_out if want_ld else None)
+
+    def _forward_precise(self, input, ld, want_ld, reverse, needs_grad):
+        """fp32-class mode (precise.py): split-bf16 products on the same tensor-core tiles."""
+        from .. import precise
+        if self.flow_coupling != "affine":
+            raise NotImplementedError("bf16x3 precision is built for the affine coupling")
+        with torch.set_grad_enabled(needs_grad):
+            fp = precise.folded_params(self)
+            if not reverse:
+                z, ld_out = precise.FlowStep2dX3Fn.apply(input, ld, self.hidden_channels, *fp)
+            else:
+                if needs_grad:
+                    raise NotImplementedError("gradients through the 2-D inverse pass are not built")
+                k = self._consts(True)
+                z, ld_out = precise.flowstep2d_reverse_x3(input.contiguous(), ld.contiguous(), self.hidden_channels,
+                                                          (k.Wf, k.bf, k.sl), *fp[3:])
         return z, (ld_out if want_ld else None)
 
     def normal_flow(self, input, y_onehot, logdet):
@@ -392,3 +414,14 @@ class Glow(nn.Module):
         for _, module in self.named_modules():
             if isinstance(module, (ActNorm2d, ActNorm1d)):
                 module.inited = True
+
+    def set_precision(self, precision: str):
+        """Arithmetic of the 2-D coupling-net GEMMs: "bf16" (default: bf16 operands, fp32 accumulation) or "bf16x3"
+        (fp32-class: every operand split hi + lo, three partial products; ~3x the tensor-core work). Everything else
+        (z path, log-dets, Split2d, prior, losses, the whole 1-D path) is fp32 in both."""
+        if precision not in ("bf16", "bf16x3"):
+            raise ValueError("precision must be 'bf16' or 'bf16x3'")
+        for layer in self.flow.layers:
+            if isinstance(layer, FlowStep):
+                layer.precision = precision
+        return self

@@ -442,3 +442,83 @@ def test_one_rank_and_two_ranks_make_the_same_update_on_a_fixed_global_batch(tmp
         tot += d.numel()
         assert d.max().item() <= 2.1 * 5e-4, k
     assert bad <= 1e-4 * tot, (bad, tot)
+
+
+# ------------------------------------------------------------------------------------------------ fp32-class mode
+def rel_l2(a, b):
+    a, b = a.detach().double().cpu().flatten(), b.detach().double().cpu().flatten()
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+# gradients that reach the loss WITHOUT passing a ReLU mask of this step's coupling net (everything else does)
+UNKINKED = ("block.2.actnorm.logs", "block.4.logs", "block.4.conv.weight", "block.4.conv.bias")
+
+
+@pytest.mark.parametrize("C,H,B", [(12, 16, 40), (24, 8, 20), (48, 4, 37)])
+def test_bf16x3_precision_flowstep_matches_the_fp32_oracle(C, H, B):
+    """precision="bf16x3" (nf_distillation_b200/precise.py, csrc/split3.cu): every coupling-net operand split into
+    h + m bf16 parts, three partial products per GEMM, fp32 accumulation. Against the fp32 oracle (the reference's own
+    arithmetic, /root/reference/models/layers.py:209-228): outputs 1e-4 of max|z| and log-det 1e-5 (measured 2e-6 /
+    6e-7: fp32 level). Gradients: 5e-5 of max|grad| on every tensor that no ReLU mask separates from the loss; on the
+    others a handful of the ~5 M ReLU units have |pre-activation| < 5e-6 and take the other mask than the reference,
+    each moving its row of a weight gradient by O(1/sqrt(M)) — held to 5e-3 in relative L2 and 1.5e-2 in max-norm
+    (measured 1e-3..3e-3 / 7e-3; the bf16 mode measures 2e-2 / 6e-2 on the same tensors)."""
+    from oracle import glow_oracle as O
+    st, sd = make_step(C, 512, 300 + C)
+    st.precision = "bf16x3"
+    g = torch.Generator().manual_seed(C + 1)
+    x = torch.randn(B, C, H, H, generator=g)
+    ld0 = torch.randn(B, generator=g)
+    wz, wl = torch.randn(B, C, H, H, generator=g), torch.randn(B, generator=g)
+    names = dict(st.named_parameters())
+    osd = {k: (v.clone().requires_grad_(True) if k in names else v) for k, v in sd.items()}
+    xo = x.clone().requires_grad_(True)
+    z32, ld32 = O.flowstep(xo, osd, "", ld0, False)
+    ((z32 * wz).sum() + (ld32 * wl).sum()).backward()
+    st = st.to(dev)
+    xg = x.to(dev).requires_grad_(True)
+    zt, ldt = st(xg, logdet=ld0.to(dev), reverse=False)
+    ((zt * wz.to(dev)).sum() + (ldt * wl.to(dev)).sum()).backward()
+    assert rel(zt, z32) < 1e-4 and rel(ldt, ld32) < 1e-5
+    assert rel_l2(xg.grad, xo.grad) < 5e-3 and rel(xg.grad, xo.grad) < 1.5e-2
+    for n_, p in st.named_parameters():
+        e, e2 = rel(p.grad, osd[n_].grad), rel_l2(p.grad, osd[n_].grad)
+        if n_ in UNKINKED:
+            assert e < 5e-5, (n_, e, e2)
+        else:   # one flipped unit weighs 1/sqrt(M) of a gradient entry summed over M pixels
+            assert e < max(1.5e-2, (B * H * H) ** -0.5) and e2 < 5e-3, (n_, e, e2)
+    # inverse in the same mode undoes the forward (and the no-grad forward equals the training forward)
+    with torch.no_grad():
+        zi, ldi = st(x.to(dev), logdet=ld0.to(dev), reverse=False)
+        back, ldb = st(zi, logdet=ldi, reverse=True)
+    assert torch.equal(zi, zt.detach())
+    assert rel(back, x) < 1e-4 and rel(ldb, ld0) < 1e-4
+
+
+def test_bf16x3_precision_kd_step_taps_and_gradients_at_fp32_level(monkeypatch):
+    """The KD training step (teacher K=4, student K=2, L=3, hidden 512, B=16) with both models in bf16x3 mode against
+    the fp32 oracle: loss terms 1e-5, the student's KD taps 1e-4 of max|z| (the bf16 mode's bound is 1e-2), student
+    gradients 5e-3 in relative L2 and 1.5e-2 in max-norm per tensor, median 5e-4 (ReLU-mask flips, see above; bf16
+    mode: median 1e-2, worst 0.1 in max-norm)."""
+    from nf_distillation_b200.models import utils as U
+    m, s_cfg, t_cfg, s_sd, t_sd = kd_models(2, 4, 512, seed=3)
+    m.student.set_precision("bf16x3")
+    m.teacher.set_precision("bf16x3")
+    names = set(dict(m.student.named_parameters()))
+    g = torch.Generator().manual_seed(21)
+    B = 16
+    x = images(B, 32, g)
+    n1, n2 = torch.rand(B, 3, 32, 32, generator=g) / 256, torch.rand(B, 3, 32, 32, generator=g) / 256
+    l32, g32, z32 = oracle_kd_grads(s_sd, s_cfg, t_sd, t_cfg, x, n1, n2, names, False)
+    m.to(dev)
+    q = [n1.to(dev), n2.to(dev)]
+    monkeypatch.setattr(U, "dequant_noise", lambda t_, n: q.pop(0))
+    fw = m.forward([x.to(dev), None])
+    for i in m.student_kd_indices:
+        assert rel(fw["student_z"][i], z32[i]) < 1e-4, i
+    losses = m.loss(fw)
+    losses["result_loss"].backward()
+    for k_, r in (("nll", "nll"), ("kd", "kd"), ("result_loss", "result_loss")):
+        assert abs(losses[k_].item() - l32[r]) < 1e-5 * abs(l32[r]) + 1e-7, (k_, losses[k_].item(), l32[r])
+    errs = sorted((rel(p.grad, g32[n_]), rel_l2(p.grad, g32[n_]), n_) for n_, p in m.student.named_parameters())
+    assert errs[-1][0] < 1.5e-2 and max(e[1] for e in errs) < 5e-3 and errs[len(errs) // 2][0] < 5e-4, errs[-3:]

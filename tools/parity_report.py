@@ -9,8 +9,9 @@ from oracle import glow_oracle as O
 dev = "cuda"
 
 
-def flowstep(C, H, B):
+def flowstep(C, H, B, precision="bf16"):
     st, sd = T.make_step(C, 512, 100 + C)
+    st.precision = precision
     g = torch.Generator().manual_seed(C)
     x = torch.randn(B, C, H, H, generator=g); ld0 = torch.randn(B, generator=g)
     wz, wl = torch.randn(B, C, H, H, generator=g), torch.randn(B, generator=g)
@@ -26,7 +27,7 @@ def flowstep(C, H, B):
     xg = x.to(dev).requires_grad_(True)
     zt, ldt = st(xg, logdet=ld0.to(dev), reverse=False)
     ((zt * wz.to(dev)).sum() + (ldt * wl.to(dev)).sum()).backward()
-    print(f"--- FlowStep C={C} H={H} B={B} (M={B*H*H})")
+    print(f"--- FlowStep C={C} H={H} B={B} (M={B*H*H}) precision={precision}")
     for bf16 in (False, True):
         z, ld, dx, gr = res[bf16]
         tag = "bf16-oracle" if bf16 else "fp32-oracle"
@@ -68,5 +69,8 @@ if __name__ == "__main__":
     if "steps" in what:
         for C, H, B in ((12, 16, 40), (24, 8, 136), (48, 4, 520)):
             flowstep(C, H, B)
+    if "x3" in what:
+        for C, H, B in ((12, 16, 40), (24, 8, 20)):
+            flowstep(C, H, B, "bf16x3")
     if "kd" in what:
         kd_step()

@@ -157,6 +157,21 @@ int nfk_split2d_rev(const float* z1, const float* w, const float* bias, const fl
 int nfk_split2d_bwd(const float* x, const float* w, const float* bias, const float* logs, const float* g_z1,
                     const float* g_ld, float* dx, float* dw, float* dbias, float* dlogs, int B, int C, int H, int W,
                     void* stream);
+/* Split2d with the following SqueezeLayer folded in (models/layers.py:32-44,316-327): z1_sq_out (optional,
+ * [B, 4*C/2, H/2, W/2]) receives the space-to-depth copy of z1 in the same pass; the backward reads the gradient of
+ * that squeezed tensor (g_z1_sq, optional) through the same index map and adds it to g_z1's. */
+int nfk_split2d_squeeze_fwd(const float* x, const float* w, const float* bias, const float* logs, float* z1_out,
+                            float* z1_sq_out, float* ld, int B, int C, int H, int W, void* stream);
+int nfk_split2d_squeeze_bwd(const float* x, const float* w, const float* bias, const float* logs, const float* g_z1,
+                            const float* g_z1_sq, const float* g_ld, float* dx, float* dw, float* dbias, float* dlogs,
+                            int B, int C, int H, int W, void* stream);
+/* First kernel of the 2-D flow (csrc/preproc.cu): data/src/utils.py:7-18 preprocess (when src is raw uint8 pixels:
+ * floor(u8 / 2^(8-n_bits)) / 2^n_bits - 0.5; src_is_u8 == 0: src is fp32 and already preprocessed) + the dequantisation
+ * noise of models/utils.py:26-41 (noise: U(0, 1/2^n_bits) drawn by the caller, optional) + the first SqueezeLayer
+ * (models/layers.py:32-44): x_out [B,C,H,W] = v + noise (optional; may alias an fp32 src: in-place like the reference),
+ * sq_out [B,4C,H/2,W/2] = its space-to-depth copy (optional). W % 4 == 0, H even. */
+int nfk_dequant_squeeze(const void* src, int src_is_u8, int n_bits, const float* noise, float* x_out, float* sq_out,
+                        int B, int C, int H, int W, void* stream);
 int nfk_prior_bpd_fwd(const float* z, const float* mean, const float* logs, const float* logdet, int B, int n,
                       float scale, float* out, void* stream);
 int nfk_prior_bpd_bwd(const float* z, const float* mean, const float* logs, const float* g_bpd, int B, int n,

@@ -78,6 +78,9 @@ SIGNATURES: dict[str, list] = {
     "nfk_split2d_fwd": [_vp] * 6 + [_i] * 4 + [_vp],
     "nfk_split2d_rev": [_vp] * 5 + [_f, _vp] + [_i] * 4 + [_vp],
     "nfk_split2d_bwd": [_vp] * 10 + [_i] * 4 + [_vp],
+    "nfk_split2d_squeeze_fwd": [_vp] * 7 + [_i] * 4 + [_vp],
+    "nfk_split2d_squeeze_bwd": [_vp] * 11 + [_i] * 4 + [_vp],
+    "nfk_dequant_squeeze": [_vp, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "nfk_prior_bpd_fwd": [_vp] * 4 + [_i, _i, _f, _vp, _vp],
     "nfk_prior_bpd_bwd": [_vp] * 4 + [_i, _i, _f, _vp, _vp, _vp],
     "nfk_kd_mse_fwd": [_vp, _vp, _i, _i, _f, _vp, _vp],

@@ -15,7 +15,20 @@ constexpr float kLog2Pi = 1.8378770664093453f;
 
 struct SGeo {
   int B, C, HW, W, H, ipc, pixt;
+  // SqueezeLayer (models/layers.py:32-44,316-327) folded into the split: the level's output z1 is ALSO written in
+  // space-to-depth layout [B, 4*C/2, H/2, W/2] (forward), and the gradient of that squeezed tensor is read through the
+  // same index map (backward) — the next level's input costs no separate permute/copy pass.
+  float* z1_sq;
+  const float* g_z1_sq;
 };
+
+// element (b, c, pixel p) of a [B, CH, H, W] map inside its 2x2 space-to-depth image [B, 4*CH, H/2, W/2]:
+// channel c*4 + (y&1)*2 + (x&1), position (y/2, x/2)
+__device__ __forceinline__ long long squeezed_index(int b, int c, int p, int CH, int H, int W) {
+  const int y = p / W, x = p - y * W;
+  return ((static_cast<long long>(b) * 4 * CH + c * 4 + (y & 1) * 2 + (x & 1)) * (H >> 1) + (y >> 1)) * (W >> 1) +
+         (x >> 1);
+}
 
 // smem: ws[C*CH*9] | bsc[2*C] (bias, exp(3 logs)) | z1s[CH*ldp] | z2s[CH*ldp] | ls[CH*ldp]
 __global__ void __launch_bounds__(ST)
@@ -46,6 +59,7 @@ split2d_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, con
     if (!reverse) {
       z2s[c * ldp + img * g.HW + p] = x[base + static_cast<long long>(CH + c) * g.HW + p];
       z1_out[(static_cast<long long>(b0 + img) * CH + c) * g.HW + p] = v1;
+      if (g.z1_sq) g.z1_sq[squeezed_index(b0 + img, c, p, CH, g.H, g.W)] = v1;
     } else {
       out_full[(static_cast<long long>(b0 + img) * C + c) * g.HW + p] = v1;
       z2s[c * ldp + img * g.HW + p] =
@@ -196,7 +210,9 @@ split2d_bwd_kernel(const float* __restrict__ x, const float* __restrict__ w, con
           for (int co = 0; co < C; ++co) a = fmaf(dps[co * ldp + q], wp[co * CH * 9], a);
         }
         const long long gi = (static_cast<long long>(b0 + img) * CH + ci) * g.HW + rem;
-        dx[(static_cast<long long>(b0 + img) * C + ci) * g.HW + rem] = a + (g_z1 ? g_z1[gi] : 0.f);
+        dx[(static_cast<long long>(b0 + img) * C + ci) * g.HW + rem] =
+            a + (g_z1 ? g_z1[gi] : 0.f) +
+            (g.g_z1_sq ? g.g_z1_sq[squeezed_index(b0 + img, ci, rem, CH, g.H, g.W)] : 0.f);
       }
     }
     // dw[co][ci][tap] += sum_m dpre[co, m] * z1[ci, m + off(tap)]   (entry e is owned by thread e % ST)
@@ -280,8 +296,12 @@ split2d_fwd_px_kernel(const float* __restrict__ x, const float* __restrict__ w, 
     const int img = pl / g.HW, p = pl - img * g.HW;
     const float v1 = x[(static_cast<long long>(b0 + img) * cin_total + c) * g.HW + p];
     z1s[c * ldp + pl] = v1;
-    if (!reverse) z1_out[(static_cast<long long>(b0 + img) * CH + c) * g.HW + p] = v1;
-    else out_full[(static_cast<long long>(b0 + img) * C + c) * g.HW + p] = v1;
+    if (!reverse) {
+      z1_out[(static_cast<long long>(b0 + img) * CH + c) * g.HW + p] = v1;
+      if (g.z1_sq) g.z1_sq[squeezed_index(b0 + img, c, p, CH, g.H, g.W)] = v1;
+    } else {
+      out_full[(static_cast<long long>(b0 + img) * C + c) * g.HW + p] = v1;
+    }
   }
   __syncthreads();
   for (int pl0 = 0; pl0 < npix; pl0 += ST) {
@@ -443,7 +463,9 @@ split2d_bwd_px_kernel(const float* __restrict__ x, const float* __restrict__ w, 
 #pragma unroll
       for (int ci = 0; ci < CH; ++ci) {
         const long long gi = (static_cast<long long>(b0 + img) * CH + ci) * g.HW + rem;
-        dx[(static_cast<long long>(b0 + img) * C + ci) * g.HW + rem] = a[ci] + (g_z1 ? g_z1[gi] : 0.f);
+        dx[(static_cast<long long>(b0 + img) * C + ci) * g.HW + rem] =
+            a[ci] + (g_z1 ? g_z1[gi] : 0.f) +
+            (g.g_z1_sq ? g.g_z1_sq[squeezed_index(b0 + img, ci, rem, CH, g.H, g.W)] : 0.f);
       }
     }
     // ---- C: dw[co][ci][tap] += sum_m dpre[co, m] * z1[ci, m + off(tap)]; thread tile = 4 co x one (ci, tap)
@@ -568,6 +590,7 @@ __global__ void kd_mse_bwd_kernel(const float* __restrict__ s, const float* __re
 
 static SGeo make_sgeo(int B, int C, int H, int W, int target) {
   SGeo g;
+  g.z1_sq = nullptr; g.g_z1_sq = nullptr;
   g.B = B; g.C = C; g.H = H; g.W = W; g.HW = H * W;
   g.ipc = g.HW >= target ? 1 : target / g.HW;
   if (g.ipc > B) g.ipc = B;
@@ -631,9 +654,17 @@ using namespace nfk;
 
 extern "C" int nfk_split2d_fwd(const float* x, const float* w, const float* bias, const float* logs, float* z1_out,
                                float* ld, int B, int C, int H, int W, void* stream) {
+  return nfk_split2d_squeeze_fwd(x, w, bias, logs, z1_out, nullptr, ld, B, C, H, W, stream);
+}
+
+extern "C" int nfk_split2d_squeeze_fwd(const float* x, const float* w, const float* bias, const float* logs,
+                                       float* z1_out, float* z1_sq_out, float* ld, int B, int C, int H, int W,
+                                       void* stream) {
   if (B <= 0 || C <= 0 || C % 2 || C > 128 || H * W > 4096) return NFK_ERR_SHAPE;
+  if (z1_sq_out && ((H | W) & 1)) return NFK_ERR_SHAPE;
   if (!x || !w || !bias || !logs || !z1_out) return NFK_ERR_ARG;
   SGeo g = make_sgeo(B, C, H, W, 256);
+  g.z1_sq = z1_sq_out;
   if (int rc = split_fwd_px(x, w, bias, logs, z1_out, nullptr, 0.f, nullptr, ld, g, 0, stream); rc != 1) return rc;
   const int smem = (C * (C / 2) * 9 + 2 * C + 3 * (C / 2) * (g.pixt + 1)) * 4;
   if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(split2d_fwd_kernel), smem)) return rc;
@@ -659,9 +690,18 @@ extern "C" int nfk_split2d_rev(const float* z1, const float* w, const float* bia
 extern "C" int nfk_split2d_bwd(const float* x, const float* w, const float* bias, const float* logs,
                                const float* g_z1, const float* g_ld, float* dx, float* dw, float* dbias,
                                float* dlogs, int B, int C, int H, int W, void* stream) {
+  return nfk_split2d_squeeze_bwd(x, w, bias, logs, g_z1, nullptr, g_ld, dx, dw, dbias, dlogs, B, C, H, W, stream);
+}
+
+extern "C" int nfk_split2d_squeeze_bwd(const float* x, const float* w, const float* bias, const float* logs,
+                                       const float* g_z1, const float* g_z1_sq, const float* g_ld, float* dx,
+                                       float* dw, float* dbias, float* dlogs, int B, int C, int H, int W,
+                                       void* stream) {
   if (B <= 0 || C <= 0 || C % 2 || C > 128 || H * W > 4096) return NFK_ERR_SHAPE;
+  if (g_z1_sq && ((H | W) & 1)) return NFK_ERR_SHAPE;
   if (!x || !w || !bias || !logs || !g_ld || !dx || !dw || !dbias || !dlogs) return NFK_ERR_ARG;
   SGeo g = make_sgeo(B, C, H, W, 128);
+  g.g_z1_sq = g_z1_sq;
   if (int rc = split_bwd_px(x, w, bias, logs, g_z1, g_ld, dx, dw, dbias, dlogs, g, stream); rc != 1) return rc;
   const int smem = (2 * C * (C / 2) * 9 + 2 * C + (C / 2 + C) * (g.pixt + 1) + 2 * C) * 4;
   if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(split2d_bwd_kernel), smem)) return rc;

@@ -411,6 +411,38 @@ class Split2dFn(torch.autograd.Function):
         return dx, g_ld, dw, dbias, dlogs
 
 
+class Split2dSqueezeFn(torch.autograd.Function):
+    """Split2d followed by the next level's SqueezeLayer in ONE kernel each way (layers.py:293-327): returns z1, its
+    space-to-depth copy [B, 4*C/2, H/2, W/2] and the log-det; the backward reads the squeezed tensor's gradient through
+    the same index map (no permute / contiguous pass in either direction)."""
+
+    @staticmethod
+    def forward(ctx, x, ld_in, w, bias, logs):
+        B, C, H, W = x.shape
+        x = x.contiguous()
+        z1 = torch.empty(B, C // 2, H, W, device=x.device, dtype=F32)
+        z1_sq = torch.empty(B, 2 * C, H // 2, W // 2, device=x.device, dtype=F32)
+        ld = ld_in.clone()
+        ops.split2d_fwd(x, w, bias, logs, z1, ld, B, C, H, W, z1_sq=z1_sq)
+        ctx.save_for_backward(x, w, bias, logs)
+        return z1, z1_sq, ld
+
+    @staticmethod
+    def backward(ctx, g_z1, g_sq, g_ld):
+        x, w, bias, logs = ctx.saved_tensors
+        B, C, H, W = x.shape
+        dev = x.device
+        g_ld = torch.zeros(B, device=dev, dtype=F32) if g_ld is None else g_ld.contiguous()
+        g_z1 = None if g_z1 is None else g_z1.contiguous()
+        g_sq = None if g_sq is None else g_sq.contiguous()
+        dx = torch.empty_like(x)
+        nw = w.numel()
+        arena = torch.zeros(nw + 2 * C, device=dev, dtype=F32)
+        dw, dbias, dlogs = arena[:nw].view_as(w), arena[nw:nw + C].view_as(bias), arena[nw + C:].view_as(logs)
+        ops.split2d_bwd(x, w, bias, logs, g_z1, g_ld, dx, dw, dbias, dlogs, B, C, H, W, g_z1_sq=g_sq)
+        return dx, g_ld, dw, dbias, dlogs
+
+
 def split2d_reverse(z1, w, bias, logs, eps, temperature):
     B, CH, H, W = z1.shape
     out = torch.empty(B, 2 * CH, H, W, device=z1.device, dtype=F32)

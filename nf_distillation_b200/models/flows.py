@@ -14,7 +14,8 @@ import torch.nn as nn
 from .. import functional as Fn
 from .layers import (ActNorm1d, ActNorm2d, Conv2d, Conv2dZeros, InvertibleConv1x1, LinearZeros, Permute2d, Split2d,
                      SqueezeLayer, _as_logdet, _require_cuda, gaussian_likelihood, gaussian_sample)
-from .utils import split_feature, uniform_binning_correction
+from .utils import (can_fuse_dequant_squeeze, dequantize_and_squeeze, split_feature,
+                    uniform_binning_correction)
 
 logger = logging.getLogger(__name__)
 
@@ -294,15 +295,40 @@ class FlowNet(nn.Module):
                 self.output_shapes.append([-1, C // 2, H, W])
                 C = C // 2
 
-    def forward(self, input, y_onehot=None, logdet=0.0, reverse=False, temperature=None):
+    def forward(self, input, y_onehot=None, logdet=0.0, reverse=False, temperature=None, _sq0=None):
         if reverse:
             return self.decode(input, y_onehot=y_onehot, temperature=temperature)
-        return self.encode(input, y_onehot=y_onehot, logdet=logdet)
+        return self.encode(input, y_onehot=y_onehot, logdet=logdet, _sq0=_sq0)
 
-    def encode(self, z, y_onehot=None, logdet=0.0):
+    def _encode_layers(self, z, y_onehot, logdet, sq0=None):
+        """Generator over (layer output, logdet) in layer order. Squeezes are folded into their neighbours: the first
+        one arrives precomputed from the dequantisation kernel (`sq0`), a SqueezeLayer(2) after a Split2d is produced
+        by the Split2d kernel itself (layers.py:32-44 as an index map, no permute/contiguous pass)."""
+        layers = self.layers
+        i, n = 0, len(layers)
+        while i < n:
+            layer = layers[i]
+            if i == 0 and sq0 is not None and isinstance(layer, SqueezeLayer) and layer.factor == 2:
+                z = sq0
+                yield z, logdet
+                i += 1
+                continue
+            nxt = layers[i + 1] if i + 1 < n else None
+            if (isinstance(layer, Split2d) and isinstance(nxt, SqueezeLayer) and nxt.factor == 2
+                    and z.shape[2] % 2 == 0 and z.shape[3] % 2 == 0):
+                z1, z, logdet = layer.forward_with_squeeze(z, logdet=logdet)
+                yield z1, logdet
+                yield z, logdet
+                i += 2
+                continue
+            z, logdet = layer(z, y_onehot=y_onehot, logdet=logdet, reverse=False)
+            yield z, logdet
+            i += 1
+
+    def encode(self, z, y_onehot=None, logdet=0.0, _sq0=None):
         with Fn.use_prep(Fn.prepare_steps(self.layers, False)):   # one K0 launch for every trainable step
-            for layer in self.layers:
-                z, logdet = layer(z, y_onehot=y_onehot, logdet=logdet, reverse=False)
+            for z, logdet in self._encode_layers(z, y_onehot, logdet, _sq0):
+                pass
         return z, logdet
 
     def decode(self, z, y_onehot=None, temperature=None):
@@ -395,11 +421,14 @@ class Glow(nn.Module):
 
     def normal_flow(self, x, y_onehot=None):
         _require_cuda(x, "Glow")
+        sq0 = None
         if self.is_1d:
             logdet = torch.zeros(x.shape[0], device=x.device, dtype=torch.float32)
+        elif can_fuse_dequant_squeeze(x):
+            x, logdet, sq0 = dequantize_and_squeeze(x)
         else:
             x, logdet = uniform_binning_correction(x)
-        z, logdet = self.flow(x, y_onehot=y_onehot, logdet=logdet, reverse=False)
+        z, logdet = self.flow(x, y_onehot=y_onehot, logdet=logdet, reverse=False, _sq0=sq0)
         bpd = self._objective(x, z, logdet, y_onehot)
         y_logits = self.project_class(z.mean(2).mean(2)) if self.y_condition else None
         return z, bpd, y_logits

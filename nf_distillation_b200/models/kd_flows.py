@@ -11,7 +11,7 @@ import torch
 from .. import functional as Fn
 from .flows import FlowNet, FlowStep, Glow
 from .layers import Split2d, _require_cuda
-from .utils import uniform_binning_correction
+from .utils import can_fuse_dequant_squeeze, dequantize_and_squeeze, uniform_binning_correction
 
 logger = logging.getLogger(__name__)
 
@@ -19,11 +19,10 @@ logger = logging.getLogger(__name__)
 class FlowNetGetAllOutputs(FlowNet):
     """encode/decode return the list of all layer outputs (kd_flows.py:15-73)."""
 
-    def encode(self, z, y_onehot=None, logdet=0.0):
+    def encode(self, z, y_onehot=None, logdet=0.0, _sq0=None):
         all_outputs = []
         with Fn.use_prep(Fn.prepare_steps(self.layers, False)):   # one K0 launch for every trainable step
-            for layer in self.layers:
-                z, logdet = layer(z, y_onehot=y_onehot, logdet=logdet, reverse=False)
+            for z, logdet in self._encode_layers(z, y_onehot, logdet, _sq0):
                 all_outputs.append(z)
         return all_outputs, logdet
 
@@ -56,16 +55,20 @@ class GlowGetAllOutputs(Glow):
 
     def normal_flow(self, x, y_onehot):
         _require_cuda(x, "GlowGetAllOutputs")
+        sq0 = None
         if self.is_1d:
             logdet = torch.zeros(x.shape[0], device=x.device, dtype=torch.float32)
+        elif can_fuse_dequant_squeeze(x):
+            x, logdet, sq0 = dequantize_and_squeeze(x)     # noise + first squeeze (+ uint8 preprocess): one kernel
         else:
             x, logdet = uniform_binning_correction(x)
-        return self.flow_from_dequantized(x, logdet, y_onehot)
+        return self.flow_from_dequantized(x, logdet, y_onehot, _sq0=sq0)
 
-    def flow_from_dequantized(self, x, logdet, y_onehot=None):
+    def flow_from_dequantized(self, x, logdet, y_onehot=None, _sq0=None):
         """Everything of normal_flow after the (in-place) dequantisation; NFModel uses it to run the teacher and the
-        student concurrently on two streams while keeping the reference's in-place noise semantics."""
-        z, logdet = self.flow(x, y_onehot=y_onehot, logdet=logdet, reverse=False)
+        student concurrently on two streams while keeping the reference's in-place noise semantics. `_sq0`: the first
+        SqueezeLayer's output when the dequantisation kernel already produced it (x is then only read for its shape)."""
+        z, logdet = self.flow(x, y_onehot=y_onehot, logdet=logdet, reverse=False, _sq0=_sq0)
         last_z = z[-1]
         bpd = self._objective(x, last_z, logdet, y_onehot)
         if self.y_condition:
@@ -75,7 +78,7 @@ class GlowGetAllOutputs(Glow):
             y_logits = None
         return z, bpd, y_logits
 
-    def deferred_objective(self, x, logdet, y_onehot=None):
+    def deferred_objective(self, x, logdet, y_onehot=None, _sq0=None):
         """flow_from_dequantized WITHOUT the prior / bits-per-dim reduction: returns (z list, logdet [B],
         (mean_row, logs_row), nll_scale) so that NFModel.loss can fold the objective (kd_flows.py:134-150) into its
         single fused loss kernel (functional.KdNllLossFn); None when the prior is not a batch-independent row
@@ -83,7 +86,7 @@ class GlowGetAllOutputs(Glow):
         rows = self._prior_rows()
         if rows is None:
             return None
-        z, logdet = self.flow(x, y_onehot=y_onehot, logdet=logdet, reverse=False)
+        z, logdet = self.flow(x, y_onehot=y_onehot, logdet=logdet, reverse=False, _sq0=_sq0)
         scale = 1.0 if self.is_1d else 1.0 / (math.log(2.0) * x.shape[1] * x.shape[2] * x.shape[3])
         return z, logdet, rows, scale
 

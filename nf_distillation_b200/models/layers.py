@@ -272,6 +272,20 @@ class Split2d(nn.Module):
             return Fn.Split2dFn.apply(input, ld, w, b, l)
 
 
+    def forward_with_squeeze(self, input, logdet=0.0):
+        """Forward of this Split2d AND of the SqueezeLayer(2) that follows it in FlowNet, one kernel:
+        returns (z1, squeeze2d(z1, 2), logdet)."""
+        _require_cuda(input, "Split2d")
+        w, b, l = self._params()
+        ld = _as_logdet(logdet, input.shape[0], input.device)
+        if ld is None:
+            ld = torch.zeros(input.shape[0], device=input.device)
+        if torch.is_grad_enabled() and (input.requires_grad or w.requires_grad):
+            return Fn.Split2dSqueezeFn.apply(input, ld, w, b, l)
+        with torch.no_grad():
+            return Fn.Split2dSqueezeFn.apply(input, ld, w, b, l)
+
+
 class SqueezeLayer(nn.Module):
     def __init__(self, factor):
         super().__init__()

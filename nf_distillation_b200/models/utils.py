@@ -37,6 +37,27 @@ def uniform_binning_correction(x: torch.Tensor, n_bits: int = 8):
     return x, objective
 
 
+def can_fuse_dequant_squeeze(x: torch.Tensor) -> bool:
+    return (x.is_cuda and x.dim() == 4 and x.shape[3] % 4 == 0 and x.shape[2] % 2 == 0 and x.is_contiguous()
+            and x.dtype in (torch.float32, torch.uint8))
+
+
+def dequantize_and_squeeze(x: torch.Tensor, n_bits: int = 8):
+    """uniform_binning_correction (models/utils.py:26-41) + the first SqueezeLayer (models/layers.py:32-44) — and, when the
+    batch arrives as raw uint8 pixels, preprocess (data/src/utils.py:7-18) — in ONE kernel (csrc/preproc.cu).
+    Returns (x, objective, squeezed): for a float batch `x` is the caller's tensor with the noise added IN PLACE (the
+    reference's semantics: a second call noises it again); for a uint8 batch it is a new fp32 tensor."""
+    from .. import ops
+    b, c, h, w = x.shape
+    n_bins = 2 ** n_bits
+    ref = x if x.dtype == torch.float32 else torch.empty(x.shape, device=x.device, dtype=torch.float32)
+    noise = dequant_noise(ref, n_bins).contiguous()
+    sq = torch.empty(b, 4 * c, h // 2, w // 2, device=x.device, dtype=torch.float32)
+    ops.dequant_squeeze(x, noise, ref, sq, n_bits)
+    objective = torch.full((b,), -math.log(n_bins) * c * h * w, device=x.device, dtype=torch.float32)
+    return ref, objective, sq
+
+
 def split_feature(tensor: torch.Tensor, type: str = "split"):
     """'split': first / second half of the channels; 'cross': even / odd channels (reference: models/utils.py:44-52)."""
     C = tensor.size(1)

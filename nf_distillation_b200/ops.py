@@ -198,10 +198,19 @@ def affine1x1_bwd(dy, dcol, K1p, x, Wf, dx, dWf, dbf, B, C, H, W):
           "nfk_affine1x1_bwd")
 
 
-def split2d_fwd(x, w, bias, logs, z1_out, ld, B, C, H, W):
+def split2d_fwd(x, w, bias, logs, z1_out, ld, B, C, H, W, z1_sq=None):
+    """z1_sq (optional): the squeezed copy of z1 written in the same pass (the next level's input)."""
     _count()
-    check(LIB.nfk_split2d_fwd(_p(x), _p(w), _p(bias), _p(logs), _p(z1_out), _p(ld), B, C, H, W, _st()),
-          "nfk_split2d_fwd")
+    check(LIB.nfk_split2d_squeeze_fwd(_p(x), _p(w), _p(bias), _p(logs), _p(z1_out), _p(z1_sq), _p(ld), B, C, H, W,
+                                      _st()), "nfk_split2d_squeeze_fwd")
+
+
+def dequant_squeeze(src, noise, x_out, sq_out, n_bits=8):
+    """preprocess (uint8 src) + dequantisation noise + first squeeze in one pass (csrc/preproc.cu)."""
+    _count()
+    B, C, H, W = src.shape
+    check(LIB.nfk_dequant_squeeze(_p(src), int(src.dtype == torch.uint8), n_bits, _p(noise), _p(x_out), _p(sq_out),
+                                  B, C, H, W, _st()), "nfk_dequant_squeeze")
 
 
 def split2d_rev(z1, w, bias, logs, eps, temperature, out, B, C, H, W):
@@ -210,10 +219,10 @@ def split2d_rev(z1, w, bias, logs, eps, temperature, out, B, C, H, W):
                               _st()), "nfk_split2d_rev")
 
 
-def split2d_bwd(x, w, bias, logs, g_z1, g_ld, dx, dw, dbias, dlogs, B, C, H, W):
+def split2d_bwd(x, w, bias, logs, g_z1, g_ld, dx, dw, dbias, dlogs, B, C, H, W, g_z1_sq=None):
     _count()
-    check(LIB.nfk_split2d_bwd(_p(x), _p(w), _p(bias), _p(logs), _p(g_z1), _p(g_ld), _p(dx), _p(dw), _p(dbias),
-                              _p(dlogs), B, C, H, W, _st()), "nfk_split2d_bwd")
+    check(LIB.nfk_split2d_squeeze_bwd(_p(x), _p(w), _p(bias), _p(logs), _p(g_z1), _p(g_z1_sq), _p(g_ld), _p(dx),
+                                      _p(dw), _p(dbias), _p(dlogs), B, C, H, W, _st()), "nfk_split2d_squeeze_bwd")
 
 
 def prior_bpd_fwd(z, mean, logs, logdet, B, n, scale, out):

@@ -114,21 +114,28 @@ class NFModel(nn.Module):
         cond = y if self.params["student"]["y_condition"] else None
         teacher_z = None
         objective = None
+        two_streams = (self.kd_weight > 0 and self.concurrent_teacher and x.is_cuda
+                       and not self.params["student"]["is_1d"] and not self.params["teacher"]["is_1d"])
+        if x.dtype == torch.uint8 and not two_streams:
+            # raw pixels on the sequential path: preprocess once (data/src/utils.py:7-18) so that student and teacher
+            # share one fp32 batch and the noise accumulates in it like in the reference
+            from . import ops
+            xf = torch.empty(x.shape, device=x.device, dtype=torch.float32)
+            ops.dequant_squeeze(x.contiguous(), None, xf, None)
+            x = xf
         defer = _defer_objective and hasattr(self.student, "deferred_objective") \
             and self.student._prior_rows() is not None
-        if (self.kd_weight > 0 and self.concurrent_teacher and x.is_cuda and not self.params["student"]["is_1d"]
-                and not self.params["teacher"]["is_1d"]):
+        if two_streams:
             student_z, student_nll, teacher_z = self._forward_two_streams(x, cond, defer)
             if defer:
                 objective, student_nll = student_nll, None
         else:
             if defer:
                 if self.params["student"]["is_1d"]:
-                    ld0 = torch.zeros(x.shape[0], device=x.device, dtype=torch.float32)
+                    ld0, sq0 = torch.zeros(x.shape[0], device=x.device, dtype=torch.float32), None
                 else:
-                    from .models.utils import uniform_binning_correction
-                    x, ld0 = uniform_binning_correction(x)
-                student_z, ld, rows, scale = self.student.deferred_objective(x, ld0, cond)
+                    x, ld0, sq0 = self._dequantize(x)
+                student_z, ld, rows, scale = self.student.deferred_objective(x, ld0, cond, _sq0=sq0)
                 objective, student_nll = (ld, rows, scale), None
             else:
                 student_z, student_nll, _ = self.student(x, cond)
@@ -145,25 +152,37 @@ class NFModel(nn.Module):
         return {"student_nll": student_nll, "student_z": student_z, "teacher_z": teacher_z,
                 "student_x": student_x, "teacher_x": teacher_x, "weights": weights, "student_objective": objective}
 
+    @staticmethod
+    def _dequantize(x):
+        """(x with the dequantisation noise added in place, constant log-det, first SqueezeLayer's output or None):
+        one fused kernel when the batch layout allows it (also takes raw uint8 pixels), else the reference's
+        uniform_binning_correction followed by the model's own squeeze."""
+        from .models.utils import can_fuse_dequant_squeeze, dequantize_and_squeeze, uniform_binning_correction
+        if can_fuse_dequant_squeeze(x):
+            return dequantize_and_squeeze(x)
+        x, ld = uniform_binning_correction(x)
+        return x, ld, None
+
     def _forward_two_streams(self, x, cond, defer=False):
         """Same arithmetic and in-place side effects as the sequential code above (student noise, then teacher noise
         on top, both added to the caller's batch), but the frozen teacher runs on a second stream: its many small
-        level-2/3 kernels fill the SMs the student leaves idle. Captured CUDA graphs keep the fork/join."""
-        from .models.utils import uniform_binning_correction
+        level-2/3 kernels fill the SMs the student leaves idle. Captured CUDA graphs keep the fork/join. The
+        dequantisation kernel hands each model its own squeezed copy of the noised batch, so the teacher's second,
+        in-place noise draw cannot disturb the student (no clone of the batch)."""
         main = torch.cuda.current_stream()
         if self._side is None:
             self._side = torch.cuda.Stream()
-        x, ld_s = uniform_binning_correction(x)            # student's dequantisation noise, in place
-        xs = x.clone()                                     # the student's view of the input
+        x, ld_s, sq_s = self._dequantize(x)                # student's dequantisation noise, in place
+        xs = x if sq_s is not None else x.clone()          # (unfused layout: the student needs its own view of x)
         self._side.wait_stream(main)
         with torch.cuda.stream(self._side), torch.no_grad():
-            xt, ld_t = uniform_binning_correction(x)       # teacher's noise on top, in place (reference semantics)
-            teacher_z, _, _ = self.teacher.flow_from_dequantized(xt, ld_t, cond)
+            xt, ld_t, sq_t = self._dequantize(x)           # teacher's noise on top, in place (reference semantics)
+            teacher_z, _, _ = self.teacher.flow_from_dequantized(xt, ld_t, cond, _sq0=sq_t)
         if defer:
-            student_z, ld, rows, scale = self.student.deferred_objective(xs, ld_s, cond)
+            student_z, ld, rows, scale = self.student.deferred_objective(xs, ld_s, cond, _sq0=sq_s)
             student_nll = (ld, rows, scale)
         else:
-            student_z, student_nll, _ = self.student.flow_from_dequantized(xs, ld_s, cond)
+            student_z, student_nll, _ = self.student.flow_from_dequantized(xs, ld_s, cond, _sq0=sq_s)
         main.wait_stream(self._side)
         for i in self.teacher_kd_indices:
             teacher_z[i].record_stream(main)

@@ -120,7 +120,9 @@ class KDTrainer:
     """Owns the NFModel, its optimiser, the static device buffers and the captured graphs."""
 
     def __init__(self, config: dict, batch_shape: tp.Sequence[int], device: torch.device, use_graphs: bool = True,
-                 seed: int = 42):
+                 seed: int = 42, input_dtype: torch.dtype = torch.float32):
+        """input_dtype=torch.uint8: image batches arrive as raw pixels (a quarter of the host-to-device bytes); the
+        first kernel of the step does the reference's preprocess together with the noise and the first squeeze."""
         self.device = device
         self.world = dist.get_world_size() if dist.is_initialized() else 1
         torch.manual_seed(seed)                       # identical initial weights on every rank (train.py:41)
@@ -137,7 +139,7 @@ class KDTrainer:
         # them instead of launching one "+=" kernel per parameter
         self.opt = FlatAdam(params, lr=config["learning_rate"], weight_decay=config["weight_decay"],
                             kind=config["optimizer"])
-        self.x = torch.zeros(*batch_shape, device=device)          # static input buffer
+        self.x = torch.zeros(*batch_shape, device=device, dtype=input_dtype)          # static input buffer
         self.losses = torch.zeros(4, device=device)                 # nll, kd, perceptual, loss
         self.use_graphs = use_graphs
         self.g_fb: tp.Optional[torch.cuda.CUDAGraph] = None

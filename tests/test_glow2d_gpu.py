@@ -264,3 +264,48 @@ def test_additive_coupling_and_fixed_permutations_golden(name, patched_noise):
     # (3 samples of 16x16: fewer terms average the bf16 rounding of the weight-gradient GEMMs than in the 32x32 KD
     # fixture above, so the worst tensor is allowed 0.25 of its max instead of 0.15; the median bound is the same)
     assert errs and errs[len(errs) // 2] < 1e-2 and errs[-1] < 0.25, (errs[len(errs) // 2], errs[-1])
+
+
+def test_raw_uint8_batches_and_folded_squeezes_match_the_float_path(patched_noise):
+    """csrc/preproc.cu + the squeeze folded into Split2d: (a) the fused dequantisation kernel on an fp32 batch is
+    bit-identical to `x += noise` followed by squeeze2d (and mutates the caller's batch like the reference); (b) a raw
+    uint8 batch gives the outputs of preprocess (data/src/utils.py:7-18) on the float path; (c) Split2d's squeezed
+    second output equals squeeze2d of its first, forward and backward."""
+    from nf_distillation_b200 import functional as Fn
+    from nf_distillation_b200.models.layers import squeeze2d
+    from nf_distillation_b200.models.utils import dequantize_and_squeeze
+    d, cfg, m = build("glow2d_cifar_k2_h64")
+    g = torch.Generator().manual_seed(1)
+    u8 = torch.randint(0, 256, (4, 3, 32, 32), generator=g, dtype=torch.uint8)
+    xf = (u8.float() / 255 * 255) / 256 - 0.5                 # ToTensor + the reference's preprocess
+    noise = (torch.rand(4, 3, 32, 32, generator=g) / 256).to(dev)
+    patched_noise["q"] = [noise]
+    x1 = xf.clone().to(dev)
+    xo, obj, sq = dequantize_and_squeeze(x1)
+    assert xo.data_ptr() == x1.data_ptr() and torch.equal(x1, xf.to(dev) + noise)
+    assert torch.equal(sq, squeeze2d(xf.to(dev) + noise, 2)) and obj.shape == (4,)
+    patched_noise["q"] = [noise, noise]
+    with torch.no_grad():
+        o_f, bpd_f, _ = m(xf.clone().to(dev), None)
+        o_u, bpd_u, _ = m(u8.to(dev), None)
+    assert (bpd_u - bpd_f).abs().max().item() < 1e-5 * bpd_f.abs().max().item()
+    for a, b in zip(o_u, o_f):
+        assert rel(a, b) < 1e-5
+    # Split2d + squeeze: forward values and gradients of both outputs against the unfused composition
+    x = torch.randn(6, 12, 16, 16, device=dev, generator=torch.Generator(device=dev).manual_seed(3))
+    lay = m.flow.layers[3]                                     # the first Split2d (C = 12)
+    w = [p.detach().clone().requires_grad_(True) for p in lay._params()]
+    xa = x.clone().requires_grad_(True)
+    ld0 = torch.zeros(6, device=dev)
+    z1, z1s, ld = Fn.Split2dSqueezeFn.apply(xa, ld0, *w)
+    g1, g2 = torch.randn_like(z1), torch.randn_like(z1s)
+    ((z1 * g1).sum() + (z1s * g2).sum() + ld.sum()).backward()
+    w2 = [p.detach().clone().requires_grad_(True) for p in lay._params()]
+    xb = x.clone().requires_grad_(True)
+    r1, rld = Fn.Split2dFn.apply(xb, ld0, *w2)
+    r1s = squeeze2d(r1, 2)
+    ((r1 * g1).sum() + (r1s * g2).sum() + rld.sum()).backward()
+    assert torch.equal(z1, r1) and torch.equal(z1s, r1s) and rel(ld, rld) < 1e-6
+    assert rel(xa.grad, xb.grad) < 1e-5
+    for a, b in zip(w, w2):
+        assert rel(a.grad, b.grad) < 1e-4

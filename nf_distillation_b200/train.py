@@ -189,17 +189,34 @@ class KDTrainer:
         torch.cuda.synchronize()
         if not self.use_graphs:
             return
-        self.g_fb = torch.cuda.CUDAGraph()
-        if self.world == 1:      # no collective between the halves: the whole step is ONE graph
-            with torch.cuda.graph(self.g_fb):
-                self._forward_backward()
-                self._clip_and_update()
-        else:
+        # One rank: the whole step (forward, backward, clip + optimiser) is ONE graph. Several ranks: two graphs with
+        # the NCCL all-reduce launched eagerly in between (the configuration measured at 2 and 8 GPUs).
+        # NFK_GRAPH_NCCL=1 captures the collective inside a single graph instead — EXPERIMENTAL and off by default: the
+        # one 2-GPU attempt made with it in round 2 did not finish inside its time limit and was not investigated.
+        one_graph = self.world == 1 or os.environ.get("NFK_GRAPH_NCCL", "0") == "1"
+        if one_graph:
+            try:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._forward_backward()
+                    self._allreduce()
+                    self._clip_and_update()
+                self.g_fb, self.g_opt = g, None
+            except Exception as e:   # noqa: BLE001  (capture of the collective not supported by this stack)
+                if self.world == 1:
+                    raise
+                import warnings
+                warnings.warn(f"single-graph capture with the NCCL all-reduce failed ({e}); using two graphs")
+                torch.cuda.synchronize()
+                one_graph = False
+        if not one_graph:
+            self.g_fb = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.g_fb):
                 self._forward_backward()
             self.g_opt = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.g_opt, pool=self.g_fb.pool()):
                 self._clip_and_update()
+        self.one_graph = one_graph
         torch.cuda.synchronize()
 
     def step_device(self):

@@ -283,6 +283,12 @@ int nfk_cnet_set_prof(void* buf); /* diagnostics: per-CTA cycle counters of the 
 int nfk_cnet_fwd_fused(const void* col, int K1p, const void* B1, const void* B2, const float* bias1,
                        const float* bias2, void* h1, void* h2, void* mask1, void* mask2, long long ldmask, int M,
                        int hid, void* stream);
+/* Same kernel for MADE's masked linears: the second weight matrix is block lower triangular (degree-sorted hidden
+ * units), so for output channels [0, 256) only its first kb2_end_half0 k-blocks of 64 input channels are non-zero;
+ * the remaining B2 tiles of that half are neither loaded nor multiplied (1 <= kb2_end_half0 <= 8; 8 = dense). */
+int nfk_cnet_fwd_fused_ranged(const void* col, int K1p, const void* B1, const void* B2, const float* bias1,
+                              const float* bias2, void* h1, void* h2, void* mask1, void* mask2, long long ldmask,
+                              int M, int hid, int kb2_end_half0, void* stream);
 
 /* ---- the tail of the KD training step (csrc/loss_optim.cu) -------------------------------------------------------
  * NFModel.loss (pl_module.py:257-320) in ONE launch: per sample

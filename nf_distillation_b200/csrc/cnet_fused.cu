@@ -39,6 +39,10 @@ struct CnetArgs {
   long long ldmask;
   int store_h1;
   long long* prof;   // diagnostics: [grid][8] cycle counters of the MMA issuer
+  // conv#2 k-blocks (64 input channels each) that are not structurally zero for output half 0 / 1; 8 = all. MADE's
+  // degree-sorted hidden mask is block lower triangular: the low-degree half of the outputs never sees the high-degree
+  // inputs, so those B2 tiles are neither loaded nor multiplied (they are exact zeros: the result is bit-identical).
+  int kb2_end[2];
 };
 
 struct CnetSmem {
@@ -105,7 +109,7 @@ cnet_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmCol, const __grid_co
             load(&tmB1, kb * 64, h * 256 + static_cast<int>(rank) * 128);
           }
         for (int h = 0; h < 2; ++h)
-          for (int kb = 0; kb < 8; ++kb) load(&tmB2, kb * 64, h * 256 + static_cast<int>(rank) * 128);
+          for (int kb = 0; kb < g.kb2_end[h]; ++kb) load(&tmB2, kb * 64, h * 256 + static_cast<int>(rank) * 128);
       }
     }
   } else if (warp == 1) {
@@ -157,14 +161,16 @@ cnet_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmCol, const __grid_co
         }
         // ---- conv#2: A = the h1 panels the epilogue warps just wrote (both CTAs), B2 streamed
         //      k-block kb only needs h1 panel kb, so conv#2 starts as soon as the first panels have been written
+        int panels_seen = 0;      // h1 panels of this tile already waited for
         for (int h = 0; h < 2; ++h) {
           const uint32_t d = acc_begin();
-          for (int kb = 0; kb < 8; ++kb) {
-            if (h == 0) {
+          for (int kb = 0; kb < g.kb2_end[h]; ++kb) {
+            if (kb >= panels_seen) {
               const long long c0 = g.prof ? clock64() : 0;
               mbar_wait(&h1_full[kb], tile_ph);
               if (g.prof) w_h1 += clock64() - c0;
               tc_fence_after();
+              panels_seen = kb + 1;
             }
             const uint32_t b = take();
 #pragma unroll
@@ -364,11 +370,18 @@ extern "C" int nfk_cnet_set_prof(void* buf) {
 extern "C" int nfk_cnet_fwd_fused(const void* col, int K1p, const void* B1, const void* B2, const float* bias1,
                                   const float* bias2, void* h1, void* h2, void* mask1, void* mask2,
                                   long long ldmask, int M, int hid, void* stream) {
+  return nfk_cnet_fwd_fused_ranged(col, K1p, B1, B2, bias1, bias2, h1, h2, mask1, mask2, ldmask, M, hid, 8, stream);
+}
+
+extern "C" int nfk_cnet_fwd_fused_ranged(const void* col, int K1p, const void* B1, const void* B2, const float* bias1,
+                                         const float* bias2, void* h1, void* h2, void* mask1, void* mask2,
+                                         long long ldmask, int M, int hid, int kb2_end_half0, void* stream) {
   if (M <= 0 || hid != CF_HID || K1p % 64 || K1p < 64 || K1p > 512) return NFK_ERR_SHAPE;
+  if (kb2_end_half0 < 1 || kb2_end_half0 > 8) return NFK_ERR_ARG;
   if (!col || !B1 || !B2 || !bias1 || !bias2 || !h2) return NFK_ERR_ARG;
   if ((mask1 || mask2) && ldmask < M) return NFK_ERR_ARG;
   CnetArgs g{M, K1p / 64, bias1, bias2, static_cast<uint32_t*>(mask1), static_cast<uint32_t*>(mask2), ldmask,
-             h1 ? 1 : 0, g_cnet_prof};
+             h1 ? 1 : 0, g_cnet_prof, {kb2_end_half0, 8}};
   CUtensorMap tmCol, tmB1, tmB2, tmH1, tmH2;
   int rc;
   if ((rc = cf_tmap(&tmCol, col, K1p, M, K1p, 128, false))) return rc;

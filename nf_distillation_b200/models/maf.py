@@ -144,13 +144,20 @@ class MADE(nn.Module):
         key = (self.deg1.data_ptr(), self.deg1._version, self.deg2.data_ptr(), self.deg2._version)
         if self._range_cache is None or self._range_cache[0] != key:
             d1, d2 = self.deg1.detach().cpu().long(), self.deg2.detach().cpu().long()
+            nkb = self.H // 64
             if bool((d1[1:] >= d1[:-1]).all() and (d2[1:] >= d2[:-1]).all()):
                 r, rt = _kb_ranges(d2, d1, self.bn), _kb_ranges_t(d2, d1, self.bn)
+                half0 = _kb_ranges(d2, d1, 256)[1][0] if self.H == 512 else nkb   # fused kernel: outputs [0, 256)
             else:
-                nt, nkb = (self.H + self.bn - 1) // self.bn, self.H // 64
+                nt = (self.H + self.bn - 1) // self.bn
                 r = rt = ([0] * nt, [nkb] * nt)
-            self._range_cache = (key, (r, rt))
+                half0 = nkb
+            self._range_cache = (key, (r, rt, half0))
         return self._range_cache[1]
+
+    @property
+    def _fused_kb_end_half0(self):
+        return self._kb_ranges_now()[2]
 
     @property
     def _ranges(self):
@@ -220,7 +227,10 @@ class MADE(nn.Module):
             # memory as the second GEMM's A operand and is only written out when training). The masks are zeros in the
             # bf16 weights here; skipping their k-blocks would save < what the h1 round trip through HBM costs.
             h1 = torch.empty(Bn, H, device=dev, dtype=BF16) if keep else None
-            ops.cnet_fwd_fused(xb, Dp, B1, B2, b1, b2, h2, Bn, H, h1=h1, mask1=m1, mask2=m2)
+            # k-blocks of the hidden weight that output channels [0, 256) can see (block-triangular mask): the rest
+            # are exact zeros in B2 and are skipped
+            ops.cnet_fwd_fused(xb, Dp, B1, B2, b1, b2, h2, Bn, H, h1=h1, mask1=m1, mask2=m2,
+                               kb2_end_half0=self._fused_kb_end_half0)
         else:
             h1 = torch.empty(Bn, H, device=dev, dtype=BF16)
             ops.gemm_nt(xb, B1, Bn, H, Dp, ops.EPI_BIAS_RELU_BF16, h1, bias=b1, aux=m1)

@@ -393,12 +393,14 @@ def cnet_fused_supported(hid, K1p) -> bool:
     return hid == 512 and K1p % 64 == 0 and 64 <= K1p <= 512
 
 
-def cnet_fwd_fused(col, K1p, B1, B2, bias1, bias2, h2, M, hid, h1=None, mask1=None, mask2=None):
-    """conv3x3 -> ReLU -> conv1x1 -> ReLU in one kernel: h1 never leaves the SM (training also stores it + masks)."""
+def cnet_fwd_fused(col, K1p, B1, B2, bias1, bias2, h2, M, hid, h1=None, mask1=None, mask2=None, kb2_end_half0=8):
+    """conv3x3 -> ReLU -> conv1x1 -> ReLU in one kernel: h1 never leaves the SM (training also stores it + masks).
+    kb2_end_half0 < 8: the k-blocks of B2 beyond it are structurally zero for output channels [0, 256) and are skipped
+    (MADE's block-triangular hidden mask)."""
     _count()
     ldm = 0 if mask1 is None else mask1.stride(0)
-    check(LIB.nfk_cnet_fwd_fused(_p(col), K1p, _p(B1), _p(B2), _p(bias1), _p(bias2), _p(h1), _p(h2), _p(mask1),
-                                 _p(mask2), ldm, M, hid, _st()), "nfk_cnet_fwd_fused")
+    check(LIB.nfk_cnet_fwd_fused_ranged(_p(col), K1p, _p(B1), _p(B2), _p(bias1), _p(bias2), _p(h1), _p(h2), _p(mask1),
+                                        _p(mask2), ldm, M, hid, int(kb2_end_half0), _st()), "nfk_cnet_fwd_fused_ranged")
 
 
 def _loss_levels(s_list, t_list, ds_list=None):

@@ -271,3 +271,24 @@ def test_resident_inverse_planner_error_codes():
     assert L.nfk_made_inverse_resident(None, None, None, None, None, None, 1, 0, N3p, None, None, None, 4, D, H, Dp,
                                        1, 0, None) == -3
     assert L.nfk_made_inverse_pack(None, 1, None, None, None, N3p, D, H, Dp, 0, None, None) == -3
+
+
+def test_reference_arm_of_the_bench_never_loads_the_product():
+    """`bench.py --impl reference` times the reference's CPU algorithm (oracle port) with weights from the oracle's own
+    seeded initialiser and must not touch the product: bench.py asserts, after the run, that no nf_distillation_b200
+    module was imported into the process (so libnfk.so cannot have been mapped). Here: the arm runs, exits 0 (the
+    assertion held) and prints one JSON line with the contract's keys."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, "bench.py")).read()
+    assert 'assert not any(m.startswith("nf_distillation_b200") for m in sys.modules)' in src
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--workload", "glow1d_bsds300_kd_t5_s3"], capture_output=True, text=True, timeout=300,
+                         cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["cpu_baseline"]["kind"] == "port" and line["value"] > 0
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["dtype"] == "f32"

@@ -63,6 +63,7 @@ cnet_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmCol, const __grid_co
                       const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmH1,
                       const __grid_constant__ CUtensorMap tmH2, const CnetArgs g) {
   extern __shared__ __align__(1024) uint8_t smem[];
+  pdl_launch_dependents();
   if (smem_u32(smem) & 1023u) __trap();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -90,6 +91,7 @@ cnet_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmCol, const __grid_co
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();      // the prologue above overlapped the previous kernel's tail; global memory only from here on
 
   if (warp == 0) {
     // ===================================================== TMA producer (both CTAs; bytes land on the leader's barrier)
@@ -396,7 +398,7 @@ extern "C" int nfk_cnet_fwd_fused_ranged(const void* col, int K1p, const void* B
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int tiles = (M + 255) / 256;
   const int pairs = tiles < sms / 2 ? tiles : sms / 2;
-  cnet_fwd_fused_kernel<<<2 * pairs, CF_THREADS, CnetSmem::total, static_cast<cudaStream_t>(stream)>>>(
-      tmCol, tmB1, tmB2, tmH1, tmH2, g);
-  return cudaGetLastError() == cudaSuccess ? NFK_OK : NFK_ERR_LAUNCH;
+  const cudaError_t le = launch_pdl(cnet_fwd_fused_kernel, dim3(2 * pairs), dim3(CF_THREADS), CnetSmem::total,
+                                    static_cast<cudaStream_t>(stream), tmCol, tmB1, tmB2, tmH1, tmH2, g);
+  return (le == cudaSuccess && cudaGetLastError() == cudaSuccess) ? NFK_OK : NFK_ERR_LAUNCH;
 }

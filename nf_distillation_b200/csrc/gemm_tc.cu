@@ -153,6 +153,7 @@ template <int EPI, bool PAIR>
 __device__ __forceinline__ void gemm_nt_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
                                              const GemmArgs& g) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
+  pdl_launch_dependents();
   uint8_t* smem = smem_raw;   // 1024-byte aligned (no static shared memory in this kernel): SWIZZLE_128B requirement
   if (smem_u32(smem) & 1023u) __trap();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -198,6 +199,7 @@ __device__ __forceinline__ void gemm_nt_body(const CUtensorMap& tmA, const CUten
   if constexpr (PAIR) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();      // prologue overlapped the previous kernel's tail; global memory only from here on
 
   if (warp == 0) {
     if (lane == 0) {
@@ -458,6 +460,7 @@ gemm_nt_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 __global__ void __launch_bounds__(TN_THREADS, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
+  pdl_launch_dependents();
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int BOX = 64 * 128;  // one TMA box: 64 pixel rows x 64 channels (128 B)
@@ -496,6 +499,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -738,10 +742,12 @@ static int gemm_nt_launch(const void* A, long long lda, const void* B, long long
 #define NFK_LAUNCH_NT(E)                                                                     \
   if (pair) {                                                                                \
     if ((rc = set_smem(gemm_nt_pair_kernel<E>, smem))) return rc;                            \
-    gemm_nt_pair_kernel<E><<<grid, GEMM_THREADS, smem, st>>>(tmA, tmB, tmC, g);              \
+    if (launch_pdl(gemm_nt_pair_kernel<E>, grid, dim3(GEMM_THREADS), smem, st, tmA, tmB, tmC, g) != cudaSuccess) \
+      return NFK_ERR_LAUNCH;                                                                  \
   } else {                                                                                   \
     if ((rc = set_smem(gemm_nt_kernel<E>, smem))) return rc;                                 \
-    gemm_nt_kernel<E><<<grid, GEMM_THREADS, smem, st>>>(tmA, tmB, tmC, g);                   \
+    if (launch_pdl(gemm_nt_kernel<E>, grid, dim3(GEMM_THREADS), smem, st, tmA, tmB, tmC, g) != cudaSuccess) \
+      return NFK_ERR_LAUNCH;                                                                  \
   }
   switch (epi) {
     case NFK_EPI_F32: NFK_LAUNCH_NT(NFK_EPI_F32); break;
@@ -778,6 +784,6 @@ extern "C" int nfk_gemm_tn_bf16(const void* A, long long lda, const void* B, lon
   const int smem = g.stages * stage_bytes + 1024 + 256;
   if ((rc = set_smem(gemm_tn_kernel, smem))) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  gemm_tn_kernel<<<dim3(tiles, splits), TN_THREADS, smem, st>>>(tmA, tmB, g);
-  return cudaGetLastError() == cudaSuccess ? NFK_OK : NFK_ERR_LAUNCH;
+  const cudaError_t le = launch_pdl(gemm_tn_kernel, dim3(tiles, splits), dim3(TN_THREADS), smem, st, tmA, tmB, g);
+  return (le == cudaSuccess && cudaGetLastError() == cudaSuccess) ? NFK_OK : NFK_ERR_LAUNCH;
 }

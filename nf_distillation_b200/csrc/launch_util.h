@@ -2,6 +2,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include <mutex>
 #include <unordered_map>
 
@@ -23,6 +25,33 @@ inline int ensure_dyn_smem(const void* kernel, int bytes) {
     return NFK_ERR_LAUNCH;
   done[kernel] = true;
   return NFK_OK;
+}
+
+// Launch with programmatic dependent launch allowed (see ptx.cuh: pdl_wait / pdl_launch_dependents). NFK_PDL=0 in the
+// environment turns the attribute off (the kernels' griddepcontrol instructions are then no-ops).
+inline bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("NFK_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
 }  // namespace nfk

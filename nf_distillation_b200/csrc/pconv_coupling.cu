@@ -80,6 +80,7 @@ pconv_coupling_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
   constexpr int K3 = 9 * C, J = C / 2;
   constexpr int ACC_COLS = MB * NPIX;   // TMEM columns of one accumulator stage
   extern __shared__ __align__(1024) uint8_t smem[];
+  pdl_launch_dependents();
   if (smem_u32(smem) & 1023u) __trap();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* S = reinterpret_cast<float*>(smem + Sm::off_s);
@@ -89,7 +90,6 @@ pconv_coupling_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
   uint64_t* tmem_empty = tmem_full + 2;      // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   float* bias_s = reinterpret_cast<float*>(smem + Sm::off_bias);
-  if (threadIdx.x < C) bias_s[threadIdx.x] = g.bias3[threadIdx.x];
 
   const int num_tiles = g.banded ? g.B * g.nb : static_cast<int>((g.M + NPIX - 1) / NPIX);
   if (warp == 0 && lane == 0) {
@@ -100,6 +100,8 @@ pconv_coupling_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
     fence_mbar_init();
   }
   if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  pdl_wait();      // barrier init / TMEM allocation above overlap the previous kernel's tail
+  if (threadIdx.x < C) bias_s[threadIdx.x] = g.bias3[threadIdx.x];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -323,8 +325,9 @@ static int pc_launch(const void* h2, const void* B3, int K3p, const PcArgs& g, i
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int tiles = g.banded ? g.B * g.nb : static_cast<int>((g.M + Cfg::NPIX - 1) / Cfg::NPIX);
-  pconv_coupling_kernel<C><<<tiles < sms ? tiles : sms, PC_THREADS, PcSmem<C>::total, st>>>(tmW, tmH, g);
-  return cudaGetLastError() == cudaSuccess ? NFK_OK : NFK_ERR_LAUNCH;
+  const cudaError_t le = launch_pdl(pconv_coupling_kernel<C>, dim3(tiles < sms ? tiles : sms), dim3(PC_THREADS),
+                                    PcSmem<C>::total, st, tmW, tmH, g);
+  return (le == cudaSuccess && cudaGetLastError() == cudaSuccess) ? NFK_OK : NFK_ERR_LAUNCH;
 }
 
 }  // namespace nfk

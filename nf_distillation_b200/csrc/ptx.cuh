@@ -20,6 +20,17 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch (PDL)
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its predecessor in the
+// stream is still draining. pdl_launch_dependents(): let MY successor do the same (issued first thing, so that the
+// successor's CTAs take over SMs as mine retire); pdl_wait(): block until the predecessor grid has completed and its
+// writes are visible — everything before it (barrier init, TMEM allocation, tensor-map prefetch, smem carve-up) overlaps
+// the predecessor's tail wave, everything that touches global memory comes after it. Every kernel launched with the
+// attribute executes pdl_wait() on all control paths that do work: a grid that never waited could complete before its
+// predecessor and break the chain for ITS successor. Both are no-ops when the launch did not carry the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

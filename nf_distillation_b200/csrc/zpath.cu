@@ -13,6 +13,7 @@
 
 #include "../../include/nfk.h"
 #include "launch_util.h"
+#include "ptx.cuh"
 
 namespace nfk {
 
@@ -72,6 +73,8 @@ __global__ void __launch_bounds__(ZT)
 affine1x1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ Wf, const float* __restrict__ bf,
                      const float* __restrict__ sl, float* __restrict__ y, __nv_bfloat16* __restrict__ col,
                      const float* __restrict__ ld_in, float* __restrict__ ld_out, Geo g, int K1p) {
+  pdl_launch_dependents();
+  pdl_wait();   // (reads global memory from its first instruction: only the launch latency overlaps)
   extern __shared__ float sm[];
   constexpr int CH = C / 2;
   float* Ws = sm;
@@ -270,6 +273,8 @@ __global__ void __launch_bounds__(ZT)
 coupling_bwd_kernel(const float* __restrict__ g_out, const float* __restrict__ g_ld, const float* __restrict__ z_out,
                     const float* __restrict__ hsave, float* __restrict__ dy, __nv_bfloat16* __restrict__ dhcol,
                     int K3p, float* __restrict__ dbias3, Geo g, int brows) {
+  pdl_launch_dependents();
+  pdl_wait();   // (reads global memory from its first instruction: only the launch latency overlaps)
   extern __shared__ float sm[];
   constexpr int J = C / 2;
   const int bands = g.H / brows;               // > 1 only with ipc == 1
@@ -414,6 +419,8 @@ __global__ void __launch_bounds__(ZT)
 affine1x1_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ dcol, int K1p,
                      const float* __restrict__ x, const float* __restrict__ Wf, float* __restrict__ dx,
                      float* __restrict__ dWf, float* __restrict__ dbf, Geo g, int tile_floats) {
+  pdl_launch_dependents();
+  pdl_wait();   // (reads global memory from its first instruction: only the launch latency overlaps)
   extern __shared__ float sm[];
   constexpr int CH = C / 2;
   const int ldp = g.pixt + 1;
@@ -641,8 +648,9 @@ extern "C" int nfk_affine1x1_fwd(const float* x, const float* Wf, const float* b
   NFK_DISPATCH_C(C, {
     int rc = ensure_smem(affine1x1_fwd_kernel<CC>, smem);
     if (rc) return rc;
-    affine1x1_fwd_kernel<CC><<<grid, ZT, smem, st>>>(x, Wf, bf, sl, y, static_cast<__nv_bfloat16*>(col), ld_in,
-                                                     ld_out, g, K1p);
+    if (launch_pdl(affine1x1_fwd_kernel<CC>, dim3(grid), dim3(ZT), smem, st, x, Wf, bf, sl, y,
+                   static_cast<__nv_bfloat16*>(col), ld_in, ld_out, g, K1p) != cudaSuccess)
+      return NFK_ERR_LAUNCH;
   });
   return cudaGetLastError() == cudaSuccess ? NFK_OK : NFK_ERR_LAUNCH;
 }
@@ -685,8 +693,9 @@ extern "C" int nfk_coupling_bwd(const float* g_out, const float* g_ld, const flo
   NFK_DISPATCH_C(C, {
     int rc = ensure_smem(coupling_bwd_kernel<CC>, smem);
     if (rc) return rc;
-    coupling_bwd_kernel<CC><<<grid, ZT, smem, st>>>(g_out, g_ld, z_out, hsave, dy,
-                                                    static_cast<__nv_bfloat16*>(dhcol), K3p, dbias3, g, brows);
+    if (launch_pdl(coupling_bwd_kernel<CC>, dim3(grid), dim3(ZT), smem, st, g_out, g_ld, z_out, hsave, dy,
+                   static_cast<__nv_bfloat16*>(dhcol), K3p, dbias3, g, brows) != cudaSuccess)
+      return NFK_ERR_LAUNCH;
   });
   return cudaGetLastError() == cudaSuccess ? NFK_OK : NFK_ERR_LAUNCH;
 }
@@ -707,7 +716,9 @@ extern "C" int nfk_affine1x1_bwd(const float* dy, const float* dcol, int K1p, co
   NFK_DISPATCH_C(C, {
     int rc = ensure_smem(affine1x1_bwd_kernel<CC>, smem);
     if (rc) return rc;
-    affine1x1_bwd_kernel<CC><<<grid, ZT, smem, st>>>(dy, dcol, K1p, x, Wf, dx, dWf, dbf, g, tile_floats);
+    if (launch_pdl(affine1x1_bwd_kernel<CC>, dim3(grid), dim3(ZT), smem, st, dy, dcol, K1p, x, Wf, dx, dWf, dbf, g,
+                   tile_floats) != cudaSuccess)
+      return NFK_ERR_LAUNCH;
   });
   return cudaGetLastError() == cudaSuccess ? NFK_OK : NFK_ERR_LAUNCH;
 }

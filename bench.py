@@ -578,6 +578,9 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16x3"],
                     help="arithmetic of the 2-D coupling-net GEMMs: bf16 operands (default) or the fp32-class "
                          "3-term split (models.flows.Glow.set_precision)")
+    ap.add_argument("--no-pipeline", action="store_true",
+                    help="2-D KD workloads: do NOT prefetch the frozen teacher's forward of the next batch beside the "
+                         "student's step (train.KDTrainer(pipelined=...)); default is pipelined")
     ap.add_argument("--u8-input", action="store_true",
                     help="image workloads: feed raw uint8 pixels (a quarter of the H2D bytes); preprocess + noise + first "
                          "squeeze run as the step's first kernel")
@@ -626,7 +629,7 @@ def main():
         shape = (B, C, H, W)
     u8 = args.u8_input and not is_1d
     trainer = KDTrainer(config, shape, device, use_graphs=not args.no_graphs,
-                        input_dtype=torch.uint8 if u8 else torch.float32)
+                        input_dtype=torch.uint8 if u8 else torch.float32, pipelined=not args.no_pipeline)
     dtype = wl["dtype"]
     if args.precision != "bf16":
         if is_1d:
@@ -722,6 +725,9 @@ def main():
         gb = B * world
         cfg_desc.update(per_gpu_batch=B, global_batch=gb, parallelism=f"dp{world}",
                         cuda_graphs=not args.no_graphs, input="uint8 pixels" if u8 else "fp32 (preprocessed)",
+                        teacher_prefetch=("1 batch: the frozen teacher's forward of batch t+1 runs beside the student's "
+                                          "step on batch t (same updates; one batch consumed and one update made per "
+                                          "step)") if trainer.pipelined else "off",
                         l2="per-step working set (activations ~GBs) exceeds the 126 MB L2; inputs rotate over 4 batches")
         out = {"metric": METRIC, "value": gb / (ms * 1e-3), "unit": "samples/s", "n_gpus": world,
                "steps": args.steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True,

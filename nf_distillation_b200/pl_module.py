@@ -235,6 +235,38 @@ class NFModel(nn.Module):
             return torch.optim.Adamax(self.student.parameters(), **kw)
         raise NameError("Unknown optimizer name")
 
+    # ---- software pipelining of the frozen teacher (used by train.KDTrainer(pipelined=True))
+    def can_stage(self) -> bool:
+        """True when the teacher's work for a batch can be done ahead of the student's: 2-D Glow pair with a KD term,
+        no perceptual term, unconditioned, fused dequantisation available, fixed-row student prior."""
+        return (self.kd_weight > 0 and self.perceptual_weight == 0 and not self.params["student"]["is_1d"]
+                and not self.params["teacher"]["is_1d"] and not self.params["student"]["y_condition"]
+                and hasattr(self.student, "deferred_objective") and self.student._prior_rows() is not None)
+
+    @torch.no_grad()
+    def stage_batch(self, x):
+        """Everything of forward() that does not depend on the student's weights, for ONE batch: the student's
+        dequantisation noise (in place) and its squeezed copy, then the teacher's noise on top and the frozen teacher's
+        forward. Returns (sq_s, ld_s, [teacher taps in KD order]). The teacher is frozen, so running this for batch t+1
+        while the student trains on batch t changes no result (pl_module.py:215-227: same draws, same order per batch)."""
+        x, ld_s, sq_s = self._dequantize(x)
+        assert sq_s is not None, "staging needs the fused dequantisation layout (fp32 / uint8 NCHW, W % 4 == 0)"
+        xt, ld_t, sq_t = self._dequantize(x)
+        teacher_z, _, _ = self.teacher.flow_from_dequantized(xt, ld_t, None, _sq0=sq_t)
+        return sq_s, ld_s, [teacher_z[i] for i in self.teacher_kd_indices]
+
+    def train_on_staged(self, sq_s, ld_s, taps, x_shape):
+        """The student's half of training_step for a staged batch: forward from the squeezed noised input, the fused
+        loss against the staged teacher taps; returns the same dict as training_step."""
+        x_like = torch.empty(x_shape, device="meta")           # placeholder: only its shape is consulted below
+        student_z, ld, rows, scale = self.student.deferred_objective(x_like, ld_s, None, _sq0=sq_s)
+        t_all = {t: tap for t, tap in zip(self.teacher_kd_indices, taps)}
+        out = {"student_nll": None, "student_z": student_z, "teacher_z": t_all, "student_x": None, "teacher_x": None,
+               "weights": None, "student_objective": (ld, rows, scale)}
+        losses = self.loss(out)
+        return {"nll": losses["nll"], "kd": losses["kd"], "perceptual": losses["perceptual"],
+                "loss": losses["result_loss"]}
+
     # ---- pl_module.py:365-382
     def training_step(self, batch, batch_idx=0):
         losses = self.loss(self.forward(batch, _defer_objective=True))

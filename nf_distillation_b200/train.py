@@ -120,9 +120,16 @@ class KDTrainer:
     """Owns the NFModel, its optimiser, the static device buffers and the captured graphs."""
 
     def __init__(self, config: dict, batch_shape: tp.Sequence[int], device: torch.device, use_graphs: bool = True,
-                 seed: int = 42, input_dtype: torch.dtype = torch.float32):
+                 seed: int = 42, input_dtype: torch.dtype = torch.float32, pipelined: bool = False):
         """input_dtype=torch.uint8: image batches arrive as raw pixels (a quarter of the host-to-device bytes); the
-        first kernel of the step does the reference's preprocess together with the noise and the first squeeze."""
+        first kernel of the step does the reference's preprocess together with the noise and the first squeeze.
+
+        pipelined=True (2-D Glow pairs, see NFModel.can_stage): the FROZEN teacher's forward for the batch in `self.x`
+        runs concurrently with the student's forward / backward / update on the PREVIOUS batch (teacher prefetch of
+        depth one). A step still consumes one batch and makes one optimiser update; the updates are the same as without
+        pipelining (the teacher does not depend on the student), `self.losses` after `step()` are those of the batch
+        handed to the previous `step()`. The dependent launch chain of a step is then max(teacher, student) instead of
+        teacher followed by the student's backward, which is what bounds the step at small per-GPU batches."""
         self.device = device
         self.world = dist.get_world_size() if dist.is_initialized() else 1
         torch.manual_seed(seed)                       # identical initial weights on every rank (train.py:41)
@@ -142,6 +149,9 @@ class KDTrainer:
         self.x = torch.zeros(*batch_shape, device=device, dtype=input_dtype)          # static input buffer
         self.losses = torch.zeros(4, device=device)                 # nll, kd, perceptual, loss
         self.use_graphs = use_graphs
+        self.pipelined = bool(pipelined) and self.module.can_stage()
+        self.staged = None          # (sq_s, ld_s, taps) of the batch the student trains on next
+        self._side = torch.cuda.Stream(device=device) if self.pipelined else None
         self.g_fb: tp.Optional[torch.cuda.CUDAGraph] = None
         self.g_opt: tp.Optional[torch.cuda.CUDAGraph] = None
         torch.manual_seed(seed + 1000 + (dist.get_rank() if dist.is_initialized() else 0))  # per-rank noise stream
@@ -150,11 +160,46 @@ class KDTrainer:
     def _forward_backward(self):
         for p in self.params:
             p.grad = None
+        if self.pipelined:
+            return self._forward_backward_pipelined()
         batch = [self.x] if self.is_1d else [self.x, None]
         out = self.module.training_step(batch, 0)
         out["loss"].backward()
         self.losses.copy_(torch.stack([out["nll"], out["kd"], out["perceptual"], out["loss"]]).detach())
         self.opt.gather_grads()
+
+    def _stage_into_buffers(self):
+        """Teacher side of the batch in self.x -> the static `staged` buffers (allocated on first use)."""
+        sq, ld, taps = self.module.stage_batch(self.x)
+        if self.staged is None:
+            self.staged = (torch.empty_like(sq), torch.empty_like(ld), [torch.empty_like(t) for t in taps])
+        return sq, ld, taps
+
+    def _forward_backward_pipelined(self):
+        """student(batch t) on the main stream  ||  teacher(batch t+1, in self.x) on the side stream; then t+1's staged
+        tensors replace t's. The first call only stages (prime())."""
+        main = torch.cuda.current_stream()
+        self._side.wait_stream(main)
+        with torch.cuda.stream(self._side):
+            nxt = self._stage_into_buffers()
+        sq, ld, taps = self.staged
+        out = self.module.train_on_staged(sq, ld, taps, tuple(self.x.shape))
+        out["loss"].backward()
+        self.losses.copy_(torch.stack([out["nll"], out["kd"], out["perceptual"], out["loss"]]).detach())
+        self.opt.gather_grads()
+        main.wait_stream(self._side)
+        for t in (nxt[0], nxt[1], *nxt[2]):
+            t.record_stream(main)
+        sq.copy_(nxt[0]); ld.copy_(nxt[1])
+        torch._foreach_copy_(taps, nxt[2])
+
+    def prime(self):
+        """Pipelined mode: stage the batch currently in self.x (no training). Call once before the first step."""
+        if not self.pipelined:
+            return
+        sq, ld, taps = self._stage_into_buffers()
+        self.staged[0].copy_(sq); self.staged[1].copy_(ld)
+        torch._foreach_copy_(self.staged[2], taps)
 
     def _clip_and_update(self):
         self.opt.step()
@@ -181,6 +226,7 @@ class KDTrainer:
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
+            self.prime()
             for _ in range(iters):
                 self._forward_backward()
                 self._allreduce()

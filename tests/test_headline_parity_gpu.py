@@ -522,3 +522,60 @@ def test_bf16x3_precision_kd_step_taps_and_gradients_at_fp32_level(monkeypatch):
         assert abs(losses[k_].item() - l32[r]) < 1e-5 * abs(l32[r]) + 1e-7, (k_, losses[k_].item(), l32[r])
     errs = sorted((rel(p.grad, g32[n_]), rel_l2(p.grad, g32[n_]), n_) for n_, p in m.student.named_parameters())
     assert errs[-1][0] < 1.5e-2 and max(e[1] for e in errs) < 5e-3 and errs[len(errs) // 2][0] < 5e-4, errs[-3:]
+
+
+# ------------------------------------------------------------------------------------------------ teacher prefetch
+@pytest.mark.parametrize("use_graphs", [True, False])
+def test_pipelined_trainer_makes_the_same_updates_as_the_sequential_one(use_graphs, monkeypatch):
+    """KDTrainer(pipelined=True) runs the frozen teacher's forward of batch t+1 beside the student's step on batch t.
+    The teacher does not depend on the student, so the sequence of updates must be THE SAME as without pipelining:
+    three steps on the same batches / noise from the same weights -> identical loss values (shifted by one call) and
+    weights equal to fp32 atomics noise."""
+    from nf_distillation_b200.models import utils as U
+    from nf_distillation_b200.train import KDTrainer, glow_cfg, kd_config
+    s_cfg, t_cfg = glow_cfg((32, 32, 3), 2, 3, 128), glow_cfg((32, 32, 3), 3, 3, 128)
+    B, steps = 16, 3
+    g = torch.Generator().manual_seed(8)
+    xs = [images(B, 32, g) for _ in range(steps + 1)]
+    noises = [(torch.rand(B, 3, 32, 32, generator=g) / 256, torch.rand(B, 3, 32, 32, generator=g) / 256)
+              for _ in range(steps + 1)]
+    results = {}
+    for mode in ("plain", "pipelined"):
+        noise = StaticNoise((B, 3, 32, 32))
+        monkeypatch.setattr(U, "dequant_noise", noise)
+        tr = KDTrainer(kd_config(s_cfg, t_cfg), (B, 3, 32, 32), torch.device(dev), use_graphs=use_graphs, seed=42,
+                       pipelined=(mode == "pipelined"))
+        assert tr.pipelined == (mode == "pipelined")
+        init = {k: v.detach().cpu().clone() for k, v in tr.module.student.state_dict().items()}
+        tr.x.copy_(xs[0].to(dev)); noise.set(*noises[0])
+        tr.warmup(iters=1)
+        tr.reset_state(init)
+        losses, g1 = [], None
+        if mode == "pipelined":
+            tr.x.copy_(xs[0].to(dev)); noise.set(*noises[0]); noise.i = 0
+            tr.prime()                                          # stage batch 0
+        for t in range(steps):
+            nxt = t + (mode == "pipelined")                     # pipelined: train on batch t while staging batch t + 1
+            noise.set(*noises[nxt])
+            losses.append(tr.step(xs[nxt].pin_memory()).tolist())
+            if t == 0:
+                g1 = tr.flat_grad_view().detach().cpu().clone()
+        torch.cuda.synchronize()
+        results[mode] = (losses, {k: v.detach().cpu().clone() for k, v in tr.module.student.state_dict().items()}, g1)
+    for a, b in zip(results["plain"][0], results["pipelined"][0]):
+        for u, v in zip(a, b):
+            assert abs(u - v) <= 1e-5 * abs(u) + 1e-8, (results["plain"][0], results["pipelined"][0])
+    # first step: the same weights see the same batch -> the same gradient (fp32 atomics order aside)
+    assert rel(results["pipelined"][2], results["plain"][2]) < 1e-5
+    # after three Adam steps: Adam divides by sqrt(v), so an element whose gradient is small against the 1e-5 * max|g|
+    # run-to-run noise of the fp32 atomics gets a visibly different normalised step (two runs of the SAME mode differ
+    # the same way); the weights agree to a tenth of one step size on all but a handful of elements
+    bad = tot = 0
+    lr = 5e-4
+    for k, w in results["plain"][1].items():
+        if w.dtype.is_floating_point:
+            d = (results["pipelined"][1][k] - w).abs()
+            bad += (d > 0.1 * lr).sum().item()
+            tot += d.numel()
+            assert d.max().item() <= 2.1 * lr * steps, k
+    assert bad <= 1e-2 * tot, (bad, tot)

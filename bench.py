@@ -195,6 +195,70 @@ def cnet_roofline(B, H, W, C_img, hid, device):
             "shape": {"M": M, "K1": K1, "K1p": K1p, "hid": hid}}
 
 
+def kernel_table(B, H, W, C_img, hid, device):
+    """Live roofline fractions of the OTHER kernels of the 2-D step at the level-0 shape of this run (the `roofline` key
+    holds the dominant one): each timed alone like cnet_roofline, algorithmic bytes / FLOPs as in DESIGN.md §3, against
+    the measured HBM copy bandwidth or bf16 burst peak."""
+    from nf_distillation_b200 import ops
+    pk = peaks()
+    C = 4 * C_img
+    Hs, Ws = H // 2, W // 2
+    M = B * Hs * Ws
+    K1p, K3p = ops.round_up(9 * C // 2, 64), ops.round_up(9 * C, 64)
+    bf16, f32 = torch.bfloat16, torch.float32
+    rows = []
+
+    def add(name, bound, work, us):
+        peak = pk["hbm_gbs"] if bound == "hbm" else pk["bf16_tflops"]
+        ach = work / (us * 1e-6) / (1e9 if bound == "hbm" else 1e12)
+        rows.append({"kernel": name, "bound": bound, "achieved": round(ach, 1), "peak": peak,
+                     "unit": "GB/s" if bound == "hbm" else "TFLOP/s", "frac": round(ach / peak, 3),
+                     "us_per_launch": round(us, 1)})
+
+    nb = 2
+    h2 = [(torch.randn(M, hid, device=device).clamp_min(0) * 0.5).to(bf16) for _ in range(nb)]
+    ys = [torch.randn(B, C, Hs, Ws, device=device) for _ in range(nb)]
+    xs = [torch.randn(B, C, Hs, Ws, device=device) for _ in range(nb)]
+    ld = torch.zeros(B, device=device)
+    B3 = (torch.randn(K3p, hid, device=device) * 0.02).to(bf16)
+    b3 = torch.zeros(C, device=device)
+    if ops.pconv_coupling_supported(C, Hs, Ws, hid):
+        us = time_graph(lambda i: ops.pconv_coupling_fwd(h2[i], B3, K3p, b3, ys[i], None, ld, B, C, Hs, Ws, hid, False),
+                        10, nb) * 1e3
+        add(f"pconv_coupling_kernel<{C}> (Conv2dZeros + coupling, reads h2 once)", "hbm", 2.0 * M * hid + 4.0 * M * C, us)
+    Wf, bfv, sl = torch.randn(C, C, device=device) * 0.3, torch.randn(C, device=device), torch.zeros(1, device=device)
+    cols = [torch.empty(M, K1p, device=device, dtype=bf16) for _ in range(nb)]
+    ld1 = torch.zeros(B, device=device)
+    us = time_graph(lambda i: ops.affine1x1_fwd(xs[i], Wf, bfv, sl, ys[i], cols[i], K1p, ld, ld1, B, C, Hs, Ws), 10, nb) * 1e3
+    add(f"affine1x1_fwd_kernel<{C}> (ActNorm o invconv + bf16 im2col)", "hbm", M * (8.0 * C + 2.0 * K1p), us)
+    # backward kernels of the student
+    dpre = [(torch.randn(M, hid, device=device) * 0.1).to(bf16) for _ in range(nb)]
+    dW = torch.zeros(hid, hid, device=device)
+    us = time_graph(lambda i: ops.gemm_tn(dpre[i], h2[i], hid, hid, M, dW), 10, nb) * 1e3
+    add("gemm_tn_kernel (conv#2 weight gradient, split-K)", "tensor", 2.0 * M * hid * hid, us)
+    W2T = (torch.randn(hid, hid, device=device) * 0.05).to(bf16)
+    mask = ops.relu_mask_like(M, hid, device)
+    mask.fill_(-1)
+    cs = torch.zeros(hid, device=device)
+    outs = [torch.empty(M, hid, device=device, dtype=bf16) for _ in range(nb)]
+    us = time_graph(lambda i: ops.gemm_nt(dpre[i], W2T, M, hid, hid, ops.EPI_MASK_BF16, outs[i], aux=mask, colsum=cs),
+                    10, nb) * 1e3
+    add("gemm_nt_pair_kernel<MASK_BF16> (conv#2 input gradient + ReLU mask + bias gradient)", "tensor",
+        2.0 * M * hid * hid, us)
+    del h2, dpre, outs, mask
+    hsv = [torch.randn(M, C, device=device) for _ in range(nb)]
+    dys = [torch.empty(B, C, Hs, Ws, device=device) for _ in range(nb)]
+    dhc = [torch.empty(M, K3p, device=device, dtype=bf16) for _ in range(nb)]
+    db3 = torch.zeros(C, device=device)
+    us = time_graph(lambda i: ops.coupling_bwd(xs[i], ld, ys[i], hsv[i], dys[i], dhc[i], K3p, db3, B, C, Hs, Ws), 10, nb) * 1e3
+    add(f"coupling_bwd_kernel<{C}> (coupling backward + bf16 im2col of dh)", "hbm", M * (14.0 * C + 2.0 * K3p), us)
+    dcol = [torch.randn(M, K1p, device=device) * 0.1 for _ in range(nb)]
+    dWf, dbf = torch.zeros(C, C, device=device), torch.zeros(C, device=device)
+    us = time_graph(lambda i: ops.affine1x1_bwd(dys[i], dcol[i], K1p, xs[i], Wf, ys[i], dWf, dbf, B, C, Hs, Ws), 10, nb) * 1e3
+    add(f"affine1x1_bwd_kernel<{C}> (col2im + W'^T dy + dW')", "hbm", M * (12.0 * C + 4.0 * K1p), us)
+    return rows
+
+
 def flow1d_roofline(B, D, hid, device):
     """1-D Glow: the fused FlowStep kernel (csrc/flow1d.cu) is fp32-FMA bound, its HBM side is 8*D bytes per sample;
     report the HBM fraction (the bound the tier's contract names for non-GEMM paths) of the inference kernel."""
@@ -574,6 +638,8 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-graphs", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-kernel-table", action="store_true",
+                    help="skip the live roofline table of the non-dominant kernels (key `kernels`)")
     ap.add_argument("--cpu-batch", type=int, default=32)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16x3"],
                     help="arithmetic of the 2-D coupling-net GEMMs: bf16 operands (default) or the fp32-class "
@@ -712,6 +778,12 @@ def main():
     ms, ms_e2e = t.tolist()
 
     roof = roofline_for(wl, B, device) if rank == 0 and args.precision == "bf16" else None
+    ktable = None
+    pipelined = trainer.pipelined
+    if rank == 0 and world == 1 and not is_1d and args.precision == "bf16" and not args.no_kernel_table:
+        del trainer, dev_pool
+        torch.cuda.empty_cache()
+        ktable = kernel_table(B, H, W, C, wl["hidden"], device)
 
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -727,7 +799,7 @@ def main():
                         cuda_graphs=not args.no_graphs, input="uint8 pixels" if u8 else "fp32 (preprocessed)",
                         teacher_prefetch=("1 batch: the frozen teacher's forward of batch t+1 runs beside the student's "
                                           "step on batch t (same updates; one batch consumed and one update made per "
-                                          "step)") if trainer.pipelined else "off",
+                                          "step)") if pipelined else "off",
                         l2="per-step working set (activations ~GBs) exceeds the 126 MB L2; inputs rotate over 4 batches")
         out = {"metric": METRIC, "value": gb / (ms * 1e-3), "unit": "samples/s", "n_gpus": world,
                "steps": args.steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True,
@@ -738,7 +810,7 @@ def main():
                        "d2h_bytes_per_step": 16},
                "gpu_launches": launches_per_step * args.steps, "gpu_launches_per_step": launches_per_step,
                "losses_last_step": dict(zip(("nll", "kd", "perceptual", "loss"), losses)),
-               "logp_delta": delta, "roofline": roof, "cpu_baseline": cpu_base}
+               "logp_delta": delta, "roofline": roof, "kernels": ktable, "cpu_baseline": cpu_base}
         print(json.dumps(out))
     if world > 1:
         dist.barrier()

@@ -168,8 +168,8 @@ class KDTrainer:
         self.losses.copy_(torch.stack([out["nll"], out["kd"], out["perceptual"], out["loss"]]).detach())
         self.opt.gather_grads()
 
-    def _stage_into_buffers(self):
-        """Teacher side of the batch in self.x -> the static `staged` buffers (allocated on first use)."""
+    def _stage_next(self):
+        """Teacher side of the batch in self.x as fresh tensors (the static `staged` buffers are allocated on first use)."""
         sq, ld, taps = self.module.stage_batch(self.x)
         if self.staged is None:
             self.staged = (torch.empty_like(sq), torch.empty_like(ld), [torch.empty_like(t) for t in taps])
@@ -181,7 +181,7 @@ class KDTrainer:
         main = torch.cuda.current_stream()
         self._side.wait_stream(main)
         with torch.cuda.stream(self._side):
-            nxt = self._stage_into_buffers()
+            nxt = self._stage_next()
         sq, ld, taps = self.staged
         out = self.module.train_on_staged(sq, ld, taps, tuple(self.x.shape))
         out["loss"].backward()
@@ -197,7 +197,7 @@ class KDTrainer:
         """Pipelined mode: stage the batch currently in self.x (no training). Call once before the first step."""
         if not self.pipelined:
             return
-        sq, ld, taps = self._stage_into_buffers()
+        sq, ld, taps = self._stage_next()
         self.staged[0].copy_(sq); self.staged[1].copy_(ld)
         torch._foreach_copy_(self.staged[2], taps)
 

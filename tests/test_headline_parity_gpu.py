@@ -562,9 +562,11 @@ def test_pipelined_trainer_makes_the_same_updates_as_the_sequential_one(use_grap
                 g1 = tr.flat_grad_view().detach().cpu().clone()
         torch.cuda.synchronize()
         results[mode] = (losses, {k: v.detach().cpu().clone() for k, v in tr.module.student.state_dict().items()}, g1)
-    for a, b in zip(results["plain"][0], results["pipelined"][0]):
+    # step 1 starts from identical weights: identical losses up to atomics order; later steps inherit the (Adam-
+    # normalised) run-to-run noise of the earlier updates, measured at ~1e-5 of the kd term
+    for i, (a, b) in enumerate(zip(results["plain"][0], results["pipelined"][0])):
         for u, v in zip(a, b):
-            assert abs(u - v) <= 1e-5 * abs(u) + 1e-8, (results["plain"][0], results["pipelined"][0])
+            assert abs(u - v) <= (2e-6 if i == 0 else 1e-4) * abs(u) + 1e-8, (results["plain"][0], results["pipelined"][0])
     # first step: the same weights see the same batch -> the same gradient (fp32 atomics order aside)
     assert rel(results["pipelined"][2], results["plain"][2]) < 1e-5
     # after three Adam steps: Adam divides by sqrt(v), so an element whose gradient is small against the 1e-5 * max|g|

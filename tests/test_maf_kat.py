@@ -149,3 +149,67 @@ def test_cuda_maf_is_autoregressive_at_full_size():
         back, ldb = made(u0, logdet=ld0, reverse=True)
         assert ((back - x).abs().max() / x.abs().max()).item() < 2e-2      # bf16 operands in the conditioner
         assert ldb.abs().max().item() < 2e-2 * (ld0.abs().max().item() + 1)
+
+
+# ------------------------------------------------------------------------------------------------ BASELINE shapes
+def graph_kat(D):
+    d = load(f"maf_kat_graph_d{D}")
+    sd = {k[3:]: torch.from_numpy(v.copy()) for k, v in d.items() if k.startswith("sd.")}
+    return d, sd
+
+
+@pytest.mark.parametrize("D", [6, 63])
+def test_maf_oracle_matches_the_graph_interpreter_at_baseline_shapes(D):
+    """oracle/make_maf_kat_graph.py: a sparse MADE layer at D = 6 / 63, hidden 512 (BASELINE configs[0] / [1]) evaluated
+    connection by connection in float64 — no masks, no matrix products — with decoy weights on illegal positions.
+    The paper restatement must reproduce it, and the fixture's degrees must be the product's own assignment."""
+    from nf_distillation_b200.models.maf import hidden_degrees
+    from oracle import maf_oracle as MO
+    d, sd = graph_kat(D)
+    assert torch.equal(sd["deg1"].long(), hidden_degrees(D, 512).long())
+    sd64 = {"l." + k: (v.double() if v.dtype.is_floating_point else v) for k, v in sd.items()}
+    x = t(d["x"])
+    u, ld = MO.made_forward(x, sd64, "l.", D, flip=False)
+    assert (u - t(d["u_x_order"])).abs().max() < 1e-12 and (ld - t(d["logdet"])).abs().max() < 1e-12
+    xr, _ = MO.made_inverse(t(d["u_x_order"]), sd64, "l.", D, flip=False)
+    assert (xr - x).abs().max() < 1e-9
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("D", [6, 63])
+def test_cuda_made_layer_matches_the_graph_interpreter_at_baseline_shapes(D):
+    """The CUDA MADE layer at the benchmark shapes against the float64 graph interpreter. All weights / inputs / hidden
+    activations are dyadic and fit bf16, so the tensor-core products are exact: forward u and log-det 3e-6 through BOTH
+    forward paths (the per-layer GEMMs with k-block skipping at B = 64, and the fused two-GEMM kernel with its skipped
+    B2 tiles at B = 8256), the inverse through the push kernel, the pull kernel and the D-pass GEMM fallback."""
+    from nf_distillation_b200.models.maf import MADE
+    d, sd = graph_kat(D)
+    made = MADE(D, 512, flip=False)
+    made.load_state_dict(sd)
+    made = made.cuda().eval()
+    rel = lambda a, b: ((a.double().cpu() - b).abs().max() / b.abs().max()).item()
+    x = t(d["x"]).float().cuda()
+    u_ref, ld_ref = t(d["u_x_order"]), t(d["logdet"])
+    with torch.no_grad():
+        u, ld = made(x, logdet=torch.zeros(x.shape[0], device="cuda"))
+        assert rel(u, u_ref) < 3e-6 and rel(ld, ld_ref) < 3e-6
+        reps = 129
+        xb = x.repeat(reps, 1)                                   # 8256 rows: the fused kernel's path
+        ub, ldb = made(xb, logdet=torch.zeros(xb.shape[0], device="cuda"))
+        assert rel(ub, u_ref.repeat(reps, 1)) < 3e-6 and rel(ldb, ld_ref.repeat(reps)) < 3e-6
+        for push, resident in ((True, True), (False, True), (False, False)):
+            made.push_inverse, made.resident_inverse = push, resident
+            back, ld0 = made(u_ref.float().cuda(), logdet=ld_ref.float().cuda(), reverse=True)
+            assert rel(back, t(d["x"])) < 1e-5, (push, resident)
+            assert ld0.abs().max().item() < 1e-4, (push, resident)
+    # training forward (activation-saving kernels) agrees too, and gradients reach only legal connections
+    made.push_inverse = made.resident_inverse = True
+    xg = x.clone().requires_grad_(True)
+    ug, ldg = made(xg, logdet=torch.zeros(x.shape[0], device="cuda"))
+    assert rel(ug.detach(), u_ref) < 3e-6
+    (ug.sum() + ldg.sum()).backward()
+    assert xg.grad.triu(0).shape == xg.grad.shape            # (shape sanity)
+    from oracle import maf_oracle as MO
+    m1, m2, m3 = MO.masks(D, made.deg1.cpu().long(), made.deg2.cpu().long())
+    assert (made.fc1.weight.grad.cpu()[m1 == 0] == 0).all() and (made.fc2.weight.grad.cpu()[m2 == 0] == 0).all()
+    assert (made.fc3.weight.grad.cpu()[m3 == 0] == 0).all()

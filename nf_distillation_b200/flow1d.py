@@ -184,8 +184,6 @@ def flowstep1d(step, input, y_onehot, logdet, reverse):
     needs_grad = torch.is_grad_enabled() and (input.requires_grad or ld.requires_grad
                                               or any(p.requires_grad for p in params))
     if needs_grad:
-        if not step.invconv.LU_decomposed:
-            raise NotImplementedError("training with LU_decomposed=False is not built")
         ws, bs = _mlp_params(step)
         pctx, idx, token = Fn.prep_for(step, bool(reverse))
         z, ld_out = FlowStep1dFn.apply(input, ld, cond, step, bool(reverse), token, pctx, idx, *ws, *bs)

@@ -95,7 +95,10 @@ class PrepCtx:
         flat = []
         for st in self.steps:
             iv = st.invconv
-            flat += [st.actnorm.bias, st.actnorm.logs, iv.lower, iv.upper, iv.log_s]
+            if iv.LU_decomposed:
+                flat += [st.actnorm.bias, st.actnorm.logs, iv.lower, iv.upper, iv.log_s]
+            else:   # plain weight (layers.py:366-375): same five slots, the matrix in the first, the others unused
+                flat += [st.actnorm.bias, st.actnorm.logs, iv.weight, iv.weight, iv.weight]
         for st in self.steps:
             if not st.is_1d:
                 flat += list(st._coupling_params_2d())
@@ -166,8 +169,12 @@ class PrepAllFn(torch.autograd.Function):
             bf = buf[off:off + C]; off += ops.round_up(C, 4)
             sl = buf[off:off + 1]; off += 4
             an_bias, an_logs, lower, upper, log_s = flat[5 * i:5 * i + 5]
-            it = ops.invconv_item(an_bias, an_logs, lower, upper, log_s, st.invconv.p, st.invconv.sign_s, None, C,
-                                  pctx.reverse, st.is_1d, Wf, bf, sl)
+            if st.invconv.LU_decomposed:
+                it = ops.invconv_item(an_bias, an_logs, lower, upper, log_s, st.invconv.p, st.invconv.sign_s, None, C,
+                                      pctx.reverse, st.is_1d, Wf, bf, sl)
+            else:
+                it = ops.invconv_item(an_bias, an_logs, None, None, None, None, None, lower, C, pctx.reverse,
+                                      st.is_1d, Wf, bf, sl)
             items.append(it)
             pctx.consts[i] = (Wf, bf, sl)
             pctx.items[i] = it
@@ -218,11 +225,16 @@ class PrepAllFn(torch.autograd.Function):
             C = pctx.steps[i].in_channels
             d = [arena[offs[5 * j + k]:offs[5 * j + k] + sizes[5 * j + k]] for k in range(5)]
             d_bias, d_logs = d[0].view_as(flat[5 * i]), d[1].view_as(flat[5 * i + 1])
-            d_lower, d_upper, d_log_s = d[2].view(C, C), d[3].view(C, C), d[4].view_as(flat[5 * i + 4])
+            d_lower, d_upper, d_log_s = d[2].view(C, C), d[3].view(C, C), d[4]   # (d_log_s: [C], like log_s)
             dWf, dWf_ld, dbf, g_ld, B, pixels = pctx.grads[i]
-            items.append(ops.invconv_bwd_item(pctx.items[i], dWf.data_ptr(), dWf_ld, dbf, g_ld, B, pixels, d_bias,
-                                              d_logs, d_lower, d_upper, d_log_s))
-            out[5 * i:5 * i + 5] = [d_bias, d_logs, d_lower, d_upper, d_log_s]
+            if pctx.steps[i].invconv.LU_decomposed:
+                items.append(ops.invconv_bwd_item(pctx.items[i], dWf.data_ptr(), dWf_ld, dbf, g_ld, B, pixels, d_bias,
+                                                  d_logs, d_lower, d_upper, d_log_s))
+                out[5 * i:5 * i + 5] = [d_bias, d_logs, d_lower, d_upper, d_log_s]
+            else:   # gradient of the plain weight lands in the first of its three slots
+                items.append(ops.invconv_bwd_item(pctx.items[i], dWf.data_ptr(), dWf_ld, dbf, g_ld, B, pixels, d_bias,
+                                                  d_logs, None, None, None, d_weight=d_lower))
+                out[5 * i:5 * i + 5] = [d_bias, d_logs, d_lower, None, None]
         ops.invconv_prep_bwd_batch(items)
         pctx.grads = [None] * n
         # coupling-net parameters of the 2-D steps

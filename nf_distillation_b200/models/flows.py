@@ -160,9 +160,10 @@ class FlowStep(nn.Module):
         return k
 
     def _batched_prep_ok(self):
-        """True when this step's fused affine can be built by the batched K0 launch (functional.PrepCtx)."""
+        """True when this step's fused affine can be built by the batched K0 launch (functional.PrepCtx): LU-parametrised
+        steps, fixed permutations (an LU with frozen factors) and plain-weight steps (LU_decomposed=False) alike."""
         self._sync_permutation()
-        return bool(self.invconv.LU_decomposed)
+        return True
 
     def _check_actnorm_inited(self, input):
         """Reference layers.py:129-133: an ActNorm that was never initialised runs its data-dependent init on the first
@@ -225,8 +226,6 @@ class FlowStep(nn.Module):
             return self._forward_precise(input, ld, want_ld, reverse, needs_grad)
         if not reverse:
             if needs_grad:
-                if not self.invconv.LU_decomposed:
-                    raise NotImplementedError("training with LU_decomposed=False is not built")
                 pctx, idx, token = Fn.prep_for(self, False)
                 z, ld_out = Fn.FlowStep2dFn.apply(input, ld, self.hidden_channels, token, pctx, idx)
             else:

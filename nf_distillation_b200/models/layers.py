@@ -307,7 +307,7 @@ class InvertibleConv1x1(nn.Module):
         w_shape = [num_channels, num_channels]
         w_init = torch.linalg.qr(torch.randn(*w_shape))[0]
         if not LU_decomposed:
-            self.weight = nn.Parameter(torch.Tensor(w_init))
+            self.weight = nn.Parameter(w_init.contiguous())   # (QR returns a column-major Q; the kernels read rows)
         else:
             p, lower, upper = torch.lu_unpack(*torch.linalg.lu_factor(w_init))
             s = torch.diag(upper)

@@ -283,6 +283,16 @@ int nfk_cnet_set_prof(void* buf); /* diagnostics: per-CTA cycle counters of the 
 int nfk_cnet_fwd_fused(const void* col, int K1p, const void* B1, const void* B2, const float* bias1,
                        const float* bias2, void* h1, void* h2, void* mask1, void* mask2, long long ldmask, int M,
                        int hid, void* stream);
+/* The same pipeline for the BACKWARD chain of the coupling net (student training): d2 = relu'(h2) .* (dhcol B3T^T) —
+ * the Conv2dZeros input gradient through the ReLU mask of h2 — stays in shared memory as the A operand of
+ * d1 = relu'(h1) .* (d2 B2T^T); both are written out as bf16 [M, 512] (the weight-gradient GEMMs read them) and their
+ * column sums are added into dbias2 / dbias1 (fp32 [512], caller-zeroed; NULL = not needed). dhcol [M, K3p] bf16
+ * (nfk_coupling_bwd), B3T [512, K3p], B2T [512, 512] bf16 (nfk_coupling_prep, transposed operands), masks as written by
+ * nfk_cnet_fwd_fused / nfk_gemm_nt_bf16 (word-major, [16][ldmask >= M]). Replaces two nfk_gemm_nt_bf16 calls with
+ * NFK_EPI_MASK_BF16 (autograd of models/flows.py:25-34). hid must be 512, K3p a multiple of 64 up to 512. */
+int nfk_cnet_bwd_fused(const void* dhcol, int K3p, const void* B3T, const void* B2T, const void* mask_h2,
+                       const void* mask_h1, long long ldmask, void* dpre2, void* dpre1, float* dbias2, float* dbias1,
+                       int M, int hid, void* stream);
 /* Same kernel for MADE's masked linears: the second weight matrix is block lower triangular (degree-sorted hidden
  * units), so for output channels [0, 256) only its first kb2_end_half0 k-blocks of 64 input channels are non-zero;
  * the remaining B2 tiles of that half are neither loaded nor multiplied (1 <= kb2_end_half0 <= 8; 8 = dense). */

@@ -43,6 +43,10 @@ struct CnetArgs {
   // degree-sorted hidden mask is block lower triangular: the low-degree half of the outputs never sees the high-degree
   // inputs, so those B2 tiles are neither loaded nor multiplied (they are exact zeros: the result is bit-identical).
   int kb2_end[2];
+  // MODE 1 (backward chain): mask1 / mask2 are the INPUT ReLU masks applied to the outputs of GEMM 1 / GEMM 2, and the
+  // column sums of those masked outputs (the bias gradients) are accumulated here
+  float* colsum1;
+  float* colsum2;
 };
 
 struct CnetSmem {
@@ -58,10 +62,15 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CF_THREADS, 1)
-cnet_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmCol, const __grid_constant__ CUtensorMap tmB1,
-                      const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmH1,
-                      const __grid_constant__ CUtensorMap tmH2, const CnetArgs g) {
+// MODE 0: forward   h1 = relu(col B1^T + b1), h2 = relu(h1 B2^T + b2)                      (+ optional h1 / mask outputs)
+// MODE 1: backward  d2 = mask_a .* (dhcol B3T^T),  d1 = mask_b .* (d2 B2T^T)                (the two dgrads of the chain:
+//         Conv2dZeros input gradient -> ReLU mask of h2 -> conv1x1 input gradient -> ReLU mask of h1), both written
+//         out as bf16 (the weight-gradient GEMMs read them) with their column sums = the two bias gradients. Same tiles,
+//         same pipeline: d2 stays in the shared-memory panels as the A operand of the second GEMM.
+template <int MODE>
+__device__ __forceinline__ void cnet_fused_body(const CUtensorMap& tmCol, const CUtensorMap& tmB1,
+                                                const CUtensorMap& tmB2, const CUtensorMap& tmH1,
+                                                const CUtensorMap& tmH2, const CnetArgs& g) {
   extern __shared__ __align__(1024) uint8_t smem[];
   pdl_launch_dependents();
   if (smem_u32(smem) & 1023u) __trap();
@@ -245,6 +254,41 @@ cnet_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmCol, const __grid_co
         mask[static_cast<long long>((col0 + 32) >> 5) * g.ldmask + row] = b2 | (b3 << 16);
       }
     };
+    // ---- MODE 1 pieces: masked copy of 16 accumulator columns, a 64-column panel, and the column sums of a panel
+    auto epi16m = [&](const uint32_t (&r)[16], uint32_t bits16, uint8_t* dst, int cc0) {
+      uint32_t p[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float lo = ((bits16 >> (2 * k)) & 1u) ? __uint_as_float(r[2 * k]) : 0.f;
+        const float hi = ((bits16 >> (2 * k + 1)) & 1u) ? __uint_as_float(r[2 * k + 1]) : 0.f;
+        p[k] = pack2(lo, hi);
+      }
+      *reinterpret_cast<uint4*>(dst + ((static_cast<uint32_t>(cc0) ^ sw) << 4)) = make_uint4(p[0], p[1], p[2], p[3]);
+      *reinterpret_cast<uint4*>(dst + ((static_cast<uint32_t>(cc0 + 1) ^ sw) << 4)) =
+          make_uint4(p[4], p[5], p[6], p[7]);
+    };
+    auto panel64m = [&](const uint32_t (&r0)[16], const uint32_t (&r1)[16], const uint32_t (&r2)[16],
+                        const uint32_t (&r3)[16], uint32_t w0, uint32_t w1, uint8_t* dst_rows) {
+      uint8_t* dst = dst_rows + lane * 128;
+      epi16m(r0, w0 & 0xFFFFu, dst, 0); epi16m(r1, w0 >> 16, dst, 2);
+      epi16m(r2, w1 & 0xFFFFu, dst, 4); epi16m(r3, w1 >> 16, dst, 6);
+    };
+    // column sums of this warp's 32 x 64 panel slice, straight from the staged bf16 rows: lane owns the column pair
+    // (lane >> 2) * 8 + (lane & 3) * 2 (+1); at row r the 32 lanes read the whole 128-byte row (conflict-free)
+    auto panel_colsum = [&](const uint8_t* rows, float& s0, float& s1) {
+      const uint8_t* pb = rows + (lane & 3) * 4;
+      const uint32_t chunk = static_cast<uint32_t>(lane >> 2);
+      float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+#pragma unroll 8
+      for (int r = 0; r < 32; r += 2) {
+        const uint32_t w0 = *reinterpret_cast<const uint32_t*>(pb + r * 128 + ((chunk ^ (r & 7)) << 4));
+        const uint32_t w1 = *reinterpret_cast<const uint32_t*>(pb + (r + 1) * 128 + ((chunk ^ ((r + 1) & 7)) << 4));
+        a0 += __uint_as_float(w0 << 16); a1 += __uint_as_float(w0 & 0xFFFF0000u);
+        b0 += __uint_as_float(w1 << 16); b1 += __uint_as_float(w1 & 0xFFFF0000u);
+      }
+      s0 += a0 + b0; s1 += a1 + b1;
+    };
+    float cs1[4][2] = {}, cs2[4][2] = {};    // [2 h + pz][column of the pair]: bias-gradient partial sums of this CTA
     // this warp's 128 accumulator columns -> registers, all loads in flight at once; the accumulator stage can be
     // handed back to the MMA issuer as soon as they have landed, before any of the epilogue math
     auto load128 = [&](uint32_t tm, uint32_t (&R)[8][16]) {
@@ -255,6 +299,19 @@ cnet_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmCol, const __grid_co
     for (int t = pair; t < num_tiles; t += num_pairs) {
       const int row0 = t * 256 + static_cast<int>(rank) * 128 + qd * 32;
       const long long row = row0 + lane;
+      uint32_t mw1[8], mw2[8];     // MODE 1: this thread's ReLU-mask words of the tile (fetched before the waits)
+      if constexpr (MODE == 1) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {            // i = 2 h + pz
+          const int c1 = (4 * (i >> 1) + 2 * (i & 1) + hf) * 64;            // GEMM 1: panel columns
+          const int c2 = (i >> 1) * 256 + hf * 128 + (i & 1) * 64;           // GEMM 2: staged columns
+          const bool ok = row < g.M;
+          mw1[2 * i] = ok ? __ldg(g.mask1 + static_cast<long long>(c1 >> 5) * g.ldmask + row) : 0u;
+          mw1[2 * i + 1] = ok ? __ldg(g.mask1 + static_cast<long long>((c1 + 32) >> 5) * g.ldmask + row) : 0u;
+          mw2[2 * i] = ok ? __ldg(g.mask2 + static_cast<long long>(c2 >> 5) * g.ldmask + row) : 0u;
+          mw2[2 * i + 1] = ok ? __ldg(g.mask2 + static_cast<long long>((c2 + 32) >> 5) * g.ldmask + row) : 0u;
+        }
+      }
       // h1 of the previous tile must be dead (its conv#2 MMAs retired); its optional h1 stores must have been read
       mbar_wait(h1_empty, tile_ph ^ 1);
       if (g.store_h1) {
@@ -281,10 +338,21 @@ cnet_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmCol, const __grid_co
         for (int pz = 0; pz < 2; ++pz) {
           const int panel = 4 * h + 2 * pz + hf;
           uint8_t* dst = smem + CnetSmem::h1 + panel * CF_PANEL + qd * 32 * 128;
-          if (pz == 0) panel64(R[0], R[1], R[2], R[3], g.bias1 + panel * 64, dst, g.mask1, row, panel * 64);
-          else panel64(R[4], R[5], R[6], R[7], g.bias1 + panel * 64, dst, g.mask1, row, panel * 64);
+          if constexpr (MODE == 0) {
+            if (pz == 0) panel64(R[0], R[1], R[2], R[3], g.bias1 + panel * 64, dst, g.mask1, row, panel * 64);
+            else panel64(R[4], R[5], R[6], R[7], g.bias1 + panel * 64, dst, g.mask1, row, panel * 64);
+          } else {
+            // (h is a run-time loop variable: select with ternaries so the word arrays stay in registers)
+            if (pz == 0) panel64m(R[0], R[1], R[2], R[3], h ? mw1[4] : mw1[0], h ? mw1[5] : mw1[1], dst);
+            else panel64m(R[4], R[5], R[6], R[7], h ? mw1[6] : mw1[2], h ? mw1[7] : mw1[3], dst);
+          }
           fence_proxy_async();
           __syncwarp();
+          if constexpr (MODE == 1) {
+            float s0 = 0.f, s1 = 0.f;
+            panel_colsum(dst, s0, s1);
+            if (h == 0) { cs1[pz][0] += s0; cs1[pz][1] += s1; } else { cs1[2 + pz][0] += s0; cs1[2 + pz][1] += s1; }
+          }
           if (lane == 0) {
             mbar_arrive_cluster(&h1_full[panel], 0);
             if (g.store_h1 && row0 < g.M) tma_store_2d(dst, &tmH1, panel * 64, row0);
@@ -311,10 +379,20 @@ cnet_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmCol, const __grid_co
           // same wait also covers the h1 stores, which only READ the h1 panels that conv#2 is reading anyway.)
           if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
           __syncwarp();
-          if (pz == 0) panel64(R[0], R[1], R[2], R[3], g.bias2 + col0, stage, g.mask2, row, col0);
-          else panel64(R[4], R[5], R[6], R[7], g.bias2 + col0, stage, g.mask2, row, col0);
+          if constexpr (MODE == 0) {
+            if (pz == 0) panel64(R[0], R[1], R[2], R[3], g.bias2 + col0, stage, g.mask2, row, col0);
+            else panel64(R[4], R[5], R[6], R[7], g.bias2 + col0, stage, g.mask2, row, col0);
+          } else {
+            if (pz == 0) panel64m(R[0], R[1], R[2], R[3], h ? mw2[4] : mw2[0], h ? mw2[5] : mw2[1], stage);
+            else panel64m(R[4], R[5], R[6], R[7], h ? mw2[6] : mw2[2], h ? mw2[7] : mw2[3], stage);
+          }
           fence_proxy_async();
           __syncwarp();
+          if constexpr (MODE == 1) {
+            float s0 = 0.f, s1 = 0.f;
+            panel_colsum(stage, s0, s1);
+            if (h == 0) { cs2[pz][0] += s0; cs2[pz][1] += s1; } else { cs2[2 + pz][0] += s0; cs2[2 + pz][1] += s1; }
+          }
           if (lane == 0 && row0 < g.M) {
             tma_store_2d(stage, &tmH2, col0, row0);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -324,11 +402,35 @@ cnet_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmCol, const __grid_co
       }
       tile_ph ^= 1;
     }
+    if constexpr (MODE == 1) {   // one atomic per column pair, accumulator and CTA
+      const int cpair = (lane >> 2) * 8 + (lane & 3) * 2;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int c1 = (4 * (i >> 1) + 2 * (i & 1) + hf) * 64 + cpair;
+        const int c2 = (i >> 1) * 256 + hf * 128 + (i & 1) * 64 + cpair;
+        if (g.colsum1) { atomicAdd(g.colsum1 + c1, cs1[i][0]); atomicAdd(g.colsum1 + c1 + 1, cs1[i][1]); }
+        if (g.colsum2) { atomicAdd(g.colsum2 + c2, cs2[i][0]); atomicAdd(g.colsum2 + c2 + 1, cs2[i][1]); }
+      }
+    }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
   tc_fence_before();
   cluster_sync_all();
   if (warp == 1) tmem_dealloc_pair(tmem_base, 512);
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CF_THREADS, 1)
+cnet_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmCol, const __grid_constant__ CUtensorMap tmB1,
+                      const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmH1,
+                      const __grid_constant__ CUtensorMap tmH2, const CnetArgs g) {
+  cnet_fused_body<0>(tmCol, tmB1, tmB2, tmH1, tmH2, g);
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CF_THREADS, 1)
+cnet_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmCol, const __grid_constant__ CUtensorMap tmB1,
+                      const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmH1,
+                      const __grid_constant__ CUtensorMap tmH2, const CnetArgs g) {
+  cnet_fused_body<1>(tmCol, tmB1, tmB2, tmH1, tmH2, g);
 }
 
 typedef CUresult (*EncodeTiledFn2)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -383,7 +485,7 @@ extern "C" int nfk_cnet_fwd_fused_ranged(const void* col, int K1p, const void* B
   if (!col || !B1 || !B2 || !bias1 || !bias2 || !h2) return NFK_ERR_ARG;
   if ((mask1 || mask2) && ldmask < M) return NFK_ERR_ARG;
   CnetArgs g{M, K1p / 64, bias1, bias2, static_cast<uint32_t*>(mask1), static_cast<uint32_t*>(mask2), ldmask,
-             h1 ? 1 : 0, g_cnet_prof, {kb2_end_half0, 8}};
+             h1 ? 1 : 0, g_cnet_prof, {kb2_end_half0, 8}, nullptr, nullptr};
   CUtensorMap tmCol, tmB1, tmB2, tmH1, tmH2;
   int rc;
   if ((rc = cf_tmap(&tmCol, col, K1p, M, K1p, 128, false))) return rc;
@@ -400,5 +502,31 @@ extern "C" int nfk_cnet_fwd_fused_ranged(const void* col, int K1p, const void* B
   const int pairs = tiles < sms / 2 ? tiles : sms / 2;
   const cudaError_t le = launch_pdl(cnet_fwd_fused_kernel, dim3(2 * pairs), dim3(CF_THREADS), CnetSmem::total,
                                     static_cast<cudaStream_t>(stream), tmCol, tmB1, tmB2, tmH1, tmH2, g);
+  return (le == cudaSuccess && cudaGetLastError() == cudaSuccess) ? NFK_OK : NFK_ERR_LAUNCH;
+}
+
+extern "C" int nfk_cnet_bwd_fused(const void* dhcol, int K3p, const void* B3T, const void* B2T, const void* mask_h2,
+                                  const void* mask_h1, long long ldmask, void* dpre2, void* dpre1, float* dbias2,
+                                  float* dbias1, int M, int hid, void* stream) {
+  if (M <= 0 || hid != CF_HID || K3p % 64 || K3p < 64 || K3p > 512) return NFK_ERR_SHAPE;
+  if (!dhcol || !B3T || !B2T || !mask_h2 || !mask_h1 || !dpre2 || !dpre1) return NFK_ERR_ARG;
+  if (ldmask < M) return NFK_ERR_ARG;
+  CnetArgs g{M, K3p / 64, nullptr, nullptr, static_cast<uint32_t*>(const_cast<void*>(mask_h2)),
+             static_cast<uint32_t*>(const_cast<void*>(mask_h1)), ldmask, 1, nullptr, {8, 8}, dbias2, dbias1};
+  CUtensorMap tmA, tmB1, tmB2, tmD2, tmD1;
+  int rc;
+  if ((rc = cf_tmap(&tmA, dhcol, K3p, M, K3p, 128, false))) return rc;
+  if ((rc = cf_tmap(&tmB1, B3T, K3p, hid, K3p, 128, false))) return rc;
+  if ((rc = cf_tmap(&tmB2, B2T, hid, hid, hid, 128, false))) return rc;
+  if ((rc = cf_tmap(&tmD2, dpre2, hid, M, hid, 32, false))) return rc;
+  if ((rc = cf_tmap(&tmD1, dpre1, hid, M, hid, 32, false))) return rc;
+  if ((rc = ensure_dyn_smem(reinterpret_cast<const void*>(cnet_bwd_fused_kernel), CnetSmem::total))) return rc;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int tiles = (M + 255) / 256;
+  const int pairs = tiles < sms / 2 ? tiles : sms / 2;
+  const cudaError_t le = launch_pdl(cnet_bwd_fused_kernel, dim3(2 * pairs), dim3(CF_THREADS), CnetSmem::total,
+                                    static_cast<cudaStream_t>(stream), tmA, tmB1, tmB2, tmD2, tmD1, g);
   return (le == cudaSuccess && cudaGetLastError() == cudaSuccess) ? NFK_OK : NFK_ERR_LAUNCH;
 }

@@ -17,6 +17,7 @@ BF16 = torch.bfloat16
 F32 = torch.float32
 USE_FUSED_CNET = os.environ.get("NFK_FUSED_CNET", "1") != "0"
 USE_FUSED_PCONV = os.environ.get("NFK_FUSED_PCONV", "1") != "0"
+USE_FUSED_CNET_BWD = os.environ.get("NFK_FUSED_CNET_BWD", "1") != "0"
 
 # ------------------------------------------------------------------------------------------------ parameter epoch
 # The no-grad paths cache operands derived from the parameters (fused affine, folded bf16 conv weights, packed MLP /
@@ -378,10 +379,14 @@ class FlowStep2dFn(torch.autograd.Function):
         dhcol = torch.empty(M, K3p, device=dev, dtype=BF16)
         ops.coupling_bwd(g_out, g_ld, z_out, hsave, dy, dhcol, K3p, dbias3, B, C, H, W)
         dpre2 = torch.empty(M, hid, device=dev, dtype=BF16)
-        ops.gemm_nt(dhcol, B3T, M, hid, K3p, ops.EPI_MASK_BF16, dpre2, aux=m2, colsum=dbias2)
-        ops.gemm_tn(dhcol, h2, K3p, hid, M, dB3)
         dpre1 = torch.empty(M, hid, device=dev, dtype=BF16)
-        ops.gemm_nt(dpre2, B2T, M, hid, hid, ops.EPI_MASK_BF16, dpre1, aux=m1, colsum=dbias1)
+        if USE_FUSED_CNET_BWD and ops.cnet_fused_supported(hid, K3p) and M >= 8192:
+            # both dgrads of the chain in ONE kernel: dpre2 stays in shared memory as the second GEMM's A operand
+            ops.cnet_bwd_fused(dhcol, K3p, B3T, B2T, m2, m1, dpre2, dpre1, dbias2, dbias1, M, hid)
+        else:
+            ops.gemm_nt(dhcol, B3T, M, hid, K3p, ops.EPI_MASK_BF16, dpre2, aux=m2, colsum=dbias2)
+            ops.gemm_nt(dpre2, B2T, M, hid, hid, ops.EPI_MASK_BF16, dpre1, aux=m1, colsum=dbias1)
+        ops.gemm_tn(dhcol, h2, K3p, hid, M, dB3)
         ops.gemm_tn(dpre2, h1, hid, hid, M, dB2)
         dcol = torch.empty(M, K1p, device=dev, dtype=F32)
         ops.gemm_nt(dpre1, B1T, M, K1p, hid, ops.EPI_F32, dcol)

@@ -455,3 +455,10 @@ def adam_step(p, g, m, v, partials, step, max_norm, lr, beta1, beta2, eps, weigh
     check(LIB.nfk_adam_step(_p(p), _p(g), _p(m), _p(v), p.numel(), _p(partials), _p(step), float(max_norm), float(lr),
                             float(beta1), float(beta2), float(eps), float(weight_decay), int(adamax), _p(norm_out),
                             _st()), "nfk_adam_step")
+
+
+def cnet_bwd_fused(dhcol, K3p, B3T, B2T, mask_h2, mask_h1, dpre2, dpre1, dbias2, dbias1, M, hid):
+    """Both dgrads of the coupling net's backward chain in one kernel (include/nfk.h: nfk_cnet_bwd_fused)."""
+    _count()
+    check(LIB.nfk_cnet_bwd_fused(_p(dhcol), K3p, _p(B3T), _p(B2T), _p(mask_h2), _p(mask_h1), mask_h2.stride(0),
+                                 _p(dpre2), _p(dpre1), _p(dbias2), _p(dbias1), M, hid, _st()), "nfk_cnet_bwd_fused")

@@ -581,3 +581,29 @@ def test_pipelined_trainer_makes_the_same_updates_as_the_sequential_one(use_grap
             tot += d.numel()
             assert d.max().item() <= 2.1 * lr * steps, k
     assert bad <= 1e-2 * tot, (bad, tot)
+
+
+@pytest.mark.parametrize("M,K3p", [(8192, 128), (8200, 256), (33000, 448), (65536, 128)])
+def test_cnet_bwd_fused_kernel_matches_the_two_masked_gemms(M, K3p):
+    """csrc/cnet_fused.cu in backward mode (both dgrads of the coupling net's chain in one kernel) against the two
+    tcgen05 GEMMs with the ReLU-mask epilogue it replaces: same bf16 products, same k-block order -> dpre2 and dpre1
+    identical bit for bit (ragged M included); the bias-gradient column sums agree to fp32 summation order."""
+    from nf_distillation_b200 import ops
+    hid = 512
+    g = torch.Generator(device=dev).manual_seed(M + K3p)
+    dhcol = (torch.randn(M, K3p, device=dev, generator=g) * 0.5).bfloat16()
+    B3T = (torch.randn(hid, K3p, device=dev, generator=g) * 0.1).bfloat16()
+    B2T = (torch.randn(hid, hid, device=dev, generator=g) * 0.05).bfloat16()
+    m2 = torch.randint(-2 ** 31, 2 ** 31 - 1, (hid // 32, M), device=dev, generator=g, dtype=torch.int32)
+    m1 = torch.randint(-2 ** 31, 2 ** 31 - 1, (hid // 32, M), device=dev, generator=g, dtype=torch.int32)
+    d2a, d1a = torch.empty(M, hid, device=dev, dtype=torch.bfloat16), torch.empty(M, hid, device=dev, dtype=torch.bfloat16)
+    b2a, b1a = torch.zeros(hid, device=dev), torch.zeros(hid, device=dev)
+    ops.gemm_nt(dhcol, B3T, M, hid, K3p, ops.EPI_MASK_BF16, d2a, aux=m2, colsum=b2a)
+    ops.gemm_nt(d2a, B2T, M, hid, hid, ops.EPI_MASK_BF16, d1a, aux=m1, colsum=b1a)
+    d2b, d1b = torch.full_like(d2a, float("nan")), torch.full_like(d1a, float("nan"))
+    b2b, b1b = torch.zeros(hid, device=dev), torch.zeros(hid, device=dev)
+    ops.cnet_bwd_fused(dhcol, K3p, B3T, B2T, m2, m1, d2b, d1b, b2b, b1b, M, hid)
+    assert torch.equal(d2a, d2b) and torch.equal(d1a, d1b)
+    assert rel(b2b, b2a) < 1e-5 and rel(b1b, b1a) < 1e-5
+    ref = (dhcol.float() @ B3T.float().T) * unpack_mask(m2, hid)
+    assert rel(d2b, ref.bfloat16()) < 1e-2 and rel(b2b, d2b.float().sum(0)) < 1e-5

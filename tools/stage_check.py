@@ -88,15 +88,20 @@ def run(C, H, B, hid=512):
         dhcol_r = torch.stack(cols, 1).permute(0, 3, 4, 1, 2).reshape(M, 9 * C)
         stats("dhcol", dhcol[:, :9 * C], dhcol_r.to(BF), bf16=True)
         dpre2 = torch.empty(M, hid, device=dev, dtype=BF); dbias2 = torch.zeros(hid, device=dev)
-        ops.gemm_nt(dhcol, k.B3T, M, hid, K3p, ops.EPI_MASK_BF16, dpre2, aux=m2, colsum=dbias2)
+        dpre1 = torch.empty(M, hid, device=dev, dtype=BF); dbias1 = torch.zeros(hid, device=dev)
+        fused_bwd = Fn.USE_FUSED_CNET_BWD and ops.cnet_fused_supported(hid, K3p) and M >= 8192
+        if fused_bwd:     # the path FlowStep2dFn.backward takes at this size: both dgrads in one kernel
+            ops.cnet_bwd_fused(dhcol, K3p, k.B3T, k.B2T, m2, m1, dpre2, dpre1, dbias2, dbias1, M, hid)
+        else:
+            ops.gemm_nt(dhcol, k.B3T, M, hid, K3p, ops.EPI_MASK_BF16, dpre2, aux=m2, colsum=dbias2)
         dpre2_r = ((dhcol.float() @ k.B3T.float().T) * (h2 > 0)).to(BF)
         stats("dpre2", dpre2, dpre2_r, bf16=True)
         stats("dbias2", dbias2, dpre2.float().sum(0))
         stats("B3T==B3^T", k.B3T, k.B3.T)
         dB3 = torch.zeros(K3p, hid, device=dev); ops.gemm_tn(dhcol, h2, K3p, hid, M, dB3)
         stats("dB3", dB3, dhcol.float().T @ h2.float())
-        dpre1 = torch.empty(M, hid, device=dev, dtype=BF); dbias1 = torch.zeros(hid, device=dev)
-        ops.gemm_nt(dpre2, k.B2T, M, hid, hid, ops.EPI_MASK_BF16, dpre1, aux=m1, colsum=dbias1)
+        if not fused_bwd:
+            ops.gemm_nt(dpre2, k.B2T, M, hid, hid, ops.EPI_MASK_BF16, dpre1, aux=m1, colsum=dbias1)
         dpre1_r = ((dpre2.float() @ k.B2T.float().T) * (h1 > 0)).to(BF)
         stats("dpre1", dpre1, dpre1_r, bf16=True)
         stats("dbias1", dbias1, dpre1.float().sum(0))

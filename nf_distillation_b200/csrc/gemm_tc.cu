@@ -566,6 +566,118 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 1) tmem_dealloc(tmem_base, ncols);
 }
 
+// ------------------------------------------------------------------------------------------------ TN kernel, CTA pairs
+// Same contraction on cta_group::2: one 256 x BN output tile per PAIR of SMs (M = 256 rows = channels of A, 128 per
+// CTA; the BN columns of B are split, BN/2 per CTA). Per k-block of 64 pixels a CTA now stages 16 KB of A and
+// BN/2 * 128 B of B for a 128 x BN x 64 share of the MMAs: half the shared-memory fill and half the B-operand reads per
+// FLOP of the single-CTA 128 x BN tile, which is shared-memory-bandwidth bound (94 B/clk of fills + 94 B/clk of operand
+// reads against 128 B/clk: 0.68 of the tensor peak, measured 0.64-0.68). Used when Mo % 256 == 0-ish and BN >= 128.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TN_THREADS, 1)
+gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const GemmArgs g) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  pdl_launch_dependents();
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  constexpr int BOX = 64 * 128;          // one TMA box: 64 pixel rows x 64 channels (128 B)
+  const int a_bytes = 2 * BOX;           // this CTA's 128 rows of the tile
+  const int nb_boxes = g.BN / 128;       // this CTA's BN/2 columns of B, 64 per box
+  const int stage_bytes = a_bytes + nb_boxes * BOX;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + g.stages * stage_bytes);   // (leader's copy collects both CTAs' bytes)
+  uint64_t* empty = full + g.stages;
+  uint64_t* tmem_full = empty + g.stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int pair = blockIdx.x >> 1;
+  const int n_tile = pair % g.n_tiles;
+  const int m_tile = pair / g.n_tiles;
+  const int total_kb = (g.K + BK - 1) / BK;
+  const int kb0 = blockIdx.y * g.kb_per_split;
+  const int kb1 = min(kb0 + g.kb_per_split, total_kb);
+  const int num_kb = kb1 - kb0;           // (the host sizes the splits so that no pair is empty)
+  const uint32_t ncols = tmem_cols_pow2(g.BN);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < g.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(tmem_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) { tmem_alloc_pair(tmem_slot, ncols); tmem_relinquish_pair(); }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      const int m0 = m_tile * 2 * BM + static_cast<int>(rank) * BM;
+      const int n0 = n_tile * g.BN + static_cast<int>(rank) * (g.BN / 2);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&empty[s], ph ^ 1);
+        uint8_t* sa = smem + s * stage_bytes;
+        if (rank == 0) mbar_expect_tx(&full[s], 2 * stage_bytes);
+        tma_load_2d_pair(sa, &tmA, &full[s], m0, kb * BK);
+        tma_load_2d_pair(sa + BOX, &tmA, &full[s], m0 + 64, kb * BK);
+        for (int j = 0; j < nb_boxes; ++j)
+          tma_load_2d_pair(sa + a_bytes + j * BOX, &tmB, &full[s], n0 + j * 64, kb * BK);
+        if (++s == g.stages) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc = umma_idesc_bf16(2 * BM, g.BN, true, true);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int i = 0; i < num_kb; ++i) {
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
+        const uint32_t b_addr = a_addr + a_bytes;
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k) {
+          const uint64_t ad = umma_desc_sw128(a_addr + k * (UMMA_K * 128), BOX, 1024);
+          const uint64_t bd = umma_desc_sw128(b_addr + k * (UMMA_K * 128), BOX, 1024);
+          umma_f16_pair(tmem_base, ad, bd, idesc, (i | k) != 0 ? 1u : 0u);
+        }
+        umma_commit_pair(&empty[s], 3);
+        if (++s == g.stages) { s = 0; ph ^= 1; }
+      }
+      umma_commit_pair(tmem_full, 3);
+    }
+  } else {
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const int q = warp & 3;
+    const long long row = static_cast<long long>(m_tile) * 2 * BM + rank * BM + q * 32 + lane;
+    const bool row_ok = row < g.M;
+    for (int c = 0; c < g.BN; c += 16) {
+      uint32_t r[16];
+      tmem_ld16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c, r);
+      tmem_ld_wait();
+      const int col = n_tile * g.BN + c;
+      if (col >= g.N) break;
+      if (row_ok) {
+        float* o = static_cast<float*>(g.out) + row * g.ldo + col;
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + j), "f"(__uint_as_float(r[j])),
+                       "f"(__uint_as_float(r[j + 1])), "f"(__uint_as_float(r[j + 2])), "f"(__uint_as_float(r[j + 3]))
+                       : "memory");
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) tmem_dealloc_pair(tmem_base, ncols);
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -767,12 +879,35 @@ extern "C" int nfk_gemm_tn_bf16(const void* A, long long lda, const void* B, lon
   g.M = Mo; g.N = No; g.K = Kpix;
   g.BN = No <= 256 ? No : (No % 256 == 0 ? 256 : (No % 192 == 0 ? 192 : (No % 128 == 0 ? 128 : 64)));
   g.n_tiles = (No + g.BN - 1) / g.BN;
+  if (sm_count <= 0) sm_count = 148;
+  // CTA pairs (256-row tiles) when the output is tall and wide enough to fill them: conv#2 weight gradients (512 x 512)
+  // and the deeper levels' Conv2dZeros ones; the narrow ones (64 / 128 wide) are HBM-bound and stay on single CTAs
+  static const bool tn_pairs = [] { const char* e = getenv("NFK_TN_PAIRS"); return !(e && e[0] == '0'); }();
+  if (tn_pairs && Mo > BM && g.BN % 128 == 0 && Kpix >= 4096) {
+    const int m_tiles2 = (Mo + 2 * BM - 1) / (2 * BM);
+    const int ptiles = m_tiles2 * g.n_tiles;
+    const int total_kb2 = (Kpix + BK - 1) / BK;
+    int psplits = max(1, min(total_kb2, (sm_count / 2) / ptiles));
+    g.kb_per_split = (total_kb2 + psplits - 1) / psplits;
+    psplits = (total_kb2 + g.kb_per_split - 1) / g.kb_per_split;
+    const int pstage = 2 * 64 * 128 + (g.BN / 128) * 64 * 128;
+    g.stages = min(8, (196 * 1024) / pstage);
+    g.out = out; g.ldo = ldo;
+    CUtensorMap ptmA, ptmB;
+    int prc;
+    if ((prc = make_tmap_bf16(&ptmA, A, Mo, Kpix, lda, 64)) != NFK_OK) return prc;
+    if ((prc = make_tmap_bf16(&ptmB, B, No, Kpix, ldb, 64)) != NFK_OK) return prc;
+    const int psmem = g.stages * pstage + 1024 + 256;
+    if ((prc = set_smem(gemm_tn_pair_kernel, psmem))) return prc;
+    const cudaError_t ple = launch_pdl(gemm_tn_pair_kernel, dim3(2 * ptiles, psplits), dim3(TN_THREADS), psmem,
+                                       static_cast<cudaStream_t>(stream), ptmA, ptmB, g);
+    return (ple == cudaSuccess && cudaGetLastError() == cudaSuccess) ? NFK_OK : NFK_ERR_LAUNCH;
+  }
   const int stage_bytes = 2 * 64 * 128 + (g.BN / 64) * 64 * 128;
   g.stages = min(8, (196 * 1024) / stage_bytes);
   g.out = out; g.ldo = ldo;
   const int tiles = ((Mo + BM - 1) / BM) * g.n_tiles;
   const int total_kb = (Kpix + BK - 1) / BK;
-  if (sm_count <= 0) sm_count = 148;
   // one wave: tiles * splits <= SMs (one CTA per SM; 152 CTAs on 148 SMs would run as two waves at half the speed)
   int splits = max(1, min(total_kb, sm_count / tiles));
   g.kb_per_split = (total_kb + splits - 1) / splits;

@@ -235,7 +235,7 @@ def kernel_table(B, H, W, C_img, hid, device):
     dpre = [(torch.randn(M, hid, device=device) * 0.1).to(bf16) for _ in range(nb)]
     dW = torch.zeros(hid, hid, device=device)
     us = time_graph(lambda i: ops.gemm_tn(dpre[i], h2[i], hid, hid, M, dW), 10, nb) * 1e3
-    add("gemm_tn_kernel (conv#2 weight gradient, split-K)", "tensor", 2.0 * M * hid * hid, us)
+    add("gemm_tn_pair_kernel (conv#2 weight gradient, split-K over pixels, cta_group::2)", "tensor", 2.0 * M * hid * hid, us)
     W2T = (torch.randn(hid, hid, device=device) * 0.05).to(bf16)
     mask = ops.relu_mask_like(M, hid, device)
     mask.fill_(-1)

@@ -237,14 +237,23 @@ def kernel_table(B, H, W, C_img, hid, device):
     us = time_graph(lambda i: ops.gemm_tn(dpre[i], h2[i], hid, hid, M, dW), 10, nb) * 1e3
     add("gemm_tn_pair_kernel (conv#2 weight gradient, split-K over pixels, cta_group::2)", "tensor", 2.0 * M * hid * hid, us)
     W2T = (torch.randn(hid, hid, device=device) * 0.05).to(bf16)
+    W3T = (torch.randn(hid, K3p, device=device) * 0.05).to(bf16)
     mask = ops.relu_mask_like(M, hid, device)
     mask.fill_(-1)
-    cs = torch.zeros(hid, device=device)
+    cs, cs2 = torch.zeros(hid, device=device), torch.zeros(hid, device=device)
     outs = [torch.empty(M, hid, device=device, dtype=bf16) for _ in range(nb)]
-    us = time_graph(lambda i: ops.gemm_nt(dpre[i], W2T, M, hid, hid, ops.EPI_MASK_BF16, outs[i], aux=mask, colsum=cs),
-                    10, nb) * 1e3
-    add("gemm_nt_pair_kernel<MASK_BF16> (conv#2 input gradient + ReLU mask + bias gradient)", "tensor",
-        2.0 * M * hid * hid, us)
+    if ops.cnet_fused_supported(hid, K3p) and M >= 8192:
+        dhc_ = [(torch.randn(M, K3p, device=device) * 0.1).to(bf16) for _ in range(nb)]
+        us = time_graph(lambda i: ops.cnet_bwd_fused(dhc_[i], K3p, W3T, W2T, mask, mask, dpre[i], outs[i], cs, cs2, M,
+                                                     hid), 10, nb) * 1e3
+        add("cnet_bwd_fused_kernel (Conv2dZeros dgrad -> ReLU mask -> conv1x1 dgrad -> ReLU mask + both bias gradients)",
+            "tensor", 2.0 * M * hid * (9 * C + hid), us)
+        del dhc_
+    else:
+        us = time_graph(lambda i: ops.gemm_nt(dpre[i], W2T, M, hid, hid, ops.EPI_MASK_BF16, outs[i], aux=mask,
+                                              colsum=cs), 10, nb) * 1e3
+        add("gemm_nt_pair_kernel<MASK_BF16> (conv#2 input gradient + ReLU mask + bias gradient)", "tensor",
+            2.0 * M * hid * hid, us)
     del h2, dpre, outs, mask
     hsv = [torch.randn(M, C, device=device) for _ in range(nb)]
     dys = [torch.empty(B, C, Hs, Ws, device=device) for _ in range(nb)]

@@ -16,6 +16,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <cstdlib>
 
 #include "../../include/nfk.h"
 #include "launch_util.h"
@@ -74,8 +75,8 @@ __device__ __forceinline__ void cnet_fused_body(const CUtensorMap& tmCol, const 
   extern __shared__ __align__(1024) uint8_t smem[];
   pdl_launch_dependents();
   if (smem_u32(smem) & 1023u) __trap();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
+  const int warp = static_cast<int>(uniform_u32(threadIdx.x >> 5)), lane = threadIdx.x & 31;
+  const uint32_t rank = blockIdx.x & 1;      // == %cluster_ctarank for (2,1,1) clusters on a 1-D grid, provably uniform
   const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
   const int num_tiles = (g.M + 255) / 256;
 
@@ -99,17 +100,17 @@ __device__ __forceinline__ void cnet_fused_body(const CUtensorMap& tmCol, const 
   tc_fence_before();
   cluster_sync_all();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = uniform_u32(*tmem_slot);
   pdl_wait();      // the prologue above overlapped the previous kernel's tail; global memory only from here on
 
   if (warp == 0) {
     // ===================================================== TMA producer (both CTAs; bytes land on the leader's barrier)
-    if (lane == 0) {
+    {   // whole warp, uniform control flow; single-thread instructions elected inside the asm (ptx.cuh)
       int s = 0; uint32_t ph = 0;
       auto load = [&](const CUtensorMap* tm, int c0, int c1) {
-        mbar_wait(&empty[s], ph ^ 1);
-        if (rank == 0) mbar_expect_tx(&full[s], 2 * CF_SLOT);
-        tma_load_2d_pair(smem + CnetSmem::ring + s * CF_SLOT, tm, &full[s], c0, c1);
+        mbar_wait_warp(&empty[s], ph ^ 1);
+        if (rank == 0) mbar_expect_tx_elect(&full[s], 2 * CF_SLOT);
+        tma_load_2d_pair_elect(smem + CnetSmem::ring + s * CF_SLOT, tm, &full[s], c0, c1);
         if (++s == CF_SLOTS) { s = 0; ph ^= 1; }
       };
       for (int t = pair; t < num_tiles; t += num_pairs) {
@@ -124,8 +125,8 @@ __device__ __forceinline__ void cnet_fused_body(const CUtensorMap& tmCol, const 
       }
     }
   } else if (warp == 1) {
-    // ===================================================== MMA issuer (leader CTA, one thread)
-    if (lane == 0 && rank == 0) {
+    // ===================================================== MMA issuer (leader CTA; whole warp, uniform control flow)
+    if (rank == 0) {
       const uint32_t idesc = umma_idesc_bf16(256, 256, false, false);
       const uint32_t ring_addr = smem_u32(smem + CnetSmem::ring);
       const uint32_t h1_addr = smem_u32(smem + CnetSmem::h1);
@@ -136,22 +137,22 @@ __device__ __forceinline__ void cnet_fused_body(const CUtensorMap& tmCol, const 
       const long long t_begin = g.prof ? clock64() : 0;
       auto take = [&]() {
         const long long c0 = g.prof ? clock64() : 0;
-        mbar_wait(&full[s], ph);
+        mbar_wait_warp(&full[s], ph);
         if (g.prof) w_op += clock64() - c0;
         tc_fence_after();
         return ring_addr + s * CF_SLOT;
       };
       auto advance = [&]() { if (++s == CF_SLOTS) { s = 0; ph ^= 1; } };
-      auto release = [&]() { umma_commit_pair(&empty[s], 3); advance(); };
+      auto release = [&]() { umma_commit_pair_elect(&empty[s], 3); advance(); };
       auto acc_begin = [&]() {
         const uint32_t st = nacc & 1;
         const long long c0 = g.prof ? clock64() : 0;
-        mbar_wait(&acc_empty[st], ((nacc >> 1) & 1) ^ 1);
+        mbar_wait_warp(&acc_empty[st], ((nacc >> 1) & 1) ^ 1);
         if (g.prof) w_acc += clock64() - c0;
         tc_fence_after();
         return tmem_base + st * 256;
       };
-      auto acc_end = [&]() { umma_commit_pair(&acc_full[nacc & 1], 3); ++nacc; };
+      auto acc_end = [&]() { umma_commit_pair_elect(&acc_full[nacc & 1], 3); ++nacc; };
       for (int t = pair; t < num_tiles; t += num_pairs) {
         // ---- conv#1: two 256-channel halves; each k-step consumes two slots (im2col tile, B1 tile)
         for (int h = 0; h < 2; ++h) {
@@ -163,9 +164,9 @@ __device__ __forceinline__ void cnet_fused_body(const CUtensorMap& tmCol, const 
             const uint32_t b = take();
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              umma_f16_pair(d, umma_desc_sw128(a + k * 32, 16, 1024), umma_desc_sw128(b + k * 32, 16, 1024), idesc,
+              umma_f16_pair_elect(d, umma_desc_sw128(a + k * 32, 16, 1024), umma_desc_sw128(b + k * 32, 16, 1024), idesc,
                             (kb > 0 || k > 0) ? 1u : 0u);
-            umma_commit_pair(&empty[sa], 3);
+            umma_commit_pair_elect(&empty[sa], 3);
             release();
           }
           acc_end();
@@ -178,7 +179,7 @@ __device__ __forceinline__ void cnet_fused_body(const CUtensorMap& tmCol, const 
           for (int kb = 0; kb < g.kb2_end[h]; ++kb) {
             if (kb >= panels_seen) {
               const long long c0 = g.prof ? clock64() : 0;
-              mbar_wait(&h1_full[kb], tile_ph);
+              mbar_wait_warp(&h1_full[kb], tile_ph);
               if (g.prof) w_h1 += clock64() - c0;
               tc_fence_after();
               panels_seen = kb + 1;
@@ -186,16 +187,16 @@ __device__ __forceinline__ void cnet_fused_body(const CUtensorMap& tmCol, const 
             const uint32_t b = take();
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              umma_f16_pair(d, umma_desc_sw128(h1_addr + kb * CF_PANEL + k * 32, 16, 1024),
+              umma_f16_pair_elect(d, umma_desc_sw128(h1_addr + kb * CF_PANEL + k * 32, 16, 1024),
                             umma_desc_sw128(b + k * 32, 16, 1024), idesc, (kb > 0 || k > 0) ? 1u : 0u);
             release();
           }
           acc_end();
         }
-        umma_commit_pair(h1_empty, 3);      // h1 is free once every MMA issued so far has retired
+        umma_commit_pair_elect(h1_empty, 3);      // h1 is free once every MMA issued so far has retired
         tile_ph ^= 1;
       }
-      if (g.prof) {
+      if (g.prof && lane == 0) {
         long long* o = g.prof + blockIdx.x * 8;
         o[0] = clock64() - t_begin; o[1] = w_op; o[2] = w_acc; o[3] = w_h1;
       }
@@ -461,6 +462,19 @@ static int cf_tmap(CUtensorMap* m, const void* ptr, uint64_t cols, uint64_t rows
              : NFK_ERR_DRIVER;
 }
 
+// cnet_ts.cu: the same two GEMMs with h1 resident in tensor memory (A operand of conv#2 read from TMEM). Default path;
+// NFK_CNET_TS=0 in the environment selects the shared-memory-panel kernels of this file instead.
+int cnet_ts_fwd(const void* col, int K1p, const void* B1, const void* B2, const float* bias1, const float* bias2,
+                void* h1, void* h2, void* mask1, void* mask2, long long ldmask, int M, int kb2_end_half0,
+                long long* prof, void* stream);
+int cnet_ts_bwd(const void* dhcol, int K3p, const void* B3T, const void* B2T, const void* mask_h2,
+                const void* mask_h1, long long ldmask, void* dpre2, void* dpre1, float* dbias2, float* dbias1, int M,
+                void* stream);
+static bool cnet_use_ts() {
+  static const bool v = [] { const char* e = getenv("NFK_CNET_TS"); return !(e && e[0] == '0'); }();
+  return v;
+}
+
 }  // namespace nfk
 
 using namespace nfk;
@@ -484,6 +498,9 @@ extern "C" int nfk_cnet_fwd_fused_ranged(const void* col, int K1p, const void* B
   if (kb2_end_half0 < 1 || kb2_end_half0 > 8) return NFK_ERR_ARG;
   if (!col || !B1 || !B2 || !bias1 || !bias2 || !h2) return NFK_ERR_ARG;
   if ((mask1 || mask2) && ldmask < M) return NFK_ERR_ARG;
+  if (cnet_use_ts())
+    return cnet_ts_fwd(col, K1p, B1, B2, bias1, bias2, h1, h2, mask1, mask2, ldmask, M, kb2_end_half0, g_cnet_prof,
+                       stream);
   CnetArgs g{M, K1p / 64, bias1, bias2, static_cast<uint32_t*>(mask1), static_cast<uint32_t*>(mask2), ldmask,
              h1 ? 1 : 0, g_cnet_prof, {kb2_end_half0, 8}, nullptr, nullptr};
   CUtensorMap tmCol, tmB1, tmB2, tmH1, tmH2;
@@ -511,6 +528,8 @@ extern "C" int nfk_cnet_bwd_fused(const void* dhcol, int K3p, const void* B3T, c
   if (M <= 0 || hid != CF_HID || K3p % 64 || K3p < 64 || K3p > 512) return NFK_ERR_SHAPE;
   if (!dhcol || !B3T || !B2T || !mask_h2 || !mask_h1 || !dpre2 || !dpre1) return NFK_ERR_ARG;
   if (ldmask < M) return NFK_ERR_ARG;
+  if (cnet_use_ts())
+    return cnet_ts_bwd(dhcol, K3p, B3T, B2T, mask_h2, mask_h1, ldmask, dpre2, dpre1, dbias2, dbias1, M, stream);
   CnetArgs g{M, K3p / 64, nullptr, nullptr, static_cast<uint32_t*>(const_cast<void*>(mask_h2)),
              static_cast<uint32_t*>(const_cast<void*>(mask_h1)), ldmask, 1, nullptr, {8, 8}, dbias2, dbias1};
   CUtensorMap tmA, tmB1, tmB2, tmD2, tmD1;

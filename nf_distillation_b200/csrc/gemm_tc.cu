@@ -156,7 +156,7 @@ __device__ __forceinline__ void gemm_nt_body(const CUtensorMap& tmA, const CUten
   pdl_launch_dependents();
   uint8_t* smem = smem_raw;   // 1024-byte aligned (no static shared memory in this kernel): SWIZZLE_128B requirement
   if (smem_u32(smem) & 1023u) __trap();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = static_cast<int>(uniform_u32(threadIdx.x >> 5)), lane = threadIdx.x & 31;
   const int a_bytes = BM * 128;
   const int b_bytes = (PAIR ? g.BN / 2 : g.BN) * 128;
   const int stage_bytes = a_bytes + b_bytes;
@@ -168,7 +168,7 @@ __device__ __forceinline__ void gemm_nt_body(const CUtensorMap& tmA, const CUten
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   float* bias_s = reinterpret_cast<float*>(tmem_slot + 4);  // [2][256] (one per accumulator stage)
 
-  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const uint32_t rank = PAIR ? (blockIdx.x & 1u) : 0u;   // == %cluster_ctarank ((2,1,1) clusters along x), provably uniform
   const int worker = PAIR ? (blockIdx.x >> 1) : blockIdx.x;
   const int num_workers = PAIR ? (gridDim.x >> 1) : gridDim.x;
   constexpr int TM = PAIR ? 2 * BM : BM;    // tile rows
@@ -198,35 +198,35 @@ __device__ __forceinline__ void gemm_nt_body(const CUtensorMap& tmA, const CUten
   tc_fence_before();
   if constexpr (PAIR) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = uniform_u32(*tmem_slot);
   pdl_wait();      // prologue overlapped the previous kernel's tail; global memory only from here on
 
   if (warp == 0) {
-    if (lane == 0) {
+    {   // whole warp, uniform control flow: single-thread instructions are elected inside the asm (ptx.cuh)
       int s = 0;
       uint32_t ph = 0;
       for (int t = worker; t < num_tiles; t += num_workers) {
         const int n_tile = t % g.n_tiles, m_tile = t / g.n_tiles;
         const int kb0 = g.kb_begin[n_tile & 15], kb1 = g.kb_end[n_tile & 15] ? g.kb_end[n_tile & 15] : num_kb;
         for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&empty[s], ph ^ 1);
+          mbar_wait_warp(&empty[s], ph ^ 1);
           uint8_t* sa = smem + s * stage_bytes;
           if constexpr (PAIR) {
-            if (rank == 0) mbar_expect_tx(&full[s], 2 * stage_bytes);  // both CTAs' bytes land on the leader's barrier
-            tma_load_2d_pair(sa, &tmA, &full[s], kb * BK, m_tile * TM + static_cast<int>(rank) * BM);
-            tma_load_2d_pair(sa + a_bytes, &tmB, &full[s], kb * BK,
+            if (rank == 0) mbar_expect_tx_elect(&full[s], 2 * stage_bytes);  // both CTAs' bytes land on the leader's barrier
+            tma_load_2d_pair_elect(sa, &tmA, &full[s], kb * BK, m_tile * TM + static_cast<int>(rank) * BM);
+            tma_load_2d_pair_elect(sa + a_bytes, &tmB, &full[s], kb * BK,
                              n_tile * g.BN + static_cast<int>(rank) * (g.BN / 2));
           } else {
-            mbar_expect_tx(&full[s], stage_bytes);
-            tma_load_2d(sa, &tmA, &full[s], kb * BK, m_tile * BM);
-            tma_load_2d(sa + a_bytes, &tmB, &full[s], kb * BK, n_tile * g.BN);
+            mbar_expect_tx_elect(&full[s], stage_bytes);
+            tma_load_2d_elect(sa, &tmA, &full[s], kb * BK, m_tile * BM);
+            tma_load_2d_elect(sa + a_bytes, &tmB, &full[s], kb * BK, n_tile * g.BN);
           }
           if (++s == g.stages) { s = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && rank == 0) {
+    if (rank == 0) {   // whole warp, uniform control flow (ptx.cuh: *_elect)
       const uint32_t idesc = umma_idesc_bf16(TM, g.BN, false, false);
       int s = 0;
       uint32_t ph = 0;
@@ -237,7 +237,7 @@ __device__ __forceinline__ void gemm_nt_body(const CUtensorMap& tmA, const CUten
         const int acc = it & 1;
         const uint32_t acc_ph = (it >> 1) & 1;
         long long t0 = g.prof ? clock64() : 0;
-        mbar_wait(&tmem_empty[acc], acc_ph ^ 1);  // epilogue has drained this accumulator stage
+        mbar_wait_warp(&tmem_empty[acc], acc_ph ^ 1);  // epilogue has drained this accumulator stage
         if (g.prof) { pw_tmem += clock64() - t0; }
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * g.BN;
@@ -245,7 +245,7 @@ __device__ __forceinline__ void gemm_nt_body(const CUtensorMap& tmA, const CUten
         const int kb0 = g.kb_begin[n_tile & 15], kb1 = g.kb_end[n_tile & 15] ? g.kb_end[n_tile & 15] : num_kb;
         for (int kb = kb0; kb < kb1; ++kb) {
           t0 = g.prof ? clock64() : 0;
-          mbar_wait(&full[s], ph);
+          mbar_wait_warp(&full[s], ph);
           if (g.prof) { pw_full += clock64() - t0; }
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
@@ -254,16 +254,16 @@ __device__ __forceinline__ void gemm_nt_body(const CUtensorMap& tmA, const CUten
           for (int k = 0; k < BK / UMMA_K; ++k) {
             const uint64_t ad = umma_desc_sw128(a_addr + k * (UMMA_K * 2), 16, 1024);
             const uint64_t bd = umma_desc_sw128(b_addr + k * (UMMA_K * 2), 16, 1024);
-            if constexpr (PAIR) umma_f16_pair(tmem_d, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-            else umma_f16(tmem_d, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if constexpr (PAIR) umma_f16_pair_elect(tmem_d, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            else umma_f16_elect(tmem_d, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
           // free the smem stage (in both CTAs of a pair) when these MMAs retire
-          if constexpr (PAIR) umma_commit_pair(&empty[s], 3); else umma_commit(&empty[s]);
+          if constexpr (PAIR) umma_commit_pair_elect(&empty[s], 3); else umma_commit_elect(&empty[s]);
           if (++s == g.stages) { s = 0; ph ^= 1; }
         }
-        if constexpr (PAIR) umma_commit_pair(&tmem_full[acc], 3); else umma_commit(&tmem_full[acc]);
+        if constexpr (PAIR) umma_commit_pair_elect(&tmem_full[acc], 3); else umma_commit_elect(&tmem_full[acc]);
       }
-      if (g.prof) {
+      if (g.prof && lane == 0) {
         g.prof[blockIdx.x * 8 + 0] = clock64() - pt0;
         g.prof[blockIdx.x * 8 + 1] = pw_tmem;
         g.prof[blockIdx.x * 8 + 2] = pw_full;
@@ -462,7 +462,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   pdl_launch_dependents();
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = static_cast<int>(uniform_u32(threadIdx.x >> 5)), lane = threadIdx.x & 31;
   constexpr int BOX = 64 * 128;  // one TMA box: 64 pixel rows x 64 channels (128 B)
   const int a_bytes = 2 * BOX;
   const int nb_boxes = g.BN / 64;
@@ -498,31 +498,31 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = uniform_u32(*tmem_slot);
   pdl_wait();
 
   if (warp == 0) {
-    if (lane == 0) {
+    {   // whole warp, uniform control flow: single-thread instructions are elected inside the asm (ptx.cuh)
       int s = 0;
       uint32_t ph = 0;
       for (int kb = kb0; kb < kb1; ++kb) {
-        mbar_wait(&empty[s], ph ^ 1);
+        mbar_wait_warp(&empty[s], ph ^ 1);
         uint8_t* sa = smem + s * stage_bytes;
-        mbar_expect_tx(&full[s], stage_bytes);
-        tma_load_2d(sa, &tmA, &full[s], m_tile * BM, kb * BK);
-        tma_load_2d(sa + BOX, &tmA, &full[s], m_tile * BM + 64, kb * BK);
+        mbar_expect_tx_elect(&full[s], stage_bytes);
+        tma_load_2d_elect(sa, &tmA, &full[s], m_tile * BM, kb * BK);
+        tma_load_2d_elect(sa + BOX, &tmA, &full[s], m_tile * BM + 64, kb * BK);
         for (int j = 0; j < nb_boxes; ++j)
-          tma_load_2d(sa + a_bytes + j * BOX, &tmB, &full[s], n_tile * g.BN + j * 64, kb * BK);
+          tma_load_2d_elect(sa + a_bytes + j * BOX, &tmB, &full[s], n_tile * g.BN + j * 64, kb * BK);
         if (++s == g.stages) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {   // whole warp, uniform control flow: single-thread instructions are elected inside the asm (ptx.cuh)
       const uint32_t idesc = umma_idesc_bf16(BM, g.BN, true, true);
       int s = 0;
       uint32_t ph = 0;
       for (int i = 0; i < num_kb; ++i) {
-        mbar_wait(&full[s], ph);
+        mbar_wait_warp(&full[s], ph);
         tc_fence_after();
         const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
         const uint32_t b_addr = a_addr + a_bytes;
@@ -531,12 +531,12 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           // 16 pixel rows per MMA = two 8-row swizzle groups (SBO = 1024 B); 64-channel blocks are BOX apart (LBO).
           const uint64_t ad = umma_desc_sw128(a_addr + k * (UMMA_K * 128), BOX, 1024);
           const uint64_t bd = umma_desc_sw128(b_addr + k * (UMMA_K * 128), BOX, 1024);
-          umma_f16(tmem_base, ad, bd, idesc, (i | k) != 0 ? 1u : 0u);
+          umma_f16_elect(tmem_base, ad, bd, idesc, (i | k) != 0 ? 1u : 0u);
         }
-        umma_commit(&empty[s]);
+        umma_commit_elect(&empty[s]);
         if (++s == g.stages) { s = 0; ph ^= 1; }
       }
-      umma_commit(tmem_full);
+      umma_commit_elect(tmem_full);
     }
   } else {
     mbar_wait(tmem_full, 0);
@@ -578,8 +578,8 @@ gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   pdl_launch_dependents();
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
+  const int warp = static_cast<int>(uniform_u32(threadIdx.x >> 5)), lane = threadIdx.x & 31;
+  const uint32_t rank = blockIdx.x & 1u;   // == %cluster_ctarank ((2,1,1) clusters along x), provably uniform
   constexpr int BOX = 64 * 128;          // one TMA box: 64 pixel rows x 64 channels (128 B)
   const int a_bytes = 2 * BOX;           // this CTA's 128 rows of the tile
   const int nb_boxes = g.BN / 128;       // this CTA's BN/2 columns of B, 64 per box
@@ -609,33 +609,33 @@ gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   tc_fence_before();
   cluster_sync_all();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = uniform_u32(*tmem_slot);
   pdl_wait();
 
   if (warp == 0) {
-    if (lane == 0) {
+    {   // whole warp, uniform control flow: single-thread instructions are elected inside the asm (ptx.cuh)
       int s = 0;
       uint32_t ph = 0;
       const int m0 = m_tile * 2 * BM + static_cast<int>(rank) * BM;
       const int n0 = n_tile * g.BN + static_cast<int>(rank) * (g.BN / 2);
       for (int kb = kb0; kb < kb1; ++kb) {
-        mbar_wait(&empty[s], ph ^ 1);
+        mbar_wait_warp(&empty[s], ph ^ 1);
         uint8_t* sa = smem + s * stage_bytes;
-        if (rank == 0) mbar_expect_tx(&full[s], 2 * stage_bytes);
-        tma_load_2d_pair(sa, &tmA, &full[s], m0, kb * BK);
-        tma_load_2d_pair(sa + BOX, &tmA, &full[s], m0 + 64, kb * BK);
+        if (rank == 0) mbar_expect_tx_elect(&full[s], 2 * stage_bytes);
+        tma_load_2d_pair_elect(sa, &tmA, &full[s], m0, kb * BK);
+        tma_load_2d_pair_elect(sa + BOX, &tmA, &full[s], m0 + 64, kb * BK);
         for (int j = 0; j < nb_boxes; ++j)
-          tma_load_2d_pair(sa + a_bytes + j * BOX, &tmB, &full[s], n0 + j * 64, kb * BK);
+          tma_load_2d_pair_elect(sa + a_bytes + j * BOX, &tmB, &full[s], n0 + j * 64, kb * BK);
         if (++s == g.stages) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && rank == 0) {
+    if (rank == 0) {   // whole warp, uniform control flow (ptx.cuh: *_elect)
       const uint32_t idesc = umma_idesc_bf16(2 * BM, g.BN, true, true);
       int s = 0;
       uint32_t ph = 0;
       for (int i = 0; i < num_kb; ++i) {
-        mbar_wait(&full[s], ph);
+        mbar_wait_warp(&full[s], ph);
         tc_fence_after();
         const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
         const uint32_t b_addr = a_addr + a_bytes;
@@ -643,12 +643,12 @@ gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int k = 0; k < BK / UMMA_K; ++k) {
           const uint64_t ad = umma_desc_sw128(a_addr + k * (UMMA_K * 128), BOX, 1024);
           const uint64_t bd = umma_desc_sw128(b_addr + k * (UMMA_K * 128), BOX, 1024);
-          umma_f16_pair(tmem_base, ad, bd, idesc, (i | k) != 0 ? 1u : 0u);
+          umma_f16_pair_elect(tmem_base, ad, bd, idesc, (i | k) != 0 ? 1u : 0u);
         }
-        umma_commit_pair(&empty[s], 3);
+        umma_commit_pair_elect(&empty[s], 3);
         if (++s == g.stages) { s = 0; ph ^= 1; }
       }
-      umma_commit_pair(tmem_full, 3);
+      umma_commit_pair_elect(tmem_full, 3);
     }
   } else {
     mbar_wait(tmem_full, 0);

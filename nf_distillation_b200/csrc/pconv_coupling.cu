@@ -82,7 +82,7 @@ pconv_coupling_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
   extern __shared__ __align__(1024) uint8_t smem[];
   pdl_launch_dependents();
   if (smem_u32(smem) & 1023u) __trap();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = static_cast<int>(uniform_u32(threadIdx.x >> 5)), lane = threadIdx.x & 31;
   float* S = reinterpret_cast<float*>(smem + Sm::off_s);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + Sm::off_bar);
   uint64_t* empty = full + PC_STAGES;
@@ -105,36 +105,36 @@ pconv_coupling_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = uniform_u32(*tmem_slot);
 
   if (warp == 0) {
-    if (lane == 0) {
+    {   // whole warp, uniform control flow: single-thread instructions are elected inside the asm (ptx.cuh)
       int s = 0;
       uint32_t ph = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         for (int kb = 0; kb < g.num_kb; ++kb) {
-          mbar_wait(&empty[s], ph ^ 1);
+          mbar_wait_warp(&empty[s], ph ^ 1);
           uint8_t* sa = smem + s * Sm::stage_bytes;
-          mbar_expect_tx(&full[s], Sm::stage_bytes);
+          mbar_expect_tx_elect(&full[s], Sm::stage_bytes);
 #pragma unroll
-          for (int mb = 0; mb < MB; ++mb) tma_load_2d(sa + mb * 128 * 128, &tmW, &full[s], kb * PC_BK, mb * 128);
-          tma_load_2d(sa + Sm::a_bytes, &tmH, &full[s], kb * PC_BK, static_cast<int>(pc_tile_pix0<NPIX>(g, t)));
+          for (int mb = 0; mb < MB; ++mb) tma_load_2d_elect(sa + mb * 128 * 128, &tmW, &full[s], kb * PC_BK, mb * 128);
+          tma_load_2d_elect(sa + Sm::a_bytes, &tmH, &full[s], kb * PC_BK, static_cast<int>(pc_tile_pix0<NPIX>(g, t)));
           if (++s == PC_STAGES) { s = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {   // whole warp, uniform control flow: single-thread instructions are elected inside the asm (ptx.cuh)
       const uint32_t idesc = umma_idesc_bf16(128, NPIX, false, false);
       int s = 0, it = 0;
       uint32_t ph = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
         const int acc = it & 1;
-        mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);
+        mbar_wait_warp(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * ACC_COLS;
         for (int kb = 0; kb < g.num_kb; ++kb) {
-          mbar_wait(&full[s], ph);
+          mbar_wait_warp(&full[s], ph);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + s * Sm::stage_bytes);
           const uint32_t b_addr = a_addr + Sm::a_bytes;
@@ -144,13 +144,13 @@ pconv_coupling_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
 #pragma unroll
             for (int mb = 0; mb < MB; ++mb) {
               const uint64_t ad = umma_desc_sw128(a_addr + mb * 128 * 128 + k * 32, 16, 1024);
-              umma_f16(tmem_d + mb * NPIX, ad, bd, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+              umma_f16_elect(tmem_d + mb * NPIX, ad, bd, idesc, (kb > 0 || k > 0) ? 1u : 0u);
             }
           }
-          umma_commit(&empty[s]);
+          umma_commit_elect(&empty[s]);
           if (++s == PC_STAGES) { s = 0; ph ^= 1; }
         }
-        umma_commit(&tmem_full[acc]);
+        umma_commit_elect(&tmem_full[acc]);
       }
     }
   } else {

@@ -14,9 +14,9 @@
 //
 //   TMEM   [0,256) h1 (bf16x2 per column) | [256,384) accumulator 0 | [384,512) accumulator 1
 //          -> a tile is 4 + 4 quarter-GEMMs of N = 128 (M = 256 over the CTA pair), ping-pong over the two accumulators
-//   smem   A tile of GEMM 1 (kb1 x 16 KB, loaded once per tile, prefetched a tile ahead) | store staging 8 warps x 2 x
+//   smem   A tile of GEMM 1 (kb1 x 16 KB, loaded once per tile, prefetched a tile ahead) | store staging 16 warps x
 //          4 KB | weight ring nslots x 8 KB (64 weight rows x 64 K per CTA and slot)
-//   warps  0: TMA producer, 1: MMA issuer (leader CTA) + TMEM alloc, 2-9: epilogue (2 per TMEM lane quadrant)
+//   warps  0: TMA producer, 1: MMA issuer (leader CTA) + TMEM alloc, 2-17: epilogue (4 per TMEM lane quadrant)
 //
 // MODE 0: forward (+ optional h1 / 1-bit ReLU mask outputs for training); MODE 1: the student's backward chain
 // d2 = mask .* (dhcol B3T^T), d1 = mask .* (d2 B2T^T) with both bias gradients (see cnet_fused.cu). Results are
@@ -26,6 +26,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <cstdlib>
 
 #include "../../include/nfk.h"
 #include "launch_util.h"
@@ -33,13 +34,17 @@
 
 namespace nfk {
 
-constexpr int TS_THREADS = 320;
+constexpr int TS_THREADS = 576;      // 18 warps: TMA producer, MMA issuer, 16 epilogue warps
 constexpr int TS_HID = 512;
-constexpr int TS_SLOT = 8192;         // ring slot: this CTA's 64 rows of a 128-row weight tile x 128 B of K
-constexpr int TS_MAX_SLOTS = 16;
+constexpr int TS_BOX = 8192;          // one weight box: this CTA's 64 rows of a 128-row weight tile x 64 K (128 B)
+constexpr int TS_SLOT = 2 * TS_BOX;   // ring slot = two consecutive k-blocks of one quarter: ONE barrier round trip per
+                                      // 8 MMAs (a single-warp wait + expect_tx + issue loop costs ~280 cycles per
+                                      // iteration, tools/micro/tma_bench.cu: at one 8 KB box per iteration the producer
+                                      // delivers 29 B/clk against the 32 B/clk the quarter MMAs consume)
+constexpr int TS_MAX_SLOTS = 8;
 constexpr int TS_COLBLK = 16384;      // 128 rows x 128 B: one k-block of the A tile of GEMM 1
 constexpr int TS_STAGE = 4096;        // 32 rows x 128 B store staging panel
-constexpr int TS_STAGE_BYTES = 8 * 2 * TS_STAGE;
+constexpr int TS_STAGE_BYTES = 16 * TS_STAGE;   // one panel per epilogue warp
 constexpr int TS_BAR_BYTES = 512;
 constexpr uint32_t TS_ACC0 = 256;     // first accumulator column
 
@@ -94,8 +99,8 @@ __device__ __forceinline__ void cnet_ts_body(const CUtensorMap& tmCol, const CUt
   uint8_t* colbuf = smem;
   uint8_t* stage_base = colbuf + g.kb1 * TS_COLBLK;
   uint8_t* ring = stage_base + TS_STAGE_BYTES;
-  uint64_t* full = reinterpret_cast<uint64_t*>(ring + nslots * TS_SLOT);   // [16] slot filled (leader)
-  uint64_t* empty = full + TS_MAX_SLOTS;                                    // [16] slot consumed (local)
+  uint64_t* full = reinterpret_cast<uint64_t*>(ring + nslots * TS_SLOT);   // [8] slot filled (leader)
+  uint64_t* empty = full + TS_MAX_SLOTS;                                    // [8] slot consumed (local)
   uint64_t* acc_full = empty + TS_MAX_SLOTS;                                // [2]
   uint64_t* acc_empty = acc_full + 2;                                       // [2] (leader, 16 arrivals)
   uint64_t* h1_full = acc_empty + 2;                                        // [8] per 64 channels of h1 (leader, 8 arrivals)
@@ -126,10 +131,13 @@ __device__ __forceinline__ void cnet_ts_body(const CUtensorMap& tmCol, const CUt
     // (whole warp in uniform control flow, single-thread instructions elected inside the asm: see ptx.cuh)
     {
       int s = 0; uint32_t ph = 0, col_ph = 0;
-      auto load = [&](const CUtensorMap* tm, int c0, int c1) {
+      // one slot: k-blocks kb, kb + 1 (< kend) of the weight rows starting at `row`
+      auto load = [&](const CUtensorMap* tm, int kb, int kend, int row) {
+        const int nkb = kend - kb < 2 ? kend - kb : 2;
         mbar_wait_warp(&empty[s], ph ^ 1);
-        if (rank == 0) mbar_expect_tx_elect(&full[s], 2 * TS_SLOT);
-        tma_load_2d_pair_elect(ring + s * TS_SLOT, tm, &full[s], c0, c1);
+        if (rank == 0) mbar_expect_tx_elect(&full[s], static_cast<uint32_t>(2 * nkb * TS_BOX));
+        for (int j = 0; j < nkb; ++j)
+          tma_load_2d_pair_elect(ring + s * TS_SLOT + j * TS_BOX, tm, &full[s], (kb + j) * 64, row);
         if (++s == nslots) { s = 0; ph ^= 1; }
       };
       auto load_col = [&](int t) {
@@ -144,9 +152,11 @@ __device__ __forceinline__ void cnet_ts_body(const CUtensorMap& tmCol, const CUt
       for (int t = pair; t < num_tiles; t += num_pairs) {
         const int wrow = static_cast<int>(rank) * 64;
         for (int q = 0; q < 4; ++q)
-          for (int kb = 0; kb < g.kb1; ++kb) load(&tmB1, kb * 64, q * 128 + wrow);
+          for (int kb = 0; kb < g.kb1; kb += 2) load(&tmB1, kb, g.kb1, q * 128 + wrow);
         for (int q = 0; q < 4; ++q) {
-          for (int kb = 0; kb < g.kb2_end[q >> 1]; ++kb) load(&tmB2, kb * 64, q * 128 + wrow);
+          const int qe = q;
+          const int kend = qe < 2 ? g.kb2_end[0] : g.kb2_end[1];
+          for (int kb = 0; kb < kend; kb += 2) load(&tmB2, kb, kend, qe * 128 + wrow);
           // the next tile's A tile: GEMM 1 of this tile has retired by the time the first GEMM-2 quarter's weights are
           // in flight, so the wait inside load_col does not hold back the weight stream
           if (q == 0 && t + num_pairs < num_tiles) load_col(t + num_pairs);
@@ -162,7 +172,7 @@ __device__ __forceinline__ void cnet_ts_body(const CUtensorMap& tmCol, const CUt
       int s = 0; uint32_t ph = 0;
       uint32_t nacc = 0;          // accumulator uses so far (stage = nacc & 1, phase = (nacc >> 1) & 1)
       uint32_t tile_ph = 0;
-      long long w_op = 0, w_acc = 0, w_h1 = 0;
+      long long w_op = 0, w_acc = 0, w_h1 = 0, w_col = 0, w_b1 = 0, w_q0 = 0;
       const long long t_begin = g.prof ? clock64() : 0;
       auto take = [&]() {
         const long long c0 = g.prof ? clock64() : 0;
@@ -186,61 +196,79 @@ __device__ __forceinline__ void cnet_ts_body(const CUtensorMap& tmCol, const CUt
         {
           const long long c0 = g.prof ? clock64() : 0;
           mbar_wait_warp(col_full, tile_ph);
-          if (g.prof) w_op += clock64() - c0;
+          if (g.prof) { w_op += clock64() - c0; w_col += clock64() - c0; }
           tc_fence_after();
         }
+        const long long w_op_g1 = w_op;
         for (int q = 0; q < 4; ++q) {
           const uint32_t d = acc_begin();
-          for (int kb = 0; kb < g.kb1; ++kb) {
+          for (int kb = 0; kb < g.kb1; kb += 2) {
             const uint32_t b = take();
+            const int nkb = g.kb1 - kb < 2 ? g.kb1 - kb : 2;
+            for (int j = 0; j < nkb; ++j) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_f16_pair_elect(d, umma_desc_sw128(col_addr + kb * TS_COLBLK + k * 32, 16, 1024),
-                            umma_desc_sw128(b + k * 32, 16, 1024), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+              for (int k = 0; k < 4; ++k)
+                umma_f16_pair_elect(d, umma_desc_sw128(col_addr + (kb + j) * TS_COLBLK + k * 32, 16, 1024),
+                                    umma_desc_sw128(b + j * TS_BOX + k * 32, 16, 1024), idesc,
+                                    (kb + j > 0 || k > 0) ? 1u : 0u);
+            }
             release();
           }
           acc_end();
         }
         umma_commit_pair_elect(col_empty, 3);
+        w_b1 += w_op - w_op_g1;
         // ---- GEMM 2: A = h1 in tensor memory (written by the epilogue warps of both CTAs), weights streamed.
         //      k-block kb only needs h1 channels [64 kb, 64 kb + 64), so it starts as soon as those have been written
         int blocks_seen = 0;
         for (int q = 0; q < 4; ++q) {
           const uint32_t d = acc_begin();
-          const int kend = g.kb2_end[q >> 1];
-          for (int kb = 0; kb < kend; ++kb) {
-            if (kb >= blocks_seen) {
-              const long long c0 = g.prof ? clock64() : 0;
-              mbar_wait_warp(&h1_full[kb], tile_ph);
-              if (g.prof) w_h1 += clock64() - c0;
-              tc_fence_after();
-              blocks_seen = kb + 1;
-            }
+          const long long w_op_q = w_op;
+          const int kend = q < 2 ? g.kb2_end[0] : g.kb2_end[1];
+          for (int kb = 0; kb < kend; kb += 2) {
             const uint32_t b = take();
+            const int nkb = kend - kb < 2 ? kend - kb : 2;
+            for (int j = 0; j < nkb; ++j) {
+              if (kb + j >= blocks_seen) {
+                const long long c0 = g.prof ? clock64() : 0;
+                mbar_wait_warp(&h1_full[kb + j], tile_ph);
+                if (g.prof) w_h1 += clock64() - c0;
+                tc_fence_after();
+                blocks_seen = kb + j + 1;
+              }
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_f16_pair_ts_elect(d, tmem_base + static_cast<uint32_t>(kb * 32 + k * 8),
-                               umma_desc_sw128(b + k * 32, 16, 1024), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+              for (int k = 0; k < 4; ++k)
+                umma_f16_pair_ts_elect(d, tmem_base + static_cast<uint32_t>((kb + j) * 32 + k * 8),
+                                       umma_desc_sw128(b + j * TS_BOX + k * 32, 16, 1024), idesc,
+                                       (kb + j > 0 || k > 0) ? 1u : 0u);
+            }
             release();
           }
           acc_end();
+          if (q == 0) w_q0 += w_op - w_op_q;
         }
         umma_commit_pair_elect(h1_empty, 3);      // h1 is free once every MMA issued so far has retired
         tile_ph ^= 1;
       }
       if (g.prof && lane == 0) {
         long long* o = g.prof + blockIdx.x * 8;
-        o[0] = clock64() - t_begin; o[1] = w_op; o[2] = w_acc; o[3] = w_h1;
+        o[0] = clock64() - t_begin; o[1] = w_op; o[2] = w_acc; o[3] = w_h1; o[4] = w_col; o[5] = w_b1; o[6] = w_q0;
       }
     }
   } else {
-    // ===================================================== epilogue warps
+    // ===================================================== epilogue warps (16: four per TMEM lane quadrant)
+    // Warp set ws = 0 / 1 drains accumulator ws, i.e. the quarters q with (q & 1) == ws of both GEMMs; inside a set, the
+    // two warps of a lane quadrant take the two 64-column halves of the quarter. Two quarters are therefore converted
+    // at the same time (the GEMM-1 quarters gate GEMM 2 of the tile: the tensor pipe idles while they are converted),
+    // and four warps per scheduler hide the tcgen05.ld / fence / barrier round trips of one another.
+    const int ew = warp - 2;               // 0..15
     const int qd = warp & 3;               // TMEM lane quadrant
-    const int hf = (warp - 2) >> 2;        // which 64-column half of a 128-column accumulator
+    const int hf = (ew >> 2) & 1;          // which 64-column half of a 128-column accumulator
+    const int ws = ew >> 3;                // accumulator stage owned by this warp
     const uint32_t lane_off = static_cast<uint32_t>(qd * 32) << 16;
     const uint32_t sw = static_cast<uint32_t>(lane & 7);
-    uint8_t* stage2 = stage_base + (warp - 2) * 2 * TS_STAGE;
-    uint32_t nacc = 0, tile_ph = 0, nst = 0;
+    uint8_t* panel = stage_base + ew * TS_STAGE;
+    uint32_t nuse = 0, tile_ph = 0;        // uses of accumulator ws so far
     // 16 accumulator columns -> bias + ReLU -> 8 packed bf16x2 words (+ the 16 ReLU mask bits). Packed arithmetic:
     // add.f32x2, round to bf16x2, max.bf16x2 with +0 (equals rounding the fp32 ReLU: rounding is monotonic)
     auto epi16 = [&](const uint32_t (&r)[16], const float* bias16, uint32_t (&p)[8], bool want_bits) -> uint32_t {
@@ -277,8 +305,11 @@ __device__ __forceinline__ void cnet_ts_body(const CUtensorMap& tmCol, const CUt
         p[k] = *reinterpret_cast<uint32_t*>(&v);
       }
     };
-    // this thread's 64 packed columns (P[i] = columns 16 i .. 16 i + 15) -> its 128-byte row of a swizzled panel
-    auto to_panel = [&](const uint32_t (&P)[4][8], uint8_t* panel) {
+    // this thread's 64 packed columns (P[i] = columns 16 i .. 16 i + 15) -> its 128-byte row of the swizzled panel.
+    // The panel is reused: the previous bulk store must have finished reading it.
+    auto to_panel = [&](const uint32_t (&P)[4][8]) {
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      __syncwarp();
       uint8_t* dst = panel + lane * 128;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -287,11 +318,13 @@ __device__ __forceinline__ void cnet_ts_body(const CUtensorMap& tmCol, const CUt
         *reinterpret_cast<uint4*>(dst + ((static_cast<uint32_t>(2 * i + 1) ^ sw) << 4)) =
             make_uint4(P[i][4], P[i][5], P[i][6], P[i][7]);
       }
+      fence_proxy_async();
+      __syncwarp();
     };
     // column sums of this warp's 32 x 64 panel, straight from the staged bf16 rows: lane owns the column pair
     // (lane >> 2) * 8 + (lane & 3) * 2 (+1); at row r the 32 lanes read the whole 128-byte row (conflict-free)
-    auto panel_colsum = [&](const uint8_t* rows, float& s0, float& s1) {
-      const uint8_t* pb = rows + (lane & 3) * 4;
+    auto panel_colsum = [&](float& s0, float& s1) {
+      const uint8_t* pb = panel + (lane & 3) * 4;
       const uint32_t chunk = static_cast<uint32_t>(lane >> 2);
       float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
 #pragma unroll 8
@@ -303,47 +336,37 @@ __device__ __forceinline__ void cnet_ts_body(const CUtensorMap& tmCol, const CUt
       }
       s0 += a0 + b0; s1 += a1 + b1;
     };
-    // the staging panel to write next: two per warp, so the bulk store of one panel overlaps the math of the next.
-    // Every staged panel commits exactly one bulk group, so "at most one group still reading" frees the older panel
-    auto next_stage = [&]() -> uint8_t* {
-      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-      __syncwarp();
-      uint8_t* p = stage2 + (nst & 1) * TS_STAGE;
-      ++nst;
-      return p;
-    };
-    float cs1[4][2] = {}, cs2[4][2] = {};    // [quarter][column of the pair]: bias-gradient partial sums of this CTA
+    float cs1[2][2] = {}, cs2[2][2] = {};    // [this warp's quarter][column of the pair]: bias-gradient partial sums
 
     for (int t = pair; t < num_tiles; t += num_pairs) {
       const int row0 = t * 256 + static_cast<int>(rank) * 128 + qd * 32;
       const long long row = row0 + lane;
       const bool row_ok = row < g.M;
-      uint32_t mw1[8], mw2[8];     // MODE 1: this thread's ReLU-mask words of the tile (fetched before the waits)
+      uint32_t mw1[4], mw2[4];     // MODE 1: this thread's ReLU-mask words of the tile (fetched before the waits)
       if constexpr (MODE == 1) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int c = q * 128 + hf * 64;
-          mw1[2 * q] = row_ok ? __ldg(g.mask1 + static_cast<long long>(c >> 5) * g.ldmask + row) : 0u;
-          mw1[2 * q + 1] = row_ok ? __ldg(g.mask1 + static_cast<long long>((c + 32) >> 5) * g.ldmask + row) : 0u;
-          mw2[2 * q] = row_ok ? __ldg(g.mask2 + static_cast<long long>(c >> 5) * g.ldmask + row) : 0u;
-          mw2[2 * q + 1] = row_ok ? __ldg(g.mask2 + static_cast<long long>((c + 32) >> 5) * g.ldmask + row) : 0u;
+        for (int qq = 0; qq < 2; ++qq) {
+          const int c = (2 * qq + ws) * 128 + hf * 64;
+          mw1[2 * qq] = row_ok ? __ldg(g.mask1 + static_cast<long long>(c >> 5) * g.ldmask + row) : 0u;
+          mw1[2 * qq + 1] = row_ok ? __ldg(g.mask1 + static_cast<long long>((c + 32) >> 5) * g.ldmask + row) : 0u;
+          mw2[2 * qq] = row_ok ? __ldg(g.mask2 + static_cast<long long>(c >> 5) * g.ldmask + row) : 0u;
+          mw2[2 * qq + 1] = row_ok ? __ldg(g.mask2 + static_cast<long long>((c + 32) >> 5) * g.ldmask + row) : 0u;
         }
       }
+      const uint32_t tm = tmem_base + TS_ACC0 + ws * 128 + hf * 64 + lane_off;
       // ---- GEMM 1 quarters -> h1 in tensor memory (+ staged copy -> TMA store when h1 is an output)
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const uint32_t st = nacc & 1;
-        mbar_wait(&acc_full[st], (nacc >> 1) & 1);
+      for (int qq = 0; qq < 2; ++qq) {
+        mbar_wait(&acc_full[ws], nuse & 1);
         tc_fence_after();
-        const uint32_t tm = tmem_base + TS_ACC0 + st * 128 + hf * 64 + lane_off;
         uint32_t R[4][16];
 #pragma unroll
         for (int i = 0; i < 4; ++i) tmem_ld16(tm + 16 * i, R[i]);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(&acc_empty[st], 0);   // the MMAs of the quarter after next may overwrite it
-        const int col0 = q * 128 + hf * 64;
+        if (lane == 0) mbar_arrive_cluster(&acc_empty[ws], 0);   // the quarter after next may overwrite it
+        const int col0 = (2 * qq + ws) * 128 + hf * 64;
         uint32_t P[4][8];
         if constexpr (MODE == 0) {
           const bool wb = g.mask1 != nullptr;
@@ -355,10 +378,10 @@ __device__ __forceinline__ void cnet_ts_body(const CUtensorMap& tmCol, const CUt
             g.mask1[static_cast<long long>((col0 + 32) >> 5) * g.ldmask + row] = b[2] | (b[3] << 16);
           }
         } else {
-          epi16m(R[0], mw1[2 * q] & 0xFFFFu, P[0]); epi16m(R[1], mw1[2 * q] >> 16, P[1]);
-          epi16m(R[2], mw1[2 * q + 1] & 0xFFFFu, P[2]); epi16m(R[3], mw1[2 * q + 1] >> 16, P[3]);
+          epi16m(R[0], mw1[2 * qq] & 0xFFFFu, P[0]); epi16m(R[1], mw1[2 * qq] >> 16, P[1]);
+          epi16m(R[2], mw1[2 * qq + 1] & 0xFFFFu, P[2]); epi16m(R[3], mw1[2 * qq + 1] >> 16, P[3]);
         }
-        if (q == 0) {
+        if (qq == 0) {
           // h1 of the previous tile must be dead: its GEMM-2 MMAs have retired
           mbar_wait(h1_empty, tile_ph ^ 1);
           tc_fence_after();
@@ -366,42 +389,37 @@ __device__ __forceinline__ void cnet_ts_body(const CUtensorMap& tmCol, const CUt
         const uint32_t th = tmem_base + lane_off + static_cast<uint32_t>(col0 >> 1);
         tmem_st16(th, P[0], P[1]);
         tmem_st16(th + 16, P[2], P[3]);
-        if (g.store_h1) {
-          uint8_t* panel = next_stage();
-          to_panel(P, panel);
-          fence_proxy_async();
-          __syncwarp();
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(&h1_full[2 * (2 * qq + ws) + hf], 0);   // GEMM 2 may read these channels
+        if (g.store_h1) {     // the copy for HBM comes after the hand-off: it is not on the tensor pipe's critical path
+          to_panel(P);
           if constexpr (MODE == 1) {
             float s0 = 0.f, s1 = 0.f;
-            panel_colsum(panel, s0, s1);
-            cs1[q][0] += s0; cs1[q][1] += s1;
+            panel_colsum(s0, s1);
+            cs1[qq][0] += s0; cs1[qq][1] += s1;
           }
           if (lane == 0) {
             if (row0 < g.M) tma_store_2d(panel, &tmH1, col0, row0);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
         }
-        tmem_st_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(&h1_full[2 * q + hf], 0);
-        ++nacc;
+        ++nuse;
       }
       // ---- GEMM 2 quarters -> staging panel -> TMA store of h2
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const uint32_t st = nacc & 1;
-        mbar_wait(&acc_full[st], (nacc >> 1) & 1);
+      for (int qq = 0; qq < 2; ++qq) {
+        mbar_wait(&acc_full[ws], nuse & 1);
         tc_fence_after();
-        const uint32_t tm = tmem_base + TS_ACC0 + st * 128 + hf * 64 + lane_off;
         uint32_t R[4][16];
 #pragma unroll
         for (int i = 0; i < 4; ++i) tmem_ld16(tm + 16 * i, R[i]);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(&acc_empty[st], 0);
-        const int col0 = q * 128 + hf * 64;
+        if (lane == 0) mbar_arrive_cluster(&acc_empty[ws], 0);
+        const int col0 = (2 * qq + ws) * 128 + hf * 64;
         uint32_t P[4][8];
         if constexpr (MODE == 0) {
           const bool wb = g.mask2 != nullptr;
@@ -413,33 +431,30 @@ __device__ __forceinline__ void cnet_ts_body(const CUtensorMap& tmCol, const CUt
             g.mask2[static_cast<long long>((col0 + 32) >> 5) * g.ldmask + row] = b[2] | (b[3] << 16);
           }
         } else {
-          epi16m(R[0], mw2[2 * q] & 0xFFFFu, P[0]); epi16m(R[1], mw2[2 * q] >> 16, P[1]);
-          epi16m(R[2], mw2[2 * q + 1] & 0xFFFFu, P[2]); epi16m(R[3], mw2[2 * q + 1] >> 16, P[3]);
+          epi16m(R[0], mw2[2 * qq] & 0xFFFFu, P[0]); epi16m(R[1], mw2[2 * qq] >> 16, P[1]);
+          epi16m(R[2], mw2[2 * qq + 1] & 0xFFFFu, P[2]); epi16m(R[3], mw2[2 * qq + 1] >> 16, P[3]);
         }
-        uint8_t* panel = next_stage();
-        to_panel(P, panel);
-        fence_proxy_async();
-        __syncwarp();
+        to_panel(P);
         if constexpr (MODE == 1) {
           float s0 = 0.f, s1 = 0.f;
-          panel_colsum(panel, s0, s1);
-          cs2[q][0] += s0; cs2[q][1] += s1;
+          panel_colsum(s0, s1);
+          cs2[qq][0] += s0; cs2[qq][1] += s1;
         }
         if (lane == 0) {
           if (row0 < g.M) tma_store_2d(panel, &tmH2, col0, row0);
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
-        ++nacc;
+        ++nuse;
       }
       tile_ph ^= 1;
     }
     if constexpr (MODE == 1) {   // one atomic per column, accumulator quarter and CTA
       const int cpair = (lane >> 2) * 8 + (lane & 3) * 2;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int c = q * 128 + hf * 64 + cpair;
-        if (g.colsum1) { atomicAdd(g.colsum1 + c, cs1[q][0]); atomicAdd(g.colsum1 + c + 1, cs1[q][1]); }
-        if (g.colsum2) { atomicAdd(g.colsum2 + c, cs2[q][0]); atomicAdd(g.colsum2 + c + 1, cs2[q][1]); }
+      for (int qq = 0; qq < 2; ++qq) {
+        const int c = (2 * qq + ws) * 128 + hf * 64 + cpair;
+        if (g.colsum1) { atomicAdd(g.colsum1 + c, cs1[qq][0]); atomicAdd(g.colsum1 + c + 1, cs1[qq][1]); }
+        if (g.colsum2) { atomicAdd(g.colsum2 + c, cs2[qq][0]); atomicAdd(g.colsum2 + c + 1, cs2[qq][1]); }
       }
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -494,6 +509,8 @@ static int ts_smem_plan(int kb1, int* nslots) {
   const int fixed = kb1 * TS_COLBLK + TS_STAGE_BYTES + TS_BAR_BYTES;
   int n = (227 * 1024 - fixed) / TS_SLOT;
   if (n > TS_MAX_SLOTS) n = TS_MAX_SLOTS;
+  static const int cap = [] { const char* e = getenv("NFK_CNET_SLOTS"); return e ? atoi(e) : 0; }();   // experiments
+  if (cap >= 2 && n > cap) n = cap;
   *nslots = n;
   return fixed + n * TS_SLOT;
 }
@@ -505,7 +522,7 @@ static int ts_launch(const void* A, int Ka, const void* W1, const void* W2, void
                      cudaStream_t stream) {
   int nslots = 0;
   const int smem_bytes = ts_smem_plan(Ka / 64, &nslots);
-  if (nslots < 4) return NFK_ERR_SHAPE;
+  if (nslots < 2) return NFK_ERR_SHAPE;
   g.nslots = nslots;
   CUtensorMap tmA, tmW1, tmW2, tmO1, tmO2;
   int rc;

@@ -43,6 +43,11 @@ for (M, K1p) in CASES:
     if M == 262144:
         prof = torch.zeros(148, 8, device=dev, dtype=torch.int64)
         LIB.nfk_cnet_set_prof(prof.data_ptr()); fused(); torch.cuda.synchronize(); LIB.nfk_cnet_set_prof(None)
-        p = prof.cpu().double(); p = p[p[:, 0] > 0]
-        names = ["total", "wait operands", "wait acc-free", "wait h1"]
+        p = prof.cpu().double()
+        pe = p[1::2]; pe = pe[pe[:, 0] > 0]
+        p = p[0::2]; p = p[p[:, 0] > 0]
+        names = ["total", "wait operands", "wait acc-free", "wait h1", "of operands: A tile", "weights GEMM 1", "weights GEMM 2 first quarter"]
         print("   MMA issuer cycles per CTA:", {n: int(p[:, i].mean()) for i, n in enumerate(names)}, "tiles/CTA %.1f" % (1024 / 74))
+        if len(pe):
+            en = ["total", "wait acc GEMM1", "wait acc GEMM2", "wait h1-free", "wait staging", "tcgen05.ld GEMM2", "stage+fence+store GEMM2"]
+            print("   epilogue warp 2 (odd CTA):", {n: int(pe[:, i].mean()) for i, n in enumerate(en)})

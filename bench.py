@@ -156,6 +156,12 @@ def time_graph(run, reps, nbuf):
     return k0.elapsed_time(k1) / reps
 
 
+def fused_kernel_name():
+    """The fused conv kernel the library dispatches to: the tensor-memory variant (csrc/cnet_ts.cu) unless NFK_CNET_TS=0
+    selects the shared-memory-panel one (csrc/cnet_fused.cu)."""
+    return "cnet_fwd_fused_kernel" if os.environ.get("NFK_CNET_TS", "1").startswith("0") else "cnet_fwd_ts_kernel"
+
+
 def cnet_roofline(B, H, W, C_img, hid, device):
     """Roofline of the dominant kernel of every 2-D Glow workload (profiles/r02_launches_*.txt): the fused
     conv3x3 -> ReLU -> conv1x1 -> ReLU of the coupling net at the level-0 shape, M = B*(H/2)*(W/2) pixels, timed alone.
@@ -184,7 +190,7 @@ def cnet_roofline(B, H, W, C_img, hid, device):
     flops = 2.0 * M * hid * ((K1 if fused else 0) + hid)
     ach = flops / (kms * 1e-3) / 1e12
     alg_bytes = 2.0 * (M * K1 + M * hid + hid * K1 + hid * hid)
-    kname = "cnet_fwd_fused_kernel" if fused else "gemm_nt_pair_kernel<1>"
+    kname = fused_kernel_name() if fused else "gemm_nt_pair_kernel<1>"
     traffic, tsrc = profiled_traffic(kname, M, K1p) if fused else (None, "not captured")
     return {"bound": "tensor",
             "kernel": kname + (" (conv#1+conv#2 of the coupling net, level 0)" if fused else " (conv#2, level 0)"),
@@ -311,8 +317,8 @@ def maf_roofline(B, D, H, device):
     # algorithmic = the non-zero part of the masked products: layer 1 D x H, layer 2 ~ half of H x H (degree-sorted)
     flops = 2.0 * B * H * (D + H / 2.0)
     ach = flops / (kms * 1e-3) / 1e12
-    traffic, tsrc = profiled_traffic("cnet_fwd_fused_kernel", B, Dp)
-    return {"bound": "tensor", "kernel": "cnet_fwd_fused_kernel (both masked linears of a MADE layer)",
+    traffic, tsrc = profiled_traffic(fused_kernel_name(), B, Dp)
+    return {"bound": "tensor", "kernel": fused_kernel_name() + " (both masked linears of a MADE layer)",
             "achieved": ach, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops"],
             "traffic": traffic, "traffic_src": tsrc, "peak_src": pk["src"] + " burst (kernel timed alone)",
             "us_per_launch": kms * 1e3, "flops_per_launch": flops,

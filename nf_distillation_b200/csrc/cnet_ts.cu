@@ -46,6 +46,7 @@ constexpr int TS_COLBLK = 16384;      // 128 rows x 128 B: one k-block of the A 
 constexpr int TS_STAGE = 4096;        // 32 rows x 128 B store staging panel
 constexpr int TS_STAGE_BYTES = 16 * TS_STAGE;   // one panel per epilogue warp
 constexpr int TS_BAR_BYTES = 512;
+constexpr int TS_BIAS_BYTES = 2 * TS_HID * 4;   // both bias vectors, staged once per CTA (MODE 0)
 constexpr uint32_t TS_ACC0 = 256;     // first accumulator column
 
 struct TsArgs {
@@ -82,6 +83,12 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&a)[8]
         "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7])
       : "memory");
 }
+// {lo, hi} -> bf16x2 word (lo in bits 0-15) with ReLU folded into the conversion
+__device__ __forceinline__ uint32_t relu_bf16x2(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 template <int MODE>
@@ -108,6 +115,7 @@ __device__ __forceinline__ void cnet_ts_body(const CUtensorMap& tmCol, const CUt
   uint64_t* col_full = h1_empty + 1;                                        // A tile of GEMM 1 landed (leader)
   uint64_t* col_empty = col_full + 1;                                       // GEMM 1 of the tile has finished reading it
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(col_empty + 1);
+  float* bias_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full) + TS_BAR_BYTES);   // [2][512]
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmCol); tma_prefetch_desc(&tmB1); tma_prefetch_desc(&tmB2); tma_prefetch_desc(&tmH2);
@@ -191,8 +199,16 @@ __device__ __forceinline__ void cnet_ts_body(const CUtensorMap& tmCol, const CUt
         return tmem_base + TS_ACC0 + st * 128;
       };
       auto acc_end = [&]() { umma_commit_pair_elect(&acc_full[nacc & 1], 3); ++nacc; };
+#ifdef NFK_CNET_TIMELINE
+      auto mstamp = [&](int t, int idx) {
+        if (g.prof && blockIdx.x == 0 && t == 6 * num_pairs && lane == 0) g.prof[150 * 8 + idx] = clock64();
+      };
+#else
+      auto mstamp = [](int, int) {};
+#endif
       for (int t = pair; t < num_tiles; t += num_pairs) {
         // ---- GEMM 1: four 128-channel quarters, A = the tile's im2col rows in shared memory
+        mstamp(t, 0);
         {
           const long long c0 = g.prof ? clock64() : 0;
           mbar_wait_warp(col_full, tile_ph);
@@ -202,6 +218,7 @@ __device__ __forceinline__ void cnet_ts_body(const CUtensorMap& tmCol, const CUt
         const long long w_op_g1 = w_op;
         for (int q = 0; q < 4; ++q) {
           const uint32_t d = acc_begin();
+          if (q == 0) mstamp(t, 1);
           for (int kb = 0; kb < g.kb1; kb += 2) {
             const uint32_t b = take();
             const int nkb = g.kb1 - kb < 2 ? g.kb1 - kb : 2;
@@ -217,12 +234,14 @@ __device__ __forceinline__ void cnet_ts_body(const CUtensorMap& tmCol, const CUt
           acc_end();
         }
         umma_commit_pair_elect(col_empty, 3);
+        mstamp(t, 2);
         w_b1 += w_op - w_op_g1;
         // ---- GEMM 2: A = h1 in tensor memory (written by the epilogue warps of both CTAs), weights streamed.
         //      k-block kb only needs h1 channels [64 kb, 64 kb + 64), so it starts as soon as those have been written
         int blocks_seen = 0;
         for (int q = 0; q < 4; ++q) {
           const uint32_t d = acc_begin();
+          mstamp(t, 3 + q);
           const long long w_op_q = w_op;
           const int kend = q < 2 ? g.kb2_end[0] : g.kb2_end[1];
           for (int kb = 0; kb < kend; kb += 2) {
@@ -246,6 +265,7 @@ __device__ __forceinline__ void cnet_ts_body(const CUtensorMap& tmCol, const CUt
           }
           acc_end();
           if (q == 0) w_q0 += w_op - w_op_q;
+          if (q == 3) mstamp(t, 7);
         }
         umma_commit_pair_elect(h1_empty, 3);      // h1 is free once every MMA issued so far has retired
         tile_ph ^= 1;
@@ -270,20 +290,18 @@ __device__ __forceinline__ void cnet_ts_body(const CUtensorMap& tmCol, const CUt
     uint8_t* panel = stage_base + ew * TS_STAGE;
     uint32_t nuse = 0, tile_ph = 0;        // uses of accumulator ws so far
     // 16 accumulator columns -> bias + ReLU -> 8 packed bf16x2 words (+ the 16 ReLU mask bits). Packed arithmetic:
-    // add.f32x2, round to bf16x2, max.bf16x2 with +0 (equals rounding the fp32 ReLU: rounding is monotonic)
+    // add.f32x2, then ONE cvt.rn.relu.bf16x2.f32 per pair (round to nearest even, negatives -> +0: equals rounding the
+    // fp32 ReLU, rounding is monotonic and keeps the sign)
     auto epi16 = [&](const uint32_t (&r)[16], const float* bias16, uint32_t (&p)[8], bool want_bits) -> uint32_t {
-      const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
 #pragma unroll
       for (int j = 0; j < 16; j += 4) {
-        const float4 b = __ldg(reinterpret_cast<const float4*>(bias16 + j));
+        const float4 b = *reinterpret_cast<const float4*>(bias16 + j);
         const float2 s0 = __fadd2_rn(make_float2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])),
                                      make_float2(b.x, b.y));
         const float2 s1 = __fadd2_rn(make_float2(__uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])),
                                      make_float2(b.z, b.w));
-        const __nv_bfloat162 h0 = __hmax2(__float22bfloat162_rn(s0), zero2);
-        const __nv_bfloat162 h1 = __hmax2(__float22bfloat162_rn(s1), zero2);
-        p[j / 2] = *reinterpret_cast<const uint32_t*>(&h0);
-        p[j / 2 + 1] = *reinterpret_cast<const uint32_t*>(&h1);
+        p[j / 2] = relu_bf16x2(s0.x, s0.y);
+        p[j / 2 + 1] = relu_bf16x2(s1.x, s1.y);
       }
       uint32_t bits = 0;
       if (want_bits) {   // value > 0  <=>  the (non-negative) bf16 is not +0
@@ -337,7 +355,27 @@ __device__ __forceinline__ void cnet_ts_body(const CUtensorMap& tmCol, const CUt
       s0 += a0 + b0; s1 += a1 + b1;
     };
     float cs1[2][2] = {}, cs2[2][2] = {};    // [this warp's quarter][column of the pair]: bias-gradient partial sums
+    if constexpr (MODE == 0) {
+      // both bias vectors into shared memory (the 16 epilogue warps only: the producer and the MMA issuer are already
+      // streaming). Read per use from global memory they sat on the conversion's critical path: the first quarter's
+      // conversion of a tile measured ~3 k cycles, ~1 k of arithmetic
+      for (int i = threadIdx.x - 64; i < TS_HID; i += TS_THREADS - 64) {
+        bias_s[i] = __ldg(g.bias1 + i);
+        bias_s[TS_HID + i] = __ldg(g.bias2 + i);
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(TS_THREADS - 64) : "memory");
+    }
 
+    // timeline probe (diagnostics, compiled in with -DNFK_CNET_TIMELINE): the 7th tile of pair 0, one warp per set
+    // writes its event clocks to prof rows 148/149 (tools/cnet_diag.py prints them)
+#ifdef NFK_CNET_TIMELINE
+    auto stamp = [&](int t, int idx) {
+      if (g.prof && blockIdx.x == 0 && t == 6 * num_pairs && qd == 0 && hf == 0 && lane == 0)
+        g.prof[(148 + ws) * 8 + idx] = clock64();
+    };
+#else
+    auto stamp = [](int, int) {};
+#endif
     for (int t = pair; t < num_tiles; t += num_pairs) {
       const int row0 = t * 256 + static_cast<int>(rank) * 128 + qd * 32;
       const long long row = row0 + lane;
@@ -358,11 +396,13 @@ __device__ __forceinline__ void cnet_ts_body(const CUtensorMap& tmCol, const CUt
 #pragma unroll
       for (int qq = 0; qq < 2; ++qq) {
         mbar_wait(&acc_full[ws], nuse & 1);
+        stamp(t, qq == 0 ? 0 : 6);
         tc_fence_after();
         uint32_t R[4][16];
 #pragma unroll
         for (int i = 0; i < 4; ++i) tmem_ld16(tm + 16 * i, R[i]);
         tmem_ld_wait();
+        if (qq == 0) stamp(t, 1);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(&acc_empty[ws], 0);   // the quarter after next may overwrite it
@@ -372,7 +412,7 @@ __device__ __forceinline__ void cnet_ts_body(const CUtensorMap& tmCol, const CUt
           const bool wb = g.mask1 != nullptr;
           uint32_t b[4];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) b[i] = epi16(R[i], g.bias1 + col0 + 16 * i, P[i], wb);
+          for (int i = 0; i < 4; ++i) b[i] = epi16(R[i], bias_s + col0 + 16 * i, P[i], wb);
           if (wb && row_ok) {
             g.mask1[static_cast<long long>(col0 >> 5) * g.ldmask + row] = b[0] | (b[1] << 16);
             g.mask1[static_cast<long long>((col0 + 32) >> 5) * g.ldmask + row] = b[2] | (b[3] << 16);
@@ -381,18 +421,22 @@ __device__ __forceinline__ void cnet_ts_body(const CUtensorMap& tmCol, const CUt
           epi16m(R[0], mw1[2 * qq] & 0xFFFFu, P[0]); epi16m(R[1], mw1[2 * qq] >> 16, P[1]);
           epi16m(R[2], mw1[2 * qq + 1] & 0xFFFFu, P[2]); epi16m(R[3], mw1[2 * qq + 1] >> 16, P[3]);
         }
+        if (qq == 0) stamp(t, 2);
         if (qq == 0) {
           // h1 of the previous tile must be dead: its GEMM-2 MMAs have retired
           mbar_wait(h1_empty, tile_ph ^ 1);
           tc_fence_after();
         }
+        if (qq == 0) stamp(t, 3);
         const uint32_t th = tmem_base + lane_off + static_cast<uint32_t>(col0 >> 1);
         tmem_st16(th, P[0], P[1]);
         tmem_st16(th + 16, P[2], P[3]);
         tmem_st_wait();
+        if (qq == 0) stamp(t, 4);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(&h1_full[2 * (2 * qq + ws) + hf], 0);   // GEMM 2 may read these channels
+        stamp(t, qq == 0 ? 5 : 7);
         if (g.store_h1) {     // the copy for HBM comes after the hand-off: it is not on the tensor pipe's critical path
           to_panel(P);
           if constexpr (MODE == 1) {
@@ -425,7 +469,7 @@ __device__ __forceinline__ void cnet_ts_body(const CUtensorMap& tmCol, const CUt
           const bool wb = g.mask2 != nullptr;
           uint32_t b[4];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) b[i] = epi16(R[i], g.bias2 + col0 + 16 * i, P[i], wb);
+          for (int i = 0; i < 4; ++i) b[i] = epi16(R[i], bias_s + TS_HID + col0 + 16 * i, P[i], wb);
           if (wb && row_ok) {
             g.mask2[static_cast<long long>(col0 >> 5) * g.ldmask + row] = b[0] | (b[1] << 16);
             g.mask2[static_cast<long long>((col0 + 32) >> 5) * g.ldmask + row] = b[2] | (b[3] << 16);
@@ -506,7 +550,7 @@ static int ts_tmap(CUtensorMap* m, const void* ptr, uint64_t cols, uint64_t rows
 }
 
 static int ts_smem_plan(int kb1, int* nslots) {
-  const int fixed = kb1 * TS_COLBLK + TS_STAGE_BYTES + TS_BAR_BYTES;
+  const int fixed = kb1 * TS_COLBLK + TS_STAGE_BYTES + TS_BAR_BYTES + TS_BIAS_BYTES;
   int n = (227 * 1024 - fixed) / TS_SLOT;
   if (n > TS_MAX_SLOTS) n = TS_MAX_SLOTS;
   static const int cap = [] { const char* e = getenv("NFK_CNET_SLOTS"); return e ? atoi(e) : 0; }();   // experiments

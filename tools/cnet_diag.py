@@ -41,9 +41,10 @@ for (M, K1p) in CASES:
     fl = 2.0 * M * hid * (K1p + hid)
     print(f"M={M} K1p={K1p}: equal(h2 train, h2 infer, h1, m1, m2)={ok} | unfused {tu:.1f} us, fused {tf:.1f} us ({fl/tf/1e6:.0f} TFLOP/s), fused+save {tt:.1f} us")
     if M == 262144:
-        prof = torch.zeros(148, 8, device=dev, dtype=torch.int64)
+        prof = torch.zeros(152, 8, device=dev, dtype=torch.int64)
         LIB.nfk_cnet_set_prof(prof.data_ptr()); fused(); torch.cuda.synchronize(); LIB.nfk_cnet_set_prof(None)
         p = prof.cpu().double()
+        tl = p[148:151].clone(); p = p[:148]
         pe = p[1::2]; pe = pe[pe[:, 0] > 0]
         p = p[0::2]; p = p[p[:, 0] > 0]
         names = ["total", "wait operands", "wait acc-free", "wait h1", "of operands: A tile", "weights GEMM 1", "weights GEMM 2 first quarter"]
@@ -51,3 +52,9 @@ for (M, K1p) in CASES:
         if len(pe):
             en = ["total", "wait acc GEMM1", "wait acc GEMM2", "wait h1-free", "wait staging", "tcgen05.ld GEMM2", "stage+fence+store GEMM2"]
             print("   epilogue warp 2 (odd CTA):", {n: int(pe[:, i].mean()) for i, n in enumerate(en)})
+        if tl.abs().sum() > 0:   # timeline of one tile (cycles relative to the MMA issuer reaching the tile)
+            t0 = tl[2, 0]
+            f = lambda r: [int(v - t0) if v > 0 else None for v in r]
+            print("   timeline, MMA issuer [tile start, G1 q0 acc ready, G1 issued, G2 q0 start, q1, q2, q3, G2 issued]:", f(tl[2]))
+            for wsi in (0, 1):
+                print(f"   timeline, epilogue set {wsi} [G1 a: acc full, ld done, math done, h1 free, st done, handed | G1 b: acc full, handed]:", f(tl[wsi]))

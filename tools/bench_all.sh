@@ -1,10 +1,10 @@
 #!/bin/bash
 # Every single-GPU bench line of the round (one JSON file per workload under gpurun_out/), each under its own timeout.
-run() { name=$1; shift; timeout 400 python bench.py "$@" > gpurun_out/r02_bench_$name.json 2> gpurun_out/r02_bench_$name.err || echo "FAILED $name"; tail -c 300 gpurun_out/r02_bench_$name.json | head -c 0; python - "$name" <<'PY'
+run() { name=$1; shift; timeout 400 python bench.py "$@" > gpurun_out/r03_bench_$name.json 2> gpurun_out/r03_bench_$name.err || echo "FAILED $name"; tail -c 300 gpurun_out/r03_bench_$name.json | head -c 0; python - "$name" <<'PY'
 import json, sys
 n = sys.argv[1]
 try:
-    d = json.loads(open(f"gpurun_out/r02_bench_{n}.json").read().strip().splitlines()[-1])
+    d = json.loads(open(f"gpurun_out/r03_bench_{n}.json").read().strip().splitlines()[-1])
     r = d.get("roofline") or {}
     print(f"{n:28s} {d['value']:14.1f} {d['unit']}  {d['ms_per_step']:8.3f} ms  launches {d.get('gpu_launches_per_step')}  roofline {r.get('frac')}  logp_delta {(d.get('logp_delta') or {}).get('max_rel_err_per_sample_logp')}  cpu {(d.get('cpu_baseline') or {}).get('value')}")
 except Exception as e:

@@ -164,8 +164,10 @@ def test_every_kernel_of_a_flowstep_is_exact_on_its_own_inputs(C, H, B):
 
 @pytest.mark.parametrize("M,K1p", [(8192, 64), (8200, 128), (33000, 256), (65536, 64)])
 def test_cnet_fused_kernel_is_bit_identical_to_the_two_gemms(M, K1p):
-    """csrc/cnet_fused.cu against the two tcgen05 GEMMs it fuses (csrc/gemm_tc.cu): same bf16 products, same fp32
-    accumulation order per k-block -> h2 (both modes), h1 and both masks identical bit for bit; ragged M included."""
+    """The fused conv kernel the library dispatches to (csrc/cnet_ts.cu, h1 in tensor memory; NFK_CNET_TS=0:
+    csrc/cnet_fused.cu, h1 in shared-memory panels) against the two tcgen05 GEMMs it fuses (csrc/gemm_tc.cu): same bf16
+    products, same fp32 accumulation order per k-block -> h2 (both modes), h1 and both masks identical bit for bit;
+    ragged M included."""
     from nf_distillation_b200 import ops
     hid = 512
     g = torch.Generator(device=dev).manual_seed(M + K1p)
@@ -186,6 +188,18 @@ def test_cnet_fused_kernel_is_bit_identical_to_the_two_gemms(M, K1p):
     assert torch.equal(m1a, m1b) and torch.equal(m2a, m2b)
     ref = torch.relu(col.float() @ B1.float().T + b1).bfloat16()
     assert rel(h1a, ref) < 1e-2
+
+
+def test_shared_memory_variant_of_the_fused_conv_kernels_stays_bit_identical():
+    """NFK_CNET_TS=0 (read once per process) selects the round-2 kernels of csrc/cnet_fused.cu; the forward and
+    backward bit-identity tests of this file are re-run against them in a child process."""
+    import subprocess
+    env = dict(os.environ, NFK_CNET_TS="0")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-m", "gpu", "-k",
+                        "bit_identical_to_the_two_gemms or matches_the_two_masked_gemms"], env=env, cwd=ROOT,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "passed" in r.stdout and "failed" not in r.stdout
 
 
 # ------------------------------------------------------------------------------------------------ the KD step

@@ -19,6 +19,32 @@ USE_FUSED_CNET = os.environ.get("NFK_FUSED_CNET", "1") != "0"
 USE_FUSED_PCONV = os.environ.get("NFK_FUSED_PCONV", "1") != "0"
 USE_FUSED_CNET_BWD = os.environ.get("NFK_FUSED_CNET_BWD", "1") != "0"
 
+# ---- weight gradients beside the backward chain (small batches) --------------------------------------------------
+# A student FlowStep's backward is a chain of dependent launches: coupling_bwd -> both dgrads -> (3 weight-gradient
+# GEMMs) -> conv#1 dgrad -> affine1x1_bwd. The weight gradients feed nothing in that chain (only the batched parameter
+# chain rule at the very end of the pass), and at the reference's batch size every launch is one tile's latency, so
+# they are issued on a second stream: fork after the dgrads, join at the start of the next step's backward (and in
+# PrepAllFn.backward before their results are read). The buffers that stream reads are kept alive until the join.
+# Large maps saturate the GPU anyway and keep the single stream (and do not hold a step's activations any longer).
+WGRAD_STREAM_MAX_M = int(os.environ.get("NFK_WGRAD_STREAM_MAX_M", "65536"))   # 0 disables
+_wgrad_streams: dict = {}
+_wgrad_keepalive: list = []
+
+
+def _wgrad_stream(dev):
+    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+    st = _wgrad_streams.get(key)
+    if st is None:
+        st = _wgrad_streams[key] = torch.cuda.Stream(device=dev)
+    return st
+
+
+def _join_wgrads(dev):
+    """Make the current stream wait for the weight-gradient stream; then the buffers it was reading may be freed."""
+    if _wgrad_keepalive:
+        torch.cuda.current_stream(dev).wait_stream(_wgrad_stream(dev))
+        _wgrad_keepalive.clear()
+
 # ------------------------------------------------------------------------------------------------ parameter epoch
 # The no-grad paths cache operands derived from the parameters (fused affine, folded bf16 conv weights, packed MLP /
 # MADE weights) keyed on (data_ptr, _version) of the parameters. An optimiser step replayed from a CUDA graph (or a
@@ -210,6 +236,7 @@ class PrepAllFn(torch.autograd.Function):
         pctx = ctx.pctx
         flat = ctx.saved_tensors
         dev = flat[0].device
+        _join_wgrads(dev)      # the last steps' weight gradients may still be in flight on the second stream
         n = len(pctx.steps)
         live = [i for i in range(n) if pctx.grads[i] is not None]
         sizes = []
@@ -364,6 +391,7 @@ class FlowStep2dFn(torch.autograd.Function):
         M, cin = B * H * W, C // 2
         K1p, K3p = ops.round_up(9 * cin, 64), ops.round_up(9 * C, 64)
         dev = x.device
+        _join_wgrads(dev)      # the previous step's weight gradients (before anything here can reuse their buffers)
         g_out = torch.zeros_like(x) if g_out is None else g_out.contiguous()
         g_ld = torch.zeros(B, device=dev, dtype=F32) if g_ld is None else g_ld.contiguous()
         # one zero-filled arena for every accumulate-into buffer of this step
@@ -386,11 +414,22 @@ class FlowStep2dFn(torch.autograd.Function):
         else:
             ops.gemm_nt(dhcol, B3T, M, hid, K3p, ops.EPI_MASK_BF16, dpre2, aux=m2, colsum=dbias2)
             ops.gemm_nt(dpre2, B2T, M, hid, hid, ops.EPI_MASK_BF16, dpre1, aux=m1, colsum=dbias1)
-        ops.gemm_tn(dhcol, h2, K3p, hid, M, dB3)
-        ops.gemm_tn(dpre2, h1, hid, hid, M, dB2)
-        dcol = torch.empty(M, K1p, device=dev, dtype=F32)
-        ops.gemm_nt(dpre1, B1T, M, K1p, hid, ops.EPI_F32, dcol)
-        ops.gemm_tn(dpre1, col, hid, K1p, M, dB1)
+        if 0 < M <= WGRAD_STREAM_MAX_M:
+            cur, side = torch.cuda.current_stream(dev), _wgrad_stream(dev)
+            side.wait_stream(cur)                          # fork: dhcol / dpre2 / dpre1 and the zeroed arena exist
+            with torch.cuda.stream(side):
+                ops.gemm_tn(dhcol, h2, K3p, hid, M, dB3)
+                ops.gemm_tn(dpre2, h1, hid, hid, M, dB2)
+                ops.gemm_tn(dpre1, col, hid, K1p, M, dB1)
+            _wgrad_keepalive.append((dhcol, dpre2, dpre1, h1, h2, col, arena))
+            dcol = torch.empty(M, K1p, device=dev, dtype=F32)
+            ops.gemm_nt(dpre1, B1T, M, K1p, hid, ops.EPI_F32, dcol)
+        else:
+            ops.gemm_tn(dhcol, h2, K3p, hid, M, dB3)
+            ops.gemm_tn(dpre2, h1, hid, hid, M, dB2)
+            dcol = torch.empty(M, K1p, device=dev, dtype=F32)
+            ops.gemm_nt(dpre1, B1T, M, K1p, hid, ops.EPI_F32, dcol)
+            ops.gemm_tn(dpre1, col, hid, K1p, M, dB1)
         dx = torch.empty_like(x)
         ops.affine1x1_bwd(dy, dcol, K1p, x, Wf, dx, dWf, dbf, B, C, H, W)
 

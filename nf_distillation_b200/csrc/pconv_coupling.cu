@@ -10,7 +10,8 @@
 // in place on the fp32 NCHW map. What used to be a GEMM writing P [M, 9C] fp32, and a second kernel reading it back,
 // is one kernel whose HBM traffic is the bf16 h2 read plus the z2 update.
 //
-// Warp roles (320 threads): warp 0 TMA producer, warp 1 MMA issuer (+ TMEM allocation), warps 2-9 epilogue.
+// Warp roles (448 threads): warp 0 TMA producer, warp 1 MMA issuer (+ TMEM allocation), warps 2-13 epilogue (the
+// col2im + coupling gather is what bounds the C = 24 kernel: twelve warps share it, eight of them drain TMEM).
 // Two TMEM accumulator stages: the epilogue of tile i overlaps the MMAs of tile i+1.
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -23,7 +24,8 @@
 
 namespace nfk {
 
-constexpr int PC_THREADS = 320;
+constexpr int PC_EPI = 384;            // epilogue threads: 12 warps (8 of them also drain TMEM, all 12 gather)
+constexpr int PC_THREADS = 64 + PC_EPI;
 constexpr int PC_BK = 64;
 
 template <int C> struct PcCfg;
@@ -154,30 +156,33 @@ pconv_coupling_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
       }
     }
   } else {
-    // ---- epilogue: 8 warps; warp w owns TMEM lanes (w % 4) * 32.. and half (w - 2) / 4 of the tile's columns.
+    // ---- epilogue: 12 warps; for the drain, warp w < 10 owns TMEM lanes (w % 4) * 32.. and half (w - 2) / 4 of the
+    // window's columns (warps 10-13 only gather).
     // Per tile: (1) prefetch this thread's z2 values (their HBM latency hides behind the wait for the MMAs and the
     // drain), (2) drain the whole accumulator P^T [9C, NPIX] into shared memory, (3) per (pixel, channel pair): sum
     // the nine shifted taps, bias, coupling, in-place z2 update, log-det partial sums.
     const int q = warp & 3, half = (warp - 2) >> 2;
-    const int et = threadIdx.x - 64;   // 0..255
+    const int et = threadIdx.x - 64;   // 0..383
+    const bool drains = half < 2;
+    const bool banded = (C == 12) && g.banded;   // only the C = 12 kernel has a band mode: elsewhere OH folds to HALF
     const int HW = g.H * g.W, HWm = HW - 1, Wm = g.W - 1;
-    constexpr int ITEMS = J * NPIX / 256;       // (pixel, j) items per thread: item i = et + 256 k, pixel fastest
-    static_assert(J * NPIX % 512 == 0, "each half's items must divide over the 256 epilogue threads");
+    constexpr int ITEMS = J * NPIX / PC_EPI;    // (pixel, j) items per thread: item i = et + PC_EPI k, pixel fastest
+    static_assert(J * NPIX % (2 * PC_EPI) == 0, "each half's items must divide over the epilogue threads");
     // output pixels of one half: HALF consecutive pixels, or in band mode rb/2 image rows after the halo row
-    const int OH = g.banded ? (g.rb >> 1) * g.W : HALF;
+    const int OH = banded ? (g.rb >> 1) * g.W : HALF;
     int it = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
       const int acc = it & 1;
       const long long tile_base = pc_tile_pix0<NPIX>(g, t);
-      const int row0 = g.banded ? (t % g.nb) * g.rb - 1 : 0;                   // band mode: image row of tile row 0
-      const int row_end = g.banded ? min(g.H, row0 + 1 + g.rb) : 0;            //            first image row not owned
+      const int row0 = banded ? (t % g.nb) * g.rb - 1 : 0;                   // band mode: image row of tile row 0
+      const int row_end = banded ? min(g.H, row0 + 1 + g.rb) : 0;            //            first image row not owned
       // item ih of half hf -> (channel pair j, tile-local pixel pl, global pixel m); live = it exists and is ours
       auto decode = [&](int hf, int ih, int& j, int& pl, long long& m) -> bool {
         j = ih / OH;
-        pl = (g.banded ? g.W : 0) + hf * OH + (ih - j * OH);
+        pl = (banded ? g.W : 0) + hf * OH + (ih - j * OH);
         m = tile_base + pl;
         if (j >= J) return false;
-        if (!g.banded) return m < g.M;
+        if (!banded) return m < g.M;
         return row0 + (pl >> g.lgW) < row_end;   // (rows past the image end would alias the next image's first rows)
       };
       float z2v[ITEMS];
@@ -186,7 +191,7 @@ pconv_coupling_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
         const int hf = k / (ITEMS / 2);
         int j, pl;
         long long m;
-        const bool live = decode(hf, et + 256 * (k - hf * (ITEMS / 2)), j, pl, m);
+        const bool live = decode(hf, et + PC_EPI * (k - hf * (ITEMS / 2)), j, pl, m);
         const int b = static_cast<int>(m >> g.lgHW), rem = static_cast<int>(m) & HWm;
         z2v[k] = live ? g.y[((static_cast<long long>(b) * C + J + j) << g.lgHW) + rem] : 0.f;
       }
@@ -197,7 +202,7 @@ pconv_coupling_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
         // source window of this half's outputs: the half itself when it holds whole images, else grown by the halo
         // and clipped to the tile (= the image)
         const int w0 = (WIN == HALF) ? hf * HALF : (hf == 0 ? 0 : NPIX - WIN);
-        if (hf == 1) asm volatile("bar.sync 1, 256;" ::: "memory");   // first half's gather is done with S
+        if (hf == 1) asm volatile("bar.sync 1, %0;" ::"n"(PC_EPI) : "memory");   // first half's gather is done with S
         // drain: TMEM [row][w0 .. w0+WIN) -> S[row][0 .. WIN); the two warps of a lane quadrant split the columns
         constexpr int HCOLS = WIN / 2;
         static_assert(HCOLS % 16 == 0, "window halves are drained 16 columns at a time");
@@ -207,7 +212,7 @@ pconv_coupling_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
           const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * ACC_COLS + mb * NPIX + w0 +
                                  half * HCOLS;
           float* srow = S + row * Sm::pitch + half * HCOLS;
-          if (mb * 128 + q * 32 < K3) {   // warp-uniform: this block of 32 rows holds real taps
+          if (drains && mb * 128 + q * 32 < K3) {   // warp-uniform: this block of 32 rows holds real taps
 #pragma unroll 1
             for (int c = 0; c < HCOLS; c += 32) {
               uint32_t r0[16], r1[16];
@@ -226,18 +231,18 @@ pconv_coupling_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
             }
           }
         }
-        if (hf == 1) {   // last TMEM read of this tile: accumulator stage back to the MMA warp
+        if (hf == 1 && drains) {   // last TMEM read of this tile: accumulator stage back to the MMA warp
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tmem_empty[acc]);
         }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(PC_EPI) : "memory");
 #pragma unroll
         for (int kk = 0; kk < ITEMS / 2; ++kk) {
           const int k = hf * (ITEMS / 2) + kk;
           int j, pl;                                        // item inside this half: (j, pixel), pixel fastest
           long long m;
-          const bool live = decode(hf, et + 256 * kk, j, pl, m);
+          const bool live = decode(hf, et + PC_EPI * kk, j, pl, m);
           const int b = static_cast<int>(m >> g.lgHW);
           float lsum = 0.f;
           if (live) {
@@ -280,7 +285,7 @@ pconv_coupling_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
           }
         }
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");   // S is free for the next tile
+      asm volatile("bar.sync 1, %0;" ::"n"(PC_EPI) : "memory");   // S is free for the next tile
     }
   }
   tc_fence_before();

@@ -26,6 +26,10 @@ NVCC_FLAGS = [
 ]
 
 
+# diagnostics builds: extra nvcc flags (e.g. NFK_NVCC_EXTRA="-DNFK_CNET_TIMELINE" for the fused kernel's per-tile probes)
+NVCC_FLAGS += os.environ.get("NFK_NVCC_EXTRA", "").split()
+
+
 def sources() -> list[str]:
     return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
 

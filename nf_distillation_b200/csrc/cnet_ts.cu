@@ -370,8 +370,10 @@ __device__ __forceinline__ void cnet_ts_body(const CUtensorMap& tmCol, const CUt
     // writes its event clocks to prof rows 148/149 (tools/cnet_diag.py prints them)
 #ifdef NFK_CNET_TIMELINE
     auto stamp = [&](int t, int idx) {
-      if (g.prof && blockIdx.x == 0 && t == 6 * num_pairs && qd == 0 && hf == 0 && lane == 0)
-        g.prof[(148 + ws) * 8 + idx] = clock64();
+      if (g.prof && blockIdx.x == 0 && t == 6 * num_pairs && lane == 0) {
+        if (qd == 0 && hf == 0) g.prof[(148 + ws) * 8 + idx] = clock64();
+        g.prof[(152 + ew) * 8 + idx] = clock64();      // every epilogue warp of the leader CTA: rows 152..167
+      }
     };
 #else
     auto stamp = [](int, int) {};

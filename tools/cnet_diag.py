@@ -41,10 +41,10 @@ for (M, K1p) in CASES:
     fl = 2.0 * M * hid * (K1p + hid)
     print(f"M={M} K1p={K1p}: equal(h2 train, h2 infer, h1, m1, m2)={ok} | unfused {tu:.1f} us, fused {tf:.1f} us ({fl/tf/1e6:.0f} TFLOP/s), fused+save {tt:.1f} us")
     if M == 262144:
-        prof = torch.zeros(152, 8, device=dev, dtype=torch.int64)
+        prof = torch.zeros(168, 8, device=dev, dtype=torch.int64)
         LIB.nfk_cnet_set_prof(prof.data_ptr()); fused(); torch.cuda.synchronize(); LIB.nfk_cnet_set_prof(None)
         p = prof.cpu().double()
-        tl = p[148:151].clone(); p = p[:148]
+        tl = p[148:151].clone(); tw = p[152:168].clone(); p = p[:148]
         pe = p[1::2]; pe = pe[pe[:, 0] > 0]
         p = p[0::2]; p = p[p[:, 0] > 0]
         names = ["total", "wait operands", "wait acc-free", "wait h1", "of operands: A tile", "weights GEMM 1", "weights GEMM 2 first quarter"]
@@ -58,3 +58,8 @@ for (M, K1p) in CASES:
             print("   timeline, MMA issuer [tile start, G1 q0 acc ready, G1 issued, G2 q0 start, q1, q2, q3, G2 issued]:", f(tl[2]))
             for wsi in (0, 1):
                 print(f"   timeline, epilogue set {wsi} [G1 a: acc full, ld done, math done, h1 free, st done, handed | G1 b: acc full, handed]:", f(tl[wsi]))
+            if tw.abs().sum() > 0:
+                print("   per epilogue warp (ew: set = ew>>3, hf = (ew>>2)&1, quadrant = (ew+2)&3): G1 a [acc full, ld done, math done, handed], G1 b [acc full, handed]")
+                for ew in range(16):
+                    r = tw[ew]
+                    print(f"     ew {ew:2d}:", [int(r[i] - t0) if r[i] > 0 else None for i in (0, 1, 2, 5, 6, 7)])

@@ -159,7 +159,8 @@ def test_forward_vs_oracle_fresh(B, K, hid, patched_noise):
 
 @pytest.mark.parametrize("B,C,H,reverse", [(5, 12, 16, False), (5, 12, 16, True), (7, 24, 8, False), (300, 12, 16, False),
                                              (37, 48, 4, False), (37, 48, 4, True), (9, 12, 8, False), (3, 24, 4, True),
-                                             (3, 12, 32, False), (2, 12, 32, True)])   # 32x32: row bands with halo
+                                             (3, 12, 32, False), (2, 12, 32, True),    # 32x32: row bands with halo
+                                             (2500, 48, 4, False)])   # 4x4 maps: > 2 tiles per CTA of csrc/pconv_px.cu
 def test_fused_conv3_coupling_matches_two_kernel_path_and_torch(B, C, H, reverse):
     """csrc/pconv_coupling.cu (Conv2dZeros + coupling in one kernel) against (a) the per-tap GEMM + col2im/coupling
     kernels it replaces — same bf16 products, fp32 sums in a different order: 1e-6 — and (b) torch's conv2d on the same
@@ -195,6 +196,16 @@ def test_fused_conv3_coupling_matches_two_kernel_path_and_torch(B, C, H, reverse
     assert rel(yf[:, C // 2:], z2r) < 1e-4 and torch.equal(yf[:, :C // 2], y0[:, :C // 2])
     assert rel(ldf, ldr) < 1e-5
     assert rel(hsf.view(B, H, W, C).permute(0, 3, 1, 2), out) < 1e-4
+
+
+def test_pixel_major_kernel_of_the_4x4_level_is_bit_identical_to_the_weight_major_one():
+    """csrc/pconv_px.cu (pixels on the MMA's M axis, col2im through warp shuffles) against pconv_coupling_kernel<48>
+    (NFK_PCONV_PX=0, child process): outputs and saved conv outputs bit for bit, ragged tiles, both directions."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "pconv_px_check.py")], cwd=root,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
 VARIANTS = ["glow2d_16_additive_shuffle_k2_h64", "glow2d_16_affine_reverse_k2_h64", "glow2d_16_learntop_k1_h64"]

@@ -336,9 +336,10 @@ static int pc_launch(const void* h2, const void* B3, int K3p, const PcArgs& g, i
   return (le == cudaSuccess && cudaGetLastError() == cudaSuccess) ? NFK_OK : NFK_ERR_LAUNCH;
 }
 
-// pconv_px.cu: the 4x4-map level (C = 48) with the pixels on the MMA's M axis; NFK_PCONV_PX=0 keeps pconv_coupling_kernel<48>
-int pconv_px48_launch(const void* h2, const void* B3, int K3p, const float* bias3, float* y, float* hsave, float* ld,
-                      int B, int hid, int reverse, cudaStream_t st);
+// pconv_px.cu: the 4x4-map levels (C = 48, 96) with the pixels on the MMA's M axis; NFK_PCONV_PX=0 keeps
+// pconv_coupling_kernel<48> (and leaves C = 96 to the per-tap GEMM + coupling_fwd path)
+int pconv_px_launch(const void* h2, const void* B3, int K3p, const float* bias3, float* y, float* hsave, float* ld,
+                    int B, int C, int hid, int reverse, cudaStream_t st);
 static bool pconv_use_px() {
   static const bool v = [] { const char* e = getenv("NFK_PCONV_PX"); return !(e && e[0] == '0'); }();
   return v;
@@ -362,6 +363,7 @@ extern "C" int nfk_pconv_coupling_supported(int C, int H, int W, int hid) {
   }
   if (C == 24) return HW <= PcCfg<24>::NPIX / 2 && HW >= 4;
   if (C == 48) return HW <= PcCfg<48>::NPIX / 2 && HW >= 4;
+  if (C == 96) return H == 4 && W == 4 && pconv_use_px();      // pixel-major kernel only (pconv_px.cu)
   return 0;
 }
 
@@ -384,8 +386,8 @@ extern "C" int nfk_pconv_coupling_fwd(const void* h2, const void* B3, int K3p, c
     g.nb = (H + g.rb - 1) / g.rb;
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (C == 48 && H == 4 && W == 4 && pconv_use_px())
-    return pconv_px48_launch(h2, B3, K3p, bias3, y, hsave, ld, B, hid, reverse, st);
+  if ((C == 48 || C == 96) && H == 4 && W == 4 && pconv_use_px())
+    return pconv_px_launch(h2, B3, K3p, bias3, y, hsave, ld, B, C, hid, reverse, st);
   if (C == 12) return pc_launch<12>(h2, B3, K3p, g, hid, st);
   if (C == 24) return pc_launch<24>(h2, B3, K3p, g, hid, st);
   return pc_launch<48>(h2, B3, K3p, g, hid, st);

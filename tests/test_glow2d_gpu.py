@@ -160,7 +160,8 @@ def test_forward_vs_oracle_fresh(B, K, hid, patched_noise):
 @pytest.mark.parametrize("B,C,H,reverse", [(5, 12, 16, False), (5, 12, 16, True), (7, 24, 8, False), (300, 12, 16, False),
                                              (37, 48, 4, False), (37, 48, 4, True), (9, 12, 8, False), (3, 24, 4, True),
                                              (3, 12, 32, False), (2, 12, 32, True),    # 32x32: row bands with halo
-                                             (2500, 48, 4, False)])   # 4x4 maps: > 2 tiles per CTA of csrc/pconv_px.cu
+                                             (2500, 48, 4, False),    # 4x4 maps: > 2 tiles per CTA of csrc/pconv_px.cu
+                                             (5, 96, 4, False), (41, 96, 4, True), (1300, 96, 4, False)])   # CelebA top level
 def test_fused_conv3_coupling_matches_two_kernel_path_and_torch(B, C, H, reverse):
     """csrc/pconv_coupling.cu (Conv2dZeros + coupling in one kernel) against (a) the per-tap GEMM + col2im/coupling
     kernels it replaces — same bf16 products, fp32 sums in a different order: 1e-6 — and (b) torch's conv2d on the same

@@ -252,7 +252,8 @@ def kernel_table(B, H, W, C_img, hid, device):
         dhc_ = [(torch.randn(M, K3p, device=device) * 0.1).to(bf16) for _ in range(nb)]
         us = time_graph(lambda i: ops.cnet_bwd_fused(dhc_[i], K3p, W3T, W2T, mask, mask, dpre[i], outs[i], cs, cs2, M,
                                                      hid), 10, nb) * 1e3
-        add("cnet_bwd_fused_kernel (Conv2dZeros dgrad -> ReLU mask -> conv1x1 dgrad -> ReLU mask + both bias gradients)",
+        add(fused_kernel_name().replace("fwd", "bwd") +
+            " (Conv2dZeros dgrad -> ReLU mask -> conv1x1 dgrad -> ReLU mask + both bias gradients)",
             "tensor", 2.0 * M * hid * (9 * C + hid), us)
         del dhc_
     else:
